@@ -1,0 +1,1162 @@
+// idn_gpu.cu -- host side of libidn_gpu.so: the C-ABI declared in include/idn_gpu.h.
+//
+// Owns the device context (stream, workspaces, uploaded model tables) and sequences the kernels of
+// idn_kernels.cuh.  There is no CPU fallback anywhere in this file: every entry point needs a CUDA device.
+#include "../../include/idn_gpu.h"
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "idn_kernels.cuh"
+
+using namespace idn;
+
+namespace {
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    cudaError_t ensure(size_t n) {
+        if (n <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        size_t want = n + n / 8 + 256;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e != cudaSuccess) {
+            (void)cudaGetLastError();
+            e = cudaMalloc(&p, n);
+            want = n;
+        }
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+    template <class T>
+    T* as() const {
+        return reinterpret_cast<T*>(p);
+    }
+};
+
+struct ModelSlot {
+    bool used = false;
+    ModelDev dev{};
+    void* d_map = nullptr;
+    void* d_hkeys = nullptr;
+    void* d_hvals = nullptr;
+    void* d_enc = nullptr;
+    void* d_dec = nullptr;
+    void free_all() {
+        cudaFree(d_map);
+        cudaFree(d_hkeys);
+        cudaFree(d_hvals);
+        cudaFree(d_enc);
+        cudaFree(d_dec);
+        d_map = d_hkeys = d_hvals = d_enc = d_dec = nullptr;
+        used = false;
+    }
+};
+
+constexpr uint32_t kMaxSlots = 1024;
+constexpr uint64_t kDenseSpecLimit = 1ull << 22;  // dense u16 map up to 8 MB, hash above
+
+}  // namespace
+
+struct idn_gpu_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;  // used by the host-pointer entry points
+    cudaEvent_t ev = nullptr;
+    std::string err;
+    uint64_t launches = 0;
+    std::vector<ModelSlot> slots;
+    ModelDev* d_models = nullptr;  // [kMaxSlots], mirrors slots[].dev
+    uint32_t* d_crc_tab = nullptr;  // [256]
+    uint32_t* d_xpow = nullptr;     // [64]
+    // workspaces of the *_dev paths
+    DevBuf w_scratch, w_paylen, w_sizes, w_chosen, w_tiles, w_sliceoff, w_readblock, w_small, w_crcpart, w_crclen;
+    DevBuf w_index;  // decode-side per-read index
+    DevBuf w_blk;    // decode-side per-block counters
+    // staging of the host-pointer paths
+    DevBuf s_acids, s_quals, s_readoff, s_blockfirst, s_prefix, s_names, s_nameoff, s_out, s_blockoff, s_crc, s_stats,
+        s_sizes, s_blocks, s_aout, s_qout, s_offout, s_status, s_idx;
+};
+
+namespace {
+
+int32_t fail(idn_gpu_ctx* c, int32_t code, const char* fmt, ...) {
+    if (c) {
+        char buf[512];
+        va_list ap;
+        va_start(ap, fmt);
+        vsnprintf(buf, sizeof buf, fmt, ap);
+        va_end(ap);
+        c->err = buf;
+    }
+    return code;
+}
+
+#define CU(call)                                                                                       \
+    do {                                                                                               \
+        cudaError_t e__ = (call);                                                                      \
+        if (e__ != cudaSuccess) {                                                                      \
+            (void)cudaGetLastError();                                                                  \
+            return fail(ctx, IDN_E_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__, \
+                        __LINE__);                                                                     \
+        }                                                                                              \
+    } while (0)
+
+#define LAUNCHED()                                                                                 \
+    do {                                                                                           \
+        ctx->launches++;                                                                           \
+        cudaError_t e__ = cudaGetLastError();                                                      \
+        if (e__ != cudaSuccess)                                                                    \
+            return fail(ctx, IDN_E_CUDA, "kernel launch failed: %s (%s:%d)", cudaGetErrorString(e__), \
+                        __FILE__, __LINE__);                                                       \
+    } while (0)
+
+uint32_t bitlen(uint64_t v) {
+    uint32_t n = 0;
+    while (v) {
+        n++;
+        v >>= 1;
+    }
+    return n;
+}
+uint64_t ipow(uint64_t b, uint32_t n) {
+    uint64_t r = 1;
+    while (n--) r *= b;
+    return r;
+}
+
+// IntQueue::num_bits (int_queue.rs:40-43) and the generator parameters (context_spec.rs:218-529)
+bool make_spec(int32_t kind, int32_t ao, int32_t qo, int32_t pb, int32_t qmax, SpecDev* s, uint32_t* total_bits) {
+    if (kind != IDN_SPEC_GENERIC && kind != IDN_SPEC_LIGHT) return false;
+    if (ao < 0 || ao > kHist || qo < 0 || qo > kHist || pb < 0 || pb > 16) return false;
+    memset(s, 0, sizeof *s);
+    s->ao = (uint32_t)ao;
+    s->qo = (uint32_t)qo;
+    s->pb = (uint32_t)pb;
+    s->light = kind == IDN_SPEC_LIGHT;
+    if (s->light) {
+        if (qmax < 1 || qmax > 94) return false;
+        s->qmax = (uint32_t)qmax;
+        s->base_a = 4;
+        s->base_q = (uint32_t)qmax;
+        for (uint32_t q = 0; q < 94; q++)  // the multiply-shift in light_map must equal q*qmax/94
+            if (((q * s->qmax * 11156u) >> 20) != q * s->qmax / 94) return false;
+    } else {
+        s->base_a = 5;
+        s->base_q = 94;
+    }
+    uint64_t pa = ipow(s->base_a, s->ao), pq = ipow(s->base_q, s->qo);
+    if (pa > (1ull << 31) || pq > (1ull << 31)) return false;
+    s->abits = bitlen(pa - 1);
+    s->qbits = bitlen(pq - 1);
+    if (s->abits + s->qbits + s->pb > 31) return false;
+    s->pow_a = s->ao ? (uint32_t)ipow(s->base_a, s->ao - 1) : 0;
+    s->pow_q = s->qo ? (uint32_t)ipow(s->base_q, s->qo - 1) : 0;
+    s->div_base_a = make_fastdiv(s->base_a);
+    s->div_base_q = make_fastdiv(s->base_q);
+    s->div_pow_a = make_fastdiv(s->pow_a);
+    s->div_pow_q = make_fastdiv(s->pow_q);
+    *total_bits = s->abits + s->qbits + s->pb;
+    return true;
+}
+
+uint32_t host_hash32(uint32_t k) {
+    k ^= k >> 16;
+    k *= 0x7feb352dU;
+    k ^= k >> 15;
+    k *= 0x846ca68bU;
+    k ^= k >> 16;
+    return k;
+}
+
+cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
+
+int32_t sync_models(idn_gpu_ctx* ctx) {
+    std::vector<ModelDev> host(kMaxSlots);
+    memset(host.data(), 0, sizeof(ModelDev) * kMaxSlots);
+    for (size_t i = 0; i < ctx->slots.size(); i++)
+        if (ctx->slots[i].used) host[i] = ctx->slots[i].dev;
+    CU(cudaMemcpy(ctx->d_models, host.data(), sizeof(ModelDev) * kMaxSlots, cudaMemcpyHostToDevice));
+    return IDN_OK;
+}
+
+int32_t check_models(idn_gpu_ctx* ctx, const idn_model_t* models, uint32_t n_models) {
+    if (!models && n_models) return fail(ctx, IDN_E_INVALID_ARG, "models is NULL");
+    if (n_models > IDN_MAX_MODELS) return fail(ctx, IDN_E_INVALID_ARG, "more than %d models", IDN_MAX_MODELS);
+    for (uint32_t i = 0; i < n_models; i++)
+        if (models[i] < 0 || (size_t)models[i] >= ctx->slots.size() || !ctx->slots[models[i]].used)
+            return fail(ctx, IDN_E_UNKNOWN_MODEL, "model handle %d is not live", (int)models[i]);
+    return IDN_OK;
+}
+
+// small per-call parameter block living in w_small (device):
+struct SmallParams {
+    int32_t model_ids[256];            // container index -> slot
+    uint32_t cand_cols[2 * kMaxCand];  // candidate -> column of the score matrix
+    int32_t cand_model[2 * kMaxCand];  // candidate -> slot
+    uint8_t cand_index[2 * kMaxCand];  // candidate -> SwitchModel index
+    uint32_t n_cand[2];
+    uint32_t has_sizes[2];
+    int32_t score_ids[256];  // score-matrix column -> slot
+    uint32_t err;            // bit 0: invalid symbol
+    uint32_t pad[3];
+    unsigned long long stats[8];
+    int32_t status[4];
+};
+
+}  // namespace
+
+// ======================================================================================================
+// lifecycle
+// ======================================================================================================
+extern "C" int32_t idn_gpu_abi_version(void) { return IDN_GPU_ABI_VERSION; }
+
+extern "C" int32_t idn_gpu_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        (void)cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+static void make_crc_tables(uint32_t* tab, uint32_t* xpow) {
+    for (uint32_t i = 0; i < 256; i++) {
+        uint32_t c = i;
+        for (int k = 0; k < 8; k++) c = (c >> 1) ^ ((c & 1) ? 0xEDB88320u : 0);
+        tab[i] = c;
+    }
+    // reflected polynomial arithmetic: bit 31 is x^0.  x^8 = 0x00800000.
+    auto mul = [](uint32_t a, uint32_t b) {
+        uint32_t p = 0;
+        for (int i = 0; i < 32; i++) {
+            if (b & 0x80000000u) p ^= a;
+            a = (a >> 1) ^ ((a & 1) ? 0xEDB88320u : 0);
+            b <<= 1;
+        }
+        return p;
+    };
+    xpow[0] = 0x00800000u;
+    for (int k = 1; k < 64; k++) xpow[k] = mul(xpow[k - 1], xpow[k - 1]);
+}
+
+extern "C" int32_t idn_gpu_create(int32_t device, idn_gpu_ctx** out) {
+    if (!out) return IDN_E_INVALID_ARG;
+    *out = nullptr;
+    int n = idn_gpu_device_count();
+    if (n <= 0 || device < 0 || device >= n) return IDN_E_CUDA;  // no CPU fallback
+    idn_gpu_ctx* ctx = new idn_gpu_ctx();
+    ctx->device = device;
+    auto bail = [&](const char* what) {
+        fprintf(stderr, "idn_gpu_create: %s failed: %s\n", what, cudaGetErrorString(cudaGetLastError()));
+        delete ctx;
+        return (int32_t)IDN_E_CUDA;
+    };
+    if (cudaSetDevice(device) != cudaSuccess) return bail("cudaSetDevice");
+    if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) return bail("cudaStreamCreate");
+    if (cudaEventCreateWithFlags(&ctx->ev, cudaEventDisableTiming) != cudaSuccess) return bail("cudaEventCreate");
+    if (cudaMalloc(&ctx->d_models, sizeof(ModelDev) * kMaxSlots) != cudaSuccess) return bail("cudaMalloc");
+    if (cudaMemset(ctx->d_models, 0, sizeof(ModelDev) * kMaxSlots) != cudaSuccess) return bail("cudaMemset");
+    uint32_t tab[256], xpow[64];
+    make_crc_tables(tab, xpow);
+    if (cudaMalloc(&ctx->d_crc_tab, sizeof tab) != cudaSuccess) return bail("cudaMalloc");
+    if (cudaMalloc(&ctx->d_xpow, sizeof xpow) != cudaSuccess) return bail("cudaMalloc");
+    if (cudaMemcpy(ctx->d_crc_tab, tab, sizeof tab, cudaMemcpyHostToDevice) != cudaSuccess) return bail("cudaMemcpy");
+    if (cudaMemcpy(ctx->d_xpow, xpow, sizeof xpow, cudaMemcpyHostToDevice) != cudaSuccess) return bail("cudaMemcpy");
+    *out = ctx;
+    return IDN_OK;
+}
+
+extern "C" void idn_gpu_destroy(idn_gpu_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaDeviceSynchronize();
+    for (auto& s : ctx->slots)
+        if (s.used) s.free_all();
+    DevBuf* bufs[] = {&ctx->w_scratch, &ctx->w_paylen,  &ctx->w_sizes,   &ctx->w_chosen,     &ctx->w_tiles,  &ctx->w_sliceoff,
+                      &ctx->w_readblock, &ctx->w_small, &ctx->w_crcpart, &ctx->w_crclen,     &ctx->w_index,  &ctx->w_blk,
+                      &ctx->s_acids,   &ctx->s_quals,   &ctx->s_readoff, &ctx->s_blockfirst, &ctx->s_prefix, &ctx->s_names,
+                      &ctx->s_nameoff, &ctx->s_out,     &ctx->s_blockoff, &ctx->s_crc,       &ctx->s_stats,  &ctx->s_sizes,
+                      &ctx->s_blocks,  &ctx->s_aout,    &ctx->s_qout,    &ctx->s_offout,     &ctx->s_status, &ctx->s_idx};
+    for (DevBuf* b : bufs) b->release();
+    cudaFree(ctx->d_models);
+    cudaFree(ctx->d_crc_tab);
+    cudaFree(ctx->d_xpow);
+    if (ctx->ev) cudaEventDestroy(ctx->ev);
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+extern "C" const char* idn_gpu_last_error(const idn_gpu_ctx* ctx) { return ctx ? ctx->err.c_str() : "no context"; }
+extern "C" uint64_t idn_gpu_launch_count(const idn_gpu_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+// ======================================================================================================
+// models
+// ======================================================================================================
+extern "C" int32_t idn_gpu_model_upload(idn_gpu_ctx* ctx, int32_t model_type, int32_t spec_kind, int32_t acid_order,
+                                        int32_t q_order, int32_t pos_bits, int32_t q_max, uint32_t n_ctx,
+                                        const uint16_t* cum, const uint32_t* spec_keys, const uint32_t* spec_ctx,
+                                        uint64_t n_specs, idn_model_t* handle) {
+    if (!ctx || !handle || !cum) return fail(ctx, IDN_E_INVALID_ARG, "NULL argument");
+    if (model_type != IDN_MODEL_ACID && model_type != IDN_MODEL_QSCORE)
+        return fail(ctx, IDN_E_INVALID_ARG, "bad model type %d", model_type);
+    if (n_ctx > 65535) return fail(ctx, IDN_E_UNSUPPORTED, "model has %u contexts (limit 65535)", n_ctx);
+    if (n_specs && (!spec_keys || !spec_ctx)) return fail(ctx, IDN_E_INVALID_ARG, "NULL spec table");
+    CU(cudaSetDevice(ctx->device));
+    SpecDev spec;
+    uint32_t bits = 0;
+    if (!make_spec(spec_kind, acid_order, q_order, pos_bits, q_max, &spec, &bits))
+        return fail(ctx, IDN_E_UNSUPPORTED, "unsupported context spec type (kind %d ao %d qo %d pb %d qmax %d)", spec_kind,
+                    acid_order, q_order, pos_bits, q_max);
+    const uint64_t spec_num = 1ull << bits;
+    const uint32_t nsym = model_type == IDN_MODEL_ACID ? kAcidSyms : kQSyms;
+    const uint32_t n_rows = n_ctx + 1;
+    const uint32_t total = 1u << kScaleBits;
+
+    // validate the integer tables (Context::as_integer_cum_freqs asserts, context.rs:366-367)
+    for (uint32_t r = 0; r < n_rows; r++) {
+        const uint16_t* row = cum + (size_t)r * (nsym + 1);
+        if (row[0] != 0 || row[nsym] != total) return fail(ctx, IDN_E_INVALID_ARG, "cum row %u does not span [0, 2^14]", r);
+        for (uint32_t s = 0; s < nsym; s++)
+            if (row[s + 1] <= row[s]) return fail(ctx, IDN_E_INVALID_ARG, "cum row %u has a zero frequency", r);
+    }
+    for (uint64_t i = 0; i < n_specs; i++) {
+        if (spec_keys[i] >= spec_num) return fail(ctx, IDN_E_INVALID_ARG, "spec key %u out of range", spec_keys[i]);
+        if (spec_ctx[i] >= n_ctx) return fail(ctx, IDN_E_INVALID_ARG, "context index %u out of range", spec_ctx[i]);
+    }
+
+    ModelSlot slot;
+    slot.dev.spec = spec;
+    slot.dev.type = (uint32_t)model_type;
+    slot.dev.nsym = nsym;
+    slot.dev.n_rows = n_rows;
+
+    // spec -> row (RansEncModel::from_model map, sequence_compressor.rs:31-40): dense u16 or open-addressing hash
+    if (n_specs == 0) {
+        // model without contexts: every spec is the dummy row
+    } else if (spec_num <= kDenseSpecLimit) {
+        std::vector<uint16_t> map(spec_num, 0);
+        for (uint64_t i = 0; i < n_specs; i++) map[spec_keys[i]] = (uint16_t)(spec_ctx[i] + 1);
+        CU(cudaMalloc(&slot.d_map, spec_num * sizeof(uint16_t)));
+        CU(cudaMemcpy(slot.d_map, map.data(), spec_num * sizeof(uint16_t), cudaMemcpyHostToDevice));
+        slot.dev.map = (const uint16_t*)slot.d_map;
+    } else {
+        uint64_t capn = 16;
+        while (capn < 2 * n_specs) capn <<= 1;
+        std::vector<uint32_t> hk(capn, 0xffffffffu);
+        std::vector<uint16_t> hv(capn, 0);
+        for (uint64_t i = 0; i < n_specs; i++) {
+            uint32_t h = host_hash32(spec_keys[i]) & (uint32_t)(capn - 1);
+            while (hk[h] != 0xffffffffu && hk[h] != spec_keys[i]) h = (h + 1) & (uint32_t)(capn - 1);
+            hk[h] = spec_keys[i];
+            hv[h] = (uint16_t)(spec_ctx[i] + 1);
+        }
+        CU(cudaMalloc(&slot.d_hkeys, capn * sizeof(uint32_t)));
+        CU(cudaMalloc(&slot.d_hvals, capn * sizeof(uint16_t)));
+        CU(cudaMemcpy(slot.d_hkeys, hk.data(), capn * sizeof(uint32_t), cudaMemcpyHostToDevice));
+        CU(cudaMemcpy(slot.d_hvals, hv.data(), capn * sizeof(uint16_t), cudaMemcpyHostToDevice));
+        slot.dev.hkeys = (const uint32_t*)slot.d_hkeys;
+        slot.dev.hvals = (const uint16_t*)slot.d_hvals;
+        slot.dev.hmask = (uint32_t)(capn - 1);
+    }
+
+    // encoder entries: RansEncSymbolInit (ryg rans_byte.h) folded into {rcp_freq, start | freq<<14 | rcp_shift<<28}
+    std::vector<uint2> enc((size_t)n_rows * nsym);
+    for (uint32_t r = 0; r < n_rows; r++) {
+        const uint16_t* row = cum + (size_t)r * (nsym + 1);
+        for (uint32_t s = 0; s < nsym; s++) {
+            uint32_t start = row[s], freq = (uint32_t)row[s + 1] - row[s];
+            uint32_t rcp = 0xffffffffu, rshift = 0;
+            if (freq >= 2) {
+                uint32_t shift = 0;
+                while (freq > (1u << shift)) shift++;
+                rcp = (uint32_t)(((1ull << (shift + 31)) + freq - 1) / freq);
+                rshift = shift - 1;
+            }
+            enc[(size_t)r * nsym + s] = make_uint2(rcp, start | (freq << 14) | (rshift << 28));
+        }
+    }
+    CU(cudaMalloc(&slot.d_enc, enc.size() * sizeof(uint2)));
+    CU(cudaMemcpy(slot.d_enc, enc.data(), enc.size() * sizeof(uint2), cudaMemcpyHostToDevice));
+    slot.dev.enc = (const uint2*)slot.d_enc;
+
+    // decoder rows: cumulative frequencies searched directly (no 2^14-entry LUT per context)
+    std::vector<uint16_t> dec;
+    if (model_type == IDN_MODEL_ACID) {
+        dec.resize((size_t)n_rows * 4);
+        for (uint32_t r = 0; r < n_rows; r++)
+            for (uint32_t k = 0; k < 4; k++) dec[(size_t)r * 4 + k] = cum[(size_t)r * 6 + 1 + k];
+    } else {
+        dec.assign((size_t)n_rows * kQRowStride, 0x7fff);
+        for (uint32_t r = 0; r < n_rows; r++) {
+            const uint16_t* row = cum + (size_t)r * 95;
+            uint16_t* d = dec.data() + (size_t)r * kQRowStride;
+            for (uint32_t k = 0; k < 16; k++) d[k] = 8 * k <= 94 ? row[8 * k] : 0x7fff;
+            for (uint32_t k = 0; k < 95; k++) d[16 + k] = row[k];
+        }
+    }
+    CU(cudaMalloc(&slot.d_dec, dec.size() * sizeof(uint16_t)));
+    CU(cudaMemcpy(slot.d_dec, dec.data(), dec.size() * sizeof(uint16_t), cudaMemcpyHostToDevice));
+    slot.dev.dec = (const uint16_t*)slot.d_dec;
+    slot.used = true;
+
+    size_t idx = ctx->slots.size();
+    for (size_t i = 0; i < ctx->slots.size(); i++)
+        if (!ctx->slots[i].used) {
+            idx = i;
+            break;
+        }
+    if (idx >= kMaxSlots) {
+        slot.free_all();
+        return fail(ctx, IDN_E_UNSUPPORTED, "too many live models");
+    }
+    if (idx == ctx->slots.size()) ctx->slots.push_back(slot);
+    else ctx->slots[idx] = slot;
+    *handle = (idn_model_t)idx;
+    return sync_models(ctx);
+}
+
+extern "C" int32_t idn_gpu_model_release(idn_gpu_ctx* ctx, idn_model_t h) {
+    if (!ctx) return IDN_E_INVALID_ARG;
+    if (h < 0 || (size_t)h >= ctx->slots.size() || !ctx->slots[h].used)
+        return fail(ctx, IDN_E_UNKNOWN_MODEL, "model handle %d is not live", (int)h);
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaDeviceSynchronize());
+    ctx->slots[h].free_all();
+    return sync_models(ctx);
+}
+
+// ======================================================================================================
+// scoring
+// ======================================================================================================
+static int32_t check_batch(idn_gpu_ctx* ctx, const idn_batch* b) {
+    if (!b) return fail(ctx, IDN_E_INVALID_ARG, "batch is NULL");
+    if (b->n_reads && !b->read_off) return fail(ctx, IDN_E_INVALID_ARG, "read_off is NULL");
+    if (b->n_symbols && (!b->acids || !b->quals)) return fail(ctx, IDN_E_INVALID_ARG, "symbol arrays are NULL");
+    if (b->n_reads >= (1ull << 32) - 1) return fail(ctx, IDN_E_INVALID_ARG, "too many reads in one batch");
+    if ((b->names != nullptr) != (b->name_off != nullptr)) return fail(ctx, IDN_E_INVALID_ARG, "names and name_off go together");
+    return IDN_OK;
+}
+
+static int32_t upload_small(idn_gpu_ctx* ctx, const SmallParams& sp, cudaStream_t st) {
+    CU(ctx->w_small.ensure(sizeof(SmallParams)));
+    // pageable source: cudaMemcpyAsync stages it before returning, so `sp` may live on the caller's stack
+    CU(cudaMemcpyAsync(ctx->w_small.p, &sp, sizeof sp, cudaMemcpyHostToDevice, st));
+    return IDN_OK;
+}
+
+extern "C" int32_t idn_gpu_score_dev(idn_gpu_ctx* ctx, const idn_batch* batch, const idn_model_t* models,
+                                     uint32_t n_models, uint32_t* sizes, void* stream) {
+    if (!ctx) return IDN_E_INVALID_ARG;
+    int32_t rc = check_batch(ctx, batch);
+    if (rc) return rc;
+    rc = check_models(ctx, models, n_models);
+    if (rc) return rc;
+    if (n_models == 0 || batch->n_reads == 0) return IDN_OK;
+    if (!sizes) return fail(ctx, IDN_E_INVALID_ARG, "sizes is NULL");
+    CU(cudaSetDevice(ctx->device));
+    cudaStream_t st = as_stream(stream);
+    SmallParams sp;
+    memset(&sp, 0, sizeof sp);
+    for (uint32_t i = 0; i < n_models; i++) sp.score_ids[i] = models[i];
+    rc = upload_small(ctx, sp, st);
+    if (rc) return rc;
+    SmallParams* dsp = ctx->w_small.as<SmallParams>();
+    uint64_t threads = batch->n_reads * n_models;
+    score_kernel<<<(unsigned)((threads + 127) / 128), 128, 0, st>>>(ctx->d_models, dsp->score_ids, n_models, batch->acids,
+                                                                   batch->quals, batch->read_off, batch->n_reads, sizes,
+                                                                   &dsp->err);
+    LAUNCHED();
+    return IDN_OK;
+}
+
+extern "C" int32_t idn_gpu_score(idn_gpu_ctx* ctx, const idn_batch* b, const idn_model_t* models, uint32_t n_models,
+                                 uint32_t* sizes) {
+    if (!ctx) return IDN_E_INVALID_ARG;
+    int32_t rc = check_batch(ctx, b);
+    if (rc) return rc;
+    if (n_models == 0 || b->n_reads == 0) return check_models(ctx, models, n_models);
+    if (!sizes) return fail(ctx, IDN_E_INVALID_ARG, "sizes is NULL");
+    CU(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    CU(ctx->s_acids.ensure(b->n_symbols + 16));
+    CU(ctx->s_quals.ensure(b->n_symbols + 16));
+    CU(ctx->s_readoff.ensure((b->n_reads + 1) * 8));
+    CU(ctx->s_sizes.ensure(b->n_reads * n_models * 4));
+    CU(cudaMemcpyAsync(ctx->s_acids.p, b->acids, b->n_symbols, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(ctx->s_quals.p, b->quals, b->n_symbols, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(ctx->s_readoff.p, b->read_off, (b->n_reads + 1) * 8, cudaMemcpyHostToDevice, st));
+    idn_batch d = *b;
+    d.acids = ctx->s_acids.as<uint8_t>();
+    d.quals = ctx->s_quals.as<uint8_t>();
+    d.read_off = ctx->s_readoff.as<uint64_t>();
+    d.names = nullptr;
+    d.name_off = nullptr;
+    d.block_first_read = nullptr;
+    rc = idn_gpu_score_dev(ctx, &d, models, n_models, ctx->s_sizes.as<uint32_t>(), st);
+    if (rc) return rc;
+    uint32_t err = 0;
+    CU(cudaMemcpyAsync(sizes, ctx->s_sizes.p, b->n_reads * n_models * 4, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(&err, &ctx->w_small.as<SmallParams>()->err, 4, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    if (err & 1) return fail(ctx, IDN_E_INVALID_SYMBOL, "input holds an acid > 4 or a quality score > 93");
+    return IDN_OK;
+}
+
+// ======================================================================================================
+// compression
+// ======================================================================================================
+extern "C" uint64_t idn_gpu_compress_bound(uint64_t n_reads, uint64_t n_symbols, uint32_t n_blocks, uint64_t prefix_total) {
+    // per read: two switches (4) + sequence header (9) + payload (<= 4*len + 8); per block: header 8 + fast switches 4
+    return 4 * n_symbols + 21 * n_reads + 12ull * n_blocks + prefix_total;
+}
+
+static int32_t idn_gpu_block_crc_dev_impl(idn_gpu_ctx* ctx, const idn_batch* batch, uint32_t* block_crc, uint8_t* out,
+                                          const unsigned long long* block_off, uint64_t out_cap, cudaStream_t st);
+
+extern "C" int32_t idn_gpu_compress_blocks_dev(idn_gpu_ctx* ctx, const idn_batch* batch, int32_t mode,
+                                               const idn_model_t* models, uint32_t n_models, int32_t fast,
+                                               const uint32_t* prefix_len, uint8_t* out, uint64_t out_cap,
+                                               uint64_t* block_off, uint32_t* block_crc, idn_compress_stats* stats_dev,
+                                               void* stream) {
+    if (!ctx) return IDN_E_INVALID_ARG;
+    int32_t rc = check_batch(ctx, batch);
+    if (rc) return rc;
+    rc = check_models(ctx, models, n_models);
+    if (rc) return rc;
+    if (mode != IDN_MODE_COMPAT) return fail(ctx, IDN_E_UNSUPPORTED, "mode %d is not implemented", mode);
+    if (!batch->block_first_read || !block_off || (!out && out_cap)) return fail(ctx, IDN_E_INVALID_ARG, "NULL argument");
+    if (batch->n_blocks == 0) return fail(ctx, IDN_E_INVALID_ARG, "batch has no blocks");
+    CU(cudaSetDevice(ctx->device));
+    cudaStream_t st = as_stream(stream);
+    const uint64_t R = batch->n_reads, S = batch->n_symbols;
+    const uint32_t B = batch->n_blocks;
+
+    // candidate lists per type, in provider order (model_provider.rs:210-238)
+    SmallParams sp;
+    memset(&sp, 0, sizeof sp);
+    uint32_t n_score = 0;
+    for (uint32_t i = 0; i < n_models; i++) {
+        uint32_t t = ctx->slots[models[i]].dev.type;
+        if (sp.n_cand[t] >= (uint32_t)kMaxCand) return fail(ctx, IDN_E_UNSUPPORTED, "more than %d models of one type", kMaxCand);
+        uint32_t k = sp.n_cand[t]++;
+        sp.cand_model[t * kMaxCand + k] = models[i];
+        sp.cand_index[t * kMaxCand + k] = (uint8_t)i;
+    }
+    if (R > 0 && (sp.n_cand[0] == 0 || sp.n_cand[1] == 0))
+        return fail(ctx, IDN_E_INVALID_STATE, "need at least one acid model and one quality score model");
+    if (fast && n_models != 2) return fail(ctx, IDN_E_INVALID_STATE, "fast mode needs exactly 2 models (compressor_block.rs:96)");
+    for (uint32_t t = 0; t < 2; t++) {
+        sp.has_sizes[t] = !fast && sp.n_cand[t] > 1;
+        if (sp.has_sizes[t])
+            for (uint32_t k = 0; k < sp.n_cand[t]; k++) {
+                sp.cand_cols[t * kMaxCand + k] = n_score;
+                sp.score_ids[n_score++] = sp.cand_model[t * kMaxCand + k];
+            }
+    }
+    rc = upload_small(ctx, sp, st);
+    if (rc) return rc;
+    SmallParams* dsp = ctx->w_small.as<SmallParams>();
+
+    CU(ctx->w_scratch.ensure(4 * S + 8 * R + 16));
+    CU(ctx->w_paylen.ensure((R + 1) * 4));
+    CU(ctx->w_sliceoff.ensure((R + 2) * 8));
+    CU(ctx->w_readblock.ensure((R + 1) * 4));
+    const uint32_t n_tiles = (uint32_t)((R + kScanTile - 1) / kScanTile);
+    CU(ctx->w_tiles.ensure(((size_t)n_tiles + 2) * 8));
+    uint8_t* chosen = nullptr;
+    uint8_t* switched = nullptr;
+    if (!fast) {
+        CU(ctx->w_chosen.ensure(4 * R + 16));
+        chosen = ctx->w_chosen.as<uint8_t>();
+        switched = chosen + 2 * R;
+    }
+
+    if (R > 0) {
+        if (n_score) {  // K2
+            CU(ctx->w_sizes.ensure(R * n_score * 4));
+            uint64_t threads = R * n_score;
+            score_kernel<<<(unsigned)((threads + 127) / 128), 128, 0, st>>>(ctx->d_models, dsp->score_ids, n_score,
+                                                                           batch->acids, batch->quals, batch->read_off, R,
+                                                                           ctx->w_sizes.as<uint32_t>(), &dsp->err);
+            LAUNCHED();
+        }
+        if (!fast) {  // K3
+            switch_kernel<<<2 * B, 32, 0, st>>>(ctx->w_sizes.as<uint32_t>(), n_score, dsp->cand_cols, dsp->n_cand,
+                                                dsp->has_sizes, batch->block_first_read, B, chosen, switched, R);
+            LAUNCHED();
+        }
+        EncodeArgs ea;  // K4
+        ea.models = ctx->d_models;
+        ea.acids = batch->acids;
+        ea.quals = batch->quals;
+        ea.read_off = batch->read_off;
+        ea.n_reads = R;
+        ea.fixed_acid = sp.cand_model[0];
+        ea.fixed_q = sp.cand_model[kMaxCand];
+        ea.chosen = chosen;
+        ea.cand_model = dsp->cand_model;
+        ea.scratch = ctx->w_scratch.as<uint8_t>();
+        ea.pay_len = ctx->w_paylen.as<uint32_t>();
+        ea.err = &dsp->err;
+        encode_kernel<<<(unsigned)((R + 127) / 128), 128, 0, st>>>(ea);
+        LAUNCHED();
+    }
+
+    // slice offsets: exclusive scan of per-read slice sizes
+    SliceSize fn{ctx->w_paylen.as<uint32_t>(), switched, R};
+    unsigned long long* tiles = ctx->w_tiles.as<unsigned long long>();
+    unsigned long long* slice_off = ctx->w_sliceoff.as<unsigned long long>();
+    if (n_tiles) {
+        scan_reduce_kernel<<<n_tiles, kScanBlock, 0, st>>>(fn, R, tiles);
+        LAUNCHED();
+    }
+    scan_tiles_kernel<<<1, kScanBlock, 0, st>>>(tiles, n_tiles);
+    LAUNCHED();
+    if (n_tiles) {
+        scan_apply_kernel<<<n_tiles, kScanBlock, 0, st>>>(fn, R, tiles, slice_off);
+        LAUNCHED();
+    } else {
+        CU(cudaMemsetAsync(slice_off, 0, 8, st));
+    }
+    block_layout_kernel<<<1, 32, 0, st>>>(slice_off, batch->block_first_read, B, prefix_len, fast,
+                                          reinterpret_cast<unsigned long long*>(block_off), out, out_cap, dsp->stats);
+    LAUNCHED();
+    if (R > 0) {
+        read_block_kernel<<<B, 256, 0, st>>>(batch->block_first_read, B, ctx->w_readblock.as<uint32_t>());
+        LAUNCHED();
+        AssembleArgs aa;
+        aa.read_off = batch->read_off;
+        aa.n_reads = R;
+        aa.pay_len = ctx->w_paylen.as<uint32_t>();
+        aa.scratch = ctx->w_scratch.as<uint8_t>();
+        aa.slice_off = slice_off;
+        aa.block_off = reinterpret_cast<unsigned long long*>(block_off);
+        aa.block_first = batch->block_first_read;
+        aa.read_block = ctx->w_readblock.as<uint32_t>();
+        aa.prefix_len = prefix_len;
+        aa.fast = fast;
+        aa.chosen = chosen;
+        aa.switched = switched;
+        aa.cand_index = dsp->cand_index;
+        aa.out = out;
+        aa.out_cap = out_cap;
+        assemble_kernel<<<(unsigned)((R * 32 + 255) / 256), 256, 0, st>>>(aa);
+        LAUNCHED();
+        stats_kernel<<<592, 256, 0, st>>>(ctx->w_paylen.as<uint32_t>(), switched, R, dsp->stats);
+        LAUNCHED();
+    }
+    // K7: block CRCs into the block headers
+    rc = idn_gpu_block_crc_dev_impl(ctx, batch, block_crc, out, reinterpret_cast<unsigned long long*>(block_off), out_cap, st);
+    if (rc) return rc;
+    if (stats_dev) {
+        finish_stats_kernel<<<1, 32, 0, st>>>(dsp->stats, &dsp->err, reinterpret_cast<unsigned long long*>(stats_dev));
+        LAUNCHED();
+    }
+    return IDN_OK;
+}
+
+static int32_t idn_gpu_block_crc_dev_impl(idn_gpu_ctx* ctx, const idn_batch* batch, uint32_t* block_crc, uint8_t* out,
+                                          const unsigned long long* block_off, uint64_t out_cap, cudaStream_t st) {
+    const uint64_t R = batch->n_reads;
+    CU(ctx->w_crcpart.ensure((R + 1) * 4));
+    CU(ctx->w_crclen.ensure((R + 1) * 8));
+    if (R > 0) {
+        crc_read_kernel<<<(unsigned)((R + 127) / 128), 128, 0, st>>>(
+            batch->acids, batch->quals, reinterpret_cast<const unsigned long long*>(batch->read_off), batch->names,
+            reinterpret_cast<const unsigned long long*>(batch->name_off), R, nullptr, nullptr, ctx->d_crc_tab, ctx->d_xpow,
+            ctx->w_crcpart.as<uint32_t>(), ctx->w_crclen.as<unsigned long long>());
+        LAUNCHED();
+    }
+    crc_block_kernel<<<batch->n_blocks, 256, 0, st>>>(ctx->w_crcpart.as<uint32_t>(), ctx->w_crclen.as<unsigned long long>(),
+                                                      batch->block_first_read, batch->n_blocks, ctx->d_xpow, block_crc, out,
+                                                      block_off, out_cap);
+    LAUNCHED();
+    return IDN_OK;
+}
+
+// upload a host batch into the staging buffers; returns the device view
+static int32_t stage_batch(idn_gpu_ctx* ctx, const idn_batch* b, idn_batch* d, cudaStream_t st) {
+    CU(ctx->s_acids.ensure(b->n_symbols + 16));
+    CU(ctx->s_quals.ensure(b->n_symbols + 16));
+    CU(ctx->s_readoff.ensure((b->n_reads + 1) * 8));
+    CU(ctx->s_blockfirst.ensure(((size_t)b->n_blocks + 1) * 4));
+    if (b->n_symbols) {
+        CU(cudaMemcpyAsync(ctx->s_acids.p, b->acids, b->n_symbols, cudaMemcpyHostToDevice, st));
+        CU(cudaMemcpyAsync(ctx->s_quals.p, b->quals, b->n_symbols, cudaMemcpyHostToDevice, st));
+    }
+    if (b->n_reads) {
+        CU(cudaMemcpyAsync(ctx->s_readoff.p, b->read_off, (b->n_reads + 1) * 8, cudaMemcpyHostToDevice, st));
+    } else {
+        CU(cudaMemsetAsync(ctx->s_readoff.p, 0, 8, st));
+    }
+    CU(cudaMemcpyAsync(ctx->s_blockfirst.p, b->block_first_read, ((size_t)b->n_blocks + 1) * 4, cudaMemcpyHostToDevice, st));
+    *d = *b;
+    d->acids = ctx->s_acids.as<uint8_t>();
+    d->quals = ctx->s_quals.as<uint8_t>();
+    d->read_off = ctx->s_readoff.as<uint64_t>();
+    d->block_first_read = ctx->s_blockfirst.as<uint32_t>();
+    d->names = nullptr;
+    d->name_off = nullptr;
+    if (b->names && b->n_reads) {
+        uint64_t nbytes = b->name_off[b->n_reads];
+        CU(ctx->s_names.ensure(nbytes + 16));
+        CU(ctx->s_nameoff.ensure((b->n_reads + 1) * 8));
+        if (nbytes) CU(cudaMemcpyAsync(ctx->s_names.p, b->names, nbytes, cudaMemcpyHostToDevice, st));
+        CU(cudaMemcpyAsync(ctx->s_nameoff.p, b->name_off, (b->n_reads + 1) * 8, cudaMemcpyHostToDevice, st));
+        d->names = ctx->s_names.as<uint8_t>();
+        d->name_off = ctx->s_nameoff.as<uint64_t>();
+    }
+    return IDN_OK;
+}
+
+static int32_t check_host_batch(idn_gpu_ctx* ctx, const idn_batch* b, bool need_blocks) {
+    int32_t rc = check_batch(ctx, b);
+    if (rc) return rc;
+    if (b->n_reads) {
+        if (b->read_off[0] != 0 || b->read_off[b->n_reads] != b->n_symbols)
+            return fail(ctx, IDN_E_INVALID_ARG, "read_off does not span [0, n_symbols]");
+        for (uint64_t r = 0; r < b->n_reads; r++) {
+            if (b->read_off[r + 1] < b->read_off[r]) return fail(ctx, IDN_E_INVALID_ARG, "read_off is not monotone");
+            if (b->read_off[r + 1] - b->read_off[r] > (1ull << 26))
+                return fail(ctx, IDN_E_SEQUENCE_TOO_LONG, "read %llu is longer than 2^26 symbols", (unsigned long long)r);
+        }
+    } else if (b->n_symbols) {
+        return fail(ctx, IDN_E_INVALID_ARG, "symbols without reads");
+    }
+    if (need_blocks) {
+        if (!b->block_first_read || b->n_blocks == 0) return fail(ctx, IDN_E_INVALID_ARG, "batch has no blocks");
+        if (b->block_first_read[0] != 0 || b->block_first_read[b->n_blocks] != b->n_reads)
+            return fail(ctx, IDN_E_INVALID_ARG, "block_first_read does not span [0, n_reads]");
+        for (uint32_t i = 0; i < b->n_blocks; i++)
+            if (b->block_first_read[i + 1] < b->block_first_read[i])
+                return fail(ctx, IDN_E_INVALID_ARG, "block_first_read is not monotone");
+    }
+    return IDN_OK;
+}
+
+extern "C" int32_t idn_gpu_compress_blocks(idn_gpu_ctx* ctx, const idn_batch* b, int32_t mode, const idn_model_t* models,
+                                           uint32_t n_models, int32_t fast, const uint32_t* prefix_len, uint8_t* out,
+                                           uint64_t out_cap, uint64_t* block_off, uint32_t* block_crc,
+                                           idn_compress_stats* stats) {
+    if (!ctx) return IDN_E_INVALID_ARG;
+    int32_t rc = check_host_batch(ctx, b, true);
+    if (rc) return rc;
+    if (!block_off) return fail(ctx, IDN_E_INVALID_ARG, "block_off is NULL");
+    CU(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    idn_batch d;
+    rc = stage_batch(ctx, b, &d, st);
+    if (rc) return rc;
+    uint32_t* d_prefix = nullptr;
+    uint64_t prefix_total = 0;
+    if (prefix_len) {
+        for (uint32_t i = 0; i < b->n_blocks; i++) prefix_total += prefix_len[i];
+        CU(ctx->s_prefix.ensure((size_t)b->n_blocks * 4));
+        CU(cudaMemcpyAsync(ctx->s_prefix.p, prefix_len, (size_t)b->n_blocks * 4, cudaMemcpyHostToDevice, st));
+        d_prefix = ctx->s_prefix.as<uint32_t>();
+    }
+    uint64_t bound = idn_gpu_compress_bound(b->n_reads, b->n_symbols, b->n_blocks, prefix_total);
+    uint64_t dcap = out_cap < bound ? out_cap : bound;
+    CU(ctx->s_out.ensure(dcap + 16));
+    CU(ctx->s_blockoff.ensure(((size_t)b->n_blocks + 1) * 8));
+    CU(ctx->s_crc.ensure((size_t)b->n_blocks * 4));
+    CU(ctx->s_stats.ensure(sizeof(idn_compress_stats)));
+    rc = idn_gpu_compress_blocks_dev(ctx, &d, mode, models, n_models, fast, d_prefix, ctx->s_out.as<uint8_t>(), dcap,
+                                     ctx->s_blockoff.as<uint64_t>(), ctx->s_crc.as<uint32_t>(),
+                                     ctx->s_stats.as<idn_compress_stats>(), st);
+    if (rc) return rc;
+    idn_compress_stats hs;
+    uint32_t err = 0;
+    CU(cudaMemcpyAsync(&hs, ctx->s_stats.p, sizeof hs, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(&err, &ctx->w_small.as<SmallParams>()->err, 4, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    if (stats) *stats = hs;
+    if (err & 1) return fail(ctx, IDN_E_INVALID_SYMBOL, "input holds an acid > 4 or a quality score > 93");
+    if (hs.required_bytes > out_cap) {
+        if (stats) stats->out_bytes = 0;
+        return fail(ctx, IDN_E_NOSPACE, "output needs %llu bytes, capacity is %llu", (unsigned long long)hs.required_bytes,
+                    (unsigned long long)out_cap);
+    }
+    if (hs.out_bytes) CU(cudaMemcpyAsync(out, ctx->s_out.p, hs.out_bytes, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(block_off, ctx->s_blockoff.p, ((size_t)b->n_blocks + 1) * 8, cudaMemcpyDeviceToHost, st));
+    if (block_crc) CU(cudaMemcpyAsync(block_crc, ctx->s_crc.p, (size_t)b->n_blocks * 4, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    return IDN_OK;
+}
+
+extern "C" int32_t idn_gpu_block_crc(idn_gpu_ctx* ctx, const idn_batch* b, uint32_t* block_crc) {
+    if (!ctx) return IDN_E_INVALID_ARG;
+    int32_t rc = check_host_batch(ctx, b, true);
+    if (rc) return rc;
+    if (!block_crc) return fail(ctx, IDN_E_INVALID_ARG, "block_crc is NULL");
+    CU(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    idn_batch d;
+    rc = stage_batch(ctx, b, &d, st);
+    if (rc) return rc;
+    CU(ctx->s_crc.ensure((size_t)b->n_blocks * 4));
+    rc = idn_gpu_block_crc_dev_impl(ctx, &d, ctx->s_crc.as<uint32_t>(), nullptr, nullptr, 0, st);
+    if (rc) return rc;
+    CU(cudaMemcpyAsync(block_crc, ctx->s_crc.p, (size_t)b->n_blocks * 4, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    return IDN_OK;
+}
+
+// ======================================================================================================
+// decompression
+// ======================================================================================================
+namespace {
+struct IndexView {  // per-read index arrays carved out of w_index for `cap` reads
+    unsigned long long* pay_off;
+    unsigned long long* out_off;  // [cap+1]
+    uint32_t* pay_len;
+    uint32_t* seq_len;
+    uint8_t* am;
+    uint8_t* qm;
+    static size_t bytes(uint64_t cap) { return (cap + 2) * (8 + 8 + 4 + 4 + 1 + 1) + 64; }
+    void carve(void* base, uint64_t cap) {
+        uint8_t* p = reinterpret_cast<uint8_t*>(base);
+        pay_off = reinterpret_cast<unsigned long long*>(p);
+        p += (cap + 2) * 8;
+        out_off = reinterpret_cast<unsigned long long*>(p);
+        p += (cap + 2) * 8;
+        pay_len = reinterpret_cast<uint32_t*>(p);
+        p += (cap + 2) * 4;
+        seq_len = reinterpret_cast<uint32_t*>(p);
+        p += (cap + 2) * 4;
+        am = p;
+        p += cap + 2;
+        qm = p;
+    }
+};
+}  // namespace
+
+// shared by idn_gpu_index_blocks and the decoders: count pass + scan.  Leaves per-block read/symbol bases in w_blk:
+//   blk_reads[0..B] (exclusive scan, [B] = total), blk_syms[0..B]
+static int32_t index_count(idn_gpu_ctx* ctx, const uint8_t* blocks, const unsigned long long* block_off, uint32_t B,
+                           const SmallParams* dsp, uint32_t n_models, cudaStream_t st) {
+    CU(ctx->w_blk.ensure(((size_t)B + 2) * 8 * 2));
+    unsigned long long* blk_reads = ctx->w_blk.as<unsigned long long>();
+    unsigned long long* blk_syms = blk_reads + B + 2;
+    index_count_kernel<<<(B + 31) / 32, 32, 0, st>>>(blocks, block_off, B, ctx->d_models, dsp->model_ids, n_models, blk_reads,
+                                                     blk_syms, const_cast<int32_t*>(dsp->status));
+    LAUNCHED();
+    scan_tiles_kernel<<<1, kScanBlock, 0, st>>>(blk_reads, B);
+    LAUNCHED();
+    scan_tiles_kernel<<<1, kScanBlock, 0, st>>>(blk_syms, B);
+    LAUNCHED();
+    return IDN_OK;
+}
+
+extern "C" int32_t idn_gpu_decompress_blocks_dev(idn_gpu_ctx* ctx, const uint8_t* blocks, const uint64_t* block_off,
+                                                 const uint32_t* block_crc, uint32_t n_blocks, uint64_t blocks_bytes,
+                                                 int32_t mode, const idn_model_t* models, uint32_t n_models,
+                                                 uint8_t* acids_out, uint8_t* quals_out, uint64_t* read_off_out,
+                                                 uint64_t out_reads_cap, uint64_t out_symbols_cap, int32_t* status_dev,
+                                                 void* stream) {
+    if (!ctx) return IDN_E_INVALID_ARG;
+    int32_t rc = check_models(ctx, models, n_models);
+    if (rc) return rc;
+    if (mode != IDN_MODE_COMPAT) return fail(ctx, IDN_E_UNSUPPORTED, "mode %d is not implemented", mode);
+    if (!block_off || !status_dev || (!blocks && blocks_bytes)) return fail(ctx, IDN_E_INVALID_ARG, "NULL argument");
+    if (out_reads_cap >= (1ull << 32) - 2) return fail(ctx, IDN_E_INVALID_ARG, "out_reads_cap too large");
+    CU(cudaSetDevice(ctx->device));
+    cudaStream_t st = as_stream(stream);
+    SmallParams sp;
+    memset(&sp, 0, sizeof sp);
+    for (uint32_t i = 0; i < n_models; i++) sp.model_ids[i] = models[i];
+    sp.status[1] = -1;
+    rc = upload_small(ctx, sp, st);
+    if (rc) return rc;
+    SmallParams* dsp = ctx->w_small.as<SmallParams>();
+    const unsigned long long* boff = reinterpret_cast<const unsigned long long*>(block_off);
+    if (n_blocks) {
+        rc = index_count(ctx, blocks, boff, n_blocks, dsp, n_models, st);
+        if (rc) return rc;
+    } else {
+        CU(ctx->w_blk.ensure(4 * 8 * 2));
+        CU(cudaMemsetAsync(ctx->w_blk.p, 0, 4 * 8 * 2, st));
+    }
+    unsigned long long* blk_reads = ctx->w_blk.as<unsigned long long>();
+    unsigned long long* blk_syms = blk_reads + n_blocks + 2;
+    CU(ctx->w_index.ensure(IndexView::bytes(out_reads_cap)));
+    IndexView iv;
+    iv.carve(ctx->w_index.p, out_reads_cap);
+    CU(ctx->w_readblock.ensure(((size_t)n_blocks + 2) * 4));
+    uint32_t* block_first = ctx->w_readblock.as<uint32_t>();
+    // capacity check on the device; on failure the later kernels see n_reads = 0
+    index_check_kernel<<<1, 32, 0, st>>>(blk_reads, blk_syms, n_blocks, out_reads_cap, out_symbols_cap, dsp->status);
+    LAUNCHED();
+    index_fill_kernel<<<(n_blocks + 1 + 31) / 32, 32, 0, st>>>(blocks, boff, n_blocks, ctx->d_models, dsp->model_ids, n_models,
+                                                              blk_reads, blk_syms, iv.pay_off, iv.pay_len, iv.seq_len,
+                                                              iv.out_off, iv.am, iv.qm, block_first, dsp->status);
+    LAUNCHED();
+    DecodeArgs da;
+    da.models = ctx->d_models;
+    da.model_ids = dsp->model_ids;
+    da.payload = blocks;
+    da.pay_off = iv.pay_off;
+    da.pay_len = iv.pay_len;
+    da.seq_len = iv.seq_len;
+    da.out_off = iv.out_off;
+    da.acid_model = iv.am;
+    da.q_model = iv.qm;
+    da.n_reads = 0;
+    da.n_reads_dev = blk_reads + n_blocks;
+    da.status = dsp->status;
+    da.acids_out = acids_out;
+    da.quals_out = quals_out;
+    da.read_status = nullptr;
+    da.err = &dsp->err;
+    if (out_reads_cap) {
+        decode_kernel<<<(unsigned)((out_reads_cap + 127) / 128), 128, 0, st>>>(da);
+        LAUNCHED();
+    }
+    // CRC of the decoded symbols per block, compared with the header value (decompressor_block.rs:131-144)
+    if (block_crc && n_blocks && out_reads_cap) {
+        CU(ctx->w_crcpart.ensure((out_reads_cap + 1) * 4));
+        CU(ctx->w_crclen.ensure((out_reads_cap + 1) * 8));
+        crc_read_kernel<<<(unsigned)((out_reads_cap + 127) / 128), 128, 0, st>>>(
+            acids_out, quals_out, iv.out_off, nullptr, nullptr, 0, blk_reads + n_blocks, dsp->status, ctx->d_crc_tab,
+            ctx->d_xpow, ctx->w_crcpart.as<uint32_t>(), ctx->w_crclen.as<unsigned long long>());
+        LAUNCHED();
+        crc_verify_kernel<<<n_blocks, 256, 0, st>>>(ctx->w_crcpart.as<uint32_t>(), ctx->w_crclen.as<unsigned long long>(),
+                                                    block_first, n_blocks, ctx->d_xpow, block_crc, dsp->status);
+        LAUNCHED();
+    }
+    finish_decode_kernel<<<(unsigned)((out_reads_cap + 1 + 255) / 256), 256, 0, st>>>(
+        dsp->status, &dsp->err, blk_reads + n_blocks, blk_syms + n_blocks, iv.out_off, reinterpret_cast<unsigned long long*>(read_off_out), out_reads_cap, status_dev);
+    LAUNCHED();
+    return IDN_OK;
+}
+
+static int32_t status_to_error(idn_gpu_ctx* ctx, const int32_t st[4]) {
+    switch (st[0]) {
+        case IDN_OK: return IDN_OK;
+        case IDN_E_SERIALIZE: return fail(ctx, st[0], "malformed slice in block %d", st[1]);
+        case IDN_E_INVALID_MODEL_INDEX: return fail(ctx, st[0], "SwitchModel index out of range in block %d", st[1]);
+        case IDN_E_NO_ACTIVE_MODEL: return fail(ctx, st[0], "sequence slice before any SwitchModel in block %d", st[1]);
+        case IDN_E_CHECKSUM: return fail(ctx, st[0], "checksum mismatch in block %d", st[1]);
+        case IDN_E_NOSPACE: return fail(ctx, st[0], "output capacity too small (%d reads needed)", st[2]);
+        default: return fail(ctx, st[0], "decode failed with status %d in block %d", st[0], st[1]);
+    }
+}
+
+extern "C" int32_t idn_gpu_index_blocks(idn_gpu_ctx* ctx, const uint8_t* blocks, const uint64_t* block_off, uint32_t n_blocks,
+                                        const idn_model_t* models, uint32_t n_models, idn_block_index_totals* totals,
+                                        uint32_t* block_first_read) {
+    if (!ctx) return IDN_E_INVALID_ARG;
+    int32_t rc = check_models(ctx, models, n_models);
+    if (rc) return rc;
+    if (!totals || !block_off) return fail(ctx, IDN_E_INVALID_ARG, "NULL argument");
+    totals->n_reads = totals->n_symbols = 0;
+    if (block_first_read) block_first_read[0] = 0;
+    if (n_blocks == 0) return IDN_OK;
+    for (uint32_t i = 0; i < n_blocks; i++)
+        if (block_off[i + 1] < block_off[i]) return fail(ctx, IDN_E_INVALID_ARG, "block_off is not monotone");
+    if (!blocks && block_off[n_blocks]) return fail(ctx, IDN_E_INVALID_ARG, "blocks is NULL");
+    CU(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    uint64_t nbytes = block_off[n_blocks];
+    CU(ctx->s_blocks.ensure(nbytes + 16));
+    CU(ctx->s_blockoff.ensure(((size_t)n_blocks + 1) * 8));
+    if (nbytes) CU(cudaMemcpyAsync(ctx->s_blocks.p, blocks, nbytes, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(ctx->s_blockoff.p, block_off, ((size_t)n_blocks + 1) * 8, cudaMemcpyHostToDevice, st));
+    SmallParams sp;
+    memset(&sp, 0, sizeof sp);
+    for (uint32_t i = 0; i < n_models; i++) sp.model_ids[i] = models[i];
+    sp.status[1] = -1;
+    rc = upload_small(ctx, sp, st);
+    if (rc) return rc;
+    SmallParams* dsp = ctx->w_small.as<SmallParams>();
+    rc = index_count(ctx, ctx->s_blocks.as<uint8_t>(), ctx->s_blockoff.as<unsigned long long>(), n_blocks, dsp, n_models, st);
+    if (rc) return rc;
+    std::vector<unsigned long long> hr(n_blocks + 1), hsym(n_blocks + 1);
+    int32_t hst[4];
+    unsigned long long* blk_reads = ctx->w_blk.as<unsigned long long>();
+    CU(cudaMemcpyAsync(hr.data(), blk_reads, ((size_t)n_blocks + 1) * 8, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(hsym.data(), blk_reads + n_blocks + 2, ((size_t)n_blocks + 1) * 8, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(hst, dsp->status, sizeof hst, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    if (hst[0]) return status_to_error(ctx, hst);
+    totals->n_reads = hr[n_blocks];
+    totals->n_symbols = hsym[n_blocks];
+    if (block_first_read)
+        for (uint32_t i = 0; i <= n_blocks; i++) block_first_read[i] = (uint32_t)hr[i];
+    return IDN_OK;
+}
+
+extern "C" int32_t idn_gpu_decompress_blocks(idn_gpu_ctx* ctx, const uint8_t* blocks, const uint64_t* block_off,
+                                             const uint32_t* block_crc, uint32_t n_blocks, int32_t mode,
+                                             const idn_model_t* models, uint32_t n_models, const uint8_t* names,
+                                             const uint64_t* name_off, uint8_t* acids_out, uint8_t* quals_out,
+                                             uint64_t* read_off_out, uint64_t out_reads_cap, uint64_t out_symbols_cap,
+                                             int32_t* bad_block) {
+    if (!ctx) return IDN_E_INVALID_ARG;
+    if (bad_block) *bad_block = -1;
+    if (!block_off || !read_off_out) return fail(ctx, IDN_E_INVALID_ARG, "NULL argument");
+    if ((names != nullptr) != (name_off != nullptr)) return fail(ctx, IDN_E_INVALID_ARG, "names and name_off go together");
+    if (out_symbols_cap && (!acids_out || !quals_out)) return fail(ctx, IDN_E_INVALID_ARG, "NULL output");
+    for (uint32_t i = 0; i < n_blocks; i++)
+        if (block_off[i + 1] < block_off[i]) return fail(ctx, IDN_E_INVALID_ARG, "block_off is not monotone");
+    uint64_t nbytes = n_blocks ? block_off[n_blocks] : 0;
+    if (!blocks && nbytes) return fail(ctx, IDN_E_INVALID_ARG, "blocks is NULL");
+    CU(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    CU(ctx->s_blocks.ensure(nbytes + 16));
+    CU(ctx->s_blockoff.ensure(((size_t)n_blocks + 1) * 8));
+    CU(ctx->s_crc.ensure(((size_t)n_blocks + 1) * 4));
+    CU(ctx->s_aout.ensure(out_symbols_cap + 16));
+    CU(ctx->s_qout.ensure(out_symbols_cap + 16));
+    CU(ctx->s_offout.ensure((out_reads_cap + 1) * 8));
+    CU(ctx->s_status.ensure(64));
+    if (nbytes) CU(cudaMemcpyAsync(ctx->s_blocks.p, blocks, nbytes, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(ctx->s_blockoff.p, block_off, ((size_t)n_blocks + 1) * 8, cudaMemcpyHostToDevice, st));
+    // names join the block CRC (sequence.rs:381-394): when given, the device verifies symbols only and the name bytes are
+    // folded in on the host below; otherwise the device compares against the header directly.
+    const bool host_crc = names != nullptr;
+    if (block_crc && !host_crc && n_blocks)
+        CU(cudaMemcpyAsync(ctx->s_crc.p, block_crc, (size_t)n_blocks * 4, cudaMemcpyHostToDevice, st));
+    int32_t rc = idn_gpu_decompress_blocks_dev(ctx, ctx->s_blocks.as<uint8_t>(), ctx->s_blockoff.as<uint64_t>(),
+                                               (block_crc && !host_crc) ? ctx->s_crc.as<uint32_t>() : nullptr, n_blocks, nbytes,
+                                               mode, models, n_models, ctx->s_aout.as<uint8_t>(), ctx->s_qout.as<uint8_t>(),
+                                               ctx->s_offout.as<uint64_t>(), out_reads_cap, out_symbols_cap,
+                                               ctx->s_status.as<int32_t>(), st);
+    if (rc) return rc;
+    int32_t hst[4];
+    unsigned long long tot[2];
+    CU(cudaMemcpyAsync(hst, ctx->s_status.p, sizeof hst, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(&tot[0], ctx->w_blk.as<unsigned long long>() + n_blocks, 8, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(&tot[1], ctx->w_blk.as<unsigned long long>() + n_blocks + 2 + n_blocks, 8, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    if (hst[0]) {
+        if (bad_block) *bad_block = hst[1];
+        return status_to_error(ctx, hst);
+    }
+    uint64_t R = tot[0], S = tot[1];
+    if (S) {
+        CU(cudaMemcpyAsync(acids_out, ctx->s_aout.p, S, cudaMemcpyDeviceToHost, st));
+        CU(cudaMemcpyAsync(quals_out, ctx->s_qout.p, S, cudaMemcpyDeviceToHost, st));
+    }
+    CU(cudaMemcpyAsync(read_off_out, ctx->s_offout.p, (R + 1) * 8, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    if (host_crc && block_crc && n_blocks) {
+        // CRC with names on the device: stage names and run the CRC kernels over the decoded batch
+        idn_batch d;
+        memset(&d, 0, sizeof d);
+        d.n_reads = R;
+        d.n_symbols = S;
+        d.n_blocks = n_blocks;
+        d.acids = ctx->s_aout.as<uint8_t>();
+        d.quals = ctx->s_qout.as<uint8_t>();
+        d.read_off = ctx->s_offout.as<uint64_t>();
+        d.block_first_read = ctx->w_readblock.as<uint32_t>();
+        uint64_t nb = R ? name_off[R] : 0;
+        CU(ctx->s_names.ensure(nb + 16));
+        CU(ctx->s_nameoff.ensure((R + 1) * 8));
+        if (nb) CU(cudaMemcpyAsync(ctx->s_names.p, names, nb, cudaMemcpyHostToDevice, st));
+        CU(cudaMemcpyAsync(ctx->s_nameoff.p, name_off, (R + 1) * 8, cudaMemcpyHostToDevice, st));
+        d.names = ctx->s_names.as<uint8_t>();
+        d.name_off = ctx->s_nameoff.as<uint64_t>();
+        rc = idn_gpu_block_crc_dev_impl(ctx, &d, ctx->s_crc.as<uint32_t>(), nullptr, nullptr, 0, st);
+        if (rc) return rc;
+        std::vector<uint32_t> got(n_blocks);
+        CU(cudaMemcpyAsync(got.data(), ctx->s_crc.p, (size_t)n_blocks * 4, cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+        for (uint32_t i = 0; i < n_blocks; i++)
+            if (got[i] != block_crc[i]) {
+                if (bad_block) *bad_block = (int32_t)i;
+                return fail(ctx, IDN_E_CHECKSUM, "checksum mismatch in block %u", i);
+            }
+    }
+    return IDN_OK;
+}
+
+extern "C" int32_t idn_gpu_decompress_reads(idn_gpu_ctx* ctx, const uint8_t* payload, uint64_t payload_bytes,
+                                            const idn_read_index* index, const idn_model_t* models, uint32_t n_models,
+                                            uint8_t* acids_out, uint8_t* quals_out, uint32_t* read_status) {
+    if (!ctx) return IDN_E_INVALID_ARG;
+    int32_t rc = check_models(ctx, models, n_models);
+    if (rc) return rc;
+    if (!index) return fail(ctx, IDN_E_INVALID_ARG, "index is NULL");
+    const uint64_t R = index->n_reads;
+    if (R == 0) return IDN_OK;
+    if (!index->pay_off || !index->pay_len || !index->seq_len || !index->out_off || !index->acid_model || !index->q_model)
+        return fail(ctx, IDN_E_INVALID_ARG, "NULL index array");
+    if (!payload && payload_bytes) return fail(ctx, IDN_E_INVALID_ARG, "payload is NULL");
+    uint64_t S = 0;
+    for (uint64_t r = 0; r < R; r++) {
+        if (index->pay_off[r] + index->pay_len[r] > payload_bytes) return fail(ctx, IDN_E_SERIALIZE, "read %llu payload out of range", (unsigned long long)r);
+        if (index->out_off[r] != S) return fail(ctx, IDN_E_INVALID_ARG, "out_off is not the exclusive scan of seq_len");
+        S += index->seq_len[r];
+        if (index->acid_model[r] >= n_models || index->q_model[r] >= n_models)
+            return fail(ctx, IDN_E_INVALID_MODEL_INDEX, "read %llu names model index out of range", (unsigned long long)r);
+        if (ctx->slots[models[index->acid_model[r]]].dev.type != IDN_MODEL_ACID ||
+            ctx->slots[models[index->q_model[r]]].dev.type != IDN_MODEL_QSCORE)
+            return fail(ctx, IDN_E_INVALID_MODEL_INDEX, "read %llu names a model of the wrong type", (unsigned long long)r);
+    }
+    if (index->out_off[R] != S) return fail(ctx, IDN_E_INVALID_ARG, "out_off[n_reads] != sum of seq_len");
+    if (S && (!acids_out || !quals_out)) return fail(ctx, IDN_E_INVALID_ARG, "NULL output");
+    CU(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    SmallParams sp;
+    memset(&sp, 0, sizeof sp);
+    for (uint32_t i = 0; i < n_models; i++) sp.model_ids[i] = models[i];
+    rc = upload_small(ctx, sp, st);
+    if (rc) return rc;
+    SmallParams* dsp = ctx->w_small.as<SmallParams>();
+    CU(ctx->s_blocks.ensure(payload_bytes + 16));
+    CU(ctx->w_index.ensure(IndexView::bytes(R)));
+    CU(ctx->s_aout.ensure(S + 16));
+    CU(ctx->s_qout.ensure(S + 16));
+    CU(ctx->s_idx.ensure((R + 1) * 4));
+    IndexView iv;
+    iv.carve(ctx->w_index.p, R);
+    if (payload_bytes) CU(cudaMemcpyAsync(ctx->s_blocks.p, payload, payload_bytes, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(iv.pay_off, index->pay_off, R * 8, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(iv.out_off, index->out_off, (R + 1) * 8, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(iv.pay_len, index->pay_len, R * 4, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(iv.seq_len, index->seq_len, R * 4, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(iv.am, index->acid_model, R, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(iv.qm, index->q_model, R, cudaMemcpyHostToDevice, st));
+    DecodeArgs da;
+    da.models = ctx->d_models;
+    da.model_ids = dsp->model_ids;
+    da.payload = ctx->s_blocks.as<uint8_t>();
+    da.pay_off = iv.pay_off;
+    da.pay_len = iv.pay_len;
+    da.seq_len = iv.seq_len;
+    da.out_off = iv.out_off;
+    da.acid_model = iv.am;
+    da.q_model = iv.qm;
+    da.n_reads = R;
+    da.n_reads_dev = nullptr;
+    da.status = nullptr;
+    da.acids_out = ctx->s_aout.as<uint8_t>();
+    da.quals_out = ctx->s_qout.as<uint8_t>();
+    da.read_status = ctx->s_idx.as<uint32_t>();
+    da.err = &dsp->err;
+    decode_kernel<<<(unsigned)((R + 127) / 128), 128, 0, st>>>(da);
+    LAUNCHED();
+    uint32_t err = 0;
+    if (S) {
+        CU(cudaMemcpyAsync(acids_out, ctx->s_aout.p, S, cudaMemcpyDeviceToHost, st));
+        CU(cudaMemcpyAsync(quals_out, ctx->s_qout.p, S, cudaMemcpyDeviceToHost, st));
+    }
+    if (read_status) CU(cudaMemcpyAsync(read_status, ctx->s_idx.p, R * 4, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(&err, &dsp->err, 4, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    if (err & 1) return fail(ctx, IDN_E_SERIALIZE, "a sequence payload ended before its symbols were decoded");
+    return IDN_OK;
+}

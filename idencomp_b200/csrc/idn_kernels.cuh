@@ -1,0 +1,931 @@
+// idn_kernels.cuh -- the CUDA kernels of the hot path (sm_100a).  See DESIGN.md for the launch plan.
+//
+//   K2  score_kernel      ModelTester::compute_size           idn/model_chooser.rs:215-243
+//   K3  switch_kernel     get_best_model_for + switch_to_*    idn/model_chooser.rs:168-198, compressor_block.rs:232-280
+//   K4  encode_kernel     SequenceCompressor::compress        sequence_compressor.rs:82-155, compressor.rs:83-98
+//       layout/assemble   BlockWriter                         idn/writer_block.rs:27-82
+//   K5  decode_kernel     SequenceDecompressor::decompress    sequence_compressor.rs:231-278, compressor.rs:173-193
+//       index kernels     IdnBlockDecompressor slice walk     idn/decompressor_block.rs:115-129,194-239
+//   K7  crc kernels       crc32 over name|acids|quals         writer_block.rs:64, sequence.rs:381-394
+#pragma once
+#include "idn_device.cuh"
+
+namespace idn {
+
+// ---------------------------------------------------------------------------------------------------
+// byte readers / writers on 4-byte words (threads walk their read sequentially; word access keeps the
+// divergent traffic at one 32-byte sector per 32 bytes instead of one per byte)
+// ---------------------------------------------------------------------------------------------------
+struct BackReader {  // reads bytes at decreasing global indices
+    const uint8_t* base;
+    uint32_t word;
+    __device__ __forceinline__ uint32_t get(long long g) {  // g may be < first valid index -> caller guards
+        uint32_t sh = (uint32_t)(g & 3) * 8;
+        if (sh == 24 || word == 0xffffffffu) word = __ldg(reinterpret_cast<const uint32_t*>(base + (g & ~3ll)));
+        return (word >> sh) & 0xffu;
+    }
+};
+
+struct FwdReader {  // reads bytes at increasing global indices
+    const uint8_t* base;
+    uint32_t word;
+    bool primed;
+    __device__ __forceinline__ void init(const uint8_t* b) {
+        base = b;
+        primed = false;
+        word = 0;
+    }
+    __device__ __forceinline__ uint32_t get(unsigned long long g) {
+        uint32_t sh = (uint32_t)(g & 3) * 8;
+        if (sh == 0 || !primed) {
+            word = __ldg(reinterpret_cast<const uint32_t*>(base + (g & ~3ull)));
+            primed = true;
+        }
+        return (word >> sh) & 0xffu;
+    }
+};
+
+// writes bytes at decreasing addresses, 4 at a time.  `end` must be 4-byte aligned.
+struct BackWriter {
+    uint32_t* wptr;  // next word to fill is wptr[-1]
+    uint32_t acc, n;
+    __device__ __forceinline__ void init(uint8_t* end) {
+        wptr = reinterpret_cast<uint32_t*>(end);
+        acc = 0;
+        n = 0;
+    }
+    __device__ __forceinline__ void push(uint32_t b) {
+        acc = (acc >> 8) | (b << 24);
+        if (++n == 4) {
+            *--wptr = acc;
+            n = 0;
+        }
+    }
+    __device__ __forceinline__ void push_u32_le(uint32_t x) {  // RansEncFlush: x stored little-endian below ptr
+        push(x >> 24);
+        push((x >> 16) & 0xffu);
+        push((x >> 8) & 0xffu);
+        push(x & 0xffu);
+    }
+    __device__ __forceinline__ void finish() {  // leftover bytes sit in the high bytes of acc
+        uint8_t* p = reinterpret_cast<uint8_t*>(wptr);
+        for (uint32_t k = 0; k < n; k++) p[-1 - (int)k] = (uint8_t)(acc >> (24 - 8 * k));
+    }
+};
+
+// writes bytes at increasing addresses starting anywhere
+struct FwdWriter {
+    uint8_t* p;
+    uint32_t acc, n;
+    __device__ __forceinline__ void init(uint8_t* dst) {
+        p = dst;
+        acc = 0;
+        n = 0;
+    }
+    __device__ __forceinline__ void push(uint32_t b) {
+        if ((reinterpret_cast<uintptr_t>(p) & 3) != 0 && n == 0) {  // head: byte stores until aligned
+            *p++ = (uint8_t)b;
+            return;
+        }
+        acc |= b << (8 * n);
+        if (++n == 4) {
+            *reinterpret_cast<uint32_t*>(p) = acc;
+            p += 4;
+            acc = 0;
+            n = 0;
+        }
+    }
+    __device__ __forceinline__ void finish() {
+        for (uint32_t k = 0; k < n; k++) p[k] = (uint8_t)(acc >> (8 * k));
+    }
+};
+
+// ---------------------------------------------------------------------------------------------------
+// K2: forward single-state scorer.  One thread per (read, model).
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128)
+score_kernel(const ModelDev* __restrict__ models, const int32_t* __restrict__ model_ids, uint32_t n_models,
+             const uint8_t* __restrict__ acids, const uint8_t* __restrict__ quals,
+             const uint64_t* __restrict__ read_off, uint64_t n_reads, uint32_t* __restrict__ sizes,
+             uint32_t* __restrict__ err) {
+    uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    uint64_t r = t / n_models;
+    if (r >= n_reads) return;
+    uint32_t mi = (uint32_t)(t - r * n_models);
+    const ModelDev& m = models[model_ids[mi]];
+    uint64_t off = read_off[r];
+    uint32_t len = (uint32_t)(read_off[r + 1] - off);
+    GenFwd g;
+    g.init();
+    FwdReader ra, rq;
+    ra.init(acids);
+    rq.init(quals);
+    uint32_t x = kRansL, bytes = 0;
+    bool bad = false;
+    for (uint32_t i = 0; i < len; i++) {
+        uint32_t a = ra.get(off + i), q = rq.get(off + i);
+        if (a > 4 || q > 93) {
+            bad = true;
+            a = a > 4 ? 0 : a;
+            q = q > 93 ? 0 : q;
+        }
+        uint32_t row = ctx_row(m, g.spec(m.spec));
+        uint32_t sym = m.type == 0 ? a : q;
+        uint2 e = __ldg(m.enc + (size_t)row * m.nsym + sym);
+        rans_put_count(x, e, bytes);
+        g.update(m.spec, a, q, len);
+    }
+    sizes[r * n_models + mi] = bytes + 4;
+    if (bad) atomicOr(err, 1u);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// K3: greedy per-read model choice inside each block.  One warp per (block, model type).
+// The choice for read r depends on the model active after read r-1, so the warp composes per-chunk
+// transition functions: lane l simulates its chunk for every possible incoming state, a 32-step
+// sequential pass picks the true incoming state of every lane, and each lane then replays its chunk.
+// State space: "none" (block start) or one of the candidate models of the type (<= kMaxCand).
+// ---------------------------------------------------------------------------------------------------
+constexpr int kMaxCand = 16;
+
+__device__ __forceinline__ uint32_t pick_model(const uint32_t* __restrict__ sz, uint32_t n_cand, uint32_t cur) {
+    // first minimum of size + (k == cur ? 0 : 2)   (Iterator::min_by keeps the first; penalty model_chooser.rs:175-186)
+    uint32_t best = 0, best_len = 0xffffffffu;
+    for (uint32_t k = 0; k < n_cand; k++) {
+        uint32_t l = sz[k] + (k == cur ? 0u : 2u);
+        if (l < best_len) {
+            best_len = l;
+            best = k;
+        }
+    }
+    return best;
+}
+
+// sizes: [n_reads][n_models] (all models); cand[type][k] = column of candidate k of that type.
+// chosen[type][r] = candidate index (0..n_cand-1) ; switched[type][r] = 1 when a SwitchModel slice precedes r.
+__global__ void __launch_bounds__(32)
+switch_kernel(const uint32_t* __restrict__ sizes_all, uint32_t n_models, const uint32_t* __restrict__ cand,
+              const uint32_t* __restrict__ n_cand2, const uint32_t* __restrict__ has_sizes,
+              const uint32_t* __restrict__ block_first, uint32_t n_blocks, uint8_t* __restrict__ chosen,
+              uint8_t* __restrict__ switched, uint64_t n_reads) {
+    uint32_t b = blockIdx.x >> 1, type = blockIdx.x & 1;
+    if (b >= n_blocks) return;
+    uint32_t n_cand = n_cand2[type];
+    const uint32_t* sizes = has_sizes[type] ? sizes_all : nullptr;  // single candidate: nothing to compare
+    const uint32_t* cols = cand + type * kMaxCand;
+    uint32_t lane = threadIdx.x;
+    uint64_t r0 = block_first[b], r1 = block_first[b + 1];
+    uint64_t n = r1 - r0, per = (n + 31) / 32;
+    uint64_t c0 = r0 + lane * per, c1 = c0 + per;
+    if (c0 > r1) c0 = r1;
+    if (c1 > r1) c1 = r1;
+    uint8_t* ch = chosen + (size_t)type * n_reads;
+    uint8_t* sw = switched + (size_t)type * n_reads;
+    const uint32_t NONE = 0xffu;
+
+    uint32_t sz[kMaxCand];
+    // phase 1: out[s] = state after the chunk when entering with state s (s = n_cand means NONE)
+    uint32_t out[kMaxCand + 1];
+    for (uint32_t s = 0; s <= n_cand; s++) out[s] = s == n_cand ? NONE : s;
+    for (uint64_t r = c0; r < c1; r++) {
+        for (uint32_t k = 0; k < n_cand; k++) sz[k] = sizes ? sizes[r * n_models + cols[k]] : 0u;
+        // the result depends on cur only through "is cur == k"; evaluate once per distinct incoming state
+        uint32_t res[kMaxCand + 1];
+        for (uint32_t s = 0; s <= n_cand; s++) res[s] = pick_model(sz, n_cand, s == n_cand ? NONE : s);
+        for (uint32_t s = 0; s <= n_cand; s++) {
+            uint32_t cur = out[s];
+            out[s] = res[cur == NONE ? n_cand : cur];
+        }
+    }
+    // phase 2: lane l+1 enters with the state lane l leaves with (lane 0 enters with NONE)
+    uint32_t in_state = NONE;
+    for (uint32_t l = 0; l < 31; l++) {
+        uint32_t my_out = out[in_state == NONE ? n_cand : in_state];
+        uint32_t from_l = __shfl_sync(0xffffffffu, my_out, l);
+        if (lane == l + 1) in_state = from_l;
+    }
+    // phase 3: replay
+    uint32_t cur = in_state;
+    for (uint64_t r = c0; r < c1; r++) {
+        for (uint32_t k = 0; k < n_cand; k++) sz[k] = sizes ? sizes[r * n_models + cols[k]] : 0u;
+        uint32_t best = pick_model(sz, n_cand, cur);
+        ch[r] = (uint8_t)best;
+        sw[r] = best != cur;
+        cur = best;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// K4: two-state per-read rANS encode.  One thread per read, symbols walked last -> first.
+// Writes the payload right-aligned into the read's scratch slot [slot_end - pay_len, slot_end).
+// ---------------------------------------------------------------------------------------------------
+struct EncodeArgs {
+    const ModelDev* models;
+    const uint8_t* acids;
+    const uint8_t* quals;
+    const uint64_t* read_off;
+    uint64_t n_reads;
+    // model choice: either fixed (fast / single model per type) or per read
+    int32_t fixed_acid, fixed_q;        // indices into models[], used when chosen == nullptr
+    const uint8_t* chosen;              // [2][n_reads] candidate index per type, or nullptr
+    const int32_t* cand_model;          // [2][kMaxCand] candidate -> models[] index
+    uint8_t* scratch;                   // slot of read r ends at 4*read_off[r+1] + 8*(r+1)
+    uint32_t* pay_len;                  // [n_reads]
+    uint32_t* err;
+};
+
+__global__ void __launch_bounds__(128)
+encode_kernel(EncodeArgs A) {
+    uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= A.n_reads) return;
+    int32_t ia = A.fixed_acid, iq = A.fixed_q;
+    if (A.chosen) {
+        ia = A.cand_model[A.chosen[r]];
+        iq = A.cand_model[kMaxCand + A.chosen[A.n_reads + r]];
+    }
+    const ModelDev& ma = A.models[ia];
+    const ModelDev& mq = A.models[iq];
+    const long long off = (long long)A.read_off[r];
+    const uint32_t len = (uint32_t)(A.read_off[r + 1] - A.read_off[r]);
+    uint8_t* slot_end = A.scratch + 4ull * A.read_off[r + 1] + 8ull * (r + 1);
+
+    BackReader ra{A.acids, 0xffffffffu}, rq{A.quals, 0xffffffffu};
+    SymWindow w;
+    w.init();
+    bool bad = false;
+    long long front = (long long)len - 1;  // next position to pull into the window
+    auto pull = [&]() {
+        uint32_t a = 0, q = 0;
+        if (front >= 0) {
+            a = ra.get(off + front);
+            q = rq.get(off + front);
+            if (a > 4 || q > 93) {
+                bad = true;
+                a = a > 4 ? 0 : a;
+                q = q > 93 ? 0 : q;
+            }
+        }
+        front--;
+        w.shift_in(a, q);
+    };
+#pragma unroll 1
+    for (int t = 0; t < kHist; t++) pull();  // e_k = symbol at len-k
+
+    GenBack ga, gq;
+    ga.init(ma.spec, w, len);
+    gq.init(mq.spec, w, len);
+
+    BackWriter out;
+    out.init(slot_end);
+    uint32_t total = 0;
+    auto emit = [&](uint32_t b) {
+        out.push(b);
+        total++;
+    };
+    uint32_t x0 = kRansL, x1 = kRansL;  // state 0 = acids, state 1 = quality scores (compressor.rs:95-96)
+#pragma unroll 1
+    for (uint32_t i = len; i-- > 0;) {
+        pull();  // e_0 = symbol i
+        ga.step_back(ma.spec, w, len);
+        gq.step_back(mq.spec, w, len);
+        uint32_t a = w.acid(0), q = w.qual(0);
+        uint32_t row_a = ctx_row(ma, ga.spec(ma.spec));
+        uint32_t row_q = ctx_row(mq, gq.spec(mq.spec));
+        uint2 ea = __ldg(ma.enc + (size_t)row_a * kAcidSyms + a);
+        uint2 eq = __ldg(mq.enc + (size_t)row_q * kQSyms + q);
+        rans_put(x0, ea, emit);
+        rans_put(x1, eq, emit);
+    }
+    out.push_u32_le(x0);  // flush_all: state 0 then state 1
+    out.push_u32_le(x1);
+    total += 8;
+    out.finish();
+    A.pay_len[r] = total;
+    if (bad) atomicOr(A.err, 1u);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// exclusive scan over u64 (three launches; sizes of a few million elements)
+// ---------------------------------------------------------------------------------------------------
+constexpr int kScanBlock = 256;
+constexpr int kScanItems = 8;
+constexpr int kScanTile = kScanBlock * kScanItems;
+
+__device__ __forceinline__ unsigned long long block_exclusive_scan(unsigned long long v, unsigned long long* total,
+                                                                  unsigned long long* smem /*[kScanBlock/32]*/) {
+    uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    unsigned long long inc = v;
+    for (int d = 1; d < 32; d <<= 1) {
+        unsigned long long o = __shfl_up_sync(0xffffffffu, inc, d);
+        if (lane >= (uint32_t)d) inc += o;
+    }
+    if (lane == 31) smem[wid] = inc;
+    __syncthreads();
+    if (wid == 0) {
+        unsigned long long s = lane < kScanBlock / 32 ? smem[lane] : 0;
+        unsigned long long sinc = s;
+        for (int d = 1; d < 32; d <<= 1) {
+            unsigned long long o = __shfl_up_sync(0xffffffffu, sinc, d);
+            if (lane >= (uint32_t)d) sinc += o;
+        }
+        if (lane < kScanBlock / 32) smem[lane] = sinc - s;
+        if (lane == kScanBlock / 32 - 1) *total = sinc;
+    }
+    __syncthreads();
+    unsigned long long r = inc - v + smem[wid];
+    __syncthreads();
+    return r;
+}
+
+// per-read slice size -> per-tile sums
+template <class SizeFn>
+__global__ void __launch_bounds__(kScanBlock)
+scan_reduce_kernel(SizeFn fn, uint64_t n, unsigned long long* __restrict__ tile_sum) {
+    __shared__ unsigned long long smem[kScanBlock / 32];
+    __shared__ unsigned long long total;
+    uint64_t base = (uint64_t)blockIdx.x * kScanTile + (uint64_t)threadIdx.x * kScanItems;
+    unsigned long long v = 0;
+#pragma unroll
+    for (int k = 0; k < kScanItems; k++)
+        if (base + k < n) v += fn(base + k);
+    block_exclusive_scan(v, &total, smem);
+    if (threadIdx.x == 0) tile_sum[blockIdx.x] = total;
+}
+
+// single block: exclusive scan of tile sums in place; grand total to tile_sum[n_tiles]
+__global__ void __launch_bounds__(kScanBlock)
+scan_tiles_kernel(unsigned long long* __restrict__ tile_sum, uint32_t n_tiles) {
+    __shared__ unsigned long long smem[kScanBlock / 32];
+    __shared__ unsigned long long total;
+    unsigned long long carry = 0;
+    for (uint32_t base = 0; base < n_tiles; base += kScanBlock) {
+        uint32_t i = base + threadIdx.x;
+        unsigned long long v = i < n_tiles ? tile_sum[i] : 0;
+        unsigned long long ex = block_exclusive_scan(v, &total, smem);
+        if (i < n_tiles) tile_sum[i] = carry + ex;
+        carry += total;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) tile_sum[n_tiles] = carry;
+}
+
+template <class SizeFn>
+__global__ void __launch_bounds__(kScanBlock)
+scan_apply_kernel(SizeFn fn, uint64_t n, const unsigned long long* __restrict__ tile_sum,
+                  unsigned long long* __restrict__ out /*[n+1]*/) {
+    __shared__ unsigned long long smem[kScanBlock / 32];
+    __shared__ unsigned long long total;
+    uint64_t base = (uint64_t)blockIdx.x * kScanTile + (uint64_t)threadIdx.x * kScanItems;
+    unsigned long long item[kScanItems], v = 0;
+#pragma unroll
+    for (int k = 0; k < kScanItems; k++) {
+        item[k] = base + k < n ? fn(base + k) : 0;
+        v += item[k];
+    }
+    unsigned long long ex = block_exclusive_scan(v, &total, smem) + tile_sum[blockIdx.x];
+#pragma unroll
+    for (int k = 0; k < kScanItems; k++) {
+        if (base + k < n) out[base + k] = ex;
+        ex += item[k];
+    }
+    if (blockIdx.x == gridDim.x - 1 && threadIdx.x == 0) out[n] = tile_sum[gridDim.x];
+}
+
+// ---------------------------------------------------------------------------------------------------
+// compat-mode container layout (writer_block.rs:27-82, data.rs:35-84)
+//   block b: [u32be length][u32be crc][prefix_len[b] bytes reserved][fast: 01 00 01 01] then per read
+//            [01 idx]* [02 u32be len u32be seq_len payload]
+// slice_off[r] = offset of read r's first slice byte counted over all reads' slices only (scan of
+// slice sizes); block overheads are added per block through block_base[b].
+// ---------------------------------------------------------------------------------------------------
+struct SliceSize {
+    const uint32_t* pay_len;
+    const uint8_t* switched;  // [2][n_reads] or nullptr
+    uint64_t n_reads;
+    __device__ __forceinline__ unsigned long long operator()(uint64_t r) const {
+        unsigned long long s = 9ull + pay_len[r];
+        if (switched) s += 2u * switched[r] + 2u * switched[n_reads + r];
+        return s;
+    }
+};
+
+// one thread per block: block_base[b] = absolute offset of block b's header in `out`
+// (sequential over blocks inside one thread block of 1 warp; n_blocks is small -- hundreds)
+__global__ void __launch_bounds__(32)
+block_layout_kernel(const unsigned long long* __restrict__ slice_off, const uint32_t* __restrict__ block_first,
+                    uint32_t n_blocks, const uint32_t* __restrict__ prefix_len, int fast,
+                    unsigned long long* __restrict__ block_off /*[n_blocks+1]*/, uint8_t* __restrict__ out,
+                    uint64_t out_cap, unsigned long long* __restrict__ stats /*[8]*/) {
+    if (threadIdx.x != 0) return;
+    unsigned long long pos = 0;
+    for (uint32_t b = 0; b < n_blocks; b++) {
+        block_off[b] = pos;
+        unsigned long long body = slice_off[block_first[b + 1]] - slice_off[block_first[b]];
+        bool empty = block_first[b + 1] == block_first[b];
+        unsigned long long extra = (prefix_len ? prefix_len[b] : 0) + ((fast && !empty) ? 4 : 0);
+        unsigned long long length = body + extra;
+        if (pos + 8 <= out_cap) {
+            uint32_t l = (uint32_t)length;
+            out[pos + 0] = (uint8_t)(l >> 24);
+            out[pos + 1] = (uint8_t)(l >> 16);
+            out[pos + 2] = (uint8_t)(l >> 8);
+            out[pos + 3] = (uint8_t)l;
+            uint64_t f = pos + 8 + (prefix_len ? prefix_len[b] : 0);
+            if (fast && !empty && f + 4 <= out_cap) {  // compressor_block.rs:95-99
+                out[f + 0] = 1;
+                out[f + 1] = 0;
+                out[f + 2] = 1;
+                out[f + 3] = 1;
+            }
+        }
+        pos += 8 + length;
+    }
+    block_off[n_blocks] = pos;
+    stats[0] = pos;  // out_bytes / required_bytes
+}
+
+// one warp per read: slice headers + payload copy from the scratch slot to its final place
+struct AssembleArgs {
+    const uint64_t* read_off;
+    uint64_t n_reads;
+    const uint32_t* pay_len;
+    const uint8_t* scratch;
+    const unsigned long long* slice_off;
+    const unsigned long long* block_off;
+    const uint32_t* block_first;
+    const uint32_t* read_block;  // [n_reads] block of each read
+    const uint32_t* prefix_len;
+    int fast;
+    const uint8_t* chosen;    // [2][n_reads] or nullptr
+    const uint8_t* switched;  // [2][n_reads] or nullptr
+    const uint8_t* cand_index;  // [2][kMaxCand] candidate -> SwitchModel index (position in models[])
+    uint8_t* out;
+    uint64_t out_cap;
+};
+
+__global__ void __launch_bounds__(256)
+assemble_kernel(AssembleArgs A) {
+    uint64_t r = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    uint32_t lane = threadIdx.x & 31;
+    if (r >= A.n_reads) return;
+    uint32_t b = A.read_block[r];
+    bool empty = false;
+    unsigned long long dst = A.block_off[b] + 8 + (A.prefix_len ? A.prefix_len[b] : 0) + (A.fast && !empty ? 4 : 0) +
+                             (A.slice_off[r] - A.slice_off[A.block_first[b]]);
+    uint32_t plen = A.pay_len[r];
+    uint32_t len = (uint32_t)(A.read_off[r + 1] - A.read_off[r]);
+    uint32_t nsw = 0;
+    if (A.switched) nsw = A.switched[r] + A.switched[A.n_reads + r];
+    if (dst + 2ull * nsw + 9 + plen > A.out_cap) return;  // IDN_E_NOSPACE is reported by the host from stats
+    if (lane == 0) {
+        uint8_t* p = A.out + dst;
+        if (A.switched) {
+            if (A.switched[r]) {  // acid first (compressor_block.rs:103-104)
+                *p++ = 1;
+                *p++ = A.cand_index[A.chosen[r]];
+            }
+            if (A.switched[A.n_reads + r]) {
+                *p++ = 1;
+                *p++ = A.cand_index[kMaxCand + A.chosen[A.n_reads + r]];
+            }
+        }
+        p[0] = 2;
+        p[1] = (uint8_t)(plen >> 24);
+        p[2] = (uint8_t)(plen >> 16);
+        p[3] = (uint8_t)(plen >> 8);
+        p[4] = (uint8_t)plen;
+        p[5] = (uint8_t)(len >> 24);
+        p[6] = (uint8_t)(len >> 16);
+        p[7] = (uint8_t)(len >> 8);
+        p[8] = (uint8_t)len;
+    }
+    const uint8_t* src = A.scratch + 4ull * A.read_off[r + 1] + 8ull * (r + 1) - plen;
+    uint8_t* d = A.out + dst + 2ull * nsw + 9;
+    for (uint32_t i = lane; i < plen; i += 32) d[i] = src[i];
+}
+
+// read -> block map (one thread per block fills its range; blocks are large, so use a grid-stride loop)
+__global__ void read_block_kernel(const uint32_t* __restrict__ block_first, uint32_t n_blocks,
+                                  uint32_t* __restrict__ read_block) {
+    uint32_t b = blockIdx.x;
+    if (b >= n_blocks) return;
+    for (uint64_t r = block_first[b] + threadIdx.x; r < block_first[b + 1]; r += blockDim.x) read_block[r] = b;
+}
+
+// stats: payload bytes and switch counts (one pass, block reduce + atomics)
+__global__ void __launch_bounds__(256)
+stats_kernel(const uint32_t* __restrict__ pay_len, const uint8_t* __restrict__ switched, uint64_t n_reads,
+             unsigned long long* __restrict__ stats) {
+    unsigned long long pay = 0, sa = 0, sq = 0;
+    for (uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n_reads; r += (uint64_t)gridDim.x * blockDim.x) {
+        pay += pay_len[r];
+        if (switched) {
+            sa += switched[r];
+            sq += switched[n_reads + r];
+        }
+    }
+    for (int d = 16; d > 0; d >>= 1) {
+        pay += __shfl_down_sync(0xffffffffu, pay, d);
+        sa += __shfl_down_sync(0xffffffffu, sa, d);
+        sq += __shfl_down_sync(0xffffffffu, sq, d);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        atomicAdd(&stats[1], sa);
+        atomicAdd(&stats[2], sq);
+        atomicAdd(&stats[3], pay);
+    }
+}
+
+// stats[0] = bytes the container needs, [1] acid switches, [2] q switches, [3] payload bytes
+// -> idn_compress_stats {out_bytes, acid_switches, q_switches, payload_bytes, required_bytes}
+__global__ void finish_stats_kernel(const unsigned long long* __restrict__ stats, const uint32_t* __restrict__ err,
+                                    unsigned long long* __restrict__ out) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    out[0] = stats[0];
+    out[1] = stats[1];
+    out[2] = stats[2];
+    out[3] = stats[3];
+    out[4] = stats[0];
+    (void)err;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// K7: CRC-32 (IEEE, reflected 0xEDB88320) of name|acids|quals per read, combined per block.
+// Per-read partials are combined with the GF(2) "multiply by x^(8n) mod P" operator, which is associative,
+// so a block's CRC is a tree reduction over (crc, length) pairs.
+// ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t gf2_mul(uint32_t a, uint32_t b) {  // a*b mod P, reflected representation
+    uint32_t p = 0;
+#pragma unroll 4
+    for (int i = 0; i < 32; i++) {
+        p ^= (0u - (b >> 31)) & a;
+        a = (a >> 1) ^ ((0u - (a & 1u)) & 0xEDB88320u);
+        b <<= 1;
+    }
+    return p;
+}
+
+// x^(8n) mod P via the table xpow[k] = x^(8 * 2^k) mod P
+__device__ __forceinline__ uint32_t x8n_mod_p(unsigned long long n, const uint32_t* __restrict__ xpow) {
+    uint32_t r = 0x80000000u;  // the polynomial "1"
+    for (int k = 0; n; k++, n >>= 1)
+        if (n & 1) r = gf2_mul(r, xpow[k]);
+    return r;
+}
+
+struct CrcPair {
+    uint32_t crc;
+    unsigned long long len;
+};
+// crc of A|B from crc(A), crc(B), len(B)  (zlib crc32_combine)
+__device__ __forceinline__ CrcPair crc_concat(CrcPair a, CrcPair b, const uint32_t* __restrict__ xpow) {
+    if (b.len == 0) return a;
+    if (a.len == 0) return b;
+    CrcPair o;
+    o.crc = gf2_mul(x8n_mod_p(b.len, xpow), a.crc) ^ b.crc;
+    o.len = a.len + b.len;
+    return o;
+}
+
+__device__ __forceinline__ uint32_t crc_bytes(const uint8_t* __restrict__ base, unsigned long long off, uint32_t n,
+                                              const uint32_t* __restrict__ tab /*smem[256]*/) {
+    uint32_t c = 0xffffffffu;
+    FwdReader rd;
+    rd.init(base);
+    for (uint32_t i = 0; i < n; i++) c = tab[(c ^ rd.get(off + i)) & 0xffu] ^ (c >> 8);
+    return ~c;
+}
+
+// one thread per read: partial = crc(name|acids|quals), length = name_len + 2*len.
+// n_reads_dev / status (optional) serve the decode path, where the read count only exists on the device.
+__global__ void __launch_bounds__(128)
+crc_read_kernel(const uint8_t* __restrict__ acids, const uint8_t* __restrict__ quals,
+                const unsigned long long* __restrict__ read_off, const uint8_t* __restrict__ names,
+                const unsigned long long* __restrict__ name_off, uint64_t n_reads,
+                const unsigned long long* __restrict__ n_reads_dev, const int32_t* __restrict__ status,
+                const uint32_t* __restrict__ crc_tab, const uint32_t* __restrict__ xpow_g,
+                uint32_t* __restrict__ part_crc, unsigned long long* __restrict__ part_len) {
+    __shared__ uint32_t tab[256];
+    __shared__ uint32_t xpow[64];
+    if (status && status[0] != 0) return;
+    if (n_reads_dev) n_reads = *n_reads_dev;
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) tab[i] = crc_tab[i];
+    for (int i = threadIdx.x; i < 64; i += blockDim.x) xpow[i] = xpow_g[i];
+    __syncthreads();
+    uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n_reads) return;
+    unsigned long long off = read_off[r];
+    uint32_t len = (uint32_t)(read_off[r + 1] - off);
+    CrcPair p{0, 0};
+    if (names && name_off) {
+        uint32_t nl = (uint32_t)(name_off[r + 1] - name_off[r]);
+        p.crc = crc_bytes(names, name_off[r], nl, tab);
+        p.len = nl;
+    }
+    CrcPair a{crc_bytes(acids, off, len, tab), len};
+    CrcPair q{crc_bytes(quals, off, len, tab), len};
+    p = crc_concat(crc_concat(p, a, xpow), q, xpow);
+    part_crc[r] = p.crc;
+    part_len[r] = p.len;
+}
+
+// ordered tree reduction of the per-read partials of reads [r0, r1) by one 256-thread block; result in thread 0
+__device__ __forceinline__ uint32_t block_crc_reduce(const uint32_t* __restrict__ part_crc,
+                                                     const unsigned long long* __restrict__ part_len, uint64_t r0,
+                                                     uint64_t r1, const uint32_t* __restrict__ xpow, uint32_t* s_crc,
+                                                     unsigned long long* s_len) {
+    uint64_t n = r1 - r0, per = (n + blockDim.x - 1) / blockDim.x;
+    uint64_t c0 = r0 + threadIdx.x * per, c1 = c0 + per;
+    if (c0 > r1) c0 = r1;
+    if (c1 > r1) c1 = r1;
+    CrcPair acc{0, 0};
+    for (uint64_t r = c0; r < c1; r++) acc = crc_concat(acc, CrcPair{part_crc[r], part_len[r]}, xpow);
+    s_crc[threadIdx.x] = acc.crc;
+    s_len[threadIdx.x] = acc.len;
+    __syncthreads();
+    for (uint32_t d = 1; d < blockDim.x; d <<= 1) {  // ordered pairwise combine: [i] <- [i] ++ [i+d]
+        CrcPair m{0, 0};
+        bool act = (threadIdx.x % (2 * d)) == 0 && threadIdx.x + d < blockDim.x;
+        if (act)
+            m = crc_concat(CrcPair{s_crc[threadIdx.x], s_len[threadIdx.x]},
+                           CrcPair{s_crc[threadIdx.x + d], s_len[threadIdx.x + d]}, xpow);
+        __syncthreads();
+        if (act) {
+            s_crc[threadIdx.x] = m.crc;
+            s_len[threadIdx.x] = m.len;
+        }
+        __syncthreads();
+    }
+    return s_crc[0];
+}
+
+// one thread block per container block: CRC into block_crc[] and/or the block header in `out`
+__global__ void __launch_bounds__(256)
+crc_block_kernel(const uint32_t* __restrict__ part_crc, const unsigned long long* __restrict__ part_len,
+                 const uint32_t* __restrict__ block_first, uint32_t n_blocks, const uint32_t* __restrict__ xpow_g,
+                 uint32_t* __restrict__ block_crc, uint8_t* __restrict__ out,
+                 const unsigned long long* __restrict__ block_off, uint64_t out_cap) {
+    __shared__ uint32_t xpow[64];
+    __shared__ uint32_t s_crc[256];
+    __shared__ unsigned long long s_len[256];
+    for (int i = threadIdx.x; i < 64; i += blockDim.x) xpow[i] = xpow_g[i];
+    __syncthreads();
+    uint32_t b = blockIdx.x;
+    if (b >= n_blocks) return;
+    uint32_t c = block_crc_reduce(part_crc, part_len, block_first[b], block_first[b + 1], xpow, s_crc, s_len);
+    if (threadIdx.x == 0) {
+        if (block_crc) block_crc[b] = c;
+        if (out && block_off && block_off[b] + 8 <= out_cap) {
+            uint8_t* p = out + block_off[b] + 4;
+            p[0] = (uint8_t)(c >> 24);
+            p[1] = (uint8_t)(c >> 16);
+            p[2] = (uint8_t)(c >> 8);
+            p[3] = (uint8_t)c;
+        }
+    }
+}
+
+// decode side: compare with the block header value (IdnBlockDecompressor::check_checksum, decompressor_block.rs:131-144)
+__global__ void __launch_bounds__(256)
+crc_verify_kernel(const uint32_t* __restrict__ part_crc, const unsigned long long* __restrict__ part_len,
+                  const uint32_t* __restrict__ block_first, uint32_t n_blocks, const uint32_t* __restrict__ xpow_g,
+                  const uint32_t* __restrict__ expect, int32_t* __restrict__ status) {
+    __shared__ uint32_t xpow[64];
+    __shared__ uint32_t s_crc[256];
+    __shared__ unsigned long long s_len[256];
+    if (status[0] != 0 && status[0] != 6) return;
+    for (int i = threadIdx.x; i < 64; i += blockDim.x) xpow[i] = xpow_g[i];
+    __syncthreads();
+    uint32_t b = blockIdx.x;
+    if (b >= n_blocks) return;
+    uint32_t c = block_crc_reduce(part_crc, part_len, block_first[b], block_first[b + 1], xpow, s_crc, s_len);
+    if (threadIdx.x == 0 && c != expect[b]) {
+        atomicCAS(&status[0], 0, 6);  // IDN_E_CHECKSUM
+        atomicMin(&status[3], (int32_t)b);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// container slice walk (decode side).  The chain "header -> next header" is serial inside a block, so one
+// thread walks one block; blocks run in parallel.  Pass 1 counts reads/symbols per block, pass 2 (after a
+// scan) fills the per-read index.
+// ---------------------------------------------------------------------------------------------------
+struct WalkResult {
+    uint32_t n_reads;
+    unsigned long long n_symbols;
+    int32_t status;  // IDN_* code
+};
+
+__device__ __forceinline__ uint32_t load_u32be(const uint8_t* p) {
+    return ((uint32_t)p[0] << 24) | ((uint32_t)p[1] << 16) | ((uint32_t)p[2] << 8) | p[3];
+}
+
+template <bool kFill>
+__device__ __forceinline__ WalkResult walk_block(const uint8_t* __restrict__ p, unsigned long long n,
+                                                 const ModelDev* __restrict__ models, const int32_t* __restrict__ model_ids,
+                                                 uint32_t n_models, unsigned long long blk_base, uint64_t r_base,
+                                                 unsigned long long sym_base, unsigned long long* __restrict__ pay_off,
+                                                 uint32_t* __restrict__ pay_len, uint32_t* __restrict__ seq_len,
+                                                 unsigned long long* __restrict__ out_off, uint8_t* __restrict__ am,
+                                                 uint8_t* __restrict__ qm) {
+    WalkResult w{0, 0, 0};
+    unsigned long long pos = 0;
+    int cur_a = -1, cur_q = -1;
+    while (pos < n) {
+        uint8_t kind = p[pos++];
+        if (kind == 0) {  // Identifiers: skipped on the device (names stay on the host)
+            if (pos + 5 > n) { w.status = 3; break; }
+            uint32_t len = load_u32be(p + pos);
+            pos += 5;
+            if (pos + len > n) { w.status = 3; break; }
+            pos += len;
+        } else if (kind == 1) {  // SwitchModel  decompressor_block.rs:194-214
+            if (pos + 1 > n) { w.status = 3; break; }
+            uint32_t idx = p[pos++];
+            if (idx >= n_models) { w.status = 7; break; }
+            if (models[model_ids[idx]].type == 0) cur_a = (int)idx; else cur_q = (int)idx;
+        } else if (kind == 2) {  // Sequence  :216-239
+            if (pos + 8 > n) { w.status = 3; break; }
+            uint32_t len = load_u32be(p + pos), sl = load_u32be(p + pos + 4);
+            pos += 8;
+            if (pos + len > n || len < 8) { w.status = 3; break; }
+            if (cur_a < 0 || cur_q < 0) { w.status = 8; break; }
+            if (kFill) {
+                uint64_t r = r_base + w.n_reads;
+                pay_off[r] = blk_base + pos;
+                pay_len[r] = len;
+                seq_len[r] = sl;
+                out_off[r] = sym_base + w.n_symbols;
+                am[r] = (uint8_t)cur_a;
+                qm[r] = (uint8_t)cur_q;
+            }
+            w.n_reads++;
+            w.n_symbols += sl;
+            pos += len;
+        } else {
+            w.status = 3;
+            break;
+        }
+    }
+    return w;
+}
+
+__global__ void __launch_bounds__(32)
+index_count_kernel(const uint8_t* __restrict__ blocks, const unsigned long long* __restrict__ block_off, uint32_t n_blocks,
+                   const ModelDev* __restrict__ models, const int32_t* __restrict__ model_ids, uint32_t n_models,
+                   unsigned long long* __restrict__ blk_reads, unsigned long long* __restrict__ blk_syms,
+                   int32_t* __restrict__ status /*[2]: code, block*/) {
+    uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= n_blocks) return;
+    WalkResult w = walk_block<false>(blocks + block_off[b], block_off[b + 1] - block_off[b], models, model_ids, n_models,
+                                     0, 0, 0, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr);
+    blk_reads[b] = w.n_reads;
+    blk_syms[b] = w.n_symbols;
+    if (w.status != 0) {
+        int old = atomicCAS(&status[0], 0, w.status);
+        if (old == 0) status[1] = (int32_t)b;
+    }
+}
+
+__global__ void __launch_bounds__(32)
+index_fill_kernel(const uint8_t* __restrict__ blocks, const unsigned long long* __restrict__ block_off, uint32_t n_blocks,
+                  const ModelDev* __restrict__ models, const int32_t* __restrict__ model_ids, uint32_t n_models,
+                  const unsigned long long* __restrict__ blk_read_base, const unsigned long long* __restrict__ blk_sym_base,
+                  unsigned long long* __restrict__ pay_off, uint32_t* __restrict__ pay_len, uint32_t* __restrict__ seq_len,
+                  unsigned long long* __restrict__ out_off, uint8_t* __restrict__ am, uint8_t* __restrict__ qm,
+                  uint32_t* __restrict__ block_first, const int32_t* __restrict__ status) {
+    uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b > n_blocks || status[0] != 0) return;
+    if (b == n_blocks) {
+        if (block_first) block_first[b] = (uint32_t)blk_read_base[b];
+        out_off[blk_read_base[b]] = blk_sym_base[b];
+        return;
+    }
+    if (block_first) block_first[b] = (uint32_t)blk_read_base[b];
+    walk_block<true>(blocks + block_off[b], block_off[b + 1] - block_off[b], models, model_ids, n_models, block_off[b],
+                     blk_read_base[b], blk_sym_base[b], pay_off, pay_len, seq_len, out_off, am, qm);
+}
+
+// totals against the caller's capacities; on failure every later kernel of the call is a no-op
+__global__ void index_check_kernel(const unsigned long long* __restrict__ blk_reads, const unsigned long long* __restrict__ blk_syms,
+                                   uint32_t n_blocks, uint64_t reads_cap, uint64_t syms_cap, int32_t* __restrict__ status) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    status[3] = 0x7fffffff;  // first block with a checksum mismatch
+    if (status[0] != 0) return;
+    if (blk_reads[n_blocks] > reads_cap || blk_syms[n_blocks] > syms_cap) {
+        status[0] = 11;  // IDN_E_NOSPACE
+        status[1] = -1;
+        status[2] = (int32_t)(blk_reads[n_blocks] > 0x7fffffffull ? 0x7fffffff : blk_reads[n_blocks]);
+    }
+}
+
+struct IdentU64 {
+    const unsigned long long* v;
+    __device__ __forceinline__ unsigned long long operator()(uint64_t i) const { return v[i]; }
+};
+
+// ---------------------------------------------------------------------------------------------------
+// K5: two-state per-read rANS decode.  One thread per read.
+// status bits: 1 = payload exhausted / malformed, 2 = final states or length mismatch (diagnostic only)
+// ---------------------------------------------------------------------------------------------------
+struct DecodeArgs {
+    const ModelDev* models;
+    const int32_t* model_ids;  // container index -> models[]
+    const uint8_t* payload;
+    const unsigned long long* pay_off;
+    const uint32_t* pay_len;
+    const uint32_t* seq_len;
+    const unsigned long long* out_off;
+    const uint8_t* acid_model;
+    const uint8_t* q_model;
+    uint64_t n_reads;
+    const unsigned long long* n_reads_dev;  // when set, overrides n_reads (count produced by the index kernels)
+    const int32_t* status;                  // when set and != 0 the kernel does nothing
+    uint8_t* acids_out;
+    uint8_t* quals_out;
+    uint32_t* read_status;  // optional
+    uint32_t* err;
+};
+
+__global__ void __launch_bounds__(128)
+decode_kernel(DecodeArgs A) {
+    uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (A.status && A.status[0] != 0) return;
+    if (r >= (A.n_reads_dev ? *A.n_reads_dev : A.n_reads)) return;
+    const ModelDev& ma = A.models[A.model_ids[A.acid_model[r]]];
+    const ModelDev& mq = A.models[A.model_ids[A.q_model[r]]];
+    const unsigned long long poff = A.pay_off[r];
+    const uint32_t plen = A.pay_len[r], len = A.seq_len[r];
+    FwdReader in;
+    in.init(A.payload);
+    uint32_t cur = 0, st = 0;
+    auto next = [&]() -> uint32_t {
+        if (cur >= plen) {
+            st |= 1;
+            return 0;
+        }
+        return in.get(poff + cur++);
+    };
+    // RansDecInit x2: decoder state 0 = quality scores, state 1 = acids (compressor.rs:181-182)
+    uint32_t xq = next();
+    xq |= next() << 8;
+    xq |= next() << 16;
+    xq |= next() << 24;
+    uint32_t xa = next();
+    xa |= next() << 8;
+    xa |= next() << 16;
+    xa |= next() << 24;
+
+    GenFwd ga, gq;
+    ga.init();
+    gq.init();
+    FwdWriter oa, oq;
+    oa.init(A.acids_out + A.out_off[r]);
+    oq.init(A.quals_out + A.out_off[r]);
+#pragma unroll 1
+    for (uint32_t i = 0; i < len && !(st & 1); i++) {
+        uint32_t row_a = ctx_row(ma, ga.spec(ma.spec));
+        uint32_t row_q = ctx_row(mq, gq.spec(mq.spec));
+        uint32_t slot_q = xq & kSlotMask, slot_a = xa & kSlotMask;
+        uint32_t start, freq;
+        uint32_t sq = q_find(mq.dec + (size_t)row_q * kQRowStride, slot_q, start, freq);
+        xq = freq * (xq >> kScaleBits) + slot_q - start;  // RansDecAdvanceStep
+        uint2 pk = __ldg(reinterpret_cast<const uint2*>(ma.dec) + row_a);
+        uint32_t sa = acid_find(pk, slot_a, start, freq);
+        xa = freq * (xa >> kScaleBits) + slot_a - start;
+        while (xq < kRansL && !(st & 1)) xq = (xq << 8) | next();  // renorm_all: state 0 then state 1
+        while (xa < kRansL && !(st & 1)) xa = (xa << 8) | next();
+        oa.push(sa);
+        oq.push(sq);
+        ga.update(ma.spec, sa, sq, len);
+        gq.update(mq.spec, sa, sq, len);
+    }
+    oa.finish();
+    oq.finish();
+    if (!(st & 1) && (xq != kRansL || xa != kRansL || cur != plen)) st |= 2;
+    if (A.read_status) A.read_status[r] = st;
+    if (st & 1) atomicOr(A.err, 1u);
+}
+
+// final status word of a device-side decompress call + copy of the read offsets
+__global__ void __launch_bounds__(256)
+finish_decode_kernel(const int32_t* __restrict__ status, const uint32_t* __restrict__ err,
+                     const unsigned long long* __restrict__ n_reads_total, const unsigned long long* __restrict__ n_syms_total,
+                     const unsigned long long* __restrict__ out_off, unsigned long long* __restrict__ read_off_out,
+                     uint64_t reads_cap, int32_t* __restrict__ status_dev) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int32_t code = status[0];
+    uint64_t R = *n_reads_total;
+    if (i == 0) {
+        int32_t blk = status[1];
+        if (code == 0 && (*err & 1u)) code = 3;  // a payload ran out: IDN_E_SERIALIZE
+        if (code == 6) blk = status[3];
+        status_dev[0] = code;
+        status_dev[1] = blk;
+        status_dev[2] = code == 11 ? status[2] : (int32_t)(R > 0x7fffffffull ? 0x7fffffff : R);
+        status_dev[3] = (int32_t)(*n_syms_total & 0x7fffffffull);
+    }
+    if (code == 0 && read_off_out && i <= R && i <= reads_cap) read_off_out[i] = out_off[i];
+}
+
+}  // namespace idn

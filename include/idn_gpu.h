@@ -1,0 +1,193 @@
+/*
+ * idn_gpu.h -- C-ABI of libidn_gpu.so: the B200 (sm_100a) implementation of idencomp's rANS hot path.
+ *
+ * This is the drop-in boundary.  The reference has no FFI today; the seam a
+ * maintainer would bind is "one call per batch of blocks" replacing
+ *     IdnBlockCompressor::process      idencomp/src/idn/compressor_block.rs:76-120
+ *     IdnBlockDecompressor::process    idencomp/src/idn/decompressor_block.rs:77-129
+ *     ModelProvider::preprocess_*      idencomp/src/idn/model_provider.rs:154-173
+ *     ModelTester::compute_size        idencomp/src/idn/model_chooser.rs:215-243
+ * INTEGRATION.md shows the Rust `extern "C"` block + build.rs a maintainer would add.
+ *
+ * Conventions: every entry point returns an int32 status (0 = IDN_OK); plain pointers and sizes only;
+ * the caller owns every buffer it passes; the library owns device memory inside `idn_gpu_ctx`; no pointer
+ * escapes a call.  A ctx is single-owner (one per device per host thread); model handles are immutable
+ * after upload.  Functions ending in `_dev` take DEVICE pointers and enqueue on `stream` (a cudaStream_t
+ * passed as void*; NULL = the legacy default stream) without synchronising; the others take HOST pointers
+ * (pinned memory recommended), do the H2D/D2H copies themselves and return when the result is in the
+ * caller's buffers.  There is no CPU fallback: every call fails with IDN_E_CUDA when no device is usable.
+ */
+#ifndef IDN_GPU_H
+#define IDN_GPU_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define IDN_GPU_ABI_VERSION 1
+
+/* Status codes: 1..9 map 1:1 onto the reference's error enums
+ * (IdnCompressorError idn/compressor.rs:22-33, IdnDecompressorError idn/decompressor.rs:25-48). */
+enum {
+    IDN_OK = 0,
+    IDN_E_INVALID_STATE = 1,
+    IDN_E_IO = 2,
+    IDN_E_SERIALIZE = 3,        /* malformed container / slice */
+    IDN_E_SEQUENCE_TOO_LONG = 4,
+    IDN_E_INVALID_VERSION = 5,
+    IDN_E_CHECKSUM = 6,         /* BlockChecksumMismatch */
+    IDN_E_INVALID_MODEL_INDEX = 7,
+    IDN_E_NO_ACTIVE_MODEL = 8,
+    IDN_E_UNKNOWN_MODEL = 9,
+    IDN_E_UNSUPPORTED = 10,     /* e.g. model with > 65535 contexts (reference limit 65536, :209-219) */
+    IDN_E_NOSPACE = 11,         /* output capacity too small; required size is reported */
+    IDN_E_INVALID_ARG = 12,
+    IDN_E_INVALID_SYMBOL = 13,  /* acid > 4 or quality score > 93 in the input */
+    IDN_E_CUDA = 100
+};
+
+enum { IDN_MODEL_ACID = 0, IDN_MODEL_QSCORE = 1 };   /* ModelType, model.rs:56-61 */
+enum { IDN_SPEC_GENERIC = 0, IDN_SPEC_LIGHT = 1 };   /* context_spec.rs:218,421 ("dummy" = generic 0,0,0) */
+enum { IDN_MODE_COMPAT = 1, IDN_MODE_NATIVE = 2 };   /* container version byte (idn/data.rs:3-8) */
+
+#define IDN_SCALE_BITS 14   /* idn/model_provider.rs:407 */
+#define IDN_ACID_SYMS 5
+#define IDN_Q_SYMS 94
+#define IDN_MAX_MODELS 255  /* SwitchModel index is a u8 (idn/data.rs:72-76) */
+
+typedef struct idn_gpu_ctx idn_gpu_ctx;
+typedef int32_t idn_model_t; /* handle, >= 0 */
+
+/* ---- lifecycle ------------------------------------------------------------------------------------- */
+int32_t idn_gpu_abi_version(void);
+int32_t idn_gpu_device_count(void);
+int32_t idn_gpu_create(int32_t device, idn_gpu_ctx **ctx);
+void idn_gpu_destroy(idn_gpu_ctx *ctx);
+const char *idn_gpu_last_error(const idn_gpu_ctx *ctx);
+/* number of kernel launches this ctx has issued since creation (bench.py's gpu_launches) */
+uint64_t idn_gpu_launch_count(const idn_gpu_ctx *ctx);
+
+/* ---- models: replaces RansEncModel/RansDecModel::from_model (sequence_compressor.rs:21-48,175-201) --
+ * `cum`: integer cumulative frequencies, row-major [(n_ctx+1)][nsym+1] u16, row 0 = the uniform dummy
+ * context (sequence_compressor.rs:26-29), last column = 1<<14; produced on the host by the bit-exact
+ * f32 quantiser (context.rs:346-394).  `spec_keys[i]` -> 0-based context index `spec_ctx[i]`; specs not
+ * listed map to the dummy context (sequence_compressor.rs:37-40). */
+int32_t idn_gpu_model_upload(idn_gpu_ctx *ctx, int32_t model_type, int32_t spec_kind, int32_t acid_order,
+                             int32_t q_order, int32_t pos_bits, int32_t q_max, uint32_t n_ctx,
+                             const uint16_t *cum, const uint32_t *spec_keys, const uint32_t *spec_ctx,
+                             uint64_t n_specs, idn_model_t *handle);
+int32_t idn_gpu_model_release(idn_gpu_ctx *ctx, idn_model_t handle);
+
+/* ---- batches ----------------------------------------------------------------------------------------
+ * SoA batch of reads grouped into blocks (block forming stays on the host: idn/compressor.rs:517-559).
+ * acids: 0..4 (N,A,C,T,G  sequence.rs:401-413); quals: 0..93.  Block b holds reads
+ * [block_first_read[b], block_first_read[b+1]).  `names`/`name_off` are optional (NULL = empty names);
+ * when given, the block CRC covers name bytes as the reference's does (sequence.rs:381-394). */
+typedef struct {
+    uint64_t n_reads;
+    uint64_t n_symbols;               /* = read_off[n_reads] */
+    uint32_t n_blocks;
+    const uint8_t *acids;             /* [n_symbols] */
+    const uint8_t *quals;             /* [n_symbols] */
+    const uint64_t *read_off;         /* [n_reads+1] */
+    const uint32_t *block_first_read; /* [n_blocks+1] */
+    const uint8_t *names;             /* optional */
+    const uint64_t *name_off;         /* optional [n_reads+1] */
+} idn_batch;
+
+typedef struct {
+    uint64_t out_bytes;         /* bytes written to `out` */
+    uint64_t acid_switches;     /* SwitchModel slices emitted per type */
+    uint64_t q_switches;
+    uint64_t payload_bytes;     /* sum of rANS payload lengths */
+    uint64_t required_bytes;    /* set on IDN_E_NOSPACE */
+} idn_compress_stats;
+
+/* a6: ModelTester::compute_size for every (read, model): sizes[r * n_models + m] = byte length of a
+ * forward single-state rANS encode of read r under models[m] (+4 flush bytes). */
+int32_t idn_gpu_score(idn_gpu_ctx *ctx, const idn_batch *batch, const idn_model_t *models, uint32_t n_models,
+                      uint32_t *sizes);
+int32_t idn_gpu_score_dev(idn_gpu_ctx *ctx, const idn_batch *batch, const idn_model_t *models,
+                          uint32_t n_models, uint32_t *sizes, void *stream);
+
+/* a7+a8+a10: compress a batch of blocks.
+ * `models[k]` is the retained provider list in container order (k = SwitchModel index; acid ids first,
+ * then q-score ids: compressor_initializer.rs:57-65).  fast != 0 reproduces `--fast`
+ * (compressor_block.rs:95-106: exactly 2 models, switches 0 and 1 at the start of each block).
+ * prefix_len[b] (optional, NULL = 0) reserves room right after the block header for the identifiers
+ * slice, which the host compresses and copies in (names stay on the host as in the reference).
+ * Output, for each block b at out[block_off[b] .. block_off[b+1]):
+ *     u32be length | u32be crc32 | prefix_len[b] reserved bytes | SwitchModel / Sequence slices
+ * i.e. exactly the bytes IdnBlockCompressor::write emits (compressor_block.rs:122-128,
+ * writer_block.rs:27-40) once the host has filled the reserved bytes.  block_crc[b] (optional) also
+ * receives the CRC.  With IDN_MODE_NATIVE the slices use the multi-lane layout of DESIGN.md. */
+int32_t idn_gpu_compress_blocks(idn_gpu_ctx *ctx, const idn_batch *batch, int32_t mode,
+                                const idn_model_t *models, uint32_t n_models, int32_t fast,
+                                const uint32_t *prefix_len, uint8_t *out, uint64_t out_cap,
+                                uint64_t *block_off, uint32_t *block_crc, idn_compress_stats *stats);
+int32_t idn_gpu_compress_blocks_dev(idn_gpu_ctx *ctx, const idn_batch *batch, int32_t mode,
+                                    const idn_model_t *models, uint32_t n_models, int32_t fast,
+                                    const uint32_t *prefix_len, uint8_t *out, uint64_t out_cap,
+                                    uint64_t *block_off, uint32_t *block_crc, idn_compress_stats *stats_dev,
+                                    void *stream);
+/* upper bound of the output size of idn_gpu_compress_blocks for a batch shape */
+uint64_t idn_gpu_compress_bound(uint64_t n_reads, uint64_t n_symbols, uint32_t n_blocks, uint64_t prefix_total);
+
+/* a9+a11: decompress a batch of blocks given as container bytes.
+ * `blocks` holds the block payloads back to back (WITHOUT the 8-byte block headers); block b is
+ * blocks[block_off[b] .. block_off[b+1]) and block_crc[b] its header checksum.  The library walks the
+ * slices (Identifiers slices are skipped: names stay on the host), tracks the active models per type
+ * (decompressor_block.rs:194-214), decodes every Sequence slice and verifies the CRC of the symbols
+ * (names, if any, are passed per read through `names`/`name_off` after the host inflated them; NULL =
+ * the block has no names).
+ * Two-step use: idn_gpu_index_blocks returns the read count / symbol count so the caller can size the
+ * outputs, then idn_gpu_decompress_blocks fills them. */
+typedef struct {
+    uint64_t n_reads;
+    uint64_t n_symbols;
+} idn_block_index_totals;
+
+int32_t idn_gpu_index_blocks(idn_gpu_ctx *ctx, const uint8_t *blocks, const uint64_t *block_off,
+                             uint32_t n_blocks, const idn_model_t *models, uint32_t n_models,
+                             idn_block_index_totals *totals, uint32_t *block_first_read /*[n_blocks+1], optional*/);
+int32_t idn_gpu_decompress_blocks(idn_gpu_ctx *ctx, const uint8_t *blocks, const uint64_t *block_off,
+                                  const uint32_t *block_crc, uint32_t n_blocks, int32_t mode,
+                                  const idn_model_t *models, uint32_t n_models, const uint8_t *names,
+                                  const uint64_t *name_off, uint8_t *acids_out, uint8_t *quals_out,
+                                  uint64_t *read_off_out /*[n_reads+1]*/, uint64_t out_reads_cap,
+                                  uint64_t out_symbols_cap, int32_t *bad_block /* first failing block or -1 */);
+int32_t idn_gpu_decompress_blocks_dev(idn_gpu_ctx *ctx, const uint8_t *blocks, const uint64_t *block_off,
+                                      const uint32_t *block_crc, uint32_t n_blocks, uint64_t blocks_bytes,
+                                      int32_t mode, const idn_model_t *models, uint32_t n_models,
+                                      uint8_t *acids_out, uint8_t *quals_out, uint64_t *read_off_out,
+                                      uint64_t out_reads_cap, uint64_t out_symbols_cap,
+                                      int32_t *status_dev /* [4]: code, bad block, n_reads, n_symbols(lo) */,
+                                      void *stream);
+
+/* per-read form (host already holds the slice index): decode read r from payload[pay_off[r] ..
+ * pay_off[r]+pay_len[r]) into acids_out/quals_out at out_off[r]; model index per read into models[]. */
+typedef struct {
+    uint64_t n_reads;
+    const uint64_t *pay_off;
+    const uint32_t *pay_len;
+    const uint32_t *seq_len;
+    const uint64_t *out_off;   /* [n_reads+1] exclusive scan of seq_len */
+    const uint8_t *acid_model; /* index into models[] */
+    const uint8_t *q_model;
+} idn_read_index;
+
+int32_t idn_gpu_decompress_reads(idn_gpu_ctx *ctx, const uint8_t *payload, uint64_t payload_bytes,
+                                 const idn_read_index *index, const idn_model_t *models, uint32_t n_models,
+                                 uint8_t *acids_out, uint8_t *quals_out, uint32_t *read_status /* optional */);
+
+/* IEEE CRC-32 of the per-read stream name|acids|quals for each block (writer_block.rs:64,
+ * sequence.rs:381-394), computed on the device. */
+int32_t idn_gpu_block_crc(idn_gpu_ctx *ctx, const idn_batch *batch, uint32_t *block_crc);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* IDN_GPU_H */

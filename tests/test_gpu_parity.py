@@ -1,0 +1,304 @@
+"""Parity tests proper: the CUDA path, called through the C-ABI (libidn_gpu.so), against the CPU oracle and the
+reference's golden container.  Everything here is integer / byte work, so the bar is BIT-EXACT.
+
+Run on the B200 box: python -m pytest tests -m gpu
+"""
+import zlib
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN
+from gpu_util import blocks_of, upload
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def gctx():
+    from idencomp_b200 import capi
+    ctx = capi.Context(0)
+    yield ctx
+    ctx.close()
+
+
+@pytest.fixture(scope="module")
+def toy_handles(gctx, O, toy_models):
+    return [upload(gctx, O, m) for m in toy_models]
+
+
+@pytest.fixture(scope="module")
+def bundled(gctx, O, model_data):
+    """name -> (oracle Model, device handle) for every bundled model."""
+    out = {}
+    for name, md in model_data.items():
+        m = O.Model(md)
+        out[name] = (m, upload(gctx, O, m))
+    return out
+
+
+def oracle_blocks(O, models, reads, block_first, *, fast, names):
+    """Expected bytes per block: slices only (compressor_block.rs:83-120) + crc."""
+    out = []
+    for b in range(len(block_first) - 1):
+        data, crc, stats = O.compress_block(models, reads, int(block_first[b]), int(block_first[b + 1] - block_first[b]),
+                                            include_identifiers=names, fast=fast)
+        out.append((data, crc, stats))
+    return out
+
+
+def check_container(out, block_off, crc, expect, prefix=None):
+    for b, (data, ecrc, _) in enumerate(expect):
+        lo, hi = int(block_off[b]), int(block_off[b + 1])
+        blk = out[lo:hi].tobytes()
+        plen = 0 if prefix is None else int(prefix[b])
+        assert int.from_bytes(blk[0:4], "big") == len(blk) - 8 == len(data), f"block {b} length"
+        assert int.from_bytes(blk[4:8], "big") == ecrc == int(crc[b]), f"block {b} crc"
+        assert blk[8 + plen:] == data[plen:], f"block {b} slices differ"
+
+
+# ---- the golden container (idencomp/tests/simple_ctx.rs:19-32), encode side --------------------------------------
+def test_encode_1m_matches_golden_container(gctx, toy_handles, reads_1m):
+    golden = (GOLDEN / "1M.idn").read_bytes()
+    block = golden[76:76 + 8 + 538705]  # header + the one data block
+    names_slice = block[8:8 + 37]
+    out, block_off, crc, stats = gctx.compress_blocks(reads_1m.read_off, reads_1m.acids, reads_1m.quals, [0, 1],
+                                                      toy_handles, prefix_len=[37], name_off=reads_1m.name_off,
+                                                      names=reads_1m.names)
+    out = bytearray(out.tobytes())
+    out[8:8 + 37] = names_slice  # names are compressed on the host (as in the reference); the device reserves room
+    assert bytes(out) == block
+    assert stats["payload_bytes"] == 538655 and stats["acid_switches"] == 1 and stats["q_switches"] == 1
+    assert int(crc[0]) == 0xC1F69A94
+
+
+def test_decode_1m_golden_container(gctx, toy_handles, reads_1m):
+    golden = (GOLDEN / "1M.idn").read_bytes()
+    payload = np.frombuffer(golden[84:84 + 538705], dtype=np.uint8)
+    crc = int.from_bytes(golden[80:84], "big")
+    ro, a, q = gctx.decompress_blocks(payload, [0, len(payload)], [crc], toy_handles, name_off=reads_1m.name_off,
+                                      names=reads_1m.names)
+    assert ro.tolist() == [0, 500000]
+    assert np.array_equal(a, reads_1m.acids) and np.array_equal(q, reads_1m.quals)
+
+
+def test_score_1m(gctx, toy_handles, reads_1m):
+    sizes = gctx.score((reads_1m.read_off, reads_1m.acids, reads_1m.quals), toy_handles)
+    assert sizes.tolist() == [[188868, 349787]]
+
+
+# ---- 1k reads against the oracle, several block shapes ------------------------------------------------------------
+@pytest.mark.parametrize("block_len", [4 * 1024 * 1024, 10000, 200])
+@pytest.mark.parametrize("fast", [False, True])
+def test_encode_1k_vs_oracle(gctx, O, toy_models, toy_handles, reads_1k, block_len, fast):
+    bf = blocks_of(reads_1k, block_len)
+    expect = oracle_blocks(O, toy_models, reads_1k, bf, fast=fast, names=False)
+    out, block_off, crc, stats = gctx.compress_blocks(reads_1k.read_off, reads_1k.acids, reads_1k.quals, bf, toy_handles,
+                                                      fast=fast)
+    check_container(out, block_off, crc, expect)
+    assert stats["out_bytes"] == int(block_off[-1]) == sum(len(d) + 8 for d, _, _ in expect)
+
+
+def test_encode_1k_with_names_and_prefix(gctx, O, toy_models, toy_handles, reads_1k):
+    bf = blocks_of(reads_1k, 5000)
+    expect = oracle_blocks(O, toy_models, reads_1k, bf, fast=False, names=True)
+    prefix = [6 + int.from_bytes(d[1:5], "big") for d, _, _ in expect]  # Identifiers slice: 00 | u32 len | u8 | data
+    out, block_off, crc, _ = gctx.compress_blocks(reads_1k.read_off, reads_1k.acids, reads_1k.quals, bf, toy_handles,
+                                                  prefix_len=prefix, name_off=reads_1k.name_off, names=reads_1k.names)
+    check_container(out, block_off, crc, expect, prefix)
+
+
+def _decode_all(gctx, O, models, handles, reads, bf, fast):
+    """compress on the device, decompress on the device, compare with the input; also feed the device output to the
+    oracle decoder and the oracle output to the device decoder."""
+    out, block_off, crc, _ = gctx.compress_blocks(reads.read_off, reads.acids, reads.quals, bf, handles, fast=fast)
+    nb = len(bf) - 1
+    payload = np.concatenate([out[int(block_off[b]) + 8:int(block_off[b + 1])] for b in range(nb)]) if nb else out[:0]
+    sizes = [int(block_off[b + 1] - block_off[b]) - 8 for b in range(nb)]
+    poff = np.concatenate([[0], np.cumsum(sizes)]).astype(np.uint64)
+    ro, a, q = gctx.decompress_blocks(payload, poff, crc, handles)
+    assert np.array_equal(ro, reads.read_off)
+    assert np.array_equal(a, reads.acids) and np.array_equal(q, reads.quals)
+    return out, block_off, crc
+
+
+@pytest.mark.parametrize("block_len", [4 * 1024 * 1024, 200])
+@pytest.mark.parametrize("fast", [False, True])
+def test_round_trip_1k_device(gctx, O, toy_models, toy_handles, reads_1k, block_len, fast):
+    _decode_all(gctx, O, toy_models, toy_handles, reads_1k, blocks_of(reads_1k, block_len), fast)
+
+
+def test_device_output_decodes_with_oracle(gctx, O, toy_models, toy_handles, reads_1k):
+    """A whole .idn file assembled from device blocks is read back by the oracle's file decoder."""
+    bf = blocks_of(reads_1k, 20000)
+    out, block_off, crc, _ = gctx.compress_blocks(reads_1k.read_off, reads_1k.acids, reads_1k.quals, bf, toy_handles)
+    ids = b"".join(m.md.identifier for m in toy_models)
+    idn = b"IDENCOMP\x01" + bytes([1, 0, len(toy_models)]) + ids + out.tobytes() + b"\x00" * 8
+    back = O.decompress(toy_models, idn)
+    assert np.array_equal(back.read_off, reads_1k.read_off)
+    assert np.array_equal(back.acids, reads_1k.acids) and np.array_equal(back.quals, reads_1k.quals)
+    # and the oracle's own file is bit-identical outside the names slices
+    ref = O.compress(toy_models, reads_1k, max_block_total_len=20000, include_identifiers=False)
+    assert ref == idn
+
+
+# ---- every bundled model pair: dense maps, the sparse (hashed) 2^27-spec model, all spec kinds --------------------
+def test_bundled_pairs_vs_oracle(gctx, O, bundled, reads_1k):
+    acids = [k for k, (m, _) in bundled.items() if m.mtype == O.ACID]
+    quals = [k for k, (m, _) in bundled.items() if m.mtype == O.QSCORE]
+    bf = blocks_of(reads_1k, 30000)
+    for i in range(max(len(acids), len(quals))):
+        an, qn = acids[i % len(acids)], quals[i % len(quals)]
+        models = [bundled[an][0], bundled[qn][0]]
+        handles = [bundled[an][1], bundled[qn][1]]
+        expect = oracle_blocks(O, models, reads_1k, bf, fast=True, names=False)
+        out, block_off, crc, _ = gctx.compress_blocks(reads_1k.read_off, reads_1k.acids, reads_1k.quals, bf, handles,
+                                                      fast=True)
+        check_container(out, block_off, crc, expect)
+        _decode_all(gctx, O, models, handles, reads_1k, bf, True)
+
+
+def test_scores_vs_oracle_all_models(gctx, O, bundled, reads_1k):
+    names = list(bundled)
+    handles = [bundled[n][1] for n in names]
+    n = 120
+    ro = reads_1k.read_off[:n + 1]
+    sizes = gctx.score((ro, reads_1k.acids[:int(ro[-1])], reads_1k.quals[:int(ro[-1])]), handles)
+    for j, name in enumerate(names):
+        m = bundled[name][0]
+        for r in range(n):
+            lo, hi = int(ro[r]), int(ro[r + 1])
+            assert int(sizes[r, j]) == O.score_read(m, reads_1k.acids[lo:hi], reads_1k.quals[lo:hi]), (name, r)
+
+
+def test_model_selection_vs_oracle(gctx, O, bundled, reads_1k):
+    """Non-fast mode with several candidates per type: scoring + greedy switching (model_chooser.rs:168-198,
+    compressor_block.rs:232-280) must reproduce the oracle's switch slices byte for byte."""
+    acids = [k for k, (m, _) in bundled.items() if m.mtype == O.ACID][:4]
+    quals = [k for k, (m, _) in bundled.items() if m.mtype == O.QSCORE][:4]
+    order = acids + quals  # acid ids first, then q ids (compressor_initializer.rs:57-65)
+    models = [bundled[k][0] for k in order]
+    handles = [bundled[k][1] for k in order]
+    bf = blocks_of(reads_1k, 9000)
+    expect = oracle_blocks(O, models, reads_1k, bf, fast=False, names=False)
+    out, block_off, crc, stats = gctx.compress_blocks(reads_1k.read_off, reads_1k.acids, reads_1k.quals, bf, handles)
+    check_container(out, block_off, crc, expect)
+    assert stats["acid_switches"] == sum(s["acid_switches"] for _, _, s in expect)
+    assert stats["q_switches"] == sum(s["q_switches"] for _, _, s in expect)
+    _decode_all(gctx, O, models, handles, reads_1k, bf, False)
+
+
+def test_interleaved_model_order(gctx, O, bundled, reads_1k):
+    """SwitchModel indices are positions in the provider list whatever the type order."""
+    a = [k for k, (m, _) in bundled.items() if m.mtype == O.ACID][:2]
+    q = [k for k, (m, _) in bundled.items() if m.mtype == O.QSCORE][:2]
+    order = [q[0], a[0], q[1], a[1]]
+    models = [bundled[k][0] for k in order]
+    handles = [bundled[k][1] for k in order]
+    bf = blocks_of(reads_1k, 40000)
+    expect = oracle_blocks(O, models, reads_1k, bf, fast=False, names=False)
+    out, block_off, crc, _ = gctx.compress_blocks(reads_1k.read_off, reads_1k.acids, reads_1k.quals, bf, handles)
+    check_container(out, block_off, crc, expect)
+
+
+# ---- edge cases ----------------------------------------------------------------------------------------------------
+def test_empty_and_ragged_reads(gctx, O):
+    models = [O.Model(O.ModelData.empty(O.ACID)), O.Model(O.ModelData.empty(O.QSCORE))]
+    handles = [upload(gctx, O, m) for m in models]
+    rng = np.random.default_rng(7)
+    seqs = [("", [], [])]
+    for ln in [1, 2, 3, 4, 5, 7, 8, 9, 15, 16, 17, 31, 33, 0, 64, 100, 1, 0, 255, 1000]:
+        seqs.append(("", rng.integers(0, 5, ln), rng.integers(0, 94, ln)))
+    reads = O.Reads.from_lists(seqs)
+    bf = np.asarray([0, 1, 1, 5, reads.n_reads], dtype=np.uint32)  # includes an empty block and a block of one empty read
+    expect = oracle_blocks(O, models, reads, bf, fast=False, names=False)
+    out, block_off, crc, _ = gctx.compress_blocks(reads.read_off, reads.acids, reads.quals, bf, handles)
+    check_container(out, block_off, crc, expect)
+    _decode_all(gctx, O, models, handles, reads, bf, False)
+
+
+def test_zero_reads_batch(gctx, toy_handles):
+    out, block_off, crc, stats = gctx.compress_blocks([0], [], [], [0, 0], toy_handles)
+    assert out.tobytes() == b"\x00" * 8 and block_off.tolist() == [0, 8] and int(crc[0]) == 0
+
+
+def test_random_symbols_all_spec_types(gctx, O, bundled):
+    """Uniformly random symbols mostly fall through to the dummy context (sequence_compressor.rs:37-40) and hit every
+    quality value / N handling path of the generic and light generators."""
+    rng = np.random.default_rng(11)
+    seqs = []
+    for ln in rng.integers(1, 400, 300):
+        seqs.append(("", rng.integers(0, 5, ln), rng.integers(0, 94, ln)))
+    reads = O.Reads.from_lists(seqs)
+    bf = blocks_of(reads, 10000)
+    acids = [k for k, (m, _) in bundled.items() if m.mtype == O.ACID]
+    quals = [k for k, (m, _) in bundled.items() if m.mtype == O.QSCORE]
+    for i in range(max(len(acids), len(quals))):
+        an, qn = acids[i % len(acids)], quals[(i + 3) % len(quals)]
+        models = [bundled[an][0], bundled[qn][0]]
+        handles = [bundled[an][1], bundled[qn][1]]
+        expect = oracle_blocks(O, models, reads, bf, fast=True, names=False)
+        out, block_off, crc, _ = gctx.compress_blocks(reads.read_off, reads.acids, reads.quals, bf, handles, fast=True)
+        check_container(out, block_off, crc, expect)
+        _decode_all(gctx, O, models, handles, reads, bf, True)
+
+
+def test_block_crc_matches_zlib(gctx, reads_1k):
+    bf = blocks_of(reads_1k, 7000)
+    got = gctx.block_crc(reads_1k.read_off, reads_1k.acids, reads_1k.quals, bf, reads_1k.name_off, reads_1k.names)
+    for b in range(len(bf) - 1):
+        c = 0
+        for r in range(int(bf[b]), int(bf[b + 1])):
+            lo, hi = int(reads_1k.read_off[r]), int(reads_1k.read_off[r + 1])
+            c = zlib.crc32(reads_1k.name(r), c)
+            c = zlib.crc32(reads_1k.acids[lo:hi].tobytes(), c)
+            c = zlib.crc32(reads_1k.quals[lo:hi].tobytes(), c)
+        assert int(got[b]) == c
+
+
+# ---- error behaviour (IdnCompressorError / IdnDecompressorError variants) -----------------------------------------
+def test_errors(gctx, O, toy_models, toy_handles, reads_1k):
+    from idencomp_b200.capi import IdnGpuError
+    bf = blocks_of(reads_1k, 20000)
+    out, block_off, crc, _ = gctx.compress_blocks(reads_1k.read_off, reads_1k.acids, reads_1k.quals, bf, toy_handles)
+    nb = len(bf) - 1
+    payload = np.concatenate([out[int(block_off[b]) + 8:int(block_off[b + 1])] for b in range(nb)])
+    sizes = [int(block_off[b + 1] - block_off[b]) - 8 for b in range(nb)]
+    poff = np.concatenate([[0], np.cumsum(sizes)]).astype(np.uint64)
+    # checksum mismatch names the block
+    bad_crc = crc.copy()
+    bad_crc[1] ^= 1
+    with pytest.raises(IdnGpuError) as e:
+        gctx.decompress_blocks(payload, poff, bad_crc, toy_handles)
+    assert e.value.kind == "BlockChecksumMismatch" and e.value.bad_block == 1
+    # sequence slice before any SwitchModel
+    with pytest.raises(IdnGpuError) as e:
+        gctx.decompress_blocks(payload[4:int(poff[1])], [0, int(poff[1]) - 4], None, toy_handles)
+    assert e.value.kind == "NoActiveModel"
+    # SwitchModel index out of range
+    broken = payload[:int(poff[1])].copy()
+    broken[1] = 9
+    with pytest.raises(IdnGpuError) as e:
+        gctx.decompress_blocks(broken, [0, len(broken)], None, toy_handles)
+    assert e.value.kind == "InvalidModelIndex"
+    # truncated block
+    with pytest.raises(IdnGpuError) as e:
+        gctx.decompress_blocks(payload[:int(poff[1]) - 3], [0, int(poff[1]) - 3], None, toy_handles)
+    assert e.value.kind == "SerializeError"
+    # output capacity
+    with pytest.raises(IdnGpuError) as e:
+        gctx.compress_blocks(reads_1k.read_off, reads_1k.acids, reads_1k.quals, bf, toy_handles, out_cap=1000)
+    assert e.value.kind == "NoSpace" and e.value.stats["required_bytes"] == int(block_off[-1])
+    # invalid symbols
+    bad = reads_1k.acids.copy()
+    bad[5] = 7
+    with pytest.raises(IdnGpuError) as e:
+        gctx.compress_blocks(reads_1k.read_off, bad, reads_1k.quals, bf, toy_handles)
+    assert e.value.kind == "InvalidSymbol"
+    # fast mode with != 2 models, unknown handle
+    with pytest.raises(IdnGpuError) as e:
+        gctx.compress_blocks(reads_1k.read_off, reads_1k.acids, reads_1k.quals, bf, toy_handles + toy_handles[:1], fast=True)
+    assert e.value.kind == "InvalidState"
+    with pytest.raises(IdnGpuError) as e:
+        gctx.compress_blocks(reads_1k.read_off, reads_1k.acids, reads_1k.quals, bf, [999, 998])
+    assert e.value.kind == "UnknownModel"
