@@ -55,7 +55,7 @@ struct BackWriter {
         n = 0;
     }
     __device__ __forceinline__ void push(uint32_t b) {
-        acc = (acc >> 8) | (b << 24);
+        acc = (acc << 8) | b;  // the first byte pushed lands at the highest address
         if (++n == 4) {
             *--wptr = acc;
             n = 0;
@@ -67,9 +67,9 @@ struct BackWriter {
         push((x >> 8) & 0xffu);
         push(x & 0xffu);
     }
-    __device__ __forceinline__ void finish() {  // leftover bytes sit in the high bytes of acc
+    __device__ __forceinline__ void finish() {  // leftover bytes sit in the low bytes of acc, oldest highest
         uint8_t* p = reinterpret_cast<uint8_t*>(wptr);
-        for (uint32_t k = 0; k < n; k++) p[-1 - (int)k] = (uint8_t)(acc >> (24 - 8 * k));
+        for (uint32_t k = 0; k < n; k++) p[-1 - (int)k] = (uint8_t)(acc >> (8 * (n - 1 - k)));
     }
 };
 
