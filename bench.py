@@ -1,0 +1,582 @@
+#!/usr/bin/env python
+"""bench.py -- FASTQ compress/decompress throughput of the rANS hot path on B200 (BASELINE.json's metric).
+
+    python bench.py --gpus N --steps K --warmup W            # this repository's CUDA path
+    python bench.py --impl reference --gpus N ...            # the reference algorithm on the box's host cores
+
+A step = one pass of the hot path over the workload's batch: compress every block, then decompress every block.
+`value` = FASTQ text bytes through the codec per second (2 x FASTQ bytes / (t_compress + t_decompress)), inputs
+resident in HBM, timed with CUDA events on the launching stream.  `e2e` = the same through the host-pointer C-ABI
+calls (pinned host buffers, H2D/D2H inside the timed region).  Nothing here reads /root/reference.
+The oracle (oracle/) is used only for `cpu_baseline` / `--impl reference`: the Rust reference cannot be built in
+this image, so its CPU restatement (pinned bit-exactly to the reference's golden container) is what is timed.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+if str(ROOT) not in sys.path:
+    sys.path.insert(0, str(ROOT))
+
+MODELS = ROOT / "models"
+BLOCK_SYMBOLS = 4 * 1024 * 1024  # IdnCompressorParams::max_block_total_len default, idn/compressor.rs:187
+
+# SURVEY.md 8d.  fastq_overhead = bytes of a FASTQ record besides the 2*L symbol characters: '@' + name + '\n',
+# '\n' after the acids, "+\n", '\n' after the quality scores.
+WORKLOADS = {
+    # config 2: 10 GB HiSeq 2000-shaped, 100 bp, compat mode.  The ERR174310 q-score model is missing from the
+    # reference checkout (.MISSING_LARGE_BLOBS), SRR2962693 (same spec type, HiSeq 2500) stands in.
+    "hiseq100": dict(acid="ERR174310__human__illumina_hiseq_2000__acids", q="SRR2962693__human__illumina_hiseq_2500__q_scores",
+                     read_len=(100, 100), reads=40_485_830, name_len=41, seed=20240601, n_ppm=500, mode="compat",
+                     desc="synthetic 10 GB Illumina HiSeq 2000-shaped FASTQ, 100 bp, compat mode (BASELINE.json configs[1])"),
+    "novaseq150": dict(acid="SRR8861483__human__illumina_novaseq_6000__acids", q="SRR8861483__human__illumina_novaseq_6000__q_scores",
+                       read_len=(150, 150), reads=28_500_000, name_len=44, seed=20240602, n_ppm=500, mode="compat",
+                       desc="synthetic 10 GB NovaSeq 6000-shaped FASTQ, 150 bp (a 10 GB shard of configs[2])"),
+    "pacbio": dict(acid="m64187e__sars_cov_2__sequel_ii_e__acids", q="m64187e__sars_cov_2__sequel_ii_e__q_scores",
+                   read_len=(10_000, 20_000), reads=166_000, name_len=40, seed=20240603, n_ppm=0, mode="compat",
+                   desc="synthetic 5 GB PacBio Sequel II-shaped FASTQ, 10-20 kb reads (configs[4])"),
+}
+
+
+def read_lengths(w: dict, n_reads: int, first: int) -> np.ndarray:
+    lo, hi = w["read_len"]
+    if lo == hi:
+        return np.full(n_reads, lo, dtype=np.uint64)
+    rng = np.random.Generator(np.random.PCG64(w["seed"] + first))
+    return rng.integers(lo, hi + 1, size=n_reads, dtype=np.uint64)
+
+
+def form_blocks(lens: np.ndarray, max_len: int = BLOCK_SYMBOLS) -> np.ndarray:
+    """IdnCompressor::add_sequence block forming (idn/compressor.rs:517-540) -> block_first_read."""
+    if len(lens) and lens.min() == lens.max():
+        per = max(1, max_len // int(lens[0]))
+        first = np.arange(0, len(lens), per, dtype=np.uint32)
+        return np.append(first, np.uint32(len(lens))).astype(np.uint32)
+    first, cur = [0], 0
+    for r, ln in enumerate(lens.tolist()):
+        if cur + ln > max_len and cur > 0:
+            first.append(r)
+            cur = 0
+        cur += ln
+    first.append(len(lens))
+    return np.asarray(first, dtype=np.uint32)
+
+
+def fastq_bytes(w: dict, n_reads: int, n_symbols: int) -> int:
+    return 2 * n_symbols + n_reads * (6 + w["name_len"])
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons DURING the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device: int):
+        self.device = device
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.device)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            self.proc = None
+
+    def stop(self) -> dict:
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            out, _ = self.proc.communicate(timeout=10)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+            out, _ = self.proc.communicate()
+        sm, smax, power, reasons = [], [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in out.splitlines():
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                smax.append(float(f[2]))
+                power.append(float(f[3]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(smax), "power_w_max": max(power), "samples": len(sm),
+                "reasons": sorted(reasons)}
+
+
+def measured_peak_gbs():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        try:
+            return float(json.loads(p.read_text())["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# ---------------------------------------------------------------------------------------------------------
+# CPU arm: the reference algorithm (oracle restatement) on the host cores
+# ---------------------------------------------------------------------------------------------------------
+def cpu_sample(w: dict, n_blocks: int, threads: int):
+    from oracle import oracle as O
+    am = O.Model(O.ModelData.load_msgpack(MODELS / (w["acid"] + ".msgpack")))
+    qm = O.Model(O.ModelData.load_msgpack(MODELS / (w["q"] + ".msgpack")))
+    lo, hi = w["read_len"]
+    n_reads = max(1, int(n_blocks * BLOCK_SYMBOLS // ((lo + hi) // 2)))
+    lens = read_lengths(w, n_reads, 0)
+    ro = np.zeros(n_reads + 1, dtype=np.uint64)
+    np.cumsum(lens, out=ro[1:])
+    reads = O.synth_reads(am, qm, ro, 0, w["seed"], w["n_ppm"], threads=threads)
+    return O, [am, qm], reads
+
+
+def cpu_step(O, models, reads, threads: int):
+    """compress + decompress once; returns (t_compress, t_decompress, container bytes)."""
+    t0 = time.perf_counter()
+    idn = O.compress(models, reads, max_block_total_len=BLOCK_SYMBOLS, include_identifiers=False, quality=7, fast=False,
+                     threads=threads)
+    t1 = time.perf_counter()
+    back = O.decompress(models, idn, threads=threads)
+    t2 = time.perf_counter()
+    assert np.array_equal(back.acids, reads.acids) and np.array_equal(back.quals, reads.quals)
+    return t1 - t0, t2 - t1, len(idn)
+
+
+def run_reference(args, w: dict):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    # bounded sample: two blocks per core keeps every worker busy; sized so K+W steps end within minutes
+    n_blocks = args.cpu_blocks or max(8, min(2 * cores, 256))
+    O, models, reads = cpu_sample(w, n_blocks, cores)
+    fq = fastq_bytes(w, reads.n_reads, int(reads.read_off[-1]))
+    for _ in range(args.warmup):
+        cpu_step(O, models, reads, cores)
+    tc = td = 0.0
+    nbytes = 0
+    for _ in range(args.steps):
+        a, b, nbytes = cpu_step(O, models, reads, cores)
+        tc += a
+        td += b
+    val = 2 * fq * args.steps / (tc + td) / 1e9
+    sample = f"first {reads.n_reads} reads ({n_blocks} blocks, {fq / 1e6:.0f} MB FASTQ) of the workload per step"
+    line = {
+        "impl": "reference", "metric": "fastq_compress_decompress_GBps", "value": val, "unit": "GB/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": (tc + td) / args.steps * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
+        "config": {"workload": w["desc"], "name": args.workload, "acid_model": w["acid"], "q_model": w["q"], "block_symbols": BLOCK_SYMBOLS,
+                   "sample": sample},
+        "compress_GBps": fq * args.steps / tc / 1e9, "decompress_GBps": fq * args.steps / td / 1e9,
+        "container_bytes_per_read": nbytes / reads.n_reads,
+        "cpu_baseline": {"value": val, "unit": "GB/s", "cores": cores, "kind": "port", "sample": sample,
+                         "note": "reference-algorithm CPU restatement (oracle/), bit-identical to the reference's golden "
+                                 "samples/1M.idn; the Rust reference cannot be built in this image (no rustc/cargo)"},
+        "e2e": {"value": val, "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+# ---------------------------------------------------------------------------------------------------------
+# GPU arm
+# ---------------------------------------------------------------------------------------------------------
+class Chunk:
+    __slots__ = ("r0", "r1", "b0", "b1", "s0", "s1", "n_reads", "n_syms", "n_blocks", "read_off", "block_first", "out_base",
+                 "out_cap", "block_off", "block_crc", "stats", "dec_off", "dec_len", "dec_status", "dec_read_off", "batch")
+
+
+def run_gpu(args, w: dict):
+    import torch
+
+    from idencomp_b200 import capi, host
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: there is no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+
+    ctx = capi.Context(local)
+    L = ctx.L
+    am = host.Model.load(MODELS / (w["acid"] + ".msgpack"))
+    qm = host.Model.load(MODELS / (w["q"] + ".msgpack"))
+    handles = np.asarray([am.upload(ctx), qm.upload(ctx)], dtype=np.int32)
+    stream = torch.cuda.current_stream()
+    sp = C.c_void_p(stream.cuda_stream)
+
+    # ---- the shard of this rank (weak scaling: every rank holds the workload's read count) ----
+    n_reads = args.reads or w["reads"]
+    first_index = rank * n_reads
+    lens = read_lengths(w, n_reads, first_index)
+    read_off_h = np.zeros(n_reads + 1, dtype=np.uint64)
+    np.cumsum(lens, out=read_off_h[1:])
+    S = int(read_off_h[-1])
+    block_first_h = form_blocks(lens)
+    n_blocks = len(block_first_h) - 1
+    fq = fastq_bytes(w, n_reads, S)
+
+    read_off_d = torch.from_numpy(read_off_h.view(np.int64)).to(dev)
+    acids_d = torch.empty(S + 16, dtype=torch.uint8, device=dev)
+    quals_d = torch.empty(S + 16, dtype=torch.uint8, device=dev)
+    ctx.check(L.idn_gpu_synth_reads_dev(ctx.h, int(handles[0]), int(handles[1]), read_off_d.data_ptr(), n_reads, first_index,
+                                        w["seed"], w["n_ppm"], acids_d.data_ptr(), quals_d.data_ptr(), sp))
+    torch.cuda.synchronize()
+
+    # ---- chunks of whole blocks: one library call per chunk and direction ----
+    cb = args.chunk_blocks
+    chunks = []
+    out_total = 0
+    for b0 in range(0, n_blocks, cb):
+        c = Chunk()
+        c.b0, c.b1 = b0, min(n_blocks, b0 + cb)
+        c.r0, c.r1 = int(block_first_h[c.b0]), int(block_first_h[c.b1])
+        c.s0, c.s1 = int(read_off_h[c.r0]), int(read_off_h[c.r1])
+        c.n_reads, c.n_syms, c.n_blocks = c.r1 - c.r0, c.s1 - c.s0, c.b1 - c.b0
+        c.read_off = torch.from_numpy((read_off_h[c.r0:c.r1 + 1] - read_off_h[c.r0]).view(np.int64)).to(dev)
+        c.block_first = torch.from_numpy((block_first_h[c.b0:c.b1 + 1] - block_first_h[c.b0]).astype(np.int32)).to(dev)
+        c.out_cap = int(L.idn_gpu_compress_bound(c.n_reads, c.n_syms, c.n_blocks, 0))
+        if not args.full_bound:  # measured containers are ~0.35 B/symbol; 1.5 B/symbol + headers is ample and is checked
+            c.out_cap = min(c.out_cap, int(1.5 * c.n_syms) + 21 * c.n_reads + 12 * c.n_blocks)
+        c.out_base = out_total
+        out_total += (c.out_cap + 255) // 256 * 256
+        c.block_off = torch.zeros(c.n_blocks + 1, dtype=torch.int64, device=dev)
+        c.block_crc = torch.zeros(c.n_blocks, dtype=torch.int32, device=dev)
+        c.stats = torch.zeros(8, dtype=torch.int64, device=dev)
+        c.dec_status = torch.zeros(4, dtype=torch.int32, device=dev)
+        c.dec_read_off = torch.zeros(c.n_reads + 1, dtype=torch.int64, device=dev)
+        b = capi.Batch()
+        b.n_reads, b.n_symbols, b.n_blocks = c.n_reads, c.n_syms, c.n_blocks
+        b.acids, b.quals = acids_d.data_ptr() + c.s0, quals_d.data_ptr() + c.s0
+        b.read_off, b.block_first_read = c.read_off.data_ptr(), c.block_first.data_ptr()
+        c.batch = b
+        chunks.append(c)
+    out_d = torch.empty(out_total + 16, dtype=torch.uint8, device=dev)
+    dec_a = torch.empty(S + 16, dtype=torch.uint8, device=dev)
+    dec_q = torch.empty(S + 16, dtype=torch.uint8, device=dev)
+
+    def compress_all():
+        for c in chunks:
+            ctx.check(L.idn_gpu_compress_blocks_dev(ctx.h, C.byref(c.batch), capi.MODE_COMPAT, handles.ctypes.data, 2, 0, None,
+                                                    out_d.data_ptr() + c.out_base, c.out_cap, c.block_off.data_ptr(),
+                                                    c.block_crc.data_ptr(), c.stats.data_ptr(), sp))
+
+    def prepare_decode():
+        """block table of the decode calls from the compress outputs (device ops, outside the timed region)."""
+        for c in chunks:
+            st = c.stats.cpu().numpy()
+            if int(st[4]) > c.out_cap:
+                raise SystemExit(f"container chunk needs {int(st[4])} bytes, capacity {c.out_cap}: rerun with --full-bound")
+            c.dec_len = (c.block_off[1:] - c.block_off[:-1] - 8).to(torch.int32).contiguous()
+            c.dec_off = torch.cat([c.block_off[:-1] + 8, c.block_off[-1:]]).contiguous()
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- warm-up (also sizes the library workspaces and fixes the decode block tables) ----
+    compress_all()
+    torch.cuda.synchronize()
+    prepare_decode()
+    sizes, out_bytes, payload_bytes = {}, 0, 0
+    for c in chunks:
+        st = c.stats.cpu().numpy()
+        sizes[id(c)] = int(st[0])
+        out_bytes += int(st[0])
+        payload_bytes += int(st[3])
+
+    def decompress_all():
+        for c in chunks:
+            ctx.check(L.idn_gpu_decompress_blocks_dev(ctx.h, out_d.data_ptr() + c.out_base, c.dec_off.data_ptr(),
+                                                      c.dec_len.data_ptr(), c.block_crc.data_ptr(), c.n_blocks, sizes[id(c)],
+                                                      capi.MODE_COMPAT, handles.ctypes.data, 2, dec_a.data_ptr() + c.s0,
+                                                      dec_q.data_ptr() + c.s0, c.dec_read_off.data_ptr(), c.n_reads, c.n_syms,
+                                                      c.dec_status.data_ptr(), sp))
+
+    decompress_all()
+    torch.cuda.synchronize()
+    for c in chunks:
+        stt = c.dec_status.cpu().numpy()
+        if int(stt[0]) != 0:
+            raise SystemExit(f"decode failed: status {stt.tolist()}")
+    for _ in range(max(0, args.warmup - 1)):
+        compress_all()
+        decompress_all()
+    barrier()
+
+    # ---- timed region: exactly K steps, CUDA events on the launching stream ----
+    ctx.profile(True)
+    launches0 = ctx.launches
+    sampler = ClockSampler(local)
+    sampler.start()
+    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(args.steps)]
+    t_wall0 = time.perf_counter()
+    for k in range(args.steps):
+        ev[k][0].record(stream)
+        compress_all()
+        ev[k][1].record(stream)
+        decompress_all()
+        ev[k][2].record(stream)
+    torch.cuda.synchronize()
+    t_wall = time.perf_counter() - t_wall0
+    clocks = sampler.stop()
+    launches = ctx.launches - launches0
+    prof = ctx.profile_read()
+    ctx.profile(False)
+    tc = sum(ev[k][0].elapsed_time(ev[k][1]) for k in range(args.steps)) / 1e3
+    td = sum(ev[k][1].elapsed_time(ev[k][2]) for k in range(args.steps)) / 1e3
+    t_total = ev[0][0].elapsed_time(ev[-1][2]) / 1e3
+
+    # ---- verification outside the timed region: lossless round trip of the whole workload on the device ----
+    verified = bool(torch.equal(dec_a[:S], acids_d[:S]) and torch.equal(dec_q[:S], quals_d[:S]))
+    for c in chunks:
+        stt = c.dec_status.cpu().numpy()
+        verified = verified and int(stt[0]) == 0 and int(stt[2]) == c.n_reads
+    if not verified:
+        raise SystemExit("round trip mismatch: the decoded symbols differ from the input")
+
+    # ---- e2e: the host-pointer C-ABI calls on pinned host buffers, several ctx in flight ----
+    e2e = None
+    if not args.no_e2e:
+        e2e = run_e2e(args, w, capi, host, torch, local, chunks, acids_d, quals_d, read_off_h, block_first_h, sizes, dist, fq)
+
+    # ---- max over ranks ----
+    t_max = t_total
+    tc_max, td_max = tc, td
+    if dist is not None:
+        t = torch.tensor([t_total, tc, td, e2e["_t"] if e2e else 0.0], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        t_max, tc_max, td_max = float(t[0]), float(t[1]), float(t[2])
+        if e2e:
+            e2e["_t"] = float(t[3])
+    value = 2 * fq * args.steps * world / t_max / 1e9
+
+    # ---- roofline of the dominant kernel (by device time inside the timed region) ----
+    peak, peak_src = measured_peak_gbs()
+    ksum = sum(ms for _, ms in prof.values()) or 1.0
+    dom = max(prof.items(), key=lambda kv: kv[1][1])
+    dname, (dn, dms) = dom
+    # algorithmic bytes per launch (DESIGN.md "Kernels"): encode reads 2 B/symbol and writes the rANS payloads;
+    # decode reads the container chunk and writes 2 B/symbol; score reads 2 B/symbol per launch
+    per_chunk = len(chunks)
+    alg = {"encode": (2 * S + payload_bytes) / per_chunk, "decode": (2 * S + out_bytes) / per_chunk,
+           "score": 2 * S / per_chunk, "assemble": 2 * payload_bytes / per_chunk, "crc_read": 2 * S / per_chunk}.get(dname, 2 * S / per_chunk)
+    achieved = alg / (dms / dn / 1e3) / 1e9
+    traffic = None
+    tpath = ROOT / "profiles" / "traffic.json"
+    if tpath.exists():
+        try:
+            traffic = json.loads(tpath.read_text()).get(dname)
+        except Exception:
+            traffic = None
+    roofline = {"bound": "hbm", "kernel": dname + "_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_launch": alg,
+                "avg_launch_ms": dms / dn, "share_of_step": dms / ksum,
+                "whole_path": {"compress_GBps_alg": (2 * S + out_bytes) * args.steps / tc / 1e9,
+                               "decompress_GBps_alg": (2 * S + out_bytes) * args.steps / td / 1e9},
+                "kernels_ms_per_step": {k: v[1] / args.steps for k, v in sorted(prof.items(), key=lambda kv: -kv[1][1])}}
+
+    if rank == 0:
+        cpu = None
+        if world == 1 and not args.no_cpu_baseline:
+            cpu = cpu_baseline(args, w)
+        line = {
+            "metric": "fastq_compress_decompress_GBps", "value": value, "unit": "GB/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": t_max / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "u32", "data": "synthetic (model-driven sampler, SURVEY.md 8d)",
+            "config": {"workload": w["desc"], "name": args.workload, "mode": w["mode"], "acid_model": w["acid"], "q_model": w["q"],
+                       "reads_per_gpu": n_reads, "symbols_per_gpu": S, "fastq_bytes_per_gpu": fq, "blocks_per_gpu": n_blocks,
+                       "block_symbols": BLOCK_SYMBOLS, "chunk_blocks": cb, "names": "not stored (--no-identifiers protocol, "
+                       "util/benchmark.py:161-179); their bytes count as FASTQ input", "l2": f"inputs {2 * S / 1e9:.1f} GB >> 126 MB L2, no flush needed",
+                       "model_selection": "explicit pair (1 acid + 1 q-score model), quality 7 semantics"},
+            "compress_GBps": fq * args.steps * world / tc_max / 1e9, "decompress_GBps": fq * args.steps * world / td_max / 1e9,
+            "container_bytes_per_read": out_bytes / n_reads, "bits_per_base": 8 * payload_bytes / S, "verified_round_trip": verified,
+            "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "wall_s_timed": t_wall,
+        }
+        if e2e:
+            line["e2e"] = {"value": 2 * fq * e2e["steps"] * world / e2e["_t"] / 1e9, "unit": "GB/s",
+                           "h2d_bytes_per_step": e2e["h2d"], "d2h_bytes_per_step": e2e["d2h"], "steps": e2e["steps"],
+                           "threads": e2e["threads"], "compress_GBps": e2e["cGBps"], "decompress_GBps": e2e["dGBps"], "sample": e2e["sample"]}
+        if cpu:
+            line["cpu_baseline"] = cpu
+        print(json.dumps(line))
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+    ctx.close()
+
+
+def cpu_baseline(args, w: dict) -> dict:
+    cores = os.cpu_count() or 1
+    n_blocks = args.cpu_blocks or max(8, min(2 * cores, 256))
+    O, models, reads = cpu_sample(w, n_blocks, cores)
+    fq = fastq_bytes(w, reads.n_reads, int(reads.read_off[-1]))
+    cpu_step(O, models, reads, cores)  # warm-up
+    tc, td, _ = cpu_step(O, models, reads, cores)
+    return {"value": 2 * fq / (tc + td) / 1e9, "unit": "GB/s", "cores": cores, "kind": "port",
+            "sample": f"first {reads.n_reads} reads ({n_blocks} blocks, {fq / 1e6:.0f} MB FASTQ) of the workload, one timed pass after one warm-up",
+            "compress_GBps": fq / tc / 1e9, "decompress_GBps": fq / td / 1e9,
+            "note": "reference-algorithm CPU restatement (oracle/), one worker thread per block like idn/thread_pool.rs"}
+
+
+def run_e2e(args, w, capi, host, torch, local, chunks, acids_d, quals_d, read_off_h, block_first_h, sizes, dist, fq_total):
+    """Same step through idn_gpu_compress_blocks / idn_gpu_decompress_blocks with HOST buffers."""
+    import psutil
+    S = int(read_off_h[-1])
+    n_threads = max(1, min(args.e2e_threads, len(chunks)))
+    # pinned inputs, pinned container, pinned decoded output
+    use = chunks
+    need = 4 * S + sum(sizes.values()) * 2
+    avail = psutil.virtual_memory().available
+    if need * 1.5 > avail:
+        keep = max(1, int(len(chunks) * avail / (need * 1.5)))
+        use = chunks[:keep]
+    s_end = use[-1].s1
+    r_end = use[-1].r1
+    acids_h = torch.empty(s_end, dtype=torch.uint8, pin_memory=True)
+    quals_h = torch.empty(s_end, dtype=torch.uint8, pin_memory=True)
+    acids_h.copy_(acids_d[:s_end])
+    quals_h.copy_(quals_d[:s_end])
+    torch.cuda.synchronize()
+    a_np, q_np = acids_h.numpy(), quals_h.numpy()
+    stride = (max(sizes[id(c)] for c in use) * 21 // 20 + 4096) // 256 * 256
+    cont_h = torch.empty(stride * len(use), dtype=torch.uint8, pin_memory=True)
+    cont_np = cont_h.numpy()
+    da_h = torch.empty(s_end, dtype=torch.uint8, pin_memory=True)
+    dq_h = torch.empty(s_end, dtype=torch.uint8, pin_memory=True)
+    da_np, dq_np = da_h.numpy(), dq_h.numpy()
+    ctxs = []
+    for _ in range(n_threads):
+        cx = capi.Context(local)
+        am = host.Model.load(MODELS / (w["acid"] + ".msgpack"))
+        qm = host.Model.load(MODELS / (w["q"] + ".msgpack"))
+        ctxs.append((cx, np.asarray([am.upload(cx), qm.upload(cx)], dtype=np.int32)))
+    per_chunk = []
+    for i, c in enumerate(use):
+        ro = np.ascontiguousarray(read_off_h[c.r0:c.r1 + 1] - read_off_h[c.r0])
+        bf = np.ascontiguousarray((block_first_h[c.b0:c.b1 + 1] - block_first_h[c.b0]).astype(np.uint32))
+        b = capi.Batch()
+        b.n_reads, b.n_symbols, b.n_blocks = c.n_reads, c.n_syms, c.n_blocks
+        b.acids, b.quals = a_np.ctypes.data + c.s0, q_np.ctypes.data + c.s0
+        b.read_off, b.block_first_read = ro.ctypes.data, bf.ctypes.data
+        per_chunk.append(dict(batch=b, keep=(ro, bf), block_off=np.zeros(c.n_blocks + 1, dtype=np.uint64),
+                              crc=np.zeros(c.n_blocks, dtype=np.uint32), stats=capi.CompressStats(),
+                              ro_out=np.zeros(c.n_reads + 1, dtype=np.uint64), bad=C.c_int32(-1)))
+    errors = []
+
+    def worker(t, phase):
+        cx, hd = ctxs[t]
+        L = cx.L
+        try:
+            for i in range(t, len(use), n_threads):
+                c, pc = use[i], per_chunk[i]
+                base = cont_np.ctypes.data + i * stride
+                if phase == 0:
+                    cx.check(L.idn_gpu_compress_blocks(cx.h, C.byref(pc["batch"]), capi.MODE_COMPAT, hd.ctypes.data, 2, 0, None,
+                                                       base, stride, pc["block_off"].ctypes.data, pc["crc"].ctypes.data,
+                                                       C.byref(pc["stats"])))
+                else:
+                    bo = pc["block_off"]
+                    doff = np.append(bo[:-1] + 8, bo[-1]).astype(np.uint64)
+                    dlen = (bo[1:] - bo[:-1] - 8).astype(np.uint32)
+                    cx.check(L.idn_gpu_decompress_blocks(cx.h, base, doff.ctypes.data, dlen.ctypes.data, pc["crc"].ctypes.data,
+                                                         c.n_blocks, capi.MODE_COMPAT, hd.ctypes.data, 2, None, None,
+                                                         da_np.ctypes.data + c.s0, dq_np.ctypes.data + c.s0,
+                                                         pc["ro_out"].ctypes.data, c.n_reads, c.n_syms, C.byref(pc["bad"])))
+        except Exception as e:  # surfaced after the join
+            errors.append(e)
+
+    def phase(p):
+        ts = [threading.Thread(target=worker, args=(t, p)) for t in range(n_threads)]
+        t0 = time.perf_counter()
+        for t in ts:
+            t.start()
+        for t in ts:
+            t.join()
+        torch.cuda.synchronize()
+        if errors:
+            raise errors[0]
+        return time.perf_counter() - t0
+
+    steps = max(1, min(args.steps, args.e2e_steps))
+    for _ in range(2):  # warm-up: sizes the staging buffers of every ctx
+        phase(0)
+        phase(1)
+    if dist is not None:
+        dist.barrier()
+    torch.cuda.synchronize()
+    tc = td = 0.0
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        tc += phase(0)
+        td += phase(1)
+    t_all = time.perf_counter() - t0
+    ok = np.array_equal(da_np[:s_end], a_np[:s_end]) and np.array_equal(dq_np[:s_end], q_np[:s_end])
+    if not ok:
+        raise SystemExit("e2e round trip mismatch")
+    for cx, _ in ctxs:
+        cx.close()
+    frac = s_end / S
+    fq = fq_total * frac
+    cbytes = sum(int(pc["stats"].out_bytes) for pc in per_chunk)
+    h2d = 2 * s_end + 8 * (r_end + len(use)) + cbytes
+    d2h = cbytes + 2 * s_end + 8 * (r_end + len(use))
+    return {"_t": t_all / frac, "steps": steps, "h2d": int(h2d / frac), "d2h": int(d2h / frac), "threads": n_threads,
+            "cGBps": fq * steps / tc / 1e9, "dGBps": fq * steps / td / 1e9,
+            "sample": "whole workload" if use is chunks else f"first {len(use)} of {len(chunks)} chunks (host memory), scaled"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="hiseq100", choices=sorted(WORKLOADS))
+    ap.add_argument("--reads", type=int, default=0, help="reads per GPU (default: the workload's)")
+    ap.add_argument("--chunk-blocks", type=int, default=128, help="blocks per library call")
+    ap.add_argument("--full-bound", action="store_true", help="size container chunks by idn_gpu_compress_bound")
+    ap.add_argument("--cpu-blocks", type=int, default=0, help="blocks in the CPU sample (default 2 per core)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--e2e-threads", type=int, default=3)
+    ap.add_argument("--e2e-steps", type=int, default=3)
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3
+    w = WORKLOADS[args.workload]
+    if args.impl == "reference":
+        run_reference(args, w)
+    else:
+        run_gpu(args, w)
+
+
+if __name__ == "__main__":
+    main()

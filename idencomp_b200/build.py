@@ -40,8 +40,28 @@ def build_gpu(force: bool = False, verbose: bool = False) -> Path:
     return out
 
 
+HOST_SRCS = ["model.cpp", "capi_host.cpp"]
+# -ffp-contract=off / no -ffast-math: the f32 quantiser must round exactly like the reference (context.rs:346-371)
+GXX_FLAGS = ["-O2", "-std=c++17", "-fPIC", "-shared", "-Wall", "-ffp-contract=off", "-fno-fast-math", "-pthread"]
+
+
+def build_host(force: bool = False) -> Path:
+    """libidn_host.so: C++ host mirror of the reference API; links only against the C-ABI of libidn_gpu.so."""
+    out = PKG / "libidn_host.so"
+    host = CSRC / "host"
+    srcs = [host / s for s in HOST_SRCS]
+    deps = srcs + list(host.glob("*.hpp")) + [ROOT / "include" / "idn_host.h", ROOT / "include" / "idn_gpu.h"]
+    if force or _stale(out, deps):
+        cxx = os.environ.get("CXX") or shutil.which("g++") or "g++"
+        cmd = [cxx, *GXX_FLAGS, "-o", str(out), *map(str, srcs), f"-L{PKG}", "-lidn_gpu", "-lz",
+               "-Wl,-rpath,$ORIGIN"]
+        subprocess.run(cmd, check=True)
+    return out
+
+
 def build_all(force: bool = False) -> None:
     build_gpu(force)
+    build_host(force)
 
 
 if __name__ == "__main__":

@@ -30,6 +30,7 @@ EXPORTS = [
     "idn_gpu_launch_count", "idn_gpu_model_upload", "idn_gpu_model_release", "idn_gpu_score", "idn_gpu_score_dev",
     "idn_gpu_compress_blocks", "idn_gpu_compress_blocks_dev", "idn_gpu_compress_bound", "idn_gpu_index_blocks",
     "idn_gpu_decompress_blocks", "idn_gpu_decompress_blocks_dev", "idn_gpu_decompress_reads", "idn_gpu_block_crc",
+    "idn_gpu_synth_reads_dev", "idn_gpu_profile", "idn_gpu_profile_read",
 ]
 
 
@@ -100,17 +101,23 @@ def load():
     L.idn_gpu_compress_blocks_dev.restype = i32
     L.idn_gpu_compress_bound.argtypes = [u64, u64, u32, u64]
     L.idn_gpu_compress_bound.restype = u64
-    L.idn_gpu_index_blocks.argtypes = [vp, vp, vp, u32, vp, u32, C.POINTER(IndexTotals), vp]
+    L.idn_gpu_index_blocks.argtypes = [vp, vp, vp, vp, u32, vp, u32, C.POINTER(IndexTotals), vp]
     L.idn_gpu_index_blocks.restype = i32
-    L.idn_gpu_decompress_blocks.argtypes = [vp, vp, vp, vp, u32, i32, vp, u32, vp, vp, vp, vp, vp, u64, u64,
+    L.idn_gpu_decompress_blocks.argtypes = [vp, vp, vp, vp, vp, u32, i32, vp, u32, vp, vp, vp, vp, vp, u64, u64,
                                             C.POINTER(i32)]
     L.idn_gpu_decompress_blocks.restype = i32
-    L.idn_gpu_decompress_blocks_dev.argtypes = [vp, vp, vp, vp, u32, u64, i32, vp, u32, vp, vp, vp, u64, u64, vp, vp]
+    L.idn_gpu_decompress_blocks_dev.argtypes = [vp, vp, vp, vp, vp, u32, u64, i32, vp, u32, vp, vp, vp, u64, u64, vp, vp]
     L.idn_gpu_decompress_blocks_dev.restype = i32
     L.idn_gpu_decompress_reads.argtypes = [vp, vp, u64, C.POINTER(ReadIndex), vp, u32, vp, vp, vp]
     L.idn_gpu_decompress_reads.restype = i32
     L.idn_gpu_block_crc.argtypes = [vp, C.POINTER(Batch), vp]
     L.idn_gpu_block_crc.restype = i32
+    L.idn_gpu_synth_reads_dev.argtypes = [vp, i32, i32, vp, u64, u64, u64, u32, vp, vp, vp]
+    L.idn_gpu_synth_reads_dev.restype = i32
+    L.idn_gpu_profile.argtypes = [vp, i32]
+    L.idn_gpu_profile.restype = i32
+    L.idn_gpu_profile_read.argtypes = [vp, C.c_char_p, u64]
+    L.idn_gpu_profile_read.restype = i32
     _LIB = L
     return L
 
@@ -184,6 +191,19 @@ class Context:
     def launches(self) -> int:
         return int(self.L.idn_gpu_launch_count(self.h))
 
+    def profile(self, enable: bool):
+        self.check(self.L.idn_gpu_profile(self.h, int(enable)))
+
+    def profile_read(self) -> dict:
+        """{kernel: (launches, total_ms)} since the last read."""
+        buf = C.create_string_buffer(1 << 16)
+        self.check(self.L.idn_gpu_profile_read(self.h, buf, len(buf)))
+        out = {}
+        for ln in buf.value.decode().splitlines():
+            name, n, ms = ln.split()
+            out[name] = (int(n), float(ms))
+        return out
+
     # ---- models -------------------------------------------------------------------------------
     def upload_model(self, mtype: int, kind: int, ao: int, qo: int, pb: int, qmax: int, cum, spec_keys, spec_ctx) -> int:
         cum = _c(cum, np.uint16)
@@ -226,24 +246,26 @@ class Context:
             raise e
         return out[:st.out_bytes], block_off, crc[:b.n_blocks], st.as_dict()
 
-    def index_blocks(self, blocks, block_off, models):
+    def index_blocks(self, blocks, block_off, models, block_len=None):
         blocks = _c(blocks, np.uint8)
         bo = _c(block_off, np.uint64)
+        bl = None if block_len is None else _c(block_len, np.uint32)
         m = _c(models, np.int32)
         tot = IndexTotals()
         bf = np.zeros(len(bo), dtype=np.uint32)
-        self.check(self.L.idn_gpu_index_blocks(self.h, _p(blocks), bo.ctypes.data, len(bo) - 1, _p(m), len(m),
+        self.check(self.L.idn_gpu_index_blocks(self.h, _p(blocks), bo.ctypes.data, _p(bl), len(bo) - 1, _p(m), len(m),
                                                C.byref(tot), bf.ctypes.data))
         return int(tot.n_reads), int(tot.n_symbols), bf
 
     def decompress_blocks(self, blocks, block_off, block_crc, models, *, name_off=None, names=None, reads_cap=None,
-                          symbols_cap=None, mode=MODE_COMPAT):
+                          symbols_cap=None, mode=MODE_COMPAT, block_len=None):
         blocks = _c(blocks, np.uint8)
         bo = _c(block_off, np.uint64)
+        bl = None if block_len is None else _c(block_len, np.uint32)
         m = _c(models, np.int32)
         nb = len(bo) - 1
         if reads_cap is None or symbols_cap is None:
-            reads_cap, symbols_cap, _ = self.index_blocks(blocks, bo, m)
+            reads_cap, symbols_cap, _ = self.index_blocks(blocks, bo, m, bl)
         crc = None if block_crc is None else _c(block_crc, np.uint32)
         a = np.zeros(max(symbols_cap, 1), dtype=np.uint8)
         q = np.zeros(max(symbols_cap, 1), dtype=np.uint8)
@@ -255,7 +277,7 @@ class Context:
             nm = _c(names, np.uint8)
             if nm.size == 0:
                 nm = np.zeros(1, dtype=np.uint8)
-        rc = self.L.idn_gpu_decompress_blocks(self.h, _p(blocks), bo.ctypes.data, _p(crc), nb, mode, _p(m), len(m),
+        rc = self.L.idn_gpu_decompress_blocks(self.h, _p(blocks), bo.ctypes.data, _p(bl), _p(crc), nb, mode, _p(m), len(m),
                                               None if nm is None else nm.ctypes.data,
                                               None if no is None else no.ctypes.data, a.ctypes.data, q.ctypes.data,
                                               ro.ctypes.data, reads_cap, symbols_cap, C.byref(bad))

@@ -243,6 +243,16 @@ void Model::spec_table(std::vector<uint32_t>* keys, std::vector<uint32_t>* ctx) 
         }
 }
 
+int32_t upload_model(idn_gpu_ctx* ctx, const Model& m, idn_model_t* handle) {
+    const ContextSpecType& st = m.context_spec_type();
+    std::vector<uint16_t> cum = m.cum_table();
+    std::vector<uint32_t> keys, cidx;
+    m.spec_table(&keys, &cidx);
+    return idn_gpu_model_upload(ctx, (int32_t)m.model_type(), st.kind == ContextSpecType::Light ? IDN_SPEC_LIGHT : IDN_SPEC_GENERIC,
+                                st.acid_order, st.q_score_order, st.position_bits, st.q_score_max, (uint32_t)m.len(), cum.data(),
+                                keys.data(), cidx.data(), keys.size(), handle);
+}
+
 // ---- ModelProvider ---------------------------------------------------------------------------------------------------
 ModelProvider ModelProvider::with_empty_models() {
     return ModelProvider({std::make_shared<const Model>(Model::empty(ModelType::Acids)),

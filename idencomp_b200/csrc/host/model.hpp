@@ -12,6 +12,8 @@
 #include <string>
 #include <vector>
 
+#include "../../../include/idn_gpu.h"
+
 namespace idencomp {
 
 constexpr uint32_t kScaleBits = 14;  // idn/model_provider.rs:407
@@ -72,6 +74,9 @@ private:
 
 // Context::as_integer_cum_freqs (context.rs:346-371): cum[nsym] exclusive prefix sums, all freqs >= 1, total 2^scale_bits
 std::vector<uint32_t> quantise(const float* probs, size_t nsym, uint32_t scale_bits);
+
+// RansEncModel/RansDecModel::from_model on the device: integer tables -> idn_gpu_model_upload
+int32_t upload_model(idn_gpu_ctx* ctx, const Model& m, idn_model_t* handle);
 
 class ModelProvider {
 public:

@@ -75,6 +75,16 @@ struct idn_gpu_ctx {
     cudaEvent_t ev = nullptr;
     std::string err;
     uint64_t launches = 0;
+    // optional per-kernel timing (idn_gpu_profile): an event after every launch; a kernel's time is the gap to the
+    // previous event on the same stream (kernels of one call are serialised on one stream)
+    bool profiling = false;
+    std::vector<cudaEvent_t> prof_pool;
+    size_t prof_used = 0;
+    struct ProfMark {
+        const char* name;  // nullptr = start of a call
+        cudaEvent_t ev;
+    };
+    std::vector<ProfMark> prof_marks;
     std::vector<ModelSlot> slots;
     ModelDev* d_models = nullptr;  // [kMaxSlots], mirrors slots[].dev
     uint32_t* d_crc_tab = nullptr;  // [256]
@@ -85,7 +95,7 @@ struct idn_gpu_ctx {
     DevBuf w_blk;    // decode-side per-block counters
     // staging of the host-pointer paths
     DevBuf s_acids, s_quals, s_readoff, s_blockfirst, s_prefix, s_names, s_nameoff, s_out, s_blockoff, s_crc, s_stats,
-        s_sizes, s_blocks, s_aout, s_qout, s_offout, s_status, s_idx;
+        s_sizes, s_blocks, s_blocklen, s_aout, s_qout, s_offout, s_status, s_idx;
 };
 
 namespace {
@@ -112,13 +122,29 @@ int32_t fail(idn_gpu_ctx* c, int32_t code, const char* fmt, ...) {
         }                                                                                              \
     } while (0)
 
-#define LAUNCHED()                                                                                 \
+#define LAUNCHED(name)                                                                             \
     do {                                                                                           \
         ctx->launches++;                                                                           \
+        if (ctx->profiling) prof_mark(ctx, name, st);                                              \
         cudaError_t e__ = cudaGetLastError();                                                      \
         if (e__ != cudaSuccess)                                                                    \
             return fail(ctx, IDN_E_CUDA, "kernel launch failed: %s (%s:%d)", cudaGetErrorString(e__), \
                         __FILE__, __LINE__);                                                       \
+    } while (0)
+
+void prof_mark(idn_gpu_ctx* c, const char* name, cudaStream_t st) {
+    if (c->prof_used == c->prof_pool.size()) {
+        cudaEvent_t e;
+        if (cudaEventCreate(&e) != cudaSuccess) return;
+        c->prof_pool.push_back(e);
+    }
+    cudaEvent_t e = c->prof_pool[c->prof_used++];
+    cudaEventRecord(e, st);
+    c->prof_marks.push_back({name, e});
+}
+#define PROF_BEGIN()                                  \
+    do {                                              \
+        if (ctx->profiling) prof_mark(ctx, nullptr, st); \
     } while (0)
 
 uint32_t bitlen(uint64_t v) {
@@ -287,7 +313,7 @@ extern "C" void idn_gpu_destroy(idn_gpu_ctx* ctx) {
                       &ctx->w_readblock, &ctx->w_small, &ctx->w_crcpart, &ctx->w_crclen,     &ctx->w_index,  &ctx->w_blk,
                       &ctx->s_acids,   &ctx->s_quals,   &ctx->s_readoff, &ctx->s_blockfirst, &ctx->s_prefix, &ctx->s_names,
                       &ctx->s_nameoff, &ctx->s_out,     &ctx->s_blockoff, &ctx->s_crc,       &ctx->s_stats,  &ctx->s_sizes,
-                      &ctx->s_blocks,  &ctx->s_aout,    &ctx->s_qout,    &ctx->s_offout,     &ctx->s_status, &ctx->s_idx};
+                      &ctx->s_blocks,  &ctx->s_blocklen, &ctx->s_aout,    &ctx->s_qout,    &ctx->s_offout,     &ctx->s_status, &ctx->s_idx};
     for (DevBuf* b : bufs) b->release();
     cudaFree(ctx->d_models);
     cudaFree(ctx->d_crc_tab);
@@ -466,6 +492,7 @@ extern "C" int32_t idn_gpu_score_dev(idn_gpu_ctx* ctx, const idn_batch* batch, c
     if (!sizes) return fail(ctx, IDN_E_INVALID_ARG, "sizes is NULL");
     CU(cudaSetDevice(ctx->device));
     cudaStream_t st = as_stream(stream);
+    PROF_BEGIN();
     SmallParams sp;
     memset(&sp, 0, sizeof sp);
     for (uint32_t i = 0; i < n_models; i++) sp.score_ids[i] = models[i];
@@ -476,7 +503,7 @@ extern "C" int32_t idn_gpu_score_dev(idn_gpu_ctx* ctx, const idn_batch* batch, c
     score_kernel<<<(unsigned)((threads + 127) / 128), 128, 0, st>>>(ctx->d_models, dsp->score_ids, n_models, batch->acids,
                                                                    batch->quals, batch->read_off, batch->n_reads, sizes,
                                                                    &dsp->err);
-    LAUNCHED();
+    LAUNCHED("score");
     return IDN_OK;
 }
 
@@ -539,6 +566,7 @@ extern "C" int32_t idn_gpu_compress_blocks_dev(idn_gpu_ctx* ctx, const idn_batch
     if (batch->n_blocks == 0) return fail(ctx, IDN_E_INVALID_ARG, "batch has no blocks");
     CU(cudaSetDevice(ctx->device));
     cudaStream_t st = as_stream(stream);
+    PROF_BEGIN();
     const uint64_t R = batch->n_reads, S = batch->n_symbols;
     const uint32_t B = batch->n_blocks;
 
@@ -589,12 +617,12 @@ extern "C" int32_t idn_gpu_compress_blocks_dev(idn_gpu_ctx* ctx, const idn_batch
             score_kernel<<<(unsigned)((threads + 127) / 128), 128, 0, st>>>(ctx->d_models, dsp->score_ids, n_score,
                                                                            batch->acids, batch->quals, batch->read_off, R,
                                                                            ctx->w_sizes.as<uint32_t>(), &dsp->err);
-            LAUNCHED();
+            LAUNCHED("score");
         }
         if (!fast) {  // K3
             switch_kernel<<<2 * B, 32, 0, st>>>(ctx->w_sizes.as<uint32_t>(), n_score, dsp->cand_cols, dsp->n_cand,
                                                 dsp->has_sizes, batch->block_first_read, B, chosen, switched, R);
-            LAUNCHED();
+            LAUNCHED("switch");
         }
         EncodeArgs ea;  // K4
         ea.models = ctx->d_models;
@@ -610,7 +638,7 @@ extern "C" int32_t idn_gpu_compress_blocks_dev(idn_gpu_ctx* ctx, const idn_batch
         ea.pay_len = ctx->w_paylen.as<uint32_t>();
         ea.err = &dsp->err;
         encode_kernel<<<(unsigned)((R + 127) / 128), 128, 0, st>>>(ea);
-        LAUNCHED();
+        LAUNCHED("encode");
     }
 
     // slice offsets: exclusive scan of per-read slice sizes
@@ -619,22 +647,22 @@ extern "C" int32_t idn_gpu_compress_blocks_dev(idn_gpu_ctx* ctx, const idn_batch
     unsigned long long* slice_off = ctx->w_sliceoff.as<unsigned long long>();
     if (n_tiles) {
         scan_reduce_kernel<<<n_tiles, kScanBlock, 0, st>>>(fn, R, tiles);
-        LAUNCHED();
+        LAUNCHED("scan_reduce");
     }
     scan_tiles_kernel<<<1, kScanBlock, 0, st>>>(tiles, n_tiles);
-    LAUNCHED();
+    LAUNCHED("scan_tiles");
     if (n_tiles) {
         scan_apply_kernel<<<n_tiles, kScanBlock, 0, st>>>(fn, R, tiles, slice_off);
-        LAUNCHED();
+        LAUNCHED("scan_apply");
     } else {
         CU(cudaMemsetAsync(slice_off, 0, 8, st));
     }
     block_layout_kernel<<<1, 32, 0, st>>>(slice_off, batch->block_first_read, B, prefix_len, fast,
                                           reinterpret_cast<unsigned long long*>(block_off), out, out_cap, dsp->stats);
-    LAUNCHED();
+    LAUNCHED("block_layout");
     if (R > 0) {
         read_block_kernel<<<B, 256, 0, st>>>(batch->block_first_read, B, ctx->w_readblock.as<uint32_t>());
-        LAUNCHED();
+        LAUNCHED("read_block");
         AssembleArgs aa;
         aa.read_off = batch->read_off;
         aa.n_reads = R;
@@ -652,16 +680,16 @@ extern "C" int32_t idn_gpu_compress_blocks_dev(idn_gpu_ctx* ctx, const idn_batch
         aa.out = out;
         aa.out_cap = out_cap;
         assemble_kernel<<<(unsigned)((R * 32 + 255) / 256), 256, 0, st>>>(aa);
-        LAUNCHED();
+        LAUNCHED("assemble");
         stats_kernel<<<592, 256, 0, st>>>(ctx->w_paylen.as<uint32_t>(), switched, R, dsp->stats);
-        LAUNCHED();
+        LAUNCHED("stats");
     }
     // K7: block CRCs into the block headers
     rc = idn_gpu_block_crc_dev_impl(ctx, batch, block_crc, out, reinterpret_cast<unsigned long long*>(block_off), out_cap, st);
     if (rc) return rc;
     if (stats_dev) {
         finish_stats_kernel<<<1, 32, 0, st>>>(dsp->stats, &dsp->err, reinterpret_cast<unsigned long long*>(stats_dev));
-        LAUNCHED();
+        LAUNCHED("finish_stats");
     }
     return IDN_OK;
 }
@@ -676,12 +704,12 @@ static int32_t idn_gpu_block_crc_dev_impl(idn_gpu_ctx* ctx, const idn_batch* bat
             batch->acids, batch->quals, reinterpret_cast<const unsigned long long*>(batch->read_off), batch->names,
             reinterpret_cast<const unsigned long long*>(batch->name_off), R, nullptr, nullptr, ctx->d_crc_tab, ctx->d_xpow,
             ctx->w_crcpart.as<uint32_t>(), ctx->w_crclen.as<unsigned long long>());
-        LAUNCHED();
+        LAUNCHED("crc_read");
     }
     crc_block_kernel<<<batch->n_blocks, 256, 0, st>>>(ctx->w_crcpart.as<uint32_t>(), ctx->w_crclen.as<unsigned long long>(),
                                                       batch->block_first_read, batch->n_blocks, ctx->d_xpow, block_crc, out,
                                                       block_off, out_cap);
-    LAUNCHED();
+    LAUNCHED("crc_block");
     return IDN_OK;
 }
 
@@ -844,23 +872,23 @@ struct IndexView {  // per-read index arrays carved out of w_index for `cap` rea
 
 // shared by idn_gpu_index_blocks and the decoders: count pass + scan.  Leaves per-block read/symbol bases in w_blk:
 //   blk_reads[0..B] (exclusive scan, [B] = total), blk_syms[0..B]
-static int32_t index_count(idn_gpu_ctx* ctx, const uint8_t* blocks, const unsigned long long* block_off, uint32_t B,
-                           const SmallParams* dsp, uint32_t n_models, cudaStream_t st) {
+static int32_t index_count(idn_gpu_ctx* ctx, const uint8_t* blocks, const unsigned long long* block_off,
+                           const uint32_t* block_len, uint32_t B, uint64_t blocks_bytes, const SmallParams* dsp, uint32_t n_models, cudaStream_t st) {
     CU(ctx->w_blk.ensure(((size_t)B + 2) * 8 * 2));
     unsigned long long* blk_reads = ctx->w_blk.as<unsigned long long>();
     unsigned long long* blk_syms = blk_reads + B + 2;
-    index_count_kernel<<<(B + 31) / 32, 32, 0, st>>>(blocks, block_off, B, ctx->d_models, dsp->model_ids, n_models, blk_reads,
+    index_count_kernel<<<(B + 31) / 32, 32, 0, st>>>(blocks, block_off, block_len, B, blocks_bytes, ctx->d_models, dsp->model_ids, n_models, blk_reads,
                                                      blk_syms, const_cast<int32_t*>(dsp->status));
-    LAUNCHED();
+    LAUNCHED("index_count");
     scan_tiles_kernel<<<1, kScanBlock, 0, st>>>(blk_reads, B);
-    LAUNCHED();
+    LAUNCHED("scan_tiles");
     scan_tiles_kernel<<<1, kScanBlock, 0, st>>>(blk_syms, B);
-    LAUNCHED();
+    LAUNCHED("scan_tiles");
     return IDN_OK;
 }
 
 extern "C" int32_t idn_gpu_decompress_blocks_dev(idn_gpu_ctx* ctx, const uint8_t* blocks, const uint64_t* block_off,
-                                                 const uint32_t* block_crc, uint32_t n_blocks, uint64_t blocks_bytes,
+                                                 const uint32_t* block_len, const uint32_t* block_crc, uint32_t n_blocks, uint64_t blocks_bytes,
                                                  int32_t mode, const idn_model_t* models, uint32_t n_models,
                                                  uint8_t* acids_out, uint8_t* quals_out, uint64_t* read_off_out,
                                                  uint64_t out_reads_cap, uint64_t out_symbols_cap, int32_t* status_dev,
@@ -873,6 +901,7 @@ extern "C" int32_t idn_gpu_decompress_blocks_dev(idn_gpu_ctx* ctx, const uint8_t
     if (out_reads_cap >= (1ull << 32) - 2) return fail(ctx, IDN_E_INVALID_ARG, "out_reads_cap too large");
     CU(cudaSetDevice(ctx->device));
     cudaStream_t st = as_stream(stream);
+    PROF_BEGIN();
     SmallParams sp;
     memset(&sp, 0, sizeof sp);
     for (uint32_t i = 0; i < n_models; i++) sp.model_ids[i] = models[i];
@@ -882,7 +911,7 @@ extern "C" int32_t idn_gpu_decompress_blocks_dev(idn_gpu_ctx* ctx, const uint8_t
     SmallParams* dsp = ctx->w_small.as<SmallParams>();
     const unsigned long long* boff = reinterpret_cast<const unsigned long long*>(block_off);
     if (n_blocks) {
-        rc = index_count(ctx, blocks, boff, n_blocks, dsp, n_models, st);
+        rc = index_count(ctx, blocks, boff, block_len, n_blocks, blocks_bytes, dsp, n_models, st);
         if (rc) return rc;
     } else {
         CU(ctx->w_blk.ensure(4 * 8 * 2));
@@ -897,11 +926,11 @@ extern "C" int32_t idn_gpu_decompress_blocks_dev(idn_gpu_ctx* ctx, const uint8_t
     uint32_t* block_first = ctx->w_readblock.as<uint32_t>();
     // capacity check on the device; on failure the later kernels see n_reads = 0
     index_check_kernel<<<1, 32, 0, st>>>(blk_reads, blk_syms, n_blocks, out_reads_cap, out_symbols_cap, dsp->status);
-    LAUNCHED();
-    index_fill_kernel<<<(n_blocks + 1 + 31) / 32, 32, 0, st>>>(blocks, boff, n_blocks, ctx->d_models, dsp->model_ids, n_models,
+    LAUNCHED("index_check");
+    index_fill_kernel<<<(n_blocks + 1 + 31) / 32, 32, 0, st>>>(blocks, boff, block_len, n_blocks, ctx->d_models, dsp->model_ids, n_models,
                                                               blk_reads, blk_syms, iv.pay_off, iv.pay_len, iv.seq_len,
                                                               iv.out_off, iv.am, iv.qm, block_first, dsp->status);
-    LAUNCHED();
+    LAUNCHED("index_fill");
     DecodeArgs da;
     da.models = ctx->d_models;
     da.model_ids = dsp->model_ids;
@@ -921,7 +950,7 @@ extern "C" int32_t idn_gpu_decompress_blocks_dev(idn_gpu_ctx* ctx, const uint8_t
     da.err = &dsp->err;
     if (out_reads_cap) {
         decode_kernel<<<(unsigned)((out_reads_cap + 127) / 128), 128, 0, st>>>(da);
-        LAUNCHED();
+        LAUNCHED("decode");
     }
     // CRC of the decoded symbols per block, compared with the header value (decompressor_block.rs:131-144)
     if (block_crc && n_blocks && out_reads_cap) {
@@ -930,14 +959,26 @@ extern "C" int32_t idn_gpu_decompress_blocks_dev(idn_gpu_ctx* ctx, const uint8_t
         crc_read_kernel<<<(unsigned)((out_reads_cap + 127) / 128), 128, 0, st>>>(
             acids_out, quals_out, iv.out_off, nullptr, nullptr, 0, blk_reads + n_blocks, dsp->status, ctx->d_crc_tab,
             ctx->d_xpow, ctx->w_crcpart.as<uint32_t>(), ctx->w_crclen.as<unsigned long long>());
-        LAUNCHED();
+        LAUNCHED("crc_read");
         crc_verify_kernel<<<n_blocks, 256, 0, st>>>(ctx->w_crcpart.as<uint32_t>(), ctx->w_crclen.as<unsigned long long>(),
                                                     block_first, n_blocks, ctx->d_xpow, block_crc, dsp->status);
-        LAUNCHED();
+        LAUNCHED("crc_verify");
     }
     finish_decode_kernel<<<(unsigned)((out_reads_cap + 1 + 255) / 256), 256, 0, st>>>(
         dsp->status, &dsp->err, blk_reads + n_blocks, blk_syms + n_blocks, iv.out_off, reinterpret_cast<unsigned long long*>(read_off_out), out_reads_cap, status_dev);
-    LAUNCHED();
+    LAUNCHED("finish_decode");
+    return IDN_OK;
+}
+
+// block b = blocks[block_off[b] .. block_off[b] + len_b), len_b = block_len ? block_len[b] : block_off[b+1] - block_off[b];
+// block_off[n_blocks] = size of the `blocks` region.  With block_len the region may hold other bytes between
+// blocks (e.g. the 8-byte block headers of a container chunk copied as is).
+static int32_t check_block_table(idn_gpu_ctx* ctx, const uint64_t* block_off, const uint32_t* block_len, uint32_t n_blocks) {
+    for (uint32_t i = 0; i < n_blocks; i++) {
+        if (block_off[i + 1] < block_off[i]) return fail(ctx, IDN_E_INVALID_ARG, "block_off is not monotone");
+        if (block_len && block_off[i] + block_len[i] > block_off[n_blocks])
+            return fail(ctx, IDN_E_SERIALIZE, "block %u runs past the end of the input", i);
+    }
     return IDN_OK;
 }
 
@@ -953,8 +994,8 @@ static int32_t status_to_error(idn_gpu_ctx* ctx, const int32_t st[4]) {
     }
 }
 
-extern "C" int32_t idn_gpu_index_blocks(idn_gpu_ctx* ctx, const uint8_t* blocks, const uint64_t* block_off, uint32_t n_blocks,
-                                        const idn_model_t* models, uint32_t n_models, idn_block_index_totals* totals,
+extern "C" int32_t idn_gpu_index_blocks(idn_gpu_ctx* ctx, const uint8_t* blocks, const uint64_t* block_off,
+                                        const uint32_t* block_len, uint32_t n_blocks, const idn_model_t* models, uint32_t n_models, idn_block_index_totals* totals,
                                         uint32_t* block_first_read) {
     if (!ctx) return IDN_E_INVALID_ARG;
     int32_t rc = check_models(ctx, models, n_models);
@@ -963,16 +1004,18 @@ extern "C" int32_t idn_gpu_index_blocks(idn_gpu_ctx* ctx, const uint8_t* blocks,
     totals->n_reads = totals->n_symbols = 0;
     if (block_first_read) block_first_read[0] = 0;
     if (n_blocks == 0) return IDN_OK;
-    for (uint32_t i = 0; i < n_blocks; i++)
-        if (block_off[i + 1] < block_off[i]) return fail(ctx, IDN_E_INVALID_ARG, "block_off is not monotone");
+    int32_t rc0 = check_block_table(ctx, block_off, block_len, n_blocks);
+    if (rc0) return rc0;
     if (!blocks && block_off[n_blocks]) return fail(ctx, IDN_E_INVALID_ARG, "blocks is NULL");
     CU(cudaSetDevice(ctx->device));
     cudaStream_t st = ctx->stream;
     uint64_t nbytes = block_off[n_blocks];
     CU(ctx->s_blocks.ensure(nbytes + 16));
     CU(ctx->s_blockoff.ensure(((size_t)n_blocks + 1) * 8));
+    CU(ctx->s_blocklen.ensure(((size_t)n_blocks + 1) * 4));
     if (nbytes) CU(cudaMemcpyAsync(ctx->s_blocks.p, blocks, nbytes, cudaMemcpyHostToDevice, st));
     CU(cudaMemcpyAsync(ctx->s_blockoff.p, block_off, ((size_t)n_blocks + 1) * 8, cudaMemcpyHostToDevice, st));
+    if (block_len) CU(cudaMemcpyAsync(ctx->s_blocklen.p, block_len, (size_t)n_blocks * 4, cudaMemcpyHostToDevice, st));
     SmallParams sp;
     memset(&sp, 0, sizeof sp);
     for (uint32_t i = 0; i < n_models; i++) sp.model_ids[i] = models[i];
@@ -980,7 +1023,8 @@ extern "C" int32_t idn_gpu_index_blocks(idn_gpu_ctx* ctx, const uint8_t* blocks,
     rc = upload_small(ctx, sp, st);
     if (rc) return rc;
     SmallParams* dsp = ctx->w_small.as<SmallParams>();
-    rc = index_count(ctx, ctx->s_blocks.as<uint8_t>(), ctx->s_blockoff.as<unsigned long long>(), n_blocks, dsp, n_models, st);
+    rc = index_count(ctx, ctx->s_blocks.as<uint8_t>(), ctx->s_blockoff.as<unsigned long long>(),
+                     block_len ? ctx->s_blocklen.as<uint32_t>() : nullptr, n_blocks, nbytes, dsp, n_models, st);
     if (rc) return rc;
     std::vector<unsigned long long> hr(n_blocks + 1), hsym(n_blocks + 1);
     int32_t hst[4];
@@ -998,7 +1042,7 @@ extern "C" int32_t idn_gpu_index_blocks(idn_gpu_ctx* ctx, const uint8_t* blocks,
 }
 
 extern "C" int32_t idn_gpu_decompress_blocks(idn_gpu_ctx* ctx, const uint8_t* blocks, const uint64_t* block_off,
-                                             const uint32_t* block_crc, uint32_t n_blocks, int32_t mode,
+                                             const uint32_t* block_len, const uint32_t* block_crc, uint32_t n_blocks, int32_t mode,
                                              const idn_model_t* models, uint32_t n_models, const uint8_t* names,
                                              const uint64_t* name_off, uint8_t* acids_out, uint8_t* quals_out,
                                              uint64_t* read_off_out, uint64_t out_reads_cap, uint64_t out_symbols_cap,
@@ -1008,8 +1052,8 @@ extern "C" int32_t idn_gpu_decompress_blocks(idn_gpu_ctx* ctx, const uint8_t* bl
     if (!block_off || !read_off_out) return fail(ctx, IDN_E_INVALID_ARG, "NULL argument");
     if ((names != nullptr) != (name_off != nullptr)) return fail(ctx, IDN_E_INVALID_ARG, "names and name_off go together");
     if (out_symbols_cap && (!acids_out || !quals_out)) return fail(ctx, IDN_E_INVALID_ARG, "NULL output");
-    for (uint32_t i = 0; i < n_blocks; i++)
-        if (block_off[i + 1] < block_off[i]) return fail(ctx, IDN_E_INVALID_ARG, "block_off is not monotone");
+    int32_t rc0 = check_block_table(ctx, block_off, block_len, n_blocks);
+    if (rc0) return rc0;
     uint64_t nbytes = n_blocks ? block_off[n_blocks] : 0;
     if (!blocks && nbytes) return fail(ctx, IDN_E_INVALID_ARG, "blocks is NULL");
     CU(cudaSetDevice(ctx->device));
@@ -1023,13 +1067,15 @@ extern "C" int32_t idn_gpu_decompress_blocks(idn_gpu_ctx* ctx, const uint8_t* bl
     CU(ctx->s_status.ensure(64));
     if (nbytes) CU(cudaMemcpyAsync(ctx->s_blocks.p, blocks, nbytes, cudaMemcpyHostToDevice, st));
     CU(cudaMemcpyAsync(ctx->s_blockoff.p, block_off, ((size_t)n_blocks + 1) * 8, cudaMemcpyHostToDevice, st));
+    CU(ctx->s_blocklen.ensure(((size_t)n_blocks + 1) * 4));
+    if (block_len && n_blocks) CU(cudaMemcpyAsync(ctx->s_blocklen.p, block_len, (size_t)n_blocks * 4, cudaMemcpyHostToDevice, st));
     // names join the block CRC (sequence.rs:381-394): when given, the device verifies symbols only and the name bytes are
     // folded in on the host below; otherwise the device compares against the header directly.
     const bool host_crc = names != nullptr;
     if (block_crc && !host_crc && n_blocks)
         CU(cudaMemcpyAsync(ctx->s_crc.p, block_crc, (size_t)n_blocks * 4, cudaMemcpyHostToDevice, st));
     int32_t rc = idn_gpu_decompress_blocks_dev(ctx, ctx->s_blocks.as<uint8_t>(), ctx->s_blockoff.as<uint64_t>(),
-                                               (block_crc && !host_crc) ? ctx->s_crc.as<uint32_t>() : nullptr, n_blocks, nbytes,
+                                               block_len ? ctx->s_blocklen.as<uint32_t>() : nullptr, (block_crc && !host_crc) ? ctx->s_crc.as<uint32_t>() : nullptr, n_blocks, nbytes,
                                                mode, models, n_models, ctx->s_aout.as<uint8_t>(), ctx->s_qout.as<uint8_t>(),
                                                ctx->s_offout.as<uint64_t>(), out_reads_cap, out_symbols_cap,
                                                ctx->s_status.as<int32_t>(), st);
@@ -1148,7 +1194,7 @@ extern "C" int32_t idn_gpu_decompress_reads(idn_gpu_ctx* ctx, const uint8_t* pay
     da.read_status = ctx->s_idx.as<uint32_t>();
     da.err = &dsp->err;
     decode_kernel<<<(unsigned)((R + 127) / 128), 128, 0, st>>>(da);
-    LAUNCHED();
+    LAUNCHED("decode");
     uint32_t err = 0;
     if (S) {
         CU(cudaMemcpyAsync(acids_out, ctx->s_aout.p, S, cudaMemcpyDeviceToHost, st));
@@ -1158,5 +1204,77 @@ extern "C" int32_t idn_gpu_decompress_reads(idn_gpu_ctx* ctx, const uint8_t* pay
     CU(cudaMemcpyAsync(&err, &dsp->err, 4, cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
     if (err & 1) return fail(ctx, IDN_E_SERIALIZE, "a sequence payload ended before its symbols were decoded");
+    return IDN_OK;
+}
+
+// ======================================================================================================
+// workload generator (bench/test utility)
+// ======================================================================================================
+extern "C" int32_t idn_gpu_synth_reads_dev(idn_gpu_ctx* ctx, idn_model_t acid_model, idn_model_t q_model,
+                                           const uint64_t* read_off, uint64_t n_reads, uint64_t first_read_index,
+                                           uint64_t seed, uint32_t n_ppm, uint8_t* acids, uint8_t* quals, void* stream) {
+    if (!ctx) return IDN_E_INVALID_ARG;
+    idn_model_t pair[2] = {acid_model, q_model};
+    int32_t rc = check_models(ctx, pair, 2);
+    if (rc) return rc;
+    if (ctx->slots[acid_model].dev.type != IDN_MODEL_ACID || ctx->slots[q_model].dev.type != IDN_MODEL_QSCORE)
+        return fail(ctx, IDN_E_INVALID_ARG, "need an acid model and a quality score model, in that order");
+    if (n_reads == 0) return IDN_OK;
+    if (!read_off || !acids || !quals) return fail(ctx, IDN_E_INVALID_ARG, "NULL argument");
+    CU(cudaSetDevice(ctx->device));
+    cudaStream_t st = as_stream(stream);
+    PROF_BEGIN();
+    synth_kernel<<<(unsigned)((n_reads + 127) / 128), 128, 0, st>>>(
+        ctx->d_models, acid_model, q_model, reinterpret_cast<const unsigned long long*>(read_off), n_reads, first_read_index,
+        seed, n_ppm, acids, quals);
+    LAUNCHED("synth");
+    return IDN_OK;
+}
+
+// ======================================================================================================
+// per-kernel timing
+// ======================================================================================================
+extern "C" int32_t idn_gpu_profile(idn_gpu_ctx* ctx, int32_t enable) {
+    if (!ctx) return IDN_E_INVALID_ARG;
+    ctx->profiling = enable != 0;
+    ctx->prof_marks.clear();
+    ctx->prof_used = 0;
+    return IDN_OK;
+}
+
+extern "C" int32_t idn_gpu_profile_read(idn_gpu_ctx* ctx, char* buf, uint64_t cap) {
+    if (!ctx || !buf || cap == 0) return IDN_E_INVALID_ARG;
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaDeviceSynchronize());
+    struct Acc {
+        const char* name;
+        uint64_t n;
+        double ms;
+    };
+    std::vector<Acc> acc;
+    for (size_t i = 1; i < ctx->prof_marks.size(); i++) {
+        const auto& m = ctx->prof_marks[i];
+        if (!m.name) continue;
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, ctx->prof_marks[i - 1].ev, m.ev) != cudaSuccess) {
+            (void)cudaGetLastError();
+            continue;
+        }
+        size_t k = 0;
+        while (k < acc.size() && strcmp(acc[k].name, m.name) != 0) k++;
+        if (k == acc.size()) acc.push_back({m.name, 0, 0.0});
+        acc[k].n++;
+        acc[k].ms += ms;
+    }
+    std::string out;
+    char line[160];
+    for (auto& a : acc) {
+        snprintf(line, sizeof line, "%s %llu %.6f\n", a.name, (unsigned long long)a.n, a.ms);
+        out += line;
+    }
+    ctx->prof_marks.clear();
+    ctx->prof_used = 0;
+    if (out.size() + 1 > cap) return fail(ctx, IDN_E_NOSPACE, "profile text needs %zu bytes", out.size() + 1);
+    memcpy(buf, out.c_str(), out.size() + 1);
     return IDN_OK;
 }

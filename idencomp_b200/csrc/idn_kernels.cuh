@@ -17,9 +17,15 @@ namespace idn {
 // divergent traffic at one 32-byte sector per 32 bytes instead of one per byte)
 // ---------------------------------------------------------------------------------------------------
 struct BackReader {  // reads bytes at decreasing global indices
-    const uint8_t* base;
-    uint32_t word;
+    const uint8_t* base;  // rounded down to a 4-byte boundary; `mis` bytes were dropped
+    uint32_t word, mis;
+    __device__ __forceinline__ void init(const uint8_t* b) {
+        mis = (uint32_t)(reinterpret_cast<uintptr_t>(b) & 3);
+        base = b - mis;
+        word = 0xffffffffu;
+    }
     __device__ __forceinline__ uint32_t get(long long g) {  // g may be < first valid index -> caller guards
+        g += mis;
         uint32_t sh = (uint32_t)(g & 3) * 8;
         if (sh == 24 || word == 0xffffffffu) word = __ldg(reinterpret_cast<const uint32_t*>(base + (g & ~3ll)));
         return (word >> sh) & 0xffu;
@@ -27,15 +33,17 @@ struct BackReader {  // reads bytes at decreasing global indices
 };
 
 struct FwdReader {  // reads bytes at increasing global indices
-    const uint8_t* base;
-    uint32_t word;
+    const uint8_t* base;  // rounded down to a 4-byte boundary; `mis` bytes were dropped
+    uint32_t word, mis;
     bool primed;
     __device__ __forceinline__ void init(const uint8_t* b) {
-        base = b;
+        mis = (uint32_t)(reinterpret_cast<uintptr_t>(b) & 3);
+        base = b - mis;
         primed = false;
         word = 0;
     }
     __device__ __forceinline__ uint32_t get(unsigned long long g) {
+        g += mis;
         uint32_t sh = (uint32_t)(g & 3) * 8;
         if (sh == 0 || !primed) {
             word = __ldg(reinterpret_cast<const uint32_t*>(base + (g & ~3ull)));
@@ -249,7 +257,9 @@ encode_kernel(EncodeArgs A) {
     const uint32_t len = (uint32_t)(A.read_off[r + 1] - A.read_off[r]);
     uint8_t* slot_end = A.scratch + 4ull * A.read_off[r + 1] + 8ull * (r + 1);
 
-    BackReader ra{A.acids, 0xffffffffu}, rq{A.quals, 0xffffffffu};
+    BackReader ra, rq;
+    ra.init(A.acids);
+    rq.init(A.quals);
     SymWindow w;
     w.init();
     bool bad = false;
@@ -771,14 +781,18 @@ __device__ __forceinline__ WalkResult walk_block(const uint8_t* __restrict__ p, 
 }
 
 __global__ void __launch_bounds__(32)
-index_count_kernel(const uint8_t* __restrict__ blocks, const unsigned long long* __restrict__ block_off, uint32_t n_blocks,
+index_count_kernel(const uint8_t* __restrict__ blocks, const unsigned long long* __restrict__ block_off,
+                   const uint32_t* __restrict__ block_len, uint32_t n_blocks, unsigned long long blocks_bytes,
                    const ModelDev* __restrict__ models, const int32_t* __restrict__ model_ids, uint32_t n_models,
                    unsigned long long* __restrict__ blk_reads, unsigned long long* __restrict__ blk_syms,
                    int32_t* __restrict__ status /*[2]: code, block*/) {
     uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= n_blocks) return;
-    WalkResult w = walk_block<false>(blocks + block_off[b], block_off[b + 1] - block_off[b], models, model_ids, n_models,
-                                     0, 0, 0, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr);
+    unsigned long long n = block_len ? block_len[b] : block_off[b + 1] - block_off[b];
+    WalkResult w{0, 0, 3};  // a block that runs past the input is malformed
+    if (block_off[b] <= blocks_bytes && n <= blocks_bytes - block_off[b])
+        w = walk_block<false>(blocks + block_off[b], n, models, model_ids, n_models, 0, 0, 0, nullptr, nullptr, nullptr, nullptr,
+                              nullptr, nullptr);
     blk_reads[b] = w.n_reads;
     blk_syms[b] = w.n_symbols;
     if (w.status != 0) {
@@ -788,8 +802,8 @@ index_count_kernel(const uint8_t* __restrict__ blocks, const unsigned long long*
 }
 
 __global__ void __launch_bounds__(32)
-index_fill_kernel(const uint8_t* __restrict__ blocks, const unsigned long long* __restrict__ block_off, uint32_t n_blocks,
-                  const ModelDev* __restrict__ models, const int32_t* __restrict__ model_ids, uint32_t n_models,
+index_fill_kernel(const uint8_t* __restrict__ blocks, const unsigned long long* __restrict__ block_off,
+                  const uint32_t* __restrict__ block_len, uint32_t n_blocks, const ModelDev* __restrict__ models, const int32_t* __restrict__ model_ids, uint32_t n_models,
                   const unsigned long long* __restrict__ blk_read_base, const unsigned long long* __restrict__ blk_sym_base,
                   unsigned long long* __restrict__ pay_off, uint32_t* __restrict__ pay_len, uint32_t* __restrict__ seq_len,
                   unsigned long long* __restrict__ out_off, uint8_t* __restrict__ am, uint8_t* __restrict__ qm,
@@ -802,7 +816,7 @@ index_fill_kernel(const uint8_t* __restrict__ blocks, const unsigned long long* 
         return;
     }
     if (block_first) block_first[b] = (uint32_t)blk_read_base[b];
-    walk_block<true>(blocks + block_off[b], block_off[b + 1] - block_off[b], models, model_ids, n_models, block_off[b],
+    walk_block<true>(blocks + block_off[b], block_len ? block_len[b] : block_off[b + 1] - block_off[b], models, model_ids, n_models, block_off[b],
                      blk_read_base[b], blk_sym_base[b], pay_off, pay_len, seq_len, out_off, am, qm);
 }
 
@@ -926,6 +940,58 @@ finish_decode_kernel(const int32_t* __restrict__ status, const uint32_t* __restr
         status_dev[3] = (int32_t)(*n_syms_total & 0x7fffffffull);
     }
     if (code == 0 && read_off_out && i <= R && i <= reads_cap) read_off_out[i] = out_off[i];
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Workload generator (bench/test utility, not on the reference's path): model-driven synthetic reads.
+// Every symbol is drawn from the model's own distribution for the context the generators are in
+// (SURVEY.md 8d), so the coder sees the statistics the models were trained on instead of the uniform
+// dummy context.  One thread per read; RNG = SplitMix64 keyed by (seed, read index).
+// ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned long long splitmix64(unsigned long long& s) {
+    unsigned long long z = (s += 0x9E3779B97F4A7C15ull);
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+}
+
+__global__ void __launch_bounds__(128)
+synth_kernel(const ModelDev* __restrict__ models, int32_t ia, int32_t iq, const unsigned long long* __restrict__ read_off,
+             uint64_t n_reads, uint64_t first_read_index, unsigned long long seed, uint32_t n_ppm,
+             uint8_t* __restrict__ acids, uint8_t* __restrict__ quals) {
+    uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n_reads) return;
+    const ModelDev& ma = models[ia];
+    const ModelDev& mq = models[iq];
+    unsigned long long off = read_off[r];
+    uint32_t len = (uint32_t)(read_off[r + 1] - off);
+    unsigned long long s = seed ^ ((first_read_index + r + 1) * 0xD1B54A32D192ED03ull);
+    GenFwd ga, gq;
+    ga.init();
+    gq.init();
+    FwdWriter oa, oq;
+    oa.init(acids + off);
+    oq.init(quals + off);
+    for (uint32_t i = 0; i < len; i++) {
+        unsigned long long u = splitmix64(s);
+        uint32_t slot_a = (uint32_t)u & kSlotMask, slot_q = (uint32_t)(u >> 14) & kSlotMask;
+        uint32_t start, freq;
+        uint32_t row_a = ctx_row(ma, ga.spec(ma.spec));
+        uint32_t row_q = ctx_row(mq, gq.spec(mq.spec));
+        uint2 pk = __ldg(reinterpret_cast<const uint2*>(ma.dec) + row_a);
+        uint32_t a = acid_find(pk, slot_a, start, freq);
+        uint32_t q = q_find(mq.dec + (size_t)row_q * kQRowStride, slot_q, start, freq);
+        if ((uint32_t)((u >> 32) % 1000000u) < n_ppm) {  // an N call with the Illumina "no call" quality '#'
+            a = 0;
+            q = 2;
+        }
+        oa.push(a);
+        oq.push(q);
+        ga.update(ma.spec, a, q, len);
+        gq.update(mq.spec, a, q, len);
+    }
+    oa.finish();
+    oq.finish();
 }
 
 }  // namespace idn

@@ -137,8 +137,10 @@ int32_t idn_gpu_compress_blocks_dev(idn_gpu_ctx *ctx, const idn_batch *batch, in
 uint64_t idn_gpu_compress_bound(uint64_t n_reads, uint64_t n_symbols, uint32_t n_blocks, uint64_t prefix_total);
 
 /* a9+a11: decompress a batch of blocks given as container bytes.
- * `blocks` holds the block payloads back to back (WITHOUT the 8-byte block headers); block b is
- * blocks[block_off[b] .. block_off[b+1]) and block_crc[b] its header checksum.  The library walks the
+ * Block b's payload (the slices, WITHOUT its 8-byte block header) is blocks[block_off[b] .. block_off[b] + len_b) with
+ * len_b = block_len ? block_len[b] : block_off[b+1] - block_off[b]; block_off[n_blocks] is the size of the `blocks`
+ * region and block_crc[b] the block's header checksum.  With block_len the region may hold other bytes between the
+ * payloads, so a chunk of an .idn file can be passed as it lies on disk (block_off[b] = header position + 8).  The library walks the
  * slices (Identifiers slices are skipped: names stay on the host), tracks the active models per type
  * (decompressor_block.rs:194-214), decodes every Sequence slice and verifies the CRC of the symbols
  * (names, if any, are passed per read through `names`/`name_off` after the host inflated them; NULL =
@@ -151,16 +153,16 @@ typedef struct {
 } idn_block_index_totals;
 
 int32_t idn_gpu_index_blocks(idn_gpu_ctx *ctx, const uint8_t *blocks, const uint64_t *block_off,
-                             uint32_t n_blocks, const idn_model_t *models, uint32_t n_models,
+                             const uint32_t *block_len /* optional */, uint32_t n_blocks, const idn_model_t *models, uint32_t n_models,
                              idn_block_index_totals *totals, uint32_t *block_first_read /*[n_blocks+1], optional*/);
 int32_t idn_gpu_decompress_blocks(idn_gpu_ctx *ctx, const uint8_t *blocks, const uint64_t *block_off,
-                                  const uint32_t *block_crc, uint32_t n_blocks, int32_t mode,
+                                  const uint32_t *block_len /* optional */, const uint32_t *block_crc, uint32_t n_blocks, int32_t mode,
                                   const idn_model_t *models, uint32_t n_models, const uint8_t *names,
                                   const uint64_t *name_off, uint8_t *acids_out, uint8_t *quals_out,
                                   uint64_t *read_off_out /*[n_reads+1]*/, uint64_t out_reads_cap,
                                   uint64_t out_symbols_cap, int32_t *bad_block /* first failing block or -1 */);
 int32_t idn_gpu_decompress_blocks_dev(idn_gpu_ctx *ctx, const uint8_t *blocks, const uint64_t *block_off,
-                                      const uint32_t *block_crc, uint32_t n_blocks, uint64_t blocks_bytes,
+                                      const uint32_t *block_len /* optional */, const uint32_t *block_crc, uint32_t n_blocks, uint64_t blocks_bytes,
                                       int32_t mode, const idn_model_t *models, uint32_t n_models,
                                       uint8_t *acids_out, uint8_t *quals_out, uint64_t *read_off_out,
                                       uint64_t out_reads_cap, uint64_t out_symbols_cap,
@@ -186,6 +188,22 @@ int32_t idn_gpu_decompress_reads(idn_gpu_ctx *ctx, const uint8_t *payload, uint6
 /* IEEE CRC-32 of the per-read stream name|acids|quals for each block (writer_block.rs:64,
  * sequence.rs:381-394), computed on the device. */
 int32_t idn_gpu_block_crc(idn_gpu_ctx *ctx, const idn_batch *batch, uint32_t *block_crc);
+
+/* ---- workload generator (bench/test utility; nothing in the reference corresponds to it) -------------
+ * Fills acids/quals (DEVICE pointers) with model-driven synthetic reads: each symbol is sampled from the
+ * distribution `acid_model` / `q_model` hold for the context the read is in, `n_ppm` per
+ * million positions become an N call with quality 2.  Deterministic in (seed, first_read_index + r). */
+int32_t idn_gpu_synth_reads_dev(idn_gpu_ctx *ctx, idn_model_t acid_model, idn_model_t q_model,
+                                const uint64_t *read_off /* device, [n_reads+1] */, uint64_t n_reads,
+                                uint64_t first_read_index, uint64_t seed, uint32_t n_ppm, uint8_t *acids,
+                                uint8_t *quals, void *stream);
+
+/* ---- per-kernel timing (CUDA events on the launching stream; what bench.py's roofline line is made of) ----
+ * idn_gpu_profile(ctx, 1) starts recording an event after every kernel launch of the *_dev entry points;
+ * idn_gpu_profile_read synchronises the device and writes one text line per kernel, "name launches total_ms",
+ * then clears the record. */
+int32_t idn_gpu_profile(idn_gpu_ctx *ctx, int32_t enable);
+int32_t idn_gpu_profile_read(idn_gpu_ctx *ctx, char *buf, uint64_t cap);
 
 #ifdef __cplusplus
 }

@@ -1202,3 +1202,72 @@ int orc_fastq_write(const orc_reads_t *in, orc_buf_t *out) {
     }
     return ORC_OK;
 }
+
+/* ------------------------------------------------------------------------------------------------
+ * Workload generator (bench/test utility): model-driven synthetic reads.  Restates the
+ * sampler of the device library's workload generator so that the CPU baseline and the GPU path can be
+ * fed identical inputs without copying between them: SplitMix64 keyed by (seed, read index), one draw
+ * per position: acid slot = bits 0..13, q slot = bits 14..27, N-injection = (bits 32..63) % 1e6 < n_ppm.
+ * ---------------------------------------------------------------------------------------------- */
+static uint64_t splitmix64(uint64_t *s) {
+    uint64_t z = (*s += 0x9E3779B97F4A7C15ull);
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+}
+
+static uint32_t sym_for_slot(const orc_model_t *m, uint32_t row, uint32_t slot) {
+    const uint16_t *c = m->cum + (size_t)row * (m->nsym + 1);
+    uint32_t lo = 0, hi = m->nsym; /* largest s with c[s] <= slot */
+    while (hi - lo > 1) {
+        uint32_t mid = (lo + hi) / 2;
+        if (c[mid] <= slot) lo = mid; else hi = mid;
+    }
+    return lo;
+}
+
+typedef struct {
+    const orc_model_t *am, *qm;
+    const uint64_t *read_off;
+    uint64_t n_reads, first_read_index, seed;
+    uint32_t n_ppm;
+    uint8_t *acids, *quals;
+} synth_job_t;
+
+static int synth_chunk(void *vc, uint64_t chunk) {
+    synth_job_t *j = (synth_job_t *)vc;
+    uint64_t r0 = chunk * 4096, r1 = r0 + 4096;
+    if (r1 > j->n_reads) r1 = j->n_reads;
+    for (uint64_t r = r0; r < r1; r++) {
+        uint64_t off = j->read_off[r];
+        uint32_t len = (uint32_t)(j->read_off[r + 1] - off);
+        uint64_t s = j->seed ^ ((j->first_read_index + r + 1) * 0xD1B54A32D192ED03ull);
+        orc_gen_t ga, gq;
+        orc_gen_init(&ga, &j->am->spec, len);
+        orc_gen_init(&gq, &j->qm->spec, len);
+        for (uint32_t i = 0; i < len; i++) {
+            uint64_t u = splitmix64(&s);
+            uint32_t slot_a = (uint32_t)u & 0x3fffu, slot_q = (uint32_t)(u >> 14) & 0x3fffu;
+            uint32_t a = sym_for_slot(j->am, ctx_for(j->am, orc_gen_current(&ga)), slot_a);
+            uint32_t q = sym_for_slot(j->qm, ctx_for(j->qm, orc_gen_current(&gq)), slot_q);
+            if ((uint32_t)((u >> 32) % 1000000u) < j->n_ppm) {
+                a = 0;
+                q = 2;
+            }
+            j->acids[off + i] = (uint8_t)a;
+            j->quals[off + i] = (uint8_t)q;
+            orc_gen_update(&ga, (uint8_t)a, (uint8_t)q);
+            orc_gen_update(&gq, (uint8_t)a, (uint8_t)q);
+        }
+    }
+    return 0;
+}
+
+int orc_synth_reads(const orc_model_t *am, const orc_model_t *qm, const uint64_t *read_off, uint64_t n_reads,
+                    uint64_t first_read_index, uint64_t seed, uint32_t n_ppm, int threads, uint8_t *acids,
+                    uint8_t *quals) {
+    if (am->type != ORC_TYPE_ACID || qm->type != ORC_TYPE_QSCORE)
+        return fail(ORC_E_INVALID_STATE, "need an acid model and a quality score model");
+    synth_job_t j = {am, qm, read_off, n_reads, first_read_index, seed, n_ppm, acids, quals};
+    return pool_run(threads, (n_reads + 4095) / 4096, synth_chunk, &j);
+}

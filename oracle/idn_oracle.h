@@ -167,6 +167,11 @@ int orc_decompress(const orc_model_t *const *models, uint32_t n_models, const ui
 int orc_fastq_parse(const uint8_t *text, size_t n, orc_decoded_t *out);
 int orc_fastq_write(const orc_reads_t *in, orc_buf_t *out);
 
+/* workload generator (bench/test utility): same sampler as the device library's, see idn_oracle.c */
+int orc_synth_reads(const orc_model_t *am, const orc_model_t *qm, const uint64_t *read_off, uint64_t n_reads,
+                    uint64_t first_read_index, uint64_t seed, uint32_t n_ppm, int threads, uint8_t *acids,
+                    uint8_t *quals);
+
 uint32_t orc_crc32(uint32_t crc, const uint8_t *p, size_t n);
 const char *orc_last_error(void);
 

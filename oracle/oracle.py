@@ -122,6 +122,8 @@ def lib():
         L.orc_fastq_write.argtypes = [C.POINTER(_Reads), C.POINTER(_Buf)]
         L.orc_buf_free.argtypes = [C.POINTER(_Buf)]
         L.orc_decoded_free.argtypes = [C.POINTER(_Decoded)]
+        L.orc_synth_reads.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint32,
+                                      C.c_int, C.c_void_p, C.c_void_p]
         L.orc_crc32.restype = C.c_uint32
         L.orc_crc32.argtypes = [C.c_uint32, C.c_void_p, C.c_size_t]
         _LIB = L
@@ -465,6 +467,18 @@ def decompress(models, idn: bytes, threads: int = 0, return_info: bool = False):
 # ---------------------------------------------------------------------------------------------
 # the reference's toy models (_internal_test_data.rs:245-304), rebuilt from their definitions
 # ---------------------------------------------------------------------------------------------
+def synth_reads(am: "Model", qm: "Model", read_off, first_read_index: int, seed: int, n_ppm: int,
+                threads: int = 0) -> "Reads":
+    """Model-driven synthetic reads (bench/test utility); same sampler as idn_gpu_synth_reads_dev."""
+    ro = np.ascontiguousarray(read_off, dtype=np.uint64)
+    n = int(ro[-1])
+    a = np.zeros(max(n, 1), dtype=np.uint8)
+    q = np.zeros(max(n, 1), dtype=np.uint8)
+    _check(lib().orc_synth_reads(am.h, qm.h, ro.ctypes.data, len(ro) - 1, first_read_index, seed, n_ppm, threads,
+                                 a.ctypes.data, q.ctypes.data))
+    return Reads(ro, a[:n], q[:n], None, None)
+
+
 def simple_acid_model() -> ModelData:
     """create_simple_acid_model (_internal_test_data.rs:245-262): generic_ao1_qo0_pb0, specs = acid value."""
     ctxs = [([1], [0.00, 0.80, 0.10, 0.05, 0.05]), ([2], [0.00, 0.25, 0.50, 0.15, 0.10]),

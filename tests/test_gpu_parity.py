@@ -302,3 +302,84 @@ def test_errors(gctx, O, toy_models, toy_handles, reads_1k):
     with pytest.raises(IdnGpuError) as e:
         gctx.compress_blocks(reads_1k.read_off, reads_1k.acids, reads_1k.quals, bf, [999, 998])
     assert e.value.kind == "UnknownModel"
+
+
+# ---- workload generator + container chunks passed as they lie on disk ------------------------------------------
+def test_synth_reads_match_oracle_sampler(gctx, O, bundled):
+    """idn_gpu_synth_reads_dev draws the same reads as the oracle's sampler (same SplitMix64 stream, same slot ->
+    symbol search), so the CPU baseline and the GPU path of bench.py are fed identical inputs."""
+    import ctypes as C
+
+    import torch
+    am, ha = bundled["ERR174310__human__illumina_hiseq_2000__acids"]
+    qm, hq = bundled["SRR2962693__human__illumina_hiseq_2500__q_scores"]
+    rng = np.random.default_rng(5)
+    lens = rng.integers(0, 300, size=3000).astype(np.uint64)
+    ro = np.zeros(len(lens) + 1, dtype=np.uint64)
+    np.cumsum(lens, out=ro[1:])
+    want = O.synth_reads(am, qm, ro, 1234, 20240601, 500)
+    S = int(ro[-1])
+    ro_d = torch.from_numpy(ro.view(np.int64)).cuda()
+    a_d = torch.zeros(S + 16, dtype=torch.uint8, device="cuda")
+    q_d = torch.zeros(S + 16, dtype=torch.uint8, device="cuda")
+    sp = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    gctx.check(gctx.L.idn_gpu_synth_reads_dev(gctx.h, ha, hq, ro_d.data_ptr(), len(lens), 1234, 20240601, 500,
+                                              a_d.data_ptr(), q_d.data_ptr(), sp))
+    torch.cuda.synchronize()
+    assert np.array_equal(a_d[:S].cpu().numpy(), want.acids)
+    assert np.array_equal(q_d[:S].cpu().numpy(), want.quals)
+
+
+def test_decode_container_chunk_in_place(gctx, O, toy_models, toy_handles, reads_1k):
+    """block_len lets the caller pass container bytes with the 8-byte block headers left in between the payloads."""
+    bf = blocks_of(reads_1k, 10000)
+    out, block_off, crc, _ = gctx.compress_blocks(reads_1k.read_off, reads_1k.acids, reads_1k.quals, bf, toy_handles)
+    nb = len(bf) - 1
+    doff = np.append(block_off[:-1] + 8, block_off[-1]).astype(np.uint64)
+    dlen = (block_off[1:] - block_off[:-1] - 8).astype(np.uint32)
+    ro, a, q = gctx.decompress_blocks(out, doff, crc, toy_handles, block_len=dlen)
+    assert np.array_equal(ro, reads_1k.read_off) and np.array_equal(a, reads_1k.acids) and np.array_equal(q, reads_1k.quals)
+    # a block that claims to run past the input is a malformed container, not an out-of-bounds read
+    from idencomp_b200.capi import IdnGpuError
+    bad = dlen.copy()
+    bad[nb - 1] += 64
+    with pytest.raises(IdnGpuError) as e:
+        gctx.decompress_blocks(out, doff, crc, toy_handles, block_len=bad)
+    assert e.value.kind == "SerializeError"
+
+
+def test_unaligned_batch_pointers(gctx, O, toy_models, toy_handles, reads_1k):
+    """Device entry points accept symbol arrays at any byte alignment (chunks of a larger resident batch)."""
+    import ctypes as C
+
+    import torch
+    from idencomp_b200 import capi
+    S = int(reads_1k.read_off[-1])
+    for shift in (1, 2, 3):
+        a_d = torch.zeros(S + 32, dtype=torch.uint8, device="cuda")
+        q_d = torch.zeros(S + 32, dtype=torch.uint8, device="cuda")
+        a_d[shift:shift + S] = torch.from_numpy(reads_1k.acids).cuda()
+        q_d[shift + 4:shift + 4 + S] = torch.from_numpy(reads_1k.quals).cuda()
+        ro_d = torch.from_numpy(reads_1k.read_off.view(np.int64)).cuda()
+        bf = blocks_of(reads_1k, 20000)
+        bf_d = torch.from_numpy(bf.astype(np.int32)).cuda()
+        nb = len(bf) - 1
+        cap = int(gctx.L.idn_gpu_compress_bound(reads_1k.n_reads, S, nb, 0))
+        out_d = torch.zeros(cap + 16, dtype=torch.uint8, device="cuda")
+        boff_d = torch.zeros(nb + 1, dtype=torch.int64, device="cuda")
+        crc_d = torch.zeros(nb, dtype=torch.int32, device="cuda")
+        st_d = torch.zeros(8, dtype=torch.int64, device="cuda")
+        b = capi.Batch()
+        b.n_reads, b.n_symbols, b.n_blocks = reads_1k.n_reads, S, nb
+        b.acids, b.quals = a_d.data_ptr() + shift, q_d.data_ptr() + shift + 4
+        b.read_off, b.block_first_read = ro_d.data_ptr(), bf_d.data_ptr()
+        hd = np.asarray(toy_handles, dtype=np.int32)
+        sp = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+        gctx.check(gctx.L.idn_gpu_compress_blocks_dev(gctx.h, C.byref(b), capi.MODE_COMPAT, hd.ctypes.data, 2, 0, None,
+                                                      out_d.data_ptr(), cap, boff_d.data_ptr(), crc_d.data_ptr(),
+                                                      st_d.data_ptr(), sp))
+        torch.cuda.synchronize()
+        n = int(st_d[0])
+        got = out_d[:n].cpu().numpy().tobytes()
+        ref = O.compress(toy_models, reads_1k, max_block_total_len=20000, include_identifiers=False)
+        assert got == ref[9 + 3 + 64:-8]
