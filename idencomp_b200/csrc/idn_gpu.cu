@@ -228,6 +228,7 @@ int32_t check_models(idn_gpu_ctx* ctx, const idn_model_t* models, uint32_t n_mod
 // small per-call parameter block living in w_small (device):
 struct SmallParams {
     int32_t model_ids[256];            // container index -> slot
+    uint8_t model_type[256];           // container index -> IDN_MODEL_ACID / IDN_MODEL_QSCORE
     uint32_t cand_cols[2 * kMaxCand];  // candidate -> column of the score matrix
     int32_t cand_model[2 * kMaxCand];  // candidate -> slot
     uint8_t cand_index[2 * kMaxCand];  // candidate -> SwitchModel index
@@ -845,46 +846,68 @@ extern "C" int32_t idn_gpu_block_crc(idn_gpu_ctx* ctx, const idn_batch* b, uint3
 // decompression
 // ======================================================================================================
 namespace {
-struct IndexView {  // per-read index arrays carved out of w_index for `cap` reads
-    unsigned long long* pay_off;
-    unsigned long long* out_off;  // [cap+1]
-    uint32_t* pay_len;
-    uint32_t* seq_len;
-    uint8_t* am;
-    uint8_t* qm;
-    static size_t bytes(uint64_t cap) { return (cap + 2) * (8 + 8 + 4 + 4 + 1 + 1) + 64; }
-    void carve(void* base, uint64_t cap) {
-        uint8_t* p = reinterpret_cast<uint8_t*>(base);
-        pay_off = reinterpret_cast<unsigned long long*>(p);
-        p += (cap + 2) * 8;
-        out_off = reinterpret_cast<unsigned long long*>(p);
-        p += (cap + 2) * 8;
-        pay_len = reinterpret_cast<uint32_t*>(p);
-        p += (cap + 2) * 4;
-        seq_len = reinterpret_cast<uint32_t*>(p);
-        p += (cap + 2) * 4;
-        am = p;
-        p += cap + 2;
-        qm = p;
-    }
+// per-read index arrays carved out of w_index for `cap` entries
+size_t index_bytes(uint64_t cap) { return (cap + 2) * (8 + 8 + 4 + 4 + 1 + 1) + 64; }
+ReadIndexDev carve_index(void* base, uint64_t cap) {
+    ReadIndexDev ix;
+    uint8_t* p = reinterpret_cast<uint8_t*>(base);
+    ix.pay_off = reinterpret_cast<unsigned long long*>(p);
+    p += (cap + 2) * 8;
+    ix.sym_off = reinterpret_cast<unsigned long long*>(p);
+    p += (cap + 2) * 8;
+    ix.pay_len = reinterpret_cast<uint32_t*>(p);
+    p += (cap + 2) * 4;
+    ix.seq_len = reinterpret_cast<uint32_t*>(p);
+    p += (cap + 2) * 4;
+    ix.am = p;
+    p += cap + 2;
+    ix.qm = p;
+    return ix;
+}
+// per-block counters of the decode side, carved out of w_blk: each [B + 2] u64
+struct BlockCounters {
+    unsigned long long *reads, *syms, *slots;
 };
+BlockCounters carve_counters(void* base, uint32_t B) {
+    BlockCounters c;
+    c.reads = reinterpret_cast<unsigned long long*>(base);
+    c.syms = c.reads + B + 2;
+    c.slots = c.syms + B + 2;
+    return c;
+}
 }  // namespace
 
-// shared by idn_gpu_index_blocks and the decoders: count pass + scan.  Leaves per-block read/symbol bases in w_blk:
-//   blk_reads[0..B] (exclusive scan, [B] = total), blk_syms[0..B]
-static int32_t index_count(idn_gpu_ctx* ctx, const uint8_t* blocks, const unsigned long long* block_off,
-                           const uint32_t* block_len, uint32_t B, uint64_t blocks_bytes, const SmallParams* dsp, uint32_t n_models, cudaStream_t st) {
-    CU(ctx->w_blk.ensure(((size_t)B + 2) * 8 * 2));
-    unsigned long long* blk_reads = ctx->w_blk.as<unsigned long long>();
-    unsigned long long* blk_syms = blk_reads + B + 2;
-    index_count_kernel<<<(B + 31) / 32, 32, 0, st>>>(blocks, block_off, block_len, B, blocks_bytes, ctx->d_models, dsp->model_ids, n_models, blk_reads,
-                                                     blk_syms, const_cast<int32_t*>(dsp->status));
-    LAUNCHED("index_count");
-    scan_tiles_kernel<<<1, kScanBlock, 0, st>>>(blk_reads, B);
+// shared by idn_gpu_index_blocks and the decoder: slot bases, the slice walk, and the scans.  Leaves in w_blk the
+// exclusive scans reads[0..B] / syms[0..B] ([B] = totals) and slots[0..B]; the per-read index in w_index.
+static int32_t index_walk(idn_gpu_ctx* ctx, const uint8_t* blocks, const unsigned long long* block_off,
+                          const uint32_t* block_len, uint32_t B, uint64_t blocks_bytes, const SmallParams* dsp,
+                          uint32_t n_models, cudaStream_t st) {
+    CU(ctx->w_blk.ensure(((size_t)B + 2) * 8 * 3));
+    BlockCounters bc = carve_counters(ctx->w_blk.p, B);
+    const uint64_t cap = blocks_bytes / 17 + B + 1;  // every Sequence slice takes at least 17 bytes
+    CU(ctx->w_index.ensure(index_bytes(cap)));
+    ReadIndexDev ix = carve_index(ctx->w_index.p, cap);
+    slot_count_kernel<<<(B + 127) / 128, 128, 0, st>>>(block_off, block_len, B, bc.slots);
+    LAUNCHED("slot_count");
+    scan_tiles_kernel<<<1, kScanBlock, 0, st>>>(bc.slots, B);
     LAUNCHED("scan_tiles");
-    scan_tiles_kernel<<<1, kScanBlock, 0, st>>>(blk_syms, B);
+    walk_kernel<<<B, 32, 0, st>>>(blocks, block_off, block_len, B, blocks_bytes, dsp->model_type, n_models, bc.slots, ix, bc.reads,
+                                  bc.syms, const_cast<int32_t*>(dsp->status));
+    LAUNCHED("walk");
+    scan_tiles_kernel<<<1, kScanBlock, 0, st>>>(bc.reads, B);
+    LAUNCHED("scan_tiles");
+    scan_tiles_kernel<<<1, kScanBlock, 0, st>>>(bc.syms, B);
     LAUNCHED("scan_tiles");
     return IDN_OK;
+}
+
+static void fill_decode_params(idn_gpu_ctx* ctx, SmallParams* sp, const idn_model_t* models, uint32_t n_models) {
+    memset(sp, 0, sizeof *sp);
+    for (uint32_t i = 0; i < n_models; i++) {
+        sp->model_ids[i] = models[i];
+        sp->model_type[i] = (uint8_t)ctx->slots[models[i]].dev.type;
+    }
+    sp->status[1] = -1;
 }
 
 extern "C" int32_t idn_gpu_decompress_blocks_dev(idn_gpu_ctx* ctx, const uint8_t* blocks, const uint64_t* block_off,
@@ -903,52 +926,49 @@ extern "C" int32_t idn_gpu_decompress_blocks_dev(idn_gpu_ctx* ctx, const uint8_t
     cudaStream_t st = as_stream(stream);
     PROF_BEGIN();
     SmallParams sp;
-    memset(&sp, 0, sizeof sp);
-    for (uint32_t i = 0; i < n_models; i++) sp.model_ids[i] = models[i];
-    sp.status[1] = -1;
+    fill_decode_params(ctx, &sp, models, n_models);
     rc = upload_small(ctx, sp, st);
     if (rc) return rc;
     SmallParams* dsp = ctx->w_small.as<SmallParams>();
     const unsigned long long* boff = reinterpret_cast<const unsigned long long*>(block_off);
     if (n_blocks) {
-        rc = index_count(ctx, blocks, boff, block_len, n_blocks, blocks_bytes, dsp, n_models, st);
+        rc = index_walk(ctx, blocks, boff, block_len, n_blocks, blocks_bytes, dsp, n_models, st);
         if (rc) return rc;
     } else {
-        CU(ctx->w_blk.ensure(4 * 8 * 2));
-        CU(cudaMemsetAsync(ctx->w_blk.p, 0, 4 * 8 * 2, st));
+        CU(ctx->w_blk.ensure(2 * 8 * 3));
+        CU(cudaMemsetAsync(ctx->w_blk.p, 0, 2 * 8 * 3, st));
+        CU(ctx->w_index.ensure(index_bytes(1)));
     }
-    unsigned long long* blk_reads = ctx->w_blk.as<unsigned long long>();
-    unsigned long long* blk_syms = blk_reads + n_blocks + 2;
-    CU(ctx->w_index.ensure(IndexView::bytes(out_reads_cap)));
-    IndexView iv;
-    iv.carve(ctx->w_index.p, out_reads_cap);
+    BlockCounters bc = carve_counters(ctx->w_blk.p, n_blocks);
+    ReadIndexDev ix = carve_index(ctx->w_index.p, blocks_bytes / 17 + n_blocks + 1);
     CU(ctx->w_readblock.ensure(((size_t)n_blocks + 2) * 4));
     uint32_t* block_first = ctx->w_readblock.as<uint32_t>();
-    // capacity check on the device; on failure the later kernels see n_reads = 0
-    index_check_kernel<<<1, 32, 0, st>>>(blk_reads, blk_syms, n_blocks, out_reads_cap, out_symbols_cap, dsp->status);
+    unsigned long long* roff = reinterpret_cast<unsigned long long*>(read_off_out);
+    if (!roff) {  // the CRC kernels need the per-read symbol offsets even when the caller does not
+        CU(ctx->w_sliceoff.ensure((out_reads_cap + 2) * 8));
+        roff = ctx->w_sliceoff.as<unsigned long long>();
+    }
+    // capacity check on the device; on failure the later kernels are no-ops
+    index_check_kernel<<<(n_blocks + 1 + 255) / 256, 256, 0, st>>>(bc.reads, bc.syms, n_blocks, out_reads_cap, out_symbols_cap,
+                                                                 block_first, dsp->status);
     LAUNCHED("index_check");
-    index_fill_kernel<<<(n_blocks + 1 + 31) / 32, 32, 0, st>>>(blocks, boff, block_len, n_blocks, ctx->d_models, dsp->model_ids, n_models,
-                                                              blk_reads, blk_syms, iv.pay_off, iv.pay_len, iv.seq_len,
-                                                              iv.out_off, iv.am, iv.qm, block_first, dsp->status);
-    LAUNCHED("index_fill");
     DecodeArgs da;
     da.models = ctx->d_models;
     da.model_ids = dsp->model_ids;
     da.payload = blocks;
-    da.pay_off = iv.pay_off;
-    da.pay_len = iv.pay_len;
-    da.seq_len = iv.seq_len;
-    da.out_off = iv.out_off;
-    da.acid_model = iv.am;
-    da.q_model = iv.qm;
+    da.ix = ix;
+    da.blk_read_base = bc.reads;
+    da.blk_sym_base = bc.syms;
+    da.slot_base = bc.slots;
+    da.n_blocks = n_blocks;
     da.n_reads = 0;
-    da.n_reads_dev = blk_reads + n_blocks;
     da.status = dsp->status;
     da.acids_out = acids_out;
     da.quals_out = quals_out;
+    da.read_off_out = roff;
     da.read_status = nullptr;
     da.err = &dsp->err;
-    if (out_reads_cap) {
+    if (out_reads_cap && n_blocks) {
         decode_kernel<<<(unsigned)((out_reads_cap + 127) / 128), 128, 0, st>>>(da);
         LAUNCHED("decode");
     }
@@ -957,15 +977,15 @@ extern "C" int32_t idn_gpu_decompress_blocks_dev(idn_gpu_ctx* ctx, const uint8_t
         CU(ctx->w_crcpart.ensure((out_reads_cap + 1) * 4));
         CU(ctx->w_crclen.ensure((out_reads_cap + 1) * 8));
         crc_read_kernel<<<(unsigned)((out_reads_cap + 127) / 128), 128, 0, st>>>(
-            acids_out, quals_out, iv.out_off, nullptr, nullptr, 0, blk_reads + n_blocks, dsp->status, ctx->d_crc_tab,
-            ctx->d_xpow, ctx->w_crcpart.as<uint32_t>(), ctx->w_crclen.as<unsigned long long>());
+            acids_out, quals_out, roff, nullptr, nullptr, 0, bc.reads + n_blocks, dsp->status, ctx->d_crc_tab, ctx->d_xpow,
+            ctx->w_crcpart.as<uint32_t>(), ctx->w_crclen.as<unsigned long long>());
         LAUNCHED("crc_read");
         crc_verify_kernel<<<n_blocks, 256, 0, st>>>(ctx->w_crcpart.as<uint32_t>(), ctx->w_crclen.as<unsigned long long>(),
                                                     block_first, n_blocks, ctx->d_xpow, block_crc, dsp->status);
         LAUNCHED("crc_verify");
     }
-    finish_decode_kernel<<<(unsigned)((out_reads_cap + 1 + 255) / 256), 256, 0, st>>>(
-        dsp->status, &dsp->err, blk_reads + n_blocks, blk_syms + n_blocks, iv.out_off, reinterpret_cast<unsigned long long*>(read_off_out), out_reads_cap, status_dev);
+    finish_decode_kernel<<<1, 32, 0, st>>>(dsp->status, &dsp->err, bc.reads + n_blocks, bc.syms + n_blocks,
+                                           reinterpret_cast<unsigned long long*>(read_off_out), status_dev);
     LAUNCHED("finish_decode");
     return IDN_OK;
 }
@@ -1017,20 +1037,18 @@ extern "C" int32_t idn_gpu_index_blocks(idn_gpu_ctx* ctx, const uint8_t* blocks,
     CU(cudaMemcpyAsync(ctx->s_blockoff.p, block_off, ((size_t)n_blocks + 1) * 8, cudaMemcpyHostToDevice, st));
     if (block_len) CU(cudaMemcpyAsync(ctx->s_blocklen.p, block_len, (size_t)n_blocks * 4, cudaMemcpyHostToDevice, st));
     SmallParams sp;
-    memset(&sp, 0, sizeof sp);
-    for (uint32_t i = 0; i < n_models; i++) sp.model_ids[i] = models[i];
-    sp.status[1] = -1;
+    fill_decode_params(ctx, &sp, models, n_models);
     rc = upload_small(ctx, sp, st);
     if (rc) return rc;
     SmallParams* dsp = ctx->w_small.as<SmallParams>();
-    rc = index_count(ctx, ctx->s_blocks.as<uint8_t>(), ctx->s_blockoff.as<unsigned long long>(),
-                     block_len ? ctx->s_blocklen.as<uint32_t>() : nullptr, n_blocks, nbytes, dsp, n_models, st);
+    rc = index_walk(ctx, ctx->s_blocks.as<uint8_t>(), ctx->s_blockoff.as<unsigned long long>(),
+                    block_len ? ctx->s_blocklen.as<uint32_t>() : nullptr, n_blocks, nbytes, dsp, n_models, st);
     if (rc) return rc;
     std::vector<unsigned long long> hr(n_blocks + 1), hsym(n_blocks + 1);
     int32_t hst[4];
-    unsigned long long* blk_reads = ctx->w_blk.as<unsigned long long>();
-    CU(cudaMemcpyAsync(hr.data(), blk_reads, ((size_t)n_blocks + 1) * 8, cudaMemcpyDeviceToHost, st));
-    CU(cudaMemcpyAsync(hsym.data(), blk_reads + n_blocks + 2, ((size_t)n_blocks + 1) * 8, cudaMemcpyDeviceToHost, st));
+    BlockCounters bc = carve_counters(ctx->w_blk.p, n_blocks);
+    CU(cudaMemcpyAsync(hr.data(), bc.reads, ((size_t)n_blocks + 1) * 8, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(hsym.data(), bc.syms, ((size_t)n_blocks + 1) * 8, cudaMemcpyDeviceToHost, st));
     CU(cudaMemcpyAsync(hst, dsp->status, sizeof hst, cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
     if (hst[0]) return status_to_error(ctx, hst);
@@ -1083,8 +1101,9 @@ extern "C" int32_t idn_gpu_decompress_blocks(idn_gpu_ctx* ctx, const uint8_t* bl
     int32_t hst[4];
     unsigned long long tot[2];
     CU(cudaMemcpyAsync(hst, ctx->s_status.p, sizeof hst, cudaMemcpyDeviceToHost, st));
-    CU(cudaMemcpyAsync(&tot[0], ctx->w_blk.as<unsigned long long>() + n_blocks, 8, cudaMemcpyDeviceToHost, st));
-    CU(cudaMemcpyAsync(&tot[1], ctx->w_blk.as<unsigned long long>() + n_blocks + 2 + n_blocks, 8, cudaMemcpyDeviceToHost, st));
+    BlockCounters bc = carve_counters(ctx->w_blk.p, n_blocks);
+    CU(cudaMemcpyAsync(&tot[0], bc.reads + n_blocks, 8, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(&tot[1], bc.syms + n_blocks, 8, cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
     if (hst[0]) {
         if (bad_block) *bad_block = hst[1];
@@ -1163,34 +1182,32 @@ extern "C" int32_t idn_gpu_decompress_reads(idn_gpu_ctx* ctx, const uint8_t* pay
     if (rc) return rc;
     SmallParams* dsp = ctx->w_small.as<SmallParams>();
     CU(ctx->s_blocks.ensure(payload_bytes + 16));
-    CU(ctx->w_index.ensure(IndexView::bytes(R)));
+    CU(ctx->w_index.ensure(index_bytes(R)));
     CU(ctx->s_aout.ensure(S + 16));
     CU(ctx->s_qout.ensure(S + 16));
     CU(ctx->s_idx.ensure((R + 1) * 4));
-    IndexView iv;
-    iv.carve(ctx->w_index.p, R);
+    ReadIndexDev ix = carve_index(ctx->w_index.p, R);
     if (payload_bytes) CU(cudaMemcpyAsync(ctx->s_blocks.p, payload, payload_bytes, cudaMemcpyHostToDevice, st));
-    CU(cudaMemcpyAsync(iv.pay_off, index->pay_off, R * 8, cudaMemcpyHostToDevice, st));
-    CU(cudaMemcpyAsync(iv.out_off, index->out_off, (R + 1) * 8, cudaMemcpyHostToDevice, st));
-    CU(cudaMemcpyAsync(iv.pay_len, index->pay_len, R * 4, cudaMemcpyHostToDevice, st));
-    CU(cudaMemcpyAsync(iv.seq_len, index->seq_len, R * 4, cudaMemcpyHostToDevice, st));
-    CU(cudaMemcpyAsync(iv.am, index->acid_model, R, cudaMemcpyHostToDevice, st));
-    CU(cudaMemcpyAsync(iv.qm, index->q_model, R, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(ix.pay_off, index->pay_off, R * 8, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(ix.sym_off, index->out_off, (R + 1) * 8, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(ix.pay_len, index->pay_len, R * 4, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(ix.seq_len, index->seq_len, R * 4, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(ix.am, index->acid_model, R, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(ix.qm, index->q_model, R, cudaMemcpyHostToDevice, st));
     DecodeArgs da;
     da.models = ctx->d_models;
     da.model_ids = dsp->model_ids;
     da.payload = ctx->s_blocks.as<uint8_t>();
-    da.pay_off = iv.pay_off;
-    da.pay_len = iv.pay_len;
-    da.seq_len = iv.seq_len;
-    da.out_off = iv.out_off;
-    da.acid_model = iv.am;
-    da.q_model = iv.qm;
+    da.ix = ix;
+    da.blk_read_base = nullptr;
+    da.blk_sym_base = nullptr;
+    da.slot_base = nullptr;
+    da.n_blocks = 0;
     da.n_reads = R;
-    da.n_reads_dev = nullptr;
     da.status = nullptr;
     da.acids_out = ctx->s_aout.as<uint8_t>();
     da.quals_out = ctx->s_qout.as<uint8_t>();
+    da.read_off_out = nullptr;
     da.read_status = ctx->s_idx.as<uint32_t>();
     da.err = &dsp->err;
     decode_kernel<<<(unsigned)((R + 127) / 128), 128, 0, st>>>(da);

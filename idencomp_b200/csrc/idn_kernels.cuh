@@ -716,114 +716,223 @@ crc_verify_kernel(const uint32_t* __restrict__ part_crc, const unsigned long lon
 }
 
 // ---------------------------------------------------------------------------------------------------
-// container slice walk (decode side).  The chain "header -> next header" is serial inside a block, so one
-// thread walks one block; blocks run in parallel.  Pass 1 counts reads/symbols per block, pass 2 (after a
-// scan) fills the per-read index.
+// container slice walk (decode side)   IdnBlockDecompressor::next_sequence_internal, decompressor_block.rs:115-129
+// The chain "slice header -> next slice header" is serial inside a block, so ONE WARP walks one block and blocks
+// run in parallel.  The warp stages the block through shared memory in tiles (coalesced 16-byte loads); lane 0
+// follows the chain inside the tile (shared-memory latency per hop instead of a global round trip) and only
+// records (offset, length, seq_len, models) per Sequence slice; the whole warp then turns those records into
+// index entries (prefix sum of seq_len, coalesced stores).  A single pass suffices because the entries of block
+// b are stored at slot_base[b] + i, slot_base = exclusive scan of the per-block upper bound len_b / 17 + 1
+// (a Sequence slice is at least 9 header + 8 flush bytes); the decoder maps read -> (block, i) by binary search.
 // ---------------------------------------------------------------------------------------------------
-struct WalkResult {
-    uint32_t n_reads;
-    unsigned long long n_symbols;
-    int32_t status;  // IDN_* code
-};
+constexpr int kWalkTile = 8192;
+constexpr int kWalkMaxEnt = 512;  // > kWalkTile / 17
 
 __device__ __forceinline__ uint32_t load_u32be(const uint8_t* p) {
     return ((uint32_t)p[0] << 24) | ((uint32_t)p[1] << 16) | ((uint32_t)p[2] << 8) | p[3];
 }
 
-template <bool kFill>
-__device__ __forceinline__ WalkResult walk_block(const uint8_t* __restrict__ p, unsigned long long n,
-                                                 const ModelDev* __restrict__ models, const int32_t* __restrict__ model_ids,
-                                                 uint32_t n_models, unsigned long long blk_base, uint64_t r_base,
-                                                 unsigned long long sym_base, unsigned long long* __restrict__ pay_off,
-                                                 uint32_t* __restrict__ pay_len, uint32_t* __restrict__ seq_len,
-                                                 unsigned long long* __restrict__ out_off, uint8_t* __restrict__ am,
-                                                 uint8_t* __restrict__ qm) {
-    WalkResult w{0, 0, 0};
-    unsigned long long pos = 0;
-    int cur_a = -1, cur_q = -1;
-    while (pos < n) {
-        uint8_t kind = p[pos++];
-        if (kind == 0) {  // Identifiers: skipped on the device (names stay on the host)
-            if (pos + 5 > n) { w.status = 3; break; }
-            uint32_t len = load_u32be(p + pos);
-            pos += 5;
-            if (pos + len > n) { w.status = 3; break; }
-            pos += len;
-        } else if (kind == 1) {  // SwitchModel  decompressor_block.rs:194-214
-            if (pos + 1 > n) { w.status = 3; break; }
-            uint32_t idx = p[pos++];
-            if (idx >= n_models) { w.status = 7; break; }
-            if (models[model_ids[idx]].type == 0) cur_a = (int)idx; else cur_q = (int)idx;
-        } else if (kind == 2) {  // Sequence  :216-239
-            if (pos + 8 > n) { w.status = 3; break; }
-            uint32_t len = load_u32be(p + pos), sl = load_u32be(p + pos + 4);
-            pos += 8;
-            if (pos + len > n || len < 8) { w.status = 3; break; }
-            if (cur_a < 0 || cur_q < 0) { w.status = 8; break; }
-            if (kFill) {
-                uint64_t r = r_base + w.n_reads;
-                pay_off[r] = blk_base + pos;
-                pay_len[r] = len;
-                seq_len[r] = sl;
-                out_off[r] = sym_base + w.n_symbols;
-                am[r] = (uint8_t)cur_a;
-                qm[r] = (uint8_t)cur_q;
-            }
-            w.n_reads++;
-            w.n_symbols += sl;
-            pos += len;
-        } else {
-            w.status = 3;
-            break;
-        }
-    }
-    return w;
-}
+struct ReadIndexDev {  // per-read index, strided by block (see above) or dense (idn_gpu_decompress_reads)
+    unsigned long long* pay_off;  // absolute offset of the rANS payload in `payload`
+    uint32_t* pay_len;
+    uint32_t* seq_len;
+    unsigned long long* sym_off;  // offset of the read's symbols, relative to its block's first symbol
+    uint8_t* am;                  // container model indices
+    uint8_t* qm;
+};
 
-__global__ void __launch_bounds__(32)
-index_count_kernel(const uint8_t* __restrict__ blocks, const unsigned long long* __restrict__ block_off,
-                   const uint32_t* __restrict__ block_len, uint32_t n_blocks, unsigned long long blocks_bytes,
-                   const ModelDev* __restrict__ models, const int32_t* __restrict__ model_ids, uint32_t n_models,
-                   unsigned long long* __restrict__ blk_reads, unsigned long long* __restrict__ blk_syms,
-                   int32_t* __restrict__ status /*[2]: code, block*/) {
+// upper bound of Sequence slices per block -> slot counts (scanned by scan_tiles_kernel)
+__global__ void slot_count_kernel(const unsigned long long* __restrict__ block_off, const uint32_t* __restrict__ block_len,
+                                  uint32_t n_blocks, unsigned long long* __restrict__ slot_cnt) {
     uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= n_blocks) return;
     unsigned long long n = block_len ? block_len[b] : block_off[b + 1] - block_off[b];
-    WalkResult w{0, 0, 3};  // a block that runs past the input is malformed
-    if (block_off[b] <= blocks_bytes && n <= blocks_bytes - block_off[b])
-        w = walk_block<false>(blocks + block_off[b], n, models, model_ids, n_models, 0, 0, 0, nullptr, nullptr, nullptr, nullptr,
-                              nullptr, nullptr);
-    blk_reads[b] = w.n_reads;
-    blk_syms[b] = w.n_symbols;
-    if (w.status != 0) {
-        int old = atomicCAS(&status[0], 0, w.status);
-        if (old == 0) status[1] = (int32_t)b;
+    slot_cnt[b] = n / 17 + 1;
+}
+
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
+    unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+    asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+
+// stage kWalkTile + 16 bytes starting at the 16-byte aligned absolute address A into `tile` (asynchronously where the
+// 16-byte chunk lies completely inside the caller's buffer, byte by byte with zero fill at its two ends)
+__device__ __forceinline__ void walk_stage(uint8_t* tile, uintptr_t A, uintptr_t lo16, uintptr_t hi16, uintptr_t buf_lo,
+                                           uintptr_t buf_hi, uint32_t lane) {
+#pragma unroll 1
+    for (uint32_t k = lane; k < kWalkTile / 16 + 1; k += 32) {
+        uintptr_t addr = A + 16ull * k;
+        if (addr >= lo16 && addr + 16 <= hi16) {
+            cp_async16(tile + 16 * k, reinterpret_cast<const void*>(addr));
+        } else {
+            uint32_t w[4] = {0, 0, 0, 0};
+            for (int j = 0; j < 16; j++) {
+                uintptr_t p = addr + j;
+                if (p >= buf_lo && p < buf_hi) w[j >> 2] |= (uint32_t)(*reinterpret_cast<const uint8_t*>(p)) << (8 * (j & 3));
+            }
+            *reinterpret_cast<uint4*>(tile + 16 * k) = make_uint4(w[0], w[1], w[2], w[3]);
+        }
     }
+    cp_async_commit();
 }
 
 __global__ void __launch_bounds__(32)
-index_fill_kernel(const uint8_t* __restrict__ blocks, const unsigned long long* __restrict__ block_off,
-                  const uint32_t* __restrict__ block_len, uint32_t n_blocks, const ModelDev* __restrict__ models, const int32_t* __restrict__ model_ids, uint32_t n_models,
-                  const unsigned long long* __restrict__ blk_read_base, const unsigned long long* __restrict__ blk_sym_base,
-                  unsigned long long* __restrict__ pay_off, uint32_t* __restrict__ pay_len, uint32_t* __restrict__ seq_len,
-                  unsigned long long* __restrict__ out_off, uint8_t* __restrict__ am, uint8_t* __restrict__ qm,
-                  uint32_t* __restrict__ block_first, const int32_t* __restrict__ status) {
-    uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
-    if (b > n_blocks || status[0] != 0) return;
-    if (b == n_blocks) {
-        if (block_first) block_first[b] = (uint32_t)blk_read_base[b];
-        out_off[blk_read_base[b]] = blk_sym_base[b];
-        return;
+walk_kernel(const uint8_t* __restrict__ blocks, const unsigned long long* __restrict__ block_off,
+            const uint32_t* __restrict__ block_len, uint32_t n_blocks, unsigned long long blocks_bytes,
+            const uint8_t* __restrict__ model_type /*[n_models] by container index*/, uint32_t n_models,
+            const unsigned long long* __restrict__ slot_base, ReadIndexDev ix, unsigned long long* __restrict__ blk_reads,
+            unsigned long long* __restrict__ blk_syms, int32_t* __restrict__ status /*[2]: code, block*/) {
+    __shared__ __align__(16) uint8_t tiles[2][kWalkTile + 32];
+    __shared__ uint4 ent[kWalkMaxEnt];  // {payload offset in the tile, payload length, seq_len, models}
+    const uint32_t b = blockIdx.x, lane = threadIdx.x;
+    if (b >= n_blocks) return;
+    const unsigned long long boff = block_off[b];
+    const unsigned long long n = block_len ? block_len[b] : block_off[b + 1] - boff;
+    int32_t st = 0;
+    if (boff > blocks_bytes || n > blocks_bytes - boff || n > 0xffffffffull) st = 3;  // runs past the input: malformed
+    // 16-byte chunks that lie completely inside the caller's buffer may be copied as vectors
+    const uintptr_t buf_lo = reinterpret_cast<uintptr_t>(blocks), buf_hi = buf_lo + blocks_bytes;
+    const uintptr_t lo16 = (buf_lo + 15) & ~(uintptr_t)15, hi16 = buf_hi & ~(uintptr_t)15;
+    const uintptr_t blk_abs = buf_lo + boff;
+
+    unsigned long long pos = 0;  // block-relative position of the next slice header
+    unsigned long long n_reads = 0, n_syms = 0;
+    int cur_a = -1, cur_q = -1;
+    const unsigned long long slot0 = slot_base[b];
+    uint32_t cur = 0;
+    uintptr_t A = blk_abs & ~(uintptr_t)15;  // absolute address of tile[0] of the current buffer
+    if (st == 0 && n > 0) walk_stage(tiles[0], A, lo16, hi16, buf_lo, buf_hi, lane);
+    while (st == 0 && pos < n) {
+        // prefetch the tile that follows on the assumption that the walk ends within 16 bytes of this tile's end
+        const uintptr_t A_next = A + kWalkTile - 16;
+        walk_stage(tiles[cur ^ 1], A_next, lo16, hi16, buf_lo, buf_hi, lane);
+        cp_async_wait<1>();
+        __syncwarp();
+        const uint8_t* tile = tiles[cur];
+        // block positions [t_lo, t_hi) are staged in tile[]; t_lo may lie before the block (alignment)
+        const long long t_lo = (long long)(A - blk_abs);
+        uint32_t n_ent = 0;
+        if (lane == 0) {
+            // 32-bit arithmetic only: one thread's dependent-instruction chain is what bounds this loop.
+            // p = position inside the tile; the block ends at tile offset n_off (if it ends inside the staged range)
+            uint32_t p = (uint32_t)((long long)pos - t_lo);
+            const unsigned long long left = n - pos;  // bytes of the block from pos on
+            // clamped, so that a bound accepted in 32 bits is always a true bound; rejections are rechecked in 64 bits
+            const uint32_t n_off = p + (uint32_t)(left > 0x40000000ull ? 0x40000000ull : left);
+            const uint32_t kStaged = kWalkTile + 16;
+            int mdl = (cur_a & 0xff) | ((cur_q & 0xff) << 8);  // -1 -> 0xff = none (indices are < 255)
+            const uint32_t* tw = reinterpret_cast<const uint32_t*>(tile);
+            while (p < n_off && n_ent < (uint32_t)kWalkMaxEnt && p + 9 <= kStaged) {
+                // 9 header bytes from 3 aligned words: kind = byte p, w1 = bytes p+1..p+4 and w2 = bytes p+5..p+8, big endian
+                const uint32_t wi = p >> 2, sh = p & 3;
+                const uint32_t W0 = tw[wi], W1 = tw[wi + 1], W2 = tw[wi + 2];
+                const uint32_t sel = 0x1234u + sh * 0x1111u;  // result bytes 0..3 = pair bytes o+3, o+2, o+1, o with o = sh + 1
+                const uint32_t kind = (W0 >> (8 * sh)) & 0xffu;
+                const uint32_t w1 = __byte_perm(W0, W1, sel), w2 = __byte_perm(W1, W2, sel);
+                const uint32_t room = n_off - p;  // >= 1
+                if (kind == 2) {  // Sequence: u32 length, u32 seq_len, payload   (data.rs:79-84, decompressor_block.rs:216-239)
+                    if (room < 9 || w1 > room - 9 || w1 < 8) {
+                        // n_off is clamped for blocks larger than 1 GiB: redo the bound in 64 bits before failing
+                        unsigned long long l2 = n - ((unsigned long long)((long long)p + t_lo));
+                        if (l2 < 9 || w1 > l2 - 9 || w1 < 8) { st = 3; break; }
+                    }
+                    if ((mdl & 0xff) == 0xff || (mdl >> 8) == 0xff) { st = 8; break; }
+                    ent[n_ent++] = make_uint4(p + 9, w1, w2, (uint32_t)mdl);  // tile-relative; rebased by the writers below
+                    if (w1 >= 0x7fff0000u) {  // cannot happen inside a staged tile walk without leaving it: jump in 64 bits
+                        pos = (unsigned long long)((long long)p + t_lo) + 9ull + w1;
+                        p = 0xffffffffu;
+                        break;
+                    }
+                    p += 9u + w1;
+                } else if (kind == 1) {  // SwitchModel: u8 index   (decompressor_block.rs:194-214)
+                    if (room < 2) { st = 3; break; }
+                    uint32_t idx = w1 >> 24;
+                    if (idx >= n_models || idx >= 255) { st = 7; break; }
+                    if (model_type[idx] == 0) mdl = (mdl & 0xff00) | idx; else mdl = (mdl & 0xff) | (idx << 8);
+                    p += 2;
+                } else if (kind == 0) {  // Identifiers: u32 length, u8 compression, data -- names stay on the host
+                    if (room < 6 || w1 > room - 6) {
+                        unsigned long long l2 = n - ((unsigned long long)((long long)p + t_lo));
+                        if (l2 < 6 || w1 > l2 - 6) { st = 3; break; }
+                    }
+                    if (w1 >= 0x7fff0000u) {
+                        pos = (unsigned long long)((long long)p + t_lo) + 6ull + w1;
+                        p = 0xffffffffu;
+                        break;
+                    }
+                    p += 6u + w1;
+                } else {
+                    st = 3;
+                    break;
+                }
+            }
+            if (p != 0xffffffffu) pos = (unsigned long long)((long long)p + t_lo);
+            cur_a = (mdl & 0xff) == 0xff ? -1 : (mdl & 0xff);
+            cur_q = (mdl >> 8) == 0xff ? -1 : (mdl >> 8);
+        }
+        n_ent = __shfl_sync(0xffffffffu, n_ent, 0);
+        st = __shfl_sync(0xffffffffu, st, 0);
+        pos = __shfl_sync(0xffffffffu, pos, 0);
+        // ---- the warp writes the entries of this tile ----
+        for (uint32_t base = 0; base < n_ent; base += 32) {
+            uint32_t i = base + lane;
+            const uint4 e = i < n_ent ? ent[i] : make_uint4(0, 0, 0, 0);
+            unsigned long long sl = e.z, inc = sl;
+            for (int d = 1; d < 32; d <<= 1) {
+                unsigned long long o = __shfl_up_sync(0xffffffffu, inc, d);
+                if (lane >= (uint32_t)d) inc += o;
+            }
+            if (i < n_ent) {
+                unsigned long long slot = slot0 + n_reads + i;
+                ix.pay_off[slot] = boff + (unsigned long long)(t_lo + (long long)e.x);
+                ix.pay_len[slot] = e.y;
+                ix.seq_len[slot] = e.z;
+                ix.sym_off[slot] = n_syms + inc - sl;
+                ix.am[slot] = (uint8_t)(e.w & 0xff);
+                ix.qm[slot] = (uint8_t)(e.w >> 8);
+            }
+            n_syms += __shfl_sync(0xffffffffu, inc, 31);
+        }
+        n_reads += n_ent;
+        __syncwarp();
+        if (st != 0 || pos >= n) break;
+        // the prefetched tile serves when the next header starts inside it (and the walk can make progress)
+        const long long nt_lo = (long long)(A_next - blk_abs);
+        if ((long long)pos >= nt_lo && (long long)pos + 9 <= nt_lo + kWalkTile + 16) {
+            A = A_next;
+            cur ^= 1;
+        } else {
+            cp_async_wait<0>();  // the speculative copy must land before its buffer is reused
+            __syncwarp();
+            A = (blk_abs + pos) & ~(uintptr_t)15;
+            walk_stage(tiles[cur], A, lo16, hi16, buf_lo, buf_hi, lane);
+        }
     }
-    if (block_first) block_first[b] = (uint32_t)blk_read_base[b];
-    walk_block<true>(blocks + block_off[b], block_len ? block_len[b] : block_off[b + 1] - block_off[b], models, model_ids, n_models, block_off[b],
-                     blk_read_base[b], blk_sym_base[b], pay_off, pay_len, seq_len, out_off, am, qm);
+    cp_async_wait<0>();
+    if (lane == 0) {
+        blk_reads[b] = n_reads;
+        blk_syms[b] = n_syms;
+        if (st != 0) {
+            int old = atomicCAS(&status[0], 0, st);
+            if (old == 0) status[1] = (int32_t)b;
+        }
+    }
 }
 
-// totals against the caller's capacities; on failure every later kernel of the call is a no-op
-__global__ void index_check_kernel(const unsigned long long* __restrict__ blk_reads, const unsigned long long* __restrict__ blk_syms,
-                                   uint32_t n_blocks, uint64_t reads_cap, uint64_t syms_cap, int32_t* __restrict__ status) {
-    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+// totals against the caller's capacities + u32 block_first for the CRC kernels; on failure every later kernel of the
+// call is a no-op
+__global__ void __launch_bounds__(256)
+index_check_kernel(const unsigned long long* __restrict__ blk_reads, const unsigned long long* __restrict__ blk_syms,
+                   uint32_t n_blocks, uint64_t reads_cap, uint64_t syms_cap, uint32_t* __restrict__ block_first,
+                   int32_t* __restrict__ status) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i <= n_blocks && block_first) block_first[i] = (uint32_t)blk_reads[i];
+    if (i != 0) return;
     status[3] = 0x7fffffff;  // first block with a checksum mismatch
     if (status[0] != 0) return;
     if (blk_reads[n_blocks] > reads_cap || blk_syms[n_blocks] > syms_cap) {
@@ -846,17 +955,18 @@ struct DecodeArgs {
     const ModelDev* models;
     const int32_t* model_ids;  // container index -> models[]
     const uint8_t* payload;
-    const unsigned long long* pay_off;
-    const uint32_t* pay_len;
-    const uint32_t* seq_len;
-    const unsigned long long* out_off;
-    const uint8_t* acid_model;
-    const uint8_t* q_model;
-    uint64_t n_reads;
-    const unsigned long long* n_reads_dev;  // when set, overrides n_reads (count produced by the index kernels)
+    ReadIndexDev ix;
+    // block-strided index (walk_kernel): read r -> block b by binary search over blk_read_base[0..n_blocks], entry at
+    // slot_base[b] + (r - blk_read_base[b]); nullptr = dense index, entry r, sym_off absolute
+    const unsigned long long* blk_read_base;
+    const unsigned long long* blk_sym_base;
+    const unsigned long long* slot_base;
+    uint32_t n_blocks;
+    uint64_t n_reads;                       // dense form only
     const int32_t* status;                  // when set and != 0 the kernel does nothing
     uint8_t* acids_out;
     uint8_t* quals_out;
+    unsigned long long* read_off_out;       // optional [n_reads+1]: absolute symbol offset of every read
     uint32_t* read_status;  // optional
     uint32_t* err;
 };
@@ -865,11 +975,27 @@ __global__ void __launch_bounds__(128)
 decode_kernel(DecodeArgs A) {
     uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (A.status && A.status[0] != 0) return;
-    if (r >= (A.n_reads_dev ? *A.n_reads_dev : A.n_reads)) return;
-    const ModelDev& ma = A.models[A.model_ids[A.acid_model[r]]];
-    const ModelDev& mq = A.models[A.model_ids[A.q_model[r]]];
-    const unsigned long long poff = A.pay_off[r];
-    const uint32_t plen = A.pay_len[r], len = A.seq_len[r];
+    unsigned long long slot = r, sym_base = 0;
+    if (A.blk_read_base) {
+        const unsigned long long R = A.blk_read_base[A.n_blocks];
+        if (r >= R) return;
+        uint32_t lo = 0, hi = A.n_blocks;  // largest b with blk_read_base[b] <= r
+        while (hi - lo > 1) {
+            uint32_t mid = (lo + hi) >> 1;
+            if (__ldg(A.blk_read_base + mid) <= r) lo = mid; else hi = mid;
+        }
+        slot = A.slot_base[lo] + (r - A.blk_read_base[lo]);
+        sym_base = A.blk_sym_base[lo];
+        if (r == R - 1 && A.read_off_out) A.read_off_out[R] = A.blk_sym_base[A.n_blocks];
+    } else if (r >= A.n_reads) {
+        return;
+    }
+    const ModelDev& ma = A.models[A.model_ids[A.ix.am[slot]]];
+    const ModelDev& mq = A.models[A.model_ids[A.ix.qm[slot]]];
+    const unsigned long long poff = A.ix.pay_off[slot];
+    const uint32_t plen = A.ix.pay_len[slot], len = A.ix.seq_len[slot];
+    const unsigned long long ooff = sym_base + A.ix.sym_off[slot];
+    if (A.read_off_out) A.read_off_out[r] = ooff;
     FwdReader in;
     in.init(A.payload);
     uint32_t cur = 0, st = 0;
@@ -894,8 +1020,8 @@ decode_kernel(DecodeArgs A) {
     ga.init();
     gq.init();
     FwdWriter oa, oq;
-    oa.init(A.acids_out + A.out_off[r]);
-    oq.init(A.quals_out + A.out_off[r]);
+    oa.init(A.acids_out + ooff);
+    oq.init(A.quals_out + ooff);
 #pragma unroll 1
     for (uint32_t i = 0; i < len && !(st & 1); i++) {
         uint32_t row_a = ctx_row(ma, ga.spec(ma.spec));
@@ -921,25 +1047,22 @@ decode_kernel(DecodeArgs A) {
     if (st & 1) atomicOr(A.err, 1u);
 }
 
-// final status word of a device-side decompress call + copy of the read offsets
-__global__ void __launch_bounds__(256)
-finish_decode_kernel(const int32_t* __restrict__ status, const uint32_t* __restrict__ err,
-                     const unsigned long long* __restrict__ n_reads_total, const unsigned long long* __restrict__ n_syms_total,
-                     const unsigned long long* __restrict__ out_off, unsigned long long* __restrict__ read_off_out,
-                     uint64_t reads_cap, int32_t* __restrict__ status_dev) {
-    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+// final status word of a device-side decompress call
+__global__ void finish_decode_kernel(const int32_t* __restrict__ status, const uint32_t* __restrict__ err,
+                                     const unsigned long long* __restrict__ n_reads_total,
+                                     const unsigned long long* __restrict__ n_syms_total,
+                                     unsigned long long* __restrict__ read_off_out, int32_t* __restrict__ status_dev) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
     int32_t code = status[0];
     uint64_t R = *n_reads_total;
-    if (i == 0) {
-        int32_t blk = status[1];
-        if (code == 0 && (*err & 1u)) code = 3;  // a payload ran out: IDN_E_SERIALIZE
-        if (code == 6) blk = status[3];
-        status_dev[0] = code;
-        status_dev[1] = blk;
-        status_dev[2] = code == 11 ? status[2] : (int32_t)(R > 0x7fffffffull ? 0x7fffffff : R);
-        status_dev[3] = (int32_t)(*n_syms_total & 0x7fffffffull);
-    }
-    if (code == 0 && read_off_out && i <= R && i <= reads_cap) read_off_out[i] = out_off[i];
+    int32_t blk = status[1];
+    if (code == 0 && (*err & 1u)) code = 3;  // a payload ran out: IDN_E_SERIALIZE
+    if (code == 6) blk = status[3];
+    status_dev[0] = code;
+    status_dev[1] = blk;
+    status_dev[2] = code == 11 ? status[2] : (int32_t)(R > 0x7fffffffull ? 0x7fffffff : R);
+    status_dev[3] = (int32_t)(*n_syms_total & 0x7fffffffull);
+    if (code == 0 && R == 0 && read_off_out) read_off_out[0] = 0;
 }
 
 // ---------------------------------------------------------------------------------------------------

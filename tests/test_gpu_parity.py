@@ -383,3 +383,31 @@ def test_unaligned_batch_pointers(gctx, O, toy_models, toy_handles, reads_1k):
         got = out_d[:n].cpu().numpy().tobytes()
         ref = O.compress(toy_models, reads_1k, max_block_total_len=20000, include_identifiers=False)
         assert got == ref[9 + 3 + 64:-8]
+
+
+def test_walk_skips_large_identifier_slices_and_long_reads(gctx, O, toy_models, toy_handles):
+    """The slice walk stages blocks through shared memory in 8 KiB tiles: cover slices much larger than a tile
+    (a names slice of ~40 KiB, reads of 30 000 symbols) next to tiny ones, in several blocks."""
+    rng = np.random.default_rng(11)
+    seqs = []
+    for i, ln in enumerate([30000, 3, 0, 17000, 1, 250, 9000, 64, 64, 12000]):
+        name = bytes(rng.integers(33, 127, size=4000 + i, dtype=np.uint8))
+        seqs.append((name, rng.integers(0, 5, size=ln), rng.integers(0, 94, size=ln)))
+    reads = O.Reads.from_lists(seqs)
+    idn = O.compress(toy_models, reads, max_block_total_len=60000, include_identifiers=True)
+    # split the container by hand: header 9 + metadata 3 + 2 ids
+    pos, blocks = 9 + 3 + 64, []
+    while True:
+        ln = int.from_bytes(idn[pos:pos + 4], "big")
+        crc = int.from_bytes(idn[pos + 4:pos + 8], "big")
+        if ln == 0:
+            break
+        blocks.append((pos + 8, ln, crc))
+        pos += 8 + ln
+    assert len(blocks) >= 2
+    buf = np.frombuffer(idn, dtype=np.uint8)
+    doff = np.asarray([b[0] for b in blocks] + [len(idn)], dtype=np.uint64)
+    dlen = np.asarray([b[1] for b in blocks], dtype=np.uint32)
+    crc = np.asarray([b[2] for b in blocks], dtype=np.uint32)
+    ro, a, q = gctx.decompress_blocks(buf, doff, crc, toy_handles, block_len=dlen, name_off=reads.name_off, names=reads.names)
+    assert np.array_equal(ro, reads.read_off) and np.array_equal(a, reads.acids) and np.array_equal(q, reads.quals)
