@@ -5,6 +5,10 @@
 //   * ryg rans_byte put/get     crate rans 0.2.1 -> ryg-rans-sys 1.0.7 (call sites compressor.rs:53-98,173-193)
 // The table layouts are ours (see DESIGN.md "Data layout in HBM"): the reference keeps a usize map of
 // spec_num entries and a 128 KiB slot->symbol LUT per context (compressor.rs:124-128), which would be GBs.
+//
+// The codec kernels are instruction-issue bound (profiles/r1_ncu_v1.md), so the generators are written
+// branch-free: one formula covers every legal spec type (generic / light, any order, any position bits) with
+// per-model constants instead of per-order branches.
 #pragma once
 #include <cstdint>
 #include <cuda_runtime.h>
@@ -16,19 +20,24 @@ constexpr uint32_t kAcidSyms = 5, kQSyms = 94;
 constexpr uint32_t kSlotMask = (1u << kScaleBits) - 1;
 constexpr uint32_t kRansL = 1u << 23;  // RANS_BYTE_L
 constexpr int kHist = 8;               // longest acid / q-score history any legal spec type uses
-constexpr int kQRowStride = 112;       // u16 per q-score decode row: 16 pivots + 96 cumulative freqs
-constexpr int kQBucket = 8;            // symbols per pivot bucket
+// q-score decode row: 128-byte bucket LUT (slot >> 7 -> first group) + 24 groups of 4 symbols, each symbol one
+// word freq | start << 16 (padding symbols: start = 2^14, freq = 0)
+constexpr int kQLutBytes = 128;
+constexpr int kQGroups = 24;
+constexpr int kQRowBytes = kQLutBytes + kQGroups * 16;  // 512
 
-// divide a value < 2^31 by a constant: q = m ? umulhi(x, m) >> s : x >> s
-struct FastDiv {
+// floor(x / d) for x < 2^31 as umulhi(x, m) >> s.  d = 2^k (k >= 1): m = 2^(32-k), s = 0; otherwise the round-up
+// reciprocal with s = ceil(log2 d) - 1 (the same argument as ryg's RansEncSymbolInit).  d <= 1 is never divided by.
+struct Magic {
     uint32_t m, s;
 };
-
-__host__ inline FastDiv make_fastdiv(uint32_t d) {
-    FastDiv f{0, 0};
-    if (d == 0) d = 1;
-    if ((d & (d - 1)) == 0) {  // power of two (incl. 1)
-        while ((1u << f.s) < d) f.s++;
+__host__ inline Magic make_magic(uint32_t d) {
+    Magic f{0, 0};
+    if (d <= 1) return f;
+    if ((d & (d - 1)) == 0) {
+        uint32_t k = 0;
+        while ((1u << k) < d) k++;
+        f.m = 1u << (32 - k);
         return f;
     }
     uint32_t c = 0;  // ceil(log2 d)
@@ -37,18 +46,26 @@ __host__ inline FastDiv make_fastdiv(uint32_t d) {
     f.m = (uint32_t)((((unsigned long long)1 << (32 + f.s)) + d - 1) / d);
     return f;
 }
-__device__ __forceinline__ uint32_t fastdiv(uint32_t x, FastDiv f) {
-    return (f.m ? __umulhi(x, f.m) : x) >> f.s;
-}
+
+// One IntQueue<B, n> (int_queue.rs:40-70), newest digit lowest.
+//   forward push (with_pushed_back):  s' = (s mod B^(n-1)) * B + v
+//        = s*B - floor(s / M)*M*B + v*vmul   (mod 2^32),  M = B^(n-1)
+//        n == 0: B = MB = vmul = 0 -> s stays 0;   n == 1: B = MB = 0 -> s' = v
+//   backward slide (undo the newest push, re-append the digit that had dropped out):
+//        s = floor(s' / B) + v_old * M        n == 0: everything 0
+struct QueueDev {
+    uint32_t B, m, sh, MB, vmul;  // forward
+    uint32_t mb, shb, powmul;     // backward
+    uint32_t depth;               // n
+};
 
 // parameters of one ContextSpecGenerator (generic or light); "dummy" is generic<0,0,0>
 struct SpecDev {
-    uint32_t ao, qo, pb, light, qmax;
-    uint32_t base_a, base_q;  // 5/94 generic, 4/qmax light
-    uint32_t abits, qbits;    // IntQueue::num_bits
-    uint32_t pow_a, pow_q;    // base^(order-1)  (IntQueue::last_pow), 0 when order == 0
-    FastDiv div_base_a, div_base_q;  // backward slide: state / base
-    FastDiv div_pow_a, div_pow_q;    // forward push: state % last_pow
+    QueueDev qa, qq;  // acid queue, quality score queue
+    uint32_t abits;   // IntQueue::num_bits of the acid queue
+    uint32_t pb;      // position bits
+    // symbol mapping (LightContextSpecGenerator::update, context_spec.rs:516-529): generic asub = 0, qmul = 2^20
+    uint32_t asub, qmul, light;
 };
 
 struct ModelDev {
@@ -59,7 +76,7 @@ struct ModelDev {
     const uint16_t* hvals;
     uint32_t hmask;
     const uint2* enc;             // [n_rows][nsym] {rcp_freq, start | freq << 14 | rcp_shift << 28}
-    const uint16_t* dec;          // acid: [n_rows][4] = cum[1..4]; q: [n_rows][kQRowStride]
+    const uint8_t* dec;           // acid: [n_rows] x 8 bytes = cum[1..4] u16; q: [n_rows] x kQRowBytes
 };
 
 __device__ __forceinline__ uint32_t hash32(uint32_t k) {
@@ -84,114 +101,121 @@ __device__ __forceinline__ uint32_t ctx_row(const ModelDev& m, uint32_t spec) {
     }
 }
 
-// LightContextSpecGenerator::update mapping  (context_spec.rs:516-529)
-__device__ __forceinline__ void light_map(uint32_t a, uint32_t q, uint32_t qmax, uint32_t& va, uint32_t& vq) {
-    if (a == 0 || q == 0) {
-        va = 0;
-        vq = 0;
-    } else {
-        va = a - 1;
-        vq = (q * qmax * 11156u) >> 20;  // q*qmax/94, exact for q*qmax <= 8742
-    }
+// (acid, q) -> queue digits.  z = (acid == N || q == 0), computed once per symbol for both generators.
+__device__ __forceinline__ void map_syms(const SpecDev& s, uint32_t a, uint32_t q, bool z, uint32_t& va, uint32_t& vq) {
+    va = a - s.asub;
+    vq = (q * s.qmul) >> 20;  // light: q * qmax / 94 (exact for q * qmax <= 8742); generic: q
+    const bool kill = z && s.light != 0;
+    va = kill ? 0u : va;
+    vq = kill ? 0u : vq;
 }
 
+__device__ __forceinline__ uint32_t queue_push(const QueueDev& k, uint32_t s, uint32_t v) {
+    uint32_t q = __umulhi(s, k.m) >> k.sh;
+    return s * k.B - q * k.MB + v * k.vmul;
+}
+__device__ __forceinline__ uint32_t queue_slide_back(const QueueDev& k, uint32_t s, uint32_t v_old) {
+    return (__umulhi(s, k.mb) >> k.shb) + v_old * k.powmul;
+}
+
+// position(i) = floor(i * 2^pb / len)   (context_spec.rs:313-316), kept for pbmax = the larger pb of the two
+// generators of a read; floor(floor(x * 2^k) / 2^k) = floor(x), so each generator shifts it down to its own pb.
+struct PosFwd {
+    uint32_t pos, rem, step, frac, len;
+    __device__ __forceinline__ void init(uint32_t length, uint32_t pbmax) {
+        len = length ? length : 1;
+        uint32_t P = 1u << pbmax;
+        step = P / len;
+        frac = P - step * len;
+        pos = rem = 0;
+    }
+    __device__ __forceinline__ void advance() {
+        pos += step;
+        rem += frac;
+        if (rem >= len) {
+            rem -= len;
+            pos++;
+        }
+    }
+};
+struct PosBack {  // starts at i = len and steps down
+    uint32_t pos, rem, step, frac, len;
+    __device__ __forceinline__ void init(uint32_t length, uint32_t pbmax) {
+        len = length ? length : 1;
+        uint32_t P = 1u << pbmax;
+        step = P / len;
+        frac = P - step * len;
+        pos = P;  // len * P / len
+        rem = 0;
+    }
+    __device__ __forceinline__ void retreat() {
+        pos -= step;
+        if (rem < frac) {
+            rem += len;
+            pos--;
+        }
+        rem -= frac;
+    }
+};
+
 // ---------------------------------------------------------------------------------------------------
-// Forward generator: used by the scorer and the decoder (symbols become known one by one).
+// Forward generator: scorer, decoder, workload generator (symbols become known one by one).
 //   current_context  context_spec.rs:377-383 / 508-514      update  :385-389 / :516-529
 // ---------------------------------------------------------------------------------------------------
 struct GenFwd {
-    uint32_t sa, sq;   // queue states, initial 0 (int_queue.rs:24-30)
-    uint32_t pos, rem; // pos = floor(i * 2^pb / len), rem = i * 2^pb - pos * len
-
-    __device__ __forceinline__ void init() { sa = sq = pos = rem = 0; }
-
-    __device__ __forceinline__ uint32_t spec(const SpecDev& s) const {
-        return (((sq << s.abits) | sa) << s.pb) | pos;
+    uint32_t sa, sq;  // queue states, initial 0 (int_queue.rs:24-30)
+    __device__ __forceinline__ void init() { sa = sq = 0; }
+    // pos_shared = PosFwd::pos at pbmax, pshift = pbmax - s.pb
+    __device__ __forceinline__ uint32_t spec(const SpecDev& s, uint32_t pos_shared, uint32_t pshift) const {
+        return (((sq << s.abits) | sa) << s.pb) | (pos_shared >> pshift);
     }
-
-    __device__ __forceinline__ void update(const SpecDev& s, uint32_t a, uint32_t q, uint32_t len) {
-        uint32_t va = a, vq = q;
-        if (s.light) light_map(a, q, s.qmax, va, vq);
-        if (s.ao) sa = (sa - fastdiv(sa, s.div_pow_a) * s.pow_a) * s.base_a + va;
-        if (s.qo) sq = (sq - fastdiv(sq, s.div_pow_q) * s.pow_q) * s.base_q + vq;
-        if (s.pb) {
-            rem += 1u << s.pb;
-            while (rem >= len) {
-                rem -= len;
-                pos++;
-            }
-        }
+    __device__ __forceinline__ void update(const SpecDev& s, uint32_t a, uint32_t q, bool z) {
+        uint32_t va, vq;
+        map_syms(s, a, q, z, va, vq);
+        sa = queue_push(s.qa, sa, va);
+        sq = queue_push(s.qq, sq, vq);
     }
 };
 
 // ---------------------------------------------------------------------------------------------------
-// Symbol window for the backward (encode) pass: entries e_k = symbol at position i-k, k = 0..8.
-// acids: 3 bits per entry in a u32; quality scores: 7 bits per entry in a u64.
+// Backward generator (encoder: symbols are walked last -> first).  Keeps the digits of the positions
+// i-k, k = 0..kHist, in two shift registers (3 bits per acid digit, 7 bits per q digit) fed kHist positions
+// ahead of the encode position; the state at i is the state at i+1 with the newest digit removed and the digit
+// of position i - depth re-appended.
 // ---------------------------------------------------------------------------------------------------
-struct SymWindow {
-    uint32_t wa;
-    unsigned long long wq;
-    __device__ __forceinline__ void init() {
-        wa = 0;
-        wq = 0;
-    }
-    __device__ __forceinline__ void shift_in(uint32_t a, uint32_t q) {
-        wa = (wa >> 3) | (a << (3 * kHist));
-        wq = (wq >> 7) | ((unsigned long long)q << (7 * kHist));
-    }
-    __device__ __forceinline__ uint32_t acid(uint32_t k) const { return (wa >> (3 * k)) & 7u; }
-    __device__ __forceinline__ uint32_t qual(uint32_t k) const { return (uint32_t)(wq >> (7 * k)) & 127u; }
-};
-
-// Backward generator: state at position i is rebuilt from the symbols i-order .. i-1 held in the window.
-//   state_i = floor(state_{i+1} / base) + v[i - order] * base^(order-1)
 struct GenBack {
     uint32_t sa, sq;
-    uint32_t pos, rem;
+    uint32_t wa;             // entry k at bits 3k
+    unsigned long long wq;   // entry k at bits 7k
+    uint32_t sha, shq;       // 3 * depth_a, 7 * depth_q
 
-    // state at position `len` (all symbols consumed); the window holds e_k = symbol at len-k
-    __device__ __forceinline__ void init(const SpecDev& s, const SymWindow& w, uint32_t len) {
+    __device__ __forceinline__ void clear(const SpecDev& s) {
         sa = sq = 0;
-        for (uint32_t k = s.ao; k >= 1; k--) {
-            uint32_t va = w.acid(k), vq = w.qual(k);
-            if (s.light) light_map(va, vq, s.qmax, va, vq);
-            sa = sa * s.base_a + va;
-        }
-        for (uint32_t k = s.qo; k >= 1; k--) {
-            uint32_t va = w.acid(k), vq = w.qual(k);
-            if (s.light) light_map(va, vq, s.qmax, va, vq);
-            sq = sq * s.base_q + vq;
-        }
-        // position(len) = len * 2^pb / len
-        pos = 1u << s.pb;
-        rem = 0;
-        if (s.pb == 0) pos = 0;
+        wa = 0;
+        wq = 0;
+        sha = 3 * s.qa.depth;
+        shq = 7 * s.qq.depth;
     }
-
-    // move from position i+1 to i; the window has already been shifted so that e_0 = symbol i
-    __device__ __forceinline__ void step_back(const SpecDev& s, const SymWindow& w, uint32_t len) {
-        if (s.ao) {
-            uint32_t va = w.acid(s.ao), vq = w.qual(s.ao);
-            if (s.light) light_map(va, vq, s.qmax, va, vq);
-            sa = fastdiv(sa, s.div_base_a) + va * s.pow_a;
-        }
-        if (s.qo) {
-            uint32_t va = w.acid(s.qo), vq = w.qual(s.qo);
-            if (s.light) light_map(va, vq, s.qmax, va, vq);
-            sq = fastdiv(sq, s.div_base_q) + vq * s.pow_q;
-        }
-        if (s.pb) {  // i*P = pos*len + rem  ->  (i-1)*P
-            uint32_t P = 1u << s.pb;
-            while (rem < P) {
-                rem += len;
-                pos--;
-            }
-            rem -= P;
-        }
+    // pull the symbol of the position kHist places before the one that becomes entry 0 (zeros before the read starts)
+    __device__ __forceinline__ void shift_in(const SpecDev& s, uint32_t a, uint32_t q, bool z) {
+        uint32_t va, vq;
+        map_syms(s, a, q, z, va, vq);
+        wa = (wa >> 3) | (va << (3 * kHist));
+        wq = (wq >> 7) | ((unsigned long long)vq << (7 * kHist));
     }
-
-    __device__ __forceinline__ uint32_t spec(const SpecDev& s) const {
-        return (((sq << s.abits) | sa) << s.pb) | pos;
+    // state at position `len` once the window holds entry k = digit of position len - k:  push digits oldest first
+    __device__ __forceinline__ void init_state(const SpecDev& s) {
+        sa = sq = 0;
+        for (uint32_t k = s.qa.depth; k >= 1; k--) sa = queue_push(s.qa, sa, (wa >> (3 * k)) & 7u);
+        for (uint32_t k = s.qq.depth; k >= 1; k--) sq = queue_push(s.qq, sq, (uint32_t)(wq >> (7 * k)) & 127u);
+    }
+    // from position i+1 to i; the window has already been shifted so that entry 0 is position i
+    __device__ __forceinline__ void step_back(const SpecDev& s) {
+        sa = queue_slide_back(s.qa, sa, (wa >> sha) & 7u);
+        sq = queue_slide_back(s.qq, sq, (uint32_t)(wq >> shq) & 127u);
+    }
+    __device__ __forceinline__ uint32_t spec(const SpecDev& s, uint32_t pos_shared, uint32_t pshift) const {
+        return (((sq << s.abits) | sa) << s.pb) | (pos_shared >> pshift);
     }
 };
 
@@ -226,51 +250,31 @@ __device__ __forceinline__ void rans_put_count(uint32_t& x, uint2 e, uint32_t& b
     x = x + start + q * ((1u << kScaleBits) - freq);
 }
 
-// count of 16-bit lanes a (<= 0x7fff each) with a <= s, over a 32-bit word holding two of them
-__device__ __forceinline__ uint32_t le_mask2(uint32_t w, uint32_t ss) {
-    return ((ss | 0x80008000u) - w) & 0x80008000u;
-}
-
 // acid symbol search: packed = cum[1..4] as 4 x u16.  returns symbol, sets start/freq
 __device__ __forceinline__ uint32_t acid_find(uint2 packed, uint32_t slot, uint32_t& start, uint32_t& freq) {
-    uint32_t ss = slot | (slot << 16);
-    uint32_t sym = __popc(le_mask2(packed.x, ss)) + __popc(le_mask2(packed.y, ss));  // #(cum[1..4] <= slot)
-    unsigned long long all = ((unsigned long long)packed.y << 32) | packed.x;        // field k = cum[k+1]
-    start = sym == 0 ? 0u : (uint32_t)(all >> (16 * (sym - 1))) & 0xffffu;
-    uint32_t next = sym == 4 ? (1u << kScaleBits) : (uint32_t)(all >> (16 * sym)) & 0xffffu;
+    const uint32_t c1 = packed.x & 0xffffu, c2 = packed.x >> 16, c3 = packed.y & 0xffffu, c4 = packed.y >> 16;
+    const bool p1 = slot >= c1, p2 = slot >= c2, p3 = slot >= c3, p4 = slot >= c4;
+    start = p4 ? c4 : (p3 ? c3 : (p2 ? c2 : (p1 ? c1 : 0u)));
+    const uint32_t next = !p1 ? c1 : (!p2 ? c2 : (!p3 ? c3 : (!p4 ? c4 : (1u << kScaleBits))));
     freq = next - start;
-    return sym;
+    return p4 ? 4u : (p3 ? 3u : (p2 ? 2u : (p1 ? 1u : 0u)));
 }
 
-__device__ __forceinline__ uint32_t sel4(uint4 v, uint32_t i) {
-    return (i & 2) ? ((i & 1) ? v.w : v.z) : ((i & 1) ? v.y : v.x);
-}
-__device__ __forceinline__ uint32_t half_of(uint32_t w, uint32_t odd) { return odd ? (w >> 16) : (w & 0xffffu); }
-
-// q-score symbol search in a decode row: 16 pivots (cum[8k], padded 0x7fff) then 96 cums (padded 0x7fff
-// after cum[94] = 16384).  Two dependent 16/32-byte vector loads, everything else in registers.
-__device__ __forceinline__ uint32_t q_find(const uint16_t* __restrict__ row, uint32_t slot, uint32_t& start,
+// q-score symbol search in a decode row (layout above): bucket LUT -> group of 4 symbols -> compare/select in
+// registers.  A bucket of 128 slots that spans more than one group (only possible in the low-probability tail of a
+// distribution) advances group by group.
+__device__ __forceinline__ uint32_t q_find(const uint8_t* __restrict__ row, uint32_t slot, uint32_t& start,
                                            uint32_t& freq) {
-    const uint4* r4 = reinterpret_cast<const uint4*>(row);
-    uint4 p0 = __ldg(r4), p1 = __ldg(r4 + 1);
-    uint32_t ss = slot | (slot << 16);
-    uint32_t m = le_mask2(p0.x, ss) | (le_mask2(p0.y, ss) >> 1) | (le_mask2(p0.z, ss) >> 2) |
-                 (le_mask2(p0.w, ss) >> 3) | (le_mask2(p1.x, ss) >> 4) | (le_mask2(p1.y, ss) >> 5) |
-                 (le_mask2(p1.z, ss) >> 6) | (le_mask2(p1.w, ss) >> 7);
-    uint32_t b = __popc(m) - 1;   // pivot[0] = 0 <= slot always
-    uint4 c = __ldg(r4 + 2 + b);  // cum[8b .. 8b+7]
-    uint32_t mm = le_mask2(c.x, ss) | (le_mask2(c.y, ss) >> 1) | (le_mask2(c.z, ss) >> 2) | (le_mask2(c.w, ss) >> 3);
-    uint32_t j = __popc(mm) - 1;  // 0..7
-    start = half_of(sel4(c, j >> 1), j & 1);
-    uint32_t j1 = j + 1, next;
-    if (j1 < 8) {
-        next = half_of(sel4(c, j1 >> 1), j1 & 1);
-    } else {  // cum[8(b+1)] = pivot[b+1]; b <= 10 here (bucket 11 ends at j = 5)
-        uint32_t b1 = b + 1;
-        next = half_of((b1 & 8) ? sel4(p1, (b1 >> 1) & 3) : sel4(p0, (b1 >> 1) & 3), b1 & 1);
-    }
-    freq = next - start;
-    return b * kQBucket + j;
+    uint32_t g = __ldg(row + (slot >> 7));
+    const uint4* groups = reinterpret_cast<const uint4*>(row + kQLutBytes);
+    const uint32_t T = (slot + 1) << 16;  // word = freq | start << 16:  start <= slot  <=>  word < T
+    uint4 w = __ldg(groups + g);
+    while (slot >= (w.w >> 16) + (w.w & 0xffffu)) w = __ldg(groups + ++g);  // beyond the group's last symbol
+    const bool p1 = w.y < T, p2 = w.z < T, p3 = w.w < T;
+    const uint32_t e = p3 ? w.w : (p2 ? w.z : (p1 ? w.y : w.x));
+    start = e >> 16;
+    freq = e & 0xffffu;
+    return 4 * g + (p3 ? 3u : (p2 ? 2u : (p1 ? 1u : 0u)));
 }
 
 }  // namespace idn

@@ -87,6 +87,7 @@ struct idn_gpu_ctx {
     std::vector<ProfMark> prof_marks;
     std::vector<ModelSlot> slots;
     ModelDev* d_models = nullptr;  // [kMaxSlots], mirrors slots[].dev
+    ModelDev d_models_host0{};     // all-zero placeholder for the by-value model parameters of the non-uniform kernels
     uint32_t* d_crc_tab = nullptr;  // [256]
     uint32_t* d_xpow = nullptr;     // [64]
     // workspaces of the *_dev paths
@@ -161,38 +162,61 @@ uint64_t ipow(uint64_t b, uint32_t n) {
     return r;
 }
 
-// IntQueue::num_bits (int_queue.rs:40-43) and the generator parameters (context_spec.rs:218-529)
+// IntQueue<B, n> constants for the branch-free push / slide of idn_device.cuh
+bool make_queue(uint32_t base, uint32_t order, QueueDev* q, uint32_t* bits) {
+    memset(q, 0, sizeof *q);
+    q->depth = order;
+    uint64_t pw = ipow(base, order);  // B^n
+    if (pw > (1ull << 31)) return false;
+    *bits = bitlen(pw - 1);  // IntQueue::num_bits (int_queue.rs:40-43)
+    if (order == 0) return true;  // everything 0: the state stays 0
+    q->vmul = 1;
+    uint32_t M = (uint32_t)ipow(base, order - 1);
+    q->powmul = M;
+    Magic mb = make_magic(base);  // base >= 2 whenever order >= 1 (light qmax = 1 is handled by the caller)
+    q->mb = mb.m;
+    q->shb = mb.s;
+    if (order >= 2) {
+        q->B = base;
+        Magic mm = make_magic(M);
+        q->m = mm.m;
+        q->sh = mm.s;
+        q->MB = (uint32_t)((uint64_t)M * base);
+    }
+    return true;
+}
+
+// generator parameters (context_spec.rs:218-529)
 bool make_spec(int32_t kind, int32_t ao, int32_t qo, int32_t pb, int32_t qmax, SpecDev* s, uint32_t* total_bits) {
     if (kind != IDN_SPEC_GENERIC && kind != IDN_SPEC_LIGHT) return false;
     if (ao < 0 || ao > kHist || qo < 0 || qo > kHist || pb < 0 || pb > 16) return false;
     memset(s, 0, sizeof *s);
-    s->ao = (uint32_t)ao;
-    s->qo = (uint32_t)qo;
     s->pb = (uint32_t)pb;
     s->light = kind == IDN_SPEC_LIGHT;
+    uint32_t base_a = 5, base_q = 94;
+    s->asub = 0;
+    s->qmul = 1u << 20;
     if (s->light) {
         if (qmax < 1 || qmax > 94) return false;
-        s->qmax = (uint32_t)qmax;
-        s->base_a = 4;
-        s->base_q = (uint32_t)qmax;
-        for (uint32_t q = 0; q < 94; q++)  // the multiply-shift in light_map must equal q*qmax/94
-            if (((q * s->qmax * 11156u) >> 20) != q * s->qmax / 94) return false;
-    } else {
-        s->base_a = 5;
-        s->base_q = 94;
+        base_a = 4;
+        base_q = (uint32_t)qmax;
+        s->asub = 1;
+        s->qmul = (uint32_t)qmax * 11156u;
+        for (uint32_t q = 0; q < 94; q++)  // the multiply-shift in map_syms must equal q*qmax/94
+            if (((q * s->qmul) >> 20) != q * (uint32_t)qmax / 94) return false;
     }
-    uint64_t pa = ipow(s->base_a, s->ao), pq = ipow(s->base_q, s->qo);
-    if (pa > (1ull << 31) || pq > (1ull << 31)) return false;
-    s->abits = bitlen(pa - 1);
-    s->qbits = bitlen(pq - 1);
-    if (s->abits + s->qbits + s->pb > 31) return false;
-    s->pow_a = s->ao ? (uint32_t)ipow(s->base_a, s->ao - 1) : 0;
-    s->pow_q = s->qo ? (uint32_t)ipow(s->base_q, s->qo - 1) : 0;
-    s->div_base_a = make_fastdiv(s->base_a);
-    s->div_base_q = make_fastdiv(s->base_q);
-    s->div_pow_a = make_fastdiv(s->pow_a);
-    s->div_pow_q = make_fastdiv(s->pow_q);
-    *total_bits = s->abits + s->qbits + s->pb;
+    uint32_t qbits = 0;
+    if (!make_queue(base_a, (uint32_t)ao, &s->qa, &s->abits)) return false;
+    if (base_q == 1) {
+        // IntQueue<1, n>: every digit is 0 and the state stays 0 (light qmax = 1, e.g. light_ao8_qo0_pb0_qm1)
+        memset(&s->qq, 0, sizeof s->qq);
+        s->qq.depth = (uint32_t)qo;
+        qbits = 0;
+    } else if (!make_queue(base_q, (uint32_t)qo, &s->qq, &qbits)) {
+        return false;
+    }
+    if (s->abits + qbits + s->pb > 31) return false;
+    *total_bits = s->abits + qbits + s->pb;
     return true;
 }
 
@@ -418,23 +442,32 @@ extern "C" int32_t idn_gpu_model_upload(idn_gpu_ctx* ctx, int32_t model_type, in
     slot.dev.enc = (const uint2*)slot.d_enc;
 
     // decoder rows: cumulative frequencies searched directly (no 2^14-entry LUT per context)
-    std::vector<uint16_t> dec;
+    std::vector<uint8_t> dec;
     if (model_type == IDN_MODEL_ACID) {
-        dec.resize((size_t)n_rows * 4);
+        dec.resize((size_t)n_rows * 8);
         for (uint32_t r = 0; r < n_rows; r++)
-            for (uint32_t k = 0; k < 4; k++) dec[(size_t)r * 4 + k] = cum[(size_t)r * 6 + 1 + k];
+            for (uint32_t k = 0; k < 4; k++) {
+                uint16_t c = cum[(size_t)r * 6 + 1 + k];
+                memcpy(dec.data() + (size_t)r * 8 + 2 * k, &c, 2);
+            }
     } else {
-        dec.assign((size_t)n_rows * kQRowStride, 0x7fff);
+        dec.assign((size_t)n_rows * kQRowBytes, 0);
         for (uint32_t r = 0; r < n_rows; r++) {
             const uint16_t* row = cum + (size_t)r * 95;
-            uint16_t* d = dec.data() + (size_t)r * kQRowStride;
-            for (uint32_t k = 0; k < 16; k++) d[k] = 8 * k <= 94 ? row[8 * k] : 0x7fff;
-            for (uint32_t k = 0; k < 95; k++) d[16 + k] = row[k];
+            uint8_t* d = dec.data() + (size_t)r * kQRowBytes;
+            uint32_t* words = reinterpret_cast<uint32_t*>(d + kQLutBytes);
+            for (uint32_t sidx = 0; sidx < (uint32_t)kQGroups * 4; sidx++)
+                words[sidx] = sidx < 94 ? ((uint32_t)(row[sidx + 1] - row[sidx]) | ((uint32_t)row[sidx] << 16)) : (total << 16);
+            uint32_t sidx = 0;
+            for (uint32_t k = 0; k < (uint32_t)kQLutBytes; k++) {  // group of the symbol that owns slot 128 k
+                while (row[sidx + 1] <= 128 * k) sidx++;
+                d[k] = (uint8_t)(sidx >> 2);
+            }
         }
     }
-    CU(cudaMalloc(&slot.d_dec, dec.size() * sizeof(uint16_t)));
-    CU(cudaMemcpy(slot.d_dec, dec.data(), dec.size() * sizeof(uint16_t), cudaMemcpyHostToDevice));
-    slot.dev.dec = (const uint16_t*)slot.d_dec;
+    CU(cudaMalloc(&slot.d_dec, dec.size()));
+    CU(cudaMemcpy(slot.d_dec, dec.data(), dec.size(), cudaMemcpyHostToDevice));
+    slot.dev.dec = (const uint8_t*)slot.d_dec;
     slot.used = true;
 
     size_t idx = ctx->slots.size();
@@ -638,7 +671,11 @@ extern "C" int32_t idn_gpu_compress_blocks_dev(idn_gpu_ctx* ctx, const idn_batch
         ea.scratch = ctx->w_scratch.as<uint8_t>();
         ea.pay_len = ctx->w_paylen.as<uint32_t>();
         ea.err = &dsp->err;
-        encode_kernel<<<(unsigned)((R + 127) / 128), 128, 0, st>>>(ea);
+        const bool uniform = !chosen || (sp.n_cand[0] == 1 && sp.n_cand[1] == 1);
+        const ModelDev& hma = ctx->slots[sp.cand_model[0]].dev;
+        const ModelDev& hmq = ctx->slots[sp.cand_model[kMaxCand]].dev;
+        if (uniform) encode_kernel<true><<<(unsigned)((R + 127) / 128), 128, 0, st>>>(ea, hma, hmq);
+        else encode_kernel<false><<<(unsigned)((R + 127) / 128), 128, 0, st>>>(ea, hma, hmq);
         LAUNCHED("encode");
     }
 
@@ -969,7 +1006,14 @@ extern "C" int32_t idn_gpu_decompress_blocks_dev(idn_gpu_ctx* ctx, const uint8_t
     da.read_status = nullptr;
     da.err = &dsp->err;
     if (out_reads_cap && n_blocks) {
-        decode_kernel<<<(unsigned)((out_reads_cap + 127) / 128), 128, 0, st>>>(da);
+        // one acid + one q-score model: every read uses that pair (the walk rejects anything else)
+        int ua = -1, uq = -1, na = 0, nq = 0;
+        for (uint32_t i = 0; i < n_models; i++) {
+            if (ctx->slots[models[i]].dev.type == IDN_MODEL_ACID) { ua = models[i]; na++; } else { uq = models[i]; nq++; }
+        }
+        const unsigned grid = (unsigned)((out_reads_cap + 127) / 128);
+        if (na == 1 && nq == 1) decode_kernel<true><<<grid, 128, 0, st>>>(da, ctx->slots[ua].dev, ctx->slots[uq].dev);
+        else decode_kernel<false><<<grid, 128, 0, st>>>(da, ctx->d_models_host0, ctx->d_models_host0);
         LAUNCHED("decode");
     }
     // CRC of the decoded symbols per block, compared with the header value (decompressor_block.rs:131-144)
@@ -1210,7 +1254,7 @@ extern "C" int32_t idn_gpu_decompress_reads(idn_gpu_ctx* ctx, const uint8_t* pay
     da.read_off_out = nullptr;
     da.read_status = ctx->s_idx.as<uint32_t>();
     da.err = &dsp->err;
-    decode_kernel<<<(unsigned)((R + 127) / 128), 128, 0, st>>>(da);
+    decode_kernel<false><<<(unsigned)((R + 127) / 128), 128, 0, st>>>(da, ctx->d_models_host0, ctx->d_models_host0);
     LAUNCHED("decode");
     uint32_t err = 0;
     if (S) {

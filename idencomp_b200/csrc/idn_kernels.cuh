@@ -22,12 +22,17 @@ struct BackReader {  // reads bytes at decreasing global indices
     __device__ __forceinline__ void init(const uint8_t* b) {
         mis = (uint32_t)(reinterpret_cast<uintptr_t>(b) & 3);
         base = b - mis;
-        word = 0xffffffffu;
+        word = 0;
+    }
+    // first call: g is the highest index that will be read
+    __device__ __forceinline__ void prime(long long g) {
+        g += mis;
+        word = __ldg(reinterpret_cast<const uint32_t*>(base + (g & ~3ll)));
     }
     __device__ __forceinline__ uint32_t get(long long g) {  // g may be < first valid index -> caller guards
         g += mis;
         uint32_t sh = (uint32_t)(g & 3) * 8;
-        if (sh == 24 || word == 0xffffffffu) word = __ldg(reinterpret_cast<const uint32_t*>(base + (g & ~3ll)));
+        if (sh == 24) word = __ldg(reinterpret_cast<const uint32_t*>(base + (g & ~3ll)));
         return (word >> sh) & 0xffu;
     }
 };
@@ -35,20 +40,20 @@ struct BackReader {  // reads bytes at decreasing global indices
 struct FwdReader {  // reads bytes at increasing global indices
     const uint8_t* base;  // rounded down to a 4-byte boundary; `mis` bytes were dropped
     uint32_t word, mis;
-    bool primed;
     __device__ __forceinline__ void init(const uint8_t* b) {
         mis = (uint32_t)(reinterpret_cast<uintptr_t>(b) & 3);
         base = b - mis;
-        primed = false;
         word = 0;
+    }
+    // first call: g is the lowest index that will be read
+    __device__ __forceinline__ void prime(unsigned long long g) {
+        g += mis;
+        word = __ldg(reinterpret_cast<const uint32_t*>(base + (g & ~3ull)));
     }
     __device__ __forceinline__ uint32_t get(unsigned long long g) {
         g += mis;
         uint32_t sh = (uint32_t)(g & 3) * 8;
-        if (sh == 0 || !primed) {
-            word = __ldg(reinterpret_cast<const uint32_t*>(base + (g & ~3ull)));
-            primed = true;
-        }
+        if (sh == 0) word = __ldg(reinterpret_cast<const uint32_t*>(base + g));
         return (word >> sh) & 0xffu;
     }
 };
@@ -81,30 +86,33 @@ struct BackWriter {
     }
 };
 
-// writes bytes at increasing addresses starting anywhere
+// writes one byte per call at increasing addresses starting anywhere: bytes are collected into aligned words; the
+// partial words at the two ends of the range (shared with the neighbouring reads) are written byte by byte
 struct FwdWriter {
-    uint8_t* p;
-    uint32_t acc, n;
+    uint8_t* wbase;  // aligned address of the word being filled
+    uint32_t acc, lane, first;  // lane = byte of the word the next push fills; first = first lane this range owns
     __device__ __forceinline__ void init(uint8_t* dst) {
-        p = dst;
+        lane = (uint32_t)(reinterpret_cast<uintptr_t>(dst) & 3);
+        first = lane;
+        wbase = dst - lane;
         acc = 0;
-        n = 0;
     }
     __device__ __forceinline__ void push(uint32_t b) {
-        if ((reinterpret_cast<uintptr_t>(p) & 3) != 0 && n == 0) {  // head: byte stores until aligned
-            *p++ = (uint8_t)b;
-            return;
-        }
-        acc |= b << (8 * n);
-        if (++n == 4) {
-            *reinterpret_cast<uint32_t*>(p) = acc;
-            p += 4;
+        acc |= b << (8 * lane);
+        if (++lane == 4) {
+            if (first == 0) {
+                *reinterpret_cast<uint32_t*>(wbase) = acc;
+            } else {
+                for (uint32_t k = first; k < 4; k++) wbase[k] = (uint8_t)(acc >> (8 * k));
+                first = 0;
+            }
+            wbase += 4;
             acc = 0;
-            n = 0;
+            lane = 0;
         }
     }
     __device__ __forceinline__ void finish() {
-        for (uint32_t k = 0; k < n; k++) p[k] = (uint8_t)(acc >> (8 * k));
+        for (uint32_t k = first; k < lane; k++) wbase[k] = (uint8_t)(acc >> (8 * k));
     }
 };
 
@@ -121,15 +129,24 @@ score_kernel(const ModelDev* __restrict__ models, const int32_t* __restrict__ mo
     if (r >= n_reads) return;
     uint32_t mi = (uint32_t)(t - r * n_models);
     const ModelDev& m = models[model_ids[mi]];
+    const SpecDev sp = m.spec;
     uint64_t off = read_off[r];
     uint32_t len = (uint32_t)(read_off[r + 1] - off);
     GenFwd g;
     g.init();
+    PosFwd pf;
+    pf.init(len, sp.pb);
     FwdReader ra, rq;
     ra.init(acids);
     rq.init(quals);
+    if (len) {
+        ra.prime(off);
+        rq.prime(off);
+    }
     uint32_t x = kRansL, bytes = 0;
     bool bad = false;
+    const bool is_acid = m.type == 0;
+#pragma unroll 1
     for (uint32_t i = 0; i < len; i++) {
         uint32_t a = ra.get(off + i), q = rq.get(off + i);
         if (a > 4 || q > 93) {
@@ -137,11 +154,12 @@ score_kernel(const ModelDev* __restrict__ models, const int32_t* __restrict__ mo
             a = a > 4 ? 0 : a;
             q = q > 93 ? 0 : q;
         }
-        uint32_t row = ctx_row(m, g.spec(m.spec));
-        uint32_t sym = m.type == 0 ? a : q;
+        uint32_t row = ctx_row(m, g.spec(sp, pf.pos, 0));
+        uint32_t sym = is_acid ? a : q;
         uint2 e = __ldg(m.enc + (size_t)row * m.nsym + sym);
         rans_put_count(x, e, bytes);
-        g.update(m.spec, a, q, len);
+        g.update(sp, a, q, a * q == 0);
+        pf.advance();
     }
     sizes[r * n_models + mi] = bytes + 4;
     if (bad) atomicOr(err, 1u);
@@ -242,17 +260,26 @@ struct EncodeArgs {
     uint32_t* err;
 };
 
+// kUniform: every read of the batch uses the same model pair; its parameters then live in the kernel parameter
+// space (constant bank operands) instead of ~40 registers per thread, which is what bounds occupancy here.
+//
+// The loop is software-pipelined over three positions because only the 32-bit rANS states are serial in the encoder:
+// while position i is coded, the encoder entry of position i-1 is being gathered and the context row of position i-2
+// is being looked up, so the two dependent L2 gathers per symbol (spec -> row -> entry) overlap with arithmetic.
+template <bool kUniform>
 __global__ void __launch_bounds__(128)
-encode_kernel(EncodeArgs A) {
+encode_kernel(EncodeArgs A, const ModelDev MA, const ModelDev MQ) {
     uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= A.n_reads) return;
     int32_t ia = A.fixed_acid, iq = A.fixed_q;
-    if (A.chosen) {
+    if (!kUniform && A.chosen) {
         ia = A.cand_model[A.chosen[r]];
         iq = A.cand_model[kMaxCand + A.chosen[A.n_reads + r]];
     }
-    const ModelDev& ma = A.models[ia];
-    const ModelDev& mq = A.models[iq];
+    const ModelDev& ma = kUniform ? MA : A.models[ia];
+    const ModelDev& mq = kUniform ? MQ : A.models[iq];
+    const SpecDev& sa = ma.spec;
+    const SpecDev& sq = mq.spec;
     const long long off = (long long)A.read_off[r];
     const uint32_t len = (uint32_t)(A.read_off[r + 1] - A.read_off[r]);
     uint8_t* slot_end = A.scratch + 4ull * A.read_off[r + 1] + 8ull * (r + 1);
@@ -260,10 +287,17 @@ encode_kernel(EncodeArgs A) {
     BackReader ra, rq;
     ra.init(A.acids);
     rq.init(A.quals);
-    SymWindow w;
-    w.init();
+    if (len) {
+        ra.prime(off + len - 1);
+        rq.prime(off + len - 1);
+    }
+    GenBack ga, gq;
+    ga.clear(sa);
+    gq.clear(sq);
     bool bad = false;
-    long long front = (long long)len - 1;  // next position to pull into the window
+    long long front = (long long)len - 1;  // next position to pull into the windows
+    uint32_t raw_a = 0;                    // raw symbols travel in two more shift registers (entry k = position j - k)
+    unsigned long long raw_q = 0;
     auto pull = [&]() {
         uint32_t a = 0, q = 0;
         if (front >= 0) {
@@ -276,15 +310,35 @@ encode_kernel(EncodeArgs A) {
             }
         }
         front--;
-        w.shift_in(a, q);
+        const bool z = a * q == 0;
+        ga.shift_in(sa, a, q, z);
+        gq.shift_in(sq, a, q, z);
+        raw_a = (raw_a >> 3) | (a << (3 * kHist));
+        raw_q = (raw_q >> 7) | ((unsigned long long)q << (7 * kHist));
     };
 #pragma unroll 1
-    for (int t = 0; t < kHist; t++) pull();  // e_k = symbol at len-k
+    for (int t = 0; t < kHist; t++) pull();  // entry k = symbol at len - k
+    ga.init_state(sa);
+    gq.init_state(sq);
+    const uint32_t pbmax = sa.pb > sq.pb ? sa.pb : sq.pb;
+    const uint32_t psa = pbmax - sa.pb, psq = pbmax - sq.pb;
+    PosBack pb;
+    pb.init(len, pbmax);
 
-    GenBack ga, gq;
-    ga.init(ma.spec, w, len);
-    gq.init(mq.spec, w, len);
-
+    // generator stage: moves the generators to position j (entry 0 = symbol j) and looks the two rows up
+    long long j = (long long)len;  // position the generators stand at
+    auto rows_next = [&](uint32_t& row_a, uint32_t& row_q) {
+        j--;
+        row_a = row_q = 0;
+        if (j >= 0) {
+            pull();
+            ga.step_back(sa);
+            gq.step_back(sq);
+            pb.retreat();
+            row_a = ctx_row(ma, ga.spec(sa, pb.pos, psa));
+            row_q = ctx_row(mq, gq.spec(sq, pb.pos, psq));
+        }
+    };
     BackWriter out;
     out.init(slot_end);
     uint32_t total = 0;
@@ -293,18 +347,28 @@ encode_kernel(EncodeArgs A) {
         total++;
     };
     uint32_t x0 = kRansL, x1 = kRansL;  // state 0 = acids, state 1 = quality scores (compressor.rs:95-96)
+    // prologue: rows of position len-1, its entries, rows of position len-2
+    uint32_t row_a, row_q;
+    rows_next(row_a, row_q);  // generators at len-1, entry 0 = symbol len-1
+    uint2 ea = make_uint2(0, 0), eq = make_uint2(0, 0);
+    if (len) {
+        ea = __ldg(ma.enc + (size_t)row_a * kAcidSyms + (raw_a & 7u));
+        eq = __ldg(mq.enc + (size_t)row_q * kQSyms + ((uint32_t)raw_q & 127u));
+    }
+    rows_next(row_a, row_q);  // generators at len-2
 #pragma unroll 1
     for (uint32_t i = len; i-- > 0;) {
-        pull();  // e_0 = symbol i
-        ga.step_back(ma.spec, w, len);
-        gq.step_back(mq.spec, w, len);
-        uint32_t a = w.acid(0), q = w.qual(0);
-        uint32_t row_a = ctx_row(ma, ga.spec(ma.spec));
-        uint32_t row_q = ctx_row(mq, gq.spec(mq.spec));
-        uint2 ea = __ldg(ma.enc + (size_t)row_a * kAcidSyms + a);
-        uint2 eq = __ldg(mq.enc + (size_t)row_q * kQSyms + q);
+        // entries of position i-1 (generators stand at i-1: entry 0), gathered while position i is coded
+        uint2 ea_n = make_uint2(0, 0), eq_n = make_uint2(0, 0);
+        if (i >= 1) {
+            ea_n = __ldg(ma.enc + (size_t)row_a * kAcidSyms + (raw_a & 7u));
+            eq_n = __ldg(mq.enc + (size_t)row_q * kQSyms + ((uint32_t)raw_q & 127u));
+        }
+        rows_next(row_a, row_q);  // generators to i-2
         rans_put(x0, ea, emit);
         rans_put(x1, eq, emit);
+        ea = ea_n;
+        eq = eq_n;
     }
     out.push_u32_le(x0);  // flush_all: state 0 then state 1
     out.push_u32_le(x1);
@@ -602,6 +666,7 @@ __device__ __forceinline__ uint32_t crc_bytes(const uint8_t* __restrict__ base, 
     uint32_t c = 0xffffffffu;
     FwdReader rd;
     rd.init(base);
+    if (n) rd.prime(off);
     for (uint32_t i = 0; i < n; i++) c = tab[(c ^ rd.get(off + i)) & 0xffu] ^ (c >> 8);
     return ~c;
 }
@@ -971,8 +1036,9 @@ struct DecodeArgs {
     uint32_t* err;
 };
 
+template <bool kUniform>
 __global__ void __launch_bounds__(128)
-decode_kernel(DecodeArgs A) {
+decode_kernel(DecodeArgs A, const ModelDev MA, const ModelDev MQ) {
     uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (A.status && A.status[0] != 0) return;
     unsigned long long slot = r, sym_base = 0;
@@ -990,55 +1056,65 @@ decode_kernel(DecodeArgs A) {
     } else if (r >= A.n_reads) {
         return;
     }
-    const ModelDev& ma = A.models[A.model_ids[A.ix.am[slot]]];
-    const ModelDev& mq = A.models[A.model_ids[A.ix.qm[slot]]];
+    const ModelDev& ma = kUniform ? MA : A.models[A.model_ids[A.ix.am[slot]]];
+    const ModelDev& mq = kUniform ? MQ : A.models[A.model_ids[A.ix.qm[slot]]];
     const unsigned long long poff = A.ix.pay_off[slot];
     const uint32_t plen = A.ix.pay_len[slot], len = A.ix.seq_len[slot];
     const unsigned long long ooff = sym_base + A.ix.sym_off[slot];
     if (A.read_off_out) A.read_off_out[r] = ooff;
+    const SpecDev& sa = ma.spec;
+    const SpecDev& sq = mq.spec;
     FwdReader in;
     in.init(A.payload);
+    in.prime(poff);
     uint32_t cur = 0, st = 0;
-    auto next = [&]() -> uint32_t {
-        if (cur >= plen) {
-            st |= 1;
-            return 0;
-        }
-        return in.get(poff + cur++);
-    };
+    auto next = [&]() -> uint32_t { return in.get(poff + cur++); };
+    // a valid payload holds at least the two flushed states; a truncated one is caught by the cur > plen checks below
+    // (reads stay inside the 4-byte words that hold payload bytes or the word right after them)
+    if (plen < 8) st |= 1;
     // RansDecInit x2: decoder state 0 = quality scores, state 1 = acids (compressor.rs:181-182)
-    uint32_t xq = next();
-    xq |= next() << 8;
-    xq |= next() << 16;
-    xq |= next() << 24;
-    uint32_t xa = next();
-    xa |= next() << 8;
-    xa |= next() << 16;
-    xa |= next() << 24;
-
+    uint32_t xq = 0, xa = 0;
+    if (!(st & 1)) {
+        xq = next();
+        xq |= next() << 8;
+        xq |= next() << 16;
+        xq |= next() << 24;
+        xa = next();
+        xa |= next() << 8;
+        xa |= next() << 16;
+        xa |= next() << 24;
+    }
     GenFwd ga, gq;
     ga.init();
     gq.init();
+    const uint32_t pbmax = sa.pb > sq.pb ? sa.pb : sq.pb;
+    const uint32_t psa = pbmax - sa.pb, psq = pbmax - sq.pb;
+    PosFwd pf;
+    pf.init(len, pbmax);
     FwdWriter oa, oq;
     oa.init(A.acids_out + ooff);
     oq.init(A.quals_out + ooff);
 #pragma unroll 1
     for (uint32_t i = 0; i < len && !(st & 1); i++) {
-        uint32_t row_a = ctx_row(ma, ga.spec(ma.spec));
-        uint32_t row_q = ctx_row(mq, gq.spec(mq.spec));
+        uint32_t row_a = ctx_row(ma, ga.spec(sa, pf.pos, psa));
+        uint32_t row_q = ctx_row(mq, gq.spec(sq, pf.pos, psq));
         uint32_t slot_q = xq & kSlotMask, slot_a = xa & kSlotMask;
         uint32_t start, freq;
-        uint32_t sq = q_find(mq.dec + (size_t)row_q * kQRowStride, slot_q, start, freq);
+        uint32_t vq = q_find(mq.dec + (size_t)row_q * kQRowBytes, slot_q, start, freq);
         xq = freq * (xq >> kScaleBits) + slot_q - start;  // RansDecAdvanceStep
         uint2 pk = __ldg(reinterpret_cast<const uint2*>(ma.dec) + row_a);
-        uint32_t sa = acid_find(pk, slot_a, start, freq);
+        uint32_t va = acid_find(pk, slot_a, start, freq);
         xa = freq * (xa >> kScaleBits) + slot_a - start;
-        while (xq < kRansL && !(st & 1)) xq = (xq << 8) | next();  // renorm_all: state 0 then state 1
-        while (xa < kRansL && !(st & 1)) xa = (xa << 8) | next();
-        oa.push(sa);
-        oq.push(sq);
-        ga.update(ma.spec, sa, sq, len);
-        gq.update(mq.spec, sa, sq, len);
+        // renorm_all: state 0 then state 1; at most two bytes each (x >= 2^9 after the advance)
+        while (xq < kRansL && cur < plen) xq = (xq << 8) | next();
+        while (xa < kRansL && cur < plen) xa = (xa << 8) | next();
+        if (xq < kRansL || xa < kRansL) st |= 1;  // the payload ran out
+        oa.push(va);
+        oq.push(vq);
+        const bool z = va * vq == 0;
+        ga.update(sa, va, vq, z);
+        gq.update(sq, va, vq, z);
+        pf.advance();
     }
     oa.finish();
     oq.finish();
@@ -1089,9 +1165,14 @@ synth_kernel(const ModelDev* __restrict__ models, int32_t ia, int32_t iq, const 
     unsigned long long off = read_off[r];
     uint32_t len = (uint32_t)(read_off[r + 1] - off);
     unsigned long long s = seed ^ ((first_read_index + r + 1) * 0xD1B54A32D192ED03ull);
+    const SpecDev sa = ma.spec, sq = mq.spec;
     GenFwd ga, gq;
     ga.init();
     gq.init();
+    const uint32_t pbmax = sa.pb > sq.pb ? sa.pb : sq.pb;
+    const uint32_t psa = pbmax - sa.pb, psq = pbmax - sq.pb;
+    PosFwd pf;
+    pf.init(len, pbmax);
     FwdWriter oa, oq;
     oa.init(acids + off);
     oq.init(quals + off);
@@ -1099,19 +1180,21 @@ synth_kernel(const ModelDev* __restrict__ models, int32_t ia, int32_t iq, const 
         unsigned long long u = splitmix64(s);
         uint32_t slot_a = (uint32_t)u & kSlotMask, slot_q = (uint32_t)(u >> 14) & kSlotMask;
         uint32_t start, freq;
-        uint32_t row_a = ctx_row(ma, ga.spec(ma.spec));
-        uint32_t row_q = ctx_row(mq, gq.spec(mq.spec));
+        uint32_t row_a = ctx_row(ma, ga.spec(sa, pf.pos, psa));
+        uint32_t row_q = ctx_row(mq, gq.spec(sq, pf.pos, psq));
         uint2 pk = __ldg(reinterpret_cast<const uint2*>(ma.dec) + row_a);
         uint32_t a = acid_find(pk, slot_a, start, freq);
-        uint32_t q = q_find(mq.dec + (size_t)row_q * kQRowStride, slot_q, start, freq);
+        uint32_t q = q_find(mq.dec + (size_t)row_q * kQRowBytes, slot_q, start, freq);
         if ((uint32_t)((u >> 32) % 1000000u) < n_ppm) {  // an N call with the Illumina "no call" quality '#'
             a = 0;
             q = 2;
         }
         oa.push(a);
         oq.push(q);
-        ga.update(ma.spec, a, q, len);
-        gq.update(mq.spec, a, q, len);
+        const bool z = a * q == 0;
+        ga.update(sa, a, q, z);
+        gq.update(sq, a, q, z);
+        pf.advance();
     }
     oa.finish();
     oq.finish();
