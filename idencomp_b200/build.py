@@ -31,7 +31,7 @@ def _stale(target: Path, sources) -> bool:
 def build_gpu(force: bool = False, verbose: bool = False) -> Path:
     """libidn_gpu.so: kernels + C-ABI."""
     out = PKG / "libidn_gpu.so"
-    srcs = [CSRC / "idn_gpu.cu", CSRC / "idn_kernels.cuh", CSRC / "idn_device.cuh", ROOT / "include" / "idn_gpu.h"]
+    srcs = [CSRC / "idn_gpu.cu", *sorted(CSRC.glob("*.cuh")), ROOT / "include" / "idn_gpu.h"]
     if force or _stale(out, srcs):
         cmd = [_nvcc(), *NVCC_FLAGS, "-o", str(out), str(CSRC / "idn_gpu.cu")]
         if verbose:

@@ -30,7 +30,7 @@ EXPORTS = [
     "idn_gpu_launch_count", "idn_gpu_model_upload", "idn_gpu_model_release", "idn_gpu_score", "idn_gpu_score_dev",
     "idn_gpu_compress_blocks", "idn_gpu_compress_blocks_dev", "idn_gpu_compress_bound", "idn_gpu_index_blocks",
     "idn_gpu_decompress_blocks", "idn_gpu_decompress_blocks_dev", "idn_gpu_decompress_reads", "idn_gpu_block_crc",
-    "idn_gpu_synth_reads_dev", "idn_gpu_profile", "idn_gpu_profile_read",
+    "idn_gpu_synth_reads_dev", "idn_gpu_profile", "idn_gpu_profile_read", "idn_gpu_set_lane_symbols",
 ]
 
 
@@ -101,7 +101,7 @@ def load():
     L.idn_gpu_compress_blocks_dev.restype = i32
     L.idn_gpu_compress_bound.argtypes = [u64, u64, u32, u64]
     L.idn_gpu_compress_bound.restype = u64
-    L.idn_gpu_index_blocks.argtypes = [vp, vp, vp, vp, u32, vp, u32, C.POINTER(IndexTotals), vp]
+    L.idn_gpu_index_blocks.argtypes = [vp, vp, vp, vp, u32, i32, vp, u32, C.POINTER(IndexTotals), vp]
     L.idn_gpu_index_blocks.restype = i32
     L.idn_gpu_decompress_blocks.argtypes = [vp, vp, vp, vp, vp, u32, i32, vp, u32, vp, vp, vp, vp, vp, u64, u64,
                                             C.POINTER(i32)]
@@ -114,6 +114,8 @@ def load():
     L.idn_gpu_block_crc.restype = i32
     L.idn_gpu_synth_reads_dev.argtypes = [vp, i32, i32, vp, u64, u64, u64, u32, vp, vp, vp]
     L.idn_gpu_synth_reads_dev.restype = i32
+    L.idn_gpu_set_lane_symbols.argtypes = [vp, u32]
+    L.idn_gpu_set_lane_symbols.restype = i32
     L.idn_gpu_profile.argtypes = [vp, i32]
     L.idn_gpu_profile.restype = i32
     L.idn_gpu_profile_read.argtypes = [vp, C.c_char_p, u64]
@@ -191,6 +193,9 @@ class Context:
     def launches(self) -> int:
         return int(self.L.idn_gpu_launch_count(self.h))
 
+    def set_lane_symbols(self, n: int):
+        self.check(self.L.idn_gpu_set_lane_symbols(self.h, n))
+
     def profile(self, enable: bool):
         self.check(self.L.idn_gpu_profile(self.h, int(enable)))
 
@@ -246,14 +251,14 @@ class Context:
             raise e
         return out[:st.out_bytes], block_off, crc[:b.n_blocks], st.as_dict()
 
-    def index_blocks(self, blocks, block_off, models, block_len=None):
+    def index_blocks(self, blocks, block_off, models, block_len=None, mode=MODE_COMPAT):
         blocks = _c(blocks, np.uint8)
         bo = _c(block_off, np.uint64)
         bl = None if block_len is None else _c(block_len, np.uint32)
         m = _c(models, np.int32)
         tot = IndexTotals()
         bf = np.zeros(len(bo), dtype=np.uint32)
-        self.check(self.L.idn_gpu_index_blocks(self.h, _p(blocks), bo.ctypes.data, _p(bl), len(bo) - 1, _p(m), len(m),
+        self.check(self.L.idn_gpu_index_blocks(self.h, _p(blocks), bo.ctypes.data, _p(bl), len(bo) - 1, mode, _p(m), len(m),
                                                C.byref(tot), bf.ctypes.data))
         return int(tot.n_reads), int(tot.n_symbols), bf
 
@@ -265,7 +270,7 @@ class Context:
         m = _c(models, np.int32)
         nb = len(bo) - 1
         if reads_cap is None or symbols_cap is None:
-            reads_cap, symbols_cap, _ = self.index_blocks(blocks, bo, m, bl)
+            reads_cap, symbols_cap, _ = self.index_blocks(blocks, bo, m, bl, mode)
         crc = None if block_crc is None else _c(block_crc, np.uint32)
         a = np.zeros(max(symbols_cap, 1), dtype=np.uint8)
         q = np.zeros(max(symbols_cap, 1), dtype=np.uint8)

@@ -10,7 +10,7 @@
 #include <string>
 #include <vector>
 
-#include "idn_kernels.cuh"
+#include "idn_native.cuh"
 
 using namespace idn;
 
@@ -92,6 +92,8 @@ struct idn_gpu_ctx {
     uint32_t* d_xpow = nullptr;     // [64]
     // workspaces of the *_dev paths
     DevBuf w_scratch, w_paylen, w_sizes, w_chosen, w_tiles, w_sliceoff, w_readblock, w_small, w_crcpart, w_crclen;
+    DevBuf w_lanefirst, w_laneoff, w_laneblock, w_blkinfo, w_nhdr;  // native mode
+    uint32_t lane_syms = 4096;  // lane quantum of the native format
     DevBuf w_index;  // decode-side per-read index
     DevBuf w_blk;    // decode-side per-block counters
     // staging of the host-pointer paths
@@ -336,6 +338,7 @@ extern "C" void idn_gpu_destroy(idn_gpu_ctx* ctx) {
         if (s.used) s.free_all();
     DevBuf* bufs[] = {&ctx->w_scratch, &ctx->w_paylen,  &ctx->w_sizes,   &ctx->w_chosen,     &ctx->w_tiles,  &ctx->w_sliceoff,
                       &ctx->w_readblock, &ctx->w_small, &ctx->w_crcpart, &ctx->w_crclen,     &ctx->w_index,  &ctx->w_blk,
+                      &ctx->w_lanefirst, &ctx->w_laneoff, &ctx->w_laneblock, &ctx->w_blkinfo, &ctx->w_nhdr,
                       &ctx->s_acids,   &ctx->s_quals,   &ctx->s_readoff, &ctx->s_blockfirst, &ctx->s_prefix, &ctx->s_names,
                       &ctx->s_nameoff, &ctx->s_out,     &ctx->s_blockoff, &ctx->s_crc,       &ctx->s_stats,  &ctx->s_sizes,
                       &ctx->s_blocks,  &ctx->s_blocklen, &ctx->s_aout,    &ctx->s_qout,    &ctx->s_offout,     &ctx->s_status, &ctx->s_idx};
@@ -346,6 +349,13 @@ extern "C" void idn_gpu_destroy(idn_gpu_ctx* ctx) {
     if (ctx->ev) cudaEventDestroy(ctx->ev);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
+}
+
+extern "C" int32_t idn_gpu_set_lane_symbols(idn_gpu_ctx* ctx, uint32_t lane_syms) {
+    if (!ctx) return IDN_E_INVALID_ARG;
+    if (lane_syms == 0) return fail(ctx, IDN_E_INVALID_ARG, "lane_syms must be positive");
+    ctx->lane_syms = lane_syms;
+    return IDN_OK;
 }
 
 extern "C" const char* idn_gpu_last_error(const idn_gpu_ctx* ctx) { return ctx ? ctx->err.c_str() : "no context"; }
@@ -579,11 +589,16 @@ extern "C" int32_t idn_gpu_score(idn_gpu_ctx* ctx, const idn_batch* b, const idn
 // ======================================================================================================
 extern "C" uint64_t idn_gpu_compress_bound(uint64_t n_reads, uint64_t n_symbols, uint32_t n_blocks, uint64_t prefix_total) {
     // per read: two switches (4) + sequence header (9) + payload (<= 4*len + 8); per block: header 8 + fast switches 4
-    return 4 * n_symbols + 21 * n_reads + 12ull * n_blocks + prefix_total;
+    // (the native format needs less per read but 30 bytes of headers per block)
+    return 4 * n_symbols + 21 * n_reads + 32ull * n_blocks + prefix_total;
 }
 
 static int32_t idn_gpu_block_crc_dev_impl(idn_gpu_ctx* ctx, const idn_batch* batch, uint32_t* block_crc, uint8_t* out,
                                           const unsigned long long* block_off, uint64_t out_cap, cudaStream_t st);
+static int32_t compress_native_dev(idn_gpu_ctx* ctx, const idn_batch* batch, SmallParams& sp, int32_t fast,
+                                   const uint32_t* prefix_len, uint8_t* out, uint64_t out_cap, uint64_t* block_off,
+                                   uint32_t* block_crc, idn_compress_stats* stats_dev, cudaStream_t st);
+
 
 extern "C" int32_t idn_gpu_compress_blocks_dev(idn_gpu_ctx* ctx, const idn_batch* batch, int32_t mode,
                                                const idn_model_t* models, uint32_t n_models, int32_t fast,
@@ -595,7 +610,7 @@ extern "C" int32_t idn_gpu_compress_blocks_dev(idn_gpu_ctx* ctx, const idn_batch
     if (rc) return rc;
     rc = check_models(ctx, models, n_models);
     if (rc) return rc;
-    if (mode != IDN_MODE_COMPAT) return fail(ctx, IDN_E_UNSUPPORTED, "mode %d is not implemented", mode);
+    if (mode != IDN_MODE_COMPAT && mode != IDN_MODE_NATIVE) return fail(ctx, IDN_E_UNSUPPORTED, "unknown mode %d", mode);
     if (!batch->block_first_read || !block_off || (!out && out_cap)) return fail(ctx, IDN_E_INVALID_ARG, "NULL argument");
     if (batch->n_blocks == 0) return fail(ctx, IDN_E_INVALID_ARG, "batch has no blocks");
     CU(cudaSetDevice(ctx->device));
@@ -626,6 +641,7 @@ extern "C" int32_t idn_gpu_compress_blocks_dev(idn_gpu_ctx* ctx, const idn_batch
                 sp.score_ids[n_score++] = sp.cand_model[t * kMaxCand + k];
             }
     }
+    if (mode == IDN_MODE_NATIVE) return compress_native_dev(ctx, batch, sp, fast, prefix_len, out, out_cap, block_off, block_crc, stats_dev, st);
     rc = upload_small(ctx, sp, st);
     if (rc) return rc;
     SmallParams* dsp = ctx->w_small.as<SmallParams>();
@@ -748,6 +764,155 @@ static int32_t idn_gpu_block_crc_dev_impl(idn_gpu_ctx* ctx, const idn_batch* bat
                                                       batch->block_first_read, batch->n_blocks, ctx->d_xpow, block_crc, out,
                                                       block_off, out_cap);
     LAUNCHED("crc_block");
+    return IDN_OK;
+}
+
+// ======================================================================================================
+// native multi-lane format (container version 2, idn_native.cuh)
+// ======================================================================================================
+template <class Fn>
+static int32_t scan_u64(idn_gpu_ctx* ctx, Fn fn, uint64_t n, unsigned long long* out, cudaStream_t st) {
+    const uint32_t n_tiles = (uint32_t)((n + kScanTile - 1) / kScanTile);
+    CU(ctx->w_tiles.ensure(((size_t)n_tiles + 2) * 8));
+    unsigned long long* tiles = ctx->w_tiles.as<unsigned long long>();
+    if (n_tiles) {
+        scan_reduce_kernel<<<n_tiles, kScanBlock, 0, st>>>(fn, n, tiles);
+        LAUNCHED("scan_reduce");
+    }
+    scan_tiles_kernel<<<1, kScanBlock, 0, st>>>(tiles, n_tiles);
+    LAUNCHED("scan_tiles");
+    if (n_tiles) {
+        scan_apply_kernel<<<n_tiles, kScanBlock, 0, st>>>(fn, n, tiles, out);
+        LAUNCHED("scan_apply");
+    } else {
+        CU(cudaMemsetAsync(out, 0, 8, st));
+    }
+    return IDN_OK;
+}
+
+static int32_t compress_native_dev(idn_gpu_ctx* ctx, const idn_batch* batch, SmallParams& sp, int32_t fast,
+                                   const uint32_t* prefix_len, uint8_t* out, uint64_t out_cap, uint64_t* block_off,
+                                   uint32_t* block_crc, idn_compress_stats* stats_dev, cudaStream_t st) {
+    const uint64_t R = batch->n_reads, S = batch->n_symbols;
+    const uint32_t B = batch->n_blocks;
+    const uint32_t Q = ctx->lane_syms;
+    int32_t rc = upload_small(ctx, sp, st);
+    if (rc) return rc;
+    SmallParams* dsp = ctx->w_small.as<SmallParams>();
+    uint64_t lane_cap = S / Q + 2ull * B + 1;
+    if (lane_cap > R) lane_cap = R;
+    CU(ctx->w_readblock.ensure((R + 1) * 4));
+    CU(ctx->w_sliceoff.ensure((R + 2) * 8));          // lane_scan
+    CU(ctx->w_lanefirst.ensure((lane_cap + 2) * 4));
+    CU(ctx->w_paylen.ensure((lane_cap + 1) * 4));     // lane_len
+    CU(ctx->w_laneoff.ensure((lane_cap + 2) * 8));
+    CU(ctx->w_laneblock.ensure((lane_cap + 1) * 4));
+    CU(ctx->w_blkinfo.ensure(((size_t)B + 2) * 4 * 3));
+    CU(ctx->w_scratch.ensure(4 * S + 8 * lane_cap + 16));
+    uint32_t* read_block = ctx->w_readblock.as<uint32_t>();
+    unsigned long long* lane_scan = ctx->w_sliceoff.as<unsigned long long>();
+    uint32_t* lane_first = ctx->w_lanefirst.as<uint32_t>();
+    uint32_t* lane_len = ctx->w_paylen.as<uint32_t>();
+    unsigned long long* lane_off = ctx->w_laneoff.as<unsigned long long>();
+    uint32_t* lane_block = ctx->w_laneblock.as<uint32_t>();
+    uint32_t* blk_width = ctx->w_blkinfo.as<uint32_t>();
+    uint32_t* blk_const = blk_width + B + 2;
+    uint32_t* blk_lane0 = blk_const + B + 2;
+    const unsigned long long* n_lanes_dev = lane_scan + R;
+    unsigned long long* boff = reinterpret_cast<unsigned long long*>(block_off);
+
+    LaneFlag lf{batch->read_off, batch->block_first_read, read_block, Q};
+    if (R > 0) {
+        read_block_kernel<<<B, 256, 0, st>>>(batch->block_first_read, B, read_block);
+        LAUNCHED("read_block");
+    }
+    rc = scan_u64(ctx, lf, R, lane_scan, st);
+    if (rc) return rc;
+    uint8_t* lane_choice = nullptr;
+    const bool uniform = sp.n_cand[0] == 1 && sp.n_cand[1] == 1;
+    (void)fast;  // one model pair per lane either way; fast only restricts the provider to 2 models
+    if (R > 0) {
+        lane_scatter_kernel<<<(unsigned)((R + 255) / 256), 256, 0, st>>>(lf, R, lane_scan, lane_first);
+        LAUNCHED("lane_scatter");
+        uint32_t n_score = 0;
+        for (uint32_t t = 0; t < 2; t++)
+            if (sp.has_sizes[t]) n_score += sp.n_cand[t];
+        if (n_score) {
+            CU(ctx->w_sizes.ensure(R * n_score * 4));
+            CU(ctx->w_chosen.ensure(2 * lane_cap + 16));
+            lane_choice = ctx->w_chosen.as<uint8_t>();
+            uint64_t threads = R * n_score;
+            score_kernel<<<(unsigned)((threads + 127) / 128), 128, 0, st>>>(ctx->d_models, dsp->score_ids, n_score, batch->acids,
+                                                                           batch->quals, batch->read_off, R,
+                                                                           ctx->w_sizes.as<uint32_t>(), &dsp->err);
+            LAUNCHED("score");
+            lane_choose_kernel<<<(unsigned)((2 * lane_cap + 127) / 128), 128, 0, st>>>(
+                ctx->w_sizes.as<uint32_t>(), n_score, dsp->cand_cols, dsp->n_cand, dsp->has_sizes, lane_first, n_lanes_dev,
+                lane_cap, lane_choice);
+            LAUNCHED("lane_choose");
+        }
+        EncodeLaneArgs ea;
+        ea.models = ctx->d_models;
+        ea.acids = batch->acids;
+        ea.quals = batch->quals;
+        ea.read_off = batch->read_off;
+        ea.lane_first = lane_first;
+        ea.n_lanes_dev = n_lanes_dev;
+        ea.lane_cap = lane_cap;
+        ea.lane_choice = lane_choice;
+        ea.cand_model = dsp->cand_model;
+        ea.scratch = ctx->w_scratch.as<uint8_t>();
+        ea.lane_len = lane_len;
+        ea.err = &dsp->err;
+        const ModelDev& hma = ctx->slots[sp.cand_model[0]].dev;
+        const ModelDev& hmq = ctx->slots[sp.cand_model[kMaxCand]].dev;
+        const unsigned grid = (unsigned)((lane_cap + 127) / 128);
+        if (uniform) encode_lane_kernel<true><<<grid, 128, 0, st>>>(ea, hma, hmq);
+        else encode_lane_kernel<false><<<grid, 128, 0, st>>>(ea, hma, hmq);
+        LAUNCHED("encode_lane");
+    }
+    LaneLenFn ll{lane_len, n_lanes_dev};
+    rc = scan_u64(ctx, ll, lane_cap, lane_off, st);
+    if (rc) return rc;
+    native_block_info_kernel<<<B, 256, 0, st>>>(batch->read_off, batch->block_first_read, B, lane_scan, blk_width, blk_const,
+                                                blk_lane0);
+    LAUNCHED("native_block_info");
+    native_layout_kernel<<<1, 32, 0, st>>>(batch->block_first_read, B, prefix_len, blk_width, blk_lane0, lane_off, boff, out,
+                                           out_cap, dsp->stats);
+    LAUNCHED("native_layout");
+    if (R > 0) {
+        lane_block_kernel<<<B, 256, 0, st>>>(blk_lane0, B, lane_block);
+        LAUNCHED("lane_block");
+        NativeAssembleArgs aa;
+        aa.read_off = batch->read_off;
+        aa.block_first = batch->block_first_read;
+        aa.n_blocks = B;
+        aa.prefix_len = prefix_len;
+        aa.blk_width = blk_width;
+        aa.blk_const_len = blk_const;
+        aa.blk_lane0 = blk_lane0;
+        aa.lane_first = lane_first;
+        aa.lane_len = lane_len;
+        aa.lane_off = lane_off;
+        aa.lane_choice = lane_choice;
+        aa.cand_index = dsp->cand_index;
+        aa.n_lanes_dev = n_lanes_dev;
+        aa.lane_cap = lane_cap;
+        aa.lane_syms = Q;
+        aa.block_off = boff;
+        aa.out = out;
+        aa.out_cap = out_cap;
+        native_header_kernel<<<B, 256, 0, st>>>(aa);
+        LAUNCHED("native_header");
+        native_copy_kernel<<<(unsigned)((lane_cap * 32 + 255) / 256), 256, 0, st>>>(aa, ctx->w_scratch.as<uint8_t>(), lane_block);
+        LAUNCHED("native_copy");
+    }
+    rc = idn_gpu_block_crc_dev_impl(ctx, batch, block_crc, out, boff, out_cap, st);
+    if (rc) return rc;
+    if (stats_dev) {
+        finish_stats_kernel<<<1, 32, 0, st>>>(dsp->stats, &dsp->err, reinterpret_cast<unsigned long long*>(stats_dev));
+        LAUNCHED("finish_stats");
+    }
     return IDN_OK;
 }
 
@@ -947,6 +1112,78 @@ static void fill_decode_params(idn_gpu_ctx* ctx, SmallParams* sp, const idn_mode
     sp->status[1] = -1;
 }
 
+static int32_t decompress_native_dev(idn_gpu_ctx* ctx, const uint8_t* blocks, const unsigned long long* boff,
+                                     const uint32_t* block_len, const uint32_t* block_crc, uint32_t n_blocks,
+                                     uint64_t blocks_bytes, const idn_model_t* models, uint32_t n_models, uint8_t* acids_out,
+                                     uint8_t* quals_out, uint64_t* read_off_out, uint64_t out_reads_cap,
+                                     uint64_t out_symbols_cap, int32_t* status_dev, SmallParams* dsp, cudaStream_t st) {
+    CU(ctx->w_blk.ensure(((size_t)n_blocks + 2) * 8 * 3));
+    BlockCounters bc = carve_counters(ctx->w_blk.p, n_blocks);  // reads, syms, slots (= lanes here)
+    CU(ctx->w_nhdr.ensure(((size_t)n_blocks + 1) * sizeof(NativeBlockHdr)));
+    NativeBlockHdr* hdr = ctx->w_nhdr.as<NativeBlockHdr>();
+    CU(ctx->w_index.ensure(index_bytes(out_reads_cap + 1)));
+    ReadIndexDev rix = carve_index(ctx->w_index.p, out_reads_cap + 1);
+    NativeIndex ix{rix.pay_off, rix.pay_len, rix.sym_off, rix.am, rix.qm};  // lanes <= reads
+    CU(ctx->w_readblock.ensure(((size_t)n_blocks + 2) * 4));
+    uint32_t* block_first = ctx->w_readblock.as<uint32_t>();
+    unsigned long long* roff = reinterpret_cast<unsigned long long*>(read_off_out);
+    if (!roff) {
+        CU(ctx->w_sliceoff.ensure((out_reads_cap + 2) * 8));
+        roff = ctx->w_sliceoff.as<unsigned long long>();
+    }
+    native_hdr_kernel<<<n_blocks, 32, 0, st>>>(blocks, boff, block_len, n_blocks, blocks_bytes, n_models, dsp->model_type, hdr,
+                                               bc.reads, bc.syms, bc.slots, dsp->status);
+    LAUNCHED("native_hdr");
+    scan_tiles_kernel<<<1, kScanBlock, 0, st>>>(bc.reads, n_blocks);
+    LAUNCHED("scan_tiles");
+    scan_tiles_kernel<<<1, kScanBlock, 0, st>>>(bc.syms, n_blocks);
+    LAUNCHED("scan_tiles");
+    scan_tiles_kernel<<<1, kScanBlock, 0, st>>>(bc.slots, n_blocks);
+    LAUNCHED("scan_tiles");
+    index_check_kernel<<<(n_blocks + 1 + 255) / 256, 256, 0, st>>>(bc.reads, bc.syms, n_blocks, out_reads_cap, out_symbols_cap,
+                                                                 block_first, dsp->status);
+    LAUNCHED("index_check");
+    native_fill_kernel<<<n_blocks + 1, kScanBlock, 0, st>>>(blocks, hdr, n_blocks, bc.reads, bc.syms, bc.slots, roff, ix,
+                                                            block_first, dsp->status);
+    LAUNCHED("native_fill");
+    if (out_reads_cap) {
+        DecodeLaneArgs da;
+        da.models = ctx->d_models;
+        da.model_ids = dsp->model_ids;
+        da.payload = blocks;
+        da.ix = ix;
+        da.n_lanes_dev = bc.slots + n_blocks;
+        da.read_off = roff;
+        da.status = dsp->status;
+        da.acids_out = acids_out;
+        da.quals_out = quals_out;
+        da.err = &dsp->err;
+        int ua = -1, uq = -1, na = 0, nq = 0;
+        for (uint32_t i = 0; i < n_models; i++) {
+            if (ctx->slots[models[i]].dev.type == IDN_MODEL_ACID) { ua = models[i]; na++; } else { uq = models[i]; nq++; }
+        }
+        const unsigned grid = (unsigned)((out_reads_cap + 127) / 128);
+        if (na == 1 && nq == 1) decode_lane_kernel<true><<<grid, 128, 0, st>>>(da, ctx->slots[ua].dev, ctx->slots[uq].dev);
+        else decode_lane_kernel<false><<<grid, 128, 0, st>>>(da, ctx->d_models_host0, ctx->d_models_host0);
+        LAUNCHED("decode_lane");
+    }
+    if (block_crc && out_reads_cap) {
+        CU(ctx->w_crcpart.ensure((out_reads_cap + 1) * 4));
+        CU(ctx->w_crclen.ensure((out_reads_cap + 1) * 8));
+        crc_read_kernel<<<(unsigned)((out_reads_cap + 127) / 128), 128, 0, st>>>(
+            acids_out, quals_out, roff, nullptr, nullptr, 0, bc.reads + n_blocks, dsp->status, ctx->d_crc_tab, ctx->d_xpow,
+            ctx->w_crcpart.as<uint32_t>(), ctx->w_crclen.as<unsigned long long>());
+        LAUNCHED("crc_read");
+        crc_verify_kernel<<<n_blocks, 256, 0, st>>>(ctx->w_crcpart.as<uint32_t>(), ctx->w_crclen.as<unsigned long long>(),
+                                                    block_first, n_blocks, ctx->d_xpow, block_crc, dsp->status);
+        LAUNCHED("crc_verify");
+    }
+    finish_decode_kernel<<<1, 32, 0, st>>>(dsp->status, &dsp->err, bc.reads + n_blocks, bc.syms + n_blocks,
+                                           reinterpret_cast<unsigned long long*>(read_off_out), status_dev);
+    LAUNCHED("finish_decode");
+    return IDN_OK;
+}
+
 extern "C" int32_t idn_gpu_decompress_blocks_dev(idn_gpu_ctx* ctx, const uint8_t* blocks, const uint64_t* block_off,
                                                  const uint32_t* block_len, const uint32_t* block_crc, uint32_t n_blocks, uint64_t blocks_bytes,
                                                  int32_t mode, const idn_model_t* models, uint32_t n_models,
@@ -956,7 +1193,7 @@ extern "C" int32_t idn_gpu_decompress_blocks_dev(idn_gpu_ctx* ctx, const uint8_t
     if (!ctx) return IDN_E_INVALID_ARG;
     int32_t rc = check_models(ctx, models, n_models);
     if (rc) return rc;
-    if (mode != IDN_MODE_COMPAT) return fail(ctx, IDN_E_UNSUPPORTED, "mode %d is not implemented", mode);
+    if (mode != IDN_MODE_COMPAT && mode != IDN_MODE_NATIVE) return fail(ctx, IDN_E_UNSUPPORTED, "unknown mode %d", mode);
     if (!block_off || !status_dev || (!blocks && blocks_bytes)) return fail(ctx, IDN_E_INVALID_ARG, "NULL argument");
     if (out_reads_cap >= (1ull << 32) - 2) return fail(ctx, IDN_E_INVALID_ARG, "out_reads_cap too large");
     CU(cudaSetDevice(ctx->device));
@@ -968,6 +1205,9 @@ extern "C" int32_t idn_gpu_decompress_blocks_dev(idn_gpu_ctx* ctx, const uint8_t
     if (rc) return rc;
     SmallParams* dsp = ctx->w_small.as<SmallParams>();
     const unsigned long long* boff = reinterpret_cast<const unsigned long long*>(block_off);
+    if (mode == IDN_MODE_NATIVE && n_blocks)
+        return decompress_native_dev(ctx, blocks, boff, block_len, block_crc, n_blocks, blocks_bytes, models, n_models, acids_out,
+                                     quals_out, read_off_out, out_reads_cap, out_symbols_cap, status_dev, dsp, st);
     if (n_blocks) {
         rc = index_walk(ctx, blocks, boff, block_len, n_blocks, blocks_bytes, dsp, n_models, st);
         if (rc) return rc;
@@ -1059,7 +1299,7 @@ static int32_t status_to_error(idn_gpu_ctx* ctx, const int32_t st[4]) {
 }
 
 extern "C" int32_t idn_gpu_index_blocks(idn_gpu_ctx* ctx, const uint8_t* blocks, const uint64_t* block_off,
-                                        const uint32_t* block_len, uint32_t n_blocks, const idn_model_t* models, uint32_t n_models, idn_block_index_totals* totals,
+                                        const uint32_t* block_len, uint32_t n_blocks, int32_t mode, const idn_model_t* models, uint32_t n_models, idn_block_index_totals* totals,
                                         uint32_t* block_first_read) {
     if (!ctx) return IDN_E_INVALID_ARG;
     int32_t rc = check_models(ctx, models, n_models);
@@ -1085,9 +1325,26 @@ extern "C" int32_t idn_gpu_index_blocks(idn_gpu_ctx* ctx, const uint8_t* blocks,
     rc = upload_small(ctx, sp, st);
     if (rc) return rc;
     SmallParams* dsp = ctx->w_small.as<SmallParams>();
-    rc = index_walk(ctx, ctx->s_blocks.as<uint8_t>(), ctx->s_blockoff.as<unsigned long long>(),
-                    block_len ? ctx->s_blocklen.as<uint32_t>() : nullptr, n_blocks, nbytes, dsp, n_models, st);
-    if (rc) return rc;
+    if (mode == IDN_MODE_NATIVE) {
+        CU(ctx->w_blk.ensure(((size_t)n_blocks + 2) * 8 * 3));
+        BlockCounters nbc = carve_counters(ctx->w_blk.p, n_blocks);
+        CU(ctx->w_nhdr.ensure(((size_t)n_blocks + 1) * sizeof(NativeBlockHdr)));
+        native_hdr_kernel<<<n_blocks, 32, 0, st>>>(ctx->s_blocks.as<uint8_t>(), ctx->s_blockoff.as<unsigned long long>(),
+                                                   block_len ? ctx->s_blocklen.as<uint32_t>() : nullptr, n_blocks, nbytes, n_models,
+                                                   dsp->model_type, ctx->w_nhdr.as<NativeBlockHdr>(), nbc.reads, nbc.syms,
+                                                   nbc.slots, dsp->status);
+        LAUNCHED("native_hdr");
+        scan_tiles_kernel<<<1, kScanBlock, 0, st>>>(nbc.reads, n_blocks);
+        LAUNCHED("scan_tiles");
+        scan_tiles_kernel<<<1, kScanBlock, 0, st>>>(nbc.syms, n_blocks);
+        LAUNCHED("scan_tiles");
+    } else if (mode == IDN_MODE_COMPAT) {
+        rc = index_walk(ctx, ctx->s_blocks.as<uint8_t>(), ctx->s_blockoff.as<unsigned long long>(),
+                        block_len ? ctx->s_blocklen.as<uint32_t>() : nullptr, n_blocks, nbytes, dsp, n_models, st);
+        if (rc) return rc;
+    } else {
+        return fail(ctx, IDN_E_UNSUPPORTED, "unknown mode %d", mode);
+    }
     std::vector<unsigned long long> hr(n_blocks + 1), hsym(n_blocks + 1);
     int32_t hst[4];
     BlockCounters bc = carve_counters(ctx->w_blk.p, n_blocks);

@@ -260,33 +260,38 @@ struct EncodeArgs {
     uint32_t* err;
 };
 
-// kUniform: every read of the batch uses the same model pair; its parameters then live in the kernel parameter
-// space (constant bank operands) instead of ~40 registers per thread, which is what bounds occupancy here.
+// State of one rANS output stream under construction (a read in compat mode, a lane in native mode).
+struct EncStream {
+    uint32_t x0, x1;  // state 0 = acids, state 1 = quality scores (compressor.rs:95-96)
+    BackWriter out;
+    uint32_t total;   // bytes emitted so far
+    bool bad;         // an input symbol was out of range
+    __device__ __forceinline__ void begin(uint8_t* slot_end) {
+        x0 = x1 = kRansL;
+        out.init(slot_end);
+        total = 0;
+        bad = false;
+    }
+    __device__ __forceinline__ void flush() {  // flush_all: state 0 then state 1
+        out.push_u32_le(x0);
+        out.push_u32_le(x1);
+        total += 8;
+        out.finish();
+    }
+};
+
+// Pushes one read (positions len-1 .. 0) onto the stream   SequenceCompressor::compress, sequence_compressor.rs:82-155
 //
 // The loop is software-pipelined over three positions because only the 32-bit rANS states are serial in the encoder:
 // while position i is coded, the encoder entry of position i-1 is being gathered and the context row of position i-2
 // is being looked up, so the two dependent L2 gathers per symbol (spec -> row -> entry) overlap with arithmetic.
-template <bool kUniform>
-__global__ void __launch_bounds__(128)
-encode_kernel(EncodeArgs A, const ModelDev MA, const ModelDev MQ) {
-    uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (r >= A.n_reads) return;
-    int32_t ia = A.fixed_acid, iq = A.fixed_q;
-    if (!kUniform && A.chosen) {
-        ia = A.cand_model[A.chosen[r]];
-        iq = A.cand_model[kMaxCand + A.chosen[A.n_reads + r]];
-    }
-    const ModelDev& ma = kUniform ? MA : A.models[ia];
-    const ModelDev& mq = kUniform ? MQ : A.models[iq];
+__device__ __forceinline__ void encode_read_body(const ModelDev& ma, const ModelDev& mq, const uint8_t* __restrict__ acids,
+                                                 const uint8_t* __restrict__ quals, long long off, uint32_t len, EncStream& S) {
     const SpecDev& sa = ma.spec;
     const SpecDev& sq = mq.spec;
-    const long long off = (long long)A.read_off[r];
-    const uint32_t len = (uint32_t)(A.read_off[r + 1] - A.read_off[r]);
-    uint8_t* slot_end = A.scratch + 4ull * A.read_off[r + 1] + 8ull * (r + 1);
-
     BackReader ra, rq;
-    ra.init(A.acids);
-    rq.init(A.quals);
+    ra.init(acids);
+    rq.init(quals);
     if (len) {
         ra.prime(off + len - 1);
         rq.prime(off + len - 1);
@@ -294,7 +299,6 @@ encode_kernel(EncodeArgs A, const ModelDev MA, const ModelDev MQ) {
     GenBack ga, gq;
     ga.clear(sa);
     gq.clear(sq);
-    bool bad = false;
     long long front = (long long)len - 1;  // next position to pull into the windows
     uint32_t raw_a = 0;                    // raw symbols travel in two more shift registers (entry k = position j - k)
     unsigned long long raw_q = 0;
@@ -304,7 +308,7 @@ encode_kernel(EncodeArgs A, const ModelDev MA, const ModelDev MQ) {
             a = ra.get(off + front);
             q = rq.get(off + front);
             if (a > 4 || q > 93) {
-                bad = true;
+                S.bad = true;
                 a = a > 4 ? 0 : a;
                 q = q > 93 ? 0 : q;
             }
@@ -339,14 +343,10 @@ encode_kernel(EncodeArgs A, const ModelDev MA, const ModelDev MQ) {
             row_q = ctx_row(mq, gq.spec(sq, pb.pos, psq));
         }
     };
-    BackWriter out;
-    out.init(slot_end);
-    uint32_t total = 0;
     auto emit = [&](uint32_t b) {
-        out.push(b);
-        total++;
+        S.out.push(b);
+        S.total++;
     };
-    uint32_t x0 = kRansL, x1 = kRansL;  // state 0 = acids, state 1 = quality scores (compressor.rs:95-96)
     // prologue: rows of position len-1, its entries, rows of position len-2
     uint32_t row_a, row_q;
     rows_next(row_a, row_q);  // generators at len-1, entry 0 = symbol len-1
@@ -365,17 +365,35 @@ encode_kernel(EncodeArgs A, const ModelDev MA, const ModelDev MQ) {
             eq_n = __ldg(mq.enc + (size_t)row_q * kQSyms + ((uint32_t)raw_q & 127u));
         }
         rows_next(row_a, row_q);  // generators to i-2
-        rans_put(x0, ea, emit);
-        rans_put(x1, eq, emit);
+        rans_put(S.x0, ea, emit);
+        rans_put(S.x1, eq, emit);
         ea = ea_n;
         eq = eq_n;
     }
-    out.push_u32_le(x0);  // flush_all: state 0 then state 1
-    out.push_u32_le(x1);
-    total += 8;
-    out.finish();
-    A.pay_len[r] = total;
-    if (bad) atomicOr(A.err, 1u);
+}
+
+// kUniform: every read of the batch uses the same model pair; its parameters then live in the kernel parameter
+// space (constant bank operands) instead of ~40 registers per thread, which is what bounds occupancy here.
+template <bool kUniform>
+__global__ void __launch_bounds__(128)
+encode_kernel(EncodeArgs A, const ModelDev MA, const ModelDev MQ) {
+    uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= A.n_reads) return;
+    int32_t ia = A.fixed_acid, iq = A.fixed_q;
+    if (!kUniform && A.chosen) {
+        ia = A.cand_model[A.chosen[r]];
+        iq = A.cand_model[kMaxCand + A.chosen[A.n_reads + r]];
+    }
+    const ModelDev& ma = kUniform ? MA : A.models[ia];
+    const ModelDev& mq = kUniform ? MQ : A.models[iq];
+    const long long off = (long long)A.read_off[r];
+    const uint32_t len = (uint32_t)(A.read_off[r + 1] - A.read_off[r]);
+    EncStream S;
+    S.begin(A.scratch + 4ull * A.read_off[r + 1] + 8ull * (r + 1));
+    encode_read_body(ma, mq, A.acids, A.quals, off, len, S);
+    S.flush();
+    A.pay_len[r] = S.total;
+    if (S.bad) atomicOr(A.err, 1u);
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -1036,6 +1054,72 @@ struct DecodeArgs {
     uint32_t* err;
 };
 
+// State of one rANS input stream being consumed (a read in compat mode, a lane in native mode).
+struct DecStream {
+    uint32_t xq, xa;  // decoder state 0 = quality scores, state 1 = acids (compressor.rs:181-182)
+    FwdReader in;
+    unsigned long long poff;
+    uint32_t plen, cur, st;  // st bit 0: the payload ran out / is malformed
+    __device__ __forceinline__ uint32_t next() { return in.get(poff + cur++); }
+    __device__ __forceinline__ void begin(const uint8_t* payload, unsigned long long off, uint32_t len) {
+        in.init(payload);
+        in.prime(off);
+        poff = off;
+        plen = len;
+        cur = 0;
+        st = len < 8 ? 1u : 0u;  // a valid stream holds at least the two flushed states
+        xq = xa = 0;
+        if (!st) {  // RansDecInit x2
+            xq = next();
+            xq |= next() << 8;
+            xq |= next() << 16;
+            xq |= next() << 24;
+            xa = next();
+            xa |= next() << 8;
+            xa |= next() << 16;
+            xa |= next() << 24;
+        }
+    }
+    // a valid stream ends with both states back at L and every byte consumed
+    __device__ __forceinline__ bool clean_end() const { return xq == kRansL && xa == kRansL && cur == plen; }
+};
+
+// Pops one read (positions 0 .. len-1) from the stream   SequenceDecompressor::decompress, sequence_compressor.rs:231-278
+__device__ __forceinline__ void decode_read_body(const ModelDev& ma, const ModelDev& mq, uint32_t len, DecStream& D,
+                                                 FwdWriter& oa, FwdWriter& oq) {
+    const SpecDev& sa = ma.spec;
+    const SpecDev& sq = mq.spec;
+    GenFwd ga, gq;
+    ga.init();
+    gq.init();
+    const uint32_t pbmax = sa.pb > sq.pb ? sa.pb : sq.pb;
+    const uint32_t psa = pbmax - sa.pb, psq = pbmax - sq.pb;
+    PosFwd pf;
+    pf.init(len, pbmax);
+#pragma unroll 1
+    for (uint32_t i = 0; i < len && !(D.st & 1); i++) {
+        uint32_t row_a = ctx_row(ma, ga.spec(sa, pf.pos, psa));
+        uint32_t row_q = ctx_row(mq, gq.spec(sq, pf.pos, psq));
+        uint32_t slot_q = D.xq & kSlotMask, slot_a = D.xa & kSlotMask;
+        uint32_t start, freq;
+        uint32_t vq = q_find(mq.dec + (size_t)row_q * kQRowBytes, slot_q, start, freq);
+        D.xq = freq * (D.xq >> kScaleBits) + slot_q - start;  // RansDecAdvanceStep
+        uint2 pk = __ldg(reinterpret_cast<const uint2*>(ma.dec) + row_a);
+        uint32_t va = acid_find(pk, slot_a, start, freq);
+        D.xa = freq * (D.xa >> kScaleBits) + slot_a - start;
+        // renorm_all: state 0 then state 1; at most two bytes each (x >= 2^9 after the advance)
+        while (D.xq < kRansL && D.cur < D.plen) D.xq = (D.xq << 8) | D.next();
+        while (D.xa < kRansL && D.cur < D.plen) D.xa = (D.xa << 8) | D.next();
+        if (D.xq < kRansL || D.xa < kRansL) D.st |= 1;  // the payload ran out
+        oa.push(va);
+        oq.push(vq);
+        const bool z = va * vq == 0;
+        ga.update(sa, va, vq, z);
+        gq.update(sq, va, vq, z);
+        pf.advance();
+    }
+}
+
 template <bool kUniform>
 __global__ void __launch_bounds__(128)
 decode_kernel(DecodeArgs A, const ModelDev MA, const ModelDev MQ) {
@@ -1058,67 +1142,19 @@ decode_kernel(DecodeArgs A, const ModelDev MA, const ModelDev MQ) {
     }
     const ModelDev& ma = kUniform ? MA : A.models[A.model_ids[A.ix.am[slot]]];
     const ModelDev& mq = kUniform ? MQ : A.models[A.model_ids[A.ix.qm[slot]]];
-    const unsigned long long poff = A.ix.pay_off[slot];
-    const uint32_t plen = A.ix.pay_len[slot], len = A.ix.seq_len[slot];
+    const uint32_t len = A.ix.seq_len[slot];
     const unsigned long long ooff = sym_base + A.ix.sym_off[slot];
     if (A.read_off_out) A.read_off_out[r] = ooff;
-    const SpecDev& sa = ma.spec;
-    const SpecDev& sq = mq.spec;
-    FwdReader in;
-    in.init(A.payload);
-    in.prime(poff);
-    uint32_t cur = 0, st = 0;
-    auto next = [&]() -> uint32_t { return in.get(poff + cur++); };
-    // a valid payload holds at least the two flushed states; a truncated one is caught by the cur > plen checks below
-    // (reads stay inside the 4-byte words that hold payload bytes or the word right after them)
-    if (plen < 8) st |= 1;
-    // RansDecInit x2: decoder state 0 = quality scores, state 1 = acids (compressor.rs:181-182)
-    uint32_t xq = 0, xa = 0;
-    if (!(st & 1)) {
-        xq = next();
-        xq |= next() << 8;
-        xq |= next() << 16;
-        xq |= next() << 24;
-        xa = next();
-        xa |= next() << 8;
-        xa |= next() << 16;
-        xa |= next() << 24;
-    }
-    GenFwd ga, gq;
-    ga.init();
-    gq.init();
-    const uint32_t pbmax = sa.pb > sq.pb ? sa.pb : sq.pb;
-    const uint32_t psa = pbmax - sa.pb, psq = pbmax - sq.pb;
-    PosFwd pf;
-    pf.init(len, pbmax);
+    DecStream D;
+    D.begin(A.payload, A.ix.pay_off[slot], A.ix.pay_len[slot]);
     FwdWriter oa, oq;
     oa.init(A.acids_out + ooff);
     oq.init(A.quals_out + ooff);
-#pragma unroll 1
-    for (uint32_t i = 0; i < len && !(st & 1); i++) {
-        uint32_t row_a = ctx_row(ma, ga.spec(sa, pf.pos, psa));
-        uint32_t row_q = ctx_row(mq, gq.spec(sq, pf.pos, psq));
-        uint32_t slot_q = xq & kSlotMask, slot_a = xa & kSlotMask;
-        uint32_t start, freq;
-        uint32_t vq = q_find(mq.dec + (size_t)row_q * kQRowBytes, slot_q, start, freq);
-        xq = freq * (xq >> kScaleBits) + slot_q - start;  // RansDecAdvanceStep
-        uint2 pk = __ldg(reinterpret_cast<const uint2*>(ma.dec) + row_a);
-        uint32_t va = acid_find(pk, slot_a, start, freq);
-        xa = freq * (xa >> kScaleBits) + slot_a - start;
-        // renorm_all: state 0 then state 1; at most two bytes each (x >= 2^9 after the advance)
-        while (xq < kRansL && cur < plen) xq = (xq << 8) | next();
-        while (xa < kRansL && cur < plen) xa = (xa << 8) | next();
-        if (xq < kRansL || xa < kRansL) st |= 1;  // the payload ran out
-        oa.push(va);
-        oq.push(vq);
-        const bool z = va * vq == 0;
-        ga.update(sa, va, vq, z);
-        gq.update(sq, va, vq, z);
-        pf.advance();
-    }
+    decode_read_body(ma, mq, len, D, oa, oq);
     oa.finish();
     oq.finish();
-    if (!(st & 1) && (xq != kRansL || xa != kRansL || cur != plen)) st |= 2;
+    uint32_t st = D.st;
+    if (!(st & 1) && !D.clean_end()) st |= 2;
     if (A.read_status) A.read_status[r] = st;
     if (st & 1) atomicOr(A.err, 1u);
 }

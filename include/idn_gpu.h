@@ -67,6 +67,9 @@ int32_t idn_gpu_device_count(void);
 int32_t idn_gpu_create(int32_t device, idn_gpu_ctx **ctx);
 void idn_gpu_destroy(idn_gpu_ctx *ctx);
 const char *idn_gpu_last_error(const idn_gpu_ctx *ctx);
+/* lane quantum of IDN_MODE_NATIVE compression: a lane holds the reads whose first symbol falls into the same run of
+ * `lane_syms` symbols of the block (default 4096); the value travels in the container, decoders need no setting */
+int32_t idn_gpu_set_lane_symbols(idn_gpu_ctx *ctx, uint32_t lane_syms);
 /* number of kernel launches this ctx has issued since creation (bench.py's gpu_launches) */
 uint64_t idn_gpu_launch_count(const idn_gpu_ctx *ctx);
 
@@ -153,7 +156,7 @@ typedef struct {
 } idn_block_index_totals;
 
 int32_t idn_gpu_index_blocks(idn_gpu_ctx *ctx, const uint8_t *blocks, const uint64_t *block_off,
-                             const uint32_t *block_len /* optional */, uint32_t n_blocks, const idn_model_t *models, uint32_t n_models,
+                             const uint32_t *block_len /* optional */, uint32_t n_blocks, int32_t mode, const idn_model_t *models, uint32_t n_models,
                              idn_block_index_totals *totals, uint32_t *block_first_read /*[n_blocks+1], optional*/);
 int32_t idn_gpu_decompress_blocks(idn_gpu_ctx *ctx, const uint8_t *blocks, const uint64_t *block_off,
                                   const uint32_t *block_len /* optional */, const uint32_t *block_crc, uint32_t n_blocks, int32_t mode,

@@ -1271,3 +1271,281 @@ int orc_synth_reads(const orc_model_t *am, const orc_model_t *qm, const uint64_t
     synth_job_t j = {am, qm, read_off, n_reads, first_read_index, seed, n_ppm, acids, quals};
     return pool_run(threads, (n_reads + 4095) / 4096, synth_chunk, &j);
 }
+
+/* ------------------------------------------------------------------------------------------------
+ * GPU-native multi-lane block format (container version 2).  NOT part of the reference: this is an
+ * independent CPU statement of the format specified in DESIGN.md section 8 (and in the header of
+ * idencomp_b200/csrc/idn_native.cuh), used to check the CUDA encoder/decoder of that format bit for bit.
+ * It reuses the pinned per-symbol machinery above (generators, tables, ryg put/get); only stream
+ * segmentation and framing are new.
+ * ---------------------------------------------------------------------------------------------- */
+#define NATIVE_HDR_FIXED 22u
+
+static void put_u32be(uint8_t *p, uint32_t v) {
+    p[0] = (uint8_t)(v >> 24);
+    p[1] = (uint8_t)(v >> 16);
+    p[2] = (uint8_t)(v >> 8);
+    p[3] = (uint8_t)v;
+}
+static uint32_t get_u32be(const uint8_t *p) {
+    return (uint32_t)p[0] << 24 | (uint32_t)p[1] << 16 | (uint32_t)p[2] << 8 | p[3];
+}
+
+/* one lane: reads [r0, r1) pushed last -> first onto one 2-state stream; returns the payload length */
+static size_t native_encode_lane(const orc_model_t *am, const orc_model_t *qm, const orc_reads_t *in, uint64_t r0,
+                                 uint64_t r1, uint8_t *tmp, size_t cap, uint8_t **start_out) {
+    uint32_t s0 = RANS_L, s1 = RANS_L;
+    uint8_t *ptr = tmp + cap;
+    for (uint64_t r = r1; r-- > r0;) {
+        const uint8_t *ac = in->acids + in->read_off[r];
+        const uint8_t *qu = in->quals + in->read_off[r];
+        uint32_t len = (uint32_t)(in->read_off[r + 1] - in->read_off[r]);
+        uint32_t *ctx_a = (uint32_t *)malloc(((size_t)len + 1) * 2 * sizeof(uint32_t));
+        uint32_t *ctx_q = ctx_a + len + 1;
+        orc_gen_t ga, gq;
+        orc_gen_init(&ga, &am->spec, len);
+        orc_gen_init(&gq, &qm->spec, len);
+        for (uint32_t i = 0; i < len; i++) {
+            ctx_a[i] = ctx_for(am, orc_gen_current(&ga));
+            ctx_q[i] = ctx_for(qm, orc_gen_current(&gq));
+            orc_gen_update(&ga, ac[i], qu[i]);
+            orc_gen_update(&gq, ac[i], qu[i]);
+        }
+        for (uint32_t i = len; i-- > 0;) {
+            enc_put(&s0, &ptr, &am->enc[(size_t)ctx_a[i] * ORC_ACID_SYMS + ac[i]]);
+            enc_put(&s1, &ptr, &qm->enc[(size_t)ctx_q[i] * ORC_Q_SYMS + qu[i]]);
+        }
+        free(ctx_a);
+    }
+    enc_flush(s0, &ptr);
+    enc_flush(s1, &ptr);
+    *start_out = ptr;
+    return (size_t)(tmp + cap - ptr);
+}
+
+/* slices of one version-2 block (no block header): [Identifiers] NativeLanes; crc as in version 1 */
+int orc_compress_native_block(const orc_params_t *p, const orc_reads_t *in, uint64_t first_read, uint64_t n_reads,
+                              uint32_t lane_syms, orc_buf_t *out, uint32_t *crc_out) {
+    uint32_t crc = 0;
+    *crc_out = 0;
+    if (n_reads == 0) return ORC_OK;
+    if (lane_syms == 0) return fail(ORC_E_INVALID_STATE, "lane_syms must be positive");
+    if (p->include_identifiers) {
+        orc_buf_t joined = {0}, z = {0};
+        for (uint64_t r = first_read; r < first_read + n_reads; r++) {
+            if (r > first_read) buf_u8(&joined, '\n');
+            if (in->name_off) buf_put(&joined, in->names + in->name_off[r], in->name_off[r + 1] - in->name_off[r]);
+        }
+        int rc = deflate_names(joined.data, joined.len, p->deflate_level ? p->deflate_level : 6, &z);
+        if (rc) {
+            orc_buf_free(&joined);
+            orc_buf_free(&z);
+            return rc;
+        }
+        buf_u8(out, 0x00);
+        buf_u32be(out, (uint32_t)z.len);
+        buf_u8(out, 1);
+        buf_put(out, z.data, z.len);
+        orc_buf_free(&joined);
+        orc_buf_free(&z);
+    }
+    /* candidates per type in provider order */
+    int cand[2][256], n_cand[2] = {0, 0};
+    for (uint32_t k = 0; k < p->n_models; k++) cand[p->models[k]->type][n_cand[p->models[k]->type]++] = (int)k;
+    if (!n_cand[0] || !n_cand[1]) return fail(ORC_E_INVALID_STATE, "need at least one model per type");
+    /* lane partition */
+    uint64_t base = in->read_off[first_read];
+    uint64_t *lane_first = (uint64_t *)malloc(sizeof(uint64_t) * (n_reads + 1));
+    uint64_t n_lanes = 0;
+    uint32_t mn = 0xffffffffu, mx = 0;
+    for (uint64_t i = 0; i < n_reads; i++) {
+        uint64_t r = first_read + i;
+        uint32_t len = (uint32_t)(in->read_off[r + 1] - in->read_off[r]);
+        if (len < mn) mn = len;
+        if (len > mx) mx = len;
+        if (i == 0 || (in->read_off[r] - base) / lane_syms != (in->read_off[r - 1] - base) / lane_syms) lane_first[n_lanes++] = r;
+    }
+    lane_first[n_lanes] = first_read + n_reads;
+    uint32_t width = mn == mx ? 0u : (mx < 65536u ? 2u : 4u);
+    /* per-lane model choice and payloads */
+    uint8_t *mdl = (uint8_t *)malloc(2 * n_lanes + 2);
+    uint32_t *llen = (uint32_t *)malloc(sizeof(uint32_t) * (n_lanes + 1));
+    orc_buf_t pay = {0};
+    for (uint64_t l = 0; l < n_lanes; l++) {
+        int pick[2];
+        for (int type = 0; type < 2; type++) {
+            pick[type] = cand[type][0];
+            if (n_cand[type] > 1 && !p->fast) {
+                uint64_t best = ~0ull;
+                for (int k = 0; k < n_cand[type]; k++) {
+                    uint64_t sum = 0;
+                    for (uint64_t r = lane_first[l]; r < lane_first[l + 1]; r++)
+                        sum += orc_score_read(p->models[cand[type][k]], in->acids + in->read_off[r], in->quals + in->read_off[r],
+                                              (uint32_t)(in->read_off[r + 1] - in->read_off[r]));
+                    if (sum < best) { /* first minimum wins */
+                        best = sum;
+                        pick[type] = cand[type][k];
+                    }
+                }
+            }
+        }
+        mdl[2 * l] = (uint8_t)pick[0];
+        mdl[2 * l + 1] = (uint8_t)pick[1];
+        size_t cap = 4 * (size_t)(in->read_off[lane_first[l + 1]] - in->read_off[lane_first[l]]) + 8;
+        uint8_t *tmp = (uint8_t *)malloc(cap), *start;
+        size_t n = native_encode_lane(p->models[pick[0]], p->models[pick[1]], in, lane_first[l], lane_first[l + 1], tmp, cap, &start);
+        llen[l] = (uint32_t)n;
+        buf_put(&pay, start, n);
+        free(tmp);
+    }
+    for (uint64_t r = first_read; r < first_read + n_reads; r++) {
+        uint32_t len = (uint32_t)(in->read_off[r + 1] - in->read_off[r]);
+        if (in->name_off && p->include_identifiers)
+            crc = orc_crc32(crc, in->names + in->name_off[r], in->name_off[r + 1] - in->name_off[r]);
+        crc = orc_crc32(crc, in->acids + in->read_off[r], len);
+        crc = orc_crc32(crc, in->quals + in->read_off[r], len);
+    }
+    uint64_t body = NATIVE_HDR_FIXED - 5 + n_reads * width + 6 * n_lanes + pay.len;
+    buf_u8(out, 0x03);
+    buf_u32be(out, (uint32_t)body);
+    buf_u32be(out, (uint32_t)n_reads);
+    buf_u32be(out, (uint32_t)n_lanes);
+    buf_u32be(out, lane_syms);
+    buf_u8(out, (uint8_t)width);
+    buf_u32be(out, width == 0 ? mn : 0);
+    for (uint64_t r = first_read; r < first_read + n_reads && width; r++) {
+        uint32_t len = (uint32_t)(in->read_off[r + 1] - in->read_off[r]);
+        if (width == 2) {
+            buf_u8(out, (uint8_t)(len >> 8));
+            buf_u8(out, (uint8_t)len);
+        } else {
+            buf_u32be(out, len);
+        }
+    }
+    buf_put(out, mdl, 2 * n_lanes);
+    for (uint64_t l = 0; l < n_lanes; l++) buf_u32be(out, llen[l]);
+    buf_put(out, pay.data, pay.len);
+    orc_buf_free(&pay);
+    free(mdl);
+    free(llen);
+    free(lane_first);
+    *crc_out = crc;
+    return ORC_OK;
+}
+
+/* decode the NativeLanes slice of one version-2 block (Identifiers slices are skipped); outputs are appended to
+ * acids/quals at *n_syms and lengths to read_len at *n_reads (capacities are the caller's business: sized from the
+ * header fields, which the caller can read with orc_native_block_counts) */
+int orc_native_block_counts(const uint8_t *data, size_t n, uint64_t *n_reads, uint64_t *n_syms) {
+    size_t pos = 0;
+    *n_reads = *n_syms = 0;
+    while (pos < n) {
+        if (data[pos] == 0) {
+            if (pos + 6 > n) return fail(ORC_E_SERIALIZE, "truncated identifiers slice");
+            size_t len = get_u32be(data + pos + 1);
+            if (len > n - pos - 6) return fail(ORC_E_SERIALIZE, "truncated identifiers slice");
+            pos += 6 + len;
+        } else if (data[pos] == 3) {
+            if (pos + NATIVE_HDR_FIXED > n) return fail(ORC_E_SERIALIZE, "truncated native slice");
+            uint32_t body = get_u32be(data + pos + 1), nr = get_u32be(data + pos + 5), w = data[pos + 17];
+            if (body > n - pos - 5) return fail(ORC_E_SERIALIZE, "truncated native slice");
+            *n_reads += nr;
+            if (w == 0) {
+                *n_syms += (uint64_t)nr * get_u32be(data + pos + 18);
+            } else {
+                if ((uint64_t)nr * w > body) return fail(ORC_E_SERIALIZE, "bad length table");
+                for (uint32_t i = 0; i < nr; i++)
+                    *n_syms += w == 2 ? (uint32_t)(data[pos + 22 + 2 * i] << 8 | data[pos + 23 + 2 * i])
+                                      : get_u32be(data + pos + 22 + 4 * (size_t)i);
+            }
+            pos += 5 + (size_t)body;
+        } else {
+            return fail(ORC_E_SERIALIZE, "unexpected slice kind %u in a version 2 block", data[pos]);
+        }
+    }
+    return ORC_OK;
+}
+
+int orc_decompress_native_block(const orc_model_t *const *models, uint32_t n_models, const uint8_t *data, size_t n,
+                                uint8_t *acids, uint8_t *quals, uint32_t *read_len) {
+    size_t pos = 0;
+    uint64_t out_sym = 0, out_read = 0;
+    const uint32_t mask = (1u << ORC_SCALE_BITS) - 1;
+    while (pos < n) {
+        if (data[pos] == 0) {
+            pos += 6 + (size_t)get_u32be(data + pos + 1);
+            continue;
+        }
+        if (data[pos] != 3) return fail(ORC_E_SERIALIZE, "unexpected slice kind");
+        uint32_t body = get_u32be(data + pos + 1), nr = get_u32be(data + pos + 5), nl = get_u32be(data + pos + 9);
+        uint32_t Q = get_u32be(data + pos + 13), w = data[pos + 17], cl = get_u32be(data + pos + 18);
+        const uint8_t *t_len = data + pos + NATIVE_HDR_FIXED;
+        const uint8_t *t_mdl = t_len + (size_t)nr * w;
+        const uint8_t *t_ll = t_mdl + 2 * (size_t)nl;
+        const uint8_t *pay = t_ll + 4 * (size_t)nl;
+        if (Q == 0 || (size_t)(pay - (data + pos + 5)) > body) return fail(ORC_E_SERIALIZE, "bad native header");
+        uint32_t *lens = (uint32_t *)malloc(sizeof(uint32_t) * ((size_t)nr + 1));
+        for (uint32_t i = 0; i < nr; i++)
+            lens[i] = w == 0 ? cl : (w == 2 ? (uint32_t)(t_len[2 * i] << 8 | t_len[2 * i + 1]) : get_u32be(t_len + 4 * (size_t)i));
+        uint64_t off = 0;
+        uint32_t lane = 0, r = 0;
+        while (r < nr) {
+            /* lane = maximal run of reads whose offsets share the quantum off / Q */
+            uint32_t r_end = r;
+            uint64_t o = off, q0 = off / Q;
+            while (r_end < nr && (r_end == r || o / Q == q0)) {
+                o += lens[r_end];
+                r_end++;
+            }
+            if (lane >= nl) { free(lens); return fail(ORC_E_SERIALIZE, "more lanes than the table holds"); }
+            uint32_t ia = t_mdl[2 * lane], iq = t_mdl[2 * lane + 1], ll = get_u32be(t_ll + 4 * (size_t)lane);
+            if (ia >= n_models || iq >= n_models || models[ia]->type != ORC_TYPE_ACID || models[iq]->type != ORC_TYPE_QSCORE) {
+                free(lens);
+                return fail(ORC_E_INVALID_MODEL_INDEX, "lane names a bad model");
+            }
+            if (ll < 8 || (size_t)(pay - data) + ll > pos + 5 + (size_t)body) { free(lens); return fail(ORC_E_SERIALIZE, "lane payload out of range"); }
+            const orc_model_t *am = models[ia], *qm = models[iq];
+            uint32_t sq = (uint32_t)pay[0] | (uint32_t)pay[1] << 8 | (uint32_t)pay[2] << 16 | (uint32_t)pay[3] << 24;
+            uint32_t sa = (uint32_t)pay[4] | (uint32_t)pay[5] << 8 | (uint32_t)pay[6] << 16 | (uint32_t)pay[7] << 24;
+            size_t pp = 8;
+            for (uint32_t k = r; k < r_end; k++) {
+                uint32_t len = lens[k];
+                orc_gen_t ga, gq;
+                orc_gen_init(&ga, &am->spec, len);
+                orc_gen_init(&gq, &qm->spec, len);
+                for (uint32_t i = 0; i < len; i++) {
+                    uint32_t ca = ctx_for(am, orc_gen_current(&ga)), cq = ctx_for(qm, orc_gen_current(&gq));
+                    uint32_t slot_q = sq & mask, slot_a = sa & mask;
+                    uint32_t yq = find_sym(qm, cq, slot_q), ya = find_sym(am, ca, slot_a);
+                    const uint16_t *rq = qm->cum + (size_t)cq * (ORC_Q_SYMS + 1);
+                    const uint16_t *ra = am->cum + (size_t)ca * (ORC_ACID_SYMS + 1);
+                    sq = (uint32_t)(rq[yq + 1] - rq[yq]) * (sq >> ORC_SCALE_BITS) + slot_q - rq[yq];
+                    sa = (uint32_t)(ra[ya + 1] - ra[ya]) * (sa >> ORC_SCALE_BITS) + slot_a - ra[ya];
+                    while (sq < RANS_L) {
+                        if (pp >= ll) { free(lens); return fail(ORC_E_SERIALIZE, "lane payload exhausted"); }
+                        sq = (sq << 8) | pay[pp++];
+                    }
+                    while (sa < RANS_L) {
+                        if (pp >= ll) { free(lens); return fail(ORC_E_SERIALIZE, "lane payload exhausted"); }
+                        sa = (sa << 8) | pay[pp++];
+                    }
+                    acids[out_sym] = (uint8_t)ya;
+                    quals[out_sym] = (uint8_t)yq;
+                    out_sym++;
+                    orc_gen_update(&ga, (uint8_t)ya, (uint8_t)yq);
+                    orc_gen_update(&gq, (uint8_t)ya, (uint8_t)yq);
+                }
+                read_len[out_read++] = len;
+            }
+            if (sq != RANS_L || sa != RANS_L || pp != ll) { free(lens); return fail(ORC_E_SERIALIZE, "lane does not end cleanly"); }
+            pay += ll;
+            off = o;
+            r = r_end;
+            lane++;
+        }
+        free(lens);
+        if (lane != nl || (size_t)(pay - (data + pos + 5)) != body) return fail(ORC_E_SERIALIZE, "native slice framing mismatch");
+        pos += 5 + (size_t)body;
+    }
+    return ORC_OK;
+}

@@ -167,6 +167,14 @@ int orc_decompress(const orc_model_t *const *models, uint32_t n_models, const ui
 int orc_fastq_parse(const uint8_t *text, size_t n, orc_decoded_t *out);
 int orc_fastq_write(const orc_reads_t *in, orc_buf_t *out);
 
+/* GPU-native multi-lane block format (container version 2).  Not part of the reference:
+ * an independent CPU statement of our own format, used to check the CUDA implementation of it. */
+int orc_compress_native_block(const orc_params_t *p, const orc_reads_t *in, uint64_t first_read, uint64_t n_reads,
+                              uint32_t lane_syms, orc_buf_t *out, uint32_t *crc_out);
+int orc_native_block_counts(const uint8_t *data, size_t n, uint64_t *n_reads, uint64_t *n_syms);
+int orc_decompress_native_block(const orc_model_t *const *models, uint32_t n_models, const uint8_t *data, size_t n,
+                                uint8_t *acids, uint8_t *quals, uint32_t *read_len);
+
 /* workload generator (bench/test utility): same sampler as the device library's, see idn_oracle.c */
 int orc_synth_reads(const orc_model_t *am, const orc_model_t *qm, const uint64_t *read_off, uint64_t n_reads,
                     uint64_t first_read_index, uint64_t seed, uint32_t n_ppm, int threads, uint8_t *acids,

@@ -122,6 +122,11 @@ def lib():
         L.orc_fastq_write.argtypes = [C.POINTER(_Reads), C.POINTER(_Buf)]
         L.orc_buf_free.argtypes = [C.POINTER(_Buf)]
         L.orc_decoded_free.argtypes = [C.POINTER(_Decoded)]
+        L.orc_compress_native_block.argtypes = [C.POINTER(_Params), C.POINTER(_Reads), C.c_uint64, C.c_uint64, C.c_uint32,
+                                                C.POINTER(_Buf), C.POINTER(C.c_uint32)]
+        L.orc_native_block_counts.argtypes = [C.c_void_p, C.c_size_t, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
+        L.orc_decompress_native_block.argtypes = [C.POINTER(C.c_void_p), C.c_uint32, C.c_void_p, C.c_size_t, C.c_void_p,
+                                                  C.c_void_p, C.c_void_p]
         L.orc_synth_reads.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint32,
                                       C.c_int, C.c_void_p, C.c_void_p]
         L.orc_crc32.restype = C.c_uint32
@@ -447,6 +452,36 @@ def compress_block(models, reads: Reads, first: int, n: int, *, include_identifi
     finally:
         lib().orc_buf_free(C.byref(b))
     return data, int(crc.value), {n_: int(getattr(st, n_)) for n_, _ in _Stats._fields_}
+
+
+# ---- GPU-native multi-lane format (container version 2): our own format, stated independently ----
+def compress_native_block(models, reads: Reads, first: int, n: int, *, lane_syms: int = 4096, include_identifiers=True,
+                          fast=False):
+    """Slices of one version-2 block (no block header) and its CRC."""
+    p, keep = _params(models, 0, include_identifiers, 7, fast, 0)
+    b = _Buf()
+    crc = C.c_uint32(0)
+    rd = reads if include_identifiers else reads.without_names()
+    _check(lib().orc_compress_native_block(C.byref(p), C.byref(rd._c()), first, n, lane_syms, C.byref(b), C.byref(crc)))
+    try:
+        data = C.string_at(b.data, b.len) if b.len else b""
+    finally:
+        lib().orc_buf_free(C.byref(b))
+    return data, int(crc.value)
+
+
+def decompress_native_block(models, data: bytes):
+    """(read_len[], acids, quals) of one version-2 block's slices."""
+    buf = np.frombuffer(data, dtype=np.uint8)
+    nr, ns = C.c_uint64(0), C.c_uint64(0)
+    _check(lib().orc_native_block_counts(_ptr(buf), len(buf), C.byref(nr), C.byref(ns)))
+    a = np.zeros(max(ns.value, 1), dtype=np.uint8)
+    q = np.zeros(max(ns.value, 1), dtype=np.uint8)
+    ln = np.zeros(max(nr.value, 1), dtype=np.uint32)
+    arr = (C.c_void_p * max(len(models), 1))(*[m.h for m in models])
+    _check(lib().orc_decompress_native_block(C.cast(arr, C.POINTER(C.c_void_p)), len(models), _ptr(buf), len(buf),
+                                             a.ctypes.data, q.ctypes.data, ln.ctypes.data))
+    return ln[:nr.value], a[:ns.value], q[:ns.value]
 
 
 def decompress(models, idn: bytes, threads: int = 0, return_info: bool = False):

@@ -233,3 +233,16 @@ def test_round_trip_bundled_pairs(O, model_data, reads_1k):
         models = [built[a], built[qn]]
         idn = O.compress(models, reads_1k, fast=True, include_identifiers=False)
         _same(O.decompress(models, idn), reads_1k, names=False)
+
+
+# ---- our own version-2 block format: the CPU statement round-trips (no reference golden exists for it) ----------
+@pytest.mark.parametrize("lane_syms", [1, 64, 1000, 4096])
+def test_native_cpu_statement_round_trip(O, toy_models, reads_1k, lane_syms):
+    data, crc = O.compress_native_block(toy_models, reads_1k, 0, reads_1k.n_reads, lane_syms=lane_syms, include_identifiers=False)
+    ln, a, q = O.decompress_native_block(toy_models, data)
+    assert np.array_equal(np.cumsum(ln), reads_1k.read_off[1:])
+    assert np.array_equal(a, reads_1k.acids) and np.array_equal(q, reads_1k.quals)
+    compat, crc_c, _ = O.compress_block(toy_models, reads_1k, 0, reads_1k.n_reads, include_identifiers=False)
+    assert crc == crc_c  # same checksum definition as version 1
+    if lane_syms >= 1000:
+        assert len(data) < len(compat)  # the point of the format: no per-read header and flush
