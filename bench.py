@@ -42,8 +42,8 @@ WORKLOADS = {
                      read_len=(100, 100), reads=40_485_830, name_len=41, seed=20240601, n_ppm=500, mode="compat",
                      desc="synthetic 10 GB Illumina HiSeq 2000-shaped FASTQ, 100 bp, compat mode (BASELINE.json configs[1])"),
     "novaseq150": dict(acid="SRR8861483__human__illumina_novaseq_6000__acids", q="SRR8861483__human__illumina_novaseq_6000__q_scores",
-                       read_len=(150, 150), reads=28_500_000, name_len=44, seed=20240602, n_ppm=500, mode="compat",
-                       desc="synthetic 10 GB NovaSeq 6000-shaped FASTQ, 150 bp (a 10 GB shard of configs[2])"),
+                       read_len=(150, 150), reads=28_500_000, name_len=44, seed=20240602, n_ppm=500, mode="native",
+                       desc="synthetic 10 GB NovaSeq 6000-shaped FASTQ, 150 bp, GPU-native multi-lane mode (a 10 GB per-GPU shard of BASELINE.json configs[2])"),
     "pacbio": dict(acid="m64187e__sars_cov_2__sequel_ii_e__acids", q="m64187e__sars_cov_2__sequel_ii_e__q_scores",
                    read_len=(10_000, 20_000), reads=166_000, name_len=40, seed=20240603, n_ppm=0, mode="compat",
                    desc="synthetic 5 GB PacBio Sequel II-shaped FASTQ, 10-20 kb reads (configs[4])"),
@@ -280,20 +280,42 @@ def run_gpu(args, w: dict):
     dec_a = torch.empty(S + 16, dtype=torch.uint8, device=dev)
     dec_q = torch.empty(S + 16, dtype=torch.uint8, device=dev)
 
-    def compress_all():
+    MODES = {"compat": capi.MODE_COMPAT, "native": capi.MODE_NATIVE}
+
+    def compress_all(mode):
         for c in chunks:
-            ctx.check(L.idn_gpu_compress_blocks_dev(ctx.h, C.byref(c.batch), capi.MODE_COMPAT, handles.ctypes.data, 2, 0, None,
+            ctx.check(L.idn_gpu_compress_blocks_dev(ctx.h, C.byref(c.batch), mode, handles.ctypes.data, 2, 0, None,
                                                     out_d.data_ptr() + c.out_base, c.out_cap, c.block_off.data_ptr(),
                                                     c.block_crc.data_ptr(), c.stats.data_ptr(), sp))
 
     def prepare_decode():
-        """block table of the decode calls from the compress outputs (device ops, outside the timed region)."""
+        """block table of the decode calls from the compress outputs (device ops, outside the timed region);
+        returns ({chunk: container bytes}, container bytes, payload bytes)."""
+        sizes, out_bytes, payload_bytes = {}, 0, 0
         for c in chunks:
             st = c.stats.cpu().numpy()
             if int(st[4]) > c.out_cap:
                 raise SystemExit(f"container chunk needs {int(st[4])} bytes, capacity {c.out_cap}: rerun with --full-bound")
             c.dec_len = (c.block_off[1:] - c.block_off[:-1] - 8).to(torch.int32).contiguous()
             c.dec_off = torch.cat([c.block_off[:-1] + 8, c.block_off[-1:]]).contiguous()
+            sizes[id(c)] = int(st[0])
+            out_bytes += int(st[0])
+            payload_bytes += int(st[3])
+        return sizes, out_bytes, payload_bytes
+
+    def decompress_all(mode, sizes):
+        for c in chunks:
+            ctx.check(L.idn_gpu_decompress_blocks_dev(ctx.h, out_d.data_ptr() + c.out_base, c.dec_off.data_ptr(),
+                                                      c.dec_len.data_ptr(), c.block_crc.data_ptr(), c.n_blocks, sizes[id(c)],
+                                                      mode, handles.ctypes.data, 2, dec_a.data_ptr() + c.s0,
+                                                      dec_q.data_ptr() + c.s0, c.dec_read_off.data_ptr(), c.n_reads, c.n_syms,
+                                                      c.dec_status.data_ptr(), sp))
+
+    def check_decode_status():
+        for c in chunks:
+            stt = c.dec_status.cpu().numpy()
+            if int(stt[0]) != 0 or int(stt[2]) != c.n_reads:
+                raise SystemExit(f"decode failed: status {stt.tolist()}")
 
     def barrier():
         torch.cuda.synchronize()
@@ -301,71 +323,67 @@ def run_gpu(args, w: dict):
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---- warm-up (also sizes the library workspaces and fixes the decode block tables) ----
-    compress_all()
-    torch.cuda.synchronize()
-    prepare_decode()
-    sizes, out_bytes, payload_bytes = {}, 0, 0
-    for c in chunks:
-        st = c.stats.cpu().numpy()
-        sizes[id(c)] = int(st[0])
-        out_bytes += int(st[0])
-        payload_bytes += int(st[3])
+    def measure(mode_name, steps, warmup, profile):
+        """W warm-up steps, then exactly `steps` timed steps with CUDA events on the launching stream."""
+        mode = MODES[mode_name]
+        compress_all(mode)
+        torch.cuda.synchronize()
+        sizes, out_bytes, payload_bytes = prepare_decode()
+        dec_a.zero_()
+        dec_q.zero_()
+        decompress_all(mode, sizes)
+        torch.cuda.synchronize()
+        check_decode_status()
+        for _ in range(max(0, warmup - 1)):
+            compress_all(mode)
+            decompress_all(mode, sizes)
+        barrier()
+        if profile:
+            ctx.profile(True)
+        launches0 = ctx.launches
+        sampler = ClockSampler(local)
+        sampler.start()
+        ev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(steps)]
+        t_wall0 = time.perf_counter()
+        for k in range(steps):
+            ev[k][0].record(stream)
+            compress_all(mode)
+            ev[k][1].record(stream)
+            decompress_all(mode, sizes)
+            ev[k][2].record(stream)
+        torch.cuda.synchronize()
+        t_wall = time.perf_counter() - t_wall0
+        clocks = sampler.stop()
+        res = {"launches": ctx.launches - launches0, "clocks": clocks, "t_wall": t_wall, "sizes": sizes, "out_bytes": out_bytes,
+               "payload_bytes": payload_bytes, "prof": ctx.profile_read() if profile else {},
+               "tc": sum(ev[k][0].elapsed_time(ev[k][1]) for k in range(steps)) / 1e3,
+               "td": sum(ev[k][1].elapsed_time(ev[k][2]) for k in range(steps)) / 1e3,
+               "t_total": ev[0][0].elapsed_time(ev[-1][2]) / 1e3}
+        if profile:
+            ctx.profile(False)
+        # lossless round trip of the whole workload, checked on the device outside the timed region
+        ok = bool(torch.equal(dec_a[:S], acids_d[:S]) and torch.equal(dec_q[:S], quals_d[:S]))
+        check_decode_status()
+        if not ok:
+            raise SystemExit(f"round trip mismatch in {mode_name} mode: the decoded symbols differ from the input")
+        res["verified"] = ok
+        return res
 
-    def decompress_all():
-        for c in chunks:
-            ctx.check(L.idn_gpu_decompress_blocks_dev(ctx.h, out_d.data_ptr() + c.out_base, c.dec_off.data_ptr(),
-                                                      c.dec_len.data_ptr(), c.block_crc.data_ptr(), c.n_blocks, sizes[id(c)],
-                                                      capi.MODE_COMPAT, handles.ctypes.data, 2, dec_a.data_ptr() + c.s0,
-                                                      dec_q.data_ptr() + c.s0, c.dec_read_off.data_ptr(), c.n_reads, c.n_syms,
-                                                      c.dec_status.data_ptr(), sp))
-
-    decompress_all()
-    torch.cuda.synchronize()
-    for c in chunks:
-        stt = c.dec_status.cpu().numpy()
-        if int(stt[0]) != 0:
-            raise SystemExit(f"decode failed: status {stt.tolist()}")
-    for _ in range(max(0, args.warmup - 1)):
-        compress_all()
-        decompress_all()
-    barrier()
-
-    # ---- timed region: exactly K steps, CUDA events on the launching stream ----
-    ctx.profile(True)
-    launches0 = ctx.launches
-    sampler = ClockSampler(local)
-    sampler.start()
-    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(args.steps)]
-    t_wall0 = time.perf_counter()
-    for k in range(args.steps):
-        ev[k][0].record(stream)
-        compress_all()
-        ev[k][1].record(stream)
-        decompress_all()
-        ev[k][2].record(stream)
-    torch.cuda.synchronize()
-    t_wall = time.perf_counter() - t_wall0
-    clocks = sampler.stop()
-    launches = ctx.launches - launches0
-    prof = ctx.profile_read()
-    ctx.profile(False)
-    tc = sum(ev[k][0].elapsed_time(ev[k][1]) for k in range(args.steps)) / 1e3
-    td = sum(ev[k][1].elapsed_time(ev[k][2]) for k in range(args.steps)) / 1e3
-    t_total = ev[0][0].elapsed_time(ev[-1][2]) / 1e3
-
-    # ---- verification outside the timed region: lossless round trip of the whole workload on the device ----
-    verified = bool(torch.equal(dec_a[:S], acids_d[:S]) and torch.equal(dec_q[:S], quals_d[:S]))
-    for c in chunks:
-        stt = c.dec_status.cpu().numpy()
-        verified = verified and int(stt[0]) == 0 and int(stt[2]) == c.n_reads
-    if not verified:
-        raise SystemExit("round trip mismatch: the decoded symbols differ from the input")
+    main_mode = args.mode or w["mode"]
+    other_mode = "native" if main_mode == "compat" else "compat"
+    other = None
+    if not args.no_other_mode and world == 1:  # a short look at the other container format (ratio delta, throughput); not the headline
+        other = measure(other_mode, 2, 3, False)
+    m = measure(main_mode, args.steps, args.warmup, True)
+    launches, clocks, t_wall, sizes, out_bytes, payload_bytes, prof = (m["launches"], m["clocks"], m["t_wall"], m["sizes"],
+                                                                        m["out_bytes"], m["payload_bytes"], m["prof"])
+    tc, td, t_total, verified = m["tc"], m["td"], m["t_total"], m["verified"]
 
     # ---- e2e: the host-pointer C-ABI calls on pinned host buffers, several ctx in flight ----
     e2e = None
     if not args.no_e2e:
-        e2e = run_e2e(args, w, capi, host, torch, local, chunks, acids_d, quals_d, read_off_h, block_first_h, sizes, dist, fq)
+        e2e = run_e2e(args, w, capi, host, torch, local, chunks, acids_d, quals_d, read_off_h, block_first_h, sizes, dist, fq,
+                      MODES[main_mode])
 
     # ---- max over ranks ----
     t_max = t_total
@@ -387,6 +405,7 @@ def run_gpu(args, w: dict):
     # decode reads the container chunk and writes 2 B/symbol; score reads 2 B/symbol per launch
     per_chunk = len(chunks)
     alg = {"encode": (2 * S + payload_bytes) / per_chunk, "decode": (2 * S + out_bytes) / per_chunk,
+           "encode_lane": (2 * S + payload_bytes) / per_chunk, "decode_lane": (2 * S + out_bytes) / per_chunk,
            "score": 2 * S / per_chunk, "assemble": 2 * payload_bytes / per_chunk, "crc_read": 2 * S / per_chunk}.get(dname, 2 * S / per_chunk)
     achieved = alg / (dms / dn / 1e3) / 1e9
     traffic = None
@@ -411,7 +430,7 @@ def run_gpu(args, w: dict):
             "metric": "fastq_compress_decompress_GBps", "value": value, "unit": "GB/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": t_max / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "u32", "data": "synthetic (model-driven sampler, SURVEY.md 8d)",
-            "config": {"workload": w["desc"], "name": args.workload, "mode": w["mode"], "acid_model": w["acid"], "q_model": w["q"],
+            "config": {"workload": w["desc"], "name": args.workload, "mode": main_mode, "acid_model": w["acid"], "q_model": w["q"],
                        "reads_per_gpu": n_reads, "symbols_per_gpu": S, "fastq_bytes_per_gpu": fq, "blocks_per_gpu": n_blocks,
                        "block_symbols": BLOCK_SYMBOLS, "chunk_blocks": cb, "names": "not stored (--no-identifiers protocol, "
                        "util/benchmark.py:161-179); their bytes count as FASTQ input", "l2": f"inputs {2 * S / 1e9:.1f} GB >> 126 MB L2, no flush needed",
@@ -426,6 +445,11 @@ def run_gpu(args, w: dict):
                            "threads": e2e["threads"], "compress_GBps": e2e["cGBps"], "decompress_GBps": e2e["dGBps"], "sample": e2e["sample"]}
         if cpu:
             line["cpu_baseline"] = cpu
+        if other:
+            line["other_mode"] = {"mode": other_mode, "compress_GBps": fq * 2 / other["tc"] / 1e9, "decompress_GBps": fq * 2 / other["td"] / 1e9,
+                                  "container_bytes_per_read": other["out_bytes"] / n_reads, "verified_round_trip": other["verified"],
+                                  "size_vs_main_mode": other["out_bytes"] / out_bytes, "steps": 2, "n_gpus": 1,
+                                  "note": "this rank only, device-resident, 2 timed steps"}
         print(json.dumps(line))
     if dist is not None:
         dist.barrier()
@@ -446,7 +470,7 @@ def cpu_baseline(args, w: dict) -> dict:
             "note": "reference-algorithm CPU restatement (oracle/), one worker thread per block like idn/thread_pool.rs"}
 
 
-def run_e2e(args, w, capi, host, torch, local, chunks, acids_d, quals_d, read_off_h, block_first_h, sizes, dist, fq_total):
+def run_e2e(args, w, capi, host, torch, local, chunks, acids_d, quals_d, read_off_h, block_first_h, sizes, dist, fq_total, mode):
     """Same step through idn_gpu_compress_blocks / idn_gpu_decompress_blocks with HOST buffers."""
     import psutil
     S = int(read_off_h[-1])
@@ -454,9 +478,10 @@ def run_e2e(args, w, capi, host, torch, local, chunks, acids_d, quals_d, read_of
     # pinned inputs, pinned container, pinned decoded output
     use = chunks
     need = 4 * S + sum(sizes.values()) * 2
-    avail = psutil.virtual_memory().available
-    if need * 1.5 > avail:
-        keep = max(1, int(len(chunks) * avail / (need * 1.5)))
+    # pinned host memory budget of this rank: half of what is available, shared by the ranks of the box
+    budget = 0.5 * psutil.virtual_memory().available / max(1, int(os.environ.get("LOCAL_WORLD_SIZE", os.environ.get("WORLD_SIZE", "1"))))
+    if need > budget:
+        keep = max(1, int(len(chunks) * budget / need))
         use = chunks[:keep]
     s_end = use[-1].s1
     r_end = use[-1].r1
@@ -499,7 +524,7 @@ def run_e2e(args, w, capi, host, torch, local, chunks, acids_d, quals_d, read_of
                 c, pc = use[i], per_chunk[i]
                 base = cont_np.ctypes.data + i * stride
                 if phase == 0:
-                    cx.check(L.idn_gpu_compress_blocks(cx.h, C.byref(pc["batch"]), capi.MODE_COMPAT, hd.ctypes.data, 2, 0, None,
+                    cx.check(L.idn_gpu_compress_blocks(cx.h, C.byref(pc["batch"]), mode, hd.ctypes.data, 2, 0, None,
                                                        base, stride, pc["block_off"].ctypes.data, pc["crc"].ctypes.data,
                                                        C.byref(pc["stats"])))
                 else:
@@ -507,7 +532,7 @@ def run_e2e(args, w, capi, host, torch, local, chunks, acids_d, quals_d, read_of
                     doff = np.append(bo[:-1] + 8, bo[-1]).astype(np.uint64)
                     dlen = (bo[1:] - bo[:-1] - 8).astype(np.uint32)
                     cx.check(L.idn_gpu_decompress_blocks(cx.h, base, doff.ctypes.data, dlen.ctypes.data, pc["crc"].ctypes.data,
-                                                         c.n_blocks, capi.MODE_COMPAT, hd.ctypes.data, 2, None, None,
+                                                         c.n_blocks, mode, hd.ctypes.data, 2, None, None,
                                                          da_np.ctypes.data + c.s0, dq_np.ctypes.data + c.s0,
                                                          pc["ro_out"].ctypes.data, c.n_reads, c.n_syms, C.byref(pc["bad"])))
         except Exception as e:  # surfaced after the join
@@ -566,6 +591,8 @@ def main():
     ap.add_argument("--cpu-blocks", type=int, default=0, help="blocks in the CPU sample (default 2 per core)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--mode", default="", choices=["", "compat", "native"], help="container format (default: the workload's)")
+    ap.add_argument("--no-other-mode", action="store_true", help="skip the short run of the other container format")
     ap.add_argument("--e2e-threads", type=int, default=3)
     ap.add_argument("--e2e-steps", type=int, default=3)
     args = ap.parse_args()

@@ -1212,6 +1212,7 @@ synth_kernel(const ModelDev* __restrict__ models, int32_t ia, int32_t iq, const 
     FwdWriter oa, oq;
     oa.init(acids + off);
     oq.init(quals + off);
+    uint32_t prev_q = 0;
     for (uint32_t i = 0; i < len; i++) {
         unsigned long long u = splitmix64(s);
         uint32_t slot_a = (uint32_t)u & kSlotMask, slot_q = (uint32_t)(u >> 14) & kSlotMask;
@@ -1221,10 +1222,16 @@ synth_kernel(const ModelDev* __restrict__ models, int32_t ia, int32_t iq, const 
         uint2 pk = __ldg(reinterpret_cast<const uint2*>(ma.dec) + row_a);
         uint32_t a = acid_find(pk, slot_a, start, freq);
         uint32_t q = q_find(mq.dec + (size_t)row_q * kQRowBytes, slot_q, start, freq);
+        // a context the model never saw maps to the uniform dummy row; drawing from it would leave the statistics the
+        // model was trained on for good (uniform symbols lead to more unseen contexts), which real reads do not do:
+        // keep the previous quality score and draw a plain base instead
+        if (row_a == 0) a = 1 + (slot_a & 3u);
+        if (row_q == 0 && i > 0) q = prev_q;
         if ((uint32_t)((u >> 32) % 1000000u) < n_ppm) {  // an N call with the Illumina "no call" quality '#'
             a = 0;
             q = 2;
         }
+        prev_q = q;
         oa.push(a);
         oq.push(q);
         const bool z = a * q == 0;

@@ -1245,15 +1245,21 @@ static int synth_chunk(void *vc, uint64_t chunk) {
         orc_gen_t ga, gq;
         orc_gen_init(&ga, &j->am->spec, len);
         orc_gen_init(&gq, &j->qm->spec, len);
+        uint32_t prev_q = 0;
         for (uint32_t i = 0; i < len; i++) {
             uint64_t u = splitmix64(&s);
             uint32_t slot_a = (uint32_t)u & 0x3fffu, slot_q = (uint32_t)(u >> 14) & 0x3fffu;
-            uint32_t a = sym_for_slot(j->am, ctx_for(j->am, orc_gen_current(&ga)), slot_a);
-            uint32_t q = sym_for_slot(j->qm, ctx_for(j->qm, orc_gen_current(&gq)), slot_q);
+            uint32_t row_a = ctx_for(j->am, orc_gen_current(&ga)), row_q = ctx_for(j->qm, orc_gen_current(&gq));
+            uint32_t a = sym_for_slot(j->am, row_a, slot_a);
+            uint32_t q = sym_for_slot(j->qm, row_q, slot_q);
+            /* unseen context (dummy row): plain base / previous quality score, see the device sampler */
+            if (row_a == 0) a = 1 + (slot_a & 3u);
+            if (row_q == 0 && i > 0) q = prev_q;
             if ((uint32_t)((u >> 32) % 1000000u) < j->n_ppm) {
                 a = 0;
                 q = 2;
             }
+            prev_q = q;
             j->acids[off + i] = (uint8_t)a;
             j->quals[off + i] = (uint8_t)q;
             orc_gen_update(&ga, (uint8_t)a, (uint8_t)q);
