@@ -40,7 +40,7 @@ def build_gpu(force: bool = False, verbose: bool = False) -> Path:
     return out
 
 
-HOST_SRCS = ["model.cpp", "capi_host.cpp"]
+HOST_SRCS = ["model.cpp", "idn.cpp", "capi_host.cpp"]
 # -ffp-contract=off / no -ffast-math: the f32 quantiser must round exactly like the reference (context.rs:346-371)
 GXX_FLAGS = ["-O2", "-std=c++17", "-fPIC", "-shared", "-Wall", "-ffp-contract=off", "-fno-fast-math", "-pthread"]
 

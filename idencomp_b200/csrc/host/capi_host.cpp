@@ -4,6 +4,7 @@
 #include <cstring>
 #include <string>
 
+#include "idn.hpp"
 #include "model.hpp"
 
 using namespace idencomp;
@@ -24,6 +25,8 @@ template <class F>
 int32_t guarded(F&& f) {
     try {
         return f();
+    } catch (const IdnError& e) {
+        return set_err(e.code, e.what());
     } catch (const ModelError& e) {
         return set_err(IDN_E_SERIALIZE, e.what());
     } catch (const std::exception& e) {
@@ -113,4 +116,183 @@ extern "C" int32_t idn_host_quantise(const float* probs, uint32_t nsym, uint32_t
         std::memcpy(cum_out, c.data(), c.size() * 4);
         return (int32_t)IDN_OK;
     });
+}
+
+// ---- IdnCompressor / IdnDecompressor ---------------------------------------------------------------------------------
+namespace idencomp {
+std::vector<size_t> cluster_centroids(const std::vector<uint32_t>& cost, size_t n_values, size_t n_centroids, size_t num_clusters,
+                                      std::vector<std::vector<size_t>>* members);
+std::vector<size_t> rank_models(const std::vector<uint32_t>& cost, size_t n_values, size_t n_models, size_t model_num);
+}  // namespace idencomp
+
+struct idn_host_compressor {
+    std::vector<uint8_t> out;
+    std::unique_ptr<IdnCompressor> c;
+};
+
+struct idn_host_decoded {
+    uint32_t version = 0;
+    std::vector<uint64_t> read_off{0}, name_off{0};
+    std::vector<uint8_t> acids, quals, names;
+};
+
+static ModelProvider provider_of(const idn_host_model* const* models, uint32_t n) {
+    std::vector<std::shared_ptr<const Model>> v;
+    for (uint32_t i = 0; i < n; i++) v.push_back(models[i]->m);
+    return ModelProvider(std::move(v));
+}
+
+extern "C" void idn_host_params_default(idn_host_params* p) {
+    IdnCompressorParams d;
+    p->max_block_total_len = d.max_block_total_len;
+    p->thread_num = d.thread_num;
+    p->include_identifiers = d.include_identifiers;
+    p->quality = d.quality;
+    p->fast = d.fast;
+    p->device = d.device;
+    p->mode = d.mode;
+    p->batch_blocks = d.batch_blocks;
+    p->lane_symbols = d.lane_symbols;
+}
+
+extern "C" int32_t idn_host_compressor_new(const idn_host_model* const* models, uint32_t n_models, const idn_host_params* params,
+                                           idn_host_compressor** out) {
+    if (!out || !params || (n_models && !models)) return set_err(IDN_E_INVALID_ARG, "NULL argument");
+    *out = nullptr;
+    return guarded([&] {
+        if (params->quality < 1 || params->quality > 9) throw IdnError(IDN_E_INVALID_ARG, "compression quality must be between 1 and 9");
+        IdnCompressorParams p = IdnCompressorParamsBuilder()
+                                    .model_provider(provider_of(models, n_models))
+                                    .max_block_total_len(params->max_block_total_len)
+                                    .thread_num(params->thread_num)
+                                    .include_identifiers(params->include_identifiers != 0)
+                                    .quality((uint8_t)params->quality)
+                                    .fast(params->fast != 0)
+                                    .device(params->device)
+                                    .mode(params->mode)
+                                    .batch_blocks(params->batch_blocks)
+                                    .lane_symbols(params->lane_symbols)
+                                    .build();
+        auto h = std::make_unique<idn_host_compressor>();
+        idn_host_compressor* raw = h.get();
+        h->c = std::make_unique<IdnCompressor>([raw](const uint8_t* d, size_t n) { raw->out.insert(raw->out.end(), d, d + n); }, std::move(p));
+        *out = h.release();
+        return (int32_t)IDN_OK;
+    });
+}
+
+extern "C" int32_t idn_host_compressor_add(idn_host_compressor* c, const uint8_t* name, uint64_t name_len, const uint8_t* acids,
+                                           const uint8_t* quals, uint64_t len) {
+    if (!c || (len && (!acids || !quals))) return set_err(IDN_E_INVALID_ARG, "NULL argument");
+    return guarded([&] {
+        FastqSequence s;
+        if (name && name_len) s.identifier.assign(reinterpret_cast<const char*>(name), name_len);
+        s.acids.assign(acids, acids + len);
+        s.quality_scores.assign(quals, quals + len);
+        c->c->add_sequence(std::move(s));
+        return (int32_t)IDN_OK;
+    });
+}
+
+extern "C" int32_t idn_host_compressor_add_batch(idn_host_compressor* c, uint64_t n_reads, const uint64_t* read_off,
+                                                 const uint8_t* acids, const uint8_t* quals, const uint64_t* name_off,
+                                                 const uint8_t* names) {
+    if (!c || (n_reads && !read_off)) return set_err(IDN_E_INVALID_ARG, "NULL argument");
+    return guarded([&] {
+        for (uint64_t r = 0; r < n_reads; r++) {
+            FastqSequence s;
+            if (name_off && names) s.identifier.assign(reinterpret_cast<const char*>(names) + name_off[r], name_off[r + 1] - name_off[r]);
+            s.acids.assign(acids + read_off[r], acids + read_off[r + 1]);
+            s.quality_scores.assign(quals + read_off[r], quals + read_off[r + 1]);
+            c->c->add_sequence(std::move(s));
+        }
+        return (int32_t)IDN_OK;
+    });
+}
+
+extern "C" int32_t idn_host_compressor_finish(idn_host_compressor* c) {
+    if (!c) return set_err(IDN_E_INVALID_ARG, "NULL argument");
+    return guarded([&] {
+        c->c->finish();
+        return (int32_t)IDN_OK;
+    });
+}
+
+extern "C" uint64_t idn_host_compressor_output(const idn_host_compressor* c, const uint8_t** data) {
+    if (data) *data = c->out.data();
+    return c->out.size();
+}
+
+extern "C" uint32_t idn_host_compressor_retained(const idn_host_compressor* c, uint8_t* ids, uint32_t cap) {
+    const auto& r = c->c->retained_models();
+    for (uint32_t i = 0; i < r.size() && i < cap && ids; i++) std::memcpy(ids + 32 * i, r[i].data(), 32);
+    return (uint32_t)r.size();
+}
+
+extern "C" void idn_host_compressor_stats(const idn_host_compressor* c, uint64_t out[9]) {
+    const CompressionStats& s = c->c->stats();
+    const uint64_t v[9] = {s.in_symbols, s.in_reads, s.in_identifier_bytes, s.out_bytes, s.out_identifier_bytes, s.out_payload_bytes,
+                           s.blocks, s.acid_model_switches, s.q_score_model_switches};
+    std::memcpy(out, v, sizeof v);
+}
+
+extern "C" void idn_host_compressor_free(idn_host_compressor* c) { delete c; }
+
+extern "C" int32_t idn_host_decompress(const idn_host_model* const* models, uint32_t n_models, int32_t device, uint32_t batch_blocks,
+                                       const uint8_t* idn, uint64_t idn_len, idn_host_decoded** out) {
+    if (!out || (!idn && idn_len) || (n_models && !models)) return set_err(IDN_E_INVALID_ARG, "NULL argument");
+    *out = nullptr;
+    return guarded([&] {
+        IdnDecompressorParams p;
+        p.model_provider = provider_of(models, n_models);
+        p.device = device;
+        p.batch_blocks = batch_blocks ? batch_blocks : 32;
+        uint64_t pos = 0;
+        IdnDecompressor d([&](uint8_t* dst, size_t n) {
+            size_t k = (size_t)std::min<uint64_t>(n, idn_len - pos);
+            std::memcpy(dst, idn + pos, k);
+            pos += k;
+            return k;
+        }, std::move(p));
+        auto res = std::make_unique<idn_host_decoded>();
+        while (auto s = d.next_sequence()) {
+            res->acids.insert(res->acids.end(), s->acids.begin(), s->acids.end());
+            res->quals.insert(res->quals.end(), s->quality_scores.begin(), s->quality_scores.end());
+            res->names.insert(res->names.end(), s->identifier.begin(), s->identifier.end());
+            res->read_off.push_back(res->acids.size());
+            res->name_off.push_back(res->names.size());
+        }
+        res->version = d.version();
+        *out = res.release();
+        return (int32_t)IDN_OK;
+    });
+}
+
+extern "C" uint64_t idn_host_decoded_reads(const idn_host_decoded* d) { return d->read_off.size() - 1; }
+extern "C" uint32_t idn_host_decoded_version(const idn_host_decoded* d) { return d->version; }
+extern "C" const uint64_t* idn_host_decoded_read_off(const idn_host_decoded* d) { return d->read_off.data(); }
+extern "C" const uint8_t* idn_host_decoded_acids(const idn_host_decoded* d) { return d->acids.data(); }
+extern "C" const uint8_t* idn_host_decoded_quals(const idn_host_decoded* d) { return d->quals.data(); }
+extern "C" const uint64_t* idn_host_decoded_name_off(const idn_host_decoded* d) { return d->name_off.data(); }
+extern "C" const uint8_t* idn_host_decoded_names(const idn_host_decoded* d) { return d->names.data(); }
+extern "C" void idn_host_decoded_free(idn_host_decoded* d) { delete d; }
+
+extern "C" uint32_t idn_host_cluster(const uint32_t* cost, uint64_t n_values, uint32_t n_centroids, uint32_t num_clusters,
+                                     uint32_t* centroids_out, uint32_t* value_cluster_out) {
+    std::vector<uint32_t> c(cost, cost + n_values * n_centroids);
+    std::vector<std::vector<size_t>> members;
+    std::vector<size_t> best = cluster_centroids(c, n_values, n_centroids, num_clusters, &members);
+    for (size_t k = 0; k < best.size(); k++) {
+        if (centroids_out) centroids_out[k] = (uint32_t)best[k];
+        if (value_cluster_out)
+            for (size_t v : members[k]) value_cluster_out[v] = (uint32_t)k;
+    }
+    return (uint32_t)best.size();
+}
+
+extern "C" uint32_t idn_host_rank(const uint32_t* cost, uint64_t n_values, uint32_t n_models, uint32_t model_num, uint32_t* models_out) {
+    std::vector<uint32_t> c(cost, cost + n_values * n_models);
+    std::vector<size_t> best = rank_models(c, n_values, n_models, model_num);
+    for (size_t k = 0; k < best.size(); k++) models_out[k] = (uint32_t)best[k];
+    return (uint32_t)best.size();
 }

@@ -19,8 +19,20 @@ EXPORTS = [
     "idn_host_last_error", "idn_host_model_load", "idn_host_model_from_bytes", "idn_host_model_new",
     "idn_host_model_empty", "idn_host_model_free", "idn_host_model_type", "idn_host_model_len",
     "idn_host_model_spec_name", "idn_host_model_identifier", "idn_host_model_cum_table", "idn_host_model_upload",
-    "idn_host_quantise",
+    "idn_host_quantise", "idn_host_params_default", "idn_host_compressor_new", "idn_host_compressor_add",
+    "idn_host_compressor_add_batch", "idn_host_compressor_finish", "idn_host_compressor_output",
+    "idn_host_compressor_retained", "idn_host_compressor_stats", "idn_host_compressor_free", "idn_host_decompress",
+    "idn_host_decoded_reads", "idn_host_decoded_version", "idn_host_decoded_read_off", "idn_host_decoded_acids",
+    "idn_host_decoded_quals", "idn_host_decoded_name_off", "idn_host_decoded_names", "idn_host_decoded_free",
+    "idn_host_cluster", "idn_host_rank",
 ]
+
+
+class Params(C.Structure):
+    """idn_host_params = IdnCompressorParamsBuilder (idn/compressor.rs:164-274) + device / mode / batching."""
+    _fields_ = [("max_block_total_len", C.c_uint32), ("thread_num", C.c_uint32), ("include_identifiers", C.c_int32),
+                ("quality", C.c_uint32), ("fast", C.c_int32), ("device", C.c_int32), ("mode", C.c_int32),
+                ("batch_blocks", C.c_uint32), ("lane_symbols", C.c_uint32)]
 
 _LIB = None
 
@@ -52,6 +64,31 @@ def load():
     L.idn_host_model_cum_table.restype = u64
     L.idn_host_model_upload.argtypes = [vp, vp, C.POINTER(i32)]
     L.idn_host_quantise.argtypes = [vp, u32, u32, vp]
+    L.idn_host_params_default.argtypes = [C.POINTER(Params)]
+    L.idn_host_params_default.restype = None
+    L.idn_host_compressor_new.argtypes = [vp, u32, C.POINTER(Params), C.POINTER(vp)]
+    L.idn_host_compressor_add.argtypes = [vp, vp, u64, vp, vp, u64]
+    L.idn_host_compressor_add_batch.argtypes = [vp, u64, vp, vp, vp, vp, vp]
+    L.idn_host_compressor_finish.argtypes = [vp]
+    L.idn_host_compressor_output.argtypes = [vp, C.POINTER(vp)]
+    L.idn_host_compressor_output.restype = u64
+    L.idn_host_compressor_retained.argtypes = [vp, vp, u32]
+    L.idn_host_compressor_retained.restype = u32
+    L.idn_host_compressor_stats.argtypes = [vp, vp]
+    L.idn_host_compressor_stats.restype = None
+    L.idn_host_compressor_free.argtypes = [vp]
+    L.idn_host_compressor_free.restype = None
+    L.idn_host_decompress.argtypes = [vp, u32, i32, u32, vp, u64, C.POINTER(vp)]
+    for name, rt in (("reads", u64), ("version", u32), ("read_off", vp), ("acids", vp), ("quals", vp), ("name_off", vp), ("names", vp)):
+        f = getattr(L, "idn_host_decoded_" + name)
+        f.argtypes = [vp]
+        f.restype = rt
+    L.idn_host_decoded_free.argtypes = [vp]
+    L.idn_host_decoded_free.restype = None
+    L.idn_host_cluster.argtypes = [vp, u64, u32, u32, vp, vp]
+    L.idn_host_cluster.restype = u32
+    L.idn_host_rank.argtypes = [vp, u64, u32, u32, vp]
+    L.idn_host_rank.restype = u32
     _LIB = L
     return L
 
@@ -149,3 +186,120 @@ class Model:
         h = C.c_int32(-1)
         _check(self.L.idn_host_model_upload(ctx.h, self.h, C.byref(h)))
         return int(h.value)
+
+
+def _model_array(models):
+    arr = (C.c_void_p * max(len(models), 1))(*[m.h for m in models])
+    return arr
+
+
+class IdnCompressor:
+    """idencomp::IdnCompressor (idn/compressor.rs:443-585) writing to memory.
+
+        c = IdnCompressor(models, quality=7, include_identifiers=True)   # IdnCompressor::with_params
+        c.add_sequence(b"name", acids, quals) ; ... ; idn = c.finish()
+    """
+
+    def __init__(self, models, *, max_block_total_len=4 * 1024 * 1024, thread_num=0, include_identifiers=True, quality=7,
+                 fast=False, device=0, mode=capi.MODE_COMPAT, batch_blocks=32, lane_symbols=4096):
+        self.L = load()
+        p = Params()
+        self.L.idn_host_params_default(C.byref(p))
+        p.max_block_total_len, p.thread_num, p.include_identifiers = max_block_total_len, thread_num, int(include_identifiers)
+        p.quality, p.fast, p.device, p.mode, p.batch_blocks, p.lane_symbols = quality, int(fast), device, mode, batch_blocks, lane_symbols
+        self._models = list(models)
+        h = C.c_void_p()
+        _check(self.L.idn_host_compressor_new(_model_array(self._models), len(self._models), C.byref(p), C.byref(h)))
+        self.h = h
+
+    def add_sequence(self, name: bytes, acids, quals):
+        a = np.ascontiguousarray(acids, dtype=np.uint8)
+        q = np.ascontiguousarray(quals, dtype=np.uint8)
+        if len(a) != len(q):
+            raise ValueError("acids and quality scores differ in length")
+        nm = np.frombuffer(name, dtype=np.uint8) if name else np.zeros(0, dtype=np.uint8)
+        _check(self.L.idn_host_compressor_add(self.h, nm.ctypes.data if nm.size else None, nm.size,
+                                              a.ctypes.data if a.size else None, q.ctypes.data if q.size else None, len(a)))
+
+    def add_batch(self, read_off, acids, quals, name_off=None, names=None):
+        ro = np.ascontiguousarray(read_off, dtype=np.uint64)
+        a = np.ascontiguousarray(acids, dtype=np.uint8)
+        q = np.ascontiguousarray(quals, dtype=np.uint8)
+        no = nm = None
+        if name_off is not None:
+            no = np.ascontiguousarray(name_off, dtype=np.uint64)
+            nm = np.ascontiguousarray(names, dtype=np.uint8)
+            if nm.size == 0:
+                nm = np.zeros(1, dtype=np.uint8)
+        _check(self.L.idn_host_compressor_add_batch(self.h, len(ro) - 1, ro.ctypes.data, a.ctypes.data if a.size else None,
+                                                    q.ctypes.data if q.size else None, None if no is None else no.ctypes.data,
+                                                    None if nm is None else nm.ctypes.data))
+
+    def finish(self) -> bytes:
+        _check(self.L.idn_host_compressor_finish(self.h))
+        return self.output()
+
+    def output(self) -> bytes:
+        ptr = C.c_void_p()
+        n = self.L.idn_host_compressor_output(self.h, C.byref(ptr))
+        return C.string_at(ptr, n) if n else b""
+
+    def retained_models(self):
+        buf = (C.c_uint8 * (32 * 255))()
+        n = self.L.idn_host_compressor_retained(self.h, buf, 255)
+        return [bytes(buf[32 * i:32 * i + 32]) for i in range(n)]
+
+    def stats(self) -> dict:
+        out = (C.c_uint64 * 9)()
+        self.L.idn_host_compressor_stats(self.h, out)
+        keys = ("in_symbols", "in_reads", "in_identifier_bytes", "out_bytes", "out_identifier_bytes", "out_payload_bytes",
+                "blocks", "acid_model_switches", "q_score_model_switches")
+        return dict(zip(keys, (int(v) for v in out)))
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.idn_host_compressor_free(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def decompress(models, idn: bytes, *, device=0, batch_blocks=32) -> dict:
+    """idencomp::IdnDecompressor (idn/decompressor.rs:455-566): every sequence of the file as one SoA batch."""
+    L = load()
+    buf = np.frombuffer(idn, dtype=np.uint8)
+    h = C.c_void_p()
+    models = list(models)
+    _check(L.idn_host_decompress(_model_array(models), len(models), device, batch_blocks, buf.ctypes.data if buf.size else None,
+                                 buf.size, C.byref(h)))
+    try:
+        n = int(L.idn_host_decoded_reads(h))
+        ro = np.ctypeslib.as_array(C.cast(L.idn_host_decoded_read_off(h), C.POINTER(C.c_uint64)), (n + 1,)).copy()
+        no = np.ctypeslib.as_array(C.cast(L.idn_host_decoded_name_off(h), C.POINTER(C.c_uint64)), (n + 1,)).copy()
+        S, NB = int(ro[-1]), int(no[-1])
+        take = lambda p, k: np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_uint8)), (k,)).copy() if k else np.zeros(0, dtype=np.uint8)
+        return {"version": int(L.idn_host_decoded_version(h)), "read_off": ro, "acids": take(L.idn_host_decoded_acids(h), S),
+                "quals": take(L.idn_host_decoded_quals(h), S), "name_off": no, "names": take(L.idn_host_decoded_names(h), NB)}
+    finally:
+        L.idn_host_decoded_free(h)
+
+
+def cluster(cost, num_clusters: int):
+    """Clustering::make_clusters (clustering.rs:21-118) on cost[value][centroid] -> (centroids, cluster of every value)."""
+    c = np.ascontiguousarray(cost, dtype=np.uint32)
+    cent = np.zeros(max(num_clusters, 1), dtype=np.uint32)
+    vc = np.zeros(max(c.shape[0], 1), dtype=np.uint32)
+    n = load().idn_host_cluster(c.ctypes.data, c.shape[0], c.shape[1], num_clusters, cent.ctypes.data, vc.ctypes.data)
+    return cent[:n].tolist(), vc[:c.shape[0]].tolist()
+
+
+def rank(cost, model_num: int):
+    """get_model_ranking (idn/model_chooser.rs:103-138) on cost[read][model] -> best model columns."""
+    c = np.ascontiguousarray(cost, dtype=np.uint32)
+    out = np.zeros(max(model_num, 1), dtype=np.uint32)
+    n = load().idn_host_rank(c.ctypes.data, c.shape[0], c.shape[1], model_num, out.ctypes.data)
+    return out[:n].tolist()

@@ -49,6 +49,60 @@ int32_t idn_host_model_upload(idn_gpu_ctx *ctx, const idn_host_model *m, idn_mod
 /* Context::as_integer_cum_freqs (context.rs:346-371) -- exposed for the known-answer tests */
 int32_t idn_host_quantise(const float *probs, uint32_t nsym, uint32_t scale_bits, uint32_t *cum_out);
 
+/* ---- IdnCompressor (idn/compressor.rs:443-585) ------------------------------------------------------- */
+typedef struct idn_host_compressor idn_host_compressor;
+typedef struct {                    /* IdnCompressorParamsBuilder, idn/compressor.rs:164-274 */
+    uint32_t max_block_total_len;   /* default 4 Mi */
+    uint32_t thread_num;            /* default 0 */
+    int32_t include_identifiers;    /* default 1 */
+    uint32_t quality;               /* 1..9, default 7 */
+    int32_t fast;                   /* default 0; sets quality 1 */
+    int32_t device;                 /* CUDA device, default 0 */
+    int32_t mode;                   /* IDN_MODE_COMPAT (container version 1) or IDN_MODE_NATIVE (version 2) */
+    uint32_t batch_blocks;          /* blocks per device call, default 32 */
+    uint32_t lane_symbols;          /* native mode lane quantum, default 4096 */
+} idn_host_params;
+void idn_host_params_default(idn_host_params *p);
+/* IdnCompressor::with_params over an in-memory writer; `models` is the ModelProvider (order = provider order) */
+int32_t idn_host_compressor_new(const idn_host_model *const *models, uint32_t n_models, const idn_host_params *params,
+                                idn_host_compressor **out);
+/* IdnCompressor::add_sequence; IDN_E_SEQUENCE_TOO_LONG when len > max_block_total_len / 2 */
+int32_t idn_host_compressor_add(idn_host_compressor *c, const uint8_t *name, uint64_t name_len, const uint8_t *acids,
+                                const uint8_t *quals, uint64_t len);
+/* add_sequence for every read of an SoA batch (name_off/names may be NULL) */
+int32_t idn_host_compressor_add_batch(idn_host_compressor *c, uint64_t n_reads, const uint64_t *read_off,
+                                      const uint8_t *acids, const uint8_t *quals, const uint64_t *name_off,
+                                      const uint8_t *names);
+int32_t idn_host_compressor_finish(idn_host_compressor *c);     /* IdnCompressor::finish */
+/* the container written so far (complete after finish); the pointer stays valid until the next call on `c` */
+uint64_t idn_host_compressor_output(const idn_host_compressor *c, const uint8_t **data);
+/* identifiers written to the metadata, acid models first; returns their number */
+uint32_t idn_host_compressor_retained(const idn_host_compressor *c, uint8_t *ids /* [cap][32] */, uint32_t cap);
+/* in_symbols, in_reads, in_identifier_bytes, out_bytes, out_identifier_bytes, out_payload_bytes, blocks,
+ * acid_model_switches, q_score_model_switches */
+void idn_host_compressor_stats(const idn_host_compressor *c, uint64_t out[9]);
+void idn_host_compressor_free(idn_host_compressor *c);
+
+/* ---- IdnDecompressor (idn/decompressor.rs:455-566): next_sequence until None, results as one SoA batch ---- */
+typedef struct idn_host_decoded idn_host_decoded;
+int32_t idn_host_decompress(const idn_host_model *const *models, uint32_t n_models, int32_t device, uint32_t batch_blocks,
+                            const uint8_t *idn, uint64_t idn_len, idn_host_decoded **out);
+uint64_t idn_host_decoded_reads(const idn_host_decoded *d);
+uint32_t idn_host_decoded_version(const idn_host_decoded *d);
+const uint64_t *idn_host_decoded_read_off(const idn_host_decoded *d); /* [reads+1] */
+const uint8_t *idn_host_decoded_acids(const idn_host_decoded *d);
+const uint8_t *idn_host_decoded_quals(const idn_host_decoded *d);
+const uint64_t *idn_host_decoded_name_off(const idn_host_decoded *d); /* [reads+1] */
+const uint8_t *idn_host_decoded_names(const idn_host_decoded *d);
+void idn_host_decoded_free(idn_host_decoded *d);
+
+/* ---- file-level model subset selection on a cost matrix cost[value][centroid] (exposed for the known-answer tests) ----
+ * Clustering::make_clusters (clustering.rs:21-118): centroid index per cluster and the cluster of every value;
+ * returns the number of clusters.  get_model_ranking (idn/model_chooser.rs:103-138): the best `model_num` columns. */
+uint32_t idn_host_cluster(const uint32_t *cost, uint64_t n_values, uint32_t n_centroids, uint32_t num_clusters,
+                          uint32_t *centroids_out, uint32_t *value_cluster_out);
+uint32_t idn_host_rank(const uint32_t *cost, uint64_t n_values, uint32_t n_models, uint32_t model_num, uint32_t *models_out);
+
 #ifdef __cplusplus
 }
 #endif

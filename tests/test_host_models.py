@@ -68,3 +68,29 @@ def test_corrupt_model_is_rejected(H):
         H.Model.from_bytes(bytes(data))
     with pytest.raises(H.HostError):
         H.Model.load(MODELS / "does-not-exist.msgpack")
+
+
+# ---- file-level model subset selection: clustering.rs:232-271 (the reference's own test of this code) ------------
+def _point_costs(points, centroids):
+    return [[(p[0] - c[0]) ** 2 + (p[1] - c[1]) ** 2 for c in centroids] for p in points]
+
+
+def test_cluster_trivial(H):
+    cent, vc = H.cluster(_point_costs([(0, 0)], [(2, 1), (-2, 2), (0, 0), (3, -3)]), 1)
+    assert cent == [2] and vc == [0]
+
+
+def test_cluster_points(H):
+    points = [(2, 2), (2, 3), (4, 1), (-1, 1), (-2, 1), (-3, 2), (-2, -2), (2, -2), (2, -3)]
+    centroids = [(-6, -7), (0, 0), (2, 1), (-2, 2), (-1, -1), (3, -3)]
+    cent, vc = H.cluster(_point_costs(points, centroids), 4)
+    clusters = sorted((c, [v for v, k in enumerate(vc) if k == i]) for i, c in enumerate(cent))
+    assert clusters == [(2, [0, 1, 2]), (3, [3, 4, 5]), (4, [6]), (5, [7, 8])]
+
+
+def test_rank_models(H):
+    # read 0 prefers model 2, reads 1-2 prefer model 0; ties keep provider order (stable sorts, model_chooser.rs:114-136)
+    cost = [[5, 9, 1], [1, 9, 5], [1, 9, 5], [7, 7, 7]]
+    assert H.rank(cost, 1) == [0]
+    assert H.rank(cost, 2) == [0, 2]
+    assert H.rank(cost, 5) == [0, 2, 1]
