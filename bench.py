@@ -442,7 +442,7 @@ def run_gpu(args, w: dict):
         if e2e:
             line["e2e"] = {"value": 2 * fq * e2e["steps"] * world / e2e["_t"] / 1e9, "unit": "GB/s",
                            "h2d_bytes_per_step": e2e["h2d"], "d2h_bytes_per_step": e2e["d2h"], "steps": e2e["steps"],
-                           "threads": e2e["threads"], "compress_GBps": e2e["cGBps"], "decompress_GBps": e2e["dGBps"], "sample": e2e["sample"]}
+                           "threads": e2e["threads"], "chunk_blocks": args.e2e_chunk_blocks, "compress_GBps": e2e["cGBps"], "decompress_GBps": e2e["dGBps"], "sample": e2e["sample"]}
         if cpu:
             line["cpu_baseline"] = cpu
         if other:
@@ -474,10 +474,25 @@ def run_e2e(args, w, capi, host, torch, local, chunks, acids_d, quals_d, read_of
     """Same step through idn_gpu_compress_blocks / idn_gpu_decompress_blocks with HOST buffers."""
     import psutil
     S = int(read_off_h[-1])
+    total_out = sum(sizes.values())
+    # the host-pointer calls are synchronous: overlap of H2D, kernels and D2H comes from several ctx in flight, so the
+    # e2e leg uses smaller chunks than the device-resident leg (a short pipeline fill and tail)
+    n_blocks_all = len(block_first_h) - 1
+    e2e_chunks = []
+    for b0 in range(0, n_blocks_all, args.e2e_chunk_blocks):
+        c = Chunk()
+        c.b0, c.b1 = b0, min(n_blocks_all, b0 + args.e2e_chunk_blocks)
+        c.r0, c.r1 = int(block_first_h[c.b0]), int(block_first_h[c.b1])
+        c.s0, c.s1 = int(read_off_h[c.r0]), int(read_off_h[c.r1])
+        c.n_reads, c.n_syms, c.n_blocks = c.r1 - c.r0, c.s1 - c.s0, c.b1 - c.b0
+        e2e_chunks.append(c)
+    per_sym = total_out / max(S, 1)
+    sizes = {id(c): int(per_sym * c.n_syms * 1.15) + 64 * c.n_blocks + 4096 for c in e2e_chunks}  # container capacity per chunk
+    chunks = e2e_chunks
     n_threads = max(1, min(args.e2e_threads, len(chunks)))
     # pinned inputs, pinned container, pinned decoded output
     use = chunks
-    need = 4 * S + sum(sizes.values()) * 2
+    need = 4 * S + total_out * 2
     # pinned host memory budget of this rank: half of what is available, shared by the ranks of the box
     budget = 0.5 * psutil.virtual_memory().available / max(1, int(os.environ.get("LOCAL_WORLD_SIZE", os.environ.get("WORLD_SIZE", "1"))))
     if need > budget:
@@ -554,6 +569,9 @@ def run_e2e(args, w, capi, host, torch, local, chunks, acids_d, quals_d, read_of
     for _ in range(2):  # warm-up: sizes the staging buffers of every ctx
         phase(0)
         phase(1)
+    if args.e2e_profile:
+        for cx, _ in ctxs:
+            cx.profile(True)
     if dist is not None:
         dist.barrier()
     torch.cuda.synchronize()
@@ -563,6 +581,16 @@ def run_e2e(args, w, capi, host, torch, local, chunks, acids_d, quals_d, read_of
         tc += phase(0)
         td += phase(1)
     t_all = time.perf_counter() - t0
+    if args.e2e_profile:
+        agg = {}
+        for cx, _ in ctxs:
+            for k, (n, ms) in cx.profile_read().items():
+                a = agg.setdefault(k, [0, 0.0])
+                a[0] += n
+                a[1] += ms
+            cx.profile(False)
+        print("e2e phases (summed over ctx, ms per step):", {k: (v[0] // steps, round(v[1] / steps, 1)) for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1])},
+              file=sys.stderr)
     ok = np.array_equal(da_np[:s_end], a_np[:s_end]) and np.array_equal(dq_np[:s_end], q_np[:s_end])
     if not ok:
         raise SystemExit("e2e round trip mismatch")
@@ -594,7 +622,9 @@ def main():
     ap.add_argument("--mode", default="", choices=["", "compat", "native"], help="container format (default: the workload's)")
     ap.add_argument("--no-other-mode", action="store_true", help="skip the short run of the other container format")
     ap.add_argument("--e2e-threads", type=int, default=3)
+    ap.add_argument("--e2e-chunk-blocks", type=int, default=32, help="blocks per host-pointer call in the e2e leg")
     ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--e2e-profile", action="store_true", help="print the host-side phase times of the e2e leg to stderr")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3

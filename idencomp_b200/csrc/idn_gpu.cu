@@ -6,6 +6,7 @@
 
 #include <cstdarg>
 #include <cstdio>
+#include <chrono>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -85,6 +86,13 @@ struct idn_gpu_ctx {
         cudaEvent_t ev;
     };
     std::vector<ProfMark> prof_marks;
+    // host wall-clock phases of the host-pointer entry points (reported by idn_gpu_profile_read as "host:<phase>")
+    struct HostPhase {
+        const char* name;
+        uint64_t n;
+        double ms;
+    };
+    std::vector<HostPhase> host_phases;
     std::vector<ModelSlot> slots;
     ModelDev* d_models = nullptr;  // [kMaxSlots], mirrors slots[].dev
     ModelDev d_models_host0{};     // all-zero placeholder for the by-value model parameters of the non-uniform kernels
@@ -149,6 +157,25 @@ void prof_mark(idn_gpu_ctx* c, const char* name, cudaStream_t st) {
     do {                                              \
         if (ctx->profiling) prof_mark(ctx, nullptr, st); \
     } while (0)
+
+struct HostTimer {
+    idn_gpu_ctx* c;
+    std::chrono::steady_clock::time_point t0;
+    explicit HostTimer(idn_gpu_ctx* ctx) : c(ctx), t0(std::chrono::steady_clock::now()) {}
+    void lap(const char* name) {
+        if (!c->profiling) return;
+        auto t1 = std::chrono::steady_clock::now();
+        double ms = std::chrono::duration<double, std::milli>(t1 - t0).count();
+        t0 = t1;
+        for (auto& h : c->host_phases)
+            if (strcmp(h.name, name) == 0) {
+                h.n++;
+                h.ms += ms;
+                return;
+            }
+        c->host_phases.push_back({name, 1, ms});
+    }
+};
 
 uint32_t bitlen(uint64_t v) {
     uint32_t n = 0;
@@ -981,14 +1008,18 @@ extern "C" int32_t idn_gpu_compress_blocks(idn_gpu_ctx* ctx, const idn_batch* b,
                                            uint64_t out_cap, uint64_t* block_off, uint32_t* block_crc,
                                            idn_compress_stats* stats) {
     if (!ctx) return IDN_E_INVALID_ARG;
+    HostTimer hv(ctx);
     int32_t rc = check_host_batch(ctx, b, true);
     if (rc) return rc;
+    hv.lap("host:c_validate");
     if (!block_off) return fail(ctx, IDN_E_INVALID_ARG, "block_off is NULL");
     CU(cudaSetDevice(ctx->device));
     cudaStream_t st = ctx->stream;
+    HostTimer ht(ctx);
     idn_batch d;
     rc = stage_batch(ctx, b, &d, st);
     if (rc) return rc;
+    ht.lap("host:c_stage_enqueue");
     uint32_t* d_prefix = nullptr;
     uint64_t prefix_total = 0;
     if (prefix_len) {
@@ -1011,7 +1042,9 @@ extern "C" int32_t idn_gpu_compress_blocks(idn_gpu_ctx* ctx, const idn_batch* b,
     uint32_t err = 0;
     CU(cudaMemcpyAsync(&hs, ctx->s_stats.p, sizeof hs, cudaMemcpyDeviceToHost, st));
     CU(cudaMemcpyAsync(&err, &ctx->w_small.as<SmallParams>()->err, 4, cudaMemcpyDeviceToHost, st));
+    ht.lap("host:c_kernels_enqueue");
     CU(cudaStreamSynchronize(st));
+    ht.lap("host:c_wait_h2d_kernels");
     if (stats) *stats = hs;
     if (err & 1) return fail(ctx, IDN_E_INVALID_SYMBOL, "input holds an acid > 4 or a quality score > 93");
     if (hs.required_bytes > out_cap) {
@@ -1023,6 +1056,7 @@ extern "C" int32_t idn_gpu_compress_blocks(idn_gpu_ctx* ctx, const idn_batch* b,
     CU(cudaMemcpyAsync(block_off, ctx->s_blockoff.p, ((size_t)b->n_blocks + 1) * 8, cudaMemcpyDeviceToHost, st));
     if (block_crc) CU(cudaMemcpyAsync(block_crc, ctx->s_crc.p, (size_t)b->n_blocks * 4, cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
+    ht.lap("host:c_d2h");
     return IDN_OK;
 }
 
@@ -1384,6 +1418,7 @@ extern "C" int32_t idn_gpu_decompress_blocks(idn_gpu_ctx* ctx, const uint8_t* bl
     CU(ctx->s_qout.ensure(out_symbols_cap + 16));
     CU(ctx->s_offout.ensure((out_reads_cap + 1) * 8));
     CU(ctx->s_status.ensure(64));
+    HostTimer ht(ctx);
     if (nbytes) CU(cudaMemcpyAsync(ctx->s_blocks.p, blocks, nbytes, cudaMemcpyHostToDevice, st));
     CU(cudaMemcpyAsync(ctx->s_blockoff.p, block_off, ((size_t)n_blocks + 1) * 8, cudaMemcpyHostToDevice, st));
     CU(ctx->s_blocklen.ensure(((size_t)n_blocks + 1) * 4));
@@ -1405,7 +1440,9 @@ extern "C" int32_t idn_gpu_decompress_blocks(idn_gpu_ctx* ctx, const uint8_t* bl
     BlockCounters bc = carve_counters(ctx->w_blk.p, n_blocks);
     CU(cudaMemcpyAsync(&tot[0], bc.reads + n_blocks, 8, cudaMemcpyDeviceToHost, st));
     CU(cudaMemcpyAsync(&tot[1], bc.syms + n_blocks, 8, cudaMemcpyDeviceToHost, st));
+    ht.lap("host:d_enqueue");
     CU(cudaStreamSynchronize(st));
+    ht.lap("host:d_wait_h2d_kernels");
     if (hst[0]) {
         if (bad_block) *bad_block = hst[1];
         return status_to_error(ctx, hst);
@@ -1417,6 +1454,7 @@ extern "C" int32_t idn_gpu_decompress_blocks(idn_gpu_ctx* ctx, const uint8_t* bl
     }
     CU(cudaMemcpyAsync(read_off_out, ctx->s_offout.p, (R + 1) * 8, cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
+    ht.lap("host:d_d2h");
     if (host_crc && block_crc && n_blocks) {
         // CRC with names on the device: stage names and run the CRC kernels over the decoded batch
         idn_batch d;
@@ -1590,6 +1628,11 @@ extern "C" int32_t idn_gpu_profile_read(idn_gpu_ctx* ctx, char* buf, uint64_t ca
         snprintf(line, sizeof line, "%s %llu %.6f\n", a.name, (unsigned long long)a.n, a.ms);
         out += line;
     }
+    for (auto& hph : ctx->host_phases) {
+        snprintf(line, sizeof line, "%s %llu %.6f\n", hph.name, (unsigned long long)hph.n, hph.ms);
+        out += line;
+    }
+    ctx->host_phases.clear();
     ctx->prof_marks.clear();
     ctx->prof_used = 0;
     if (out.size() + 1 > cap) return fail(ctx, IDN_E_NOSPACE, "profile text needs %zu bytes", out.size() + 1);

@@ -871,7 +871,7 @@ walk_kernel(const uint8_t* __restrict__ blocks, const unsigned long long* __rest
             const unsigned long long* __restrict__ slot_base, ReadIndexDev ix, unsigned long long* __restrict__ blk_reads,
             unsigned long long* __restrict__ blk_syms, int32_t* __restrict__ status /*[2]: code, block*/) {
     __shared__ __align__(16) uint8_t tiles[2][kWalkTile + 32];
-    __shared__ uint4 ent[kWalkMaxEnt];  // {payload offset in the tile, payload length, seq_len, models}
+    __shared__ uint16_t plist[kWalkMaxEnt];  // tile offsets of the slice headers found in the current tile
     const uint32_t b = blockIdx.x, lane = threadIdx.x;
     if (b >= n_blocks) return;
     const unsigned long long boff = block_off[b];
@@ -885,7 +885,7 @@ walk_kernel(const uint8_t* __restrict__ blocks, const unsigned long long* __rest
 
     unsigned long long pos = 0;  // block-relative position of the next slice header
     unsigned long long n_reads = 0, n_syms = 0;
-    int cur_a = -1, cur_q = -1;
+    uint32_t mdl = 0xffffu;      // active models: acid | q << 8, 0xff = none yet (container indices are < 255)
     const unsigned long long slot0 = slot_base[b];
     uint32_t cur = 0;
     uintptr_t A = blk_abs & ~(uintptr_t)15;  // absolute address of tile[0] of the current buffer
@@ -897,91 +897,105 @@ walk_kernel(const uint8_t* __restrict__ blocks, const unsigned long long* __rest
         cp_async_wait<1>();
         __syncwarp();
         const uint8_t* tile = tiles[cur];
-        // block positions [t_lo, t_hi) are staged in tile[]; t_lo may lie before the block (alignment)
+        const uint32_t* tw = reinterpret_cast<const uint32_t*>(tile);
+        // block positions [t_lo, t_lo + kStaged) are staged in tile[]; t_lo may lie before the block (alignment)
         const long long t_lo = (long long)(A - blk_abs);
-        uint32_t n_ent = 0;
+        const uint32_t kStaged = kWalkTile + 16;
+        const uint32_t p0 = (uint32_t)((long long)pos - t_lo);  // tile offset of the first header
+        const unsigned long long left = n - pos;                // bytes of the block from pos on
+        // clamped, so that a bound accepted in 32 bits is always a true bound; rejections are rechecked in 64 bits
+        const uint32_t n_off = p0 + (uint32_t)(left > 0x40000000ull ? 0x40000000ull : left);
+        // ---- lane 0 chases the chain and does nothing else: one thread's dependent-instruction latency bounds this
+        // loop, so validation, model tracking and index building are left to the whole warp below ----
+        uint32_t n_hdr = 0, p_end = p0;
         if (lane == 0) {
-            // 32-bit arithmetic only: one thread's dependent-instruction chain is what bounds this loop.
-            // p = position inside the tile; the block ends at tile offset n_off (if it ends inside the staged range)
-            uint32_t p = (uint32_t)((long long)pos - t_lo);
-            const unsigned long long left = n - pos;  // bytes of the block from pos on
-            // clamped, so that a bound accepted in 32 bits is always a true bound; rejections are rechecked in 64 bits
-            const uint32_t n_off = p + (uint32_t)(left > 0x40000000ull ? 0x40000000ull : left);
-            const uint32_t kStaged = kWalkTile + 16;
-            int mdl = (cur_a & 0xff) | ((cur_q & 0xff) << 8);  // -1 -> 0xff = none (indices are < 255)
-            const uint32_t* tw = reinterpret_cast<const uint32_t*>(tile);
-            while (p < n_off && n_ent < (uint32_t)kWalkMaxEnt && p + 9 <= kStaged) {
-                // 9 header bytes from 3 aligned words: kind = byte p, w1 = bytes p+1..p+4 and w2 = bytes p+5..p+8, big endian
+            uint32_t p = p0;
+            while (p < n_off && n_hdr < (uint32_t)kWalkMaxEnt && p + 9 <= kStaged) {
+                const uint32_t wi = p >> 2, sh = p & 3;
+                const uint32_t W0 = tw[wi], W1 = tw[wi + 1];
+                const uint32_t kind = (W0 >> (8 * sh)) & 0xffu;
+                const uint32_t w1 = __byte_perm(W0, W1, 0x1234u + sh * 0x1111u);  // bytes p+1 .. p+4, big endian
+                plist[n_hdr++] = (uint16_t)p;
+                // Sequence: 9 + length; SwitchModel: 2; Identifiers: 6 + length; anything else, or a length that cannot
+                // be real, stops the chain here (the warp reports it)
+                uint32_t step = kind == 2 ? 9u + w1 : (kind == 1 ? 2u : 6u + w1);
+                if (kind > 2 || w1 > 0x7fff0000u) step = 0x7fffffffu;
+                p = p + step > p ? p + step : 0x7fffffffu;
+            }
+            p_end = p;
+        }
+        n_hdr = __shfl_sync(0xffffffffu, n_hdr, 0);
+        p_end = __shfl_sync(0xffffffffu, p_end, 0);
+        // ---- the warp: re-read every header, validate, track the active models, emit index entries ----
+        for (uint32_t base = 0; base < n_hdr && st == 0; base += 32) {
+            const uint32_t i = base + lane;
+            const bool have = i < n_hdr;
+            uint32_t kind = 0xff, w1 = 0, w2 = 0, p = 0, bad = 0;
+            if (have) {
+                p = plist[i];
                 const uint32_t wi = p >> 2, sh = p & 3;
                 const uint32_t W0 = tw[wi], W1 = tw[wi + 1], W2 = tw[wi + 2];
-                const uint32_t sel = 0x1234u + sh * 0x1111u;  // result bytes 0..3 = pair bytes o+3, o+2, o+1, o with o = sh + 1
-                const uint32_t kind = (W0 >> (8 * sh)) & 0xffu;
-                const uint32_t w1 = __byte_perm(W0, W1, sel), w2 = __byte_perm(W1, W2, sel);
-                const uint32_t room = n_off - p;  // >= 1
+                const uint32_t sel = 0x1234u + sh * 0x1111u;
+                kind = (W0 >> (8 * sh)) & 0xffu;
+                w1 = __byte_perm(W0, W1, sel);
+                w2 = __byte_perm(W1, W2, sel);
+                const unsigned long long room = n - (unsigned long long)((long long)p + t_lo);  // bytes from this header on
                 if (kind == 2) {  // Sequence: u32 length, u32 seq_len, payload   (data.rs:79-84, decompressor_block.rs:216-239)
-                    if (room < 9 || w1 > room - 9 || w1 < 8) {
-                        // n_off is clamped for blocks larger than 1 GiB: redo the bound in 64 bits before failing
-                        unsigned long long l2 = n - ((unsigned long long)((long long)p + t_lo));
-                        if (l2 < 9 || w1 > l2 - 9 || w1 < 8) { st = 3; break; }
-                    }
-                    if ((mdl & 0xff) == 0xff || (mdl >> 8) == 0xff) { st = 8; break; }
-                    ent[n_ent++] = make_uint4(p + 9, w1, w2, (uint32_t)mdl);  // tile-relative; rebased by the writers below
-                    if (w1 >= 0x7fff0000u) {  // cannot happen inside a staged tile walk without leaving it: jump in 64 bits
-                        pos = (unsigned long long)((long long)p + t_lo) + 9ull + w1;
-                        p = 0xffffffffu;
-                        break;
-                    }
-                    p += 9u + w1;
+                    if (room < 9 || w1 > room - 9 || w1 < 8) bad = 3;
                 } else if (kind == 1) {  // SwitchModel: u8 index   (decompressor_block.rs:194-214)
-                    if (room < 2) { st = 3; break; }
-                    uint32_t idx = w1 >> 24;
-                    if (idx >= n_models || idx >= 255) { st = 7; break; }
-                    if (model_type[idx] == 0) mdl = (mdl & 0xff00) | idx; else mdl = (mdl & 0xff) | (idx << 8);
-                    p += 2;
+                    if (room < 2) bad = 3;
+                    else if ((w1 >> 24) >= n_models || (w1 >> 24) >= 255) bad = 7;
                 } else if (kind == 0) {  // Identifiers: u32 length, u8 compression, data -- names stay on the host
-                    if (room < 6 || w1 > room - 6) {
-                        unsigned long long l2 = n - ((unsigned long long)((long long)p + t_lo));
-                        if (l2 < 6 || w1 > l2 - 6) { st = 3; break; }
-                    }
-                    if (w1 >= 0x7fff0000u) {
-                        pos = (unsigned long long)((long long)p + t_lo) + 6ull + w1;
-                        p = 0xffffffffu;
-                        break;
-                    }
-                    p += 6u + w1;
+                    if (room < 6 || w1 > room - 6) bad = 3;
                 } else {
-                    st = 3;
-                    break;
+                    bad = 3;
                 }
             }
-            if (p != 0xffffffffu) pos = (unsigned long long)((long long)p + t_lo);
-            cur_a = (mdl & 0xff) == 0xff ? -1 : (mdl & 0xff);
-            cur_q = (mdl >> 8) == 0xff ? -1 : (mdl >> 8);
-        }
-        n_ent = __shfl_sync(0xffffffffu, n_ent, 0);
-        st = __shfl_sync(0xffffffffu, st, 0);
-        pos = __shfl_sync(0xffffffffu, pos, 0);
-        // ---- the warp writes the entries of this tile ----
-        for (uint32_t base = 0; base < n_ent; base += 32) {
-            uint32_t i = base + lane;
-            const uint4 e = i < n_ent ? ent[i] : make_uint4(0, 0, 0, 0);
-            unsigned long long sl = e.z, inc = sl;
+            // active models at every header: inclusive scan of "the right operand overrides what it sets"
+            uint32_t set = 0xffffu;  // what this slice sets: acid | q << 8, 0xff = nothing
+            if (have && kind == 1 && !bad) {
+                const uint32_t idx = w1 >> 24;
+                set = model_type[idx] == 0 ? (0xff00u | idx) : (0x00ffu | (idx << 8));
+            }
+            for (int d = 1; d < 32; d <<= 1) {
+                const uint32_t o = __shfl_up_sync(0xffffffffu, set, d);
+                if (lane >= (uint32_t)d) {
+                    const uint32_t a = (set & 0xffu) != 0xffu ? (set & 0xffu) : (o & 0xffu);
+                    const uint32_t q = (set & 0xff00u) != 0xff00u ? (set & 0xff00u) : (o & 0xff00u);
+                    set = a | q;
+                }
+            }
+            uint32_t act = ((set & 0xffu) != 0xffu ? (set & 0xffu) : (mdl & 0xffu)) |
+                           ((set & 0xff00u) != 0xff00u ? (set & 0xff00u) : (mdl & 0xff00u));
+            if (have && kind == 2 && !bad && ((act & 0xffu) == 0xffu || (act >> 8) == 0xffu)) bad = 8;  // NoActiveModel
+            mdl = __shfl_sync(0xffffffffu, act, 31);
+            // the first bad header decides the status (headers are in chain order)
+            const uint32_t bad_mask = __ballot_sync(0xffffffffu, bad != 0);
+            if (bad_mask) st = __shfl_sync(0xffffffffu, (int32_t)bad, __ffs(bad_mask) - 1);
+            const uint32_t ok_before = bad_mask ? ((1u << (__ffs(bad_mask) - 1)) - 1) : 0xffffffffu;
+            const bool is_seq = have && kind == 2 && ((ok_before >> lane) & 1u);
+            const uint32_t seq_mask = __ballot_sync(0xffffffffu, is_seq);
+            unsigned long long sl = is_seq ? w2 : 0, inc = sl;
             for (int d = 1; d < 32; d <<= 1) {
                 unsigned long long o = __shfl_up_sync(0xffffffffu, inc, d);
                 if (lane >= (uint32_t)d) inc += o;
             }
-            if (i < n_ent) {
-                unsigned long long slot = slot0 + n_reads + i;
-                ix.pay_off[slot] = boff + (unsigned long long)(t_lo + (long long)e.x);
-                ix.pay_len[slot] = e.y;
-                ix.seq_len[slot] = e.z;
+            if (is_seq) {
+                const unsigned long long slot = slot0 + n_reads + __popc(seq_mask & ((1u << lane) - 1));
+                ix.pay_off[slot] = boff + (unsigned long long)(t_lo + (long long)p + 9);
+                ix.pay_len[slot] = w1;
+                ix.seq_len[slot] = w2;
                 ix.sym_off[slot] = n_syms + inc - sl;
-                ix.am[slot] = (uint8_t)(e.w & 0xff);
-                ix.qm[slot] = (uint8_t)(e.w >> 8);
+                ix.am[slot] = (uint8_t)(act & 0xffu);
+                ix.qm[slot] = (uint8_t)(act >> 8);
             }
             n_syms += __shfl_sync(0xffffffffu, inc, 31);
+            n_reads += __popc(seq_mask);
         }
-        n_reads += n_ent;
+        if (st == 0) {
+            if (p_end >= 0x7fffffffu) st = 3;  // the chain stopped on a header the warp did not flag: cannot happen, but never walk on
+            else pos = (unsigned long long)((long long)p_end + t_lo);
+        }
         __syncwarp();
         if (st != 0 || pos >= n) break;
         // the prefetched tile serves when the next header starts inside it (and the walk can make progress)
