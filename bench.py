@@ -518,17 +518,29 @@ def run_e2e(args, w, capi, host, torch, local, chunks, acids_d, quals_d, read_of
         am = host.Model.load(MODELS / (w["acid"] + ".msgpack"))
         qm = host.Model.load(MODELS / (w["q"] + ".msgpack"))
         ctxs.append((cx, np.asarray([am.upload(cx), qm.upload(cx)], dtype=np.int32)))
+    def pinned(n, dtype):
+        """every buffer the C-ABI calls copy from / to is page-locked (a pageable copy is staged and synchronous)"""
+        t = torch.empty(max(int(n), 1), dtype=dtype, pin_memory=True)
+        return t, t.numpy()
+
     per_chunk = []
     for i, c in enumerate(use):
-        ro = np.ascontiguousarray(read_off_h[c.r0:c.r1 + 1] - read_off_h[c.r0])
-        bf = np.ascontiguousarray((block_first_h[c.b0:c.b1 + 1] - block_first_h[c.b0]).astype(np.uint32))
+        ro_t, ro = pinned(c.n_reads + 1, torch.int64)
+        ro[:c.n_reads + 1] = (read_off_h[c.r0:c.r1 + 1] - read_off_h[c.r0]).view(np.int64)
+        bf_t, bf = pinned(c.n_blocks + 1, torch.int32)
+        bf[:c.n_blocks + 1] = (block_first_h[c.b0:c.b1 + 1] - block_first_h[c.b0]).astype(np.int32)
+        boff_t, boff = pinned(c.n_blocks + 1, torch.int64)
+        crc_t, crc = pinned(c.n_blocks, torch.int32)
+        doff_t, doff = pinned(c.n_blocks + 1, torch.int64)
+        dlen_t, dlen = pinned(c.n_blocks, torch.int32)
+        roo_t, roo = pinned(c.n_reads + 1, torch.int64)
         b = capi.Batch()
         b.n_reads, b.n_symbols, b.n_blocks = c.n_reads, c.n_syms, c.n_blocks
         b.acids, b.quals = a_np.ctypes.data + c.s0, q_np.ctypes.data + c.s0
         b.read_off, b.block_first_read = ro.ctypes.data, bf.ctypes.data
-        per_chunk.append(dict(batch=b, keep=(ro, bf), block_off=np.zeros(c.n_blocks + 1, dtype=np.uint64),
-                              crc=np.zeros(c.n_blocks, dtype=np.uint32), stats=capi.CompressStats(),
-                              ro_out=np.zeros(c.n_reads + 1, dtype=np.uint64), bad=C.c_int32(-1)))
+        per_chunk.append(dict(batch=b, keep=(ro_t, bf_t, boff_t, crc_t, doff_t, dlen_t, roo_t), block_off=boff.view(np.uint64),
+                              crc=crc.view(np.uint32), doff=doff.view(np.uint64), dlen=dlen.view(np.uint32),
+                              stats=capi.CompressStats(), ro_out=roo.view(np.uint64), bad=C.c_int32(-1)))
     errors = []
 
     def worker(t, phase):
@@ -543,9 +555,11 @@ def run_e2e(args, w, capi, host, torch, local, chunks, acids_d, quals_d, read_of
                                                        base, stride, pc["block_off"].ctypes.data, pc["crc"].ctypes.data,
                                                        C.byref(pc["stats"])))
                 else:
-                    bo = pc["block_off"]
-                    doff = np.append(bo[:-1] + 8, bo[-1]).astype(np.uint64)
-                    dlen = (bo[1:] - bo[:-1] - 8).astype(np.uint32)
+                    bo, doff, dlen = pc["block_off"], pc["doff"], pc["dlen"]
+                    nb = c.n_blocks
+                    doff[:nb] = bo[:nb] + 8
+                    doff[nb] = bo[nb]
+                    dlen[:nb] = (bo[1:nb + 1] - bo[:nb] - 8).astype(np.uint32)
                     cx.check(L.idn_gpu_decompress_blocks(cx.h, base, doff.ctypes.data, dlen.ctypes.data, pc["crc"].ctypes.data,
                                                          c.n_blocks, mode, hd.ctypes.data, 2, None, None,
                                                          da_np.ctypes.data + c.s0, dq_np.ctypes.data + c.s0,
