@@ -411,8 +411,8 @@ def run_gpu(args, w: dict):
     traffic = None
     tpath = ROOT / "profiles" / "traffic.json"
     if tpath.exists():
-        try:
-            traffic = json.loads(tpath.read_text()).get(dname)
+        try:  # measured DRAM bytes per symbol of that kernel (one ncu --set full capture), scaled to this launch size
+            traffic = json.loads(tpath.read_text())[dname]["bytes_per_symbol"] * S / per_chunk
         except Exception:
             traffic = None
     roofline = {"bound": "hbm", "kernel": dname + "_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
