@@ -696,7 +696,11 @@ extern "C" int32_t idn_gpu_compress_blocks_dev(idn_gpu_ctx* ctx, const idn_batch
                                                                            ctx->w_sizes.as<uint32_t>(), &dsp->err);
             LAUNCHED("score");
         }
-        if (!fast) {  // K3
+        if (!fast && n_score == 0) {  // one candidate per type: no choice to make
+            CU(cudaMemsetAsync(chosen, 0, 4 * R, st));
+            switch_single_kernel<<<(B + 127) / 128, 128, 0, st>>>(batch->block_first_read, B, switched, R);
+            LAUNCHED("switch_single");
+        } else if (!fast) {  // K3
             switch_kernel<<<2 * B, 32, 0, st>>>(ctx->w_sizes.as<uint32_t>(), n_score, dsp->cand_cols, dsp->n_cand,
                                                 dsp->has_sizes, batch->block_first_read, B, chosen, switched, R);
             LAUNCHED("switch");
@@ -760,7 +764,7 @@ extern "C" int32_t idn_gpu_compress_blocks_dev(idn_gpu_ctx* ctx, const idn_batch
         aa.cand_index = dsp->cand_index;
         aa.out = out;
         aa.out_cap = out_cap;
-        assemble_kernel<<<(unsigned)((R * 32 + 255) / 256), 256, 0, st>>>(aa);
+        assemble_kernel<<<(unsigned)((R + 127) / 128), 128, 0, st>>>(aa);
         LAUNCHED("assemble");
         stats_kernel<<<592, 256, 0, st>>>(ctx->w_paylen.as<uint32_t>(), switched, R, dsp->stats);
         LAUNCHED("stats");

@@ -241,6 +241,16 @@ switch_kernel(const uint32_t* __restrict__ sizes_all, uint32_t n_models, const u
     }
 }
 
+// one candidate per type: nothing to choose; only the first read of every block carries the two SwitchModel slices
+// (chosen / switched were cleared by the caller)
+__global__ void switch_single_kernel(const uint32_t* __restrict__ block_first, uint32_t n_blocks, uint8_t* __restrict__ switched,
+                                     uint64_t n_reads) {
+    uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= n_blocks || block_first[b + 1] == block_first[b]) return;
+    switched[block_first[b]] = 1;
+    switched[n_reads + block_first[b]] = 1;
+}
+
 // ---------------------------------------------------------------------------------------------------
 // K4: two-state per-read rANS encode.  One thread per read, symbols walked last -> first.
 // Writes the payload right-aligned into the read's scratch slot [slot_end - pay_len, slot_end).
@@ -536,7 +546,6 @@ block_layout_kernel(const unsigned long long* __restrict__ slice_off, const uint
     stats[0] = pos;  // out_bytes / required_bytes
 }
 
-// one warp per read: slice headers + payload copy from the scratch slot to its final place
 struct AssembleArgs {
     const uint64_t* read_off;
     uint64_t n_reads;
@@ -555,45 +564,65 @@ struct AssembleArgs {
     uint64_t out_cap;
 };
 
-__global__ void __launch_bounds__(256)
+// copies n bytes src -> dst (any alignments) as aligned destination words built from two aligned source words
+__device__ __forceinline__ void copy_bytes_words(uint8_t* __restrict__ d, const uint8_t* __restrict__ src, uint32_t n) {
+    uint32_t head = (uint32_t)((4 - (reinterpret_cast<uintptr_t>(d) & 3)) & 3);
+    if (head > n) head = n;
+    for (uint32_t i = 0; i < head; i++) d[i] = src[i];
+    const uint32_t words = (n - head) >> 2;
+    const uint8_t* s2 = src + head;
+    const uint32_t sh = (uint32_t)(reinterpret_cast<uintptr_t>(s2) & 3);
+    const uint32_t* sw = reinterpret_cast<const uint32_t*>(s2 - sh);
+    uint32_t* dw = reinterpret_cast<uint32_t*>(d + head);
+    if (sh == 0) {
+        for (uint32_t i = 0; i < words; i++) dw[i] = sw[i];
+    } else if (words) {
+        uint32_t lo = sw[0];
+        for (uint32_t i = 0; i < words; i++) {
+            uint32_t hi = sw[i + 1];  // holds at least one byte of the range: 4 * (i + 1) - sh < 4 * words + ... <= n - head
+            dw[i] = __funnelshift_r(lo, hi, 8 * sh);
+            lo = hi;
+        }
+    }
+    for (uint32_t i = head + 4 * words; i < n; i++) d[i] = src[i];
+}
+
+// one thread per read: slice headers + payload copy from the scratch slot to its final place.  The threads of a warp
+// own neighbouring reads, i.e. neighbouring scratch slots and neighbouring destinations.
+__global__ void __launch_bounds__(128)
 assemble_kernel(AssembleArgs A) {
-    uint64_t r = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    uint32_t lane = threadIdx.x & 31;
+    uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= A.n_reads) return;
     uint32_t b = A.read_block[r];
-    bool empty = false;
-    unsigned long long dst = A.block_off[b] + 8 + (A.prefix_len ? A.prefix_len[b] : 0) + (A.fast && !empty ? 4 : 0) +
+    unsigned long long dst = A.block_off[b] + 8 + (A.prefix_len ? A.prefix_len[b] : 0) + (A.fast ? 4 : 0) +
                              (A.slice_off[r] - A.slice_off[A.block_first[b]]);
     uint32_t plen = A.pay_len[r];
     uint32_t len = (uint32_t)(A.read_off[r + 1] - A.read_off[r]);
     uint32_t nsw = 0;
     if (A.switched) nsw = A.switched[r] + A.switched[A.n_reads + r];
     if (dst + 2ull * nsw + 9 + plen > A.out_cap) return;  // IDN_E_NOSPACE is reported by the host from stats
-    if (lane == 0) {
-        uint8_t* p = A.out + dst;
-        if (A.switched) {
-            if (A.switched[r]) {  // acid first (compressor_block.rs:103-104)
-                *p++ = 1;
-                *p++ = A.cand_index[A.chosen[r]];
-            }
-            if (A.switched[A.n_reads + r]) {
-                *p++ = 1;
-                *p++ = A.cand_index[kMaxCand + A.chosen[A.n_reads + r]];
-            }
+    uint8_t* p = A.out + dst;
+    if (A.switched) {
+        if (A.switched[r]) {  // acid first (compressor_block.rs:103-104)
+            *p++ = 1;
+            *p++ = A.cand_index[A.chosen[r]];
         }
-        p[0] = 2;
-        p[1] = (uint8_t)(plen >> 24);
-        p[2] = (uint8_t)(plen >> 16);
-        p[3] = (uint8_t)(plen >> 8);
-        p[4] = (uint8_t)plen;
-        p[5] = (uint8_t)(len >> 24);
-        p[6] = (uint8_t)(len >> 16);
-        p[7] = (uint8_t)(len >> 8);
-        p[8] = (uint8_t)len;
+        if (A.switched[A.n_reads + r]) {
+            *p++ = 1;
+            *p++ = A.cand_index[kMaxCand + A.chosen[A.n_reads + r]];
+        }
     }
+    p[0] = 2;
+    p[1] = (uint8_t)(plen >> 24);
+    p[2] = (uint8_t)(plen >> 16);
+    p[3] = (uint8_t)(plen >> 8);
+    p[4] = (uint8_t)plen;
+    p[5] = (uint8_t)(len >> 24);
+    p[6] = (uint8_t)(len >> 16);
+    p[7] = (uint8_t)(len >> 8);
+    p[8] = (uint8_t)len;
     const uint8_t* src = A.scratch + 4ull * A.read_off[r + 1] + 8ull * (r + 1) - plen;
-    uint8_t* d = A.out + dst + 2ull * nsw + 9;
-    for (uint32_t i = lane; i < plen; i += 32) d[i] = src[i];
+    copy_bytes_words(p + 9, src, plen);
 }
 
 // read -> block map (one thread per block fills its range; blocks are large, so use a grid-stride loop)
