@@ -761,7 +761,23 @@ __device__ __forceinline__ uint32_t block_crc_reduce(const uint32_t* __restrict_
     if (c0 > r1) c0 = r1;
     if (c1 > r1) c1 = r1;
     CrcPair acc{0, 0};
-    for (uint64_t r = c0; r < c1; r++) acc = crc_concat(acc, CrcPair{part_crc[r], part_len[r]}, xpow);
+    // reads of one length are the rule: keep x^(8 len) mod P of the previous length instead of rebuilding it per read
+    unsigned long long last_len = 0;
+    uint32_t last_pow = 0x80000000u;
+    for (uint64_t r = c0; r < c1; r++) {
+        const CrcPair nxt{part_crc[r], part_len[r]};
+        if (nxt.len == 0) continue;
+        if (acc.len == 0) {
+            acc = nxt;
+            continue;
+        }
+        if (nxt.len != last_len) {
+            last_len = nxt.len;
+            last_pow = x8n_mod_p(nxt.len, xpow);
+        }
+        acc.crc = gf2_mul(last_pow, acc.crc) ^ nxt.crc;
+        acc.len += nxt.len;
+    }
     s_crc[threadIdx.x] = acc.crc;
     s_len[threadIdx.x] = acc.len;
     __syncthreads();
