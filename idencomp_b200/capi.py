@@ -31,6 +31,8 @@ EXPORTS = [
     "idn_gpu_compress_blocks", "idn_gpu_compress_blocks_dev", "idn_gpu_compress_bound", "idn_gpu_index_blocks",
     "idn_gpu_decompress_blocks", "idn_gpu_decompress_blocks_dev", "idn_gpu_decompress_reads", "idn_gpu_block_crc",
     "idn_gpu_synth_reads_dev", "idn_gpu_profile", "idn_gpu_profile_read", "idn_gpu_set_lane_symbols",
+    "idn_gpu_fastq_parse", "idn_gpu_fastq_parse_dev", "idn_gpu_fastq_fetch", "idn_gpu_fastq_batch_dev", "idn_gpu_fastq_format",
+    "idn_gpu_fastq_format_dev",
 ]
 
 
@@ -56,6 +58,15 @@ class CompressStats(C.Structure):
 
 class IndexTotals(C.Structure):
     _fields_ = [("n_reads", C.c_uint64), ("n_symbols", C.c_uint64)]
+
+
+class FastqInfo(C.Structure):
+    _fields_ = [("n_reads", C.c_uint64), ("n_symbols", C.c_uint64), ("n_name_bytes", C.c_uint64), ("n_lines", C.c_uint64),
+                ("error_kind", C.c_int32), ("reserved", C.c_int32), ("bad_record", C.c_uint64)]
+
+
+FASTQ_ERRORS = {1: "InvalidFormat", 2: "InvalidAcid", 3: "InvalidQualityScore", 4: "AcidAndQualityScoreLengthMismatch",
+                5: "EofReached"}
 
 
 class ReadIndex(C.Structure):
@@ -114,6 +125,18 @@ def load():
     L.idn_gpu_block_crc.restype = i32
     L.idn_gpu_synth_reads_dev.argtypes = [vp, i32, i32, vp, u64, u64, u64, u32, vp, vp, vp]
     L.idn_gpu_synth_reads_dev.restype = i32
+    L.idn_gpu_fastq_parse.argtypes = [vp, vp, u64, C.POINTER(FastqInfo)]
+    L.idn_gpu_fastq_parse.restype = i32
+    L.idn_gpu_fastq_parse_dev.argtypes = [vp, vp, u64, C.POINTER(FastqInfo), vp]
+    L.idn_gpu_fastq_parse_dev.restype = i32
+    L.idn_gpu_fastq_fetch.argtypes = [vp, vp, vp, vp, vp, vp]
+    L.idn_gpu_fastq_fetch.restype = i32
+    L.idn_gpu_fastq_batch_dev.argtypes = [vp, C.POINTER(Batch)]
+    L.idn_gpu_fastq_batch_dev.restype = i32
+    L.idn_gpu_fastq_format.argtypes = [vp, C.POINTER(Batch), i32, vp, u64, C.POINTER(u64)]
+    L.idn_gpu_fastq_format.restype = i32
+    L.idn_gpu_fastq_format_dev.argtypes = [vp, C.POINTER(Batch), i32, vp, u64, vp, vp]
+    L.idn_gpu_fastq_format_dev.restype = i32
     L.idn_gpu_set_lane_symbols.argtypes = [vp, u32]
     L.idn_gpu_set_lane_symbols.restype = i32
     L.idn_gpu_profile.argtypes = [vp, i32]
@@ -317,3 +340,34 @@ class Context:
         crc = np.zeros(max(b.n_blocks, 1), dtype=np.uint32)
         self.check(self.L.idn_gpu_block_crc(self.h, C.byref(b), crc.ctypes.data))
         return crc[:b.n_blocks]
+
+    # ---- FASTQ text <-> symbols (row f1) ------------------------------------------------------------------
+    def fastq_parse(self, text: bytes):
+        """FastqReader over a whole buffer -> (read_off, acids, quals, name_off, names).  Raises IdnGpuError
+        (SerializeError) with .fastq_error / .bad_record on malformed input."""
+        buf = np.frombuffer(text, dtype=np.uint8)
+        info = FastqInfo()
+        rc = self.L.idn_gpu_fastq_parse(self.h, buf.ctypes.data if buf.size else None, buf.size, C.byref(info))
+        if rc != OK:
+            e = IdnGpuError(rc, self.L.idn_gpu_last_error(self.h).decode())
+            e.fastq_error = FASTQ_ERRORS.get(int(info.error_kind), str(info.error_kind))
+            e.bad_record = int(info.bad_record)
+            raise e
+        a = np.zeros(max(info.n_symbols, 1), dtype=np.uint8)
+        q = np.zeros(max(info.n_symbols, 1), dtype=np.uint8)
+        ro = np.zeros(info.n_reads + 1, dtype=np.uint64)
+        nm = np.zeros(max(info.n_name_bytes, 1), dtype=np.uint8)
+        no = np.zeros(info.n_reads + 1, dtype=np.uint64)
+        self.check(self.L.idn_gpu_fastq_fetch(self.h, a.ctypes.data, q.ctypes.data, ro.ctypes.data, nm.ctypes.data, no.ctypes.data))
+        return ro, a[:info.n_symbols], q[:info.n_symbols], no, nm[:info.n_name_bytes]
+
+    def fastq_format(self, read_off, acids, quals, name_off=None, names=None, title_with_separator=False) -> bytes:
+        """FastqWriter::write_sequence for every read."""
+        b, keep = make_batch(read_off, acids, quals, None, name_off, names)
+        n_reads, S = b.n_reads, b.n_symbols
+        nb = 0 if name_off is None else int(np.asarray(name_off)[-1])
+        cap = 2 * S + 6 * n_reads + nb * (2 if title_with_separator else 1) + 16
+        out = np.zeros(cap, dtype=np.uint8)
+        n = C.c_uint64(0)
+        self.check(self.L.idn_gpu_fastq_format(self.h, C.byref(b), int(title_with_separator), out.ctypes.data, cap, C.byref(n)))
+        return out[:n.value].tobytes()

@@ -11,6 +11,7 @@
 #include <string>
 #include <vector>
 
+#include "idn_fastq.cuh"
 #include "idn_native.cuh"
 
 using namespace idn;
@@ -102,6 +103,10 @@ struct idn_gpu_ctx {
     DevBuf w_scratch, w_paylen, w_sizes, w_chosen, w_tiles, w_sliceoff, w_readblock, w_small, w_crcpart, w_crclen;
     DevBuf w_lanefirst, w_laneoff, w_laneblock, w_blkinfo, w_nhdr;  // native mode
     uint32_t lane_syms = 4096;  // lane quantum of the native format
+    // FASTQ text <-> symbols (idn_fastq.cuh): results of the last parse stay here until the next one
+    DevBuf f_text, f_tilecnt, f_tilebase, f_linestart, f_linefn, f_linestate, f_tilefn, f_tilestate, f_recscan, f_title, f_namelo,
+        f_namelen, f_readlen, f_readoff, f_nameoff, f_names, f_acids, f_quals, f_err, f_fmtoff, f_fmttext;
+    idn_fastq_info f_info{};
     DevBuf w_index;  // decode-side per-read index
     DevBuf w_blk;    // decode-side per-block counters
     // staging of the host-pointer paths
@@ -366,6 +371,9 @@ extern "C" void idn_gpu_destroy(idn_gpu_ctx* ctx) {
     DevBuf* bufs[] = {&ctx->w_scratch, &ctx->w_paylen,  &ctx->w_sizes,   &ctx->w_chosen,     &ctx->w_tiles,  &ctx->w_sliceoff,
                       &ctx->w_readblock, &ctx->w_small, &ctx->w_crcpart, &ctx->w_crclen,     &ctx->w_index,  &ctx->w_blk,
                       &ctx->w_lanefirst, &ctx->w_laneoff, &ctx->w_laneblock, &ctx->w_blkinfo, &ctx->w_nhdr,
+                      &ctx->f_text, &ctx->f_tilecnt, &ctx->f_tilebase, &ctx->f_linestart, &ctx->f_linefn, &ctx->f_linestate, &ctx->f_tilefn,
+                      &ctx->f_tilestate, &ctx->f_recscan, &ctx->f_title, &ctx->f_namelo, &ctx->f_namelen, &ctx->f_readlen, &ctx->f_readoff,
+                      &ctx->f_nameoff, &ctx->f_names, &ctx->f_acids, &ctx->f_quals, &ctx->f_err, &ctx->f_fmtoff, &ctx->f_fmttext,
                       &ctx->s_acids,   &ctx->s_quals,   &ctx->s_readoff, &ctx->s_blockfirst, &ctx->s_prefix, &ctx->s_names,
                       &ctx->s_nameoff, &ctx->s_out,     &ctx->s_blockoff, &ctx->s_crc,       &ctx->s_stats,  &ctx->s_sizes,
                       &ctx->s_blocks,  &ctx->s_blocklen, &ctx->s_aout,    &ctx->s_qout,    &ctx->s_offout,     &ctx->s_status, &ctx->s_idx};
@@ -1641,5 +1649,221 @@ extern "C" int32_t idn_gpu_profile_read(idn_gpu_ctx* ctx, char* buf, uint64_t ca
     ctx->prof_used = 0;
     if (out.size() + 1 > cap) return fail(ctx, IDN_E_NOSPACE, "profile text needs %zu bytes", out.size() + 1);
     memcpy(buf, out.c_str(), out.size() + 1);
+    return IDN_OK;
+}
+
+// ======================================================================================================
+// FASTQ text <-> symbol arrays on the device
+// ======================================================================================================
+static const char* fastq_err_name(uint32_t e) {
+    switch (e) {
+        case kFqInvalidFormat: return "invalid format (title without '@' or separator line without '+')";
+        case kFqInvalidAcid: return "invalid acid";
+        case kFqInvalidQualityScore: return "invalid quality score";
+        case kFqLengthMismatch: return "acid and quality score lengths differ";
+        case kFqEof: return "end of input inside a record";
+        default: return "ok";
+    }
+}
+
+extern "C" int32_t idn_gpu_fastq_parse_dev(idn_gpu_ctx* ctx, const uint8_t* text, uint64_t n, idn_fastq_info* info, void* stream) {
+    if (!ctx || !info || (!text && n)) return fail(ctx, IDN_E_INVALID_ARG, "NULL argument");
+    CU(cudaSetDevice(ctx->device));
+    cudaStream_t st = as_stream(stream);
+    PROF_BEGIN();
+    memset(info, 0, sizeof *info);
+    ctx->f_info = *info;
+    const uint64_t n_tiles = (n + kFqTile - 1) / kFqTile;
+    CU(ctx->f_tilecnt.ensure((n_tiles + 1) * 8));
+    CU(ctx->f_tilebase.ensure((n_tiles + 2) * 8));
+    CU(ctx->f_err.ensure(16));
+    unsigned long long* tile_cnt = ctx->f_tilecnt.as<unsigned long long>();
+    unsigned long long* tile_base = ctx->f_tilebase.as<unsigned long long>();
+    unsigned long long* first_err = ctx->f_err.as<unsigned long long>();
+    CU(cudaMemsetAsync(first_err, 0xff, 8, st));
+    uint64_t n_newlines = 0;
+    uint8_t last = '\n';
+    if (n) {
+        fq_count_kernel<<<(unsigned)n_tiles, 256, 0, st>>>(text, n, tile_cnt);
+        LAUNCHED("fq_count");
+        int32_t rc = scan_u64(ctx, TileCntFn{tile_cnt}, n_tiles, tile_base, st);
+        if (rc) return rc;
+        CU(cudaMemcpyAsync(&n_newlines, tile_base + n_tiles, 8, cudaMemcpyDeviceToHost, st));
+        CU(cudaMemcpyAsync(&last, text + n - 1, 1, cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+    }
+    const uint64_t n_lines = n_newlines + (n > 0 && last != '\n' ? 1 : 0);
+    info->n_lines = n_lines;
+    CU(ctx->f_linestart.ensure((n_newlines + 2) * 8));
+    unsigned long long* line_start = ctx->f_linestart.as<unsigned long long>();
+    uint64_t n_reads = 0;
+    if (n_lines) {
+        fq_scatter_kernel<<<(unsigned)n_tiles, 256, 0, st>>>(text, n, tile_base, line_start);
+        LAUNCHED("fq_scatter");
+        const uint64_t f_tiles = (n_lines + kFstTile - 1) / kFstTile;
+        CU(ctx->f_linefn.ensure(n_lines + 16));
+        CU(ctx->f_linestate.ensure(n_lines + 16));
+        CU(ctx->f_tilefn.ensure(f_tiles + 16));
+        CU(ctx->f_tilestate.ensure(f_tiles + 16));
+        CU(ctx->f_recscan.ensure((n_lines + 2) * 8));
+        uint8_t* line_fn = ctx->f_linefn.as<uint8_t>();
+        uint8_t* line_state = ctx->f_linestate.as<uint8_t>();
+        fst_reduce_kernel<<<(unsigned)f_tiles, 256, 0, st>>>(text, n, line_start, n_lines, n_newlines, line_fn, ctx->f_tilefn.as<uint8_t>());
+        LAUNCHED("fst_reduce");
+        fst_tiles_kernel<<<1, 256, 0, st>>>(ctx->f_tilefn.as<uint8_t>(), f_tiles, ctx->f_tilestate.as<uint8_t>());
+        LAUNCHED("fst_tiles");
+        fst_apply_kernel<<<(unsigned)f_tiles, 256, 0, st>>>(line_fn, n_lines, ctx->f_tilestate.as<uint8_t>(), line_state);
+        LAUNCHED("fst_apply");
+        TitleFlag tf{line_state, line_fn};
+        unsigned long long* rec_scan = ctx->f_recscan.as<unsigned long long>();
+        int32_t rc = scan_u64(ctx, tf, n_lines, rec_scan, st);
+        if (rc) return rc;
+        CU(cudaMemcpyAsync(&n_reads, rec_scan + n_lines, 8, cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+        CU(ctx->f_title.ensure((n_reads + 1) * 8));
+        if (n_reads) {
+            fq_titles_kernel<<<(unsigned)((n_lines + 255) / 256), 256, 0, st>>>(tf, n_lines, rec_scan, ctx->f_title.as<unsigned long long>());
+            LAUNCHED("fq_titles");
+        }
+    }
+    info->n_reads = n_reads;
+    CU(ctx->f_namelo.ensure((n_reads + 1) * 8));
+    CU(ctx->f_namelen.ensure((n_reads + 1) * 4));
+    CU(ctx->f_readlen.ensure((n_reads + 1) * 4));
+    CU(ctx->f_readoff.ensure((n_reads + 2) * 8));
+    CU(ctx->f_nameoff.ensure((n_reads + 2) * 8));
+    FastqView V{text, n, line_start, n_lines, n_newlines, ctx->f_title.as<unsigned long long>(), n_reads};
+    unsigned long long* read_off = ctx->f_readoff.as<unsigned long long>();
+    unsigned long long* name_off = ctx->f_nameoff.as<unsigned long long>();
+    if (n_reads) {
+        fq_lengths_kernel<<<(unsigned)((n_reads + 127) / 128), 128, 0, st>>>(V, ctx->f_namelo.as<unsigned long long>(),
+                                                                           ctx->f_namelen.as<uint32_t>(), ctx->f_readlen.as<uint32_t>(),
+                                                                           first_err);
+        LAUNCHED("fq_lengths");
+    }
+    int32_t rc = scan_u64(ctx, U32Fn{ctx->f_readlen.as<uint32_t>()}, n_reads, read_off, st);
+    if (rc) return rc;
+    rc = scan_u64(ctx, U32Fn{ctx->f_namelen.as<uint32_t>()}, n_reads, name_off, st);
+    if (rc) return rc;
+    unsigned long long tot[2] = {0, 0}, ferr = ~0ull;
+    CU(cudaMemcpyAsync(&tot[0], read_off + n_reads, 8, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(&tot[1], name_off + n_reads, 8, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(&ferr, first_err, 8, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    info->n_symbols = tot[0];
+    info->n_name_bytes = tot[1];
+    if (ferr == ~0ull && n_reads) {
+        CU(ctx->f_names.ensure(tot[1] + 16));
+        CU(ctx->f_acids.ensure(tot[0] + 16));
+        CU(ctx->f_quals.ensure(tot[0] + 16));
+        fq_convert_kernel<<<(unsigned)((n_reads + 127) / 128), 128, 0, st>>>(V, ctx->f_namelo.as<unsigned long long>(), name_off, read_off,
+                                                                           ctx->f_names.as<uint8_t>(), ctx->f_acids.as<uint8_t>(),
+                                                                           ctx->f_quals.as<uint8_t>(), first_err);
+        LAUNCHED("fq_convert");
+        CU(cudaMemcpyAsync(&ferr, first_err, 8, cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+    }
+    if (ferr != ~0ull) {
+        info->error_kind = (int32_t)(ferr & 0xff);
+        info->bad_record = ferr >> 8;
+        ctx->f_info = *info;
+        return fail(ctx, IDN_E_SERIALIZE, "FASTQ record %llu: %s", (unsigned long long)info->bad_record, fastq_err_name((uint32_t)(ferr & 0xff)));
+    }
+    ctx->f_info = *info;
+    return IDN_OK;
+}
+
+extern "C" int32_t idn_gpu_fastq_parse(idn_gpu_ctx* ctx, const uint8_t* text, uint64_t n, idn_fastq_info* info) {
+    if (!ctx || !info || (!text && n)) return fail(ctx, IDN_E_INVALID_ARG, "NULL argument");
+    CU(cudaSetDevice(ctx->device));
+    CU(ctx->f_text.ensure(n + 16));
+    if (n) CU(cudaMemcpyAsync(ctx->f_text.p, text, n, cudaMemcpyHostToDevice, ctx->stream));
+    return idn_gpu_fastq_parse_dev(ctx, ctx->f_text.as<uint8_t>(), n, info, ctx->stream);
+}
+
+extern "C" int32_t idn_gpu_fastq_batch_dev(idn_gpu_ctx* ctx, idn_batch* out) {
+    if (!ctx || !out) return fail(ctx, IDN_E_INVALID_ARG, "NULL argument");
+    memset(out, 0, sizeof *out);
+    out->n_reads = ctx->f_info.n_reads;
+    out->n_symbols = ctx->f_info.n_symbols;
+    out->acids = ctx->f_acids.as<uint8_t>();
+    out->quals = ctx->f_quals.as<uint8_t>();
+    out->read_off = ctx->f_readoff.as<uint64_t>();
+    out->names = ctx->f_names.as<uint8_t>();
+    out->name_off = ctx->f_nameoff.as<uint64_t>();
+    return IDN_OK;
+}
+
+extern "C" int32_t idn_gpu_fastq_fetch(idn_gpu_ctx* ctx, uint8_t* acids, uint8_t* quals, uint64_t* read_off, uint8_t* names,
+                                       uint64_t* name_off) {
+    if (!ctx) return IDN_E_INVALID_ARG;
+    CU(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    const idn_fastq_info& f = ctx->f_info;
+    if (f.error_kind) return fail(ctx, IDN_E_INVALID_STATE, "the last parse failed");
+    if (acids && f.n_symbols) CU(cudaMemcpyAsync(acids, ctx->f_acids.p, f.n_symbols, cudaMemcpyDeviceToHost, st));
+    if (quals && f.n_symbols) CU(cudaMemcpyAsync(quals, ctx->f_quals.p, f.n_symbols, cudaMemcpyDeviceToHost, st));
+    if (read_off) CU(cudaMemcpyAsync(read_off, ctx->f_readoff.p, (f.n_reads + 1) * 8, cudaMemcpyDeviceToHost, st));
+    if (names && f.n_name_bytes) CU(cudaMemcpyAsync(names, ctx->f_names.p, f.n_name_bytes, cudaMemcpyDeviceToHost, st));
+    if (name_off) CU(cudaMemcpyAsync(name_off, ctx->f_nameoff.p, (f.n_reads + 1) * 8, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    return IDN_OK;
+}
+
+extern "C" int32_t idn_gpu_fastq_format_dev(idn_gpu_ctx* ctx, const idn_batch* batch, int32_t title_with_separator, uint8_t* text,
+                                            uint64_t cap, uint64_t* n_out_dev, void* stream) {
+    if (!ctx) return IDN_E_INVALID_ARG;
+    int32_t rc = check_batch(ctx, batch);
+    if (rc) return rc;
+    if (!n_out_dev || (!text && cap)) return fail(ctx, IDN_E_INVALID_ARG, "NULL argument");
+    CU(cudaSetDevice(ctx->device));
+    cudaStream_t st = as_stream(stream);
+    PROF_BEGIN();
+    const uint64_t R = batch->n_reads;
+    CU(ctx->f_fmtoff.ensure((R + 2) * 8));
+    CU(ctx->f_err.ensure(16));
+    unsigned long long* off = ctx->f_fmtoff.as<unsigned long long>();
+    FormatSize fs{batch->read_off, batch->name_off, title_with_separator};
+    rc = scan_u64(ctx, fs, R, off, st);
+    if (rc) return rc;
+    CU(cudaMemsetAsync(ctx->f_err.p, 0, 8, st));
+    if (R) {
+        fq_format_kernel<<<(unsigned)((R + 127) / 128), 128, 0, st>>>(batch->acids, batch->quals, batch->read_off, batch->names,
+                                                                    batch->name_off, R, title_with_separator, off, text, cap,
+                                                                    ctx->f_err.as<uint32_t>());
+        LAUNCHED("fq_format");
+    }
+    CU(cudaMemcpyAsync(n_out_dev, off + R, 8, cudaMemcpyDeviceToDevice, st));
+    return IDN_OK;
+}
+
+extern "C" int32_t idn_gpu_fastq_format(idn_gpu_ctx* ctx, const idn_batch* b, int32_t title_with_separator, uint8_t* text, uint64_t cap,
+                                        uint64_t* n_out) {
+    if (!ctx || !n_out) return IDN_E_INVALID_ARG;
+    int32_t rc = check_host_batch(ctx, b, false);
+    if (rc) return rc;
+    CU(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    idn_batch h = *b;
+    uint32_t bf[2] = {0, (uint32_t)b->n_reads};
+    h.block_first_read = bf;
+    h.n_blocks = 1;
+    idn_batch d;
+    rc = stage_batch(ctx, &h, &d, st);
+    if (rc) return rc;
+    CU(ctx->f_fmttext.ensure(cap + 16));
+    CU(ctx->s_stats.ensure(64));
+    rc = idn_gpu_fastq_format_dev(ctx, &d, title_with_separator, ctx->f_fmttext.as<uint8_t>(), cap, ctx->s_stats.as<uint64_t>(), st);
+    if (rc) return rc;
+    uint64_t need = 0;
+    uint32_t err = 0;
+    CU(cudaMemcpyAsync(&need, ctx->s_stats.p, 8, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(&err, ctx->f_err.p, 4, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    *n_out = need;
+    if (err & 1) return fail(ctx, IDN_E_INVALID_SYMBOL, "input holds an acid > 4 or a quality score > 93");
+    if (need > cap) return fail(ctx, IDN_E_NOSPACE, "FASTQ text needs %llu bytes, capacity is %llu", (unsigned long long)need, (unsigned long long)cap);
+    if (need) CU(cudaMemcpyAsync(text, ctx->f_fmttext.p, need, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
     return IDN_OK;
 }

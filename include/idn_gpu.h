@@ -201,6 +201,33 @@ int32_t idn_gpu_synth_reads_dev(idn_gpu_ctx *ctx, idn_model_t acid_model, idn_mo
                                 uint64_t first_read_index, uint64_t seed, uint32_t n_ppm, uint8_t *acids,
                                 uint8_t *quals, void *stream);
 
+/* ---- FASTQ text <-> symbol arrays on the device ("next" row f1: fastq/reader.rs:166-282, fastq/writer.rs:190-245) ----
+ * Same acceptance rules as FastqReader::read_sequence for '\n'-delimited input: blank lines are skipped where a title
+ * is expected, the title starts with '@' and is trimmed, acids are ATCGN, the separator line starts with '+', quality
+ * scores are '!'..'~', both symbol lines have one length.  A violation fails with IDN_E_SERIALIZE; error_kind names
+ * the FastqReaderError variant (1 InvalidFormat, 2 InvalidAcid, 3 InvalidQualityScore, 4 length mismatch, 5 end of
+ * input inside a record) and bad_record the first offending record. */
+typedef struct {
+    uint64_t n_reads, n_symbols, n_name_bytes, n_lines;
+    int32_t error_kind;
+    int32_t reserved;
+    uint64_t bad_record;
+} idn_fastq_info;
+/* parse: the SoA result stays in the ctx until the next parse; fetch copies it to host buffers sized from `info`,
+ * batch_dev exposes it as device pointers for the *_dev entry points (block_first_read is the caller's to add) */
+int32_t idn_gpu_fastq_parse(idn_gpu_ctx *ctx, const uint8_t *text, uint64_t n, idn_fastq_info *info);
+int32_t idn_gpu_fastq_parse_dev(idn_gpu_ctx *ctx, const uint8_t *text /* device */, uint64_t n, idn_fastq_info *info,
+                                void *stream);
+int32_t idn_gpu_fastq_fetch(idn_gpu_ctx *ctx, uint8_t *acids, uint8_t *quals, uint64_t *read_off, uint8_t *names,
+                            uint64_t *name_off);
+int32_t idn_gpu_fastq_batch_dev(idn_gpu_ctx *ctx, idn_batch *out);
+/* format: "@name\nACGT\n+[name]\n!!!!\n" per read (FastqWriterParams::output_title_with_separator = the flag) */
+int32_t idn_gpu_fastq_format(idn_gpu_ctx *ctx, const idn_batch *batch, int32_t title_with_separator, uint8_t *text,
+                             uint64_t cap, uint64_t *n_out);
+int32_t idn_gpu_fastq_format_dev(idn_gpu_ctx *ctx, const idn_batch *batch /* device pointers */,
+                                 int32_t title_with_separator, uint8_t *text, uint64_t cap, uint64_t *n_out_dev,
+                                 void *stream);
+
 /* ---- per-kernel timing (CUDA events on the launching stream; what bench.py's roofline line is made of) ----
  * idn_gpu_profile(ctx, 1) starts recording an event after every kernel launch of the *_dev entry points;
  * idn_gpu_profile_read synchronises the device and writes one text line per kernel, "name launches total_ms",
