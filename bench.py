@@ -227,6 +227,24 @@ def run_gpu(args, w: dict):
     am = host.Model.load(MODELS / (w["acid"] + ".msgpack"))
     qm = host.Model.load(MODELS / (w["q"] + ".msgpack"))
     handles = np.asarray([am.upload(ctx), qm.upload(ctx)], dtype=np.int32)
+    synth_pair = (int(handles[0]), int(handles[1]))
+    model_names = [w["acid"], w["q"]]
+    if args.select > 1:
+        # per-read model selection among K acid + K q-score models (quality-7 semantics, BASELINE.json configs[3]):
+        # the workload's own pair plus the first K-1 other bundled models of each type, acid ids first
+        pool = {0: [], 1: []}
+        for pth in sorted(MODELS.glob("*.msgpack")):
+            if pth.stem in (w["acid"], w["q"]):
+                continue
+            m = host.Model.load(pth)
+            if len(pool[m.model_type]) < args.select - 1:
+                pool[m.model_type].append((pth.stem, m))
+        acid_set = [(w["acid"], am)] + pool[0]
+        q_set = [(w["q"], qm)] + pool[1]
+        hs = [int(handles[0])] + [m.upload(ctx) for _, m in pool[0]] + [int(handles[1])] + [m.upload(ctx) for _, m in pool[1]]
+        handles = np.asarray(hs, dtype=np.int32)
+        model_names = [n for n, _ in acid_set] + [n for n, _ in q_set]
+    n_handles = len(handles)
     stream = torch.cuda.current_stream()
     sp = C.c_void_p(stream.cuda_stream)
 
@@ -244,7 +262,7 @@ def run_gpu(args, w: dict):
     read_off_d = torch.from_numpy(read_off_h.view(np.int64)).to(dev)
     acids_d = torch.empty(S + 16, dtype=torch.uint8, device=dev)
     quals_d = torch.empty(S + 16, dtype=torch.uint8, device=dev)
-    ctx.check(L.idn_gpu_synth_reads_dev(ctx.h, int(handles[0]), int(handles[1]), read_off_d.data_ptr(), n_reads, first_index,
+    ctx.check(L.idn_gpu_synth_reads_dev(ctx.h, synth_pair[0], synth_pair[1], read_off_d.data_ptr(), n_reads, first_index,
                                         w["seed"], w["n_ppm"], acids_d.data_ptr(), quals_d.data_ptr(), sp))
     torch.cuda.synchronize()
 
@@ -284,7 +302,7 @@ def run_gpu(args, w: dict):
 
     def compress_all(mode):
         for c in chunks:
-            ctx.check(L.idn_gpu_compress_blocks_dev(ctx.h, C.byref(c.batch), mode, handles.ctypes.data, 2, 0, None,
+            ctx.check(L.idn_gpu_compress_blocks_dev(ctx.h, C.byref(c.batch), mode, handles.ctypes.data, n_handles, 0, None,
                                                     out_d.data_ptr() + c.out_base, c.out_cap, c.block_off.data_ptr(),
                                                     c.block_crc.data_ptr(), c.stats.data_ptr(), sp))
 
@@ -307,7 +325,7 @@ def run_gpu(args, w: dict):
         for c in chunks:
             ctx.check(L.idn_gpu_decompress_blocks_dev(ctx.h, out_d.data_ptr() + c.out_base, c.dec_off.data_ptr(),
                                                       c.dec_len.data_ptr(), c.block_crc.data_ptr(), c.n_blocks, sizes[id(c)],
-                                                      mode, handles.ctypes.data, 2, dec_a.data_ptr() + c.s0,
+                                                      mode, handles.ctypes.data, n_handles, dec_a.data_ptr() + c.s0,
                                                       dec_q.data_ptr() + c.s0, c.dec_read_off.data_ptr(), c.n_reads, c.n_syms,
                                                       c.dec_status.data_ptr(), sp))
 
@@ -379,9 +397,14 @@ def run_gpu(args, w: dict):
                                                                         m["out_bytes"], m["payload_bytes"], m["prof"])
     tc, td, t_total, verified = m["tc"], m["td"], m["t_total"], m["verified"]
 
+    # ---- row f1, timed separately: FASTQ text -> symbols (parse) and symbols -> text (format) on the device ----
+    fastq = None
+    if not args.no_fastq and rank == 0:
+        fastq = fastq_leg(args, w, capi, torch, ctx, sp, stream, acids_d, quals_d, read_off_h, min(n_reads, 4_000_000))
+
     # ---- e2e: the host-pointer C-ABI calls on pinned host buffers, several ctx in flight ----
     e2e = None
-    if not args.no_e2e:
+    if not args.no_e2e and args.select <= 1:
         e2e = run_e2e(args, w, capi, host, torch, local, chunks, acids_d, quals_d, read_off_h, block_first_h, sizes, dist, fq,
                       MODES[main_mode])
 
@@ -434,7 +457,9 @@ def run_gpu(args, w: dict):
                        "reads_per_gpu": n_reads, "symbols_per_gpu": S, "fastq_bytes_per_gpu": fq, "blocks_per_gpu": n_blocks,
                        "block_symbols": BLOCK_SYMBOLS, "chunk_blocks": cb, "names": "not stored (--no-identifiers protocol, "
                        "util/benchmark.py:161-179); their bytes count as FASTQ input", "l2": f"inputs {2 * S / 1e9:.1f} GB >> 126 MB L2, no flush needed",
-                       "model_selection": "explicit pair (1 acid + 1 q-score model), quality 7 semantics"},
+                       "model_selection": ("explicit pair (1 acid + 1 q-score model), quality 7 semantics" if args.select <= 1 else
+                                           f"per-read greedy selection among {args.select}+{args.select} models, quality 7 semantics"),
+                       "models": model_names},
             "compress_GBps": fq * args.steps * world / tc_max / 1e9, "decompress_GBps": fq * args.steps * world / td_max / 1e9,
             "container_bytes_per_read": out_bytes / n_reads, "bits_per_base": 8 * payload_bytes / S, "verified_round_trip": verified,
             "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "wall_s_timed": t_wall,
@@ -445,6 +470,8 @@ def run_gpu(args, w: dict):
                            "threads": e2e["threads"], "chunk_blocks": args.e2e_chunk_blocks, "compress_GBps": e2e["cGBps"], "decompress_GBps": e2e["dGBps"], "sample": e2e["sample"]}
         if cpu:
             line["cpu_baseline"] = cpu
+        if fastq:
+            line["fastq_text"] = fastq
         if other:
             line["other_mode"] = {"mode": other_mode, "compress_GBps": fq * 2 / other["tc"] / 1e9, "decompress_GBps": fq * 2 / other["td"] / 1e9,
                                   "container_bytes_per_read": other["out_bytes"] / n_reads, "verified_round_trip": other["verified"],
@@ -455,6 +482,52 @@ def run_gpu(args, w: dict):
         dist.barrier()
         dist.destroy_process_group()
     ctx.close()
+
+
+def fastq_leg(args, w, capi, torch, ctx, sp, stream, acids_d, quals_d, read_off_h, n):
+    """FASTQ text of the first n reads is produced on the device (format), parsed back (parse) and compared."""
+    L = ctx.L
+    dev = acids_d.device
+    S = int(read_off_h[n])
+    ro_d = torch.from_numpy(read_off_h[:n + 1].view(np.int64)).to(dev)
+    # fixed-width synthetic titles "r000000000123 1:N:0"
+    idx = torch.arange(n, dtype=torch.int64, device=dev)
+    digits = torch.stack([(idx // 10 ** k) % 10 for k in range(11, -1, -1)], dim=1).to(torch.uint8) + 48
+    tail = torch.tensor(list(b" 1:N:0"), dtype=torch.uint8, device=dev).expand(n, -1)
+    head = torch.full((n, 1), ord("r"), dtype=torch.uint8, device=dev)
+    names_d = torch.cat([head, digits, tail], dim=1).contiguous().view(-1)
+    nlen = 1 + 12 + 6
+    no_d = (torch.arange(n + 1, dtype=torch.int64, device=dev) * nlen).contiguous()
+    b = capi.Batch()
+    b.n_reads, b.n_symbols, b.n_blocks = n, S, 0
+    b.acids, b.quals, b.read_off = acids_d.data_ptr(), quals_d.data_ptr(), ro_d.data_ptr()
+    b.names, b.name_off = names_d.data_ptr(), no_d.data_ptr()
+    cap = 2 * S + n * (6 + nlen) + 64
+    text_d = torch.empty(cap, dtype=torch.uint8, device=dev)
+    n_out = torch.zeros(1, dtype=torch.int64, device=dev)
+    info = capi.FastqInfo()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+    for it in range(3):  # two warm-ups, the third pass is timed
+        ev[0].record(stream)
+        ctx.check(L.idn_gpu_fastq_format_dev(ctx.h, C.byref(b), 0, text_d.data_ptr(), cap, n_out.data_ptr(), sp))
+        ev[1].record(stream)
+        torch.cuda.synchronize()
+        nbytes = int(n_out.item())
+        ev[2].record(stream)
+        ctx.check(L.idn_gpu_fastq_parse_dev(ctx.h, text_d.data_ptr(), nbytes, C.byref(info), sp))
+        ev[3].record(stream)
+        torch.cuda.synchronize()
+    # compare on the host (outside the timed passes)
+    chk_a = np.zeros(max(S, 1), dtype=np.uint8)
+    chk_q = np.zeros(max(S, 1), dtype=np.uint8)
+    ctx.check(L.idn_gpu_fastq_fetch(ctx.h, chk_a.ctypes.data, chk_q.ctypes.data, None, None, None))
+    ok = bool(info.n_reads == n and info.n_symbols == S and np.array_equal(chk_a[:S], acids_d[:S].cpu().numpy()) and
+              np.array_equal(chk_q[:S], quals_d[:S].cpu().numpy()))
+    if not ok:
+        raise SystemExit("FASTQ text round trip mismatch")
+    return {"sample": f"first {n} reads, {nbytes / 1e9:.2f} GB of FASTQ text, device-resident, third of three passes",
+            "format_GBps": nbytes / (ev[0].elapsed_time(ev[1]) / 1e3) / 1e9, "parse_GBps": nbytes / (ev[2].elapsed_time(ev[3]) / 1e3) / 1e9,
+            "verified_round_trip": ok}
 
 
 def cpu_baseline(args, w: dict) -> dict:
@@ -633,6 +706,8 @@ def main():
     ap.add_argument("--cpu-blocks", type=int, default=0, help="blocks in the CPU sample (default 2 per core)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-fastq", action="store_true", help="skip the FASTQ text parse/format leg (row f1)")
+    ap.add_argument("--select", type=int, default=1, help="K > 1: per-read selection among K acid + K q-score models (device-resident leg only)")
     ap.add_argument("--mode", default="", choices=["", "compat", "native"], help="container format (default: the workload's)")
     ap.add_argument("--no-other-mode", action="store_true", help="skip the short run of the other container format")
     ap.add_argument("--e2e-threads", type=int, default=3)
