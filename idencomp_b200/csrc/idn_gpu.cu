@@ -560,6 +560,37 @@ static int32_t upload_small(idn_gpu_ctx* ctx, const SmallParams& sp, cudaStream_
     return IDN_OK;
 }
 
+// K2 over `n` models (slots ids[0..n)): packs of up to 8 models per launch, columns col0.. of the [reads][n_cols] matrix
+static int32_t launch_score(idn_gpu_ctx* ctx, const int32_t* ids, uint32_t n, const idn_batch* batch, uint32_t n_cols,
+                            uint32_t* sizes, uint32_t* err, cudaStream_t st) {
+    const uint64_t R = batch->n_reads;
+    const unsigned grid = (unsigned)((R + 127) / 128);
+    for (uint32_t k0 = 0; k0 < n;) {
+        uint32_t left = n - k0;
+        if (left > 4) {
+            ModelPack<8> P;
+            P.n = left < 8 ? left : 8;
+            for (uint32_t k = 0; k < 8; k++) P.m[k] = ctx->slots[ids[k0 + (k < P.n ? k : 0)]].dev;
+            score_multi_kernel<8><<<grid, 128, 0, st>>>(P, batch->acids, batch->quals, batch->read_off, R, n_cols, k0, sizes, err);
+            k0 += P.n;
+        } else if (left > 2) {
+            ModelPack<4> P;
+            P.n = left;
+            for (uint32_t k = 0; k < 4; k++) P.m[k] = ctx->slots[ids[k0 + (k < P.n ? k : 0)]].dev;
+            score_multi_kernel<4><<<grid, 128, 0, st>>>(P, batch->acids, batch->quals, batch->read_off, R, n_cols, k0, sizes, err);
+            k0 += P.n;
+        } else {
+            ModelPack<2> P;
+            P.n = left;
+            for (uint32_t k = 0; k < 2; k++) P.m[k] = ctx->slots[ids[k0 + (k < P.n ? k : 0)]].dev;
+            score_multi_kernel<2><<<grid, 128, 0, st>>>(P, batch->acids, batch->quals, batch->read_off, R, n_cols, k0, sizes, err);
+            k0 += P.n;
+        }
+        LAUNCHED("score");
+    }
+    return IDN_OK;
+}
+
 extern "C" int32_t idn_gpu_score_dev(idn_gpu_ctx* ctx, const idn_batch* batch, const idn_model_t* models,
                                      uint32_t n_models, uint32_t* sizes, void* stream) {
     if (!ctx) return IDN_E_INVALID_ARG;
@@ -578,12 +609,7 @@ extern "C" int32_t idn_gpu_score_dev(idn_gpu_ctx* ctx, const idn_batch* batch, c
     rc = upload_small(ctx, sp, st);
     if (rc) return rc;
     SmallParams* dsp = ctx->w_small.as<SmallParams>();
-    uint64_t threads = batch->n_reads * n_models;
-    score_kernel<<<(unsigned)((threads + 127) / 128), 128, 0, st>>>(ctx->d_models, dsp->score_ids, n_models, batch->acids,
-                                                                   batch->quals, batch->read_off, batch->n_reads, sizes,
-                                                                   &dsp->err);
-    LAUNCHED("score");
-    return IDN_OK;
+    return launch_score(ctx, sp.score_ids, n_models, batch, n_models, sizes, &dsp->err, st);
 }
 
 extern "C" int32_t idn_gpu_score(idn_gpu_ctx* ctx, const idn_batch* b, const idn_model_t* models, uint32_t n_models,
@@ -698,11 +724,8 @@ extern "C" int32_t idn_gpu_compress_blocks_dev(idn_gpu_ctx* ctx, const idn_batch
     if (R > 0) {
         if (n_score) {  // K2
             CU(ctx->w_sizes.ensure(R * n_score * 4));
-            uint64_t threads = R * n_score;
-            score_kernel<<<(unsigned)((threads + 127) / 128), 128, 0, st>>>(ctx->d_models, dsp->score_ids, n_score,
-                                                                           batch->acids, batch->quals, batch->read_off, R,
-                                                                           ctx->w_sizes.as<uint32_t>(), &dsp->err);
-            LAUNCHED("score");
+            rc = launch_score(ctx, sp.score_ids, n_score, batch, n_score, ctx->w_sizes.as<uint32_t>(), &dsp->err, st);
+            if (rc) return rc;
         }
         if (!fast && n_score == 0) {  // one candidate per type: no choice to make
             CU(cudaMemsetAsync(chosen, 0, 4 * R, st));
@@ -880,11 +903,8 @@ static int32_t compress_native_dev(idn_gpu_ctx* ctx, const idn_batch* batch, Sma
             CU(ctx->w_sizes.ensure(R * n_score * 4));
             CU(ctx->w_chosen.ensure(2 * lane_cap + 16));
             lane_choice = ctx->w_chosen.as<uint8_t>();
-            uint64_t threads = R * n_score;
-            score_kernel<<<(unsigned)((threads + 127) / 128), 128, 0, st>>>(ctx->d_models, dsp->score_ids, n_score, batch->acids,
-                                                                           batch->quals, batch->read_off, R,
-                                                                           ctx->w_sizes.as<uint32_t>(), &dsp->err);
-            LAUNCHED("score");
+            rc = launch_score(ctx, sp.score_ids, n_score, batch, n_score, ctx->w_sizes.as<uint32_t>(), &dsp->err, st);
+            if (rc) return rc;
             lane_choose_kernel<<<(unsigned)((2 * lane_cap + 127) / 128), 128, 0, st>>>(
                 ctx->w_sizes.as<uint32_t>(), n_score, dsp->cand_cols, dsp->n_cand, dsp->has_sizes, lane_first, n_lanes_dev,
                 lane_cap, lane_choice);

@@ -165,6 +165,78 @@ score_kernel(const ModelDev* __restrict__ models, const int32_t* __restrict__ mo
     if (bad) atomicOr(err, 1u);
 }
 
+// K2, several models at once: one thread per read walks the read ONCE and advances every candidate model per
+// position (symbols, the N/zero test and the position counter are shared; the M table-gather chains are independent,
+// which gives the memory system M requests in flight per thread).  The models travel by value in the kernel
+// parameter space, so their constants cost no registers.
+template <int M>
+struct ModelPack {
+    ModelDev m[M];
+    uint32_t n;
+};
+
+template <int M>
+__global__ void __launch_bounds__(128)
+score_multi_kernel(const ModelPack<M> P, const uint8_t* __restrict__ acids, const uint8_t* __restrict__ quals,
+                   const uint64_t* __restrict__ read_off, uint64_t n_reads, uint32_t n_cols, uint32_t col0,
+                   uint32_t* __restrict__ sizes, uint32_t* __restrict__ err) {
+    uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n_reads) return;
+    uint64_t off = read_off[r];
+    uint32_t len = (uint32_t)(read_off[r + 1] - off);
+    uint32_t pbmax = 0;
+#pragma unroll
+    for (int k = 0; k < M; k++)
+        if (k < (int)P.n) pbmax = max(pbmax, P.m[k].spec.pb);
+    PosFwd pf;
+    pf.init(len, pbmax);
+    GenFwd g[M];
+    uint32_t x[M], bytes[M];
+#pragma unroll
+    for (int k = 0; k < M; k++) {
+        g[k].init();
+        x[k] = kRansL;
+        bytes[k] = 0;
+    }
+    FwdReader ra, rq;
+    ra.init(acids);
+    rq.init(quals);
+    if (len) {
+        ra.prime(off);
+        rq.prime(off);
+    }
+    bool bad = false;
+#pragma unroll 1
+    for (uint32_t i = 0; i < len; i++) {
+        uint32_t a = ra.get(off + i), q = rq.get(off + i);
+        if (a > 4 || q > 93) {
+            bad = true;
+            a = a > 4 ? 0 : a;
+            q = q > 93 ? 0 : q;
+        }
+        const bool z = a * q == 0;
+        uint2 e[M];
+#pragma unroll
+        for (int k = 0; k < M; k++)
+            if (k < (int)P.n) {
+                const ModelDev& m = P.m[k];
+                uint32_t row = ctx_row(m, g[k].spec(m.spec, pf.pos, pbmax - m.spec.pb));
+                e[k] = __ldg(m.enc + (size_t)row * m.nsym + (m.type == 0 ? a : q));
+            }
+#pragma unroll
+        for (int k = 0; k < M; k++)
+            if (k < (int)P.n) {
+                rans_put_count(x[k], e[k], bytes[k]);
+                g[k].update(P.m[k].spec, a, q, z);
+            }
+        pf.advance();
+    }
+#pragma unroll
+    for (int k = 0; k < M; k++)
+        if (k < (int)P.n) sizes[r * n_cols + col0 + k] = bytes[k] + 4;
+    if (bad) atomicOr(err, 1u);
+}
+
 // ---------------------------------------------------------------------------------------------------
 // K3: greedy per-read model choice inside each block.  One warp per (block, model type).
 // The choice for read r depends on the model active after read r-1, so the warp composes per-chunk
