@@ -53,7 +53,7 @@ def build_host(force: bool = False) -> Path:
     deps = srcs + list(host.glob("*.hpp")) + [ROOT / "include" / "idn_host.h", ROOT / "include" / "idn_gpu.h"]
     if force or _stale(out, deps):
         cxx = os.environ.get("CXX") or shutil.which("g++") or "g++"
-        cmd = [cxx, *GXX_FLAGS, "-o", str(out), *map(str, srcs), f"-L{PKG}", "-lidn_gpu", "-lz",
+        cmd = [cxx, *GXX_FLAGS, "-o", str(out), *map(str, srcs), f"-L{PKG}", "-lidn_gpu", "-lz", "-ldl",
                "-Wl,-rpath,$ORIGIN"]
         subprocess.run(cmd, check=True)
     return out

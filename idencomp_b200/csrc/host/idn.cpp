@@ -1,6 +1,7 @@
 // idn.cpp -- see idn.hpp.  Host orchestration only: every symbol goes through the C-ABI of libidn_gpu.so.
 #include "idn.hpp"
 
+#include <dlfcn.h>
 #include <zlib.h>
 
 #include <algorithm>
@@ -60,6 +61,69 @@ std::vector<uint8_t> inflate_raw(const uint8_t* src, size_t n) {
     if (rc != Z_STREAM_END) throw IdnError(IDN_E_SERIALIZE, "identifiers slice does not inflate");
     return out;
 }
+
+// Brotli for the identifiers of quality 8-9 (compressor_block.rs:160-170: buffer 4096, quality 11, lgwin 20).  The image
+// ships libbrotlienc/libbrotlidec without headers, so the four entry points are bound at run time; when the libraries
+// are absent the quality 8-9 identifier path fails with Unsupported.  The byte stream of the C encoder differs from the
+// Rust crate's (as zlib's does from miniz_oxide's): this slice is compared after decompression.
+struct Brotli {
+    using EncFn = int (*)(int quality, int lgwin, int mode, size_t in_size, const uint8_t* in, size_t* out_size, uint8_t* out);
+    using BoundFn = size_t (*)(size_t);
+    using CreateFn = void* (*)(void*, void*, void*);
+    using StreamFn = int (*)(void* state, size_t* avail_in, const uint8_t** next_in, size_t* avail_out, uint8_t** next_out, size_t* total_out);
+    using DestroyFn = void (*)(void*);
+    EncFn enc = nullptr;
+    BoundFn bound = nullptr;
+    CreateFn create = nullptr;
+    StreamFn stream = nullptr;
+    DestroyFn destroy = nullptr;
+    Brotli() {
+        void* e = dlopen("libbrotlienc.so.1", RTLD_NOW | RTLD_LOCAL);
+        void* d = dlopen("libbrotlidec.so.1", RTLD_NOW | RTLD_LOCAL);
+        if (e) {
+            enc = (EncFn)dlsym(e, "BrotliEncoderCompress");
+            bound = (BoundFn)dlsym(e, "BrotliEncoderMaxCompressedSize");
+        }
+        if (d) {
+            create = (CreateFn)dlsym(d, "BrotliDecoderCreateInstance");
+            stream = (StreamFn)dlsym(d, "BrotliDecoderDecompressStream");
+            destroy = (DestroyFn)dlsym(d, "BrotliDecoderDestroyInstance");
+        }
+    }
+    static Brotli& get() {
+        static Brotli b;
+        return b;
+    }
+    std::vector<uint8_t> compress(const uint8_t* src, size_t n) const {
+        if (!enc || !bound) throw IdnError(IDN_E_UNSUPPORTED, "Brotli identifier slices (quality 8-9) need libbrotlienc.so.1");
+        size_t cap = bound(n) + 64;
+        std::vector<uint8_t> out(cap);
+        if (!enc(11, 20, 0, n, src, &cap, out.data())) throw IdnError(IDN_E_IO, "Brotli compression failed");
+        out.resize(cap);
+        return out;
+    }
+    std::vector<uint8_t> decompress(const uint8_t* src, size_t n) const {
+        if (!create || !stream || !destroy) throw IdnError(IDN_E_UNSUPPORTED, "Brotli identifier slices need libbrotlidec.so.1");
+        void* st = create(nullptr, nullptr, nullptr);
+        if (!st) throw IdnError(IDN_E_IO, "BrotliDecoderCreateInstance failed");
+        std::vector<uint8_t> out(std::max<size_t>(65536, 8 * n));
+        size_t avail_in = n, total = 0;
+        const uint8_t* next_in = src;
+        int rc;
+        for (;;) {
+            size_t avail_out = out.size() - total;
+            uint8_t* next_out = out.data() + total;
+            rc = stream(st, &avail_in, &next_in, &avail_out, &next_out, nullptr);
+            total = out.size() - avail_out;
+            if (rc != 3) break;  // BROTLI_DECODER_RESULT_NEEDS_MORE_OUTPUT
+            out.resize(out.size() * 2);
+        }
+        destroy(st);
+        if (rc != 1) throw IdnError(IDN_E_SERIALIZE, "identifiers slice is not a valid Brotli stream");  // 1 = SUCCESS
+        out.resize(total);
+        return out;
+    }
+};
 
 // ---- Clustering (clustering.rs:21-118).  Xoshiro256PlusPlus::seed_from_u64(404) + rand 0.8.5 choose_multiple restated
 // from the published algorithms of rand_xoshiro 0.6.0 / rand 0.8.5 (SplitMix64 seeding, Floyd's sampling for small
@@ -326,18 +390,20 @@ void IdnCompressor::flush_batch() {
     std::vector<std::vector<uint8_t>> name_slices(n_blocks);
     std::vector<uint32_t> prefix(n_blocks, 0);
     if (params_.include_identifiers) {
-        if (params_.quality >= 8) throw IdnError(IDN_E_UNSUPPORTED, "Brotli identifier slices (quality 8-9) are not available in this build");
+        const bool brotli = params_.quality >= 8;  // BROTLI_THRESHOLD (compressor_block.rs:146)
+        if (brotli && !Brotli::get().enc)  // fail early, on the caller's thread, when the library is missing
+            throw IdnError(IDN_E_UNSUPPORTED, "Brotli identifier slices (quality 8-9) need libbrotlienc.so.1");
         auto one = [&](uint32_t b) {
             std::vector<uint8_t> joined;
             for (uint32_t r = block_first_[b]; r < block_first_[b + 1]; r++) {
                 if (r > block_first_[b]) joined.push_back('\n');
                 joined.insert(joined.end(), names_.begin() + name_off_[r], names_.begin() + name_off_[r + 1]);
             }
-            std::vector<uint8_t> z = deflate_raw(joined.data(), joined.size());
+            std::vector<uint8_t> z = brotli ? Brotli::get().compress(joined.data(), joined.size()) : deflate_raw(joined.data(), joined.size());
             std::vector<uint8_t> s;
             s.push_back(0x00);  // IdnSliceHeader::Identifiers (data.rs:46-47)
             put_u32be(s, (uint32_t)z.size());
-            s.push_back(1);     // IdnIdentifierCompression::Deflate (data.rs:57-61)
+            s.push_back(brotli ? 0 : 1);  // IdnIdentifierCompression::{Brotli = 0, Deflate = 1} (data.rs:57-61)
             s.insert(s.end(), z.begin(), z.end());
             name_slices[b] = std::move(s);
         };
@@ -490,8 +556,8 @@ bool IdnDecompressor::read_batch() {
             uint32_t n = get_u32be(p + pos + 1);
             uint8_t comp = p[pos + 5];
             if (n > len[b] - pos - 6) throw IdnError(IDN_E_SERIALIZE, "truncated identifiers slice");
-            if (comp != 1) throw IdnError(IDN_E_UNSUPPORTED, "Brotli identifier slices are not available in this build");
-            std::vector<uint8_t> text = inflate_raw(p + pos + 6, n);
+            if (comp > 1) throw IdnError(IDN_E_SERIALIZE, "unknown identifier compression");
+            std::vector<uint8_t> text = comp == 0 ? Brotli::get().decompress(p + pos + 6, n) : inflate_raw(p + pos + 6, n);
             any_names = true;
             // split at '\n': one identifier per sequence, in order (identifiers_as_lines)
             size_t s = 0;

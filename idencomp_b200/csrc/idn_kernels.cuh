@@ -117,54 +117,8 @@ struct FwdWriter {
 };
 
 // ---------------------------------------------------------------------------------------------------
-// K2: forward single-state scorer.  One thread per (read, model).
+// K2: forward single-state scorer   ModelTester::compute_size, idn/model_chooser.rs:215-243
 // ---------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128)
-score_kernel(const ModelDev* __restrict__ models, const int32_t* __restrict__ model_ids, uint32_t n_models,
-             const uint8_t* __restrict__ acids, const uint8_t* __restrict__ quals,
-             const uint64_t* __restrict__ read_off, uint64_t n_reads, uint32_t* __restrict__ sizes,
-             uint32_t* __restrict__ err) {
-    uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    uint64_t r = t / n_models;
-    if (r >= n_reads) return;
-    uint32_t mi = (uint32_t)(t - r * n_models);
-    const ModelDev& m = models[model_ids[mi]];
-    const SpecDev sp = m.spec;
-    uint64_t off = read_off[r];
-    uint32_t len = (uint32_t)(read_off[r + 1] - off);
-    GenFwd g;
-    g.init();
-    PosFwd pf;
-    pf.init(len, sp.pb);
-    FwdReader ra, rq;
-    ra.init(acids);
-    rq.init(quals);
-    if (len) {
-        ra.prime(off);
-        rq.prime(off);
-    }
-    uint32_t x = kRansL, bytes = 0;
-    bool bad = false;
-    const bool is_acid = m.type == 0;
-#pragma unroll 1
-    for (uint32_t i = 0; i < len; i++) {
-        uint32_t a = ra.get(off + i), q = rq.get(off + i);
-        if (a > 4 || q > 93) {
-            bad = true;
-            a = a > 4 ? 0 : a;
-            q = q > 93 ? 0 : q;
-        }
-        uint32_t row = ctx_row(m, g.spec(sp, pf.pos, 0));
-        uint32_t sym = is_acid ? a : q;
-        uint2 e = __ldg(m.enc + (size_t)row * m.nsym + sym);
-        rans_put_count(x, e, bytes);
-        g.update(sp, a, q, a * q == 0);
-        pf.advance();
-    }
-    sizes[r * n_models + mi] = bytes + 4;
-    if (bad) atomicOr(err, 1u);
-}
-
 // K2, several models at once: one thread per read walks the read ONCE and advances every candidate model per
 // position (symbols, the N/zero test and the position counter are shared; the M table-gather chains are independent,
 // which gives the memory system M requests in flight per thread).  The models travel by value in the kernel

@@ -93,16 +93,12 @@ def test_round_trip_multiple_models(H, prefer_provider):
     assert len(c.retained_models()) == 3
 
 
-@pytest.mark.parametrize("quality", range(1, 8))  # 8-9 switch the identifiers to Brotli, which this build does not carry
+@pytest.mark.parametrize("quality", range(1, 10))  # 8-9 switch the identifiers slice to Brotli (compressor_block.rs:146-163)
 def test_round_trip_all_quals(H, prefer_provider, quality):
-    round_trip(H, prefer_provider, [PREFER_A, PREFER_C], quality=quality)
-
-
-def test_quality_8_identifiers_need_brotli(H, prefer_provider):
-    with pytest.raises(H.HostError) as e:
-        round_trip(H, prefer_provider, [PREFER_A], quality=8)
-    assert e.value.kind == "Unsupported"
-    round_trip(H, prefer_provider, [PREFER_A], [(b"", PREFER_A[1], PREFER_A[2])], quality=9, include_identifiers=False)
+    idn, _ = round_trip(H, prefer_provider, [PREFER_A, PREFER_C], quality=quality)
+    n_ids = idn[11]
+    pos = 9 + 3 + 32 * n_ids + 8  # first block's first slice
+    assert idn[pos] == 0 and idn[pos + 5] == (0 if quality >= 8 else 1)  # IdnIdentifierCompression::{Brotli, Deflate}
 
 
 # ---- tests/simple_ctx.rs -----------------------------------------------------------------------------------------

@@ -37,12 +37,13 @@ with tempfile.TemporaryDirectory() as td:
     cub = next(Path(td).glob("*.cubin"))
     dis = subprocess.run(["nvdisasm", "-g", "-c", str(cub)], capture_output=True, text=True).stdout
 
-fn = re.sub(r"\(.*", "", kname).split("::")[-1]
+fn = re.sub(r"<.*", "", re.sub(r"\(.*", "", kname)).split("::")[-1]
+tmpl = "ILb1E" if "<(bool)1>" in kname else ("ILb0E" if "<(bool)0>" in kname else "")
 lines = {}
 cur, infn = None, False
 for ln in dis.splitlines():
     if ln.startswith("//---") and ".text." in ln:
-        infn = fn in ln
+        infn = fn in ln and tmpl in ln
         continue
     if not infn:
         continue
@@ -69,7 +70,7 @@ print(f"{kname[:80]}: {len(sass)} SASS instrs, {tot_i} warp instrs executed, {to
 srcs = {}
 for (f, l), (n, st, k, thr) in sorted(agg.items(), key=lambda kv: -kv[1][0])[:top]:
     if f not in srcs:
-        cand = list(Path(__file__).resolve().parent.parent.rglob(f))
+        cand = [c for c in Path(__file__).resolve().parent.parent.rglob(f) if c.is_file()] if f not in ('?', '') else []
         srcs[f] = cand[0].read_text().splitlines() if cand else []
     text = srcs[f][l - 1].strip()[:90] if 0 < l <= len(srcs[f]) else ""
     print(f"{n / max(tot_i, 1):6.3f} instr {st / max(tot_s, 1):6.3f} stall {k:4d} sass  {f}:{l:<5d} {text}")
