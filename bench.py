@@ -299,6 +299,8 @@ def run_gpu(args, w: dict):
     dec_q = torch.empty(S + 16, dtype=torch.uint8, device=dev)
 
     MODES = {"compat": capi.MODE_COMPAT, "native": capi.MODE_NATIVE}
+    if args.lane_symbols:
+        ctx.set_lane_symbols(args.lane_symbols)
 
     def compress_all(mode):
         for c in chunks:
@@ -710,6 +712,7 @@ def main():
     ap.add_argument("--select", type=int, default=1, help="K > 1: per-read selection among K acid + K q-score models (device-resident leg only)")
     ap.add_argument("--mode", default="", choices=["", "compat", "native"], help="container format (default: the workload's)")
     ap.add_argument("--no-other-mode", action="store_true", help="skip the short run of the other container format")
+    ap.add_argument("--lane-symbols", type=int, default=0, help="native mode lane quantum (default: the library's 4096)")
     ap.add_argument("--e2e-threads", type=int, default=3)
     ap.add_argument("--e2e-chunk-blocks", type=int, default=32, help="blocks per host-pointer call in the e2e leg")
     ap.add_argument("--e2e-steps", type=int, default=3)

@@ -55,7 +55,7 @@ struct IdnCompressorParams {
     int32_t device = 0;
     int32_t mode = IDN_MODE_COMPAT;  // IDN_MODE_NATIVE writes container version 2
     uint32_t batch_blocks = 32;      // blocks per device call
-    uint32_t lane_symbols = 4096;    // native mode lane quantum
+    uint32_t lane_symbols = 2048;    // native mode lane quantum
 };
 
 class IdnCompressorParamsBuilder {

@@ -102,7 +102,7 @@ struct idn_gpu_ctx {
     // workspaces of the *_dev paths
     DevBuf w_scratch, w_paylen, w_sizes, w_chosen, w_tiles, w_sliceoff, w_readblock, w_small, w_crcpart, w_crclen;
     DevBuf w_lanefirst, w_laneoff, w_laneblock, w_blkinfo, w_nhdr;  // native mode
-    uint32_t lane_syms = 4096;  // lane quantum of the native format
+    uint32_t lane_syms = 2048;  // lane quantum of the native format (tools/lane_sweep.sh: decode is 17 % faster than at 4096 for +0.5 % size)
     // FASTQ text <-> symbols (idn_fastq.cuh): results of the last parse stay here until the next one
     DevBuf f_text, f_tilecnt, f_tilebase, f_linestart, f_linefn, f_linestate, f_tilefn, f_tilestate, f_recscan, f_title, f_namelo,
         f_namelen, f_readlen, f_readoff, f_nameoff, f_names, f_acids, f_quals, f_err, f_fmtoff, f_fmttext;
@@ -810,17 +810,35 @@ extern "C" int32_t idn_gpu_compress_blocks_dev(idn_gpu_ctx* ctx, const idn_batch
     return IDN_OK;
 }
 
+// per-read CRC partials: thread per read, or warp per read when the reads are long (avg_len = symbols per read, a hint)
+static int32_t launch_crc_read(idn_gpu_ctx* ctx, const uint8_t* acids, const uint8_t* quals, const unsigned long long* read_off,
+                               const uint8_t* names, const unsigned long long* name_off, uint64_t n_reads,
+                               const unsigned long long* n_reads_dev, const int32_t* status, uint64_t grid_reads, uint64_t avg_len,
+                               cudaStream_t st) {
+    if (avg_len >= 1024) {
+        crc_read_warp_kernel<<<(unsigned)((grid_reads * 32 + 127) / 128), 128, 0, st>>>(
+            acids, quals, read_off, names, name_off, n_reads, n_reads_dev, status, ctx->d_crc_tab, ctx->d_xpow,
+            ctx->w_crcpart.as<uint32_t>(), ctx->w_crclen.as<unsigned long long>());
+    } else {
+        crc_read_kernel<<<(unsigned)((grid_reads + 127) / 128), 128, 0, st>>>(acids, quals, read_off, names, name_off, n_reads, n_reads_dev,
+                                                                             status, ctx->d_crc_tab, ctx->d_xpow,
+                                                                             ctx->w_crcpart.as<uint32_t>(),
+                                                                             ctx->w_crclen.as<unsigned long long>());
+    }
+    LAUNCHED("crc_read");
+    return IDN_OK;
+}
+
 static int32_t idn_gpu_block_crc_dev_impl(idn_gpu_ctx* ctx, const idn_batch* batch, uint32_t* block_crc, uint8_t* out,
                                           const unsigned long long* block_off, uint64_t out_cap, cudaStream_t st) {
     const uint64_t R = batch->n_reads;
     CU(ctx->w_crcpart.ensure((R + 1) * 4));
     CU(ctx->w_crclen.ensure((R + 1) * 8));
     if (R > 0) {
-        crc_read_kernel<<<(unsigned)((R + 127) / 128), 128, 0, st>>>(
-            batch->acids, batch->quals, reinterpret_cast<const unsigned long long*>(batch->read_off), batch->names,
-            reinterpret_cast<const unsigned long long*>(batch->name_off), R, nullptr, nullptr, ctx->d_crc_tab, ctx->d_xpow,
-            ctx->w_crcpart.as<uint32_t>(), ctx->w_crclen.as<unsigned long long>());
-        LAUNCHED("crc_read");
+        int32_t rc = launch_crc_read(ctx, batch->acids, batch->quals, reinterpret_cast<const unsigned long long*>(batch->read_off),
+                                     batch->names, reinterpret_cast<const unsigned long long*>(batch->name_off), R, nullptr, nullptr, R,
+                                     batch->n_symbols / R, st);
+        if (rc) return rc;
     }
     crc_block_kernel<<<batch->n_blocks, 256, 0, st>>>(ctx->w_crcpart.as<uint32_t>(), ctx->w_crclen.as<unsigned long long>(),
                                                       batch->block_first_read, batch->n_blocks, ctx->d_xpow, block_crc, out,
@@ -1236,10 +1254,9 @@ static int32_t decompress_native_dev(idn_gpu_ctx* ctx, const uint8_t* blocks, co
     if (block_crc && out_reads_cap) {
         CU(ctx->w_crcpart.ensure((out_reads_cap + 1) * 4));
         CU(ctx->w_crclen.ensure((out_reads_cap + 1) * 8));
-        crc_read_kernel<<<(unsigned)((out_reads_cap + 127) / 128), 128, 0, st>>>(
-            acids_out, quals_out, roff, nullptr, nullptr, 0, bc.reads + n_blocks, dsp->status, ctx->d_crc_tab, ctx->d_xpow,
-            ctx->w_crcpart.as<uint32_t>(), ctx->w_crclen.as<unsigned long long>());
-        LAUNCHED("crc_read");
+        int32_t rc = launch_crc_read(ctx, acids_out, quals_out, roff, nullptr, nullptr, 0, bc.reads + n_blocks, dsp->status,
+                                     out_reads_cap, out_symbols_cap / out_reads_cap, st);
+        if (rc) return rc;
         crc_verify_kernel<<<n_blocks, 256, 0, st>>>(ctx->w_crcpart.as<uint32_t>(), ctx->w_crclen.as<unsigned long long>(),
                                                     block_first, n_blocks, ctx->d_xpow, block_crc, dsp->status);
         LAUNCHED("crc_verify");
@@ -1326,10 +1343,9 @@ extern "C" int32_t idn_gpu_decompress_blocks_dev(idn_gpu_ctx* ctx, const uint8_t
     if (block_crc && n_blocks && out_reads_cap) {
         CU(ctx->w_crcpart.ensure((out_reads_cap + 1) * 4));
         CU(ctx->w_crclen.ensure((out_reads_cap + 1) * 8));
-        crc_read_kernel<<<(unsigned)((out_reads_cap + 127) / 128), 128, 0, st>>>(
-            acids_out, quals_out, roff, nullptr, nullptr, 0, bc.reads + n_blocks, dsp->status, ctx->d_crc_tab, ctx->d_xpow,
-            ctx->w_crcpart.as<uint32_t>(), ctx->w_crclen.as<unsigned long long>());
-        LAUNCHED("crc_read");
+        rc = launch_crc_read(ctx, acids_out, quals_out, roff, nullptr, nullptr, 0, bc.reads + n_blocks, dsp->status, out_reads_cap,
+                             out_symbols_cap / out_reads_cap, st);
+        if (rc) return rc;
         crc_verify_kernel<<<n_blocks, 256, 0, st>>>(ctx->w_crcpart.as<uint32_t>(), ctx->w_crclen.as<unsigned long long>(),
                                                     block_first, n_blocks, ctx->d_xpow, block_crc, dsp->status);
         LAUNCHED("crc_verify");

@@ -777,6 +777,53 @@ crc_read_kernel(const uint8_t* __restrict__ acids, const uint8_t* __restrict__ q
     part_len[r] = p.len;
 }
 
+// CRC of n bytes by one warp: every lane takes a contiguous slice, the lanes combine in order (result in lane 0)
+__device__ __forceinline__ CrcPair crc_bytes_warp(const uint8_t* __restrict__ base, unsigned long long off, uint32_t n,
+                                                  const uint32_t* __restrict__ tab, const uint32_t* __restrict__ xpow, uint32_t lane) {
+    const uint32_t chunk = (n + 31) / 32;
+    const uint32_t lo = min(lane * chunk, n), hi = min(lo + chunk, n);
+    CrcPair p{0, hi - lo};
+    if (hi > lo) p.crc = crc_bytes(base, off + lo, hi - lo, tab);
+    for (int d = 1; d < 32; d <<= 1) {
+        CrcPair o;
+        o.crc = __shfl_down_sync(0xffffffffu, p.crc, d);
+        o.len = __shfl_down_sync(0xffffffffu, p.len, d);
+        if ((lane & (2 * d - 1)) == 0) p = crc_concat(p, o, xpow);
+    }
+    return p;
+}
+
+// long reads: one warp per read (the thread-per-read kernel would walk tens of kilobytes per thread)
+__global__ void __launch_bounds__(128)
+crc_read_warp_kernel(const uint8_t* __restrict__ acids, const uint8_t* __restrict__ quals,
+                     const unsigned long long* __restrict__ read_off, const uint8_t* __restrict__ names,
+                     const unsigned long long* __restrict__ name_off, uint64_t n_reads,
+                     const unsigned long long* __restrict__ n_reads_dev, const int32_t* __restrict__ status,
+                     const uint32_t* __restrict__ crc_tab, const uint32_t* __restrict__ xpow_g,
+                     uint32_t* __restrict__ part_crc, unsigned long long* __restrict__ part_len) {
+    __shared__ uint32_t tab[256];
+    __shared__ uint32_t xpow[64];
+    if (status && status[0] != 0) return;
+    if (n_reads_dev) n_reads = *n_reads_dev;
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) tab[i] = crc_tab[i];
+    for (int i = threadIdx.x; i < 64; i += blockDim.x) xpow[i] = xpow_g[i];
+    __syncthreads();
+    const uint32_t lane = threadIdx.x & 31;
+    uint64_t r = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (r >= n_reads) return;
+    unsigned long long off = read_off[r];
+    uint32_t len = (uint32_t)(read_off[r + 1] - off);
+    CrcPair p{0, 0};
+    if (names && name_off) p = crc_bytes_warp(names, name_off[r], (uint32_t)(name_off[r + 1] - name_off[r]), tab, xpow, lane);
+    CrcPair a = crc_bytes_warp(acids, off, len, tab, xpow, lane);
+    CrcPair q = crc_bytes_warp(quals, off, len, tab, xpow, lane);
+    if (lane == 0) {
+        p = crc_concat(crc_concat(p, a, xpow), q, xpow);
+        part_crc[r] = p.crc;
+        part_len[r] = p.len;
+    }
+}
+
 // ordered tree reduction of the per-read partials of reads [r0, r1) by one 256-thread block; result in thread 0
 __device__ __forceinline__ uint32_t block_crc_reduce(const uint32_t* __restrict__ part_crc,
                                                      const unsigned long long* __restrict__ part_len, uint64_t r0,

@@ -201,7 +201,7 @@ class IdnCompressor:
     """
 
     def __init__(self, models, *, max_block_total_len=4 * 1024 * 1024, thread_num=0, include_identifiers=True, quality=7,
-                 fast=False, device=0, mode=capi.MODE_COMPAT, batch_blocks=32, lane_symbols=4096):
+                 fast=False, device=0, mode=capi.MODE_COMPAT, batch_blocks=32, lane_symbols=2048):
         self.L = load()
         p = Params()
         self.L.idn_host_params_default(C.byref(p))

@@ -68,7 +68,7 @@ int32_t idn_gpu_create(int32_t device, idn_gpu_ctx **ctx);
 void idn_gpu_destroy(idn_gpu_ctx *ctx);
 const char *idn_gpu_last_error(const idn_gpu_ctx *ctx);
 /* lane quantum of IDN_MODE_NATIVE compression: a lane holds the reads whose first symbol falls into the same run of
- * `lane_syms` symbols of the block (default 4096); the value travels in the container, decoders need no setting */
+ * `lane_syms` symbols of the block (default 2048); the value travels in the container, decoders need no setting */
 int32_t idn_gpu_set_lane_symbols(idn_gpu_ctx *ctx, uint32_t lane_syms);
 /* number of kernel launches this ctx has issued since creation (bench.py's gpu_launches) */
 uint64_t idn_gpu_launch_count(const idn_gpu_ctx *ctx);

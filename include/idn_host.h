@@ -60,7 +60,7 @@ typedef struct {                    /* IdnCompressorParamsBuilder, idn/compresso
     int32_t device;                 /* CUDA device, default 0 */
     int32_t mode;                   /* IDN_MODE_COMPAT (container version 1) or IDN_MODE_NATIVE (version 2) */
     uint32_t batch_blocks;          /* blocks per device call, default 32 */
-    uint32_t lane_symbols;          /* native mode lane quantum, default 4096 */
+    uint32_t lane_symbols;          /* native mode lane quantum, default 2048 */
 } idn_host_params;
 void idn_host_params_default(idn_host_params *p);
 /* IdnCompressor::with_params over an in-memory writer; `models` is the ModelProvider (order = provider order) */

@@ -52,14 +52,14 @@ def test_native_encode_matches_cpu_statement(gctx, O, toy_models, toy_handles, r
     check_blocks(out, block_off, crc, oracle_native(O, toy_models, reads_1k, bf, lane_syms))
     ro, a, q = decode_all(gctx, out, block_off, crc, toy_handles)
     assert np.array_equal(ro, reads_1k.read_off) and np.array_equal(a, reads_1k.acids) and np.array_equal(q, reads_1k.quals)
-    gctx.set_lane_symbols(4096)
+    gctx.set_lane_symbols(2048)
 
 
 def test_native_long_read_golden_input(gctx, O, toy_models, toy_handles, reads_1m):
     """One read of 500 000 symbols (the reference's 1M sample): one lane, width-4 length table absent (constant)."""
     bf = np.asarray([0, 1], dtype=np.uint32)
     out, block_off, crc, _ = gctx.compress_blocks(reads_1m.read_off, reads_1m.acids, reads_1m.quals, bf, toy_handles, mode=NATIVE)
-    check_blocks(out, block_off, crc, oracle_native(O, toy_models, reads_1m, bf, 4096))
+    check_blocks(out, block_off, crc, oracle_native(O, toy_models, reads_1m, bf, 2048))
     ro, a, q = decode_all(gctx, out, block_off, crc, toy_handles)
     assert np.array_equal(a, reads_1m.acids) and np.array_equal(q, reads_1m.quals)
 
@@ -82,13 +82,13 @@ def test_native_ragged_empty_and_wide_lengths(gctx, O, toy_models, toy_handles):
             ln, a2, q2 = O.decompress_native_block(toy_models, blk)
             lo, hi = int(reads.read_off[bf[b]]), int(reads.read_off[bf[b + 1]])
             assert np.array_equal(a2, reads.acids[lo:hi]) and np.array_equal(q2, reads.quals[lo:hi])
-    gctx.set_lane_symbols(4096)
+    gctx.set_lane_symbols(2048)
 
 
 def test_native_names_prefix_and_crc(gctx, O, toy_models, toy_handles, reads_1k):
     """Identifiers stay on the host: the device reserves the prefix, the CRC covers the names."""
     bf = blocks_of(reads_1k, 20000)
-    expect = oracle_native(O, toy_models, reads_1k, bf, 4096, names=True)
+    expect = oracle_native(O, toy_models, reads_1k, bf, 2048, names=True)
     prefix = []
     for data, _ in expect:
         assert data[0] == 0
@@ -117,7 +117,7 @@ def test_native_model_choice_per_lane(gctx, O, model_data, reads_1k):
     check_blocks(out, block_off, crc, oracle_native(O, models, reads_1k, bf, 2000))
     ro, a, q = decode_all(gctx, out, block_off, crc, handles)
     assert np.array_equal(ro, reads_1k.read_off) and np.array_equal(a, reads_1k.acids) and np.array_equal(q, reads_1k.quals)
-    gctx.set_lane_symbols(4096)
+    gctx.set_lane_symbols(2048)
     for h in handles:
         gctx.release_model(h)
 
