@@ -163,6 +163,14 @@ void prof_mark(idn_gpu_ctx* c, const char* name, cudaStream_t st) {
         if (ctx->profiling) prof_mark(ctx, nullptr, st); \
     } while (0)
 
+// wait for a stream without spinning: several ctx (one host thread each) share the host's cores with the caller's own
+// threads, and a spinning cudaStreamSynchronize per thread starves them (8 ranks x 3 ctx on a 32-core host)
+cudaError_t sync_stream(idn_gpu_ctx* c, cudaStream_t st) {
+    cudaError_t e = cudaEventRecord(c->ev, st);
+    if (e != cudaSuccess) return e;
+    return cudaEventSynchronize(c->ev);
+}
+
 struct HostTimer {
     idn_gpu_ctx* c;
     std::chrono::steady_clock::time_point t0;
@@ -349,7 +357,7 @@ extern "C" int32_t idn_gpu_create(int32_t device, idn_gpu_ctx** out) {
     };
     if (cudaSetDevice(device) != cudaSuccess) return bail("cudaSetDevice");
     if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) return bail("cudaStreamCreate");
-    if (cudaEventCreateWithFlags(&ctx->ev, cudaEventDisableTiming) != cudaSuccess) return bail("cudaEventCreate");
+    if (cudaEventCreateWithFlags(&ctx->ev, cudaEventDisableTiming | cudaEventBlockingSync) != cudaSuccess) return bail("cudaEventCreate");
     if (cudaMalloc(&ctx->d_models, sizeof(ModelDev) * kMaxSlots) != cudaSuccess) return bail("cudaMalloc");
     if (cudaMemset(ctx->d_models, 0, sizeof(ModelDev) * kMaxSlots) != cudaSuccess) return bail("cudaMemset");
     uint32_t tab[256], xpow[64];
@@ -640,7 +648,7 @@ extern "C" int32_t idn_gpu_score(idn_gpu_ctx* ctx, const idn_batch* b, const idn
     uint32_t err = 0;
     CU(cudaMemcpyAsync(sizes, ctx->s_sizes.p, b->n_reads * n_models * 4, cudaMemcpyDeviceToHost, st));
     CU(cudaMemcpyAsync(&err, &ctx->w_small.as<SmallParams>()->err, 4, cudaMemcpyDeviceToHost, st));
-    CU(cudaStreamSynchronize(st));
+    CU(sync_stream(ctx, st));
     if (err & 1) return fail(ctx, IDN_E_INVALID_SYMBOL, "input holds an acid > 4 or a quality score > 93");
     return IDN_OK;
 }
@@ -1093,7 +1101,7 @@ extern "C" int32_t idn_gpu_compress_blocks(idn_gpu_ctx* ctx, const idn_batch* b,
     CU(cudaMemcpyAsync(&hs, ctx->s_stats.p, sizeof hs, cudaMemcpyDeviceToHost, st));
     CU(cudaMemcpyAsync(&err, &ctx->w_small.as<SmallParams>()->err, 4, cudaMemcpyDeviceToHost, st));
     ht.lap("host:c_kernels_enqueue");
-    CU(cudaStreamSynchronize(st));
+    CU(sync_stream(ctx, st));
     ht.lap("host:c_wait_h2d_kernels");
     if (stats) *stats = hs;
     if (err & 1) return fail(ctx, IDN_E_INVALID_SYMBOL, "input holds an acid > 4 or a quality score > 93");
@@ -1105,7 +1113,7 @@ extern "C" int32_t idn_gpu_compress_blocks(idn_gpu_ctx* ctx, const idn_batch* b,
     if (hs.out_bytes) CU(cudaMemcpyAsync(out, ctx->s_out.p, hs.out_bytes, cudaMemcpyDeviceToHost, st));
     CU(cudaMemcpyAsync(block_off, ctx->s_blockoff.p, ((size_t)b->n_blocks + 1) * 8, cudaMemcpyDeviceToHost, st));
     if (block_crc) CU(cudaMemcpyAsync(block_crc, ctx->s_crc.p, (size_t)b->n_blocks * 4, cudaMemcpyDeviceToHost, st));
-    CU(cudaStreamSynchronize(st));
+    CU(sync_stream(ctx, st));
     ht.lap("host:c_d2h");
     return IDN_OK;
 }
@@ -1124,7 +1132,7 @@ extern "C" int32_t idn_gpu_block_crc(idn_gpu_ctx* ctx, const idn_batch* b, uint3
     rc = idn_gpu_block_crc_dev_impl(ctx, &d, ctx->s_crc.as<uint32_t>(), nullptr, nullptr, 0, st);
     if (rc) return rc;
     CU(cudaMemcpyAsync(block_crc, ctx->s_crc.p, (size_t)b->n_blocks * 4, cudaMemcpyDeviceToHost, st));
-    CU(cudaStreamSynchronize(st));
+    CU(sync_stream(ctx, st));
     return IDN_OK;
 }
 
@@ -1433,7 +1441,7 @@ extern "C" int32_t idn_gpu_index_blocks(idn_gpu_ctx* ctx, const uint8_t* blocks,
     CU(cudaMemcpyAsync(hr.data(), bc.reads, ((size_t)n_blocks + 1) * 8, cudaMemcpyDeviceToHost, st));
     CU(cudaMemcpyAsync(hsym.data(), bc.syms, ((size_t)n_blocks + 1) * 8, cudaMemcpyDeviceToHost, st));
     CU(cudaMemcpyAsync(hst, dsp->status, sizeof hst, cudaMemcpyDeviceToHost, st));
-    CU(cudaStreamSynchronize(st));
+    CU(sync_stream(ctx, st));
     if (hst[0]) return status_to_error(ctx, hst);
     totals->n_reads = hr[n_blocks];
     totals->n_symbols = hsym[n_blocks];
@@ -1489,7 +1497,7 @@ extern "C" int32_t idn_gpu_decompress_blocks(idn_gpu_ctx* ctx, const uint8_t* bl
     CU(cudaMemcpyAsync(&tot[0], bc.reads + n_blocks, 8, cudaMemcpyDeviceToHost, st));
     CU(cudaMemcpyAsync(&tot[1], bc.syms + n_blocks, 8, cudaMemcpyDeviceToHost, st));
     ht.lap("host:d_enqueue");
-    CU(cudaStreamSynchronize(st));
+    CU(sync_stream(ctx, st));
     ht.lap("host:d_wait_h2d_kernels");
     if (hst[0]) {
         if (bad_block) *bad_block = hst[1];
@@ -1501,7 +1509,7 @@ extern "C" int32_t idn_gpu_decompress_blocks(idn_gpu_ctx* ctx, const uint8_t* bl
         CU(cudaMemcpyAsync(quals_out, ctx->s_qout.p, S, cudaMemcpyDeviceToHost, st));
     }
     CU(cudaMemcpyAsync(read_off_out, ctx->s_offout.p, (R + 1) * 8, cudaMemcpyDeviceToHost, st));
-    CU(cudaStreamSynchronize(st));
+    CU(sync_stream(ctx, st));
     ht.lap("host:d_d2h");
     if (host_crc && block_crc && n_blocks) {
         // CRC with names on the device: stage names and run the CRC kernels over the decoded batch
@@ -1525,7 +1533,7 @@ extern "C" int32_t idn_gpu_decompress_blocks(idn_gpu_ctx* ctx, const uint8_t* bl
         if (rc) return rc;
         std::vector<uint32_t> got(n_blocks);
         CU(cudaMemcpyAsync(got.data(), ctx->s_crc.p, (size_t)n_blocks * 4, cudaMemcpyDeviceToHost, st));
-        CU(cudaStreamSynchronize(st));
+        CU(sync_stream(ctx, st));
         for (uint32_t i = 0; i < n_blocks; i++)
             if (got[i] != block_crc[i]) {
                 if (bad_block) *bad_block = (int32_t)i;
@@ -1606,7 +1614,7 @@ extern "C" int32_t idn_gpu_decompress_reads(idn_gpu_ctx* ctx, const uint8_t* pay
     }
     if (read_status) CU(cudaMemcpyAsync(read_status, ctx->s_idx.p, R * 4, cudaMemcpyDeviceToHost, st));
     CU(cudaMemcpyAsync(&err, &dsp->err, 4, cudaMemcpyDeviceToHost, st));
-    CU(cudaStreamSynchronize(st));
+    CU(sync_stream(ctx, st));
     if (err & 1) return fail(ctx, IDN_E_SERIALIZE, "a sequence payload ended before its symbols were decoded");
     return IDN_OK;
 }
@@ -1726,7 +1734,7 @@ extern "C" int32_t idn_gpu_fastq_parse_dev(idn_gpu_ctx* ctx, const uint8_t* text
         if (rc) return rc;
         CU(cudaMemcpyAsync(&n_newlines, tile_base + n_tiles, 8, cudaMemcpyDeviceToHost, st));
         CU(cudaMemcpyAsync(&last, text + n - 1, 1, cudaMemcpyDeviceToHost, st));
-        CU(cudaStreamSynchronize(st));
+        CU(sync_stream(ctx, st));
     }
     const uint64_t n_lines = n_newlines + (n > 0 && last != '\n' ? 1 : 0);
     info->n_lines = n_lines;
@@ -1755,7 +1763,7 @@ extern "C" int32_t idn_gpu_fastq_parse_dev(idn_gpu_ctx* ctx, const uint8_t* text
         int32_t rc = scan_u64(ctx, tf, n_lines, rec_scan, st);
         if (rc) return rc;
         CU(cudaMemcpyAsync(&n_reads, rec_scan + n_lines, 8, cudaMemcpyDeviceToHost, st));
-        CU(cudaStreamSynchronize(st));
+        CU(sync_stream(ctx, st));
         CU(ctx->f_title.ensure((n_reads + 1) * 8));
         if (n_reads) {
             fq_titles_kernel<<<(unsigned)((n_lines + 255) / 256), 256, 0, st>>>(tf, n_lines, rec_scan, ctx->f_title.as<unsigned long long>());
@@ -1785,7 +1793,7 @@ extern "C" int32_t idn_gpu_fastq_parse_dev(idn_gpu_ctx* ctx, const uint8_t* text
     CU(cudaMemcpyAsync(&tot[0], read_off + n_reads, 8, cudaMemcpyDeviceToHost, st));
     CU(cudaMemcpyAsync(&tot[1], name_off + n_reads, 8, cudaMemcpyDeviceToHost, st));
     CU(cudaMemcpyAsync(&ferr, first_err, 8, cudaMemcpyDeviceToHost, st));
-    CU(cudaStreamSynchronize(st));
+    CU(sync_stream(ctx, st));
     info->n_symbols = tot[0];
     info->n_name_bytes = tot[1];
     if (ferr == ~0ull && n_reads) {
@@ -1797,7 +1805,7 @@ extern "C" int32_t idn_gpu_fastq_parse_dev(idn_gpu_ctx* ctx, const uint8_t* text
                                                                            ctx->f_quals.as<uint8_t>(), first_err);
         LAUNCHED("fq_convert");
         CU(cudaMemcpyAsync(&ferr, first_err, 8, cudaMemcpyDeviceToHost, st));
-        CU(cudaStreamSynchronize(st));
+        CU(sync_stream(ctx, st));
     }
     if (ferr != ~0ull) {
         info->error_kind = (int32_t)(ferr & 0xff);
@@ -1842,7 +1850,7 @@ extern "C" int32_t idn_gpu_fastq_fetch(idn_gpu_ctx* ctx, uint8_t* acids, uint8_t
     if (read_off) CU(cudaMemcpyAsync(read_off, ctx->f_readoff.p, (f.n_reads + 1) * 8, cudaMemcpyDeviceToHost, st));
     if (names && f.n_name_bytes) CU(cudaMemcpyAsync(names, ctx->f_names.p, f.n_name_bytes, cudaMemcpyDeviceToHost, st));
     if (name_off) CU(cudaMemcpyAsync(name_off, ctx->f_nameoff.p, (f.n_reads + 1) * 8, cudaMemcpyDeviceToHost, st));
-    CU(cudaStreamSynchronize(st));
+    CU(sync_stream(ctx, st));
     return IDN_OK;
 }
 
@@ -1895,11 +1903,11 @@ extern "C" int32_t idn_gpu_fastq_format(idn_gpu_ctx* ctx, const idn_batch* b, in
     uint32_t err = 0;
     CU(cudaMemcpyAsync(&need, ctx->s_stats.p, 8, cudaMemcpyDeviceToHost, st));
     CU(cudaMemcpyAsync(&err, ctx->f_err.p, 4, cudaMemcpyDeviceToHost, st));
-    CU(cudaStreamSynchronize(st));
+    CU(sync_stream(ctx, st));
     *n_out = need;
     if (err & 1) return fail(ctx, IDN_E_INVALID_SYMBOL, "input holds an acid > 4 or a quality score > 93");
     if (need > cap) return fail(ctx, IDN_E_NOSPACE, "FASTQ text needs %llu bytes, capacity is %llu", (unsigned long long)need, (unsigned long long)cap);
     if (need) CU(cudaMemcpyAsync(text, ctx->f_fmttext.p, need, cudaMemcpyDeviceToHost, st));
-    CU(cudaStreamSynchronize(st));
+    CU(sync_stream(ctx, st));
     return IDN_OK;
 }
