@@ -411,3 +411,77 @@ def test_walk_skips_large_identifier_slices_and_long_reads(gctx, O, toy_models, 
     crc = np.asarray([b[2] for b in blocks], dtype=np.uint32)
     ro, a, q = gctx.decompress_blocks(buf, doff, crc, toy_handles, block_len=dlen, name_off=reads.name_off, names=reads.names)
     assert np.array_equal(ro, reads.read_off) and np.array_equal(a, reads.acids) and np.array_equal(q, reads.quals)
+
+
+# ---- size-independent properties at a size the oracle would need minutes for --------------------------------------
+@pytest.mark.parametrize("mode", [1, 2])
+def test_large_device_round_trip_properties(gctx, O, bundled, mode):
+    """2 M model-driven synthetic reads (200 M symbols, 48 blocks) stay on the device: encode -> decode is the identity,
+    the block CRCs of the container equal the CRCs of the input computed independently (idn_gpu_block_crc), the
+    container is deterministic, and a spot-checked block equals the oracle's encoding of the same reads."""
+    import ctypes as C
+
+    import torch
+    from idencomp_b200 import capi
+    am, ha = bundled["ERR174310__human__illumina_hiseq_2000__acids"]
+    qm, hq = bundled["SRR2962693__human__illumina_hiseq_2500__q_scores"]
+    R, L = 2_000_000, 100
+    S = R * L
+    dev = "cuda"
+    sp = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    ro = torch.arange(R + 1, dtype=torch.int64, device=dev) * L
+    a_d = torch.zeros(S + 16, dtype=torch.uint8, device=dev)
+    q_d = torch.zeros(S + 16, dtype=torch.uint8, device=dev)
+    gctx.check(gctx.L.idn_gpu_synth_reads_dev(gctx.h, ha, hq, ro.data_ptr(), R, 7, 20240601, 500, a_d.data_ptr(), q_d.data_ptr(), sp))
+    per = 4 * 1024 * 1024 // L
+    bf_h = np.append(np.arange(0, R, per), R).astype(np.int32)
+    nb = len(bf_h) - 1
+    bf = torch.from_numpy(bf_h).to(dev)
+    b = capi.Batch()
+    b.n_reads, b.n_symbols, b.n_blocks = R, S, nb
+    b.acids, b.quals, b.read_off, b.block_first_read = a_d.data_ptr(), q_d.data_ptr(), ro.data_ptr(), bf.data_ptr()
+    hd = np.asarray([ha, hq], dtype=np.int32)
+    cap = int(gctx.L.idn_gpu_compress_bound(R, S, nb, 0))
+    outs = []
+    for _ in range(2):
+        out = torch.zeros(cap + 16, dtype=torch.uint8, device=dev)
+        boff = torch.zeros(nb + 1, dtype=torch.int64, device=dev)
+        crc = torch.zeros(nb, dtype=torch.int32, device=dev)
+        st = torch.zeros(8, dtype=torch.int64, device=dev)
+        gctx.check(gctx.L.idn_gpu_compress_blocks_dev(gctx.h, C.byref(b), mode, hd.ctypes.data, 2, 0, None, out.data_ptr(), cap,
+                                                      boff.data_ptr(), crc.data_ptr(), st.data_ptr(), sp))
+        torch.cuda.synchronize()
+        outs.append((out, boff, crc, int(st[0])))
+    (out, boff, crc, n_out), (out2, _, crc2, n_out2) = outs
+    assert n_out == n_out2 and torch.equal(out[:n_out], out2[:n_out])          # deterministic
+    # CRC of the input, computed by the stand-alone CRC entry point on host copies of two blocks
+    a_h, q_h = a_d[:S].cpu().numpy(), q_d[:S].cpu().numpy()
+    lo, hi = int(bf_h[3]) * L, int(bf_h[5]) * L
+    sub_ro = np.arange(0, (hi - lo) // L + 1, dtype=np.uint64) * L
+    want_crc = gctx.block_crc(sub_ro, a_h[lo:hi], q_h[lo:hi], np.asarray([0, per, 2 * per], dtype=np.uint32))
+    assert want_crc.tolist() == (crc[3:5].cpu().numpy().astype(np.uint32)).tolist()
+    import zlib
+    assert int(want_crc[0]) == zlib.crc32(b"".join(a_h[lo + i * L:lo + (i + 1) * L].tobytes() + q_h[lo + i * L:lo + (i + 1) * L].tobytes()
+                                                     for i in range(per)))
+    # decode on the device: identity
+    doff = torch.cat([boff[:-1] + 8, boff[-1:]]).contiguous()
+    dlen = (boff[1:] - boff[:-1] - 8).to(torch.int32).contiguous()
+    da = torch.zeros(S + 16, dtype=torch.uint8, device=dev)
+    dq = torch.zeros(S + 16, dtype=torch.uint8, device=dev)
+    dro = torch.zeros(R + 1, dtype=torch.int64, device=dev)
+    stt = torch.zeros(4, dtype=torch.int32, device=dev)
+    gctx.check(gctx.L.idn_gpu_decompress_blocks_dev(gctx.h, out.data_ptr(), doff.data_ptr(), dlen.data_ptr(), crc.data_ptr(), nb, n_out, mode,
+                                                    hd.ctypes.data, 2, da.data_ptr(), dq.data_ptr(), dro.data_ptr(), R, S, stt.data_ptr(), sp))
+    torch.cuda.synchronize()
+    assert stt.cpu().tolist()[:3] == [0, -1, R]
+    assert torch.equal(da[:S], a_d[:S]) and torch.equal(dq[:S], q_d[:S]) and torch.equal(dro, ro)
+    # one block against the oracle, byte for byte
+    k = nb - 1  # the ragged last block
+    r0, r1 = int(bf_h[k]), int(bf_h[k + 1])
+    sub = O.Reads(np.arange(0, r1 - r0 + 1, dtype=np.uint64) * L, a_h[r0 * L:r1 * L], q_h[r0 * L:r1 * L])
+    if mode == 1:
+        data, ocrc, _ = O.compress_block([am, qm], sub, 0, r1 - r0, include_identifiers=False)
+    else:
+        data, ocrc = O.compress_native_block([am, qm], sub, 0, r1 - r0, lane_syms=2048, include_identifiers=False)
+    lo_b, hi_b = int(boff[k]), int(boff[k + 1])
+    assert out[lo_b + 8:hi_b].cpu().numpy().tobytes() == data and (int(crc[k]) & 0xffffffff) == ocrc
