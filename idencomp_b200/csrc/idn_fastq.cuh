@@ -252,14 +252,13 @@ fq_convert_kernel(FastqView V, const unsigned long long* __restrict__ name_lo, c
     uint32_t err = kFqOk;
     const uint32_t len = (uint32_t)(a_hi - a_lo);
     FwdReader ra, rq;
-    ra.init(V.text);
-    rq.init(V.text);
+    ra.start(V.text + a_lo);
+    rq.start(V.text + q_lo);
     FwdWriter oa, oq;
     oa.init(acids + read_off[r]);
     oq.init(quals + read_off[r]);
-    if (len) ra.prime(a_lo);
     for (uint32_t i = 0; i < len; i++) {
-        uint32_t c = ra.get(a_lo + i), a;
+        uint32_t c = ra.get(), a;
         // FASTQ_BYTE_TO_ACID (consts.rs:41-51): N=0 A=1 C=2 T=3 G=4 (sequence.rs:401-413)
         if (c == 'A') a = 1; else if (c == 'C') a = 2; else if (c == 'T') a = 3; else if (c == 'G') a = 4; else if (c == 'N') a = 0;
         else {
@@ -272,9 +271,8 @@ fq_convert_kernel(FastqView V, const unsigned long long* __restrict__ name_lo, c
     if (!err && (s_hi == s_lo || V.text[s_lo] != '+')) err = kFqInvalidFormat;  // parse_separator (reader.rs:236-247)
     const uint32_t qlen = (uint32_t)(q_hi - q_lo);
     const uint32_t m = qlen < len ? qlen : len;
-    if (m) rq.prime(q_lo);
     for (uint32_t i = 0; i < m; i++) {
-        uint32_t c = rq.get(q_lo + i);
+        uint32_t c = rq.get();
         if (c < '!' || c > '~') {  // FASTQ_VALID_Q_SCORE_BYTES (consts.rs:53-63)
             if (!err) err = kFqInvalidQualityScore;
             c = '!';
@@ -327,14 +325,10 @@ fq_format_kernel(const uint8_t* __restrict__ acids, const uint8_t* __restrict__ 
     w.push('\n');
     bool bad = false;
     FwdReader ra, rq;
-    ra.init(acids);
-    rq.init(quals);
-    if (len) {
-        ra.prime(off);
-        rq.prime(off);
-    }
+    ra.start(acids + off);
+    rq.start(quals + off);
     for (uint32_t i = 0; i < len; i++) {
-        uint32_t a = ra.get(off + i);
+        uint32_t a = ra.get();
         if (a > 4) {
             bad = true;
             a = 0;
@@ -347,7 +341,7 @@ fq_format_kernel(const uint8_t* __restrict__ acids, const uint8_t* __restrict__ 
         for (uint32_t i = 0; i < nl; i++) w.push(names[no + i]);
     w.push('\n');
     for (uint32_t i = 0; i < len; i++) {
-        uint32_t q = rq.get(off + i);
+        uint32_t q = rq.get();
         if (q > 93) {
             bad = true;
             q = 0;

@@ -16,57 +16,74 @@ namespace idn {
 // byte readers / writers on 4-byte words (threads walk their read sequentially; word access keeps the
 // divergent traffic at one 32-byte sector per 32 bytes instead of one per byte)
 // ---------------------------------------------------------------------------------------------------
-struct BackReader {  // reads bytes at decreasing global indices
-    const uint8_t* base;  // rounded down to a 4-byte boundary; `mis` bytes were dropped
-    uint32_t word, mis;
-    __device__ __forceinline__ void init(const uint8_t* b) {
-        mis = (uint32_t)(reinterpret_cast<uintptr_t>(b) & 3);
-        base = b - mis;
+// Sequential byte readers over aligned 4-byte words: the cursor (word pointer + byte lane) moves by one byte per call and
+// a word is loaded only when its first byte is asked for, so nothing outside [first byte read, last byte read] rounded
+// to words is ever touched.
+struct BackReader {  // bytes at decreasing addresses
+    const uint32_t* wp;  // word that holds the next byte
+    uint32_t word;
+    int lane;            // byte of `word` the next get() returns; 4 = the word is not loaded yet
+    bool loaded;
+    __device__ __forceinline__ void start(const uint8_t* last) {  // the next get() returns *last
+        const uintptr_t a = reinterpret_cast<uintptr_t>(last);
+        wp = reinterpret_cast<const uint32_t*>(a & ~(uintptr_t)3);
+        lane = (int)(a & 3);
+        loaded = false;
         word = 0;
     }
-    // first call: g is the highest index that will be read
-    __device__ __forceinline__ void prime(long long g) {
-        g += mis;
-        word = __ldg(reinterpret_cast<const uint32_t*>(base + (g & ~3ll)));
-    }
-    __device__ __forceinline__ uint32_t get(long long g) {  // g may be < first valid index -> caller guards
-        g += mis;
-        uint32_t sh = (uint32_t)(g & 3) * 8;
-        if (sh == 24) word = __ldg(reinterpret_cast<const uint32_t*>(base + (g & ~3ll)));
-        return (word >> sh) & 0xffu;
+    __device__ __forceinline__ uint32_t get() {
+        if (!loaded) {
+            word = __ldg(wp);
+            loaded = true;
+        }
+        const uint32_t b = (word >> (8 * lane)) & 0xffu;
+        if (--lane < 0) {
+            lane = 3;
+            wp--;
+            loaded = false;
+        }
+        return b;
     }
 };
 
-struct FwdReader {  // reads bytes at increasing global indices
-    const uint8_t* base;  // rounded down to a 4-byte boundary; `mis` bytes were dropped
-    uint32_t word, mis;
-    __device__ __forceinline__ void init(const uint8_t* b) {
-        mis = (uint32_t)(reinterpret_cast<uintptr_t>(b) & 3);
-        base = b - mis;
+struct FwdReader {  // bytes at increasing addresses
+    const uint32_t* wp;
+    uint32_t word;
+    int lane;
+    bool loaded;
+    __device__ __forceinline__ void start(const uint8_t* first) {  // the next get() returns *first
+        const uintptr_t a = reinterpret_cast<uintptr_t>(first);
+        wp = reinterpret_cast<const uint32_t*>(a & ~(uintptr_t)3);
+        lane = (int)(a & 3);
+        loaded = false;
         word = 0;
     }
-    // first call: g is the lowest index that will be read
-    __device__ __forceinline__ void prime(unsigned long long g) {
-        g += mis;
-        word = __ldg(reinterpret_cast<const uint32_t*>(base + (g & ~3ull)));
-    }
-    __device__ __forceinline__ uint32_t get(unsigned long long g) {
-        g += mis;
-        uint32_t sh = (uint32_t)(g & 3) * 8;
-        if (sh == 0) word = __ldg(reinterpret_cast<const uint32_t*>(base + g));
-        return (word >> sh) & 0xffu;
+    __device__ __forceinline__ uint32_t get() {
+        if (!loaded) {
+            word = __ldg(wp);
+            loaded = true;
+        }
+        const uint32_t b = (word >> (8 * lane)) & 0xffu;
+        if (++lane == 4) {
+            lane = 0;
+            wp++;
+            loaded = false;
+        }
+        return b;
     }
 };
 
 // writes bytes at decreasing addresses, 4 at a time.  `end` must be 4-byte aligned.
 struct BackWriter {
     uint32_t* wptr;  // next word to fill is wptr[-1]
+    uint32_t* wend;
     uint32_t acc, n;
     __device__ __forceinline__ void init(uint8_t* end) {
-        wptr = reinterpret_cast<uint32_t*>(end);
+        wptr = wend = reinterpret_cast<uint32_t*>(end);
         acc = 0;
         n = 0;
     }
+    __device__ __forceinline__ uint32_t bytes() const { return (uint32_t)(wend - wptr) * 4u + n; }
     __device__ __forceinline__ void push(uint32_t b) {
         acc = (acc << 8) | b;  // the first byte pushed lands at the highest address
         if (++n == 4) {
@@ -153,16 +170,12 @@ score_multi_kernel(const ModelPack<M> P, const uint8_t* __restrict__ acids, cons
         bytes[k] = 0;
     }
     FwdReader ra, rq;
-    ra.init(acids);
-    rq.init(quals);
-    if (len) {
-        ra.prime(off);
-        rq.prime(off);
-    }
+    ra.start(acids + off);
+    rq.start(quals + off);
     bool bad = false;
 #pragma unroll 1
     for (uint32_t i = 0; i < len; i++) {
-        uint32_t a = ra.get(off + i), q = rq.get(off + i);
+        uint32_t a = ra.get(), q = rq.get();
         if (a > 4 || q > 93) {
             bad = true;
             a = a > 4 ? 0 : a;
@@ -300,20 +313,18 @@ struct EncodeArgs {
 struct EncStream {
     uint32_t x0, x1;  // state 0 = acids, state 1 = quality scores (compressor.rs:95-96)
     BackWriter out;
-    uint32_t total;   // bytes emitted so far
     bool bad;         // an input symbol was out of range
     __device__ __forceinline__ void begin(uint8_t* slot_end) {
         x0 = x1 = kRansL;
         out.init(slot_end);
-        total = 0;
         bad = false;
     }
     __device__ __forceinline__ void flush() {  // flush_all: state 0 then state 1
         out.push_u32_le(x0);
         out.push_u32_le(x1);
-        total += 8;
         out.finish();
     }
+    __device__ __forceinline__ uint32_t total() const { return out.bytes(); }  // bytes emitted so far
 };
 
 // Pushes one read (positions len-1 .. 0) onto the stream   SequenceCompressor::compress, sequence_compressor.rs:82-155
@@ -326,12 +337,8 @@ __device__ __forceinline__ void encode_read_body(const ModelDev& ma, const Model
     const SpecDev& sa = ma.spec;
     const SpecDev& sq = mq.spec;
     BackReader ra, rq;
-    ra.init(acids);
-    rq.init(quals);
-    if (len) {
-        ra.prime(off + len - 1);
-        rq.prime(off + len - 1);
-    }
+    ra.start(acids + off + len - 1);  // nothing is loaded before the first get()
+    rq.start(quals + off + len - 1);
     GenBack ga, gq;
     ga.clear(sa);
     gq.clear(sq);
@@ -341,8 +348,8 @@ __device__ __forceinline__ void encode_read_body(const ModelDev& ma, const Model
     auto pull = [&]() {
         uint32_t a = 0, q = 0;
         if (front >= 0) {
-            a = ra.get(off + front);
-            q = rq.get(off + front);
+            a = ra.get();
+            q = rq.get();
             if (a > 4 || q > 93) {
                 S.bad = true;
                 a = a > 4 ? 0 : a;
@@ -379,10 +386,7 @@ __device__ __forceinline__ void encode_read_body(const ModelDev& ma, const Model
             row_q = ctx_row(mq, gq.spec(sq, pb.pos, psq));
         }
     };
-    auto emit = [&](uint32_t b) {
-        S.out.push(b);
-        S.total++;
-    };
+    auto emit = [&](uint32_t b) { S.out.push(b); };
     // prologue: rows of position len-1, its entries, rows of position len-2
     uint32_t row_a, row_q;
     rows_next(row_a, row_q);  // generators at len-1, entry 0 = symbol len-1
@@ -428,7 +432,7 @@ encode_kernel(EncodeArgs A, const ModelDev MA, const ModelDev MQ) {
     S.begin(A.scratch + 4ull * A.read_off[r + 1] + 8ull * (r + 1));
     encode_read_body(ma, mq, A.acids, A.quals, off, len, S);
     S.flush();
-    A.pay_len[r] = S.total;
+    A.pay_len[r] = S.total();
     if (S.bad) atomicOr(A.err, 1u);
 }
 
@@ -737,10 +741,21 @@ __device__ __forceinline__ CrcPair crc_concat(CrcPair a, CrcPair b, const uint32
 __device__ __forceinline__ uint32_t crc_bytes(const uint8_t* __restrict__ base, unsigned long long off, uint32_t n,
                                               const uint32_t* __restrict__ tab /*smem[256]*/) {
     uint32_t c = 0xffffffffu;
-    FwdReader rd;
-    rd.init(base);
-    if (n) rd.prime(off);
-    for (uint32_t i = 0; i < n; i++) c = tab[(c ^ rd.get(off + i)) & 0xffu] ^ (c >> 8);
+    const uint8_t* p = base + off;
+    while (n && (reinterpret_cast<uintptr_t>(p) & 3)) {  // head up to a word boundary
+        c = tab[(c ^ *p++) & 0xffu] ^ (c >> 8);
+        n--;
+    }
+    const uint32_t* w = reinterpret_cast<const uint32_t*>(p);
+    for (; n >= 4; n -= 4) {  // a word at a time: xor it in, then four table steps
+        c ^= __ldg(w++);
+        c = tab[c & 0xffu] ^ (c >> 8);
+        c = tab[c & 0xffu] ^ (c >> 8);
+        c = tab[c & 0xffu] ^ (c >> 8);
+        c = tab[c & 0xffu] ^ (c >> 8);
+    }
+    p = reinterpret_cast<const uint8_t*>(w);
+    for (; n; n--) c = tab[(c ^ *p++) & 0xffu] ^ (c >> 8);
     return ~c;
 }
 
@@ -1192,10 +1207,12 @@ struct DecStream {
     FwdReader in;
     unsigned long long poff;
     uint32_t plen, cur, st;  // st bit 0: the payload ran out / is malformed
-    __device__ __forceinline__ uint32_t next() { return in.get(poff + cur++); }
+    __device__ __forceinline__ uint32_t next() {
+        cur++;
+        return in.get();
+    }
     __device__ __forceinline__ void begin(const uint8_t* payload, unsigned long long off, uint32_t len) {
-        in.init(payload);
-        in.prime(off);
+        in.start(payload + off);
         poff = off;
         plen = len;
         cur = 0;
@@ -1240,8 +1257,10 @@ __device__ __forceinline__ void decode_read_body(const ModelDev& ma, const Model
         uint32_t va = acid_find(pk, slot_a, start, freq);
         D.xa = freq * (D.xa >> kScaleBits) + slot_a - start;
         // renorm_all: state 0 then state 1; at most two bytes each (x >= 2^9 after the advance)
-        while (D.xq < kRansL && D.cur < D.plen) D.xq = (D.xq << 8) | D.next();
-        while (D.xa < kRansL && D.cur < D.plen) D.xa = (D.xa << 8) | D.next();
+        if (D.xq < kRansL && D.cur < D.plen) D.xq = (D.xq << 8) | D.next();
+        if (D.xq < kRansL && D.cur < D.plen) D.xq = (D.xq << 8) | D.next();
+        if (D.xa < kRansL && D.cur < D.plen) D.xa = (D.xa << 8) | D.next();
+        if (D.xa < kRansL && D.cur < D.plen) D.xa = (D.xa << 8) | D.next();
         if (D.xq < kRansL || D.xa < kRansL) D.st |= 1;  // the payload ran out
         oa.push(va);
         oq.push(vq);

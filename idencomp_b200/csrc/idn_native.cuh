@@ -122,7 +122,7 @@ encode_lane_kernel(EncodeLaneArgs A, const ModelDev MA, const ModelDev MQ) {
         encode_read_body(ma, mq, A.acids, A.quals, off, len, S);
     }
     S.flush();
-    A.lane_len[l] = S.total;
+    A.lane_len[l] = S.total();
     if (S.bad) atomicOr(A.err, 1u);
 }
 
