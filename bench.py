@@ -703,7 +703,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="hiseq100", choices=sorted(WORKLOADS))
     ap.add_argument("--reads", type=int, default=0, help="reads per GPU (default: the workload's)")
-    ap.add_argument("--chunk-blocks", type=int, default=256, help="blocks per library call")
+    ap.add_argument("--chunk-blocks", type=int, default=1024, help="blocks per library call of the device-resident leg")
     ap.add_argument("--full-bound", action="store_true", help="size container chunks by idn_gpu_compress_bound")
     ap.add_argument("--cpu-blocks", type=int, default=0, help="blocks in the CPU sample (default 2 per core)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
