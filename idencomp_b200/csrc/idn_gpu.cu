@@ -568,22 +568,17 @@ static int32_t upload_small(idn_gpu_ctx* ctx, const SmallParams& sp, cudaStream_
     return IDN_OK;
 }
 
-// K2 over `n` models (slots ids[0..n)): packs of up to 8 models per launch, columns col0.. of the [reads][n_cols] matrix
+// K2 over `n` models (slots ids[0..n)): packs of up to 4 models per launch (measured: 4 per pass at 56 registers beats 8
+// per pass at 85 by 1.36x, 2 per pass ties), columns col0.. of the [reads][n_cols] matrix
 static int32_t launch_score(idn_gpu_ctx* ctx, const int32_t* ids, uint32_t n, const idn_batch* batch, uint32_t n_cols,
                             uint32_t* sizes, uint32_t* err, cudaStream_t st) {
     const uint64_t R = batch->n_reads;
     const unsigned grid = (unsigned)((R + 127) / 128);
     for (uint32_t k0 = 0; k0 < n;) {
-        uint32_t left = n - k0;
-        if (left > 4) {
-            ModelPack<8> P;
-            P.n = left < 8 ? left : 8;
-            for (uint32_t k = 0; k < 8; k++) P.m[k] = ctx->slots[ids[k0 + (k < P.n ? k : 0)]].dev;
-            score_multi_kernel<8><<<grid, 128, 0, st>>>(P, batch->acids, batch->quals, batch->read_off, R, n_cols, k0, sizes, err);
-            k0 += P.n;
-        } else if (left > 2) {
+        const uint32_t left = n - k0;
+        if (left > 2) {
             ModelPack<4> P;
-            P.n = left;
+            P.n = left < 4 ? left : 4;
             for (uint32_t k = 0; k < 4; k++) P.m[k] = ctx->slots[ids[k0 + (k < P.n ? k : 0)]].dev;
             score_multi_kernel<4><<<grid, 128, 0, st>>>(P, batch->acids, batch->quals, batch->read_off, R, n_cols, k0, sizes, err);
             k0 += P.n;
