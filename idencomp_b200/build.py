@@ -33,7 +33,7 @@ def build_gpu(force: bool = False, verbose: bool = False) -> Path:
     out = PKG / "libidn_gpu.so"
     srcs = [CSRC / "idn_gpu.cu", *sorted(CSRC.glob("*.cuh")), ROOT / "include" / "idn_gpu.h"]
     if force or _stale(out, srcs):
-        cmd = [_nvcc(), *NVCC_FLAGS, "-o", str(out), str(CSRC / "idn_gpu.cu")]
+        cmd = [_nvcc(), *NVCC_FLAGS, *os.environ.get("IDN_NVCC_EXTRA", "").split(), "-o", str(out), str(CSRC / "idn_gpu.cu")]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
         subprocess.run(cmd, check=True)

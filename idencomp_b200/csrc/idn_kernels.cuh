@@ -414,8 +414,14 @@ __device__ __forceinline__ void encode_read_body(const ModelDev& ma, const Model
 
 // kUniform: every read of the batch uses the same model pair; its parameters then live in the kernel parameter
 // space (constant bank operands) instead of ~40 registers per thread, which is what bounds occupancy here.
+#ifndef IDN_ENC_MINB
+#define IDN_ENC_MINB 1
+#endif
+#ifndef IDN_DEC_MINB
+#define IDN_DEC_MINB 1
+#endif
 template <bool kUniform>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, IDN_ENC_MINB)
 encode_kernel(EncodeArgs A, const ModelDev MA, const ModelDev MQ) {
     uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= A.n_reads) return;
@@ -1272,7 +1278,7 @@ __device__ __forceinline__ void decode_read_body(const ModelDev& ma, const Model
 }
 
 template <bool kUniform>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, IDN_DEC_MINB)
 decode_kernel(DecodeArgs A, const ModelDev MA, const ModelDev MQ) {
     uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (A.status && A.status[0] != 0) return;
