@@ -31,7 +31,7 @@ constexpr int kQRowBytes = kQLutBytes + kQGroups * 16;  // 512
 struct Magic {
     uint32_t m, s;
 };
-__host__ inline Magic make_magic(uint32_t d) {
+__host__ __device__ constexpr Magic make_magic(uint32_t d) {
     Magic f{0, 0};
     if (d <= 1) return f;
     if ((d & (d - 1)) == 0) {
@@ -66,6 +66,101 @@ struct SpecDev {
     uint32_t pb;      // position bits
     // symbol mapping (LightContextSpecGenerator::update, context_spec.rs:516-529): generic asub = 0, qmul = 2^20
     uint32_t asub, qmul, light;
+};
+
+// ---- generator parameters from (kind, acid order, q order, position bits, q max)   context_spec.rs:218-529 ----
+// constexpr so that the same code builds the run-time tables (idn_gpu_model_upload) and the compile-time constants of
+// the kernels specialised for the spec types of the bundled models (StaticSpecs below).
+struct SpecBuild {
+    SpecDev spec;
+    uint32_t total_bits;
+    bool ok;
+};
+
+__host__ __device__ constexpr uint64_t spec_ipow(uint64_t b, uint32_t n) {
+    uint64_t r = 1;
+    while (n--) r *= b;
+    return r;
+}
+__host__ __device__ constexpr uint32_t spec_bitlen(uint64_t v) {  // IntQueue::num_bits (int_queue.rs:40-43) of v = B^n - 1
+    uint32_t n = 0;
+    while (v) {
+        n++;
+        v >>= 1;
+    }
+    return n;
+}
+
+// IntQueue<B, n> constants for the branch-free push / slide; returns false when B^n does not fit
+__host__ __device__ constexpr bool make_queue(uint32_t base, uint32_t order, QueueDev& q, uint32_t& bits) {
+    q = QueueDev{0, 0, 0, 0, 0, 0, 0, 0, order};
+    uint64_t pw = spec_ipow(base, order);  // B^n
+    if (pw > (1ull << 31)) return false;
+    bits = spec_bitlen(pw - 1);
+    if (order == 0) return true;  // everything 0: the state stays 0
+    q.vmul = 1;
+    uint32_t M = (uint32_t)spec_ipow(base, order - 1);
+    q.powmul = M;
+    Magic mb = make_magic(base);  // base >= 2 whenever order >= 1 (light qmax = 1 is handled by the caller)
+    q.mb = mb.m;
+    q.shb = mb.s;
+    if (order >= 2) {
+        q.B = base;
+        Magic mm = make_magic(M);
+        q.m = mm.m;
+        q.sh = mm.s;
+        q.MB = (uint32_t)((uint64_t)M * base);
+    }
+    return true;
+}
+
+__host__ __device__ constexpr SpecBuild make_spec(int kind, int ao, int qo, int pb, int qmax) {
+    SpecBuild r{SpecDev{QueueDev{0, 0, 0, 0, 0, 0, 0, 0, 0}, QueueDev{0, 0, 0, 0, 0, 0, 0, 0, 0}, 0, 0, 0, 0, 0}, 0, false};
+    if (kind != 0 && kind != 1) return r;  // IDN_SPEC_GENERIC / IDN_SPEC_LIGHT
+    if (ao < 0 || ao > kHist || qo < 0 || qo > kHist || pb < 0 || pb > 16) return r;
+    SpecDev& s = r.spec;
+    s.pb = (uint32_t)pb;
+    s.light = kind == 1;
+    uint32_t base_a = 5, base_q = 94;
+    s.asub = 0;
+    s.qmul = 1u << 20;
+    if (s.light) {
+        if (qmax < 1 || qmax > 94) return r;
+        base_a = 4;
+        base_q = (uint32_t)qmax;
+        s.asub = 1;
+        s.qmul = (uint32_t)qmax * 11156u;
+        for (uint32_t q = 0; q < 94; q++)  // the multiply-shift in map_syms must equal q*qmax/94
+            if (((q * s.qmul) >> 20) != q * (uint32_t)qmax / 94) return r;
+    }
+    uint32_t qbits = 0;
+    if (!make_queue(base_a, (uint32_t)ao, s.qa, s.abits)) return r;
+    if (base_q == 1) {
+        // IntQueue<1, n>: every digit is 0 and the state stays 0 (light qmax = 1, e.g. light_ao8_qo0_pb0_qm1)
+        s.qq = QueueDev{0, 0, 0, 0, 0, 0, 0, 0, (uint32_t)qo};
+        qbits = 0;
+    } else if (!make_queue(base_q, (uint32_t)qo, s.qq, qbits)) {
+        return r;
+    }
+    if (s.abits + qbits + s.pb > 31) return r;
+    r.total_bits = s.abits + qbits + s.pb;
+    r.ok = true;
+    return r;
+}
+
+// Spec policies of the codec kernels: DynSpecs reads the generator parameters from the model (any legal spec type);
+// StaticSpecs<...> makes them compile-time constants for one (acid spec, q spec) pair, which turns the generic
+// multiply/reciprocal queue arithmetic into shifts and masks and deletes what the pair does not use.
+struct DynSpecs {
+    static constexpr bool kStatic = false;
+    __host__ __device__ static constexpr SpecDev sa() { return make_spec(0, 0, 0, 0, 0).spec; }
+    __host__ __device__ static constexpr SpecDev sq() { return make_spec(0, 0, 0, 0, 0).spec; }
+};
+template <int KA, int AOA, int QOA, int PBA, int QMA, int KQ, int AOQ, int QOQ, int PBQ, int QMQ>
+struct StaticSpecs {
+    static constexpr bool kStatic = true;
+    __host__ __device__ static constexpr SpecDev sa() { return make_spec(KA, AOA, QOA, PBA, QMA).spec; }
+    __host__ __device__ static constexpr SpecDev sq() { return make_spec(KQ, AOQ, QOQ, PBQ, QMQ).spec; }
 };
 
 struct ModelDev {

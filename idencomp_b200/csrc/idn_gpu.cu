@@ -49,6 +49,7 @@ struct DevBuf {
 
 struct ModelSlot {
     bool used = false;
+    int32_t spec_tuple[5] = {0, 0, 0, 0, 0};  // kind, acid order, q order, position bits, q max
     ModelDev dev{};
     void* d_map = nullptr;
     void* d_hkeys = nullptr;
@@ -190,78 +191,6 @@ struct HostTimer {
     }
 };
 
-uint32_t bitlen(uint64_t v) {
-    uint32_t n = 0;
-    while (v) {
-        n++;
-        v >>= 1;
-    }
-    return n;
-}
-uint64_t ipow(uint64_t b, uint32_t n) {
-    uint64_t r = 1;
-    while (n--) r *= b;
-    return r;
-}
-
-// IntQueue<B, n> constants for the branch-free push / slide of idn_device.cuh
-bool make_queue(uint32_t base, uint32_t order, QueueDev* q, uint32_t* bits) {
-    memset(q, 0, sizeof *q);
-    q->depth = order;
-    uint64_t pw = ipow(base, order);  // B^n
-    if (pw > (1ull << 31)) return false;
-    *bits = bitlen(pw - 1);  // IntQueue::num_bits (int_queue.rs:40-43)
-    if (order == 0) return true;  // everything 0: the state stays 0
-    q->vmul = 1;
-    uint32_t M = (uint32_t)ipow(base, order - 1);
-    q->powmul = M;
-    Magic mb = make_magic(base);  // base >= 2 whenever order >= 1 (light qmax = 1 is handled by the caller)
-    q->mb = mb.m;
-    q->shb = mb.s;
-    if (order >= 2) {
-        q->B = base;
-        Magic mm = make_magic(M);
-        q->m = mm.m;
-        q->sh = mm.s;
-        q->MB = (uint32_t)((uint64_t)M * base);
-    }
-    return true;
-}
-
-// generator parameters (context_spec.rs:218-529)
-bool make_spec(int32_t kind, int32_t ao, int32_t qo, int32_t pb, int32_t qmax, SpecDev* s, uint32_t* total_bits) {
-    if (kind != IDN_SPEC_GENERIC && kind != IDN_SPEC_LIGHT) return false;
-    if (ao < 0 || ao > kHist || qo < 0 || qo > kHist || pb < 0 || pb > 16) return false;
-    memset(s, 0, sizeof *s);
-    s->pb = (uint32_t)pb;
-    s->light = kind == IDN_SPEC_LIGHT;
-    uint32_t base_a = 5, base_q = 94;
-    s->asub = 0;
-    s->qmul = 1u << 20;
-    if (s->light) {
-        if (qmax < 1 || qmax > 94) return false;
-        base_a = 4;
-        base_q = (uint32_t)qmax;
-        s->asub = 1;
-        s->qmul = (uint32_t)qmax * 11156u;
-        for (uint32_t q = 0; q < 94; q++)  // the multiply-shift in map_syms must equal q*qmax/94
-            if (((q * s->qmul) >> 20) != q * (uint32_t)qmax / 94) return false;
-    }
-    uint32_t qbits = 0;
-    if (!make_queue(base_a, (uint32_t)ao, &s->qa, &s->abits)) return false;
-    if (base_q == 1) {
-        // IntQueue<1, n>: every digit is 0 and the state stays 0 (light qmax = 1, e.g. light_ao8_qo0_pb0_qm1)
-        memset(&s->qq, 0, sizeof s->qq);
-        s->qq.depth = (uint32_t)qo;
-        qbits = 0;
-    } else if (!make_queue(base_q, (uint32_t)qo, &s->qq, &qbits)) {
-        return false;
-    }
-    if (s->abits + qbits + s->pb > 31) return false;
-    *total_bits = s->abits + qbits + s->pb;
-    return true;
-}
-
 uint32_t host_hash32(uint32_t k) {
     k ^= k >> 16;
     k *= 0x7feb352dU;
@@ -308,6 +237,39 @@ struct SmallParams {
 };
 
 }  // namespace
+
+// Kernels specialised at compile time for the (acid spec type, q-score spec type) pairs of the bundled same-sequencer
+// model files; every other pair runs the run-time-generic kernels (DynSpecs).  kind: 0 generic, 1 light.
+//                          acids: kind ao qo pb qm      q-scores: kind ao qo pb qm
+using SP0 = StaticSpecs<1, 8, 0, 0, 1, 0, 0, 2, 6, 0>;   // light_ao8_qo0_pb0_qm1  + generic_ao0_qo2_pb6   (HiSeq: ERR174310, SRR2962693)
+using SP1 = StaticSpecs<1, 8, 0, 0, 1, 0, 2, 1, 6, 0>;   // light_ao8_qo0_pb0_qm1  + generic_ao2_qo1_pb6   (NovaSeq: SRR8861483)
+using SP2 = StaticSpecs<0, 8, 0, 0, 0, 1, 0, 4, 0, 16>;  // generic_ao8_qo0_pb0    + light_ao0_qo4_pb0_qm16 (Sequel II: m64187e)
+using SP3 = StaticSpecs<1, 4, 3, 2, 8, 1, 0, 4, 3, 16>;  // light_ao4_qo3_pb2_qm8  + light_ao0_qo4_pb3_qm16 (NovaSeq: SRR18908372)
+using SP4 = StaticSpecs<0, 4, 1, 2, 0, 1, 0, 4, 3, 16>;  // generic_ao4_qo1_pb2    + light_ao0_qo4_pb3_qm16 (HiSeq 2500: SRR5373739)
+static const int32_t kStaticPairs[5][10] = {
+    {1, 8, 0, 0, 1, 0, 0, 2, 6, 0}, {1, 8, 0, 0, 1, 0, 2, 1, 6, 0}, {0, 8, 0, 0, 0, 1, 0, 4, 0, 16},
+    {1, 4, 3, 2, 8, 1, 0, 4, 3, 16}, {0, 4, 1, 2, 0, 1, 0, 4, 3, 16}};
+
+static int static_pair_index(const idn_gpu_ctx* ctx, int32_t acid_slot, int32_t q_slot) {
+    for (int i = 0; i < 5; i++) {
+        bool same = true;
+        for (int k = 0; k < 5; k++)
+            same = same && ctx->slots[acid_slot].spec_tuple[k] == kStaticPairs[i][k] && ctx->slots[q_slot].spec_tuple[k] == kStaticPairs[i][5 + k];
+        if (same) return i;
+    }
+    return -1;
+}
+
+// launch KERNEL<true, SPi> for a specialised pair, KERNEL<true, DynSpecs> otherwise
+#define IDN_LAUNCH_UNIFORM(idx, KERNEL, grid, st, ...)                                         \
+    switch (idx) {                                                                             \
+        case 0: KERNEL<true, SP0><<<grid, 128, 0, st>>>(__VA_ARGS__); break;                   \
+        case 1: KERNEL<true, SP1><<<grid, 128, 0, st>>>(__VA_ARGS__); break;                   \
+        case 2: KERNEL<true, SP2><<<grid, 128, 0, st>>>(__VA_ARGS__); break;                   \
+        case 3: KERNEL<true, SP3><<<grid, 128, 0, st>>>(__VA_ARGS__); break;                   \
+        case 4: KERNEL<true, SP4><<<grid, 128, 0, st>>>(__VA_ARGS__); break;                   \
+        default: KERNEL<true, DynSpecs><<<grid, 128, 0, st>>>(__VA_ARGS__); break;             \
+    }
 
 // ======================================================================================================
 // lifecycle
@@ -417,9 +379,10 @@ extern "C" int32_t idn_gpu_model_upload(idn_gpu_ctx* ctx, int32_t model_type, in
     if (n_ctx > 65535) return fail(ctx, IDN_E_UNSUPPORTED, "model has %u contexts (limit 65535)", n_ctx);
     if (n_specs && (!spec_keys || !spec_ctx)) return fail(ctx, IDN_E_INVALID_ARG, "NULL spec table");
     CU(cudaSetDevice(ctx->device));
-    SpecDev spec;
-    uint32_t bits = 0;
-    if (!make_spec(spec_kind, acid_order, q_order, pos_bits, q_max, &spec, &bits))
+    const SpecBuild sb = make_spec(spec_kind, acid_order, q_order, pos_bits, q_max);
+    const SpecDev spec = sb.spec;
+    const uint32_t bits = sb.total_bits;
+    if (!sb.ok)
         return fail(ctx, IDN_E_UNSUPPORTED, "unsupported context spec type (kind %d ao %d qo %d pb %d qmax %d)", spec_kind,
                     acid_order, q_order, pos_bits, q_max);
     const uint64_t spec_num = 1ull << bits;
@@ -441,6 +404,11 @@ extern "C" int32_t idn_gpu_model_upload(idn_gpu_ctx* ctx, int32_t model_type, in
 
     ModelSlot slot;
     slot.dev.spec = spec;
+    slot.spec_tuple[0] = spec_kind;
+    slot.spec_tuple[1] = acid_order;
+    slot.spec_tuple[2] = q_order;
+    slot.spec_tuple[3] = pos_bits;
+    slot.spec_tuple[4] = spec_kind == IDN_SPEC_LIGHT ? q_max : 0;
     slot.dev.type = (uint32_t)model_type;
     slot.dev.nsym = nsym;
     slot.dev.n_rows = n_rows;
@@ -755,8 +723,12 @@ extern "C" int32_t idn_gpu_compress_blocks_dev(idn_gpu_ctx* ctx, const idn_batch
         const bool uniform = !chosen || (sp.n_cand[0] == 1 && sp.n_cand[1] == 1);
         const ModelDev& hma = ctx->slots[sp.cand_model[0]].dev;
         const ModelDev& hmq = ctx->slots[sp.cand_model[kMaxCand]].dev;
-        if (uniform) encode_kernel<true><<<(unsigned)((R + 127) / 128), 128, 0, st>>>(ea, hma, hmq);
-        else encode_kernel<false><<<(unsigned)((R + 127) / 128), 128, 0, st>>>(ea, hma, hmq);
+        const unsigned egrid = (unsigned)((R + 127) / 128);
+        if (uniform) {
+            IDN_LAUNCH_UNIFORM(static_pair_index(ctx, sp.cand_model[0], sp.cand_model[kMaxCand]), encode_kernel, egrid, st, ea, hma, hmq)
+        } else {
+            encode_kernel<false, DynSpecs><<<egrid, 128, 0, st>>>(ea, hma, hmq);
+        }
         LAUNCHED("encode");
     }
 
@@ -947,8 +919,11 @@ static int32_t compress_native_dev(idn_gpu_ctx* ctx, const idn_batch* batch, Sma
         const ModelDev& hma = ctx->slots[sp.cand_model[0]].dev;
         const ModelDev& hmq = ctx->slots[sp.cand_model[kMaxCand]].dev;
         const unsigned grid = (unsigned)((lane_cap + 127) / 128);
-        if (uniform) encode_lane_kernel<true><<<grid, 128, 0, st>>>(ea, hma, hmq);
-        else encode_lane_kernel<false><<<grid, 128, 0, st>>>(ea, hma, hmq);
+        if (uniform) {
+            IDN_LAUNCH_UNIFORM(static_pair_index(ctx, sp.cand_model[0], sp.cand_model[kMaxCand]), encode_lane_kernel, grid, st, ea, hma, hmq)
+        } else {
+            encode_lane_kernel<false, DynSpecs><<<grid, 128, 0, st>>>(ea, hma, hmq);
+        }
         LAUNCHED("encode_lane");
     }
     LaneLenFn ll{lane_len, n_lanes_dev};
@@ -1250,8 +1225,11 @@ static int32_t decompress_native_dev(idn_gpu_ctx* ctx, const uint8_t* blocks, co
             if (ctx->slots[models[i]].dev.type == IDN_MODEL_ACID) { ua = models[i]; na++; } else { uq = models[i]; nq++; }
         }
         const unsigned grid = (unsigned)((out_reads_cap + 127) / 128);
-        if (na == 1 && nq == 1) decode_lane_kernel<true><<<grid, 128, 0, st>>>(da, ctx->slots[ua].dev, ctx->slots[uq].dev);
-        else decode_lane_kernel<false><<<grid, 128, 0, st>>>(da, ctx->d_models_host0, ctx->d_models_host0);
+        if (na == 1 && nq == 1) {
+            IDN_LAUNCH_UNIFORM(static_pair_index(ctx, ua, uq), decode_lane_kernel, grid, st, da, ctx->slots[ua].dev, ctx->slots[uq].dev)
+        } else {
+            decode_lane_kernel<false, DynSpecs><<<grid, 128, 0, st>>>(da, ctx->d_models_host0, ctx->d_models_host0);
+        }
         LAUNCHED("decode_lane");
     }
     if (block_crc && out_reads_cap) {
@@ -1338,8 +1316,11 @@ extern "C" int32_t idn_gpu_decompress_blocks_dev(idn_gpu_ctx* ctx, const uint8_t
             if (ctx->slots[models[i]].dev.type == IDN_MODEL_ACID) { ua = models[i]; na++; } else { uq = models[i]; nq++; }
         }
         const unsigned grid = (unsigned)((out_reads_cap + 127) / 128);
-        if (na == 1 && nq == 1) decode_kernel<true><<<grid, 128, 0, st>>>(da, ctx->slots[ua].dev, ctx->slots[uq].dev);
-        else decode_kernel<false><<<grid, 128, 0, st>>>(da, ctx->d_models_host0, ctx->d_models_host0);
+        if (na == 1 && nq == 1) {
+            IDN_LAUNCH_UNIFORM(static_pair_index(ctx, ua, uq), decode_kernel, grid, st, da, ctx->slots[ua].dev, ctx->slots[uq].dev)
+        } else {
+            decode_kernel<false, DynSpecs><<<grid, 128, 0, st>>>(da, ctx->d_models_host0, ctx->d_models_host0);
+        }
         LAUNCHED("decode");
     }
     // CRC of the decoded symbols per block, compared with the header value (decompressor_block.rs:131-144)
@@ -1600,7 +1581,7 @@ extern "C" int32_t idn_gpu_decompress_reads(idn_gpu_ctx* ctx, const uint8_t* pay
     da.read_off_out = nullptr;
     da.read_status = ctx->s_idx.as<uint32_t>();
     da.err = &dsp->err;
-    decode_kernel<false><<<(unsigned)((R + 127) / 128), 128, 0, st>>>(da, ctx->d_models_host0, ctx->d_models_host0);
+    decode_kernel<false, DynSpecs><<<(unsigned)((R + 127) / 128), 128, 0, st>>>(da, ctx->d_models_host0, ctx->d_models_host0);
     LAUNCHED("decode");
     uint32_t err = 0;
     if (S) {

@@ -332,10 +332,12 @@ struct EncStream {
 // The loop is software-pipelined over three positions because only the 32-bit rANS states are serial in the encoder:
 // while position i is coded, the encoder entry of position i-1 is being gathered and the context row of position i-2
 // is being looked up, so the two dependent L2 gathers per symbol (spec -> row -> entry) overlap with arithmetic.
+template <class P>
 __device__ __forceinline__ void encode_read_body(const ModelDev& ma, const ModelDev& mq, const uint8_t* __restrict__ acids,
                                                  const uint8_t* __restrict__ quals, long long off, uint32_t len, EncStream& S) {
-    const SpecDev& sa = ma.spec;
-    const SpecDev& sq = mq.spec;
+    constexpr SpecDev ksa = P::sa(), ksq = P::sq();  // compile-time generator parameters of a specialised pair
+    const SpecDev& sa = P::kStatic ? ksa : ma.spec;
+    const SpecDev& sq = P::kStatic ? ksq : mq.spec;
     BackReader ra, rq;
     ra.start(acids + off + len - 1);  // nothing is loaded before the first get()
     rq.start(quals + off + len - 1);
@@ -420,7 +422,7 @@ __device__ __forceinline__ void encode_read_body(const ModelDev& ma, const Model
 #ifndef IDN_DEC_MINB
 #define IDN_DEC_MINB 1
 #endif
-template <bool kUniform>
+template <bool kUniform, class P>
 __global__ void __launch_bounds__(128, IDN_ENC_MINB)
 encode_kernel(EncodeArgs A, const ModelDev MA, const ModelDev MQ) {
     uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -436,7 +438,7 @@ encode_kernel(EncodeArgs A, const ModelDev MA, const ModelDev MQ) {
     const uint32_t len = (uint32_t)(A.read_off[r + 1] - A.read_off[r]);
     EncStream S;
     S.begin(A.scratch + 4ull * A.read_off[r + 1] + 8ull * (r + 1));
-    encode_read_body(ma, mq, A.acids, A.quals, off, len, S);
+    encode_read_body<P>(ma, mq, A.acids, A.quals, off, len, S);
     S.flush();
     A.pay_len[r] = S.total();
     if (S.bad) atomicOr(A.err, 1u);
@@ -1240,10 +1242,12 @@ struct DecStream {
 };
 
 // Pops one read (positions 0 .. len-1) from the stream   SequenceDecompressor::decompress, sequence_compressor.rs:231-278
+template <class P>
 __device__ __forceinline__ void decode_read_body(const ModelDev& ma, const ModelDev& mq, uint32_t len, DecStream& D,
                                                  FwdWriter& oa, FwdWriter& oq) {
-    const SpecDev& sa = ma.spec;
-    const SpecDev& sq = mq.spec;
+    constexpr SpecDev ksa = P::sa(), ksq = P::sq();
+    const SpecDev& sa = P::kStatic ? ksa : ma.spec;
+    const SpecDev& sq = P::kStatic ? ksq : mq.spec;
     GenFwd ga, gq;
     ga.init();
     gq.init();
@@ -1277,7 +1281,7 @@ __device__ __forceinline__ void decode_read_body(const ModelDev& ma, const Model
     }
 }
 
-template <bool kUniform>
+template <bool kUniform, class P>
 __global__ void __launch_bounds__(128, IDN_DEC_MINB)
 decode_kernel(DecodeArgs A, const ModelDev MA, const ModelDev MQ) {
     uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -1307,7 +1311,7 @@ decode_kernel(DecodeArgs A, const ModelDev MA, const ModelDev MQ) {
     FwdWriter oa, oq;
     oa.init(A.acids_out + ooff);
     oq.init(A.quals_out + ooff);
-    decode_read_body(ma, mq, len, D, oa, oq);
+    decode_read_body<P>(ma, mq, len, D, oa, oq);
     oa.finish();
     oq.finish();
     uint32_t st = D.st;

@@ -100,7 +100,7 @@ struct EncodeLaneArgs {
     uint32_t* err;
 };
 
-template <bool kUniform>
+template <bool kUniform, class P>
 __global__ void __launch_bounds__(128)
 encode_lane_kernel(EncodeLaneArgs A, const ModelDev MA, const ModelDev MQ) {
     uint64_t l = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -119,7 +119,7 @@ encode_lane_kernel(EncodeLaneArgs A, const ModelDev MA, const ModelDev MQ) {
     for (uint32_t r = r1; r-- > r0;) {
         const long long off = (long long)A.read_off[r];
         const uint32_t len = (uint32_t)(A.read_off[r + 1] - A.read_off[r]);
-        encode_read_body(ma, mq, A.acids, A.quals, off, len, S);
+        encode_read_body<P>(ma, mq, A.acids, A.quals, off, len, S);
     }
     S.flush();
     A.lane_len[l] = S.total();
@@ -521,7 +521,7 @@ struct DecodeLaneArgs {
     uint32_t* err;
 };
 
-template <bool kUniform>
+template <bool kUniform, class P>
 __global__ void __launch_bounds__(128)
 decode_lane_kernel(DecodeLaneArgs A, const ModelDev MA, const ModelDev MQ) {
     uint64_t l = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -539,7 +539,7 @@ decode_lane_kernel(DecodeLaneArgs A, const ModelDev MA, const ModelDev MQ) {
 #pragma unroll 1
     for (unsigned long long r = r0; r < r1 && !(D.st & 1); r++) {
         unsigned long long o_next = A.read_off[r + 1];
-        decode_read_body(ma, mq, (uint32_t)(o_next - o), D, oa, oq);
+        decode_read_body<P>(ma, mq, (uint32_t)(o_next - o), D, oa, oq);
         o = o_next;
     }
     oa.finish();
