@@ -703,6 +703,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="hiseq100", choices=sorted(WORKLOADS))
     ap.add_argument("--reads", type=int, default=0, help="reads per GPU (default: the workload's)")
+    ap.add_argument("--acid", default="", help="acid model (file stem in models/) instead of the workload's")
+    ap.add_argument("--q", default="", help="quality score model (file stem in models/) instead of the workload's")
     ap.add_argument("--chunk-blocks", type=int, default=1024, help="blocks per library call of the device-resident leg")
     ap.add_argument("--full-bound", action="store_true", help="size container chunks by idn_gpu_compress_bound")
     ap.add_argument("--cpu-blocks", type=int, default=0, help="blocks in the CPU sample (default 2 per core)")
@@ -720,7 +722,10 @@ def main():
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
-    w = WORKLOADS[args.workload]
+    w = dict(WORKLOADS[args.workload])
+    if args.acid or args.q:
+        w["acid"], w["q"] = args.acid or w["acid"], args.q or w["q"]
+        w["desc"] += f" [models overridden: {w['acid']} + {w['q']}]"
     if args.impl == "reference":
         run_reference(args, w)
     else:
