@@ -485,3 +485,39 @@ def test_large_device_round_trip_properties(gctx, O, bundled, mode):
         data, ocrc = O.compress_native_block([am, qm], sub, 0, r1 - r0, lane_syms=2048, include_identifiers=False)
     lo_b, hi_b = int(boff[k]), int(boff[k + 1])
     assert out[lo_b + 8:hi_b].cpu().numpy().tobytes() == data and (int(crc[k]) & 0xffffffff) == ocrc
+
+
+def test_walk_speculation_survives_header_lookalikes(gctx, O, toy_models, toy_handles):
+    """The slice walk speculates on slice boundaries inside a tile.  Identifier slices full of bytes that look like
+    slice headers (02 00 00 00 0c 00 00 00 01 ..., 01 00, 00 00 00 00 03 01) must not derail it: a false boundary is
+    dropped when the true chain does not end there."""
+    rng = np.random.default_rng(3)
+    bait = (b"\x02\x00\x00\x00\x0c\x00\x00\x00\x01" + b"\x01\x00" * 6 + b"\x00\x00\x00\x00\x03\x01abc" + b"\x01\x01") * 40
+    seqs = []
+    for i in range(400):
+        ln = int(rng.integers(20, 120))
+        seqs.append((bait[i % 7:i % 7 + 30 + (i % 50)], rng.integers(0, 5, size=ln), rng.integers(0, 94, size=ln)))
+    reads = O.Reads.from_lists(seqs)
+    idn = O.compress(toy_models, reads, max_block_total_len=12000, include_identifiers=True)
+    # store the names slices uncompressed-looking: replace every Identifiers slice by one whose DATA is the bait itself
+    # (the device skips identifier data by length, whatever its bytes are)
+    pos, parts, blocks = 9 + 3 + 64, [], []
+    while True:
+        ln = int.from_bytes(idn[pos:pos + 4], "big")
+        crc = int.from_bytes(idn[pos + 4:pos + 8], "big")
+        if ln == 0:
+            break
+        body = idn[pos + 8:pos + 8 + ln]
+        assert body[0] == 0
+        nlen = int.from_bytes(body[1:5], "big")
+        fake = bait[:9000]
+        new_body = b"\x00" + len(fake).to_bytes(4, "big") + b"\x01" + fake + body[6 + nlen:]
+        blocks.append((len(b"".join(parts)) , len(new_body), crc))
+        parts.append(new_body)
+        pos += 8 + ln
+    buf = np.frombuffer(b"".join(parts), dtype=np.uint8)
+    doff = np.asarray([b[0] for b in blocks] + [len(buf)], dtype=np.uint64)
+    dlen = np.asarray([b[1] for b in blocks], dtype=np.uint32)
+    crc = np.asarray([b[2] for b in blocks], dtype=np.uint32)
+    ro, a, q = gctx.decompress_blocks(buf, doff, crc, toy_handles, block_len=dlen, name_off=reads.name_off, names=reads.names)
+    assert np.array_equal(ro, reads.read_off) and np.array_equal(a, reads.acids) and np.array_equal(q, reads.quals)
