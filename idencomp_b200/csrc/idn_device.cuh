@@ -184,8 +184,10 @@ __device__ __forceinline__ uint32_t hash32(uint32_t k) {
 }
 
 // RansEncModel/RansDecModel::context_for  (sequence_compressor.rs:60-62, 203-205)
+// kDense: the caller guarantees the dense table (the specialised kernels are only launched for such models)
+template <bool kDense = false>
 __device__ __forceinline__ uint32_t ctx_row(const ModelDev& m, uint32_t spec) {
-    if (m.map) return __ldg(m.map + spec);
+    if (kDense || m.map) return __ldg(m.map + spec);
     if (!m.hkeys) return 0;  // model without contexts
     uint32_t h = hash32(spec) & m.hmask;
     for (;;) {
@@ -262,6 +264,7 @@ struct GenFwd {
     __device__ __forceinline__ void init() { sa = sq = 0; }
     // pos_shared = PosFwd::pos at pbmax, pshift = pbmax - s.pb
     __device__ __forceinline__ uint32_t spec(const SpecDev& s, uint32_t pos_shared, uint32_t pshift) const {
+        if (s.pb == 0) return (sq << s.abits) | sa;  // position(i) < 2^pbmax for i < len: nothing to add
         return (((sq << s.abits) | sa) << s.pb) | (pos_shared >> pshift);
     }
     __device__ __forceinline__ void update(const SpecDev& s, uint32_t a, uint32_t q, bool z) {
@@ -310,6 +313,7 @@ struct GenBack {
         sq = queue_slide_back(s.qq, sq, (uint32_t)(wq >> shq) & 127u);
     }
     __device__ __forceinline__ uint32_t spec(const SpecDev& s, uint32_t pos_shared, uint32_t pshift) const {
+        if (s.pb == 0) return (sq << s.abits) | sa;
         return (((sq << s.abits) | sa) << s.pb) | (pos_shared >> pshift);
     }
 };

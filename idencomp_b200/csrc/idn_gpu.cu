@@ -251,6 +251,8 @@ static const int32_t kStaticPairs[5][10] = {
     {1, 4, 3, 2, 8, 1, 0, 4, 3, 16}, {0, 4, 1, 2, 0, 1, 0, 4, 3, 16}};
 
 static int static_pair_index(const idn_gpu_ctx* ctx, int32_t acid_slot, int32_t q_slot) {
+    // the specialised kernels index the dense spec -> row table without looking (ctx_row<true>)
+    if (!ctx->slots[acid_slot].dev.map || !ctx->slots[q_slot].dev.map) return -1;
     for (int i = 0; i < 5; i++) {
         bool same = true;
         for (int k = 0; k < 5; k++)

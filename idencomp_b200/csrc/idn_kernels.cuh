@@ -1210,41 +1210,104 @@ struct DecodeArgs {
 };
 
 // State of one rANS input stream being consumed (a read in compat mode, a lane in native mode).
+//
+// The payload is read through a 64-bit window: `w` holds the next `bits` (>= 32 at the top of every position) unread
+// payload bits, next byte lowest; one position consumes at most 4 bytes (two per state), so one conditional refill per
+// position suffices, and the word that refill shifts in was loaded one refill earlier (`nextw`), i.e. the payload load
+// is never on the state -> slot -> symbol -> context chain.  Renormalisation is branch-free: the number of bytes a state
+// needs (0, 1 or 2: x >= 2^9 after RansDecAdvanceStep) picks a byte-permute selector that shifts the state and drops
+// the bytes in at once.  Past the end of the payload the window is fed zeros; finish() reports that afterwards.
 struct DecStream {
-    uint32_t xq, xa;  // decoder state 0 = quality scores, state 1 = acids (compressor.rs:181-182)
-    FwdReader in;
-    unsigned long long poff;
-    uint32_t plen, cur, st;  // st bit 0: the payload ran out / is malformed
-    __device__ __forceinline__ uint32_t next() {
-        cur++;
-        return in.get();
+    uint32_t xq, xa;          // decoder state 0 = quality scores, state 1 = acids (compressor.rs:181-182)
+    unsigned long long w;     // unread payload bytes, next byte in bits 0..7
+    uint32_t bits;            // valid bits in w
+    uint32_t nextw;           // the word that follows the window
+    const uint32_t* wp;       // the word after nextw
+    int32_t wleft;            // payload words from wp on (<= 0: past the end, zeros are fed)
+    uint32_t lowest;          // minimum over the renormalised states; < L: the stream is malformed
+    uint32_t st, cur;         // set by finish(): st bit 0 = the payload ran out / is malformed, cur = bytes consumed
+    __device__ __forceinline__ uint32_t load_word() {
+        uint32_t v = 0;
+        if (wleft > 0) v = __ldg(wp);
+        wp++;
+        wleft--;
+        return v;
     }
     __device__ __forceinline__ void begin(const uint8_t* payload, unsigned long long off, uint32_t len) {
-        in.start(payload + off);
-        poff = off;
-        plen = len;
+        const uintptr_t a = reinterpret_cast<uintptr_t>(payload + off);
+        const uint32_t skip = (uint32_t)(a & 3);
+        wp = reinterpret_cast<const uint32_t*>(a - skip);
+        wleft = len < 8 ? 0 : (int32_t)((skip + len + 3) >> 2);  // a valid stream holds at least the two flushed states
+        const uint32_t w0 = load_word(), w1 = load_word(), w2 = load_word();
+        nextw = load_word();
+        const uint32_t sh = 8 * skip;
+        xq = __funnelshift_r(w0, w1, sh);  // RansDecInit x2: little-endian state 0, then state 1
+        xa = __funnelshift_r(w1, w2, sh);
+        w = w2 >> sh;
+        bits = 32 - sh;
+        lowest = 0xffffffffu;
+        st = 0;
         cur = 0;
-        st = len < 8 ? 1u : 0u;  // a valid stream holds at least the two flushed states
-        xq = xa = 0;
-        if (!st) {  // RansDecInit x2
-            xq = next();
-            xq |= next() << 8;
-            xq |= next() << 16;
-            xq |= next() << 24;
-            xa = next();
-            xa |= next() << 8;
-            xa |= next() << 16;
-            xa |= next() << 24;
+    }
+    __device__ __forceinline__ void refill() {
+        if (bits < 32) {
+            w |= (unsigned long long)nextw << bits;
+            bits += 32;
+            nextw = load_word();
         }
     }
+    // RansDecRenorm: while (x < L) x = (x << 8) | *ptr++   -- at most two rounds here
+    __device__ __forceinline__ void renorm(uint32_t& x) {
+        const bool one = x < kRansL, two = x < (1u << 15);
+        const uint32_t sel = two ? 0x5401u : (one ? 0x6540u : 0x7654u);  // [w1 w0 x0 x1] / [w0 x0 x1 x2] / x
+        const uint32_t sh = two ? 16u : (one ? 8u : 0u);
+        x = __byte_perm((uint32_t)w, x, sel);
+        w >>= sh;
+        bits -= sh;
+    }
+    __device__ __forceinline__ void renorm_all() {  // state 0 then state 1 (compressor.rs:188-189)
+        renorm(xq);
+        renorm(xa);
+        lowest = min(lowest, min(xq, xa));
+    }
+    __device__ __forceinline__ void finish(const uint8_t* payload, unsigned long long off, uint32_t len) {
+        const uint32_t skip = (uint32_t)(reinterpret_cast<uintptr_t>(payload + off) & 3);
+        const int32_t nw = len < 8 ? 0 : (int32_t)((skip + len + 3) >> 2);
+        const int32_t in_window = nw - wleft - 1;  // words shifted into the window so far (nextw is not)
+        const int32_t used = 4 * in_window - (int32_t)skip - (int32_t)(bits >> 3);
+        cur = (uint32_t)used;
+        st = (len < 8 || used > (int32_t)len || lowest < kRansL) ? 1u : 0u;
+    }
     // a valid stream ends with both states back at L and every byte consumed
-    __device__ __forceinline__ bool clean_end() const { return xq == kRansL && xa == kRansL && cur == plen; }
+    __device__ __forceinline__ bool clean_end(uint32_t len) const { return xq == kRansL && xa == kRansL && cur == len; }
+};
+
+// Decoded symbols of consecutive positions: whole words once both outputs are word-aligned, bytes at the ragged ends
+struct SymWriter {
+    uint8_t *pa, *pq;
+    __device__ __forceinline__ void init(uint8_t* a, uint8_t* q) {
+        pa = a;
+        pq = q;
+    }
+    __device__ __forceinline__ bool aligned() const {
+        return ((reinterpret_cast<uintptr_t>(pa) | reinterpret_cast<uintptr_t>(pq)) & 3) == 0;
+    }
+    __device__ __forceinline__ void put(uint32_t a, uint32_t q) {
+        *pa++ = (uint8_t)a;
+        *pq++ = (uint8_t)q;
+    }
+    __device__ __forceinline__ void put4(uint32_t wa, uint32_t wq) {
+        *reinterpret_cast<uint32_t*>(pa) = wa;
+        *reinterpret_cast<uint32_t*>(pq) = wq;
+        pa += 4;
+        pq += 4;
+    }
 };
 
 // Pops one read (positions 0 .. len-1) from the stream   SequenceDecompressor::decompress, sequence_compressor.rs:231-278
 template <class P>
 __device__ __forceinline__ void decode_read_body(const ModelDev& ma, const ModelDev& mq, uint32_t len, DecStream& D,
-                                                 FwdWriter& oa, FwdWriter& oq) {
+                                                 SymWriter& O) {
     constexpr SpecDev ksa = P::sa(), ksq = P::sq();
     const SpecDev& sa = P::kStatic ? ksa : ma.spec;
     const SpecDev& sq = P::kStatic ? ksq : mq.spec;
@@ -1255,29 +1318,48 @@ __device__ __forceinline__ void decode_read_body(const ModelDev& ma, const Model
     const uint32_t psa = pbmax - sa.pb, psq = pbmax - sq.pb;
     PosFwd pf;
     pf.init(len, pbmax);
-#pragma unroll 1
-    for (uint32_t i = 0; i < len && !(D.st & 1); i++) {
-        uint32_t row_a = ctx_row(ma, ga.spec(sa, pf.pos, psa));
-        uint32_t row_q = ctx_row(mq, gq.spec(sq, pf.pos, psq));
-        uint32_t slot_q = D.xq & kSlotMask, slot_a = D.xa & kSlotMask;
+    auto step = [&](uint32_t& va, uint32_t& vq) {
+        D.refill();
+        const uint32_t row_a = ctx_row<P::kStatic>(ma, ga.spec(sa, pf.pos, psa));
+        const uint32_t row_q = ctx_row<P::kStatic>(mq, gq.spec(sq, pf.pos, psq));
+        const uint32_t slot_q = D.xq & kSlotMask, slot_a = D.xa & kSlotMask;
         uint32_t start, freq;
-        uint32_t vq = q_find(mq.dec + (size_t)row_q * kQRowBytes, slot_q, start, freq);
+        vq = q_find(mq.dec + (size_t)row_q * kQRowBytes, slot_q, start, freq);
         D.xq = freq * (D.xq >> kScaleBits) + slot_q - start;  // RansDecAdvanceStep
-        uint2 pk = __ldg(reinterpret_cast<const uint2*>(ma.dec) + row_a);
-        uint32_t va = acid_find(pk, slot_a, start, freq);
+        const uint2 pk = __ldg(reinterpret_cast<const uint2*>(ma.dec) + row_a);
+        va = acid_find(pk, slot_a, start, freq);
         D.xa = freq * (D.xa >> kScaleBits) + slot_a - start;
-        // renorm_all: state 0 then state 1; at most two bytes each (x >= 2^9 after the advance)
-        if (D.xq < kRansL && D.cur < D.plen) D.xq = (D.xq << 8) | D.next();
-        if (D.xq < kRansL && D.cur < D.plen) D.xq = (D.xq << 8) | D.next();
-        if (D.xa < kRansL && D.cur < D.plen) D.xa = (D.xa << 8) | D.next();
-        if (D.xa < kRansL && D.cur < D.plen) D.xa = (D.xa << 8) | D.next();
-        if (D.xq < kRansL || D.xa < kRansL) D.st |= 1;  // the payload ran out
-        oa.push(va);
-        oq.push(vq);
+        D.renorm_all();
         const bool z = va * vq == 0;
         ga.update(sa, va, vq, z);
         gq.update(sq, va, vq, z);
         pf.advance();
+    };
+    uint32_t i = 0, va, vq;
+#pragma unroll 1
+    for (; i < len && !O.aligned(); i++) {  // up to the first word boundary (everything, if the two outputs disagree)
+        step(va, vq);
+        O.put(va, vq);
+    }
+#pragma unroll 1
+    for (; i + 4 <= len; i += 4) {
+        uint32_t wa, wq;
+        step(wa, wq);
+        step(va, vq);
+        wa = __byte_perm(wa, va, 0x3240);
+        wq = __byte_perm(wq, vq, 0x3240);
+        step(va, vq);
+        wa = __byte_perm(wa, va, 0x3410);
+        wq = __byte_perm(wq, vq, 0x3410);
+        step(va, vq);
+        wa = __byte_perm(wa, va, 0x4210);
+        wq = __byte_perm(wq, vq, 0x4210);
+        O.put4(wa, wq);
+    }
+#pragma unroll 1
+    for (; i < len; i++) {
+        step(va, vq);
+        O.put(va, vq);
     }
 }
 
@@ -1308,14 +1390,13 @@ decode_kernel(DecodeArgs A, const ModelDev MA, const ModelDev MQ) {
     if (A.read_off_out) A.read_off_out[r] = ooff;
     DecStream D;
     D.begin(A.payload, A.ix.pay_off[slot], A.ix.pay_len[slot]);
-    FwdWriter oa, oq;
-    oa.init(A.acids_out + ooff);
-    oq.init(A.quals_out + ooff);
-    decode_read_body<P>(ma, mq, len, D, oa, oq);
-    oa.finish();
-    oq.finish();
+    SymWriter O;
+    O.init(A.acids_out + ooff, A.quals_out + ooff);
+    decode_read_body<P>(ma, mq, len, D, O);
+    const uint32_t plen = A.ix.pay_len[slot];
+    D.finish(A.payload, A.ix.pay_off[slot], plen);
     uint32_t st = D.st;
-    if (!(st & 1) && !D.clean_end()) st |= 2;
+    if (!(st & 1) && !D.clean_end(plen)) st |= 2;
     if (A.read_status) A.read_status[r] = st;
     if (st & 1) atomicOr(A.err, 1u);
 }

@@ -531,20 +531,18 @@ decode_lane_kernel(DecodeLaneArgs A, const ModelDev MA, const ModelDev MQ) {
     const unsigned long long r0 = A.ix.first_read[l], r1 = A.ix.first_read[l + 1];
     DecStream D;
     D.begin(A.payload, A.ix.pay_off[l], A.ix.pay_len[l]);
-    FwdWriter oa, oq;
-    unsigned long long o0 = A.read_off[r0];
-    oa.init(A.acids_out + o0);
-    oq.init(A.quals_out + o0);
-    unsigned long long o = o0;
+    SymWriter O;
+    unsigned long long o = A.read_off[r0];
+    O.init(A.acids_out + o, A.quals_out + o);
 #pragma unroll 1
-    for (unsigned long long r = r0; r < r1 && !(D.st & 1); r++) {
+    for (unsigned long long r = r0; r < r1; r++) {
         unsigned long long o_next = A.read_off[r + 1];
-        decode_read_body<P>(ma, mq, (uint32_t)(o_next - o), D, oa, oq);
+        decode_read_body<P>(ma, mq, (uint32_t)(o_next - o), D, O);
         o = o_next;
     }
-    oa.finish();
-    oq.finish();
-    if ((D.st & 1) || !D.clean_end()) atomicOr(A.err, 1u);
+    const uint32_t plen = A.ix.pay_len[l];
+    D.finish(A.payload, A.ix.pay_off[l], plen);
+    if ((D.st & 1) || !D.clean_end(plen)) atomicOr(A.err, 1u);
 }
 
 }  // namespace idn
