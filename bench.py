@@ -332,6 +332,8 @@ def run_gpu(args, w: dict):
                                                       c.dec_status.data_ptr(), sp))
 
     def check_decode_status():
+        if os.environ.get("IDN_BENCH_NOVERIFY"):
+            return
         for c in chunks:
             stt = c.dec_status.cpu().numpy()
             if int(stt[0]) != 0 or int(stt[2]) != c.n_reads:
@@ -383,8 +385,11 @@ def run_gpu(args, w: dict):
             ctx.profile(False)
         # lossless round trip of the whole workload, checked on the device outside the timed region
         ok = bool(torch.equal(dec_a[:S], acids_d[:S]) and torch.equal(dec_q[:S], quals_d[:S]))
-        check_decode_status()
-        if not ok:
+        if os.environ.get("IDN_BENCH_NOVERIFY"):  # kernel ablation experiments (tools/var_sweep.sh) produce wrong symbols on purpose
+            ok = False
+        else:
+            check_decode_status()
+        if not ok and not os.environ.get("IDN_BENCH_NOVERIFY"):
             raise SystemExit(f"round trip mismatch in {mode_name} mode: the decoded symbols differ from the input")
         res["verified"] = ok
         return res

@@ -20,11 +20,12 @@ constexpr uint32_t kAcidSyms = 5, kQSyms = 94;
 constexpr uint32_t kSlotMask = (1u << kScaleBits) - 1;
 constexpr uint32_t kRansL = 1u << 23;  // RANS_BYTE_L
 constexpr int kHist = 8;               // longest acid / q-score history any legal spec type uses
-// q-score decode row: 128-byte bucket LUT (slot >> 7 -> first group) + 24 groups of 4 symbols, each symbol one
-// word freq | start << 16 (padding symbols: start = 2^14, freq = 0)
+// q-score decode row: 128-byte bucket LUT (slot >> 7 -> (symbol that owns the bucket's first slot) >> 2) + the row's
+// cumulative frequencies as u16 "starts" (starts[s] = cum[s], everything from index 94 on = 2^14).  The search loads
+// the 8 starts from 4 * LUT on (two 8-byte loads) and resolves the symbol in registers.
 constexpr int kQLutBytes = 128;
-constexpr int kQGroups = 24;
-constexpr int kQRowBytes = kQLutBytes + kQGroups * 16;  // 512
+constexpr int kQStarts = 104;                            // 94 symbols + the total + padding up to 4 * 23 + 8 + 4
+constexpr int kQRowBytes = 352;                          // 128 + 2 * 104 = 336, rounded up to whole 32-byte sectors
 
 // floor(x / d) for x < 2^31 as umulhi(x, m) >> s.  d = 2^k (k >= 1): m = 2^(32-k), s = 0; otherwise the round-up
 // reciprocal with s = ceil(log2 d) - 1 (the same argument as ryg's RansEncSymbolInit).  d <= 1 is never divided by.
@@ -172,6 +173,7 @@ struct ModelDev {
     uint32_t hmask;
     const uint2* enc;             // [n_rows][nsym] {rcp_freq, start | freq << 14 | rcp_shift << 28}
     const uint8_t* dec;           // acid: [n_rows] x 8 bytes = cum[1..4] u16; q: [n_rows] x kQRowBytes
+    const uint2* adirect;         // acid, small dense spec spaces: the decode row of every spec (spec -> cum[1..4]), or nullptr
 };
 
 __device__ __forceinline__ uint32_t hash32(uint32_t k) {
@@ -359,21 +361,38 @@ __device__ __forceinline__ uint32_t acid_find(uint2 packed, uint32_t slot, uint3
     return p4 ? 4u : (p3 ? 3u : (p2 ? 2u : (p1 ? 1u : 0u)));
 }
 
-// q-score symbol search in a decode row (layout above): bucket LUT -> group of 4 symbols -> compare/select in
-// registers.  A bucket of 128 slots that spans more than one group (only possible in the low-probability tail of a
-// distribution) advances group by group.
+// q-score symbol search in a decode row (layout above): bucket LUT -> window of 8 starts -> compare in registers.
+// starts[4g] <= slot holds by construction; the window resolves the symbols 4g .. 4g+6 (the freq of a symbol needs the
+// next start).  A slot beyond them (>= 4 symbols inside what is left of a 128-slot bucket: only in the flat tail of
+// a distribution) moves the window on by 4 symbols.
 __device__ __forceinline__ uint32_t q_find(const uint8_t* __restrict__ row, uint32_t slot, uint32_t& start,
                                            uint32_t& freq) {
     uint32_t g = __ldg(row + (slot >> 7));
-    const uint4* groups = reinterpret_cast<const uint4*>(row + kQLutBytes);
-    const uint32_t T = (slot + 1) << 16;  // word = freq | start << 16:  start <= slot  <=>  word < T
-    uint4 w = __ldg(groups + g);
-    while (slot >= (w.w >> 16) + (w.w & 0xffffu)) w = __ldg(groups + ++g);  // beyond the group's last symbol
-    const bool p1 = w.y < T, p2 = w.z < T, p3 = w.w < T;
-    const uint32_t e = p3 ? w.w : (p2 ? w.z : (p1 ? w.y : w.x));
-    start = e >> 16;
-    freq = e & 0xffffu;
-    return 4 * g + (p3 ? 3u : (p2 ? 2u : (p1 ? 1u : 0u)));
+    const uint2* starts = reinterpret_cast<const uint2*>(row + kQLutBytes);
+    // halves of K - W: bit 15 set <=> slot >= start (K = 0x8000 | slot in both halves, starts <= 2^14: no borrow)
+    const uint32_t K = (slot | 0x8000u) * 0x10001u;
+    uint2 lo = __ldg(starts + g), hi = __ldg(starts + g + 1);
+    uint32_t flags;
+    for (;;) {
+        flags = ((K - lo.x) & 0x80008000u) | (((K - lo.y) & 0x80008000u) >> 1) | (((K - hi.x) & 0x80008000u) >> 2) |
+                (((K - hi.y) & 0x80008000u) >> 3);
+#ifndef IDN_ABL_NOADV
+        if (!(flags & 0x10000000u)) break;  // bit 28 = the last start of the window: still <= slot -> move on
+        g++;
+        lo = hi;
+        hi = __ldg(starts + g + 1);
+#else
+        break;
+#endif
+    }
+    const uint32_t j = __popc(flags) - 1;  // index of the last start <= slot (the flags are monotone)
+    const uint32_t p = j >> 1;
+    const uint32_t w0 = p == 0 ? lo.x : (p == 1 ? lo.y : (p == 2 ? hi.x : hi.y));
+    const uint32_t w1 = p == 0 ? lo.y : (p == 1 ? hi.x : hi.y);
+    const uint32_t pair = __funnelshift_r(w0, w1, 16 * (j & 1));  // starts[j] | starts[j+1] << 16
+    start = pair & 0xffffu;
+    freq = (pair >> 16) - start;
+    return 4 * g + j;
 }
 
 }  // namespace idn

@@ -56,19 +56,22 @@ struct ModelSlot {
     void* d_hvals = nullptr;
     void* d_enc = nullptr;
     void* d_dec = nullptr;
+    void* d_adirect = nullptr;
     void free_all() {
         cudaFree(d_map);
         cudaFree(d_hkeys);
         cudaFree(d_hvals);
         cudaFree(d_enc);
         cudaFree(d_dec);
-        d_map = d_hkeys = d_hvals = d_enc = d_dec = nullptr;
+        cudaFree(d_adirect);
+        d_map = d_hkeys = d_hvals = d_enc = d_dec = d_adirect = nullptr;
         used = false;
     }
 };
 
 constexpr uint32_t kMaxSlots = 1024;
 constexpr uint64_t kDenseSpecLimit = 1ull << 22;  // dense u16 map up to 8 MB, hash above
+constexpr uint64_t kDirectSpecLimit = 1ull << 19;  // acid decode rows stored per spec (8 B each) up to 4 MB
 
 }  // namespace
 
@@ -252,7 +255,7 @@ static const int32_t kStaticPairs[5][10] = {
 
 static int static_pair_index(const idn_gpu_ctx* ctx, int32_t acid_slot, int32_t q_slot) {
     // the specialised kernels index the dense spec -> row table without looking (ctx_row<true>)
-    if (!ctx->slots[acid_slot].dev.map || !ctx->slots[q_slot].dev.map) return -1;
+    if (!ctx->slots[acid_slot].dev.map || !ctx->slots[q_slot].dev.map || !ctx->slots[acid_slot].dev.adirect) return -1;
     for (int i = 0; i < 5; i++) {
         bool same = true;
         for (int k = 0; k < 5; k++)
@@ -478,11 +481,10 @@ extern "C" int32_t idn_gpu_model_upload(idn_gpu_ctx* ctx, int32_t model_type, in
         for (uint32_t r = 0; r < n_rows; r++) {
             const uint16_t* row = cum + (size_t)r * 95;
             uint8_t* d = dec.data() + (size_t)r * kQRowBytes;
-            uint32_t* words = reinterpret_cast<uint32_t*>(d + kQLutBytes);
-            for (uint32_t sidx = 0; sidx < (uint32_t)kQGroups * 4; sidx++)
-                words[sidx] = sidx < 94 ? ((uint32_t)(row[sidx + 1] - row[sidx]) | ((uint32_t)row[sidx] << 16)) : (total << 16);
+            uint16_t* starts = reinterpret_cast<uint16_t*>(d + kQLutBytes);
+            for (uint32_t sidx = 0; sidx < (uint32_t)kQStarts; sidx++) starts[sidx] = sidx < 94 ? row[sidx] : (uint16_t)total;
             uint32_t sidx = 0;
-            for (uint32_t k = 0; k < (uint32_t)kQLutBytes; k++) {  // group of the symbol that owns slot 128 k
+            for (uint32_t k = 0; k < (uint32_t)kQLutBytes; k++) {  // the symbol that owns slot 128 k, in units of 4 symbols
                 while (row[sidx + 1] <= 128 * k) sidx++;
                 d[k] = (uint8_t)(sidx >> 2);
             }
@@ -491,6 +493,17 @@ extern "C" int32_t idn_gpu_model_upload(idn_gpu_ctx* ctx, int32_t model_type, in
     CU(cudaMalloc(&slot.d_dec, dec.size()));
     CU(cudaMemcpy(slot.d_dec, dec.data(), dec.size(), cudaMemcpyHostToDevice));
     slot.dev.dec = (const uint8_t*)slot.d_dec;
+    // acid decode rows per spec: the decoder's spec -> row -> cum-freqs chain becomes one gather
+    if (model_type == IDN_MODEL_ACID && slot.dev.map && spec_num <= kDirectSpecLimit) {
+        std::vector<uint64_t> direct(spec_num);
+        uint64_t row0;
+        memcpy(&row0, dec.data(), 8);
+        std::fill(direct.begin(), direct.end(), row0);
+        for (uint64_t i = 0; i < n_specs; i++) memcpy(&direct[spec_keys[i]], dec.data() + (size_t)(spec_ctx[i] + 1) * 8, 8);
+        CU(cudaMalloc(&slot.d_adirect, spec_num * 8));
+        CU(cudaMemcpy(slot.d_adirect, direct.data(), spec_num * 8, cudaMemcpyHostToDevice));
+        slot.dev.adirect = (const uint2*)slot.d_adirect;
+    }
     slot.used = true;
 
     size_t idx = ctx->slots.size();

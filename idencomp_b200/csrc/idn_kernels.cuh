@@ -1297,6 +1297,9 @@ struct SymWriter {
         *pq++ = (uint8_t)q;
     }
     __device__ __forceinline__ void put4(uint32_t wa, uint32_t wq) {
+#ifdef IDN_ABL_NOSTORE
+        if (wa != 0xdeadbeefu) { pa += 4; pq += 4; return; }
+#endif
         *reinterpret_cast<uint32_t*>(pa) = wa;
         *reinterpret_cast<uint32_t*>(pq) = wq;
         pa += 4;
@@ -1320,13 +1323,25 @@ __device__ __forceinline__ void decode_read_body(const ModelDev& ma, const Model
     pf.init(len, pbmax);
     auto step = [&](uint32_t& va, uint32_t& vq) {
         D.refill();
-        const uint32_t row_a = ctx_row<P::kStatic>(ma, ga.spec(sa, pf.pos, psa));
+        const uint32_t spec_a = ga.spec(sa, pf.pos, psa);
+        uint2 pk;  // cum[1..4] of the acid context
+#ifdef IDN_ACID_CG
+        if (P::kStatic || ma.adirect) pk = __ldcg(ma.adirect + spec_a);
+#else
+        if (P::kStatic || ma.adirect) pk = __ldg(ma.adirect + spec_a);
+#endif
+        else pk = __ldg(reinterpret_cast<const uint2*>(ma.dec) + ctx_row(ma, spec_a));
+#if defined(IDN_ABL_ROW1)
+        const uint32_t row_q = 1;
+#elif defined(IDN_ABL_NOQMAP)
+        const uint32_t row_q = (gq.spec(sq, pf.pos, psq) * 2654435761u >> 22) + 1;
+#else
         const uint32_t row_q = ctx_row<P::kStatic>(mq, gq.spec(sq, pf.pos, psq));
+#endif
         const uint32_t slot_q = D.xq & kSlotMask, slot_a = D.xa & kSlotMask;
         uint32_t start, freq;
         vq = q_find(mq.dec + (size_t)row_q * kQRowBytes, slot_q, start, freq);
         D.xq = freq * (D.xq >> kScaleBits) + slot_q - start;  // RansDecAdvanceStep
-        const uint2 pk = __ldg(reinterpret_cast<const uint2*>(ma.dec) + row_a);
         va = acid_find(pk, slot_a, start, freq);
         D.xa = freq * (D.xa >> kScaleBits) + slot_a - start;
         D.renorm_all();
