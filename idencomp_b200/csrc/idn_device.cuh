@@ -338,6 +338,22 @@ __device__ __forceinline__ void rans_put(uint32_t& x, uint2 e, Emit&& emit) {
     x = x + start + q * ((1u << kScaleBits) - freq);
 }
 
+// The same step without branches, for the encoder kernels: a state emits 0, 1 or 2 bytes per symbol (x < 2^31 and
+// x_max >= 2^17), `out` is a BackWriter-like sink with push_bits(bytes in emission order, 8 * count).
+template <class Out>
+__device__ __forceinline__ void rans_put_bf(uint32_t& x, uint2 e, Out& out) {
+    const uint32_t freq = (e.y >> 14) & 0x3fffu;
+    const uint32_t start = e.y & 0x3fffu;
+    const uint32_t x_max = freq << (23 - kScaleBits + 8);
+    const bool one = x >= x_max, two = (x >> 8) >= x_max;  // two implies one
+    const uint32_t sel = two ? 0x4401u : (one ? 0x4440u : 0x4444u);  // [x1 x0] / [x0] / nothing, first emitted byte highest
+    const uint32_t kbits = two ? 16u : (one ? 8u : 0u);
+    out.push_bits(__byte_perm(x, 0, sel), kbits);
+    x >>= kbits;
+    const uint32_t q = freq == 1 ? x : (__umulhi(x, e.x) >> (e.y >> 28));
+    x = x + start + q * ((1u << kScaleBits) - freq);
+}
+
 // size-only variant for the scorer (ModelTester::compute_size): counts emitted bytes
 __device__ __forceinline__ void rans_put_count(uint32_t& x, uint2 e, uint32_t& bytes) {
     uint32_t freq = (e.y >> 14) & 0x3fffu;

@@ -22,25 +22,22 @@ namespace idn {
 struct BackReader {  // bytes at decreasing addresses
     const uint32_t* wp;  // word that holds the next byte
     uint32_t word;
-    int lane;            // byte of `word` the next get() returns; 4 = the word is not loaded yet
-    bool loaded;
+    int lane;            // byte of `word` the next get() returns, + 4 while that word is not loaded yet
     __device__ __forceinline__ void start(const uint8_t* last) {  // the next get() returns *last
         const uintptr_t a = reinterpret_cast<uintptr_t>(last);
         wp = reinterpret_cast<const uint32_t*>(a & ~(uintptr_t)3);
-        lane = (int)(a & 3);
-        loaded = false;
+        lane = (int)(a & 3) + 4;
         word = 0;
     }
     __device__ __forceinline__ uint32_t get() {
-        if (!loaded) {
+        if (lane >= 4) {
             word = __ldg(wp);
-            loaded = true;
+            lane -= 4;
         }
         const uint32_t b = (word >> (8 * lane)) & 0xffu;
         if (--lane < 0) {
-            lane = 3;
+            lane = 7;
             wp--;
-            loaded = false;
         }
         return b;
     }
@@ -73,32 +70,38 @@ struct FwdReader {  // bytes at increasing addresses
     }
 };
 
-// writes bytes at decreasing addresses, 4 at a time.  `end` must be 4-byte aligned.
+// writes bytes at decreasing addresses, 4 at a time.  `end` must be 4-byte aligned.  Bytes wait in a 64-bit
+// accumulator (oldest highest); drain() stores a word once four are there, so at most 7 may be pending before it.
 struct BackWriter {
     uint32_t* wptr;  // next word to fill is wptr[-1]
     uint32_t* wend;
-    uint32_t acc, n;
+    unsigned long long acc;
+    uint32_t nbits;  // pending bytes * 8
     __device__ __forceinline__ void init(uint8_t* end) {
         wptr = wend = reinterpret_cast<uint32_t*>(end);
         acc = 0;
-        n = 0;
+        nbits = 0;
     }
-    __device__ __forceinline__ uint32_t bytes() const { return (uint32_t)(wend - wptr) * 4u + n; }
-    __device__ __forceinline__ void push(uint32_t b) {
-        acc = (acc << 8) | b;  // the first byte pushed lands at the highest address
-        if (++n == 4) {
-            *--wptr = acc;
-            n = 0;
+    __device__ __forceinline__ uint32_t bytes() const { return (uint32_t)(wend - wptr) * 4u + (nbits >> 3); }
+    // appends kbits / 8 bytes given in emission order, first emitted byte highest
+    __device__ __forceinline__ void push_bits(uint32_t bytes_be, uint32_t kbits) {
+        acc = (acc << kbits) | bytes_be;
+        nbits += kbits;
+    }
+    __device__ __forceinline__ void drain() {
+        if (nbits >= 32) {
+            nbits -= 32;
+            *--wptr = (uint32_t)(acc >> nbits);  // the first byte pushed lands at the highest address
         }
     }
     __device__ __forceinline__ void push_u32_le(uint32_t x) {  // RansEncFlush: x stored little-endian below ptr
-        push(x >> 24);
-        push((x >> 16) & 0xffu);
-        push((x >> 8) & 0xffu);
-        push(x & 0xffu);
+        acc = (acc << 32) | x;
+        nbits += 32;
+        drain();
     }
     __device__ __forceinline__ void finish() {  // leftover bytes sit in the low bytes of acc, oldest highest
         uint8_t* p = reinterpret_cast<uint8_t*>(wptr);
+        const uint32_t n = nbits >> 3;
         for (uint32_t k = 0; k < n; k++) p[-1 - (int)k] = (uint8_t)(acc >> (8 * (n - 1 - k)));
     }
 };
@@ -344,8 +347,8 @@ __device__ __forceinline__ void encode_read_body(const ModelDev& ma, const Model
     GenBack ga, gq;
     ga.clear(sa);
     gq.clear(sq);
-    long long front = (long long)len - 1;  // next position to pull into the windows
-    uint32_t raw_a = 0;                    // raw symbols travel in two more shift registers (entry k = position j - k)
+    int32_t front = (int32_t)len - 1;  // next position to pull into the windows (reads are shorter than 2^31)
+    uint32_t raw_a = 0;                // raw symbols travel in two more shift registers (entry k = position j - k)
     unsigned long long raw_q = 0;
     auto pull = [&]() {
         uint32_t a = 0, q = 0;
@@ -375,7 +378,7 @@ __device__ __forceinline__ void encode_read_body(const ModelDev& ma, const Model
     pb.init(len, pbmax);
 
     // generator stage: moves the generators to position j (entry 0 = symbol j) and looks the two rows up
-    long long j = (long long)len;  // position the generators stand at
+    int32_t j = (int32_t)len;  // position the generators stand at
     auto rows_next = [&](uint32_t& row_a, uint32_t& row_q) {
         j--;
         row_a = row_q = 0;
@@ -384,11 +387,10 @@ __device__ __forceinline__ void encode_read_body(const ModelDev& ma, const Model
             ga.step_back(sa);
             gq.step_back(sq);
             pb.retreat();
-            row_a = ctx_row(ma, ga.spec(sa, pb.pos, psa));
-            row_q = ctx_row(mq, gq.spec(sq, pb.pos, psq));
+            row_a = ctx_row<P::kStatic>(ma, ga.spec(sa, pb.pos, psa));
+            row_q = ctx_row<P::kStatic>(mq, gq.spec(sq, pb.pos, psq));
         }
     };
-    auto emit = [&](uint32_t b) { S.out.push(b); };
     // prologue: rows of position len-1, its entries, rows of position len-2
     uint32_t row_a, row_q;
     rows_next(row_a, row_q);  // generators at len-1, entry 0 = symbol len-1
@@ -407,8 +409,9 @@ __device__ __forceinline__ void encode_read_body(const ModelDev& ma, const Model
             eq_n = __ldg(mq.enc + (size_t)row_q * kQSyms + ((uint32_t)raw_q & 127u));
         }
         rows_next(row_a, row_q);  // generators to i-2
-        rans_put(S.x0, ea, emit);
-        rans_put(S.x1, eq, emit);
+        rans_put_bf(S.x0, ea, S.out);  // put_at(0, acid) then put_at(1, q)   compressor.rs:95-96
+        rans_put_bf(S.x1, eq, S.out);
+        S.out.drain();
         ea = ea_n;
         eq = eq_n;
     }
