@@ -266,14 +266,19 @@ static int static_pair_index(const idn_gpu_ctx* ctx, int32_t acid_slot, int32_t 
 }
 
 // launch KERNEL<true, SPi> for a specialised pair, KERNEL<true, DynSpecs> otherwise
+// IDN_DEBUG_SMEM=<bytes>: dynamic shared memory added to these launches, an occupancy knob for experiments
+static unsigned debug_smem() {
+    static const unsigned v = [] { const char* e = getenv("IDN_DEBUG_SMEM"); return e ? (unsigned)atoi(e) : 0u; }();
+    return v;
+}
 #define IDN_LAUNCH_UNIFORM(idx, KERNEL, grid, st, ...)                                         \
     switch (idx) {                                                                             \
-        case 0: KERNEL<true, SP0><<<grid, 128, 0, st>>>(__VA_ARGS__); break;                   \
-        case 1: KERNEL<true, SP1><<<grid, 128, 0, st>>>(__VA_ARGS__); break;                   \
-        case 2: KERNEL<true, SP2><<<grid, 128, 0, st>>>(__VA_ARGS__); break;                   \
-        case 3: KERNEL<true, SP3><<<grid, 128, 0, st>>>(__VA_ARGS__); break;                   \
-        case 4: KERNEL<true, SP4><<<grid, 128, 0, st>>>(__VA_ARGS__); break;                   \
-        default: KERNEL<true, DynSpecs><<<grid, 128, 0, st>>>(__VA_ARGS__); break;             \
+        case 0: KERNEL<true, SP0><<<grid, 128, debug_smem(), st>>>(__VA_ARGS__); break;                   \
+        case 1: KERNEL<true, SP1><<<grid, 128, debug_smem(), st>>>(__VA_ARGS__); break;                   \
+        case 2: KERNEL<true, SP2><<<grid, 128, debug_smem(), st>>>(__VA_ARGS__); break;                   \
+        case 3: KERNEL<true, SP3><<<grid, 128, debug_smem(), st>>>(__VA_ARGS__); break;                   \
+        case 4: KERNEL<true, SP4><<<grid, 128, debug_smem(), st>>>(__VA_ARGS__); break;                   \
+        default: KERNEL<true, DynSpecs><<<grid, 128, debug_smem(), st>>>(__VA_ARGS__); break;             \
     }
 
 // ======================================================================================================
@@ -1324,6 +1329,18 @@ extern "C" int32_t idn_gpu_decompress_blocks_dev(idn_gpu_ctx* ctx, const uint8_t
     da.read_off_out = roff;
     da.read_status = nullptr;
     da.err = &dsp->err;
+    da.part_crc = nullptr;
+    da.part_len = nullptr;
+    da.crc_tab = da.xpow = nullptr;
+    const bool want_crc = block_crc && n_blocks && out_reads_cap;
+    if (want_crc) {  // the decoder leaves the per-read CRC partials for crc_verify_kernel
+        CU(ctx->w_crcpart.ensure((out_reads_cap + 1) * 4));
+        CU(ctx->w_crclen.ensure((out_reads_cap + 1) * 8));
+        da.part_crc = ctx->w_crcpart.as<uint32_t>();
+        da.part_len = ctx->w_crclen.as<unsigned long long>();
+        da.crc_tab = ctx->d_crc_tab;
+        da.xpow = ctx->d_xpow;
+    }
     if (out_reads_cap && n_blocks) {
         // one acid + one q-score model: every read uses that pair (the walk rejects anything else)
         int ua = -1, uq = -1, na = 0, nq = 0;
@@ -1339,12 +1356,7 @@ extern "C" int32_t idn_gpu_decompress_blocks_dev(idn_gpu_ctx* ctx, const uint8_t
         LAUNCHED("decode");
     }
     // CRC of the decoded symbols per block, compared with the header value (decompressor_block.rs:131-144)
-    if (block_crc && n_blocks && out_reads_cap) {
-        CU(ctx->w_crcpart.ensure((out_reads_cap + 1) * 4));
-        CU(ctx->w_crclen.ensure((out_reads_cap + 1) * 8));
-        rc = launch_crc_read(ctx, acids_out, quals_out, roff, nullptr, nullptr, 0, bc.reads + n_blocks, dsp->status, out_reads_cap,
-                             out_symbols_cap / out_reads_cap, st);
-        if (rc) return rc;
+    if (want_crc) {
         crc_verify_kernel<<<n_blocks, 256, 0, st>>>(ctx->w_crcpart.as<uint32_t>(), ctx->w_crclen.as<unsigned long long>(),
                                                     block_first, n_blocks, ctx->d_xpow, block_crc, dsp->status);
         LAUNCHED("crc_verify");
@@ -1596,6 +1608,9 @@ extern "C" int32_t idn_gpu_decompress_reads(idn_gpu_ctx* ctx, const uint8_t* pay
     da.read_off_out = nullptr;
     da.read_status = ctx->s_idx.as<uint32_t>();
     da.err = &dsp->err;
+    da.part_crc = nullptr;
+    da.part_len = nullptr;
+    da.crc_tab = da.xpow = nullptr;
     decode_kernel<false, DynSpecs><<<(unsigned)((R + 127) / 128), 128, 0, st>>>(da, ctx->d_models_host0, ctx->d_models_host0);
     LAUNCHED("decode");
     uint32_t err = 0;

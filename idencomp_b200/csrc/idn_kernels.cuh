@@ -420,13 +420,13 @@ __device__ __forceinline__ void encode_read_body(const ModelDev& ma, const Model
 // kUniform: every read of the batch uses the same model pair; its parameters then live in the kernel parameter
 // space (constant bank operands) instead of ~40 registers per thread, which is what bounds occupancy here.
 #ifndef IDN_ENC_MINB
-#define IDN_ENC_MINB 1
+#define IDN_ENC_MINB 9
 #endif
 #ifndef IDN_DEC_MINB
-#define IDN_DEC_MINB 1
+#define IDN_DEC_MINB 9
 #endif
 template <bool kUniform, class P>
-__global__ void __launch_bounds__(128, IDN_ENC_MINB)
+__global__ void __launch_bounds__(128, kUniform ? IDN_ENC_MINB : 1)
 encode_kernel(EncodeArgs A, const ModelDev MA, const ModelDev MQ) {
     uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= A.n_reads) return;
@@ -1210,6 +1210,12 @@ struct DecodeArgs {
     unsigned long long* read_off_out;       // optional [n_reads+1]: absolute symbol offset of every read
     uint32_t* read_status;  // optional
     uint32_t* err;
+    // optional: CRC-32 partial of every decoded read (acids | quals), the input of crc_verify_kernel, computed while the
+    // symbols are in registers instead of by a second pass over the output (K7 fused into K5)
+    uint32_t* part_crc;
+    unsigned long long* part_len;
+    const uint32_t* crc_tab;  // [256]
+    const uint32_t* xpow;     // [64]
 };
 
 // State of one rANS input stream being consumed (a read in compat mode, a lane in native mode).
@@ -1311,9 +1317,15 @@ struct SymWriter {
 };
 
 // Pops one read (positions 0 .. len-1) from the stream   SequenceDecompressor::decompress, sequence_compressor.rs:231-278
+// crc_tab: shared-memory CRC table, or nullptr; ca / cq: running (pre-inversion) CRC registers of the two symbol streams
+struct DecCrc {
+    const uint32_t* tab;
+    uint32_t ca, cq;
+};
+
 template <class P>
 __device__ __forceinline__ void decode_read_body(const ModelDev& ma, const ModelDev& mq, uint32_t len, DecStream& D,
-                                                 SymWriter& O) {
+                                                 SymWriter& O, DecCrc& C) {
     constexpr SpecDev ksa = P::sa(), ksq = P::sq();
     const SpecDev& sa = P::kStatic ? ksa : ma.spec;
     const SpecDev& sq = P::kStatic ? ksq : mq.spec;
@@ -1328,11 +1340,7 @@ __device__ __forceinline__ void decode_read_body(const ModelDev& ma, const Model
         D.refill();
         const uint32_t spec_a = ga.spec(sa, pf.pos, psa);
         uint2 pk;  // cum[1..4] of the acid context
-#ifdef IDN_ACID_CG
-        if (P::kStatic || ma.adirect) pk = __ldcg(ma.adirect + spec_a);
-#else
         if (P::kStatic || ma.adirect) pk = __ldg(ma.adirect + spec_a);
-#endif
         else pk = __ldg(reinterpret_cast<const uint2*>(ma.dec) + ctx_row(ma, spec_a));
 #if defined(IDN_ABL_ROW1)
         const uint32_t row_q = 1;
@@ -1348,6 +1356,10 @@ __device__ __forceinline__ void decode_read_body(const ModelDev& ma, const Model
         va = acid_find(pk, slot_a, start, freq);
         D.xa = freq * (D.xa >> kScaleBits) + slot_a - start;
         D.renorm_all();
+        if (C.tab) {  // uniform per launch
+            C.ca = C.tab[(C.ca ^ va) & 0xffu] ^ (C.ca >> 8);
+            C.cq = C.tab[(C.cq ^ vq) & 0xffu] ^ (C.cq >> 8);
+        }
         const bool z = va * vq == 0;
         ga.update(sa, va, vq, z);
         gq.update(sq, va, vq, z);
@@ -1382,10 +1394,19 @@ __device__ __forceinline__ void decode_read_body(const ModelDev& ma, const Model
 }
 
 template <bool kUniform, class P>
-__global__ void __launch_bounds__(128, IDN_DEC_MINB)
+__global__ void __launch_bounds__(128, kUniform ? IDN_DEC_MINB : 1)
 decode_kernel(DecodeArgs A, const ModelDev MA, const ModelDev MQ) {
+    __shared__ uint32_t s_tab[256];
+    __shared__ uint32_t s_xpow[64];
     uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (A.status && A.status[0] != 0) return;
+    DecCrc C{nullptr, 0xffffffffu, 0xffffffffu};
+    if (A.part_crc) {
+        for (int i = threadIdx.x; i < 256; i += blockDim.x) s_tab[i] = A.crc_tab[i];
+        for (int i = threadIdx.x; i < 64; i += blockDim.x) s_xpow[i] = A.xpow[i];
+        __syncthreads();
+        C.tab = s_tab;
+    }
     unsigned long long slot = r, sym_base = 0;
     if (A.blk_read_base) {
         const unsigned long long R = A.blk_read_base[A.n_blocks];
@@ -1410,13 +1431,18 @@ decode_kernel(DecodeArgs A, const ModelDev MA, const ModelDev MQ) {
     D.begin(A.payload, A.ix.pay_off[slot], A.ix.pay_len[slot]);
     SymWriter O;
     O.init(A.acids_out + ooff, A.quals_out + ooff);
-    decode_read_body<P>(ma, mq, len, D, O);
+    decode_read_body<P>(ma, mq, len, D, O, C);
     const uint32_t plen = A.ix.pay_len[slot];
     D.finish(A.payload, A.ix.pay_off[slot], plen);
     uint32_t st = D.st;
     if (!(st & 1) && !D.clean_end(plen)) st |= 2;
     if (A.read_status) A.read_status[r] = st;
     if (st & 1) atomicOr(A.err, 1u);
+    if (A.part_crc) {  // crc(acids | quals) of this read, as crc_read_kernel would compute it
+        const CrcPair p = crc_concat(CrcPair{~C.ca, len}, CrcPair{~C.cq, len}, s_xpow);
+        A.part_crc[r] = len ? p.crc : 0u;
+        A.part_len[r] = 2ull * len;
+    }
 }
 
 // final status word of a device-side decompress call

@@ -532,12 +532,13 @@ decode_lane_kernel(DecodeLaneArgs A, const ModelDev MA, const ModelDev MQ) {
     DecStream D;
     D.begin(A.payload, A.ix.pay_off[l], A.ix.pay_len[l]);
     SymWriter O;
+    DecCrc C{nullptr, 0, 0};
     unsigned long long o = A.read_off[r0];
     O.init(A.acids_out + o, A.quals_out + o);
 #pragma unroll 1
     for (unsigned long long r = r0; r < r1; r++) {
         unsigned long long o_next = A.read_off[r + 1];
-        decode_read_body<P>(ma, mq, (uint32_t)(o_next - o), D, O);
+        decode_read_body<P>(ma, mq, (uint32_t)(o_next - o), D, O, C);
         o = o_next;
     }
     const uint32_t plen = A.ix.pay_len[l];
