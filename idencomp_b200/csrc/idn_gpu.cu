@@ -101,6 +101,7 @@ struct idn_gpu_ctx {
     std::vector<ModelSlot> slots;
     ModelDev* d_models = nullptr;  // [kMaxSlots], mirrors slots[].dev
     ModelDev d_models_host0{};     // all-zero placeholder for the by-value model parameters of the non-uniform kernels
+    int sm_count = 148;
     uint32_t* d_crc_tab = nullptr;  // [256]
     uint32_t* d_xpow = nullptr;     // [64]
     // workspaces of the *_dev paths
@@ -328,6 +329,7 @@ extern "C" int32_t idn_gpu_create(int32_t device, idn_gpu_ctx** out) {
         return (int32_t)IDN_E_CUDA;
     };
     if (cudaSetDevice(device) != cudaSuccess) return bail("cudaSetDevice");
+    if (cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device) != cudaSuccess) return bail("cudaDeviceGetAttribute");
     if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) return bail("cudaStreamCreate");
     if (cudaEventCreateWithFlags(&ctx->ev, cudaEventDisableTiming | cudaEventBlockingSync) != cudaSuccess) return bail("cudaEventCreate");
     if (cudaMalloc(&ctx->d_models, sizeof(ModelDev) * kMaxSlots) != cudaSuccess) return bail("cudaMalloc");
@@ -815,7 +817,9 @@ static int32_t launch_crc_read(idn_gpu_ctx* ctx, const uint8_t* acids, const uin
             acids, quals, read_off, names, name_off, n_reads, n_reads_dev, status, ctx->d_crc_tab, ctx->d_xpow,
             ctx->w_crcpart.as<uint32_t>(), ctx->w_crclen.as<unsigned long long>());
     } else {
-        crc_read_kernel<<<(unsigned)((grid_reads + 127) / 128), 128, 0, st>>>(acids, quals, read_off, names, name_off, n_reads, n_reads_dev,
+        const uint64_t tiles = (grid_reads + kCrcThreads - 1) / kCrcThreads;
+        const unsigned cgrid = (unsigned)std::min<uint64_t>(tiles ? tiles : 1, (uint64_t)ctx->sm_count * 2);
+        crc_read_kernel<<<cgrid, kCrcThreads, 0, st>>>(acids, quals, read_off, names, name_off, n_reads, n_reads_dev,
                                                                              status, ctx->d_crc_tab, ctx->d_xpow,
                                                                              ctx->w_crcpart.as<uint32_t>(),
                                                                              ctx->w_crclen.as<unsigned long long>());
@@ -1240,6 +1244,17 @@ static int32_t decompress_native_dev(idn_gpu_ctx* ctx, const uint8_t* blocks, co
         da.acids_out = acids_out;
         da.quals_out = quals_out;
         da.err = &dsp->err;
+        da.part_crc = nullptr;
+        da.part_len = nullptr;
+        da.crc_tab = da.xpow = nullptr;
+        if (block_crc) {  // the lane decoder leaves the per-read CRC partials for crc_verify_kernel
+            CU(ctx->w_crcpart.ensure((out_reads_cap + 1) * 4));
+            CU(ctx->w_crclen.ensure((out_reads_cap + 1) * 8));
+            da.part_crc = ctx->w_crcpart.as<uint32_t>();
+            da.part_len = ctx->w_crclen.as<unsigned long long>();
+            da.crc_tab = ctx->d_crc_tab;
+            da.xpow = ctx->d_xpow;
+        }
         int ua = -1, uq = -1, na = 0, nq = 0;
         for (uint32_t i = 0; i < n_models; i++) {
             if (ctx->slots[models[i]].dev.type == IDN_MODEL_ACID) { ua = models[i]; na++; } else { uq = models[i]; nq++; }
@@ -1253,11 +1268,6 @@ static int32_t decompress_native_dev(idn_gpu_ctx* ctx, const uint8_t* blocks, co
         LAUNCHED("decode_lane");
     }
     if (block_crc && out_reads_cap) {
-        CU(ctx->w_crcpart.ensure((out_reads_cap + 1) * 4));
-        CU(ctx->w_crclen.ensure((out_reads_cap + 1) * 8));
-        int32_t rc = launch_crc_read(ctx, acids_out, quals_out, roff, nullptr, nullptr, 0, bc.reads + n_blocks, dsp->status,
-                                     out_reads_cap, out_symbols_cap / out_reads_cap, st);
-        if (rc) return rc;
         crc_verify_kernel<<<n_blocks, 256, 0, st>>>(ctx->w_crcpart.as<uint32_t>(), ctx->w_crclen.as<unsigned long long>(),
                                                     block_first, n_blocks, ctx->d_xpow, block_crc, dsp->status);
         LAUNCHED("crc_verify");

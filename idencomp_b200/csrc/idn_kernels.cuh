@@ -770,37 +770,102 @@ __device__ __forceinline__ uint32_t crc_bytes(const uint8_t* __restrict__ base, 
     return ~c;
 }
 
-// one thread per read: partial = crc(name|acids|quals), length = name_len + 2*len.
+// CRC tables of the thread-per-read kernel: one copy of the 256-entry table per lane (entry i of lane l at
+// [i * 32 + l]), so that the 32 look-ups of a warp never share a bank, whatever the data.
+constexpr int kCrcThreads = 1024;
+__device__ __forceinline__ uint32_t crc_step(uint32_t c, const uint32_t* __restrict__ rtab /*+ lane*/) {
+    return rtab[(c & 0xffu) << 5] ^ (c >> 8);
+}
+__device__ __forceinline__ uint32_t crc_bytes_rep(const uint8_t* __restrict__ base, unsigned long long off, uint32_t n,
+                                                  const uint32_t* __restrict__ rtab) {
+    uint32_t c = 0xffffffffu;
+    const uint8_t* p = base + off;
+    while (n && (reinterpret_cast<uintptr_t>(p) & 3)) {  // head up to a word boundary
+        c = crc_step(c ^ *p++, rtab);
+        n--;
+    }
+    const uint32_t* w = reinterpret_cast<const uint32_t*>(p);
+    for (; n >= 4; n -= 4) {
+        c ^= __ldg(w++);
+        c = crc_step(c, rtab);
+        c = crc_step(c, rtab);
+        c = crc_step(c, rtab);
+        c = crc_step(c, rtab);
+    }
+    p = reinterpret_cast<const uint8_t*>(w);
+    for (; n; n--) c = crc_step(c ^ *p++, rtab);
+    return ~c;
+}
+// two byte strings of the same length and alignment (the acids and the quality scores of a read) in lock step: two
+// independent look-up chains per thread
+__device__ __forceinline__ void crc_bytes_rep2(const uint8_t* __restrict__ pa, const uint8_t* __restrict__ pq, uint32_t n,
+                                               const uint32_t* __restrict__ rtab, uint32_t& crc_a, uint32_t& crc_q) {
+    uint32_t ca = 0xffffffffu, cq = 0xffffffffu;
+    while (n && (reinterpret_cast<uintptr_t>(pa) & 3)) {
+        ca = crc_step(ca ^ *pa++, rtab);
+        cq = crc_step(cq ^ *pq++, rtab);
+        n--;
+    }
+    const uint32_t* wa = reinterpret_cast<const uint32_t*>(pa);
+    const uint32_t* wq = reinterpret_cast<const uint32_t*>(pq);
+    for (; n >= 4; n -= 4) {
+        ca ^= __ldg(wa++);
+        cq ^= __ldg(wq++);
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            ca = crc_step(ca, rtab);
+            cq = crc_step(cq, rtab);
+        }
+    }
+    pa = reinterpret_cast<const uint8_t*>(wa);
+    pq = reinterpret_cast<const uint8_t*>(wq);
+    for (; n; n--) {
+        ca = crc_step(ca ^ *pa++, rtab);
+        cq = crc_step(cq ^ *pq++, rtab);
+    }
+    crc_a = ~ca;
+    crc_q = ~cq;
+}
+
+// one thread per read: partial = crc(name|acids|quals), length = name_len + 2*len.  The CTAs walk the reads in tiles of
+// kCrcThreads (grid-stride), so the 32 KB of tables are filled once per CTA.
 // n_reads_dev / status (optional) serve the decode path, where the read count only exists on the device.
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(kCrcThreads)
 crc_read_kernel(const uint8_t* __restrict__ acids, const uint8_t* __restrict__ quals,
                 const unsigned long long* __restrict__ read_off, const uint8_t* __restrict__ names,
                 const unsigned long long* __restrict__ name_off, uint64_t n_reads,
                 const unsigned long long* __restrict__ n_reads_dev, const int32_t* __restrict__ status,
                 const uint32_t* __restrict__ crc_tab, const uint32_t* __restrict__ xpow_g,
                 uint32_t* __restrict__ part_crc, unsigned long long* __restrict__ part_len) {
-    __shared__ uint32_t tab[256];
+    __shared__ uint32_t tab[256 * 32];
     __shared__ uint32_t xpow[64];
     if (status && status[0] != 0) return;
     if (n_reads_dev) n_reads = *n_reads_dev;
-    for (int i = threadIdx.x; i < 256; i += blockDim.x) tab[i] = crc_tab[i];
+    for (int i = threadIdx.x; i < 256 * 32; i += blockDim.x) tab[i] = crc_tab[i >> 5];
     for (int i = threadIdx.x; i < 64; i += blockDim.x) xpow[i] = xpow_g[i];
     __syncthreads();
-    uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (r >= n_reads) return;
-    unsigned long long off = read_off[r];
-    uint32_t len = (uint32_t)(read_off[r + 1] - off);
-    CrcPair p{0, 0};
-    if (names && name_off) {
-        uint32_t nl = (uint32_t)(name_off[r + 1] - name_off[r]);
-        p.crc = crc_bytes(names, name_off[r], nl, tab);
-        p.len = nl;
+    const uint32_t* rtab = tab + (threadIdx.x & 31);
+    const bool same_align = ((reinterpret_cast<uintptr_t>(acids) ^ reinterpret_cast<uintptr_t>(quals)) & 3) == 0;
+    for (uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n_reads; r += (uint64_t)gridDim.x * blockDim.x) {
+        unsigned long long off = read_off[r];
+        uint32_t len = (uint32_t)(read_off[r + 1] - off);
+        CrcPair p{0, 0};
+        if (names && name_off) {
+            uint32_t nl = (uint32_t)(name_off[r + 1] - name_off[r]);
+            p.crc = crc_bytes_rep(names, name_off[r], nl, rtab);
+            p.len = nl;
+        }
+        CrcPair a{0, len}, q{0, len};
+        if (same_align) {
+            crc_bytes_rep2(acids + off, quals + off, len, rtab, a.crc, q.crc);
+        } else {
+            a.crc = crc_bytes_rep(acids, off, len, rtab);
+            q.crc = crc_bytes_rep(quals, off, len, rtab);
+        }
+        p = crc_concat(crc_concat(p, a, xpow), q, xpow);
+        part_crc[r] = p.crc;
+        part_len[r] = p.len;
     }
-    CrcPair a{crc_bytes(acids, off, len, tab), len};
-    CrcPair q{crc_bytes(quals, off, len, tab), len};
-    p = crc_concat(crc_concat(p, a, xpow), q, xpow);
-    part_crc[r] = p.crc;
-    part_len[r] = p.len;
 }
 
 // CRC of n bytes by one warp: every lane takes a contiguous slice, the lanes combine in order (result in lane 0)

@@ -519,26 +519,47 @@ struct DecodeLaneArgs {
     uint8_t* acids_out;
     uint8_t* quals_out;
     uint32_t* err;
+    // optional: per-read CRC-32 partials (acids | quals) for crc_verify_kernel, as in DecodeArgs
+    uint32_t* part_crc;
+    unsigned long long* part_len;
+    const uint32_t* crc_tab;
+    const uint32_t* xpow;
 };
 
 template <bool kUniform, class P>
 __global__ void __launch_bounds__(128)
 decode_lane_kernel(DecodeLaneArgs A, const ModelDev MA, const ModelDev MQ) {
+    __shared__ uint32_t s_tab[256];
+    __shared__ uint32_t s_xpow[64];
     uint64_t l = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (A.status[0] != 0 || l >= *A.n_lanes_dev) return;
+    if (A.status[0] != 0) return;
+    DecCrc C{nullptr, 0xffffffffu, 0xffffffffu};
+    if (A.part_crc) {
+        for (int i = threadIdx.x; i < 256; i += blockDim.x) s_tab[i] = A.crc_tab[i];
+        for (int i = threadIdx.x; i < 64; i += blockDim.x) s_xpow[i] = A.xpow[i];
+        __syncthreads();
+        C.tab = s_tab;
+    }
+    if (l >= *A.n_lanes_dev) return;
     const ModelDev& ma = kUniform ? MA : A.models[A.model_ids[A.ix.am[l]]];
     const ModelDev& mq = kUniform ? MQ : A.models[A.model_ids[A.ix.qm[l]]];
     const unsigned long long r0 = A.ix.first_read[l], r1 = A.ix.first_read[l + 1];
     DecStream D;
     D.begin(A.payload, A.ix.pay_off[l], A.ix.pay_len[l]);
     SymWriter O;
-    DecCrc C{nullptr, 0, 0};
     unsigned long long o = A.read_off[r0];
     O.init(A.acids_out + o, A.quals_out + o);
 #pragma unroll 1
     for (unsigned long long r = r0; r < r1; r++) {
         unsigned long long o_next = A.read_off[r + 1];
-        decode_read_body<P>(ma, mq, (uint32_t)(o_next - o), D, O, C);
+        const uint32_t len = (uint32_t)(o_next - o);
+        decode_read_body<P>(ma, mq, len, D, O, C);
+        if (A.part_crc) {
+            const CrcPair p = crc_concat(CrcPair{~C.ca, len}, CrcPair{~C.cq, len}, s_xpow);
+            A.part_crc[r] = len ? p.crc : 0u;
+            A.part_len[r] = 2ull * len;
+            C.ca = C.cq = 0xffffffffu;
+        }
         o = o_next;
     }
     const uint32_t plen = A.ix.pay_len[l];
