@@ -700,7 +700,7 @@ extern "C" int32_t idn_gpu_compress_blocks_dev(idn_gpu_ctx* ctx, const idn_batch
     if (rc) return rc;
     SmallParams* dsp = ctx->w_small.as<SmallParams>();
 
-    CU(ctx->w_scratch.ensure(4 * S + 8 * R + 16));
+    CU(ctx->w_scratch.ensure(4 * S + kSlotExtra * R + 16));
     CU(ctx->w_paylen.ensure((R + 1) * 4));
     CU(ctx->w_sliceoff.ensure((R + 2) * 8));
     CU(ctx->w_readblock.ensure((R + 1) * 4));
@@ -742,6 +742,8 @@ extern "C" int32_t idn_gpu_compress_blocks_dev(idn_gpu_ctx* ctx, const idn_batch
         ea.scratch = ctx->w_scratch.as<uint8_t>();
         ea.pay_len = ctx->w_paylen.as<uint32_t>();
         ea.err = &dsp->err;
+        ea.switched = switched;
+        ea.cand_index = dsp->cand_index;
         const bool uniform = !chosen || (sp.n_cand[0] == 1 && sp.n_cand[1] == 1);
         const ModelDev& hma = ctx->slots[sp.cand_model[0]].dev;
         const ModelDev& hmq = ctx->slots[sp.cand_model[kMaxCand]].dev;

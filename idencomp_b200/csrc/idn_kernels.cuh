@@ -307,10 +307,15 @@ struct EncodeArgs {
     int32_t fixed_acid, fixed_q;        // indices into models[], used when chosen == nullptr
     const uint8_t* chosen;              // [2][n_reads] candidate index per type, or nullptr
     const int32_t* cand_model;          // [2][kMaxCand] candidate -> models[] index
-    uint8_t* scratch;                   // slot of read r ends at 4*read_off[r+1] + 8*(r+1)
+    uint8_t* scratch;                   // slot of read r ends at 4*read_off[r+1] + kSlotExtra*(r+1)
     uint32_t* pay_len;                  // [n_reads]
     uint32_t* err;
+    const uint8_t* switched;            // [2][n_reads]: a SwitchModel slice precedes the read's Sequence slice, or nullptr
+    const uint8_t* cand_index;          // [2][kMaxCand] candidate -> SwitchModel index
 };
+// scratch bytes per read besides 4 per symbol: two flushed states (8) + Sequence slice header (9) + two SwitchModel
+// slices (4), rounded up to keep the slot ends word-aligned
+constexpr unsigned long long kSlotExtra = 24;
 
 // State of one rANS output stream under construction (a read in compat mode, a lane in native mode).
 struct EncStream {
@@ -322,9 +327,12 @@ struct EncStream {
         out.init(slot_end);
         bad = false;
     }
-    __device__ __forceinline__ void flush() {  // flush_all: state 0 then state 1
+    __device__ __forceinline__ void flush_states() {  // flush_all: state 0 then state 1
         out.push_u32_le(x0);
         out.push_u32_le(x1);
+    }
+    __device__ __forceinline__ void flush() {
+        flush_states();
         out.finish();
     }
     __device__ __forceinline__ uint32_t total() const { return out.bytes(); }  // bytes emitted so far
@@ -440,10 +448,28 @@ encode_kernel(EncodeArgs A, const ModelDev MA, const ModelDev MQ) {
     const long long off = (long long)A.read_off[r];
     const uint32_t len = (uint32_t)(A.read_off[r + 1] - A.read_off[r]);
     EncStream S;
-    S.begin(A.scratch + 4ull * A.read_off[r + 1] + 8ull * (r + 1));
+    S.begin(A.scratch + 4ull * A.read_off[r + 1] + kSlotExtra * (r + 1));
     encode_read_body<P>(ma, mq, A.acids, A.quals, off, len, S);
-    S.flush();
-    A.pay_len[r] = S.total();
+    S.flush_states();
+    const uint32_t plen = S.total();
+    A.pay_len[r] = plen;
+    // the read's slices, complete, in front of the payload (the writer walks down): [01 acid idx][01 q idx] 02 u32be
+    // length u32be seq_len   (data.rs:57-84, compressor_block.rs:103-110), so that assembly is one copy per read
+    S.out.push_u32_le(__byte_perm(len, 0, 0x0123));
+    S.out.push_u32_le(__byte_perm(plen, 0, 0x0123));
+    S.out.push_bits(2u, 8);
+    S.out.drain();
+    if (A.switched) {
+        if (A.switched[A.n_reads + r]) {
+            S.out.push_bits(((uint32_t)A.cand_index[kMaxCand + A.chosen[A.n_reads + r]] << 8) | 1u, 16);
+            S.out.drain();
+        }
+        if (A.switched[r]) {  // acid first (compressor_block.rs:103-104)
+            S.out.push_bits(((uint32_t)A.cand_index[A.chosen[r]] << 8) | 1u, 16);
+            S.out.drain();
+        }
+    }
+    S.out.finish();
     if (S.bad) atomicOr(A.err, 1u);
 }
 
@@ -637,33 +663,12 @@ assemble_kernel(AssembleArgs A) {
     uint32_t b = A.read_block[r];
     unsigned long long dst = A.block_off[b] + 8 + (A.prefix_len ? A.prefix_len[b] : 0) + (A.fast ? 4 : 0) +
                              (A.slice_off[r] - A.slice_off[A.block_first[b]]);
-    uint32_t plen = A.pay_len[r];
-    uint32_t len = (uint32_t)(A.read_off[r + 1] - A.read_off[r]);
     uint32_t nsw = 0;
     if (A.switched) nsw = A.switched[r] + A.switched[A.n_reads + r];
-    if (dst + 2ull * nsw + 9 + plen > A.out_cap) return;  // IDN_E_NOSPACE is reported by the host from stats
-    uint8_t* p = A.out + dst;
-    if (A.switched) {
-        if (A.switched[r]) {  // acid first (compressor_block.rs:103-104)
-            *p++ = 1;
-            *p++ = A.cand_index[A.chosen[r]];
-        }
-        if (A.switched[A.n_reads + r]) {
-            *p++ = 1;
-            *p++ = A.cand_index[kMaxCand + A.chosen[A.n_reads + r]];
-        }
-    }
-    p[0] = 2;
-    p[1] = (uint8_t)(plen >> 24);
-    p[2] = (uint8_t)(plen >> 16);
-    p[3] = (uint8_t)(plen >> 8);
-    p[4] = (uint8_t)plen;
-    p[5] = (uint8_t)(len >> 24);
-    p[6] = (uint8_t)(len >> 16);
-    p[7] = (uint8_t)(len >> 8);
-    p[8] = (uint8_t)len;
-    const uint8_t* src = A.scratch + 4ull * A.read_off[r + 1] + 8ull * (r + 1) - plen;
-    copy_bytes_words(p + 9, src, plen);
+    const uint32_t total = 2u * nsw + 9u + A.pay_len[r];  // the encoder left the read's slices complete in its scratch slot
+    if (dst + total > A.out_cap) return;  // IDN_E_NOSPACE is reported by the host from stats
+    const uint8_t* src = A.scratch + 4ull * A.read_off[r + 1] + kSlotExtra * (r + 1) - total;
+    copy_bytes_words(A.out + dst, src, total);
 }
 
 // read -> block map (one thread per block fills its range; blocks are large, so use a grid-stride loop)
