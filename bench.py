@@ -220,7 +220,18 @@ def run_gpu(args, w: dict):
     dist = None
     if world > 1:
         import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=dev)
+        # stdout carries the one JSON line and nothing else: NCCL's version banner (NCCL_DEBUG=VERSION/WARN on some boxes)
+        # goes to stderr while the communicator is set up
+        sys.stdout.flush()
+        saved_stdout = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=dev)
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            os.dup2(saved_stdout, 1)
+            os.close(saved_stdout)
 
     ctx = capi.Context(local)
     L = ctx.L
@@ -474,7 +485,8 @@ def run_gpu(args, w: dict):
         if e2e:
             line["e2e"] = {"value": 2 * fq * e2e["steps"] * world / e2e["_t"] / 1e9, "unit": "GB/s",
                            "h2d_bytes_per_step": e2e["h2d"], "d2h_bytes_per_step": e2e["d2h"], "steps": e2e["steps"],
-                           "threads": e2e["threads"], "chunk_blocks": args.e2e_chunk_blocks, "compress_GBps": e2e["cGBps"], "decompress_GBps": e2e["dGBps"], "sample": e2e["sample"]}
+                           "threads": e2e["threads"], "chunk_blocks": args.e2e_chunk_blocks, "compress_GBps": e2e["cGBps"] * world, "decompress_GBps": e2e["dGBps"] * world,
+                           "per_direction_note": "rank 0's own phase times x n_gpus", "sample": e2e["sample"]}
         if cpu:
             line["cpu_baseline"] = cpu
         if fastq:
@@ -558,6 +570,11 @@ def run_e2e(args, w, capi, host, torch, local, chunks, acids_d, quals_d, read_of
     # the host-pointer calls are synchronous: overlap of H2D, kernels and D2H comes from several ctx in flight, so the
     # e2e leg uses smaller chunks than the device-resident leg (a short pipeline fill and tail)
     n_blocks_all = len(block_first_h) - 1
+    # a call should carry enough reads to fill the GPU (one thread per read: ~170 k in flight); blocks of long reads
+    # hold a few hundred reads each, so those workloads get more blocks per call, down to 3 calls per workload
+    reads_per_block = max(1, (len(read_off_h) - 1) // max(n_blocks_all, 1))
+    want = max(args.e2e_chunk_blocks, -(-131072 // reads_per_block))
+    args.e2e_chunk_blocks = max(1, min(want, max(args.e2e_chunk_blocks, -(-n_blocks_all // 3))))
     e2e_chunks = []
     for b0 in range(0, n_blocks_all, args.e2e_chunk_blocks):
         c = Chunk()

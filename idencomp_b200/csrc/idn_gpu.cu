@@ -106,6 +106,7 @@ struct idn_gpu_ctx {
     uint32_t* d_xpow = nullptr;     // [64]
     // workspaces of the *_dev paths
     DevBuf w_scratch, w_paylen, w_sizes, w_chosen, w_tiles, w_sliceoff, w_readblock, w_small, w_crcpart, w_crclen;
+    DevBuf w_walkdone;
     DevBuf w_lanefirst, w_laneoff, w_laneblock, w_blkinfo, w_nhdr;  // native mode
     uint32_t lane_syms = 2048;  // lane quantum of the native format (tools/lane_sweep.sh: decode is 17 % faster than at 4096 for +0.5 % size)
     // FASTQ text <-> symbols (idn_fastq.cuh): results of the last parse stay here until the next one
@@ -352,7 +353,7 @@ extern "C" void idn_gpu_destroy(idn_gpu_ctx* ctx) {
         if (s.used) s.free_all();
     DevBuf* bufs[] = {&ctx->w_scratch, &ctx->w_paylen,  &ctx->w_sizes,   &ctx->w_chosen,     &ctx->w_tiles,  &ctx->w_sliceoff,
                       &ctx->w_readblock, &ctx->w_small, &ctx->w_crcpart, &ctx->w_crclen,     &ctx->w_index,  &ctx->w_blk,
-                      &ctx->w_lanefirst, &ctx->w_laneoff, &ctx->w_laneblock, &ctx->w_blkinfo, &ctx->w_nhdr,
+                      &ctx->w_lanefirst, &ctx->w_laneoff, &ctx->w_laneblock, &ctx->w_blkinfo, &ctx->w_nhdr, &ctx->w_walkdone,
                       &ctx->f_text, &ctx->f_tilecnt, &ctx->f_tilebase, &ctx->f_linestart, &ctx->f_linefn, &ctx->f_linestate, &ctx->f_tilefn,
                       &ctx->f_tilestate, &ctx->f_recscan, &ctx->f_title, &ctx->f_namelo, &ctx->f_namelen, &ctx->f_readlen, &ctx->f_readoff,
                       &ctx->f_nameoff, &ctx->f_names, &ctx->f_acids, &ctx->f_quals, &ctx->f_err, &ctx->f_fmtoff, &ctx->f_fmttext,
@@ -1181,8 +1182,18 @@ static int32_t index_walk(idn_gpu_ctx* ctx, const uint8_t* blocks, const unsigne
     LAUNCHED("slot_count");
     scan_tiles_kernel<<<1, kScanBlock, 0, st>>>(bc.slots, B);
     LAUNCHED("scan_tiles");
+    CU(ctx->w_walkdone.ensure((size_t)B + 16));
+    // IDN_WALK=serial / fast overrides the choice (tests, experiments)
+    static const char* walk_env = getenv("IDN_WALK");
+    const bool fast = walk_env ? strcmp(walk_env, "fast") == 0 : B < kWalkFastMaxBlocks;
+    uint8_t* done = fast ? ctx->w_walkdone.as<uint8_t>() : nullptr;
+    if (done) {
+        walk_fast_kernel<<<B, kWalkFastThreads, 0, st>>>(blocks, block_off, block_len, B, blocks_bytes, dsp->model_type, n_models,
+                                                         bc.slots, ix, bc.reads, bc.syms, done);
+        LAUNCHED("walk_fast");
+    }
     walk_kernel<<<B, 32, 0, st>>>(blocks, block_off, block_len, B, blocks_bytes, dsp->model_type, n_models, bc.slots, ix, bc.reads,
-                                  bc.syms, const_cast<int32_t*>(dsp->status));
+                                  bc.syms, const_cast<int32_t*>(dsp->status), done);
     LAUNCHED("walk");
     scan_tiles_kernel<<<1, kScanBlock, 0, st>>>(bc.reads, B);
     LAUNCHED("scan_tiles");
