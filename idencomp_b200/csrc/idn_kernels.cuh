@@ -1125,16 +1125,22 @@ walk_kernel(const uint8_t* __restrict__ blocks, const unsigned long long* __rest
         // loop, so validation, model tracking and index building are left to the whole warp below ----
         uint32_t n_hdr = 0, p_end = p0;
         if (lane == 0) {
+            // the dependent chain per hop is p -> shared-memory load -> byte permute -> add: a Sequence slice (the rule) goes
+            // straight to p + 9 + length, every other slice type takes the side exit
             uint32_t p = p0;
             while (p < n_off && n_hdr < (uint32_t)kWalkMaxEnt && p + 9 <= kStaged) {
                 const uint32_t wi = p >> 2, sh = p & 3;
                 const uint32_t W0 = tw[wi], W1 = tw[wi + 1];
-                const uint32_t kind = (W0 >> (8 * sh)) & 0xffu;
                 const uint32_t w1 = __byte_perm(W0, W1, 0x1234u + sh * 0x1111u);  // bytes p+1 .. p+4, big endian
+                const uint32_t kind = (W0 >> (8 * sh)) & 0xffu;
                 plist[n_hdr++] = (uint16_t)p;
-                // Sequence: 9 + length; SwitchModel: 2; Identifiers: 6 + length; anything else, or a length that cannot
-                // be real, stops the chain here (the warp reports it)
-                uint32_t step = kind == 2 ? 9u + w1 : (kind == 1 ? 2u : 6u + w1);
+                if (kind == 2 && w1 <= 0x7fff0000u) {  // Sequence: 9 + length
+                    p = p + 9u + w1;
+                    continue;
+                }
+                // SwitchModel: 2; Identifiers: 6 + length; anything else, or a length that cannot be real, stops the
+                // chain here (the warp reports it)
+                uint32_t step = kind == 1 ? 2u : 6u + w1;
                 if (kind > 2 || w1 > 0x7fff0000u) step = 0x7fffffffu;
                 p = p + step > p ? p + step : 0x7fffffffu;
             }
