@@ -359,10 +359,9 @@ __device__ __forceinline__ void rans_put_count(uint32_t& x, uint2 e, uint32_t& b
     uint32_t freq = (e.y >> 14) & 0x3fffu;
     uint32_t start = e.y & 0x3fffu;
     uint32_t x_max = freq << (23 - kScaleBits + 8);
-    while (x >= x_max) {
-        bytes++;
-        x >>= 8;
-    }
+    const uint32_t k = (x >= x_max ? 1u : 0u) + ((x >> 8) >= x_max ? 1u : 0u);  // 0, 1 or 2 bytes (see rans_put_bf)
+    bytes += k;
+    x >>= 8 * k;
     uint32_t q = freq == 1 ? x : (__umulhi(x, e.x) >> (e.y >> 28));
     x = x + start + q * ((1u << kScaleBits) - freq);
 }

@@ -521,3 +521,23 @@ def test_walk_speculation_survives_header_lookalikes(gctx, O, toy_models, toy_ha
     crc = np.asarray([b[2] for b in blocks], dtype=np.uint32)
     ro, a, q = gctx.decompress_blocks(buf, doff, crc, toy_handles, block_len=dlen, name_off=reads.name_off, names=reads.names)
     assert np.array_equal(ro, reads.read_off) and np.array_equal(a, reads.acids) and np.array_equal(q, reads.quals)
+
+
+# ---- both slice walks ----------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("walk", ["serial", "fast"])
+def test_decode_side_with_either_slice_walk(walk):
+    """The library picks the parallel speculative walk for calls of fewer than 512 blocks (every container in this
+    file) and the one-warp-per-block walk above that and as the fallback.  IDN_WALK forces one of them for a whole
+    process (it is read once), so the decode-side tests run again in a child process under each setting."""
+    import os
+    import subprocess
+    import sys
+    from conftest import ROOT
+    sel = ("test_decode_1m_golden_container or test_round_trip_1k_device or test_errors or test_decode_container_chunk_in_place "
+           "or test_walk_skips_large_identifier_slices_and_long_reads or test_walk_speculation_survives_header_lookalikes "
+           "or test_model_selection_vs_oracle or test_empty_and_ragged_reads")
+    env = dict(os.environ, IDN_WALK=walk)
+    r = subprocess.run([sys.executable, "-m", "pytest", str(ROOT / "tests" / "test_gpu_parity.py"), "-x", "-q", "-m", "gpu", "-k", sel],
+                       env=env, capture_output=True, text=True, cwd=str(ROOT))
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
+    assert " passed" in r.stdout
