@@ -26,6 +26,10 @@ constexpr int kHist = 8;               // longest acid / q-score history any leg
 constexpr int kQLutBytes = 128;
 constexpr int kQStarts = 104;                            // 94 symbols + the total + padding up to 4 * 23 + 8 + 4
 constexpr int kQRowBytes = 352;                          // 128 + 2 * 104 = 336, rounded up to whole 32-byte sectors
+// q-score "window" rows (decoder): one 16-byte entry per 128-slot bucket = {first symbol s0 of the bucket, starts of the
+// symbols s0 .. s0+6}, i.e. bucket LUT and starts window in ONE gather (2 KB per row instead of 352 B, one dependent
+// load level less).  The compact row stays for slots the window cannot resolve and for the workload generator.
+constexpr int kQWinBytes = 128 * 16;
 
 // floor(x / d) for x < 2^31 as umulhi(x, m) >> s.  d = 2^k (k >= 1): m = 2^(32-k), s = 0; otherwise the round-up
 // reciprocal with s = ceil(log2 d) - 1 (the same argument as ryg's RansEncSymbolInit).  d <= 1 is never divided by.
@@ -154,12 +158,17 @@ __host__ __device__ constexpr SpecBuild make_spec(int kind, int ao, int qo, int 
 // multiply/reciprocal queue arithmetic into shifts and masks and deletes what the pair does not use.
 struct DynSpecs {
     static constexpr bool kStatic = false;
+    static constexpr bool kQWin = false;
     __host__ __device__ static constexpr SpecDev sa() { return make_spec(0, 0, 0, 0, 0).spec; }
     __host__ __device__ static constexpr SpecDev sq() { return make_spec(0, 0, 0, 0, 0).spec; }
 };
 template <int KA, int AOA, int QOA, int PBA, int QMA, int KQ, int AOQ, int QOQ, int PBQ, int QMQ>
 struct StaticSpecs {
     static constexpr bool kStatic = true;
+    // the decoder searches q-score symbols through the 2 KB "window" rows (one gather level less, 6 x the row footprint).
+    // Measured per bundled pair on the 10 GB workloads: NovaSeq (generic_ao2_qo1_pb6, 2 154 evenly used rows) decode
+    // 46.9 -> 44.1 ms; HiSeq (generic_ao0_qo2_pb6, a few hot rows) 34.4 -> 35.7 ms; Sequel II 25.6 -> 26.6 ms.
+    static constexpr bool kQWin = KQ == 0 && AOQ == 2 && QOQ == 1 && PBQ == 6;
     __host__ __device__ static constexpr SpecDev sa() { return make_spec(KA, AOA, QOA, PBA, QMA).spec; }
     __host__ __device__ static constexpr SpecDev sq() { return make_spec(KQ, AOQ, QOQ, PBQ, QMQ).spec; }
 };
@@ -173,6 +182,7 @@ struct ModelDev {
     uint32_t hmask;
     const uint2* enc;             // [n_rows][nsym] {rcp_freq, start | freq << 14 | rcp_shift << 28}
     const uint8_t* dec;           // acid: [n_rows] x 8 bytes = cum[1..4] u16; q: [n_rows] x kQRowBytes
+    const uint4* qwin;            // q-scores: [n_rows][128] window entries (kQWinBytes per row), or nullptr
     const uint2* adirect;         // acid, small dense spec spaces: the decode row of every spec (spec -> cum[1..4]), or nullptr
 };
 
@@ -408,6 +418,27 @@ __device__ __forceinline__ uint32_t q_find(const uint8_t* __restrict__ row, uint
     start = pair & 0xffffu;
     freq = (pair >> 16) - start;
     return 4 * g + j;
+}
+
+// q-score symbol search through the window rows: entry = u16[8] {s0, start(s0), ..., start(s0+6)} of the slot's bucket;
+// start(s0) <= slot by construction.  The six symbols s0 .. s0+5 resolve in registers; a slot beyond them (seven symbol
+// boundaries inside what is left of one 128-slot bucket) goes through the compact row.
+__device__ __forceinline__ uint32_t q_find_win(const uint4* __restrict__ win_row, const uint8_t* __restrict__ row, uint32_t slot,
+                                               uint32_t& start, uint32_t& freq) {
+    const uint4 w = __ldg(win_row + (slot >> 7));
+    const uint32_t K = (slot | 0x8000u) * 0x10001u;
+    // flags of start(s0+1) .. start(s0+6) <= slot (start(s0) always is): monotone
+    const uint32_t flags = ((K - w.y) & 0x80008000u) | (((K - w.z) & 0x80008000u) >> 1) | (((K - w.w) & 0x80008000u) >> 2);
+    const uint32_t j = __popc(flags);  // 0 .. 6: the slot lies in symbol s0 + j
+    if (j == 6) return q_find(row, slot, start, freq);  // start(s0+7) is not in the window
+    const uint32_t i = j + 1;          // u16 index of start(s0+j) in the entry
+    const uint32_t p = i >> 1;
+    const uint32_t w0 = p == 0 ? w.x : (p == 1 ? w.y : (p == 2 ? w.z : w.w));
+    const uint32_t w1 = p == 0 ? w.y : (p == 1 ? w.z : w.w);
+    const uint32_t pair = __funnelshift_r(w0, w1, 16 * (i & 1));
+    start = pair & 0xffffu;
+    freq = (pair >> 16) - start;
+    return (w.x & 0xffffu) + j;
 }
 
 }  // namespace idn

@@ -57,6 +57,7 @@ struct ModelSlot {
     void* d_enc = nullptr;
     void* d_dec = nullptr;
     void* d_adirect = nullptr;
+    void* d_qwin = nullptr;
     void free_all() {
         cudaFree(d_map);
         cudaFree(d_hkeys);
@@ -64,6 +65,8 @@ struct ModelSlot {
         cudaFree(d_enc);
         cudaFree(d_dec);
         cudaFree(d_adirect);
+        cudaFree(d_qwin);
+        d_qwin = nullptr;
         d_map = d_hkeys = d_hvals = d_enc = d_dec = d_adirect = nullptr;
         used = false;
     }
@@ -257,7 +260,7 @@ static const int32_t kStaticPairs[5][10] = {
 
 static int static_pair_index(const idn_gpu_ctx* ctx, int32_t acid_slot, int32_t q_slot) {
     // the specialised kernels index the dense spec -> row table without looking (ctx_row<true>)
-    if (!ctx->slots[acid_slot].dev.map || !ctx->slots[q_slot].dev.map || !ctx->slots[acid_slot].dev.adirect) return -1;
+    if (!ctx->slots[acid_slot].dev.map || !ctx->slots[q_slot].dev.map || !ctx->slots[acid_slot].dev.adirect || !ctx->slots[q_slot].dev.qwin) return -1;
     for (int i = 0; i < 5; i++) {
         bool same = true;
         for (int k = 0; k < 5; k++)
@@ -501,6 +504,23 @@ extern "C" int32_t idn_gpu_model_upload(idn_gpu_ctx* ctx, int32_t model_type, in
     CU(cudaMalloc(&slot.d_dec, dec.size()));
     CU(cudaMemcpy(slot.d_dec, dec.data(), dec.size(), cudaMemcpyHostToDevice));
     slot.dev.dec = (const uint8_t*)slot.d_dec;
+    // q-score window rows (kQWinBytes per row): bucket LUT and starts window in one 16-byte gather
+    if (model_type == IDN_MODEL_QSCORE && (size_t)n_rows * kQWinBytes <= ((size_t)256 << 20)) {
+        std::vector<uint16_t> win((size_t)n_rows * (kQWinBytes / 2));
+        for (uint32_t r = 0; r < n_rows; r++) {
+            const uint16_t* row = cum + (size_t)r * 95;
+            uint32_t sidx = 0;
+            for (uint32_t k = 0; k < 128; k++) {
+                while (row[sidx + 1] <= 128 * k) sidx++;  // the symbol that owns slot 128 k
+                uint16_t* e = win.data() + ((size_t)r * 128 + k) * 8;
+                e[0] = (uint16_t)sidx;
+                for (uint32_t t = 0; t < 7; t++) e[1 + t] = sidx + t < 94 ? row[sidx + t] : (uint16_t)total;
+            }
+        }
+        CU(cudaMalloc(&slot.d_qwin, win.size() * 2));
+        CU(cudaMemcpy(slot.d_qwin, win.data(), win.size() * 2, cudaMemcpyHostToDevice));
+        slot.dev.qwin = (const uint4*)slot.d_qwin;
+    }
     // acid decode rows per spec: the decoder's spec -> row -> cum-freqs chain becomes one gather
     if (model_type == IDN_MODEL_ACID && slot.dev.map && spec_num <= kDirectSpecLimit) {
         std::vector<uint64_t> direct(spec_num);

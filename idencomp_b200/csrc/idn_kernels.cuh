@@ -1614,7 +1614,11 @@ __device__ __forceinline__ void decode_read_body(const ModelDev& ma, const Model
 #endif
         const uint32_t slot_q = D.xq & kSlotMask, slot_a = D.xa & kSlotMask;
         uint32_t start, freq;
-        vq = q_find(mq.dec + (size_t)row_q * kQRowBytes, slot_q, start, freq);
+#ifndef IDN_NO_QWIN
+        if (P::kQWin) vq = q_find_win(mq.qwin + (size_t)row_q * (kQWinBytes / 16), mq.dec + (size_t)row_q * kQRowBytes, slot_q, start, freq);
+        else
+#endif
+            vq = q_find(mq.dec + (size_t)row_q * kQRowBytes, slot_q, start, freq);
         D.xq = freq * (D.xq >> kScaleBits) + slot_q - start;  // RansDecAdvanceStep
         va = acid_find(pk, slot_a, start, freq);
         D.xa = freq * (D.xa >> kScaleBits) + slot_a - start;
