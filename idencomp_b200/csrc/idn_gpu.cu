@@ -591,13 +591,19 @@ static int32_t launch_score(idn_gpu_ctx* ctx, const int32_t* ids, uint32_t n, co
             ModelPack<4> P;
             P.n = left < 4 ? left : 4;
             for (uint32_t k = 0; k < 4; k++) P.m[k] = ctx->slots[ids[k0 + (k < P.n ? k : 0)]].dev;
-            score_multi_kernel<4><<<grid, 128, 0, st>>>(P, batch->acids, batch->quals, batch->read_off, R, n_cols, k0, sizes, err);
+            bool dense = true;
+            for (uint32_t k = 0; k < 4; k++) dense = dense && P.m[k].map;
+            if (dense) score_multi_kernel<4, true><<<grid, 128, 0, st>>>(P, batch->acids, batch->quals, batch->read_off, R, n_cols, k0, sizes, err);
+            else score_multi_kernel<4, false><<<grid, 128, 0, st>>>(P, batch->acids, batch->quals, batch->read_off, R, n_cols, k0, sizes, err);
             k0 += P.n;
         } else {
             ModelPack<2> P;
             P.n = left;
             for (uint32_t k = 0; k < 2; k++) P.m[k] = ctx->slots[ids[k0 + (k < P.n ? k : 0)]].dev;
-            score_multi_kernel<2><<<grid, 128, 0, st>>>(P, batch->acids, batch->quals, batch->read_off, R, n_cols, k0, sizes, err);
+            bool dense = true;
+            for (uint32_t k = 0; k < 2; k++) dense = dense && P.m[k].map;
+            if (dense) score_multi_kernel<2, true><<<grid, 128, 0, st>>>(P, batch->acids, batch->quals, batch->read_off, R, n_cols, k0, sizes, err);
+            else score_multi_kernel<2, false><<<grid, 128, 0, st>>>(P, batch->acids, batch->quals, batch->read_off, R, n_cols, k0, sizes, err);
             k0 += P.n;
         }
         LAUNCHED("score");

@@ -46,25 +46,22 @@ struct BackReader {  // bytes at decreasing addresses
 struct FwdReader {  // bytes at increasing addresses
     const uint32_t* wp;
     uint32_t word;
-    int lane;
-    bool loaded;
+    int lane;  // byte of `word` the next get() returns, - 4 while that word is not loaded yet
     __device__ __forceinline__ void start(const uint8_t* first) {  // the next get() returns *first
         const uintptr_t a = reinterpret_cast<uintptr_t>(first);
         wp = reinterpret_cast<const uint32_t*>(a & ~(uintptr_t)3);
-        lane = (int)(a & 3);
-        loaded = false;
+        lane = (int)(a & 3) - 4;
         word = 0;
     }
     __device__ __forceinline__ uint32_t get() {
-        if (!loaded) {
+        if (lane < 0) {
             word = __ldg(wp);
-            loaded = true;
+            lane += 4;
         }
         const uint32_t b = (word >> (8 * lane)) & 0xffu;
         if (++lane == 4) {
-            lane = 0;
+            lane = -4;
             wp++;
-            loaded = false;
         }
         return b;
     }
@@ -149,7 +146,8 @@ struct ModelPack {
     uint32_t n;
 };
 
-template <int M>
+// kDense: every model of the pack has the dense spec -> row table (no hash fallback in the loop)
+template <int M, bool kDense>
 __global__ void __launch_bounds__(128)
 score_multi_kernel(const ModelPack<M> P, const uint8_t* __restrict__ acids, const uint8_t* __restrict__ quals,
                    const uint64_t* __restrict__ read_off, uint64_t n_reads, uint32_t n_cols, uint32_t col0,
@@ -190,7 +188,7 @@ score_multi_kernel(const ModelPack<M> P, const uint8_t* __restrict__ acids, cons
         for (int k = 0; k < M; k++)
             if (k < (int)P.n) {
                 const ModelDev& m = P.m[k];
-                uint32_t row = ctx_row(m, g[k].spec(m.spec, pf.pos, pbmax - m.spec.pb));
+                uint32_t row = ctx_row<kDense>(m, g[k].spec(m.spec, pf.pos, pbmax - m.spec.pb));
                 e[k] = __ldg(m.enc + (size_t)row * m.nsym + (m.type == 0 ? a : q));
             }
 #pragma unroll
