@@ -1309,7 +1309,6 @@ walk_fast_kernel(const uint8_t* __restrict__ blocks, const unsigned long long* _
     __shared__ unsigned long long s_syms[kWalkFastThreads];
     __shared__ uint32_t s_cnt[kWalkFastThreads];
     __shared__ uint32_t s_set[kWalkFastThreads];   // models set inside the piece: acid | q << 8, 0xff = none
-    __shared__ uint32_t s_need[kWalkFastThreads];  // bit 0 / 1: a Sequence slice came before the piece set an acid / q model
     const uint32_t b = blockIdx.x, t = threadIdx.x;
     if (b >= n_blocks) return;
     if (t == 0) done[b] = 0;
@@ -1355,7 +1354,7 @@ walk_fast_kernel(const uint8_t* __restrict__ blocks, const unsigned long long* _
         }
 
     // 2. count along the piece [start, next)
-    uint32_t cnt = 0, set = 0xffffu, need = 0;
+    uint32_t cnt = 0, set = 0xffffu, need = 0;  // need bit 0 / 1: a Sequence slice came before the piece set an acid / q model
     unsigned long long syms = 0, p = start;
     bool ok = true;
     if (start != kWalkNone) {
@@ -1381,7 +1380,6 @@ walk_fast_kernel(const uint8_t* __restrict__ blocks, const unsigned long long* _
     s_cnt[t] = cnt;
     s_syms[t] = syms;
     s_set[t] = set;
-    s_need[t] = need;
     if (!__syncthreads_and(ok)) return;  // done[b] stays 0
 
     // 3. what the piece starts with: reads and symbols before it, models active when it is entered
