@@ -1259,6 +1259,7 @@ walk_kernel(const uint8_t* __restrict__ blocks, const unsigned long long* __rest
 constexpr int kWalkFastThreads = 128;
 constexpr int kWalkDepth = 6;
 constexpr uint32_t kWalkFastMaxBlocks = 512;
+constexpr int kWalkFixRounds = 8;  // false starts dropped per block before the serial walk takes over
 constexpr unsigned long long kWalkNone = ~0ull;
 
 struct WalkHdr {
@@ -1309,6 +1310,7 @@ walk_fast_kernel(const uint8_t* __restrict__ blocks, const unsigned long long* _
     __shared__ unsigned long long s_syms[kWalkFastThreads];
     __shared__ uint32_t s_cnt[kWalkFastThreads];
     __shared__ uint32_t s_set[kWalkFastThreads];   // models set inside the piece: acid | q << 8, 0xff = none
+    __shared__ int s_fail, s_giveup;
     const uint32_t b = blockIdx.x, t = threadIdx.x;
     if (b >= n_blocks) return;
     if (t == 0) done[b] = 0;
@@ -1345,42 +1347,91 @@ walk_fast_kernel(const uint8_t* __restrict__ blocks, const unsigned long long* _
         }
     }
     s_start[t] = start;
+    if (t == 0) {
+        s_fail = kWalkFastThreads;
+        s_giveup = 0;
+    }
     __syncthreads();
-    unsigned long long next = n;  // where the following piece starts
-    for (uint32_t j = t + 1; j < (uint32_t)kWalkFastThreads; j++)
-        if (s_start[j] != kWalkNone) {
-            next = s_start[j];
-            break;
-        }
 
-    // 2. count along the piece [start, next)
+    // 2. count along the piece [start, next), next = the following thread's start.  A start that only LOOKS true can
+    // survive the hop test by landing on a true header (e.g. a payload that ends "02 00 00" in front of a header
+    // "02 00 ..." reads as a Sequence slice of 512 bytes): then the piece before it overshoots it.  Thread 0 starts at
+    // the true beginning, so the lowest thread whose piece does not end at `next` is on the true chain and its overshoot
+    // proves that `next` is false: that start is dropped and the piece is extended, one false start per round.
+    unsigned long long next = n, piece_next = kWalkNone;
     uint32_t cnt = 0, set = 0xffffu, need = 0;  // need bit 0 / 1: a Sequence slice came before the piece set an acid / q model
-    unsigned long long syms = 0, p = start;
-    bool ok = true;
-    if (start != kWalkNone) {
-        while (p < next) {
-            const WalkHdr h = walk_load_hdr(blk + p, buf_lo, buf_hi);
-            const unsigned long long sz = walk_slice_size(h, n - p, n_models);
-            if (!sz) {
-                ok = false;
+    unsigned long long syms = 0, p = 0;
+    uint32_t state = 0;  // 0 joins, 1 valid headers but the piece ends past `next`, 2 an invalid header
+    bool all_ok = false;
+    for (int round = 0; round < kWalkFixRounds; round++) {
+        start = s_start[t];
+        next = n;  // where the following piece starts
+        for (uint32_t j = t + 1; j < (uint32_t)kWalkFastThreads; j++)
+            if (s_start[j] != kWalkNone) {
+                next = s_start[j];
                 break;
             }
-            if (h.kind == 2) {
-                cnt++;
-                syms += h.w2;
-                need |= ((set & 0xffu) == 0xffu ? 1u : 0u) | ((set >> 8) == 0xffu ? 2u : 0u);
-            } else if (h.kind == 1) {
-                const uint32_t idx = h.w1 >> 24;
-                set = model_type[idx] == 0 ? ((set & 0xff00u) | idx) : ((set & 0x00ffu) | (idx << 8));
+        if (start == kWalkNone) {
+            state = 0;
+            cnt = 0;
+            syms = 0;
+            set = 0xffffu;
+            need = 0;
+        } else if (next != piece_next) {  // first round, or the piece grew
+            piece_next = next;
+            cnt = 0;
+            syms = 0;
+            set = 0xffffu;
+            need = 0;
+            state = 0;
+            p = start;
+            while (p < next) {
+                const WalkHdr h = walk_load_hdr(blk + p, buf_lo, buf_hi);
+                const unsigned long long sz = walk_slice_size(h, n - p, n_models);
+                if (!sz) {
+                    state = 2;
+                    break;
+                }
+                if (h.kind == 2) {
+                    cnt++;
+                    syms += h.w2;
+                    need |= ((set & 0xffu) == 0xffu ? 1u : 0u) | ((set >> 8) == 0xffu ? 2u : 0u);
+                } else if (h.kind == 1) {
+                    const uint32_t idx = h.w1 >> 24;
+                    set = model_type[idx] == 0 ? ((set & 0xff00u) | idx) : ((set & 0x00ffu) | (idx << 8));
+                }
+                p += sz;
             }
-            p += sz;
+            if (state == 0 && p != next) state = 1;
         }
-        ok = ok && p == next;
+        if (state) atomicMin(&s_fail, (int)t);
+        __syncthreads();
+        const int f = s_fail;
+        __syncthreads();  // everybody has read s_fail before thread f resets it
+        if (f == kWalkFastThreads) {
+            all_ok = true;
+            break;
+        }
+        if ((int)t == f) {
+            if (state == 1 && next != n) {
+                for (uint32_t j = t + 1; j < (uint32_t)kWalkFastThreads; j++)
+                    if (s_start[j] == next) {
+                        s_start[j] = kWalkNone;
+                        break;
+                    }
+            } else {
+                s_giveup = 1;  // a bad header on the true chain, or a chain that runs past the block: walk_kernel reports it
+            }
+            s_fail = kWalkFastThreads;
+        }
+        __syncthreads();
+        if (s_giveup) return;  // done[b] stays 0
     }
+    if (!all_ok) return;
     s_cnt[t] = cnt;
     s_syms[t] = syms;
     s_set[t] = set;
-    if (!__syncthreads_and(ok)) return;  // done[b] stays 0
+    __syncthreads();
 
     // 3. what the piece starts with: reads and symbols before it, models active when it is entered
     unsigned long long first_read = 0, first_sym = 0;

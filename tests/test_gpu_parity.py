@@ -523,6 +523,29 @@ def test_walk_speculation_survives_header_lookalikes(gctx, O, toy_models, toy_ha
     assert np.array_equal(ro, reads.read_off) and np.array_equal(a, reads.acids) and np.array_equal(q, reads.quals)
 
 
+def test_walk_drops_false_starts_that_rejoin_the_chain(gctx, toy_handles):
+    """A payload that ends 02 00 00 in front of a Sequence header 02 00 00 00 41 reads, three bytes early, as a Sequence
+    slice of 0x200 bytes, and with 74-byte slices that false slice ends exactly on a true header (3 + 7 * 74 = 521): the
+    speculative walk's hop test cannot tell such a start from a true one.  The piece before it overshoots it, which is
+    how it is found and dropped.  The index must come out as the serial walk's."""
+    rng = np.random.default_rng(11)
+    blocks, expect = [], []
+    for n_reads in (20000, 7000):
+        parts = [b"\x01\x00\x01\x01"]
+        for i in range(n_reads):
+            pay = bytearray(rng.integers(3, 256, size=65, dtype=np.uint8).tobytes())  # no byte looks like a slice type
+            if i % 40 == 7:
+                pay[-3:] = b"\x02\x00\x00"
+            parts.append(b"\x02" + (65).to_bytes(4, "big") + (100 + i % 3).to_bytes(4, "big") + bytes(pay))
+        blocks.append(b"".join(parts))
+        expect.append((n_reads, sum(100 + i % 3 for i in range(n_reads))))
+    buf = np.frombuffer(b"".join(blocks), dtype=np.uint8)
+    off = np.asarray([0, len(blocks[0]), len(buf)], dtype=np.uint64)
+    n_reads, n_syms, bf = gctx.index_blocks(buf, off, toy_handles)
+    assert n_reads == sum(e[0] for e in expect) and n_syms == sum(e[1] for e in expect)
+    assert bf.tolist() == [0, expect[0][0], expect[0][0] + expect[1][0]]
+
+
 # ---- both slice walks ----------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("walk", ["serial", "fast"])
 def test_decode_side_with_either_slice_walk(walk):
@@ -535,7 +558,7 @@ def test_decode_side_with_either_slice_walk(walk):
     from conftest import ROOT
     sel = ("test_decode_1m_golden_container or test_round_trip_1k_device or test_errors or test_decode_container_chunk_in_place "
            "or test_walk_skips_large_identifier_slices_and_long_reads or test_walk_speculation_survives_header_lookalikes "
-           "or test_model_selection_vs_oracle or test_empty_and_ragged_reads")
+           "or test_model_selection_vs_oracle or test_empty_and_ragged_reads or test_walk_drops_false_starts_that_rejoin_the_chain")
     env = dict(os.environ, IDN_WALK=walk)
     r = subprocess.run([sys.executable, "-m", "pytest", str(ROOT / "tests" / "test_gpu_parity.py"), "-x", "-q", "-m", "gpu", "-k", sel],
                        env=env, capture_output=True, text=True, cwd=str(ROOT))
