@@ -32,6 +32,7 @@ if str(ROOT) not in sys.path:
 
 MODELS = ROOT / "models"
 BLOCK_SYMBOLS = 4 * 1024 * 1024  # IdnCompressorParams::max_block_total_len default, idn/compressor.rs:187
+E2E_READS_PER_CALL = 16384       # e2e leg: reads a host-pointer call should carry at least (PacBio-shaped sweep: 25 blocks 31.5, 50-64 blocks 44-45, 200 blocks 41.6 GB/s)
 
 # SURVEY.md 8d.  fastq_overhead = bytes of a FASTQ record besides the 2*L symbol characters: '@' + name + '\n',
 # '\n' after the acids, "+\n", '\n' after the quality scores.
@@ -573,8 +574,9 @@ def run_e2e(args, w, capi, host, torch, local, chunks, acids_d, quals_d, read_of
     # a call should carry enough reads to fill the GPU (one thread per read: ~170 k in flight); blocks of long reads
     # hold a few hundred reads each, so those workloads get more blocks per call, down to 3 calls per workload
     reads_per_block = max(1, (len(read_off_h) - 1) // max(n_blocks_all, 1))
-    want = max(args.e2e_chunk_blocks, -(-131072 // reads_per_block))
-    args.e2e_chunk_blocks = max(1, min(want, max(args.e2e_chunk_blocks, -(-n_blocks_all // 3))))
+    if args.e2e_chunk_blocks <= 0:  # automatic
+        want = max(32, -(-E2E_READS_PER_CALL // reads_per_block))
+        args.e2e_chunk_blocks = max(1, min(want, max(32, -(-n_blocks_all // 3))))
     e2e_chunks = []
     for b0 in range(0, n_blocks_all, args.e2e_chunk_blocks):
         c = Chunk()
@@ -738,7 +740,8 @@ def main():
     ap.add_argument("--no-other-mode", action="store_true", help="skip the short run of the other container format")
     ap.add_argument("--lane-symbols", type=int, default=0, help="native mode lane quantum (default: the library's 4096)")
     ap.add_argument("--e2e-threads", type=int, default=3)
-    ap.add_argument("--e2e-chunk-blocks", type=int, default=32, help="blocks per host-pointer call in the e2e leg")
+    ap.add_argument("--e2e-chunk-blocks", type=int, default=0,
+                    help="blocks per host-pointer call in the e2e leg (default: 32, more for long reads so that a call holds ~E2E_READS_PER_CALL reads)")
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--e2e-profile", action="store_true", help="print the host-side phase times of the e2e leg to stderr")
     args = ap.parse_args()
