@@ -30,7 +30,7 @@ EXPORTS = [
     "idn_gpu_launch_count", "idn_gpu_model_upload", "idn_gpu_model_release", "idn_gpu_score", "idn_gpu_score_dev",
     "idn_gpu_compress_blocks", "idn_gpu_compress_blocks_dev", "idn_gpu_compress_bound", "idn_gpu_index_blocks",
     "idn_gpu_decompress_blocks", "idn_gpu_decompress_blocks_dev", "idn_gpu_decompress_reads", "idn_gpu_block_crc",
-    "idn_gpu_synth_reads_dev", "idn_gpu_profile", "idn_gpu_profile_read", "idn_gpu_set_lane_symbols",
+    "idn_gpu_synth_reads_dev", "idn_gpu_profile", "idn_gpu_profile_read", "idn_gpu_set_lane_symbols", "idn_gpu_set_walk",
     "idn_gpu_fastq_parse", "idn_gpu_fastq_parse_dev", "idn_gpu_fastq_fetch", "idn_gpu_fastq_batch_dev", "idn_gpu_fastq_format",
     "idn_gpu_fastq_format_dev",
 ]
@@ -139,6 +139,8 @@ def load():
     L.idn_gpu_fastq_format_dev.restype = i32
     L.idn_gpu_set_lane_symbols.argtypes = [vp, u32]
     L.idn_gpu_set_lane_symbols.restype = i32
+    L.idn_gpu_set_walk.argtypes = [vp, i32]
+    L.idn_gpu_set_walk.restype = i32
     L.idn_gpu_profile.argtypes = [vp, i32]
     L.idn_gpu_profile.restype = i32
     L.idn_gpu_profile_read.argtypes = [vp, C.c_char_p, u64]
@@ -218,6 +220,10 @@ class Context:
 
     def set_lane_symbols(self, n: int):
         self.check(self.L.idn_gpu_set_lane_symbols(self.h, n))
+
+    def set_walk(self, mode: int):
+        """0 automatic, 1 one-warp-per-block slice walk, 2 parallel speculative walk first (include/idn_gpu.h)"""
+        self.check(self.L.idn_gpu_set_walk(self.h, mode))
 
     def profile(self, enable: bool):
         self.check(self.L.idn_gpu_profile(self.h, int(enable)))

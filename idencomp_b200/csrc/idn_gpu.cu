@@ -105,6 +105,7 @@ struct idn_gpu_ctx {
     ModelDev* d_models = nullptr;  // [kMaxSlots], mirrors slots[].dev
     ModelDev d_models_host0{};     // all-zero placeholder for the by-value model parameters of the non-uniform kernels
     int sm_count = 148;
+    int32_t walk_mode = 0;  // idn_gpu_set_walk
     uint32_t* d_crc_tab = nullptr;  // [256]
     uint32_t* d_xpow = nullptr;     // [64]
     // workspaces of the *_dev paths
@@ -327,6 +328,7 @@ extern "C" int32_t idn_gpu_create(int32_t device, idn_gpu_ctx** out) {
     if (n <= 0 || device < 0 || device >= n) return IDN_E_CUDA;  // no CPU fallback
     idn_gpu_ctx* ctx = new idn_gpu_ctx();
     ctx->device = device;
+    if (const char* w = getenv("IDN_WALK")) ctx->walk_mode = strcmp(w, "serial") == 0 ? 1 : (strcmp(w, "fast") == 0 ? 2 : 0);
     auto bail = [&](const char* what) {
         fprintf(stderr, "idn_gpu_create: %s failed: %s\n", what, cudaGetErrorString(cudaGetLastError()));
         delete ctx;
@@ -370,6 +372,13 @@ extern "C" void idn_gpu_destroy(idn_gpu_ctx* ctx) {
     if (ctx->ev) cudaEventDestroy(ctx->ev);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
+}
+
+extern "C" int32_t idn_gpu_set_walk(idn_gpu_ctx* ctx, int32_t mode) {
+    if (!ctx) return IDN_E_INVALID_ARG;
+    if (mode < 0 || mode > 2) return fail(ctx, IDN_E_INVALID_ARG, "walk mode %d", mode);
+    ctx->walk_mode = mode;
+    return IDN_OK;
 }
 
 extern "C" int32_t idn_gpu_set_lane_symbols(idn_gpu_ctx* ctx, uint32_t lane_syms) {
@@ -1209,9 +1218,7 @@ static int32_t index_walk(idn_gpu_ctx* ctx, const uint8_t* blocks, const unsigne
     scan_tiles_kernel<<<1, kScanBlock, 0, st>>>(bc.slots, B);
     LAUNCHED("scan_tiles");
     CU(ctx->w_walkdone.ensure((size_t)B + 16));
-    // IDN_WALK=serial / fast overrides the choice (tests, experiments)
-    static const char* walk_env = getenv("IDN_WALK");
-    const bool fast = walk_env ? strcmp(walk_env, "fast") == 0 : B < kWalkFastMaxBlocks;
+    const bool fast = ctx->walk_mode == 0 ? B < kWalkFastMaxBlocks : ctx->walk_mode == 2;
     uint8_t* done = fast ? ctx->w_walkdone.as<uint8_t>() : nullptr;
     if (done) {
         walk_fast_kernel<<<B, kWalkFastThreads, 0, st>>>(blocks, block_off, block_len, B, blocks_bytes, dsp->model_type, n_models,

@@ -70,6 +70,12 @@ const char *idn_gpu_last_error(const idn_gpu_ctx *ctx);
 /* lane quantum of IDN_MODE_NATIVE compression: a lane holds the reads whose first symbol falls into the same run of
  * `lane_syms` symbols of the block (default 2048); the value travels in the container, decoders need no setting */
 int32_t idn_gpu_set_lane_symbols(idn_gpu_ctx *ctx, uint32_t lane_syms);
+/* decode side, compat containers: which slice walk indexes the blocks (IdnBlockDecompressor::next_sequence_internal,
+ * idn/decompressor_block.rs:115-129).  0 = automatic (the parallel speculative walk for calls of fewer than 512 blocks,
+ * the one-warp-per-block walk otherwise and as its fallback), 1 = always the one-warp-per-block walk, 2 = always try the
+ * parallel walk first.  Results do not depend on the setting; the environment variable IDN_WALK=serial|fast sets the
+ * default of new contexts. */
+int32_t idn_gpu_set_walk(idn_gpu_ctx *ctx, int32_t mode);
 /* number of kernel launches this ctx has issued since creation (bench.py's gpu_launches) */
 uint64_t idn_gpu_launch_count(const idn_gpu_ctx *ctx);
 

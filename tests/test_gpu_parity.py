@@ -546,6 +546,60 @@ def test_walk_drops_false_starts_that_rejoin_the_chain(gctx, toy_handles):
     assert bf.tolist() == [0, expect[0][0], expect[0][0] + expect[1][0]]
 
 
+def test_both_walks_agree_on_mutated_containers(gctx, O, toy_models, toy_handles, reads_1k):
+    """Fuzz: random byte flips, truncations and splices of a valid multi-block container.  The parallel walk (with the
+    serial walk as its fallback) and the serial walk alone must give the same answer for every input -- the same index
+    totals, or the same error kind -- and neither may fault."""
+    from idencomp_b200.capi import IdnGpuError
+    bf = blocks_of(reads_1k, 9000)
+    out, block_off, crc, _ = gctx.compress_blocks(reads_1k.read_off, reads_1k.acids, reads_1k.quals, bf, toy_handles,
+                                                  name_off=reads_1k.name_off, names=reads_1k.names,
+                                                  prefix_len=np.full(len(bf) - 1, 40, dtype=np.uint32))
+    nb = len(bf) - 1
+    doff = np.append(block_off[:-1] + 8, block_off[-1]).astype(np.uint64)
+    dlen = (block_off[1:] - block_off[:-1] - 8).astype(np.uint32)
+    base = out.copy()
+    for b in range(nb):  # a syntactically valid Identifiers slice in the reserved prefix: 00 u32be(34) 01 + 34 bytes
+        lo = int(doff[b])
+        base[lo:lo + 6] = np.frombuffer(b"\x00" + (34).to_bytes(4, "big") + b"\x01", dtype=np.uint8)
+    rng = np.random.default_rng(2024)
+
+    def run(buf, off, ln, mode):
+        gctx.set_walk(mode)
+        try:
+            n_reads, n_syms, first = gctx.index_blocks(buf, off, toy_handles, block_len=ln)
+            return ("ok", n_reads, n_syms, first.tolist())
+        except IdnGpuError as e:
+            return ("err", e.kind)
+        finally:
+            gctx.set_walk(0)
+
+    n_err = 0
+    for it in range(150):
+        buf, off, ln = base.copy(), doff.copy(), dlen.copy()
+        kind = it % 5
+        if kind == 0:    # flip a few bits inside one block (one bad block: the error kind cannot depend on a race between blocks)
+            b = int(rng.integers(0, nb))
+            for p in rng.integers(int(doff[b]), int(doff[b]) + int(dlen[b]), size=int(rng.integers(1, 4))):
+                buf[p] ^= np.uint8(1 << int(rng.integers(0, 8)))
+        elif kind == 1:  # corrupt a slice header field of a random read
+            b = int(rng.integers(0, nb))
+            p = int(doff[b]) + 40 + int(rng.integers(0, 200))
+            buf[p] = np.uint8(rng.integers(0, 4))
+        elif kind == 2:  # truncate a block
+            b = int(rng.integers(0, nb))
+            ln[b] -= np.uint32(rng.integers(1, 60))
+        elif kind == 3:  # plant slice look-alikes inside a payload
+            p = int(rng.integers(int(doff[0]) + 200, len(buf) - 40))
+            buf[p:p + 9] = np.frombuffer(b"\x02\x00\x00\x00\x10\x00\x00\x00\x05", dtype=np.uint8)
+        else:            # valid as it is
+            pass
+        a, c = run(buf, off, ln, 2), run(buf, off, ln, 1)
+        assert a == c, f"iteration {it} (mutation {kind}): parallel walk {a} vs serial walk {c}"
+        n_err += a[0] == "err"
+    assert 10 < n_err < 150  # the mutations did exercise both outcomes
+
+
 # ---- both slice walks ----------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("walk", ["serial", "fast"])
 def test_decode_side_with_either_slice_walk(walk):
