@@ -189,7 +189,7 @@ score_multi_kernel(const ModelPack<M> P, const uint8_t* __restrict__ acids, cons
             if (k < (int)P.n) {
                 const ModelDev& m = P.m[k];
                 uint32_t row = ctx_row<kDense>(m, g[k].spec(m.spec, pf.pos, pbmax - m.spec.pb));
-                e[k] = __ldg(m.enc + (size_t)row * m.nsym + (m.type == 0 ? a : q));
+                e[k] = __ldg(m.enc + (row * m.nsym + (m.type == 0 ? a : q)));
             }
 #pragma unroll
         for (int k = 0; k < M; k++)
@@ -402,8 +402,8 @@ __device__ __forceinline__ void encode_read_body(const ModelDev& ma, const Model
     rows_next(row_a, row_q);  // generators at len-1, entry 0 = symbol len-1
     uint2 ea = make_uint2(0, 0), eq = make_uint2(0, 0);
     if (len) {
-        ea = __ldg(ma.enc + (size_t)row_a * kAcidSyms + (raw_a & 7u));
-        eq = __ldg(mq.enc + (size_t)row_q * kQSyms + ((uint32_t)raw_q & 127u));
+        ea = __ldg(ma.enc + (row_a * kAcidSyms + (raw_a & 7u)));
+        eq = __ldg(mq.enc + (row_q * kQSyms + ((uint32_t)raw_q & 127u)));
     }
     rows_next(row_a, row_q);  // generators at len-2
 #pragma unroll 1
@@ -411,8 +411,8 @@ __device__ __forceinline__ void encode_read_body(const ModelDev& ma, const Model
         // entries of position i-1 (generators stand at i-1: entry 0), gathered while position i is coded
         uint2 ea_n = make_uint2(0, 0), eq_n = make_uint2(0, 0);
         if (i >= 1) {
-            ea_n = __ldg(ma.enc + (size_t)row_a * kAcidSyms + (raw_a & 7u));
-            eq_n = __ldg(mq.enc + (size_t)row_q * kQSyms + ((uint32_t)raw_q & 127u));
+            ea_n = __ldg(ma.enc + (row_a * kAcidSyms + (raw_a & 7u)));
+            eq_n = __ldg(mq.enc + (row_q * kQSyms + ((uint32_t)raw_q & 127u)));
         }
         rows_next(row_a, row_q);  // generators to i-2
         rans_put_bf(S.x0, ea, S.out);  // put_at(0, acid) then put_at(1, q)   compressor.rs:95-96
@@ -1662,10 +1662,10 @@ __device__ __forceinline__ void decode_read_body(const ModelDev& ma, const Model
         const uint32_t slot_q = D.xq & kSlotMask, slot_a = D.xa & kSlotMask;
         uint32_t start, freq;
 #ifndef IDN_NO_QWIN
-        if (P::kQWin) vq = q_find_win(mq.qwin + (size_t)row_q * (kQWinBytes / 16), mq.dec + (size_t)row_q * kQRowBytes, slot_q, start, freq);
+        if (P::kQWin) vq = q_find_win(mq.qwin + row_q * (uint32_t)(kQWinBytes / 16), mq.dec + row_q * (uint32_t)kQRowBytes, slot_q, start, freq);
         else
 #endif
-            vq = q_find(mq.dec + (size_t)row_q * kQRowBytes, slot_q, start, freq);
+            vq = q_find(mq.dec + row_q * (uint32_t)kQRowBytes, slot_q, start, freq);
         D.xq = freq * (D.xq >> kScaleBits) + slot_q - start;  // RansDecAdvanceStep
         va = acid_find(pk, slot_a, start, freq);
         D.xa = freq * (D.xa >> kScaleBits) + slot_a - start;
@@ -1821,7 +1821,7 @@ synth_kernel(const ModelDev* __restrict__ models, int32_t ia, int32_t iq, const 
         uint32_t row_q = ctx_row(mq, gq.spec(sq, pf.pos, psq));
         uint2 pk = __ldg(reinterpret_cast<const uint2*>(ma.dec) + row_a);
         uint32_t a = acid_find(pk, slot_a, start, freq);
-        uint32_t q = q_find(mq.dec + (size_t)row_q * kQRowBytes, slot_q, start, freq);
+        uint32_t q = q_find(mq.dec + row_q * (uint32_t)kQRowBytes, slot_q, start, freq);
         // a context the model never saw maps to the uniform dummy row; drawing from it would leave the statistics the
         // model was trained on for good (uniform symbols lead to more unseen contexts), which real reads do not do:
         // keep the previous quality score and draw a plain base instead
