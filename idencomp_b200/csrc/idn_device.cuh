@@ -331,25 +331,9 @@ struct GenBack {
 };
 
 // ---------------------------------------------------------------------------------------------------
-// rANS encode step (RansEncPutSymbol).  `emit(byte)` receives renormalisation bytes in emission order
-// (the reference writes them at decreasing addresses).
-// ---------------------------------------------------------------------------------------------------
-template <class Emit>
-__device__ __forceinline__ void rans_put(uint32_t& x, uint2 e, Emit&& emit) {
-    uint32_t freq = (e.y >> 14) & 0x3fffu;
-    uint32_t start = e.y & 0x3fffu;
-    uint32_t x_max = freq << (23 - kScaleBits + 8);  // ((L >> scale_bits) << 8) * freq
-    while (x >= x_max) {
-        emit(x & 0xffu);
-        x >>= 8;
-    }
-    // exact floor(x / freq); ryg's reciprocal (rcp_freq, rcp_shift) is exact for x < 2^31, freq >= 2
-    uint32_t q = freq == 1 ? x : (__umulhi(x, e.x) >> (e.y >> 28));
-    x = x + start + q * ((1u << kScaleBits) - freq);
-}
-
-// The same step without branches, for the encoder kernels: a state emits 0, 1 or 2 bytes per symbol (x < 2^31 and
-// x_max >= 2^17), `out` is a BackWriter-like sink with push_bits(bytes in emission order, 8 * count).
+// rANS encode step (RansEncPutSymbol: while (x >= x_max) { *--ptr = x & 0xff; x >>= 8; } then the reciprocal
+// division), without branches: a state emits 0, 1 or 2 bytes per symbol (x < 2^31 and x_max >= 2^17).  `out` is a
+// BackWriter-like sink with push_bits(bytes in emission order, 8 * count).
 template <class Out>
 __device__ __forceinline__ void rans_put_bf(uint32_t& x, uint2 e, Out& out) {
     const uint32_t freq = (e.y >> 14) & 0x3fffu;

@@ -5,7 +5,7 @@
 //   K4  encode_kernel     SequenceCompressor::compress        sequence_compressor.rs:82-155, compressor.rs:83-98
 //       layout/assemble   BlockWriter                         idn/writer_block.rs:27-82
 //   K5  decode_kernel     SequenceDecompressor::decompress    sequence_compressor.rs:231-278, compressor.rs:173-193
-//       index kernels     IdnBlockDecompressor slice walk     idn/decompressor_block.rs:115-129,194-239
+//       walk_fast_kernel / walk_kernel   IdnBlockDecompressor slice walk   idn/decompressor_block.rs:115-129,194-239
 //   K7  crc kernels       crc32 over name|acids|quals         writer_block.rs:64, sequence.rs:381-394
 #pragma once
 #include "idn_device.cuh"
