@@ -640,11 +640,13 @@ __device__ __forceinline__ void copy_bytes_words(uint8_t* __restrict__ d, const 
     const uint32_t* sw = reinterpret_cast<const uint32_t*>(s2 - sh);
     uint32_t* dw = reinterpret_cast<uint32_t*>(d + head);
     if (sh == 0) {
-        for (uint32_t i = 0; i < words; i++) dw[i] = sw[i];
+#pragma unroll 4
+        for (uint32_t i = 0; i < words; i++) dw[i] = __ldg(sw + i);
     } else if (words) {
-        uint32_t lo = sw[0];
+        uint32_t lo = __ldg(sw);
+#pragma unroll 4
         for (uint32_t i = 0; i < words; i++) {
-            uint32_t hi = sw[i + 1];  // holds at least one byte of the range: 4 * (i + 1) - sh < 4 * words + ... <= n - head
+            uint32_t hi = __ldg(sw + i + 1);  // holds at least one byte of the range: 4 * (i + 1) - sh < 4 * words + ... <= n - head
             dw[i] = __funnelshift_r(lo, hi, 8 * sh);
             lo = hi;
         }
