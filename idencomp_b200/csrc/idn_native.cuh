@@ -101,7 +101,7 @@ struct EncodeLaneArgs {
 };
 
 template <bool kUniform, class P>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, kUniform ? IDN_ENC_MINB : 1)
 encode_lane_kernel(EncodeLaneArgs A, const ModelDev MA, const ModelDev MQ) {
     uint64_t l = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (l >= *A.n_lanes_dev) return;
@@ -527,7 +527,7 @@ struct DecodeLaneArgs {
 };
 
 template <bool kUniform, class P>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, kUniform ? IDN_DEC_MINB : 1)
 decode_lane_kernel(DecodeLaneArgs A, const ModelDev MA, const ModelDev MQ) {
     __shared__ uint32_t s_tab[256];
     __shared__ uint32_t s_xpow[64];
