@@ -110,7 +110,7 @@ struct idn_gpu_ctx {
     uint32_t* d_xpow = nullptr;     // [64]
     // workspaces of the *_dev paths
     DevBuf w_scratch, w_paylen, w_sizes, w_chosen, w_tiles, w_sliceoff, w_readblock, w_small, w_crcpart, w_crclen;
-    DevBuf w_walkdone;
+    DevBuf w_walkdone, w_blockadj;
     DevBuf w_lanefirst, w_laneoff, w_laneblock, w_blkinfo, w_nhdr;  // native mode
     uint32_t lane_syms = 2048;  // lane quantum of the native format (tools/lane_sweep.sh: decode is 17 % faster than at 4096 for +0.5 % size)
     // FASTQ text <-> symbols (idn_fastq.cuh): results of the last parse stay here until the next one
@@ -358,7 +358,7 @@ extern "C" void idn_gpu_destroy(idn_gpu_ctx* ctx) {
         if (s.used) s.free_all();
     DevBuf* bufs[] = {&ctx->w_scratch, &ctx->w_paylen,  &ctx->w_sizes,   &ctx->w_chosen,     &ctx->w_tiles,  &ctx->w_sliceoff,
                       &ctx->w_readblock, &ctx->w_small, &ctx->w_crcpart, &ctx->w_crclen,     &ctx->w_index,  &ctx->w_blk,
-                      &ctx->w_lanefirst, &ctx->w_laneoff, &ctx->w_laneblock, &ctx->w_blkinfo, &ctx->w_nhdr, &ctx->w_walkdone,
+                      &ctx->w_lanefirst, &ctx->w_laneoff, &ctx->w_laneblock, &ctx->w_blkinfo, &ctx->w_nhdr, &ctx->w_walkdone, &ctx->w_blockadj,
                       &ctx->f_text, &ctx->f_tilecnt, &ctx->f_tilebase, &ctx->f_linestart, &ctx->f_linefn, &ctx->f_linestate, &ctx->f_tilefn,
                       &ctx->f_tilestate, &ctx->f_recscan, &ctx->f_title, &ctx->f_namelo, &ctx->f_namelen, &ctx->f_readlen, &ctx->f_readoff,
                       &ctx->f_nameoff, &ctx->f_names, &ctx->f_acids, &ctx->f_quals, &ctx->f_err, &ctx->f_fmtoff, &ctx->f_fmttext,
@@ -808,8 +808,10 @@ extern "C" int32_t idn_gpu_compress_blocks_dev(idn_gpu_ctx* ctx, const idn_batch
     } else {
         CU(cudaMemsetAsync(slice_off, 0, 8, st));
     }
+    CU(ctx->w_blockadj.ensure(((size_t)B + 1) * 8));
     block_layout_kernel<<<1, 32, 0, st>>>(slice_off, batch->block_first_read, B, prefix_len, fast,
-                                          reinterpret_cast<unsigned long long*>(block_off), out, out_cap, dsp->stats);
+                                          reinterpret_cast<unsigned long long*>(block_off), out, out_cap, dsp->stats,
+                                          ctx->w_blockadj.as<unsigned long long>());
     LAUNCHED("block_layout");
     if (R > 0) {
         read_block_kernel<<<B, 256, 0, st>>>(batch->block_first_read, B, ctx->w_readblock.as<uint32_t>());
@@ -820,11 +822,8 @@ extern "C" int32_t idn_gpu_compress_blocks_dev(idn_gpu_ctx* ctx, const idn_batch
         aa.pay_len = ctx->w_paylen.as<uint32_t>();
         aa.scratch = ctx->w_scratch.as<uint8_t>();
         aa.slice_off = slice_off;
-        aa.block_off = reinterpret_cast<unsigned long long*>(block_off);
-        aa.block_first = batch->block_first_read;
+        aa.block_adj = ctx->w_blockadj.as<unsigned long long>();
         aa.read_block = ctx->w_readblock.as<uint32_t>();
-        aa.prefix_len = prefix_len;
-        aa.fast = fast;
         aa.chosen = chosen;
         aa.switched = switched;
         aa.cand_index = dsp->cand_index;

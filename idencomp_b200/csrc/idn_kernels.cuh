@@ -582,13 +582,15 @@ __global__ void __launch_bounds__(32)
 block_layout_kernel(const unsigned long long* __restrict__ slice_off, const uint32_t* __restrict__ block_first,
                     uint32_t n_blocks, const uint32_t* __restrict__ prefix_len, int fast,
                     unsigned long long* __restrict__ block_off /*[n_blocks+1]*/, uint8_t* __restrict__ out,
-                    uint64_t out_cap, unsigned long long* __restrict__ stats /*[8]*/) {
+                    uint64_t out_cap, unsigned long long* __restrict__ stats /*[8]*/,
+                    unsigned long long* __restrict__ block_adj /*[n_blocks]: slice_off[r] + block_adj[b] = where read r's slices go*/) {
     if (threadIdx.x != 0) return;
     unsigned long long pos = 0;
     for (uint32_t b = 0; b < n_blocks; b++) {
         block_off[b] = pos;
         unsigned long long body = slice_off[block_first[b + 1]] - slice_off[block_first[b]];
         bool empty = block_first[b + 1] == block_first[b];
+        block_adj[b] = pos + 8 + (prefix_len ? prefix_len[b] : 0) + (fast ? 4 : 0) - slice_off[block_first[b]];
         unsigned long long extra = (prefix_len ? prefix_len[b] : 0) + ((fast && !empty) ? 4 : 0);
         unsigned long long length = body + extra;
         if (pos + 8 <= out_cap) {
@@ -617,11 +619,8 @@ struct AssembleArgs {
     const uint32_t* pay_len;
     const uint8_t* scratch;
     const unsigned long long* slice_off;
-    const unsigned long long* block_off;
-    const uint32_t* block_first;
+    const unsigned long long* block_adj;  // [n_blocks], block_layout_kernel
     const uint32_t* read_block;  // [n_reads] block of each read
-    const uint32_t* prefix_len;
-    int fast;
     const uint8_t* chosen;    // [2][n_reads] or nullptr
     const uint8_t* switched;  // [2][n_reads] or nullptr
     const uint8_t* cand_index;  // [2][kMaxCand] candidate -> SwitchModel index (position in models[])
@@ -660,9 +659,7 @@ __global__ void __launch_bounds__(128)
 assemble_kernel(AssembleArgs A) {
     uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= A.n_reads) return;
-    uint32_t b = A.read_block[r];
-    unsigned long long dst = A.block_off[b] + 8 + (A.prefix_len ? A.prefix_len[b] : 0) + (A.fast ? 4 : 0) +
-                             (A.slice_off[r] - A.slice_off[A.block_first[b]]);
+    const unsigned long long dst = A.slice_off[r] + A.block_adj[A.read_block[r]];
     uint32_t nsw = 0;
     if (A.switched) nsw = A.switched[r] + A.switched[A.n_reads + r];
     const uint32_t total = 2u * nsw + 9u + A.pay_len[r];  // the encoder left the read's slices complete in its scratch slot
