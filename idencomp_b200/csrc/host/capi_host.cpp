@@ -4,6 +4,7 @@
 #include <cstring>
 #include <string>
 
+#include "clustering.hpp"
 #include "idn.hpp"
 #include "model.hpp"
 
@@ -119,11 +120,6 @@ extern "C" int32_t idn_host_quantise(const float* probs, uint32_t nsym, uint32_t
 }
 
 // ---- IdnCompressor / IdnDecompressor ---------------------------------------------------------------------------------
-namespace idencomp {
-std::vector<size_t> cluster_centroids(const std::vector<uint32_t>& cost, size_t n_values, size_t n_centroids, size_t num_clusters,
-                                      std::vector<std::vector<size_t>>* members);
-std::vector<size_t> rank_models(const std::vector<uint32_t>& cost, size_t n_values, size_t n_models, size_t model_num);
-}  // namespace idencomp
 
 struct idn_host_compressor {
     std::vector<uint8_t> out;
@@ -277,17 +273,48 @@ extern "C" const uint64_t* idn_host_decoded_name_off(const idn_host_decoded* d) 
 extern "C" const uint8_t* idn_host_decoded_names(const idn_host_decoded* d) { return d->names.data(); }
 extern "C" void idn_host_decoded_free(idn_host_decoded* d) { delete d; }
 
-extern "C" uint32_t idn_host_cluster(const uint32_t* cost, uint64_t n_values, uint32_t n_centroids, uint32_t num_clusters,
-                                     uint32_t* centroids_out, uint32_t* value_cluster_out) {
+struct idn_host_clustering {
+    Clustering c;
+};
+extern "C" idn_host_clustering* idn_host_clustering_new(void) { return new idn_host_clustering(); }
+extern "C" void idn_host_clustering_free(idn_host_clustering* c) { delete c; }
+
+extern "C" uint32_t idn_host_cluster(idn_host_clustering* state, const uint32_t* cost, uint64_t n_values, uint32_t n_centroids,
+                                     uint32_t num_clusters, uint32_t* centroids_out, uint32_t* value_cluster_out) {
     std::vector<uint32_t> c(cost, cost + n_values * n_centroids);
     std::vector<std::vector<size_t>> members;
-    std::vector<size_t> best = cluster_centroids(c, n_values, n_centroids, num_clusters, &members);
+    Clustering fresh;
+    std::vector<size_t> best = (state ? state->c : fresh).make_clusters(c, n_values, n_centroids, num_clusters, &members);
     for (size_t k = 0; k < best.size(); k++) {
         if (centroids_out) centroids_out[k] = (uint32_t)best[k];
         if (value_cluster_out)
             for (size_t v : members[k]) value_cluster_out[v] = (uint32_t)k;
     }
     return (uint32_t)best.size();
+}
+
+// known-answer hooks for the restated third-party generators (clustering.hpp)
+extern "C" void idn_host_splitmix64(uint64_t seed, uint32_t n, uint64_t* out) {
+    SplitMix64 g(seed);
+    for (uint32_t i = 0; i < n; i++) out[i] = g.next_u64();
+}
+extern "C" void idn_host_xoshiro256pp(const uint64_t* state4, uint64_t seed, uint32_t n, uint64_t* out) {
+    Xoshiro256PlusPlus g = state4 ? Xoshiro256PlusPlus(state4) : Xoshiro256PlusPlus(seed);
+    for (uint32_t i = 0; i < n; i++) out[i] = g.next_u64();
+}
+// rand 0.8.5 `index::sample(&mut Xoshiro256PlusPlus::seed_from_u64(seed), length, amount)`, amount < 12; with draws != NULL the
+// generator is replaced by the given u32 sequence (hand-computed cases)
+extern "C" uint32_t idn_host_sample_indices(uint64_t seed, uint32_t length, uint32_t amount, uint32_t* out) {
+    if (amount > length || amount >= 12) return 0;
+    Xoshiro256PlusPlus g(seed);
+    std::vector<uint32_t> v = sample_floyd(g, length, amount);
+    for (size_t i = 0; i < v.size(); i++) out[i] = v[i];
+    return (uint32_t)v.size();
+}
+extern "C" uint32_t idn_host_gen_range(uint64_t seed, uint32_t high, uint32_t n, uint32_t* out) {
+    Xoshiro256PlusPlus g(seed);
+    for (uint32_t i = 0; i < n; i++) out[i] = g.gen_range_inclusive(high);
+    return n;
 }
 
 extern "C" uint32_t idn_host_rank(const uint32_t* cost, uint64_t n_values, uint32_t n_models, uint32_t model_num, uint32_t* models_out) {

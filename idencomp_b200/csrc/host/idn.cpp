@@ -1,6 +1,8 @@
 // idn.cpp -- see idn.hpp.  Host orchestration only: every symbol goes through the C-ABI of libidn_gpu.so.
 #include "idn.hpp"
 
+#include "clustering.hpp"
+
 #include <dlfcn.h>
 #include <zlib.h>
 
@@ -125,133 +127,7 @@ struct Brotli {
     }
 };
 
-// ---- Clustering (clustering.rs:21-118).  Xoshiro256PlusPlus::seed_from_u64(404) + rand 0.8.5 choose_multiple restated
-// from the published algorithms of rand_xoshiro 0.6.0 / rand 0.8.5 (SplitMix64 seeding, Floyd's sampling for small
-// amounts, widening-multiply range sampling).  PARITY UNPINNED against the Rust crates: the reference's own test of
-// this code (clustering.rs:232-271) only checks the converged, sorted clusters, which tests/ reproduces.
-struct Xoshiro256PlusPlus {
-    uint64_t s[4];
-    explicit Xoshiro256PlusPlus(uint64_t seed) {  // seed_from_u64: SplitMix64 stream
-        for (auto& w : s) {
-            seed += 0x9E3779B97F4A7C15ull;
-            uint64_t z = seed;
-            z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
-            z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
-            w = z ^ (z >> 31);
-        }
-    }
-    static uint64_t rotl(uint64_t x, int k) { return (x << k) | (x >> (64 - k)); }
-    uint64_t next_u64() {
-        uint64_t r = rotl(s[0] + s[3], 23) + s[0];
-        uint64_t t = s[1] << 17;
-        s[2] ^= s[0];
-        s[3] ^= s[1];
-        s[1] ^= s[2];
-        s[0] ^= s[3];
-        s[2] ^= t;
-        s[3] = rotl(s[3], 45);
-        return r;
-    }
-    uint32_t next_u32() { return (uint32_t)(next_u64() >> 32); }
-    uint32_t gen_range_inclusive(uint32_t high) {  // UniformInt<u32>::sample_single_inclusive(0, high)
-        uint32_t range = high + 1;
-        if (range == 0) return next_u32();
-        uint32_t zone = (range << __builtin_clz(range)) - 1;
-        for (;;) {
-            uint64_t m = (uint64_t)next_u32() * range;
-            if ((uint32_t)m <= zone) return (uint32_t)(m >> 32);
-        }
-    }
-};
-
-// rand::seq::index::sample for amount < 12: Floyd's algorithm with insertion (fully shuffled variant)
-std::vector<uint32_t> sample_floyd(Xoshiro256PlusPlus& rng, uint32_t length, uint32_t amount) {
-    std::vector<uint32_t> idx;
-    for (uint32_t j = length - amount; j < length; j++) {
-        uint32_t t = rng.gen_range_inclusive(j);
-        auto pos = std::find(idx.begin(), idx.end(), t);
-        if (pos != idx.end()) {
-            idx.insert(pos, j);
-            continue;
-        }
-        idx.push_back(t);
-    }
-    return idx;
-}
-
 }  // namespace
-
-// cost[value * n_centroids + centroid]; returns the centroid index of every cluster, in cluster order
-std::vector<size_t> cluster_centroids(const std::vector<uint32_t>& cost, size_t n_values, size_t n_centroids, size_t num_clusters,
-                                      std::vector<std::vector<size_t>>* members) {
-    std::vector<size_t> best;
-    if (num_clusters == 0) return best;
-    num_clusters = std::min(num_clusters, n_centroids);
-    Xoshiro256PlusPlus rng(404);
-    std::vector<bool> avail(n_centroids, true);
-    std::vector<size_t> value_cluster(n_values, 0);
-    auto best_centroid_for = [&](const std::vector<size_t>& vals) {
-        std::vector<uint32_t> sum(n_centroids, 0);
-        for (size_t v : vals)
-            for (size_t c = 0; c < n_centroids; c++) sum[c] += cost[v * n_centroids + c];
-        size_t pick = n_centroids;
-        for (size_t c = 0; c < n_centroids; c++)  // stable sort by cost, first available
-            if (avail[c] && (pick == n_centroids || sum[c] < sum[pick])) pick = c;
-        return pick;
-    };
-    size_t amount = std::min(num_clusters, n_values);  // choose_multiple yields at most `len` items
-    for (uint32_t v : sample_floyd(rng, (uint32_t)n_values, (uint32_t)amount)) {
-        size_t c = best_centroid_for({v});
-        best.push_back(c);
-        avail[c] = false;
-    }
-    for (;;) {
-        size_t cluster_changes = 0, centroid_changes = 0;
-        for (size_t v = 0; v < n_values; v++) {
-            size_t pick = 0;
-            for (size_t k = 1; k < best.size(); k++)
-                if (cost[v * n_centroids + best[k]] < cost[v * n_centroids + best[pick]]) pick = k;
-            if (value_cluster[v] != pick) {
-                value_cluster[v] = pick;
-                cluster_changes++;
-            }
-        }
-        std::fill(avail.begin(), avail.end(), true);
-        for (size_t k = 0; k < best.size(); k++) {
-            std::vector<size_t> vals;
-            for (size_t v = 0; v < n_values; v++)
-                if (value_cluster[v] == k) vals.push_back(v);
-            size_t c = best_centroid_for(vals);
-            if (best[k] != c) {
-                best[k] = c;
-                centroid_changes++;
-            }
-            avail[c] = false;
-        }
-        if (cluster_changes == 0 && centroid_changes == 0) break;
-    }
-    if (members) {
-        members->assign(best.size(), {});
-        for (size_t v = 0; v < n_values; v++) (*members)[value_cluster[v]].push_back(v);
-    }
-    return best;
-}
-
-// get_model_ranking (idn/model_chooser.rs:103-138): per read, models sorted by size (stable) get rank 1, 2, ...; the
-// models with the smallest rank sums win (stable)
-std::vector<size_t> rank_models(const std::vector<uint32_t>& cost, size_t n_values, size_t n_models, size_t model_num) {
-    std::vector<uint32_t> score(n_models, 0);
-    std::vector<size_t> order(n_models);
-    for (size_t v = 0; v < n_values; v++) {
-        std::iota(order.begin(), order.end(), 0);
-        std::stable_sort(order.begin(), order.end(), [&](size_t a, size_t b) { return cost[v * n_models + a] < cost[v * n_models + b]; });
-        for (size_t i = 0; i < n_models; i++) score[order[i]] += (uint32_t)i + 1;
-    }
-    std::iota(order.begin(), order.end(), 0);
-    std::stable_sort(order.begin(), order.end(), [&](size_t a, size_t b) { return score[a] < score[b]; });
-    order.resize(std::min(model_num, n_models));
-    return order;
-}
 
 // ---- DeviceModels ---------------------------------------------------------------------------------------------------
 DeviceModels::~DeviceModels() {
@@ -320,13 +196,14 @@ void IdnCompressor::make_block() {
 }
 
 std::vector<ModelIdentifier> IdnCompressor::best_models(ModelType type, size_t model_num, const std::vector<uint32_t>& sizes,
-                                                        const std::vector<size_t>& cols, size_t n_cols, size_t n_reads) {
+                                                        const std::vector<size_t>& cols, size_t n_cols, size_t n_reads,
+                                                        Clustering& clustering) {
     // cost matrix of this type's models only
     const size_t n = cols.size();
     std::vector<uint32_t> cost(n_reads * n);
     for (size_t r = 0; r < n_reads; r++)
         for (size_t k = 0; k < n; k++) cost[r * n + k] = sizes[r * n_cols + cols[k]];
-    std::vector<size_t> pick = params_.quality >= 2 ? cluster_centroids(cost, n_reads, n, model_num, nullptr)  // CLUSTERING_THRESHOLD
+    std::vector<size_t> pick = params_.quality >= 2 ? clustering.make_clusters(cost, n_reads, n, model_num, nullptr)  // CLUSTERING_THRESHOLD
                                                     : rank_models(cost, n_reads, n, model_num);
     std::vector<ModelIdentifier> ids;
     for (size_t k : pick) ids.push_back(params_.model_provider[cols[k]].identifier());
@@ -358,10 +235,13 @@ void IdnCompressor::initialize() {
             int32_t rc = idn_gpu_score(dev_.ctx(), &b, dev_.handles().data(), (uint32_t)mp.len(), sizes.data());
             if (rc) dev_.raise(rc);
         }
+        // ONE Clustering (one random stream) serves the acid models and then the q-score models, as the reference's
+        // ModelChooser does (model_chooser.rs:14-24, compressor_initializer.rs:57-64)
+        Clustering clustering;
         for (int t = 0; t < 2; t++) {
             std::vector<ModelIdentifier> got;
             if (of_type[t].size() == 1) got = {mp[of_type[t][0]].identifier()};
-            else got = best_models((ModelType)t, model_num, sizes, of_type[t], mp.len(), n_reads);
+            else got = best_models((ModelType)t, model_num, sizes, of_type[t], mp.len(), n_reads, clustering);
             ids.insert(ids.end(), got.begin(), got.end());
         }
     }

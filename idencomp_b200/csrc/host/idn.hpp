@@ -111,7 +111,7 @@ private:
     void flush_batch();
     void initialize();  // CompressorInitializer::initialize (idn/compressor_initializer.rs:33-74)
     std::vector<ModelIdentifier> best_models(ModelType type, size_t model_num, const std::vector<uint32_t>& sizes,
-                                             const std::vector<size_t>& cols, size_t n_cols, size_t n_reads);
+                                             const std::vector<size_t>& cols, size_t n_cols, size_t n_reads, class Clustering& clustering);
 
     Sink sink_;
     IdnCompressorParams params_;

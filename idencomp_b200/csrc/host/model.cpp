@@ -132,7 +132,7 @@ Model::Model(ModelType type, ContextSpecType spec_type, std::vector<ModelContext
         if (c.symbol_prob.size() != nsym) throw ModelError("context has the wrong number of symbols");
         std::sort(c.specs.begin(), c.specs.end());
     }
-    if (contexts_.size() > 65535) throw ModelError("model has more than 65535 contexts");  // check_model, :209-219
+    if (contexts_.size() > 65536) throw ModelError("model has more than 65536 contexts");  // check_model, sequence_compressor.rs:209-219
     std::stable_sort(contexts_.begin(), contexts_.end(),
                      [](const ModelContext& a, const ModelContext& b) { return a.specs < b.specs; });  // map_contexts
     const uint64_t n = spec_.spec_num();

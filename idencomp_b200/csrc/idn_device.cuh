@@ -20,12 +20,19 @@ constexpr uint32_t kAcidSyms = 5, kQSyms = 94;
 constexpr uint32_t kSlotMask = (1u << kScaleBits) - 1;
 constexpr uint32_t kRansL = 1u << 23;  // RANS_BYTE_L
 constexpr int kHist = 8;               // longest acid / q-score history any legal spec type uses
-// q-score decode row: 128-byte bucket LUT (slot >> 7 -> (symbol that owns the bucket's first slot) >> 2) + the row's
-// cumulative frequencies as u16 "starts" (starts[s] = cum[s], everything from index 94 on = 2^14).  The search loads
-// the 8 starts from 4 * LUT on (two 8-byte loads) and resolves the symbol in registers.
+// q-score decode row (512 bytes): 128-byte bucket LUT (slot >> 7 -> (symbol that owns the bucket's first slot) >> 2) followed
+// by 24 overlapping 16-byte windows, window g = the cumulative frequencies ("starts", u16) of the symbols 4g .. 4g+7
+// (everything from symbol 94 on = 2^14).  The search reads one LUT byte and then ONE 16-byte window (a single gather
+// request: the kernels are bound by the number of divergent memory requests, profiles/r2_ncu_*.md) and resolves the symbol
+// in registers.
 constexpr int kQLutBytes = 128;
-constexpr int kQStarts = 104;                            // 94 symbols + the total + padding up to 4 * 23 + 8 + 4
-constexpr int kQRowBytes = 352;                          // 128 + 2 * 104 = 336, rounded up to whole 32-byte sectors
+#ifndef IDN_QROW352
+constexpr int kQWindows = 24;                            // g = 0 .. 23 (s0 <= 93; the window of g = 23 ends at 2^14: no advance)
+constexpr int kQRowBytes = kQLutBytes + 16 * kQWindows;  // 512
+#else  // round-1 layout, kept for A/B measurements: LUT + the 104 starts once, the window is two 8-byte loads
+constexpr int kQStarts = 104;
+constexpr int kQRowBytes = 352;
+#endif
 // q-score "window" rows (decoder): one 16-byte entry per 128-slot bucket = {first symbol s0 of the bucket, starts of the
 // symbols s0 .. s0+6}, i.e. bucket LUT and starts window in ONE gather (2 KB per row instead of 352 B, one dependent
 // load level less).  The compact row stays for slots the window cannot resolve and for the workload generator.
@@ -178,12 +185,14 @@ struct ModelDev {
     uint32_t type, nsym, n_rows;  // n_rows = n_ctx + 1, row 0 = dummy context
     const uint16_t* map;          // dense spec -> row, or nullptr
     const uint32_t* hkeys;        // open-addressing hash (sparse spec types)
-    const uint16_t* hvals;
+    const uint32_t* hvals;        // row per key (u32: a model may hold 65 536 contexts + the dummy row, sequence_compressor.rs:209-219)
     uint32_t hmask;
     const uint2* enc;             // [n_rows][nsym] {rcp_freq, start | freq << 14 | rcp_shift << 28}
     const uint8_t* dec;           // acid: [n_rows] x 8 bytes = cum[1..4] u16; q: [n_rows] x kQRowBytes
     const uint4* qwin;            // q-scores: [n_rows][128] window entries (kQWinBytes per row), or nullptr
     const uint2* adirect;         // acid, small dense spec spaces: the decode row of every spec (spec -> cum[1..4]), or nullptr
+    const uint2* aenc;            // acid, small dense spec spaces: the encoder entries of every spec, [spec][5] (spec -> row -> entry
+                                  // becomes ONE gather in the encoder and the scorer), or nullptr
 };
 
 __device__ __forceinline__ uint32_t hash32(uint32_t k) {
@@ -373,36 +382,62 @@ __device__ __forceinline__ uint32_t acid_find(uint2 packed, uint32_t slot, uint3
 // q-score symbol search in a decode row (layout above): bucket LUT -> window of 8 starts -> compare in registers.
 // starts[4g] <= slot holds by construction; the window resolves the symbols 4g .. 4g+6 (the freq of a symbol needs the
 // next start).  A slot beyond them (>= 4 symbols inside what is left of a 128-slot bucket: only in the flat tail of
-// a distribution) moves the window on by 4 symbols.
+// a distribution) moves on to the next window (4 symbols further).
+#ifndef IDN_QROW352
 __device__ __forceinline__ uint32_t q_find(const uint8_t* __restrict__ row, uint32_t slot, uint32_t& start,
                                            uint32_t& freq) {
     uint32_t g = __ldg(row + (slot >> 7));
-    const uint2* starts = reinterpret_cast<const uint2*>(row + kQLutBytes);
+    const uint4* wins = reinterpret_cast<const uint4*>(row + kQLutBytes);
     // halves of K - W: bit 15 set <=> slot >= start (K = 0x8000 | slot in both halves, starts <= 2^14: no borrow)
     const uint32_t K = (slot | 0x8000u) * 0x10001u;
-    uint2 lo = __ldg(starts + g), hi = __ldg(starts + g + 1);
+    uint4 w = __ldg(wins + g);
     uint32_t flags;
     for (;;) {
-        flags = ((K - lo.x) & 0x80008000u) | (((K - lo.y) & 0x80008000u) >> 1) | (((K - hi.x) & 0x80008000u) >> 2) |
-                (((K - hi.y) & 0x80008000u) >> 3);
+        flags = ((K - w.x) & 0x80008000u) | (((K - w.y) & 0x80008000u) >> 1) | (((K - w.z) & 0x80008000u) >> 2) |
+                (((K - w.w) & 0x80008000u) >> 3);
 #ifndef IDN_ABL_NOADV
         if (!(flags & 0x10000000u)) break;  // bit 28 = the last start of the window: still <= slot -> move on
         g++;
-        lo = hi;
-        hi = __ldg(starts + g + 1);
+        w = __ldg(wins + g);
 #else
         break;
 #endif
     }
     const uint32_t j = __popc(flags) - 1;  // index of the last start <= slot (the flags are monotone)
     const uint32_t p = j >> 1;
-    const uint32_t w0 = p == 0 ? lo.x : (p == 1 ? lo.y : (p == 2 ? hi.x : hi.y));
-    const uint32_t w1 = p == 0 ? lo.y : (p == 1 ? hi.x : hi.y);
+    const uint32_t w0 = p == 0 ? w.x : (p == 1 ? w.y : (p == 2 ? w.z : w.w));
+    const uint32_t w1 = p == 0 ? w.y : (p == 1 ? w.z : w.w);
     const uint32_t pair = __funnelshift_r(w0, w1, 16 * (j & 1));  // starts[j] | starts[j+1] << 16
     start = pair & 0xffffu;
     freq = (pair >> 16) - start;
     return 4 * g + j;
 }
+#else
+__device__ __forceinline__ uint32_t q_find(const uint8_t* __restrict__ row, uint32_t slot, uint32_t& start,
+                                           uint32_t& freq) {
+    uint32_t g = __ldg(row + (slot >> 7));
+    const uint2* starts = reinterpret_cast<const uint2*>(row + kQLutBytes);
+    const uint32_t K = (slot | 0x8000u) * 0x10001u;
+    uint2 lo = __ldg(starts + g), hi = __ldg(starts + g + 1);
+    uint32_t flags;
+    for (;;) {
+        flags = ((K - lo.x) & 0x80008000u) | (((K - lo.y) & 0x80008000u) >> 1) | (((K - hi.x) & 0x80008000u) >> 2) |
+                (((K - hi.y) & 0x80008000u) >> 3);
+        if (!(flags & 0x10000000u)) break;
+        g++;
+        lo = hi;
+        hi = __ldg(starts + g + 1);
+    }
+    const uint32_t j = __popc(flags) - 1;
+    const uint32_t p = j >> 1;
+    const uint32_t w0 = p == 0 ? lo.x : (p == 1 ? lo.y : (p == 2 ? hi.x : hi.y));
+    const uint32_t w1 = p == 0 ? lo.y : (p == 1 ? hi.x : hi.y);
+    const uint32_t pair = __funnelshift_r(w0, w1, 16 * (j & 1));
+    start = pair & 0xffffu;
+    freq = (pair >> 16) - start;
+    return 4 * g + j;
+}
+#endif
 
 // q-score symbol search through the window rows: entry = u16[8] {s0, start(s0), ..., start(s0+6)} of the slot's bucket;
 // start(s0) <= slot by construction.  The six symbols s0 .. s0+5 resolve in registers; a slot beyond them (seven symbol

@@ -57,6 +57,7 @@ struct ModelSlot {
     void* d_enc = nullptr;
     void* d_dec = nullptr;
     void* d_adirect = nullptr;
+    void* d_aenc = nullptr;
     void* d_qwin = nullptr;
     void free_all() {
         cudaFree(d_map);
@@ -65,8 +66,9 @@ struct ModelSlot {
         cudaFree(d_enc);
         cudaFree(d_dec);
         cudaFree(d_adirect);
+        cudaFree(d_aenc);
         cudaFree(d_qwin);
-        d_qwin = nullptr;
+        d_qwin = d_aenc = nullptr;
         d_map = d_hkeys = d_hvals = d_enc = d_dec = d_adirect = nullptr;
         used = false;
     }
@@ -250,19 +252,28 @@ struct SmallParams {
 // Kernels specialised at compile time for the (acid spec type, q-score spec type) pairs of the bundled same-sequencer
 // model files; every other pair runs the run-time-generic kernels (DynSpecs).  kind: 0 generic, 1 light.
 //                          acids: kind ao qo pb qm      q-scores: kind ao qo pb qm
-using SP0 = StaticSpecs<1, 8, 0, 0, 1, 0, 0, 2, 6, 0>;   // light_ao8_qo0_pb0_qm1  + generic_ao0_qo2_pb6   (HiSeq: ERR174310, SRR2962693)
+using SP0 = StaticSpecs<1, 8, 0, 0, 1, 0, 0, 2, 6, 0>;   // light_ao8_qo0_pb0_qm1  + generic_ao0_qo2_pb6   (HiSeq: ERR174310, SRR2962693, SRR19549058)
 using SP1 = StaticSpecs<1, 8, 0, 0, 1, 0, 2, 1, 6, 0>;   // light_ao8_qo0_pb0_qm1  + generic_ao2_qo1_pb6   (NovaSeq: SRR8861483)
 using SP2 = StaticSpecs<0, 8, 0, 0, 0, 1, 0, 4, 0, 16>;  // generic_ao8_qo0_pb0    + light_ao0_qo4_pb0_qm16 (Sequel II: m64187e)
 using SP3 = StaticSpecs<1, 4, 3, 2, 8, 1, 0, 4, 3, 16>;  // light_ao4_qo3_pb2_qm8  + light_ao0_qo4_pb3_qm16 (NovaSeq: SRR18908372)
 using SP4 = StaticSpecs<0, 4, 1, 2, 0, 1, 0, 4, 3, 16>;  // generic_ao4_qo1_pb2    + light_ao0_qo4_pb3_qm16 (HiSeq 2500: SRR5373739)
-static const int32_t kStaticPairs[5][10] = {
-    {1, 8, 0, 0, 1, 0, 0, 2, 6, 0}, {1, 8, 0, 0, 1, 0, 2, 1, 6, 0}, {0, 8, 0, 0, 0, 1, 0, 4, 0, 16},
-    {1, 4, 3, 2, 8, 1, 0, 4, 3, 16}, {0, 4, 1, 2, 0, 1, 0, 4, 3, 16}};
+using SP5 = StaticSpecs<0, 8, 0, 0, 0, 1, 2, 4, 2, 8>;   // generic_ao8_qo0_pb0    + light_ao2_qo4_pb2_qm8  (iSeq 100: ERR5462922)
+using SP6 = StaticSpecs<0, 8, 0, 0, 0, 1, 0, 3, 0, 32>;  // generic_ao8_qo0_pb0    + light_ao0_qo3_pb0_qm32 (HiSeq 2500: SRR16141966)
+using SP7 = StaticSpecs<0, 8, 0, 0, 0, 1, 0, 4, 3, 16>;  // generic_ao8_qo0_pb0    + light_ao0_qo4_pb3_qm16 (HiSeq 2500: SRR19609907)
+// (the one remaining same-sequencer pair of the reference's models/, SRR20210997 = light_ao8_qo0_pb0_qm1 + generic_ao3_qo3_pb0,
+// has a 2^27-spec q-score space served by the hashed map: it runs the run-time-generic kernels)
+constexpr int kNumStaticPairs = 8;
+static const int32_t kStaticPairs[kNumStaticPairs][10] = {
+    {1, 8, 0, 0, 1, 0, 0, 2, 6, 0}, {1, 8, 0, 0, 1, 0, 2, 1, 6, 0}, {0, 8, 0, 0, 0, 1, 0, 4, 0, 16}, {1, 4, 3, 2, 8, 1, 0, 4, 3, 16},
+    {0, 4, 1, 2, 0, 1, 0, 4, 3, 16}, {0, 8, 0, 0, 0, 1, 2, 4, 2, 8}, {0, 8, 0, 0, 0, 1, 0, 3, 0, 32}, {0, 8, 0, 0, 0, 1, 0, 4, 3, 16}};
 
 static int static_pair_index(const idn_gpu_ctx* ctx, int32_t acid_slot, int32_t q_slot) {
     // the specialised kernels index the dense spec -> row table without looking (ctx_row<true>)
     if (!ctx->slots[acid_slot].dev.map || !ctx->slots[q_slot].dev.map || !ctx->slots[acid_slot].dev.adirect || !ctx->slots[q_slot].dev.qwin) return -1;
-    for (int i = 0; i < 5; i++) {
+#ifndef IDN_NO_AENC
+    if (!ctx->slots[acid_slot].dev.aenc) return -1;
+#endif
+    for (int i = 0; i < kNumStaticPairs; i++) {
         bool same = true;
         for (int k = 0; k < 5; k++)
             same = same && ctx->slots[acid_slot].spec_tuple[k] == kStaticPairs[i][k] && ctx->slots[q_slot].spec_tuple[k] == kStaticPairs[i][5 + k];
@@ -270,6 +281,15 @@ static int static_pair_index(const idn_gpu_ctx* ctx, int32_t acid_slot, int32_t 
     }
     return -1;
 }
+
+extern "C" int32_t idn_gpu_kernel_variant(const idn_gpu_ctx* ctx, idn_model_t acid_model, idn_model_t q_model) {
+    if (!ctx) return -1;
+    for (idn_model_t h : {acid_model, q_model})
+        if (h < 0 || (size_t)h >= ctx->slots.size() || !ctx->slots[h].used) return -1;
+    if (ctx->slots[acid_model].dev.type != IDN_MODEL_ACID || ctx->slots[q_model].dev.type != IDN_MODEL_QSCORE) return -1;
+    return static_pair_index(ctx, acid_model, q_model);
+}
+extern "C" int32_t idn_gpu_kernel_variant_count(void) { return kNumStaticPairs; }
 
 // launch KERNEL<true, SPi> for a specialised pair, KERNEL<true, DynSpecs> otherwise
 // IDN_DEBUG_SMEM=<bytes>: dynamic shared memory added to these launches, an occupancy knob for experiments
@@ -284,6 +304,9 @@ static unsigned debug_smem() {
         case 2: KERNEL<true, SP2><<<grid, 128, debug_smem(), st>>>(__VA_ARGS__); break;                   \
         case 3: KERNEL<true, SP3><<<grid, 128, debug_smem(), st>>>(__VA_ARGS__); break;                   \
         case 4: KERNEL<true, SP4><<<grid, 128, debug_smem(), st>>>(__VA_ARGS__); break;                   \
+        case 5: KERNEL<true, SP5><<<grid, 128, debug_smem(), st>>>(__VA_ARGS__); break;                   \
+        case 6: KERNEL<true, SP6><<<grid, 128, debug_smem(), st>>>(__VA_ARGS__); break;                   \
+        case 7: KERNEL<true, SP7><<<grid, 128, debug_smem(), st>>>(__VA_ARGS__); break;                   \
         default: KERNEL<true, DynSpecs><<<grid, 128, debug_smem(), st>>>(__VA_ARGS__); break;             \
     }
 
@@ -401,7 +424,7 @@ extern "C" int32_t idn_gpu_model_upload(idn_gpu_ctx* ctx, int32_t model_type, in
     if (!ctx || !handle || !cum) return fail(ctx, IDN_E_INVALID_ARG, "NULL argument");
     if (model_type != IDN_MODEL_ACID && model_type != IDN_MODEL_QSCORE)
         return fail(ctx, IDN_E_INVALID_ARG, "bad model type %d", model_type);
-    if (n_ctx > 65535) return fail(ctx, IDN_E_UNSUPPORTED, "model has %u contexts (limit 65535)", n_ctx);
+    if (n_ctx > 65536) return fail(ctx, IDN_E_UNSUPPORTED, "model has %u contexts (limit 65536, check_model sequence_compressor.rs:209-219)", n_ctx);
     if (n_specs && (!spec_keys || !spec_ctx)) return fail(ctx, IDN_E_INVALID_ARG, "NULL spec table");
     CU(cudaSetDevice(ctx->device));
     const SpecBuild sb = make_spec(spec_kind, acid_order, q_order, pos_bits, q_max);
@@ -428,6 +451,12 @@ extern "C" int32_t idn_gpu_model_upload(idn_gpu_ctx* ctx, int32_t model_type, in
     }
 
     ModelSlot slot;
+    struct SlotGuard {  // every error exit below releases what was allocated so far
+        ModelSlot* s;
+        ~SlotGuard() {
+            if (s) s->free_all();
+        }
+    } guard{&slot};
     slot.dev.spec = spec;
     slot.spec_tuple[0] = spec_kind;
     slot.spec_tuple[1] = acid_order;
@@ -441,7 +470,8 @@ extern "C" int32_t idn_gpu_model_upload(idn_gpu_ctx* ctx, int32_t model_type, in
     // spec -> row (RansEncModel::from_model map, sequence_compressor.rs:31-40): dense u16 or open-addressing hash
     if (n_specs == 0) {
         // model without contexts: every spec is the dummy row
-    } else if (spec_num <= kDenseSpecLimit) {
+    } else if (spec_num <= kDenseSpecLimit && n_ctx < 65536) {  // row numbers 0 .. 65535 fit the u16 table; a model with exactly
+                                                                 // 65 536 contexts (the reference's limit) goes through the hash
         std::vector<uint16_t> map(spec_num, 0);
         for (uint64_t i = 0; i < n_specs; i++) map[spec_keys[i]] = (uint16_t)(spec_ctx[i] + 1);
         CU(cudaMalloc(&slot.d_map, spec_num * sizeof(uint16_t)));
@@ -451,19 +481,19 @@ extern "C" int32_t idn_gpu_model_upload(idn_gpu_ctx* ctx, int32_t model_type, in
         uint64_t capn = 16;
         while (capn < 2 * n_specs) capn <<= 1;
         std::vector<uint32_t> hk(capn, 0xffffffffu);
-        std::vector<uint16_t> hv(capn, 0);
+        std::vector<uint32_t> hv(capn, 0);
         for (uint64_t i = 0; i < n_specs; i++) {
             uint32_t h = host_hash32(spec_keys[i]) & (uint32_t)(capn - 1);
             while (hk[h] != 0xffffffffu && hk[h] != spec_keys[i]) h = (h + 1) & (uint32_t)(capn - 1);
             hk[h] = spec_keys[i];
-            hv[h] = (uint16_t)(spec_ctx[i] + 1);
+            hv[h] = spec_ctx[i] + 1;
         }
         CU(cudaMalloc(&slot.d_hkeys, capn * sizeof(uint32_t)));
-        CU(cudaMalloc(&slot.d_hvals, capn * sizeof(uint16_t)));
+        CU(cudaMalloc(&slot.d_hvals, capn * sizeof(uint32_t)));
         CU(cudaMemcpy(slot.d_hkeys, hk.data(), capn * sizeof(uint32_t), cudaMemcpyHostToDevice));
-        CU(cudaMemcpy(slot.d_hvals, hv.data(), capn * sizeof(uint16_t), cudaMemcpyHostToDevice));
+        CU(cudaMemcpy(slot.d_hvals, hv.data(), capn * sizeof(uint32_t), cudaMemcpyHostToDevice));
         slot.dev.hkeys = (const uint32_t*)slot.d_hkeys;
-        slot.dev.hvals = (const uint16_t*)slot.d_hvals;
+        slot.dev.hvals = (const uint32_t*)slot.d_hvals;
         slot.dev.hmask = (uint32_t)(capn - 1);
     }
 
@@ -501,8 +531,14 @@ extern "C" int32_t idn_gpu_model_upload(idn_gpu_ctx* ctx, int32_t model_type, in
         for (uint32_t r = 0; r < n_rows; r++) {
             const uint16_t* row = cum + (size_t)r * 95;
             uint8_t* d = dec.data() + (size_t)r * kQRowBytes;
+#ifndef IDN_QROW352
+            uint16_t* wins = reinterpret_cast<uint16_t*>(d + kQLutBytes);  // window g = starts of the symbols 4g .. 4g+7
+            for (uint32_t g = 0; g < (uint32_t)kQWindows; g++)
+                for (uint32_t t = 0; t < 8; t++) wins[8 * g + t] = 4 * g + t < 94 ? row[4 * g + t] : (uint16_t)total;
+#else
             uint16_t* starts = reinterpret_cast<uint16_t*>(d + kQLutBytes);
             for (uint32_t sidx = 0; sidx < (uint32_t)kQStarts; sidx++) starts[sidx] = sidx < 94 ? row[sidx] : (uint16_t)total;
+#endif
             uint32_t sidx = 0;
             for (uint32_t k = 0; k < (uint32_t)kQLutBytes; k++) {  // the symbol that owns slot 128 k, in units of 4 symbols
                 while (row[sidx + 1] <= 128 * k) sidx++;
@@ -531,7 +567,7 @@ extern "C" int32_t idn_gpu_model_upload(idn_gpu_ctx* ctx, int32_t model_type, in
         slot.dev.qwin = (const uint4*)slot.d_qwin;
     }
     // acid decode rows per spec: the decoder's spec -> row -> cum-freqs chain becomes one gather
-    if (model_type == IDN_MODEL_ACID && slot.dev.map && spec_num <= kDirectSpecLimit) {
+    if (model_type == IDN_MODEL_ACID && slot.dev.map && spec_num <= kDirectSpecLimit) {  // (dense models only: the specialised kernels want both)
         std::vector<uint64_t> direct(spec_num);
         uint64_t row0;
         memcpy(&row0, dec.data(), 8);
@@ -540,6 +576,18 @@ extern "C" int32_t idn_gpu_model_upload(idn_gpu_ctx* ctx, int32_t model_type, in
         CU(cudaMalloc(&slot.d_adirect, spec_num * 8));
         CU(cudaMemcpy(slot.d_adirect, direct.data(), spec_num * 8, cudaMemcpyHostToDevice));
         slot.dev.adirect = (const uint2*)slot.d_adirect;
+#ifndef IDN_NO_AENC
+        // the encoder entries per spec, [spec][5]: spec -> row -> entry is one gather in the encoder and the scorer
+        std::vector<uint2> aenc(spec_num * kAcidSyms);
+        for (uint64_t sp = 0; sp < spec_num; sp++)
+            for (uint32_t k = 0; k < kAcidSyms; k++) aenc[sp * kAcidSyms + k] = enc[k];  // row 0 = the dummy context
+        for (uint64_t i = 0; i < n_specs; i++)
+            for (uint32_t k = 0; k < kAcidSyms; k++)
+                aenc[(uint64_t)spec_keys[i] * kAcidSyms + k] = enc[(size_t)(spec_ctx[i] + 1) * kAcidSyms + k];
+        CU(cudaMalloc(&slot.d_aenc, aenc.size() * sizeof(uint2)));
+        CU(cudaMemcpy(slot.d_aenc, aenc.data(), aenc.size() * sizeof(uint2), cudaMemcpyHostToDevice));
+        slot.dev.aenc = (const uint2*)slot.d_aenc;
+#endif
     }
     slot.used = true;
 
@@ -549,10 +597,8 @@ extern "C" int32_t idn_gpu_model_upload(idn_gpu_ctx* ctx, int32_t model_type, in
             idx = i;
             break;
         }
-    if (idx >= kMaxSlots) {
-        slot.free_all();
-        return fail(ctx, IDN_E_UNSUPPORTED, "too many live models");
-    }
+    if (idx >= kMaxSlots) return fail(ctx, IDN_E_UNSUPPORTED, "too many live models");
+    guard.s = nullptr;  // the context owns the buffers from here on
     if (idx == ctx->slots.size()) ctx->slots.push_back(slot);
     else ctx->slots[idx] = slot;
     *handle = (idn_model_t)idx;
@@ -769,6 +815,7 @@ extern "C" int32_t idn_gpu_compress_blocks_dev(idn_gpu_ctx* ctx, const idn_batch
         ea.models = ctx->d_models;
         ea.acids = batch->acids;
         ea.quals = batch->quals;
+        ea.n_symbols = S;
         ea.read_off = batch->read_off;
         ea.n_reads = R;
         ea.fixed_acid = sp.cand_model[0];
@@ -968,6 +1015,7 @@ static int32_t compress_native_dev(idn_gpu_ctx* ctx, const idn_batch* batch, Sma
         ea.models = ctx->d_models;
         ea.acids = batch->acids;
         ea.quals = batch->quals;
+        ea.n_symbols = S;
         ea.read_off = batch->read_off;
         ea.lane_first = lane_first;
         ea.n_lanes_dev = n_lanes_dev;
@@ -1216,12 +1264,14 @@ static int32_t index_walk(idn_gpu_ctx* ctx, const uint8_t* blocks, const unsigne
     LAUNCHED("slot_count");
     scan_tiles_kernel<<<1, kScanBlock, 0, st>>>(bc.slots, B);
     LAUNCHED("scan_tiles");
+    slot_cap_check_kernel<<<1, 32, 0, st>>>(bc.slots + B, cap, const_cast<int32_t*>(dsp->status));
+    LAUNCHED("slot_cap_check");
     CU(ctx->w_walkdone.ensure((size_t)B + 16));
     const bool fast = ctx->walk_mode == 0 ? B < kWalkFastMaxBlocks : ctx->walk_mode == 2;
     uint8_t* done = fast ? ctx->w_walkdone.as<uint8_t>() : nullptr;
     if (done) {
         walk_fast_kernel<<<B, kWalkFastThreads, 0, st>>>(blocks, block_off, block_len, B, blocks_bytes, dsp->model_type, n_models,
-                                                         bc.slots, ix, bc.reads, bc.syms, done);
+                                                         bc.slots, ix, bc.reads, bc.syms, done, dsp->status);
         LAUNCHED("walk_fast");
     }
     walk_kernel<<<B, 32, 0, st>>>(blocks, block_off, block_len, B, blocks_bytes, dsp->model_type, n_models, bc.slots, ix, bc.reads,
@@ -1288,6 +1338,7 @@ static int32_t decompress_native_dev(idn_gpu_ctx* ctx, const uint8_t* blocks, co
         da.status = dsp->status;
         da.acids_out = acids_out;
         da.quals_out = quals_out;
+        da.out_dq = (long long)(quals_out - acids_out);
         da.err = &dsp->err;
         da.part_crc = nullptr;
         da.part_len = nullptr;
@@ -1381,6 +1432,7 @@ extern "C" int32_t idn_gpu_decompress_blocks_dev(idn_gpu_ctx* ctx, const uint8_t
     da.status = dsp->status;
     da.acids_out = acids_out;
     da.quals_out = quals_out;
+    da.out_dq = (long long)(quals_out - acids_out);
     da.read_off_out = roff;
     da.read_status = nullptr;
     da.err = &dsp->err;
@@ -1430,6 +1482,9 @@ static int32_t check_block_table(idn_gpu_ctx* ctx, const uint64_t* block_off, co
         if (block_off[i + 1] < block_off[i]) return fail(ctx, IDN_E_INVALID_ARG, "block_off is not monotone");
         if (block_len && block_off[i] + block_len[i] > block_off[n_blocks])
             return fail(ctx, IDN_E_SERIALIZE, "block %u runs past the end of the input", i);
+        // blocks must be disjoint: the per-read index is sized from the bytes of the region (index_walk)
+        if (block_len && i + 1 < n_blocks && block_off[i] + block_len[i] > block_off[i + 1])
+            return fail(ctx, IDN_E_INVALID_ARG, "block %u overlaps block %u", i, i + 1);
     }
     return IDN_OK;
 }
@@ -1442,6 +1497,7 @@ static int32_t status_to_error(idn_gpu_ctx* ctx, const int32_t st[4]) {
         case IDN_E_NO_ACTIVE_MODEL: return fail(ctx, st[0], "sequence slice before any SwitchModel in block %d", st[1]);
         case IDN_E_CHECKSUM: return fail(ctx, st[0], "checksum mismatch in block %d", st[1]);
         case IDN_E_NOSPACE: return fail(ctx, st[0], "output capacity too small (%d reads needed)", st[2]);
+        case IDN_E_INVALID_ARG: return fail(ctx, st[0], "the blocks of the table overlap");
         default: return fail(ctx, st[0], "decode failed with status %d in block %d", st[0], st[1]);
     }
 }
@@ -1660,6 +1716,7 @@ extern "C" int32_t idn_gpu_decompress_reads(idn_gpu_ctx* ctx, const uint8_t* pay
     da.status = nullptr;
     da.acids_out = ctx->s_aout.as<uint8_t>();
     da.quals_out = ctx->s_qout.as<uint8_t>();
+    da.out_dq = (long long)(da.quals_out - da.acids_out);
     da.read_off_out = nullptr;
     da.read_status = ctx->s_idx.as<uint32_t>();
     da.err = &dsp->err;

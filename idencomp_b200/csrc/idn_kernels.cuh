@@ -67,6 +67,79 @@ struct FwdReader {  // bytes at increasing addresses
     }
 };
 
+// The 16 bytes at the 16-byte aligned address c of a byte array [base, base + n): one vector load when the chunk lies
+// inside the array, byte loads (zeros outside) at its two ends.
+__device__ __forceinline__ uint4 load_chunk16(const uint8_t* __restrict__ base, unsigned long long n, const uint8_t* c) {
+    if (c >= base && c + 16 <= base + n) return __ldg(reinterpret_cast<const uint4*>(c));
+    uint32_t w[4] = {0, 0, 0, 0};
+#pragma unroll
+    for (int j = 0; j < 16; j++)
+        if (c + j >= base && c + j < base + n) w[j >> 2] |= (uint32_t)__ldg(c + j) << (8 * (j & 3));
+    return make_uint4(w[0], w[1], w[2], w[3]);
+}
+
+// The acids and the quality scores of a read, one position per call, last position first.  Both arrays are read at the
+// same offsets, so one cursor serves both; the symbols come in aligned 16-byte chunks (one vector load per stream per 16
+// positions: a thread's loads are 32 scattered sectors per warp request whatever their width, and the encoder is bound by
+// the number of such requests) that are consumed from the top word down.  When the two arrays disagree in their
+// alignment modulo 16 the reader falls back to byte loads.
+struct SymBackReader {
+    const uint8_t *abase, *qbase;  // the arrays (kernel parameters: constant-bank operands, no registers)
+    unsigned long long n;          // their length
+    const uint8_t* c;              // acid-side address of the chunk below the one in the registers / of the next byte (slow)
+    uint32_t ca, cq;               // current words, next byte in bits 24..31
+    uint32_t a0, a1, a2, q0, q1, q2;  // the words of the chunk still to come: x2 next
+    uint32_t left;                 // bytes of the chunk not yet returned
+    bool vec;
+    __device__ __forceinline__ void load() {
+        const uint4 va = load_chunk16(abase, n, c), vq = load_chunk16(qbase, n, qbase + (c - abase));
+        ca = va.w; a2 = va.z; a1 = va.y; a0 = va.x;
+        cq = vq.w; q2 = vq.z; q1 = vq.y; q0 = vq.x;
+        c -= 16;
+        left = 16;
+    }
+    __device__ __forceinline__ void next_word() {
+        ca = a2; a2 = a1; a1 = a0;
+        cq = q2; q2 = q1; q1 = q0;
+    }
+    // the first call of get() returns position off + len - 1; nothing is loaded when len == 0
+    __device__ __forceinline__ void start(const uint8_t* acids, const uint8_t* quals, unsigned long long n_symbols, long long off,
+                                          uint32_t len) {
+        abase = acids;
+        qbase = quals;
+        n = n_symbols;
+        vec = ((reinterpret_cast<uintptr_t>(acids) ^ reinterpret_cast<uintptr_t>(quals)) & 15) == 0;
+        ca = cq = a0 = a1 = a2 = q0 = q1 = q2 = 0;
+        left = 0;
+        const uint8_t* last = acids + off + (long long)len - 1;
+        c = last;
+        if (!vec || len == 0) return;
+        const uint32_t k = (uint32_t)(reinterpret_cast<uintptr_t>(last) & 15);  // byte of its chunk the first get() returns
+        c = last - k;
+        load();
+        for (uint32_t t = 3; t > (k >> 2); t--) next_word();  // drop the words above the one that holds byte k
+        const uint32_t sh = 8 * (3 - (k & 3));
+        ca <<= sh;
+        cq <<= sh;
+        left = k + 1;
+    }
+    __device__ __forceinline__ void get(uint32_t& a, uint32_t& q) {
+        if (!vec) {
+            a = __ldg(c);
+            q = __ldg(qbase + (c - abase));
+            c--;
+            return;
+        }
+        if (left == 0) load();  // lazily: never touches a chunk that holds no byte of the read
+        a = ca >> 24;
+        q = cq >> 24;
+        ca <<= 8;
+        cq <<= 8;
+        left--;
+        if ((left & 3) == 0 && left != 0) next_word();
+    }
+};
+
 // writes bytes at decreasing addresses, 4 at a time.  `end` must be 4-byte aligned.  Bytes wait in a 64-bit
 // accumulator (oldest highest); drain() stores a word once four are there, so at most 7 may be pending before it.
 struct BackWriter {
@@ -188,8 +261,13 @@ score_multi_kernel(const ModelPack<M> P, const uint8_t* __restrict__ acids, cons
         for (int k = 0; k < M; k++)
             if (k < (int)P.n) {
                 const ModelDev& m = P.m[k];
-                uint32_t row = ctx_row<kDense>(m, g[k].spec(m.spec, pf.pos, pbmax - m.spec.pb));
-                e[k] = __ldg(m.enc + (row * m.nsym + (m.type == 0 ? a : q)));
+                const uint32_t spec = g[k].spec(m.spec, pf.pos, pbmax - m.spec.pb);
+                if (m.aenc) {  // acid model with the encoder entries per spec: one gather instead of two
+                    e[k] = __ldg(m.aenc + (spec * kAcidSyms + a));
+                } else {
+                    const uint32_t row = ctx_row<kDense>(m, spec);
+                    e[k] = __ldg(m.enc + (row * m.nsym + (m.type == 0 ? a : q)));
+                }
             }
 #pragma unroll
         for (int k = 0; k < M; k++)
@@ -299,6 +377,7 @@ struct EncodeArgs {
     const ModelDev* models;
     const uint8_t* acids;
     const uint8_t* quals;
+    uint64_t n_symbols;
     const uint64_t* read_off;
     uint64_t n_reads;
     // model choice: either fixed (fast / single model per type) or per read
@@ -343,13 +422,20 @@ struct EncStream {
 // is being looked up, so the two dependent L2 gathers per symbol (spec -> row -> entry) overlap with arithmetic.
 template <class P>
 __device__ __forceinline__ void encode_read_body(const ModelDev& ma, const ModelDev& mq, const uint8_t* __restrict__ acids,
-                                                 const uint8_t* __restrict__ quals, long long off, uint32_t len, EncStream& S) {
+                                                 const uint8_t* __restrict__ quals, unsigned long long n_symbols, long long off,
+                                                 uint32_t len, EncStream& S) {
     constexpr SpecDev ksa = P::sa(), ksq = P::sq();  // compile-time generator parameters of a specialised pair
     const SpecDev& sa = P::kStatic ? ksa : ma.spec;
     const SpecDev& sq = P::kStatic ? ksq : mq.spec;
+#ifndef IDN_NO_SYM16
+    SymBackReader rs;
+    rs.start(acids, quals, n_symbols, off, len);  // nothing is loaded when len == 0
+#else
+    (void)n_symbols;
     BackReader ra, rq;
     ra.start(acids + off + len - 1);  // nothing is loaded before the first get()
     rq.start(quals + off + len - 1);
+#endif
     GenBack ga, gq;
     ga.clear(sa);
     gq.clear(sq);
@@ -359,8 +445,12 @@ __device__ __forceinline__ void encode_read_body(const ModelDev& ma, const Model
     auto pull = [&]() {
         uint32_t a = 0, q = 0;
         if (front >= 0) {
+#ifndef IDN_NO_SYM16
+            rs.get(a, q);
+#else
             a = ra.get();
             q = rq.get();
+#endif
             if (a > 4 || q > 93) {
                 S.bad = true;
                 a = a > 4 ? 0 : a;
@@ -383,6 +473,14 @@ __device__ __forceinline__ void encode_read_body(const ModelDev& ma, const Model
     PosBack pb;
     pb.init(len, pbmax);
 
+    // acid side: models with a small dense spec space carry the encoder entries per spec (ModelDev::aenc), i.e. the "row" of
+    // the acid side is the spec itself and spec -> row -> entry is one gather
+#ifndef IDN_NO_AENC
+    const bool direct_a = P::kStatic || ma.aenc != nullptr;
+#else
+    const bool direct_a = false;
+#endif
+    const uint2* __restrict__ enc_a = direct_a ? ma.aenc : ma.enc;
     // generator stage: moves the generators to position j (entry 0 = symbol j) and looks the two rows up
     int32_t j = (int32_t)len;  // position the generators stand at
     auto rows_next = [&](uint32_t& row_a, uint32_t& row_q) {
@@ -393,7 +491,8 @@ __device__ __forceinline__ void encode_read_body(const ModelDev& ma, const Model
             ga.step_back(sa);
             gq.step_back(sq);
             pb.retreat();
-            row_a = ctx_row<P::kStatic>(ma, ga.spec(sa, pb.pos, psa));
+            row_a = ga.spec(sa, pb.pos, psa);
+            if (!direct_a) row_a = ctx_row<P::kStatic>(ma, row_a);
             row_q = ctx_row<P::kStatic>(mq, gq.spec(sq, pb.pos, psq));
         }
     };
@@ -402,7 +501,7 @@ __device__ __forceinline__ void encode_read_body(const ModelDev& ma, const Model
     rows_next(row_a, row_q);  // generators at len-1, entry 0 = symbol len-1
     uint2 ea = make_uint2(0, 0), eq = make_uint2(0, 0);
     if (len) {
-        ea = __ldg(ma.enc + (row_a * kAcidSyms + (raw_a & 7u)));
+        ea = __ldg(enc_a + (row_a * kAcidSyms + (raw_a & 7u)));
         eq = __ldg(mq.enc + (row_q * kQSyms + ((uint32_t)raw_q & 127u)));
     }
     rows_next(row_a, row_q);  // generators at len-2
@@ -411,7 +510,7 @@ __device__ __forceinline__ void encode_read_body(const ModelDev& ma, const Model
         // entries of position i-1 (generators stand at i-1: entry 0), gathered while position i is coded
         uint2 ea_n = make_uint2(0, 0), eq_n = make_uint2(0, 0);
         if (i >= 1) {
-            ea_n = __ldg(ma.enc + (row_a * kAcidSyms + (raw_a & 7u)));
+            ea_n = __ldg(enc_a + (row_a * kAcidSyms + (raw_a & 7u)));
             eq_n = __ldg(mq.enc + (row_q * kQSyms + ((uint32_t)raw_q & 127u)));
         }
         rows_next(row_a, row_q);  // generators to i-2
@@ -447,7 +546,7 @@ encode_kernel(EncodeArgs A, const ModelDev MA, const ModelDev MQ) {
     const uint32_t len = (uint32_t)(A.read_off[r + 1] - A.read_off[r]);
     EncStream S;
     S.begin(A.scratch + 4ull * A.read_off[r + 1] + kSlotExtra * (r + 1));
-    encode_read_body<P>(ma, mq, A.acids, A.quals, off, len, S);
+    encode_read_body<P>(ma, mq, A.acids, A.quals, A.n_symbols, off, len, S);
     S.flush_states();
     const uint32_t plen = S.total();
     A.pay_len[r] = plen;
@@ -1044,6 +1143,17 @@ __global__ void slot_count_kernel(const unsigned long long* __restrict__ block_o
     slot_cnt[b] = n / 17 + 1;
 }
 
+// The per-read index holds `cap` entries = blocks_bytes / 17 + n_blocks + 1, enough for any set of DISJOINT blocks inside
+// the input region.  Blocks that overlap (only a caller of the _dev entry points can pass such a table; the host-pointer
+// calls reject it) could ask for more: refuse the call instead of writing past the index.
+__global__ void slot_cap_check_kernel(const unsigned long long* __restrict__ slot_total, unsigned long long cap,
+                                      int32_t* __restrict__ status) {
+    if (threadIdx.x == 0 && blockIdx.x == 0 && *slot_total > cap) {
+        status[0] = 12;  // IDN_E_INVALID_ARG
+        status[1] = -1;
+    }
+}
+
 __device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
     unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(gmem) : "memory");
@@ -1086,6 +1196,7 @@ walk_kernel(const uint8_t* __restrict__ blocks, const unsigned long long* __rest
     __shared__ uint16_t plist[kWalkMaxEnt];  // tile offsets of the slice headers found in the current tile
     const uint32_t b = blockIdx.x, lane = threadIdx.x;
     if (b >= n_blocks) return;
+    if (status[0] == 12) return;  // slot_cap_check_kernel refused the block table
     if (done && done[b]) return;
     const unsigned long long boff = block_off[b];
     const unsigned long long n = block_len ? block_len[b] : block_off[b + 1] - boff;
@@ -1304,7 +1415,7 @@ walk_fast_kernel(const uint8_t* __restrict__ blocks, const unsigned long long* _
                  const uint32_t* __restrict__ block_len, uint32_t n_blocks, unsigned long long blocks_bytes,
                  const uint8_t* __restrict__ model_type, uint32_t n_models, const unsigned long long* __restrict__ slot_base,
                  ReadIndexDev ix, unsigned long long* __restrict__ blk_reads, unsigned long long* __restrict__ blk_syms,
-                 uint8_t* __restrict__ done) {
+                 uint8_t* __restrict__ done, const int32_t* __restrict__ status) {
     __shared__ unsigned long long s_start[kWalkFastThreads];
     __shared__ unsigned long long s_syms[kWalkFastThreads];
     __shared__ uint32_t s_cnt[kWalkFastThreads];
@@ -1313,6 +1424,7 @@ walk_fast_kernel(const uint8_t* __restrict__ blocks, const unsigned long long* _
     const uint32_t b = blockIdx.x, t = threadIdx.x;
     if (b >= n_blocks) return;
     if (t == 0) done[b] = 0;
+    if (status[0] == 12) return;  // uniform: written by an earlier kernel of the stream
     const unsigned long long boff = block_off[b];
     const unsigned long long n = block_len ? block_len[b] : block_off[b + 1] - boff;
     if (boff > blocks_bytes || n > blocks_bytes - boff || n > 0xffffffffull) return;  // walk_kernel reports it
@@ -1499,7 +1611,10 @@ struct IdentU64 {
 
 // ---------------------------------------------------------------------------------------------------
 // K5: two-state per-read rANS decode.  One thread per read.
-// status bits: 1 = payload exhausted / malformed, 2 = final states or length mismatch (diagnostic only)
+// status bits: 1 = payload exhausted / malformed, 2 = the stream does not end cleanly (final states != L or bytes left
+// over).  Both fail the call with IDN_E_SERIALIZE, in compat and in native mode alike: a valid encoder output always ends
+// with both states back at L and every payload byte consumed (RansEncFlush / RansDecInit symmetry), so anything else is a
+// garbled payload even when no block CRC was supplied to catch it.
 // ---------------------------------------------------------------------------------------------------
 struct DecodeArgs {
     const ModelDev* models;
@@ -1516,6 +1631,7 @@ struct DecodeArgs {
     const int32_t* status;                  // when set and != 0 the kernel does nothing
     uint8_t* acids_out;
     uint8_t* quals_out;
+    long long out_dq;                       // quals_out - acids_out
     unsigned long long* read_off_out;       // optional [n_reads+1]: absolute symbol offset of every read
     uint32_t* read_status;  // optional
     uint32_t* err;
@@ -1600,28 +1716,94 @@ struct DecStream {
     __device__ __forceinline__ bool clean_end(uint32_t len) const { return xq == kRansL && xa == kRansL && cur == len; }
 };
 
-// Decoded symbols of consecutive positions: whole words once both outputs are word-aligned, bytes at the ragged ends
+// Decoded symbols of consecutive positions.  Bytes at the ragged ends of a read (the words it shares with its neighbours),
+// whole words in between; full words are collected four at a time and leave as ONE 16-byte store per stream wherever the
+// two output addresses are 16-byte aligned together.  A thread's stores are 32 scattered sectors per warp request, and
+// the codec kernels are bound by the number of such requests (l1tex data-pipe wavefronts, profiles/r2_ncu_*.md): 16 bytes
+// per request instead of 4 cuts the store requests of the decoder fourfold and fills a 32-byte sector in two writes
+// instead of eight (less read-modify-write traffic at the DRAM).  IDN_NO_SYM16 keeps the round-1 word stores for A/B runs.
 struct SymWriter {
-    uint8_t *pa, *pq;
-    __device__ __forceinline__ void init(uint8_t* a, uint8_t* q) {
+    uint8_t* pa;     // acids; the quality scores go to pa + dq
+    long long dq;    // quals_out - acids_out: a kernel parameter (constant-bank operand, no registers)
+#ifndef IDN_NO_SYM16
+    uint32_t an_lo, an_hi;    // pending acid words as nibbles (an acid is 0..4): word k of the pending four in bits 16k..16k+15
+    uint32_t q0, q1, q2, q3;  // pending quality-score words, oldest first: the last `nw` count
+    uint32_t nw;              // pending words (0..3); they end at pa; bit 31 = "pa and pa + dq share their phase modulo 16"
+#endif
+    __device__ __forceinline__ void init(uint8_t* a, long long dq_) {
         pa = a;
-        pq = q;
+        dq = dq_;
+#ifndef IDN_NO_SYM16
+        an_lo = an_hi = q0 = q1 = q2 = q3 = 0;
+        nw = (dq_ & 15) == 0 ? 0x80000000u : 0u;
+#endif
     }
     __device__ __forceinline__ bool aligned() const {
-        return ((reinterpret_cast<uintptr_t>(pa) | reinterpret_cast<uintptr_t>(pq)) & 3) == 0;
+        return ((reinterpret_cast<uintptr_t>(pa) | (uintptr_t)dq) & 3) == 0;
     }
+#ifndef IDN_NO_SYM16
+    // four acids as nibbles (16 bits) <-> one byte each
+    static __device__ __forceinline__ uint32_t pack4(uint32_t w) {
+        const uint32_t t = w | (w >> 4);          // byte 0 = b0 | b1 << 4, byte 2 = b2 | b3 << 4
+        return __byte_perm(t, 0, 0x4420);         // bytes 0 and 2 -> bits 0..15
+    }
+    static __device__ __forceinline__ uint32_t unpack4(uint32_t n16) {  // n16 in bits 0..15
+        const uint32_t t = __byte_perm(n16, 0, 0x4140);  // byte 0 -> byte 0, byte 1 -> byte 2
+        return (t | (t << 4)) & 0x0f0f0f0fu;
+    }
+    // the pending words, one store each (end of a read / lane, or a byte store is about to open a gap)
+    __device__ __forceinline__ void flush() {
+        const uint32_t k = nw & 3u;
+        uint32_t* wa = reinterpret_cast<uint32_t*>(pa);
+        uint32_t* wq = reinterpret_cast<uint32_t*>(pa + dq);
+        if (k == 3) {
+            wa[-3] = unpack4(an_lo >> 16);
+            wq[-3] = q1;
+        }
+        if (k >= 2) {
+            wa[-2] = unpack4(an_hi & 0xffffu);
+            wq[-2] = q2;
+        }
+        if (k >= 1) {
+            wa[-1] = unpack4(an_hi >> 16);
+            wq[-1] = q3;
+        }
+        nw &= 0x80000000u;
+    }
+#else
+    __device__ __forceinline__ void flush() {}
+#endif
     __device__ __forceinline__ void put(uint32_t a, uint32_t q) {
-        *pa++ = (uint8_t)a;
-        *pq++ = (uint8_t)q;
+#ifndef IDN_NO_SYM16
+        if (nw & 3u) flush();
+#endif
+        pa[0] = (uint8_t)a;
+        pa[dq] = (uint8_t)q;
+        pa++;
     }
-    __device__ __forceinline__ void put4(uint32_t wa, uint32_t wq) {
+    __device__ __forceinline__ void put4(uint32_t wa, uint32_t wq) {  // both addresses are word-aligned
 #ifdef IDN_ABL_NOSTORE
-        if (wa != 0xdeadbeefu) { pa += 4; pq += 4; return; }
+        if (wa != 0xdeadbeefu) { pa += 4; return; }
+#endif
+#ifndef IDN_NO_SYM16
+        if ((nw & 3u) || (nw && (reinterpret_cast<uintptr_t>(pa) & 15) == 0)) {
+            an_lo = __funnelshift_r(an_lo, an_hi, 16);
+            an_hi = __byte_perm(an_hi, pack4(wa), 0x5432);  // (an_hi >> 16) | pack << 16
+            q0 = q1; q1 = q2; q2 = q3; q3 = wq;
+            pa += 4;
+            nw++;
+            if ((nw & 7u) == 4) {
+                *reinterpret_cast<uint4*>(pa - 16) = make_uint4(unpack4(an_lo & 0xffffu), unpack4(an_lo >> 16),
+                                                                unpack4(an_hi & 0xffffu), unpack4(an_hi >> 16));
+                *reinterpret_cast<uint4*>(pa + dq - 16) = make_uint4(q0, q1, q2, q3);
+                nw &= 0x80000000u;
+            }
+            return;
+        }
 #endif
         *reinterpret_cast<uint32_t*>(pa) = wa;
-        *reinterpret_cast<uint32_t*>(pq) = wq;
+        *reinterpret_cast<uint32_t*>(pa + dq) = wq;
         pa += 4;
-        pq += 4;
     }
 };
 
@@ -1743,14 +1925,15 @@ decode_kernel(DecodeArgs A, const ModelDev MA, const ModelDev MQ) {
     DecStream D;
     D.begin(A.payload, A.ix.pay_off[slot], A.ix.pay_len[slot]);
     SymWriter O;
-    O.init(A.acids_out + ooff, A.quals_out + ooff);
+    O.init(A.acids_out + ooff, A.out_dq);
     decode_read_body<P>(ma, mq, len, D, O, C);
+    O.flush();
     const uint32_t plen = A.ix.pay_len[slot];
     D.finish(A.payload, A.ix.pay_off[slot], plen);
     uint32_t st = D.st;
     if (!(st & 1) && !D.clean_end(plen)) st |= 2;
     if (A.read_status) A.read_status[r] = st;
-    if (st & 1) atomicOr(A.err, 1u);
+    if (st) atomicOr(A.err, 1u);
     if (A.part_crc) {  // crc(acids | quals) of this read, as crc_read_kernel would compute it
         const CrcPair p = crc_concat(CrcPair{~C.ca, len}, CrcPair{~C.cq, len}, s_xpow);
         A.part_crc[r] = len ? p.crc : 0u;

@@ -89,6 +89,7 @@ struct EncodeLaneArgs {
     const ModelDev* models;
     const uint8_t* acids;
     const uint8_t* quals;
+    uint64_t n_symbols;
     const uint64_t* read_off;
     const uint32_t* lane_first;   // [n_lanes+1]
     const unsigned long long* n_lanes_dev;
@@ -119,7 +120,7 @@ encode_lane_kernel(EncodeLaneArgs A, const ModelDev MA, const ModelDev MQ) {
     for (uint32_t r = r1; r-- > r0;) {
         const long long off = (long long)A.read_off[r];
         const uint32_t len = (uint32_t)(A.read_off[r + 1] - A.read_off[r]);
-        encode_read_body<P>(ma, mq, A.acids, A.quals, off, len, S);
+        encode_read_body<P>(ma, mq, A.acids, A.quals, A.n_symbols, off, len, S);
     }
     S.flush();
     A.lane_len[l] = S.total();
@@ -423,8 +424,12 @@ native_fill_kernel(const uint8_t* __restrict__ blocks, const NativeBlockHdr* __r
     __shared__ unsigned long long smem[kScanBlock / 32];
     __shared__ unsigned long long total;
     __shared__ int lane_mismatch;
+    __shared__ int32_t s_status;
     const uint32_t b = blockIdx.x;
-    if (status[0] != 0) return;
+    // other CTAs of this launch may set status[0] while this one runs: every thread must take the same exit (barriers follow)
+    if (threadIdx.x == 0) s_status = status[0];
+    __syncthreads();
+    if (s_status != 0) return;
     if (b == n_blocks) {  // terminators
         if (threadIdx.x == 0) {
             block_first[n_blocks] = (uint32_t)blk_read_base[n_blocks];
@@ -518,6 +523,7 @@ struct DecodeLaneArgs {
     const int32_t* status;
     uint8_t* acids_out;
     uint8_t* quals_out;
+    long long out_dq;  // quals_out - acids_out
     uint32_t* err;
     // optional: per-read CRC-32 partials (acids | quals) for crc_verify_kernel, as in DecodeArgs
     uint32_t* part_crc;
@@ -548,7 +554,7 @@ decode_lane_kernel(DecodeLaneArgs A, const ModelDev MA, const ModelDev MQ) {
     D.begin(A.payload, A.ix.pay_off[l], A.ix.pay_len[l]);
     SymWriter O;
     unsigned long long o = A.read_off[r0];
-    O.init(A.acids_out + o, A.quals_out + o);
+    O.init(A.acids_out + o, A.out_dq);
 #pragma unroll 1
     for (unsigned long long r = r0; r < r1; r++) {
         unsigned long long o_next = A.read_off[r + 1];
@@ -562,6 +568,7 @@ decode_lane_kernel(DecodeLaneArgs A, const ModelDev MA, const ModelDev MQ) {
         }
         o = o_next;
     }
+    O.flush();
     const uint32_t plen = A.ix.pay_len[l];
     D.finish(A.payload, A.ix.pay_off[l], plen);
     if ((D.st & 1) || !D.clean_end(plen)) atomicOr(A.err, 1u);

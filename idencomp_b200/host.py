@@ -24,7 +24,8 @@ EXPORTS = [
     "idn_host_compressor_retained", "idn_host_compressor_stats", "idn_host_compressor_free", "idn_host_decompress",
     "idn_host_decoded_reads", "idn_host_decoded_version", "idn_host_decoded_read_off", "idn_host_decoded_acids",
     "idn_host_decoded_quals", "idn_host_decoded_name_off", "idn_host_decoded_names", "idn_host_decoded_free",
-    "idn_host_cluster", "idn_host_rank",
+    "idn_host_cluster", "idn_host_rank", "idn_host_clustering_new", "idn_host_clustering_free", "idn_host_splitmix64",
+    "idn_host_xoshiro256pp", "idn_host_sample_indices", "idn_host_gen_range",
 ]
 
 
@@ -85,8 +86,20 @@ def load():
         f.restype = rt
     L.idn_host_decoded_free.argtypes = [vp]
     L.idn_host_decoded_free.restype = None
-    L.idn_host_cluster.argtypes = [vp, u64, u32, u32, vp, vp]
+    L.idn_host_clustering_new.argtypes = []
+    L.idn_host_clustering_new.restype = vp
+    L.idn_host_clustering_free.argtypes = [vp]
+    L.idn_host_clustering_free.restype = None
+    L.idn_host_cluster.argtypes = [vp, vp, u64, u32, u32, vp, vp]
     L.idn_host_cluster.restype = u32
+    L.idn_host_splitmix64.argtypes = [u64, u32, vp]
+    L.idn_host_splitmix64.restype = None
+    L.idn_host_xoshiro256pp.argtypes = [vp, u64, u32, vp]
+    L.idn_host_xoshiro256pp.restype = None
+    L.idn_host_sample_indices.argtypes = [u64, u32, u32, vp]
+    L.idn_host_sample_indices.restype = u32
+    L.idn_host_gen_range.argtypes = [u64, u32, u32, vp]
+    L.idn_host_gen_range.restype = u32
     L.idn_host_rank.argtypes = [vp, u64, u32, u32, vp]
     L.idn_host_rank.restype = u32
     _LIB = L
@@ -288,13 +301,65 @@ def decompress(models, idn: bytes, *, device=0, batch_blocks=32) -> dict:
         L.idn_host_decoded_free(h)
 
 
-def cluster(cost, num_clusters: int):
-    """Clustering::make_clusters (clustering.rs:21-118) on cost[value][centroid] -> (centroids, cluster of every value)."""
+class Clustering:
+    """Clustering (clustering.rs:8-118): one random stream (Xoshiro256++ seeded with 404) that runs on from one
+    make_clusters call to the next, as the reference's ModelChooser uses it for the acid and then the q-score models."""
+
+    def __init__(self):
+        self.h = load().idn_host_clustering_new()
+
+    def make_clusters(self, cost, num_clusters: int):
+        return cluster(cost, num_clusters, self)
+
+    def close(self):
+        if self.h:
+            load().idn_host_clustering_free(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def cluster(cost, num_clusters: int, state: "Clustering | None" = None):
+    """Clustering::make_clusters (clustering.rs:21-118) on cost[value][centroid] -> (centroids, cluster of every value).
+    state = None: a fresh Clustering::new()."""
     c = np.ascontiguousarray(cost, dtype=np.uint32)
     cent = np.zeros(max(num_clusters, 1), dtype=np.uint32)
     vc = np.zeros(max(c.shape[0], 1), dtype=np.uint32)
-    n = load().idn_host_cluster(c.ctypes.data, c.shape[0], c.shape[1], num_clusters, cent.ctypes.data, vc.ctypes.data)
+    n = load().idn_host_cluster(state.h if state else None, c.ctypes.data, c.shape[0], c.shape[1], num_clusters, cent.ctypes.data,
+                                vc.ctypes.data)
     return cent[:n].tolist(), vc[:c.shape[0]].tolist()
+
+
+def splitmix64(seed: int, n: int):
+    out = np.zeros(n, dtype=np.uint64)
+    load().idn_host_splitmix64(seed, n, out.ctypes.data)
+    return out.tolist()
+
+
+def xoshiro256pp(n: int, *, state=None, seed: int = 0):
+    """n outputs of Xoshiro256++ started from four state words, or from seed_from_u64(seed)."""
+    out = np.zeros(n, dtype=np.uint64)
+    st = None if state is None else np.asarray(state, dtype=np.uint64)
+    load().idn_host_xoshiro256pp(None if st is None else st.ctypes.data, seed, n, out.ctypes.data)
+    return out.tolist()
+
+
+def sample_indices(seed: int, length: int, amount: int):
+    """rand 0.8.5 index::sample(&mut Xoshiro256PlusPlus::seed_from_u64(seed), length, amount) (amount < 12)."""
+    out = np.zeros(max(amount, 1), dtype=np.uint32)
+    n = load().idn_host_sample_indices(seed, length, amount, out.ctypes.data)
+    return out[:n].tolist()
+
+
+def gen_range(seed: int, high: int, n: int):
+    """n draws of rng.gen_range(0..=high) on Xoshiro256PlusPlus::seed_from_u64(seed)."""
+    out = np.zeros(n, dtype=np.uint32)
+    load().idn_host_gen_range(seed, high, n, out.ctypes.data)
+    return out.tolist()
 
 
 def rank(cost, model_num: int):

@@ -42,7 +42,7 @@ enum {
     IDN_E_INVALID_MODEL_INDEX = 7,
     IDN_E_NO_ACTIVE_MODEL = 8,
     IDN_E_UNKNOWN_MODEL = 9,
-    IDN_E_UNSUPPORTED = 10,     /* e.g. model with > 65535 contexts (reference limit 65536, :209-219) */
+    IDN_E_UNSUPPORTED = 10,     /* e.g. an unknown container mode, > 16 candidate models of one type */
     IDN_E_NOSPACE = 11,         /* output capacity too small; required size is reported */
     IDN_E_INVALID_ARG = 12,
     IDN_E_INVALID_SYMBOL = 13,  /* acid > 4 or quality score > 93 in the input */
@@ -78,6 +78,12 @@ int32_t idn_gpu_set_lane_symbols(idn_gpu_ctx *ctx, uint32_t lane_syms);
 int32_t idn_gpu_set_walk(idn_gpu_ctx *ctx, int32_t mode);
 /* number of kernel launches this ctx has issued since creation (bench.py's gpu_launches) */
 uint64_t idn_gpu_launch_count(const idn_gpu_ctx *ctx);
+/* which codec kernel instantiation a call with exactly this (acid, q-score) model pair launches: the index of the
+ * compile-time-specialised spec-type pair (0 .. idn_gpu_kernel_variant_count() - 1, table in idn_gpu.cu), or -1 for the
+ * run-time-generic kernels.  Lets the parity tests assert that every specialised instantiation was compared with the
+ * oracle; results never depend on the variant. */
+int32_t idn_gpu_kernel_variant(const idn_gpu_ctx *ctx, idn_model_t acid_model, idn_model_t q_model);
+int32_t idn_gpu_kernel_variant_count(void);
 
 /* ---- models: replaces RansEncModel/RansDecModel::from_model (sequence_compressor.rs:21-48,175-201) --
  * `cum`: integer cumulative frequencies, row-major [(n_ctx+1)][nsym+1] u16, row 0 = the uniform dummy
@@ -149,11 +155,14 @@ uint64_t idn_gpu_compress_bound(uint64_t n_reads, uint64_t n_symbols, uint32_t n
  * Block b's payload (the slices, WITHOUT its 8-byte block header) is blocks[block_off[b] .. block_off[b] + len_b) with
  * len_b = block_len ? block_len[b] : block_off[b+1] - block_off[b]; block_off[n_blocks] is the size of the `blocks`
  * region and block_crc[b] the block's header checksum.  With block_len the region may hold other bytes between the
- * payloads, so a chunk of an .idn file can be passed as it lies on disk (block_off[b] = header position + 8).  The library walks the
+ * payloads, so a chunk of an .idn file can be passed as it lies on disk (block_off[b] = header position + 8); the blocks
+ * must not overlap (IDN_E_INVALID_ARG).  The library walks the
  * slices (Identifiers slices are skipped: names stay on the host), tracks the active models per type
  * (decompressor_block.rs:194-214), decodes every Sequence slice and verifies the CRC of the symbols
  * (names, if any, are passed per read through `names`/`name_off` after the host inflated them; NULL =
- * the block has no names).
+ * the block has no names).  A Sequence slice (or native lane) whose rANS stream runs out early, or does not end with
+ * both states back at their initial value and every payload byte consumed, fails the call with IDN_E_SERIALIZE in both
+ * container modes, with or without a CRC to compare against.
  * Two-step use: idn_gpu_index_blocks returns the read count / symbol count so the caller can size the
  * outputs, then idn_gpu_decompress_blocks fills them. */
 typedef struct {

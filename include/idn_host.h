@@ -98,9 +98,21 @@ void idn_host_decoded_free(idn_host_decoded *d);
 
 /* ---- file-level model subset selection on a cost matrix cost[value][centroid] (exposed for the known-answer tests) ----
  * Clustering::make_clusters (clustering.rs:21-118): centroid index per cluster and the cluster of every value;
- * returns the number of clusters.  get_model_ranking (idn/model_chooser.rs:103-138): the best `model_num` columns. */
-uint32_t idn_host_cluster(const uint32_t *cost, uint64_t n_values, uint32_t n_centroids, uint32_t num_clusters,
-                          uint32_t *centroids_out, uint32_t *value_cluster_out);
+ * returns the number of clusters.  `state` = a Clustering object whose random stream runs on from call to call (the
+ * reference's ModelChooser holds ONE for the acid models and then the q-score models, model_chooser.rs:14-24); NULL = a
+ * fresh Clustering::new().  get_model_ranking (idn/model_chooser.rs:103-138): the best `model_num` columns. */
+typedef struct idn_host_clustering idn_host_clustering;
+idn_host_clustering *idn_host_clustering_new(void);
+void idn_host_clustering_free(idn_host_clustering *c);
+uint32_t idn_host_cluster(idn_host_clustering *state, const uint32_t *cost, uint64_t n_values, uint32_t n_centroids,
+                          uint32_t num_clusters, uint32_t *centroids_out, uint32_t *value_cluster_out);
+/* the restated third-party generators behind Clustering (rand_xoshiro 0.6.0, rand 0.8.5; clustering.hpp), for their
+ * published known-answer vectors: SplitMix64 stream; xoshiro256++ from four state words (state4 != NULL) or
+ * seed_from_u64(seed); index::sample / gen_range(0..=high) on seed_from_u64(seed) */
+void idn_host_splitmix64(uint64_t seed, uint32_t n, uint64_t *out);
+void idn_host_xoshiro256pp(const uint64_t *state4, uint64_t seed, uint32_t n, uint64_t *out);
+uint32_t idn_host_sample_indices(uint64_t seed, uint32_t length, uint32_t amount, uint32_t *out);
+uint32_t idn_host_gen_range(uint64_t seed, uint32_t high, uint32_t n, uint32_t *out);
 uint32_t idn_host_rank(const uint32_t *cost, uint64_t n_values, uint32_t n_models, uint32_t model_num, uint32_t *models_out);
 
 #ifdef __cplusplus
