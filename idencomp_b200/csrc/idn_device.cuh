@@ -76,6 +76,7 @@ struct SpecDev {
     QueueDev qa, qq;  // acid queue, quality score queue
     uint32_t abits;   // IntQueue::num_bits of the acid queue
     uint32_t pb;      // position bits
+    uint32_t sbits;   // bits of the two queue states together (spec bits without the position)
     // symbol mapping (LightContextSpecGenerator::update, context_spec.rs:516-529): generic asub = 0, qmul = 2^20
     uint32_t asub, qmul, light;
 };
@@ -127,7 +128,7 @@ __host__ __device__ constexpr bool make_queue(uint32_t base, uint32_t order, Que
 }
 
 __host__ __device__ constexpr SpecBuild make_spec(int kind, int ao, int qo, int pb, int qmax) {
-    SpecBuild r{SpecDev{QueueDev{0, 0, 0, 0, 0, 0, 0, 0, 0}, QueueDev{0, 0, 0, 0, 0, 0, 0, 0, 0}, 0, 0, 0, 0, 0}, 0, false};
+    SpecBuild r{SpecDev{QueueDev{0, 0, 0, 0, 0, 0, 0, 0, 0}, QueueDev{0, 0, 0, 0, 0, 0, 0, 0, 0}, 0, 0, 0, 0, 0, 0}, 0, false};
     if (kind != 0 && kind != 1) return r;  // IDN_SPEC_GENERIC / IDN_SPEC_LIGHT
     if (ao < 0 || ao > kHist || qo < 0 || qo > kHist || pb < 0 || pb > 16) return r;
     SpecDev& s = r.spec;
@@ -155,6 +156,7 @@ __host__ __device__ constexpr SpecBuild make_spec(int kind, int ao, int qo, int 
         return r;
     }
     if (s.abits + qbits + s.pb > 31) return r;
+    s.sbits = s.abits + qbits;
     r.total_bits = s.abits + qbits + s.pb;
     r.ok = true;
     return r;
@@ -175,7 +177,13 @@ struct StaticSpecs {
     // the decoder searches q-score symbols through the 2 KB "window" rows (one gather level less, 6 x the row footprint).
     // Measured per bundled pair on the 10 GB workloads: NovaSeq (generic_ao2_qo1_pb6, 2 154 evenly used rows) decode
     // 46.9 -> 44.1 ms; HiSeq (generic_ao0_qo2_pb6, a few hot rows) 34.4 -> 35.7 ms; Sequel II 25.6 -> 26.6 ms.
+#ifdef IDN_QWIN_ALL
+    static constexpr bool kQWin = true;
+#elif defined(IDN_QWIN_NONE)
+    static constexpr bool kQWin = false;
+#else
     static constexpr bool kQWin = KQ == 0 && AOQ == 2 && QOQ == 1 && PBQ == 6;
+#endif
     __host__ __device__ static constexpr SpecDev sa() { return make_spec(KA, AOA, QOA, PBA, QMA).spec; }
     __host__ __device__ static constexpr SpecDev sq() { return make_spec(KQ, AOQ, QOQ, PBQ, QMQ).spec; }
 };
@@ -204,11 +212,17 @@ __device__ __forceinline__ uint32_t hash32(uint32_t k) {
     return k;
 }
 
-// RansEncModel/RansDecModel::context_for  (sequence_compressor.rs:60-62, 203-205)
-// kDense: the caller guarantees the dense table (the specialised kernels are only launched for such models)
-template <bool kDense = false>
-__device__ __forceinline__ uint32_t ctx_row(const ModelDev& m, uint32_t spec) {
-    if (kDense || m.map) return __ldg(m.map + spec);
+// Index of a spec in the dense per-spec tables (map, adirect, aenc): the spec with its position field moved to the TOP,
+//     index = position << sbits | queue states        (spec = queue states << pb | position, context_spec.rs:377-383)
+// The reads of a thread block have similar lengths and advance in lock step, so at any moment its threads look up specs
+// of (nearly) one position: position-major tables turn those gathers into hits in one small slice (2^sbits entries, e.g.
+// 17 KB of the 2 MB map of generic_ao0_qo2_pb6) that stays in L1, and the slices are walked front to back.
+__host__ __device__ constexpr uint32_t spec_table_index(const SpecDev& s, uint32_t spec) {
+    return s.pb == 0 ? spec : (((spec & ((1u << s.pb) - 1u)) << s.sbits) | (spec >> s.pb));
+}
+
+// RansEncModel/RansDecModel::context_for  (sequence_compressor.rs:60-62, 203-205) through the hash of a sparse spec space
+__device__ __forceinline__ uint32_t ctx_row_hash(const ModelDev& m, uint32_t spec) {
     if (!m.hkeys) return 0;  // model without contexts
     uint32_t h = hash32(spec) & m.hmask;
     for (;;) {
@@ -217,6 +231,14 @@ __device__ __forceinline__ uint32_t ctx_row(const ModelDev& m, uint32_t spec) {
         if (k == 0xffffffffu) return 0;
         h = (h + 1) & m.hmask;
     }
+}
+
+// context row of the spec a generator stands at.  kDense: the caller guarantees the dense table (the specialised kernels
+// are only launched for such models)
+template <bool kDense = false, class Gen>
+__device__ __forceinline__ uint32_t gen_row(const ModelDev& m, const SpecDev& s, const Gen& g, uint32_t pos_shared, uint32_t pshift) {
+    if (kDense || m.map) return __ldg(m.map + g.index(s, pos_shared, pshift));
+    return ctx_row_hash(m, g.spec(s, pos_shared, pshift));
 }
 
 // (acid, q) -> queue digits.  z = (acid == N || q == 0), computed once per symbol for both generators.
@@ -288,6 +310,11 @@ struct GenFwd {
         if (s.pb == 0) return (sq << s.abits) | sa;  // position(i) < 2^pbmax for i < len: nothing to add
         return (((sq << s.abits) | sa) << s.pb) | (pos_shared >> pshift);
     }
+    // spec_table_index(spec()) without the detour
+    __device__ __forceinline__ uint32_t index(const SpecDev& s, uint32_t pos_shared, uint32_t pshift) const {
+        if (s.pb == 0) return (sq << s.abits) | sa;
+        return ((pos_shared >> pshift) << s.sbits) | ((sq << s.abits) | sa);
+    }
     __device__ __forceinline__ void update(const SpecDev& s, uint32_t a, uint32_t q, bool z) {
         uint32_t va, vq;
         map_syms(s, a, q, z, va, vq);
@@ -336,6 +363,10 @@ struct GenBack {
     __device__ __forceinline__ uint32_t spec(const SpecDev& s, uint32_t pos_shared, uint32_t pshift) const {
         if (s.pb == 0) return (sq << s.abits) | sa;
         return (((sq << s.abits) | sa) << s.pb) | (pos_shared >> pshift);
+    }
+    __device__ __forceinline__ uint32_t index(const SpecDev& s, uint32_t pos_shared, uint32_t pshift) const {
+        if (s.pb == 0) return (sq << s.abits) | sa;
+        return ((pos_shared >> pshift) << s.sbits) | ((sq << s.abits) | sa);
     }
 };
 

@@ -261,11 +261,10 @@ score_multi_kernel(const ModelPack<M> P, const uint8_t* __restrict__ acids, cons
         for (int k = 0; k < M; k++)
             if (k < (int)P.n) {
                 const ModelDev& m = P.m[k];
-                const uint32_t spec = g[k].spec(m.spec, pf.pos, pbmax - m.spec.pb);
                 if (m.aenc) {  // acid model with the encoder entries per spec: one gather instead of two
-                    e[k] = __ldg(m.aenc + (spec * kAcidSyms + a));
+                    e[k] = __ldg(m.aenc + (g[k].index(m.spec, pf.pos, pbmax - m.spec.pb) * kAcidSyms + a));
                 } else {
-                    const uint32_t row = ctx_row<kDense>(m, spec);
+                    const uint32_t row = gen_row<kDense>(m, m.spec, g[k], pf.pos, pbmax - m.spec.pb);
                     e[k] = __ldg(m.enc + (row * m.nsym + (m.type == 0 ? a : q)));
                 }
             }
@@ -491,9 +490,8 @@ __device__ __forceinline__ void encode_read_body(const ModelDev& ma, const Model
             ga.step_back(sa);
             gq.step_back(sq);
             pb.retreat();
-            row_a = ga.spec(sa, pb.pos, psa);
-            if (!direct_a) row_a = ctx_row<P::kStatic>(ma, row_a);
-            row_q = ctx_row<P::kStatic>(mq, gq.spec(sq, pb.pos, psq));
+            row_a = direct_a ? ga.index(sa, pb.pos, psa) : gen_row<P::kStatic>(ma, sa, ga, pb.pos, psa);
+            row_q = gen_row<P::kStatic>(mq, sq, gq, pb.pos, psq);
         }
     };
     // prologue: rows of position len-1, its entries, rows of position len-2
@@ -524,11 +522,13 @@ __device__ __forceinline__ void encode_read_body(const ModelDev& ma, const Model
 
 // kUniform: every read of the batch uses the same model pair; its parameters then live in the kernel parameter
 // space (constant bank operands) instead of ~40 registers per thread, which is what bounds occupancy here.
+// resident CTAs per SM the uniform kernels are compiled for: 8 x 128 threads = 64 registers per thread.  Round 1 ran 9
+// (56 registers); the 16-byte symbol chunks of round 2 need the room (9 CTAs spill: encode 12.1 vs 7.9 ms per 3 GB).
 #ifndef IDN_ENC_MINB
-#define IDN_ENC_MINB 9
+#define IDN_ENC_MINB 8
 #endif
 #ifndef IDN_DEC_MINB
-#define IDN_DEC_MINB 9
+#define IDN_DEC_MINB 8
 #endif
 template <bool kUniform, class P>
 __global__ void __launch_bounds__(128, kUniform ? IDN_ENC_MINB : 1)
@@ -1829,16 +1829,15 @@ __device__ __forceinline__ void decode_read_body(const ModelDev& ma, const Model
     pf.init(len, pbmax);
     auto step = [&](uint32_t& va, uint32_t& vq) {
         D.refill();
-        const uint32_t spec_a = ga.spec(sa, pf.pos, psa);
         uint2 pk;  // cum[1..4] of the acid context
-        if (P::kStatic || ma.adirect) pk = __ldg(ma.adirect + spec_a);
-        else pk = __ldg(reinterpret_cast<const uint2*>(ma.dec) + ctx_row(ma, spec_a));
+        if (P::kStatic || ma.adirect) pk = __ldg(ma.adirect + ga.index(sa, pf.pos, psa));
+        else pk = __ldg(reinterpret_cast<const uint2*>(ma.dec) + gen_row(ma, sa, ga, pf.pos, psa));
 #if defined(IDN_ABL_ROW1)
         const uint32_t row_q = 1;
 #elif defined(IDN_ABL_NOQMAP)
         const uint32_t row_q = (gq.spec(sq, pf.pos, psq) * 2654435761u >> 22) + 1;
 #else
-        const uint32_t row_q = ctx_row<P::kStatic>(mq, gq.spec(sq, pf.pos, psq));
+        const uint32_t row_q = gen_row<P::kStatic>(mq, sq, gq, pf.pos, psq);
 #endif
         const uint32_t slot_q = D.xq & kSlotMask, slot_a = D.xa & kSlotMask;
         uint32_t start, freq;
@@ -1999,8 +1998,8 @@ synth_kernel(const ModelDev* __restrict__ models, int32_t ia, int32_t iq, const 
         unsigned long long u = splitmix64(s);
         uint32_t slot_a = (uint32_t)u & kSlotMask, slot_q = (uint32_t)(u >> 14) & kSlotMask;
         uint32_t start, freq;
-        uint32_t row_a = ctx_row(ma, ga.spec(sa, pf.pos, psa));
-        uint32_t row_q = ctx_row(mq, gq.spec(sq, pf.pos, psq));
+        uint32_t row_a = gen_row(ma, sa, ga, pf.pos, psa);
+        uint32_t row_q = gen_row(mq, sq, gq, pf.pos, psq);
         uint2 pk = __ldg(reinterpret_cast<const uint2*>(ma.dec) + row_a);
         uint32_t a = acid_find(pk, slot_a, start, freq);
         uint32_t q = q_find(mq.dec + row_q * (uint32_t)kQRowBytes, slot_q, start, freq);
