@@ -40,15 +40,25 @@ WORKLOADS = {
     # config 2: 10 GB HiSeq 2000-shaped, 100 bp, compat mode.  The ERR174310 q-score model is missing from the
     # reference checkout (.MISSING_LARGE_BLOBS), SRR2962693 (same spec type, HiSeq 2500) stands in.
     "hiseq100": dict(acid="ERR174310__human__illumina_hiseq_2000__acids", q="SRR2962693__human__illumina_hiseq_2500__q_scores",
-                     read_len=(100, 100), reads=40_485_830, name_len=41, seed=20240601, n_ppm=500, mode="compat",
+                     read_len=(100, 100), reads=40_485_830, name_len=41, seed=20240601, n_ppm=500, mode="compat", select=1,
                      desc="synthetic 10 GB Illumina HiSeq 2000-shaped FASTQ, 100 bp, compat mode (BASELINE.json configs[1])"),
-    "novaseq150": dict(acid="SRR8861483__human__illumina_novaseq_6000__acids", q="SRR8861483__human__illumina_novaseq_6000__q_scores",
-                       read_len=(150, 150), reads=28_500_000, name_len=44, seed=20240602, n_ppm=500, mode="native",
-                       desc="synthetic 10 GB NovaSeq 6000-shaped FASTQ, 150 bp, GPU-native multi-lane mode (a 10 GB per-GPU shard of BASELINE.json configs[2])"),
+    # config 3: 50 GB NovaSeq-shaped, 150 bp, native mode (142 857 143 reads x 350 B); a GPU that cannot hold it takes what fits
+    "novaseq150_native": dict(acid="SRR8861483__human__illumina_novaseq_6000__acids", q="SRR8861483__human__illumina_novaseq_6000__q_scores",
+                              read_len=(150, 150), reads=142_857_143, name_len=44, seed=20240602, n_ppm=500, mode="native", select=1,
+                              desc="synthetic 50 GB NovaSeq 6000-shaped FASTQ, 150 bp, GPU-native multi-lane mode (BASELINE.json configs[2])"),
+    # config 5: PacBio Sequel II-shaped long reads, variable-length blocks
     "pacbio": dict(acid="m64187e__sars_cov_2__sequel_ii_e__acids", q="m64187e__sars_cov_2__sequel_ii_e__q_scores",
-                   read_len=(10_000, 20_000), reads=166_000, name_len=40, seed=20240603, n_ppm=0, mode="compat",
-                   desc="synthetic 5 GB PacBio Sequel II-shaped FASTQ, 10-20 kb reads (configs[4])"),
+                   read_len=(10_000, 20_000), reads=166_000, name_len=40, seed=20240603, n_ppm=0, mode="compat", select=1,
+                   desc="synthetic 5 GB PacBio Sequel II-shaped FASTQ, 10-20 kb reads, compat mode (BASELINE.json configs[4])"),
+    # configs[3] / the reference's default path: per-read greedy selection among the 4 + 4 models that quality 7 retains
+    # (idn/compressor.rs:184-194, compressor_initializer.rs:53-74) out of the whole models/ directory
+    "hiseq100_select4": dict(acid="ERR174310__human__illumina_hiseq_2000__acids", q="SRR2962693__human__illumina_hiseq_2500__q_scores",
+                             read_len=(100, 100), reads=40_485_830, name_len=41, seed=20240601, n_ppm=500, mode="compat", select=4,
+                             desc="synthetic 10 GB HiSeq-shaped FASTQ, 100 bp, compat mode, per-read model selection among the 4 + 4 "
+                                  "models quality 7 retains from the 22 bundled ones (reference default path; BASELINE.json configs[3])"),
 }
+WORKLOADS["novaseq150"] = WORKLOADS["novaseq150_native"]  # round-1 name
+EXTRA_WORKLOADS = ["novaseq150_native", "pacbio", "hiseq100_select4"]  # sub-records of the default run (the north-star shapes)
 
 
 def read_lengths(w: dict, n_reads: int, first: int) -> np.ndarray:
@@ -206,20 +216,26 @@ class Chunk:
                  "out_cap", "block_off", "block_crc", "stats", "dec_off", "dec_len", "dec_status", "dec_read_off", "batch")
 
 
-def run_gpu(args, w: dict):
+class Env:
+    """process-wide state of the GPU arm: device, torch, the library context, the process group"""
+    pass
+
+
+def setup_gpu():
     import torch
 
     from idencomp_b200 import capi, host
-
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
+    env = Env()
+    env.torch, env.capi, env.host = torch, capi, host
+    env.rank = int(os.environ.get("RANK", "0"))
+    env.world = int(os.environ.get("WORLD_SIZE", "1"))
+    env.local = int(os.environ.get("LOCAL_RANK", "0"))
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: there is no CPU fallback (use --impl reference for the CPU arm)")
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    dist = None
-    if world > 1:
+    torch.cuda.set_device(env.local)
+    env.dev = torch.device("cuda", env.local)
+    env.dist = None
+    if env.world > 1:
         import torch.distributed as dist
         # stdout carries the one JSON line and nothing else: NCCL's version banner (NCCL_DEBUG=VERSION/WARN on some boxes)
         # goes to stderr while the communicator is set up
@@ -227,41 +243,73 @@ def run_gpu(args, w: dict):
         saved_stdout = os.dup(1)
         os.dup2(2, 1)
         try:
-            dist.init_process_group("nccl", device_id=dev)
+            dist.init_process_group("nccl", device_id=env.dev)
             dist.barrier()
             torch.cuda.synchronize()
         finally:
             os.dup2(saved_stdout, 1)
             os.close(saved_stdout)
+        env.dist = dist
+    env.ctx = capi.Context(env.local)
+    env.stream = torch.cuda.current_stream()
+    env.sp = C.c_void_p(env.stream.cuda_stream)
+    env.models = {}  # file stem -> (host.Model, handle in env.ctx)
+    return env
 
-    ctx = capi.Context(local)
-    L = ctx.L
-    am = host.Model.load(MODELS / (w["acid"] + ".msgpack"))
-    qm = host.Model.load(MODELS / (w["q"] + ".msgpack"))
-    handles = np.asarray([am.upload(ctx), qm.upload(ctx)], dtype=np.int32)
-    synth_pair = (int(handles[0]), int(handles[1]))
-    model_names = [w["acid"], w["q"]]
-    if args.select > 1:
-        # per-read model selection among K acid + K q-score models (quality-7 semantics, BASELINE.json configs[3]):
-        # the workload's own pair plus the first K-1 other bundled models of each type, acid ids first
-        pool = {0: [], 1: []}
-        for pth in sorted(MODELS.glob("*.msgpack")):
-            if pth.stem in (w["acid"], w["q"]):
-                continue
-            m = host.Model.load(pth)
-            if len(pool[m.model_type]) < args.select - 1:
-                pool[m.model_type].append((pth.stem, m))
-        acid_set = [(w["acid"], am)] + pool[0]
-        q_set = [(w["q"], qm)] + pool[1]
-        hs = [int(handles[0])] + [m.upload(ctx) for _, m in pool[0]] + [int(handles[1])] + [m.upload(ctx) for _, m in pool[1]]
-        handles = np.asarray(hs, dtype=np.int32)
-        model_names = [n for n, _ in acid_set] + [n for n, _ in q_set]
-    n_handles = len(handles)
-    stream = torch.cuda.current_stream()
-    sp = C.c_void_p(stream.cuda_stream)
+
+def model_handle(env, stem: str) -> int:
+    if stem not in env.models:
+        m = env.host.Model.load(MODELS / (stem + ".msgpack"))
+        env.models[stem] = (m, m.upload(env.ctx))
+    return env.models[stem][1]
+
+
+def retained_models(env, w: dict, block_reads: int):
+    """The model set the reference's default path would code this workload with: IdnCompressor at quality 7 over the WHOLE
+    models/ directory retains (7 + 1) / 2 = 4 models per type, clustered on the cost matrix of the first block
+    (compressor_initializer.rs:53-74).  Runs the repository's host mirror (IdnCompressor, csrc/host/idn.cpp) on the first
+    block of the workload; returns the file stems in container order (acid ids first)."""
+    host, torch = env.host, env.torch
+    ro = np.zeros(block_reads + 1, dtype=np.uint64)
+    np.cumsum(read_lengths(w, block_reads, 0), out=ro[1:])
+    S = int(ro[-1])
+    a_d = torch.empty(S + 16, dtype=torch.uint8, device=env.dev)
+    q_d = torch.empty(S + 16, dtype=torch.uint8, device=env.dev)
+    ro_d = torch.from_numpy(ro.view(np.int64)).to(env.dev)
+    env.ctx.check(env.ctx.L.idn_gpu_synth_reads_dev(env.ctx.h, model_handle(env, w["acid"]), model_handle(env, w["q"]), ro_d.data_ptr(),
+                                                    block_reads, 0, w["seed"], w["n_ppm"], a_d.data_ptr(), q_d.data_ptr(), env.sp))
+    torch.cuda.synchronize()
+    stems = sorted(p.stem for p in MODELS.glob("*.msgpack"))
+    all_models = [host.Model.load(MODELS / (st + ".msgpack")) for st in stems]
+    by_id = {m.identifier: st for m, st in zip(all_models, stems)}
+    c = host.IdnCompressor(all_models, quality=7, include_identifiers=False, device=env.local)
+    c.add_batch(ro, a_d[:S].cpu().numpy(), q_d[:S].cpu().numpy())
+    c.finish()
+    names = [by_id[i] for i in c.retained_models()]
+    c.close()
+    return names
+
+
+def run_workload(env, args, name: str, w: dict, *, steps: int, warmup: int, main: bool):
+    """One workload on this rank's GPU: device-resident leg (timed with CUDA events), optional e2e leg (host buffers),
+    and for the main workload the FASTQ text leg.  Returns the raw numbers of this rank; run_gpu reduces them over ranks."""
+    torch, capi, ctx = env.torch, env.capi, env.ctx
+    L, dev, sp, stream = ctx.L, env.dev, env.sp, env.stream
+    rank, world = env.rank, env.world
+    select = args.select if main and args.select > 1 else w.get("select", 1)
 
     # ---- the shard of this rank (weak scaling: every rank holds the workload's read count) ----
     n_reads = args.reads or w["reads"]
+    lo, hi = w["read_len"]
+    note = None
+    if not (main and args.reads):
+        # device memory of the device-resident leg per symbol: symbols in (2) + decoded out (2) + container capacity (1.5) and
+        # ~1 more for the library's workspaces of a 1024-block call and the e2e staging
+        free_b, _ = torch.cuda.mem_get_info()
+        fit = int(0.80 * free_b / (6.5 * (lo + hi) / 2))
+        if n_reads > fit:
+            note = f"{n_reads} reads asked, {fit} fit the free device memory ({free_b / 1e9:.0f} GB)"
+            n_reads = fit
     first_index = rank * n_reads
     lens = read_lengths(w, n_reads, first_index)
     read_off_h = np.zeros(n_reads + 1, dtype=np.uint64)
@@ -271,11 +319,19 @@ def run_gpu(args, w: dict):
     n_blocks = len(block_first_h) - 1
     fq = fastq_bytes(w, n_reads, S)
 
+    model_names = [w["acid"], w["q"]]
+    if select > 1:
+        model_names = retained_models(env, w, int(block_first_h[1]))
+        if w["acid"] not in model_names or w["q"] not in model_names:
+            note = (note + "; " if note else "") + "the clustering did not retain the pair the reads were drawn from"
+    handles = np.asarray([model_handle(env, st) for st in model_names], dtype=np.int32)
+    n_handles = len(handles)
+
     read_off_d = torch.from_numpy(read_off_h.view(np.int64)).to(dev)
     acids_d = torch.empty(S + 16, dtype=torch.uint8, device=dev)
     quals_d = torch.empty(S + 16, dtype=torch.uint8, device=dev)
-    ctx.check(L.idn_gpu_synth_reads_dev(ctx.h, synth_pair[0], synth_pair[1], read_off_d.data_ptr(), n_reads, first_index,
-                                        w["seed"], w["n_ppm"], acids_d.data_ptr(), quals_d.data_ptr(), sp))
+    ctx.check(L.idn_gpu_synth_reads_dev(ctx.h, model_handle(env, w["acid"]), model_handle(env, w["q"]), read_off_d.data_ptr(), n_reads,
+                                        first_index, w["seed"], w["n_ppm"], acids_d.data_ptr(), quals_d.data_ptr(), sp))
     torch.cuda.synchronize()
 
     # ---- chunks of whole blocks: one library call per chunk and direction ----
@@ -353,8 +409,8 @@ def run_gpu(args, w: dict):
 
     def barrier():
         torch.cuda.synchronize()
-        if dist is not None:
-            dist.barrier()
+        if env.dist is not None:
+            env.dist.barrier()
         torch.cuda.synchronize()
 
     def measure(mode_name, steps, warmup, profile):
@@ -375,7 +431,7 @@ def run_gpu(args, w: dict):
         if profile:
             ctx.profile(True)
         launches0 = ctx.launches
-        sampler = ClockSampler(local)
+        sampler = ClockSampler(env.local)
         sampler.start()
         ev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(steps)]
         t_wall0 = time.perf_counter()
@@ -395,57 +451,74 @@ def run_gpu(args, w: dict):
                "t_total": ev[0][0].elapsed_time(ev[-1][2]) / 1e3}
         if profile:
             ctx.profile(False)
-        # lossless round trip of the whole workload, checked on the device outside the timed region
+        # lossless round trip of the whole workload, checked on the device outside the timed region (the bit-exactness of
+        # the container against the oracle is the parity tests' job: tests/test_gpu_variants.py covers every kernel variant
+        # and both container modes on reads drawn by this same generator)
         ok = bool(torch.equal(dec_a[:S], acids_d[:S]) and torch.equal(dec_q[:S], quals_d[:S]))
         if os.environ.get("IDN_BENCH_NOVERIFY"):  # kernel ablation experiments (tools/var_sweep.sh) produce wrong symbols on purpose
             ok = False
         else:
             check_decode_status()
         if not ok and not os.environ.get("IDN_BENCH_NOVERIFY"):
-            raise SystemExit(f"round trip mismatch in {mode_name} mode: the decoded symbols differ from the input")
+            raise SystemExit(f"round trip mismatch in {mode_name} mode ({name}): the decoded symbols differ from the input")
         res["verified"] = ok
         return res
 
-    main_mode = args.mode or w["mode"]
+    main_mode = (args.mode if main else "") or w["mode"]
     other_mode = "native" if main_mode == "compat" else "compat"
     other = None
-    if not args.no_other_mode and world == 1:  # a short look at the other container format (ratio delta, throughput); not the headline
+    if main and not args.no_other_mode and world == 1:  # a short look at the other container format (ratio delta, throughput)
         other = measure(other_mode, 2, 3, False)
-    m = measure(main_mode, args.steps, args.warmup, True)
-    launches, clocks, t_wall, sizes, out_bytes, payload_bytes, prof = (m["launches"], m["clocks"], m["t_wall"], m["sizes"],
-                                                                        m["out_bytes"], m["payload_bytes"], m["prof"])
-    tc, td, t_total, verified = m["tc"], m["td"], m["t_total"], m["verified"]
+    elif not main and world == 1 and main_mode == "native" and not args.no_other_mode:
+        other = measure(other_mode, 1, 3, False)  # the ratio delta against the compat output on the same input (north_star)
+    m = measure(main_mode, steps, warmup, True)
 
-    # ---- row f1, timed separately: FASTQ text -> symbols (parse) and symbols -> text (format) on the device ----
     fastq = None
-    if not args.no_fastq and rank == 0:
+    if main and not args.no_fastq and rank == 0:  # row f1, timed separately: FASTQ text <-> symbols on the device
         fastq = fastq_leg(args, w, capi, torch, ctx, sp, stream, acids_d, quals_d, read_off_h, min(n_reads, 4_000_000))
 
-    # ---- e2e: the host-pointer C-ABI calls on pinned host buffers, several ctx in flight ----
     e2e = None
-    if not args.no_e2e and args.select <= 1:
-        e2e = run_e2e(args, w, capi, host, torch, local, chunks, acids_d, quals_d, read_off_h, block_first_h, sizes, dist, fq,
-                      MODES[main_mode])
+    if not args.no_e2e:  # the host-pointer C-ABI calls on pinned host buffers
+        del dec_a, dec_q  # the e2e leg decodes into host buffers; give the device memory back first (torch caches it otherwise,
+        torch.cuda.empty_cache()  # and the other contexts of the e2e leg allocate with cudaMalloc)
+        e2e = run_e2e(args, w, env, model_names, chunks, acids_d, quals_d, read_off_h, block_first_h, m["sizes"], fq, MODES[main_mode],
+                      steps=(args.e2e_steps if main else 2), budget_bytes=(None if main else args.extra_e2e_gb * 1e9))
 
-    # ---- max over ranks ----
-    t_max = t_total
-    tc_max, td_max = tc, td
-    if dist is not None:
-        t = torch.tensor([t_total, tc, td, e2e["_t"] if e2e else 0.0], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        t_max, tc_max, td_max = float(t[0]), float(t[1]), float(t[2])
-        if e2e:
-            e2e["_t"] = float(t[3])
-    value = 2 * fq * args.steps * world / t_max / 1e9
+    rec = {"name": name, "w": w, "mode": main_mode, "n_reads": n_reads, "S": S, "fq": fq, "n_blocks": n_blocks, "chunks": len(chunks),
+           "model_names": model_names, "select": select, "m": m, "other": other, "other_mode": other_mode, "e2e": e2e, "fastq": fastq,
+           "note": note, "steps": steps, "warmup": warmup}
+    del acids_d, quals_d, out_d, chunks
+    torch.cuda.empty_cache()
+    return rec
 
-    # ---- roofline of the dominant kernel (by device time inside the timed region) ----
+
+def reduce_record(env, rec):
+    """max over ranks of the timed regions; fills the rates of one workload record"""
+    m, e2e = rec["m"], rec["e2e"]
+    t = [m["t_total"], m["tc"], m["td"], e2e["_t"] if e2e else 0.0]
+    if env.dist is not None:
+        tt = env.torch.tensor(t, dtype=env.torch.float64, device=env.dev)
+        env.dist.all_reduce(tt, op=env.dist.ReduceOp.MAX)
+        t = [float(x) for x in tt]
+    rec["t_max"], rec["tc_max"], rec["td_max"] = t[0], t[1], t[2]
+    if e2e:
+        e2e["_t"] = t[3]
+    world, fq, steps = env.world, rec["fq"], rec["steps"]
+    rec["value"] = 2 * fq * steps * world / rec["t_max"] / 1e9
+    rec["compress_GBps"] = fq * steps * world / rec["tc_max"] / 1e9
+    rec["decompress_GBps"] = fq * steps * world / rec["td_max"] / 1e9
+
+
+def roofline_of(rec):
+    """roofline of the dominant kernel (by device time inside the timed region) of one workload record"""
+    m, S, steps = rec["m"], rec["S"], rec["steps"]
+    prof, payload_bytes, out_bytes = m["prof"], m["payload_bytes"], m["out_bytes"]
     peak, peak_src = measured_peak_gbs()
     ksum = sum(ms for _, ms in prof.values()) or 1.0
-    dom = max(prof.items(), key=lambda kv: kv[1][1])
-    dname, (dn, dms) = dom
+    dname, (dn, dms) = max(prof.items(), key=lambda kv: kv[1][1])
     # algorithmic bytes per launch (DESIGN.md "Kernels"): encode reads 2 B/symbol and writes the rANS payloads;
     # decode reads the container chunk and writes 2 B/symbol; score reads 2 B/symbol per launch
-    per_chunk = len(chunks)
+    per_chunk = rec["chunks"]
     alg = {"encode": (2 * S + payload_bytes) / per_chunk, "decode": (2 * S + out_bytes) / per_chunk,
            "encode_lane": (2 * S + payload_bytes) / per_chunk, "decode_lane": (2 * S + out_bytes) / per_chunk,
            "score": 2 * S / per_chunk, "assemble": 2 * payload_bytes / per_chunk, "crc_read": 2 * S / per_chunk}.get(dname, 2 * S / per_chunk)
@@ -457,51 +530,106 @@ def run_gpu(args, w: dict):
             traffic = json.loads(tpath.read_text())[dname]["bytes_per_symbol"] * S / per_chunk
         except Exception:
             traffic = None
-    roofline = {"bound": "hbm", "kernel": dname + "_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_launch": alg,
-                "avg_launch_ms": dms / dn, "share_of_step": dms / ksum,
-                "whole_path": {"compress_GBps_alg": (2 * S + out_bytes) * args.steps / tc / 1e9,
-                               "decompress_GBps_alg": (2 * S + out_bytes) * args.steps / td / 1e9},
-                "kernels_ms_per_step": {k: v[1] / args.steps for k, v in sorted(prof.items(), key=lambda kv: -kv[1][1])}}
+    return {"bound": "hbm", "kernel": dname + "_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+            "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_launch": alg, "launches_per_step": dn / steps,
+            "avg_launch_ms": dms / dn, "share_of_step": dms / ksum,
+            "whole_path": {"compress_GBps_alg": (2 * S + out_bytes) * steps / m["tc"] / 1e9,
+                           "decompress_GBps_alg": (2 * S + out_bytes) * steps / m["td"] / 1e9},
+            "kernels_ms_per_step": {k: v[1] / steps for k, v in sorted(prof.items(), key=lambda kv: -kv[1][1])}}
 
+
+def e2e_record(env, rec):
+    e2e = rec["e2e"]
+    if not e2e:
+        return None
+    world, fq = env.world, rec["fq"]
+    return {"value": 2 * fq * e2e["steps"] * world / e2e["_t"] / 1e9, "unit": "GB/s", "h2d_bytes_per_step": e2e["h2d"],
+            "d2h_bytes_per_step": e2e["d2h"], "steps": e2e["steps"], "threads": e2e["threads"], "chunk_blocks": e2e["chunk_blocks"],
+            "compress_GBps": e2e["cGBps"] * world, "decompress_GBps": e2e["dGBps"] * world,
+            "per_direction_note": "rank 0's own phase times x n_gpus", "sample": e2e["sample"]}
+
+
+def sub_record(env, rec):
+    """what the default run reports for each of the north-star workloads besides the headline one"""
+    m, w = rec["m"], rec["w"]
+    rf = roofline_of(rec)
+    out = {"workload": w["desc"], "mode": rec["mode"], "reads_per_gpu": rec["n_reads"], "fastq_bytes_per_gpu": rec["fq"],
+           "blocks_per_gpu": rec["n_blocks"], "models": rec["model_names"], "steps": rec["steps"], "warmup": rec["warmup"],
+           "value": rec["value"], "unit": "GB/s", "compress_GBps": rec["compress_GBps"], "decompress_GBps": rec["decompress_GBps"],
+           "ms_per_step": rec["t_max"] / rec["steps"] * 1e3, "container_bytes_per_read": m["out_bytes"] / rec["n_reads"],
+           "bits_per_base": 8 * m["payload_bytes"] / rec["S"], "verified_round_trip": m["verified"], "gpu_launches": m["launches"],
+           "clocks": m["clocks"],
+           "roofline": {k: rf[k] for k in ("kernel", "achieved", "peak", "frac", "algorithmic_bytes_per_launch", "avg_launch_ms",
+                                           "share_of_step", "kernels_ms_per_step")},
+           "e2e": e2e_record(env, rec)}
+    if rec["other"]:
+        o = rec["other"]
+        out["ratio_delta_vs_" + rec["other_mode"]] = {"container_bytes_per_read": o["out_bytes"] / rec["n_reads"],
+                                                      "size_vs_" + rec["other_mode"]: m["out_bytes"] / o["out_bytes"],
+                                                      "verified_round_trip": o["verified"]}
+    if rec["note"]:
+        out["note"] = rec["note"]
+    return out
+
+
+def run_gpu(args, w: dict):
+    env = setup_gpu()
+    rank, world = env.rank, env.world
+    rec = run_workload(env, args, args.workload, w, steps=args.steps, warmup=args.warmup, main=True)
+    reduce_record(env, rec)
+    extras = {}
+    if args.extra_workloads and not (args.acid or args.q or args.reads):
+        for xname in EXTRA_WORKLOADS:
+            if xname == args.workload or WORKLOADS[xname] is w:
+                continue
+            x = run_workload(env, args, xname, dict(WORKLOADS[xname]), steps=args.extra_steps, warmup=3, main=False)
+            reduce_record(env, x)
+            extras[xname] = x
     if rank == 0:
+        m = rec["m"]
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
             cpu = cpu_baseline(args, w)
+        S, n_reads, fq = rec["S"], rec["n_reads"], rec["fq"]
         line = {
-            "metric": "fastq_compress_decompress_GBps", "value": value, "unit": "GB/s", "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": t_max / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+            "metric": "fastq_compress_decompress_GBps", "value": rec["value"], "unit": "GB/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": rec["t_max"] / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "u32", "data": "synthetic (model-driven sampler, SURVEY.md 8d)",
-            "config": {"workload": w["desc"], "name": args.workload, "mode": main_mode, "acid_model": w["acid"], "q_model": w["q"],
-                       "reads_per_gpu": n_reads, "symbols_per_gpu": S, "fastq_bytes_per_gpu": fq, "blocks_per_gpu": n_blocks,
-                       "block_symbols": BLOCK_SYMBOLS, "chunk_blocks": cb, "names": "not stored (--no-identifiers protocol, "
-                       "util/benchmark.py:161-179); their bytes count as FASTQ input", "l2": f"inputs {2 * S / 1e9:.1f} GB >> 126 MB L2, no flush needed",
-                       "model_selection": ("explicit pair (1 acid + 1 q-score model), quality 7 semantics" if args.select <= 1 else
-                                           f"per-read greedy selection among {args.select}+{args.select} models, quality 7 semantics"),
-                       "models": model_names},
-            "compress_GBps": fq * args.steps * world / tc_max / 1e9, "decompress_GBps": fq * args.steps * world / td_max / 1e9,
-            "container_bytes_per_read": out_bytes / n_reads, "bits_per_base": 8 * payload_bytes / S, "verified_round_trip": verified,
-            "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "wall_s_timed": t_wall,
+            "config": {"workload": w["desc"], "name": args.workload, "mode": rec["mode"], "acid_model": w["acid"], "q_model": w["q"],
+                       "reads_per_gpu": n_reads, "symbols_per_gpu": S, "fastq_bytes_per_gpu": fq, "blocks_per_gpu": rec["n_blocks"],
+                       "block_symbols": BLOCK_SYMBOLS, "chunk_blocks": args.chunk_blocks,
+                       "names": "not stored (--no-identifiers protocol, util/benchmark.py:161-179); their bytes count as FASTQ input: the "
+                                f"kernels touch the {2 * S / 1e9:.1f} GB of symbols of the {fq / 1e9:.1f} GB of FASTQ text (both arms alike)",
+                       "l2": f"inputs {2 * S / 1e9:.1f} GB >> 126 MB L2, no flush needed",
+                       "model_selection": ("explicit pair (1 acid + 1 q-score model), quality 7 semantics" if rec["select"] <= 1 else
+                                           "per-read greedy selection among the models quality 7 retains from models/"),
+                       "models": rec["model_names"],
+                       "parity": "round trip verified here; bit-exactness against the oracle: tests/test_gpu_variants.py, tests/test_gpu_parity.py"},
+            "compress_GBps": rec["compress_GBps"], "decompress_GBps": rec["decompress_GBps"],
+            "container_bytes_per_read": m["out_bytes"] / n_reads, "bits_per_base": 8 * m["payload_bytes"] / S,
+            "verified_round_trip": m["verified"], "gpu_launches": m["launches"], "clocks": m["clocks"], "roofline": roofline_of(rec),
+            "wall_s_timed": m["t_wall"],
         }
-        if e2e:
-            line["e2e"] = {"value": 2 * fq * e2e["steps"] * world / e2e["_t"] / 1e9, "unit": "GB/s",
-                           "h2d_bytes_per_step": e2e["h2d"], "d2h_bytes_per_step": e2e["d2h"], "steps": e2e["steps"],
-                           "threads": e2e["threads"], "chunk_blocks": args.e2e_chunk_blocks, "compress_GBps": e2e["cGBps"] * world, "decompress_GBps": e2e["dGBps"] * world,
-                           "per_direction_note": "rank 0's own phase times x n_gpus", "sample": e2e["sample"]}
+        e = e2e_record(env, rec)
+        if e:
+            line["e2e"] = e
         if cpu:
             line["cpu_baseline"] = cpu
-        if fastq:
-            line["fastq_text"] = fastq
-        if other:
-            line["other_mode"] = {"mode": other_mode, "compress_GBps": fq * 2 / other["tc"] / 1e9, "decompress_GBps": fq * 2 / other["td"] / 1e9,
-                                  "container_bytes_per_read": other["out_bytes"] / n_reads, "verified_round_trip": other["verified"],
-                                  "size_vs_main_mode": other["out_bytes"] / out_bytes, "steps": 2, "n_gpus": 1,
+        if rec["fastq"]:
+            line["fastq_text"] = rec["fastq"]
+        if rec["other"]:
+            o = rec["other"]
+            line["other_mode"] = {"mode": rec["other_mode"], "compress_GBps": fq * 2 / o["tc"] / 1e9, "decompress_GBps": fq * 2 / o["td"] / 1e9,
+                                  "container_bytes_per_read": o["out_bytes"] / n_reads, "verified_round_trip": o["verified"],
+                                  "size_vs_main_mode": o["out_bytes"] / m["out_bytes"], "steps": 2, "n_gpus": 1,
                                   "note": "this rank only, device-resident, 2 timed steps"}
+        if extras:
+            line["workloads"] = {k: sub_record(env, x) for k, x in extras.items()}
         print(json.dumps(line))
-    if dist is not None:
-        dist.barrier()
-        dist.destroy_process_group()
-    ctx.close()
+    if env.dist is not None:
+        env.dist.barrier()
+        env.dist.destroy_process_group()
+    env.ctx.close()
 
 
 def fastq_leg(args, w, capi, torch, ctx, sp, stream, acids_d, quals_d, read_off_h, n):
@@ -563,9 +691,10 @@ def cpu_baseline(args, w: dict) -> dict:
             "note": "reference-algorithm CPU restatement (oracle/), one worker thread per block like idn/thread_pool.rs"}
 
 
-def run_e2e(args, w, capi, host, torch, local, chunks, acids_d, quals_d, read_off_h, block_first_h, sizes, dist, fq_total, mode):
+def run_e2e(args, w, env, model_names, chunks, acids_d, quals_d, read_off_h, block_first_h, sizes, fq_total, mode, *, steps, budget_bytes):
     """Same step through idn_gpu_compress_blocks / idn_gpu_decompress_blocks with HOST buffers."""
     import psutil
+    torch, capi, host, local, dist = env.torch, env.capi, env.host, env.local, env.dist
     S = int(read_off_h[-1])
     total_out = sum(sizes.values())
     # the host-pointer calls are synchronous: overlap of H2D, kernels and D2H comes from several ctx in flight, so the
@@ -574,13 +703,14 @@ def run_e2e(args, w, capi, host, torch, local, chunks, acids_d, quals_d, read_of
     # a call should carry enough reads to fill the GPU (one thread per read: ~170 k in flight); blocks of long reads
     # hold a few hundred reads each, so those workloads get more blocks per call, down to 3 calls per workload
     reads_per_block = max(1, (len(read_off_h) - 1) // max(n_blocks_all, 1))
-    if args.e2e_chunk_blocks <= 0:  # automatic
+    chunk_blocks = args.e2e_chunk_blocks
+    if chunk_blocks <= 0:  # automatic
         want = max(32, -(-E2E_READS_PER_CALL // reads_per_block))
-        args.e2e_chunk_blocks = max(1, min(want, max(32, -(-n_blocks_all // 3))))
+        chunk_blocks = max(1, min(want, max(32, -(-n_blocks_all // 3))))
     e2e_chunks = []
-    for b0 in range(0, n_blocks_all, args.e2e_chunk_blocks):
+    for b0 in range(0, n_blocks_all, chunk_blocks):
         c = Chunk()
-        c.b0, c.b1 = b0, min(n_blocks_all, b0 + args.e2e_chunk_blocks)
+        c.b0, c.b1 = b0, min(n_blocks_all, b0 + chunk_blocks)
         c.r0, c.r1 = int(block_first_h[c.b0]), int(block_first_h[c.b1])
         c.s0, c.s1 = int(read_off_h[c.r0]), int(read_off_h[c.r1])
         c.n_reads, c.n_syms, c.n_blocks = c.r1 - c.r0, c.s1 - c.s0, c.b1 - c.b0
@@ -594,8 +724,10 @@ def run_e2e(args, w, capi, host, torch, local, chunks, acids_d, quals_d, read_of
     need = 4 * S + total_out * 2
     # pinned host memory budget of this rank: half of what is available, shared by the ranks of the box
     budget = 0.5 * psutil.virtual_memory().available / max(1, int(os.environ.get("LOCAL_WORLD_SIZE", os.environ.get("WORLD_SIZE", "1"))))
+    if budget_bytes:
+        budget = min(budget, budget_bytes)
     if need > budget:
-        keep = max(1, int(len(chunks) * budget / need))
+        keep = max(min(len(chunks), 2 * n_threads), int(len(chunks) * budget / need))
         use = chunks[:keep]
     s_end = use[-1].s1
     r_end = use[-1].r1
@@ -614,9 +746,9 @@ def run_e2e(args, w, capi, host, torch, local, chunks, acids_d, quals_d, read_of
     ctxs = []
     for _ in range(n_threads):
         cx = capi.Context(local)
-        am = host.Model.load(MODELS / (w["acid"] + ".msgpack"))
-        qm = host.Model.load(MODELS / (w["q"] + ".msgpack"))
-        ctxs.append((cx, np.asarray([am.upload(cx), qm.upload(cx)], dtype=np.int32)))
+        ctxs.append((cx, np.asarray([host.Model.load(MODELS / (st + ".msgpack")).upload(cx) for st in model_names], dtype=np.int32)))
+    n_models = len(model_names)
+
     def pinned(n, dtype):
         """every buffer the C-ABI calls copy from / to is page-locked (a pageable copy is staged and synchronous)"""
         t = torch.empty(max(int(n), 1), dtype=dtype, pin_memory=True)
@@ -650,7 +782,7 @@ def run_e2e(args, w, capi, host, torch, local, chunks, acids_d, quals_d, read_of
                 c, pc = use[i], per_chunk[i]
                 base = cont_np.ctypes.data + i * stride
                 if phase == 0:
-                    cx.check(L.idn_gpu_compress_blocks(cx.h, C.byref(pc["batch"]), mode, hd.ctypes.data, 2, 0, None,
+                    cx.check(L.idn_gpu_compress_blocks(cx.h, C.byref(pc["batch"]), mode, hd.ctypes.data, n_models, 0, None,
                                                        base, stride, pc["block_off"].ctypes.data, pc["crc"].ctypes.data,
                                                        C.byref(pc["stats"])))
                 else:
@@ -660,7 +792,7 @@ def run_e2e(args, w, capi, host, torch, local, chunks, acids_d, quals_d, read_of
                     doff[nb] = bo[nb]
                     dlen[:nb] = (bo[1:nb + 1] - bo[:nb] - 8).astype(np.uint32)
                     cx.check(L.idn_gpu_decompress_blocks(cx.h, base, doff.ctypes.data, dlen.ctypes.data, pc["crc"].ctypes.data,
-                                                         c.n_blocks, mode, hd.ctypes.data, 2, None, None,
+                                                         c.n_blocks, mode, hd.ctypes.data, n_models, None, None,
                                                          da_np.ctypes.data + c.s0, dq_np.ctypes.data + c.s0,
                                                          pc["ro_out"].ctypes.data, c.n_reads, c.n_syms, C.byref(pc["bad"])))
         except Exception as e:  # surfaced after the join
@@ -678,7 +810,7 @@ def run_e2e(args, w, capi, host, torch, local, chunks, acids_d, quals_d, read_of
             raise errors[0]
         return time.perf_counter() - t0
 
-    steps = max(1, min(args.steps, args.e2e_steps))
+    steps = max(1, steps)
     for _ in range(2):  # warm-up: sizes the staging buffers of every ctx
         phase(0)
         phase(1)
@@ -714,9 +846,9 @@ def run_e2e(args, w, capi, host, torch, local, chunks, acids_d, quals_d, read_of
     cbytes = sum(int(pc["stats"].out_bytes) for pc in per_chunk)
     h2d = 2 * s_end + 8 * (r_end + len(use)) + cbytes
     d2h = cbytes + 2 * s_end + 8 * (r_end + len(use))
-    return {"_t": t_all / frac, "steps": steps, "h2d": int(h2d / frac), "d2h": int(d2h / frac), "threads": n_threads,
+    return {"_t": t_all / frac, "steps": steps, "h2d": int(h2d / frac), "d2h": int(d2h / frac), "threads": n_threads, "chunk_blocks": chunk_blocks,
             "cGBps": fq * steps / tc / 1e9, "dGBps": fq * steps / td / 1e9,
-            "sample": "whole workload" if use is chunks else f"first {len(use)} of {len(chunks)} chunks (host memory), scaled"}
+            "sample": "whole workload" if use is chunks else f"first {len(use)} of {len(chunks)} chunks ({fq / 1e9:.1f} GB of FASTQ; pinned host memory budget), scaled"}
 
 
 def main():
@@ -726,6 +858,10 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="hiseq100", choices=sorted(WORKLOADS))
+    ap.add_argument("--no-extra-workloads", dest="extra_workloads", action="store_false",
+                    help="skip the sub-records of the other north-star workloads (NovaSeq native, PacBio, per-read selection)")
+    ap.add_argument("--extra-steps", type=int, default=5, help="timed steps of each extra workload")
+    ap.add_argument("--extra-e2e-gb", type=float, default=6.0, help="pinned host memory of the e2e leg of an extra workload (a sample, scaled)")
     ap.add_argument("--reads", type=int, default=0, help="reads per GPU (default: the workload's)")
     ap.add_argument("--acid", default="", help="acid model (file stem in models/) instead of the workload's")
     ap.add_argument("--q", default="", help="quality score model (file stem in models/) instead of the workload's")
@@ -735,10 +871,10 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-fastq", action="store_true", help="skip the FASTQ text parse/format leg (row f1)")
-    ap.add_argument("--select", type=int, default=1, help="K > 1: per-read selection among K acid + K q-score models (device-resident leg only)")
+    ap.add_argument("--select", type=int, default=1, help="> 1: per-read selection among the 4 + 4 models quality 7 retains from models/")
     ap.add_argument("--mode", default="", choices=["", "compat", "native"], help="container format (default: the workload's)")
     ap.add_argument("--no-other-mode", action="store_true", help="skip the short run of the other container format")
-    ap.add_argument("--lane-symbols", type=int, default=0, help="native mode lane quantum (default: the library's 4096)")
+    ap.add_argument("--lane-symbols", type=int, default=0, help="native mode lane quantum (default: the library's 2048)")
     ap.add_argument("--e2e-threads", type=int, default=3)
     ap.add_argument("--e2e-chunk-blocks", type=int, default=0,
                     help="blocks per host-pointer call in the e2e leg (default: 32, more for long reads so that a call holds ~E2E_READS_PER_CALL reads)")

@@ -27,7 +27,7 @@ MODE_COMPAT, MODE_NATIVE = 1, 2
 # every symbol include/idn_gpu.h declares (tests check the library exports all of them)
 EXPORTS = [
     "idn_gpu_abi_version", "idn_gpu_device_count", "idn_gpu_create", "idn_gpu_destroy", "idn_gpu_last_error",
-    "idn_gpu_launch_count", "idn_gpu_kernel_variant", "idn_gpu_kernel_variant_count", "idn_gpu_model_upload", "idn_gpu_model_release", "idn_gpu_score", "idn_gpu_score_dev",
+    "idn_gpu_launch_count", "idn_gpu_kernel_variant", "idn_gpu_kernel_variant_count", "idn_gpu_set_pipeline_blocks", "idn_gpu_model_upload", "idn_gpu_model_release", "idn_gpu_score", "idn_gpu_score_dev",
     "idn_gpu_compress_blocks", "idn_gpu_compress_blocks_dev", "idn_gpu_compress_bound", "idn_gpu_index_blocks",
     "idn_gpu_decompress_blocks", "idn_gpu_decompress_blocks_dev", "idn_gpu_decompress_reads", "idn_gpu_block_crc",
     "idn_gpu_synth_reads_dev", "idn_gpu_profile", "idn_gpu_profile_read", "idn_gpu_set_lane_symbols", "idn_gpu_set_walk",
@@ -100,6 +100,8 @@ def load():
     L.idn_gpu_kernel_variant.argtypes = [vp, i32, i32]
     L.idn_gpu_kernel_variant.restype = i32
     L.idn_gpu_kernel_variant_count.restype = i32
+    L.idn_gpu_set_pipeline_blocks.argtypes = [vp, u32]
+    L.idn_gpu_set_pipeline_blocks.restype = i32
     L.idn_gpu_model_upload.argtypes = [vp, i32, i32, i32, i32, i32, i32, u32, vp, vp, vp, u64, C.POINTER(i32)]
     L.idn_gpu_model_upload.restype = i32
     L.idn_gpu_model_release.argtypes = [vp, i32]
@@ -224,6 +226,10 @@ class Context:
     def kernel_variant(self, acid_handle: int, q_handle: int) -> int:
         """index of the compile-time-specialised codec kernels this pair launches, -1 = the run-time-generic ones"""
         return int(self.L.idn_gpu_kernel_variant(self.h, acid_handle, q_handle))
+
+    def set_pipeline_blocks(self, n: int):
+        """blocks per sub-chunk of the pipelined host-pointer calls (include/idn_gpu.h)"""
+        self.check(self.L.idn_gpu_set_pipeline_blocks(self.h, n))
 
     def set_lane_symbols(self, n: int):
         self.check(self.L.idn_gpu_set_lane_symbols(self.h, n))

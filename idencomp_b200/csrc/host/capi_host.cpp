@@ -1,6 +1,7 @@
 // capi_host.cpp -- flat C view (include/idn_host.h) of the C++ host mirror.
 #include "../../../include/idn_host.h"
 
+#include <algorithm>
 #include <cstring>
 #include <string>
 
@@ -145,10 +146,12 @@ extern "C" void idn_host_params_default(idn_host_params* p) {
     p->include_identifiers = d.include_identifiers;
     p->quality = d.quality;
     p->fast = d.fast;
-    p->device = d.device;
+    p->device = d.devices[0];
     p->mode = d.mode;
     p->batch_blocks = d.batch_blocks;
     p->lane_symbols = d.lane_symbols;
+    p->n_devices = 0;
+    for (int32_t& v : p->devices) v = 0;
 }
 
 extern "C" int32_t idn_host_compressor_new(const idn_host_model* const* models, uint32_t n_models, const idn_host_params* params,
@@ -164,7 +167,8 @@ extern "C" int32_t idn_host_compressor_new(const idn_host_model* const* models, 
                                     .include_identifiers(params->include_identifiers != 0)
                                     .quality((uint8_t)params->quality)
                                     .fast(params->fast != 0)
-                                    .device(params->device)
+                                    .devices(params->n_devices ? std::vector<int32_t>(params->devices, params->devices + std::min<uint32_t>(params->n_devices, 16))
+                                                               : std::vector<int32_t>{params->device})
                                     .mode(params->mode)
                                     .batch_blocks(params->batch_blocks)
                                     .lane_symbols(params->lane_symbols)
@@ -195,13 +199,7 @@ extern "C" int32_t idn_host_compressor_add_batch(idn_host_compressor* c, uint64_
                                                  const uint8_t* names) {
     if (!c || (n_reads && !read_off)) return set_err(IDN_E_INVALID_ARG, "NULL argument");
     return guarded([&] {
-        for (uint64_t r = 0; r < n_reads; r++) {
-            FastqSequence s;
-            if (name_off && names) s.identifier.assign(reinterpret_cast<const char*>(names) + name_off[r], name_off[r + 1] - name_off[r]);
-            s.acids.assign(acids + read_off[r], acids + read_off[r + 1]);
-            s.quality_scores.assign(quals + read_off[r], quals + read_off[r + 1]);
-            c->c->add_sequence(std::move(s));
-        }
+        c->c->add_batch(n_reads, read_off, acids, quals, name_off && names ? name_off : nullptr, name_off && names ? names : nullptr);
         return (int32_t)IDN_OK;
     });
 }
@@ -241,7 +239,12 @@ extern "C" int32_t idn_host_decompress(const idn_host_model* const* models, uint
     return guarded([&] {
         IdnDecompressorParams p;
         p.model_provider = provider_of(models, n_models);
-        p.device = device;
+        if (device >= 0) {
+            p.devices.assign(1, device);
+        } else {
+            p.devices.clear();
+            for (int32_t d = 0; d < -device; d++) p.devices.push_back(d);
+        }
         p.batch_blocks = batch_blocks ? batch_blocks : 32;
         uint64_t pos = 0;
         IdnDecompressor d([&](uint8_t* dst, size_t n) {
@@ -251,12 +254,16 @@ extern "C" int32_t idn_host_decompress(const idn_host_model* const* models, uint
             return k;
         }, std::move(p));
         auto res = std::make_unique<idn_host_decoded>();
-        while (auto s = d.next_sequence()) {
-            res->acids.insert(res->acids.end(), s->acids.begin(), s->acids.end());
-            res->quals.insert(res->quals.end(), s->quality_scores.begin(), s->quality_scores.end());
-            res->names.insert(res->names.end(), s->identifier.begin(), s->identifier.end());
-            res->read_off.push_back(res->acids.size());
-            res->name_off.push_back(res->names.size());
+        IdnDecompressor::DecodedBatch b;
+        while (d.next_batch(b)) {  // whole batches: no per-sequence objects on this path
+            const uint64_t n = b.read_off.size() - 1, s0 = res->acids.size(), n0 = res->names.size();
+            res->acids.insert(res->acids.end(), b.acids.begin(), b.acids.end());
+            res->quals.insert(res->quals.end(), b.quals.begin(), b.quals.end());
+            if (b.any_names) res->names.insert(res->names.end(), b.names.begin(), b.names.end());
+            for (uint64_t r = 1; r <= n; r++) {
+                res->read_off.push_back(s0 + b.read_off[r]);
+                res->name_off.push_back(n0 + (b.any_names ? b.name_off[r] : 0));
+            }
         }
         res->version = d.version();
         *out = res.release();

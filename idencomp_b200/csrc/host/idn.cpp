@@ -7,6 +7,8 @@
 #include <zlib.h>
 
 #include <algorithm>
+#include <atomic>
+#include <chrono>
 #include <cstring>
 #include <future>
 #include <numeric>
@@ -160,39 +162,80 @@ IdnCompressorParamsBuilder& IdnCompressorParamsBuilder::quality(uint8_t v) {
 IdnCompressor::IdnCompressor(Sink sink, IdnCompressorParams params) : sink_(std::move(sink)), params_(std::move(params)) {
     if (params_.fast) params_.quality = 1;  // IdnCompressorParamsBuilder::fast (idn/compressor.rs:244-251)
     if (params_.mode != IDN_MODE_COMPAT && params_.mode != IDN_MODE_NATIVE) throw IdnError(IDN_E_INVALID_STATE, "unknown container mode");
-    dev_.open(params_.device);
-    if (params_.mode == IDN_MODE_NATIVE) {
-        int32_t rc = idn_gpu_set_lane_symbols(dev_.ctx(), params_.lane_symbols);
-        if (rc) dev_.raise(rc);
+    if (params_.devices.empty()) params_.devices.assign(1, 0);
+    if (params_.batch_blocks == 0) params_.batch_blocks = 1;
+    for (int32_t d : params_.devices) {
+        workers_.push_back(std::make_unique<Worker>());
+        workers_.back()->dev.open(d);
+        if (params_.mode == IDN_MODE_NATIVE) {
+            int32_t rc = idn_gpu_set_lane_symbols(workers_.back()->dev.ctx(), params_.lane_symbols);
+            if (rc) workers_.back()->dev.raise(rc);
+        }
     }
 }
 
-IdnCompressor::~IdnCompressor() = default;
+IdnCompressor::~IdnCompressor() {
+    for (auto& f : pending_)  // jobs still running hold references to this object
+        if (f.valid()) f.wait();
+}
 
 void IdnCompressor::add_sequence(FastqSequence seq) {
-    if (finished_) throw IdnError(IDN_E_INVALID_STATE, "add_sequence after finish");
     if (seq.acids.size() != seq.quality_scores.size()) throw IdnError(IDN_E_INVALID_STATE, "acids and quality scores differ in length");
-    const uint64_t len = seq.len();
-    if (len > params_.max_block_total_len / 2)  // idn/compressor.rs:542-544
-        throw IdnError(IDN_E_SEQUENCE_TOO_LONG, "sequence too long: " + std::to_string(len) + " > " + std::to_string(params_.max_block_total_len / 2));
-    if (cur_block_len_ + len > params_.max_block_total_len) make_block();  // :526-540
-    acids_.insert(acids_.end(), seq.acids.begin(), seq.acids.end());
-    quals_.insert(quals_.end(), seq.quality_scores.begin(), seq.quality_scores.end());
-    read_off_.push_back(acids_.size());
-    if (params_.include_identifiers) names_.insert(names_.end(), seq.identifier.begin(), seq.identifier.end());
-    name_off_.push_back(names_.size());
-    cur_block_len_ += len;
-    stats_.in_symbols += len;
-    stats_.in_reads++;
-    stats_.in_identifier_bytes += seq.identifier.size();
+    const uint64_t ro[2] = {0, seq.acids.size()}, no[2] = {0, seq.identifier.size()};
+    add_batch(1, ro, seq.acids.data(), seq.quality_scores.data(), no, reinterpret_cast<const uint8_t*>(seq.identifier.data()));
+}
+
+void IdnCompressor::add_batch(uint64_t n_reads, const uint64_t* read_off, const uint8_t* acids, const uint8_t* quals,
+                              const uint64_t* name_off, const uint8_t* names) {
+    if (finished_) throw IdnError(IDN_E_INVALID_STATE, "add_sequence after finish");
+    uint64_t r = 0;
+    while (r < n_reads) {
+        // the run of reads [r, e) that goes into the batch under construction: block forming per read exactly as
+        // IdnCompressor::add_sequence does it (idn/compressor.rs:517-544); a full batch ends the run
+        uint64_t e = r;
+        const size_t sym0 = cur_.acids.size();
+        const uint64_t base = read_off[r];
+        bool dispatched = false;
+        while (e < n_reads && !dispatched) {
+            const uint64_t len = read_off[e + 1] - read_off[e];
+            if (len > params_.max_block_total_len / 2)  // idn/compressor.rs:542-544
+                throw IdnError(IDN_E_SEQUENCE_TOO_LONG, "sequence too long: " + std::to_string(len) + " > " + std::to_string(params_.max_block_total_len / 2));
+            if (cur_block_len_ + len > params_.max_block_total_len) {  // :526-540
+                const uint32_t n = (uint32_t)(cur_.read_off.size() - 1);
+                if (n != cur_.block_first.back()) {
+                    cur_.block_first.push_back(n);
+                    cur_block_len_ = 0;
+                    if (cur_.block_first.size() - 1 >= params_.batch_blocks) {
+                        dispatched = true;  // the run ends in front of read e; the batch goes out below
+                        break;
+                    }
+                }
+            }
+            cur_.read_off.push_back(sym0 + (read_off[e + 1] - base));
+            const uint64_t nl = (params_.include_identifiers && name_off) ? name_off[e + 1] - name_off[e] : 0;
+            cur_.name_off.push_back(cur_.name_off.back() + nl);
+            cur_block_len_ += len;
+            stats_.in_symbols += len;
+            stats_.in_reads++;
+            stats_.in_identifier_bytes += name_off ? name_off[e + 1] - name_off[e] : 0;
+            e++;
+        }
+        if (e > r) {
+            cur_.acids.insert(cur_.acids.end(), acids + read_off[r], acids + read_off[e]);
+            cur_.quals.insert(cur_.quals.end(), quals + read_off[r], quals + read_off[e]);
+            if (params_.include_identifiers && name_off && names) cur_.names.insert(cur_.names.end(), names + name_off[r], names + name_off[e]);
+        }
+        if (dispatched) flush_batch();
+        r = e;
+    }
 }
 
 void IdnCompressor::make_block() {
-    const uint32_t n_reads = (uint32_t)(read_off_.size() - 1);
-    if (n_reads == block_first_.back()) return;  // nothing since the last block
-    block_first_.push_back(n_reads);
+    const uint32_t n_reads = (uint32_t)(cur_.read_off.size() - 1);
+    if (n_reads == cur_.block_first.back()) return;  // nothing since the last block
+    cur_.block_first.push_back(n_reads);
     cur_block_len_ = 0;
-    if (block_first_.size() - 1 >= params_.batch_blocks) flush_batch();
+    if (cur_.block_first.size() - 1 >= params_.batch_blocks) flush_batch();
 }
 
 std::vector<ModelIdentifier> IdnCompressor::best_models(ModelType type, size_t model_num, const std::vector<uint32_t>& sizes,
@@ -213,6 +256,7 @@ std::vector<ModelIdentifier> IdnCompressor::best_models(ModelType type, size_t m
 
 void IdnCompressor::initialize() {
     ModelProvider& mp = params_.model_provider;
+    DeviceModels& dev0 = workers_[0]->dev;  // the file-level selection runs on the first device
     std::vector<size_t> of_type[2];
     for (size_t i = 0; i < mp.len(); i++) of_type[(size_t)mp[i].model_type()].push_back(i);
     if (of_type[0].empty() || of_type[1].empty()) throw IdnError(IDN_E_INVALID_STATE, "the model provider needs at least one model per type");
@@ -222,18 +266,18 @@ void IdnCompressor::initialize() {
         ids = {mp[of_type[0][0]].identifier(), mp[of_type[1][0]].identifier()};
     } else {
         // cost matrix over the reads of the FIRST block with every model of the provider (a6 on the device)
-        dev_.upload(mp);
-        const uint64_t n_reads = block_first_.size() > 1 ? block_first_[1] : read_off_.size() - 1;
+        dev0.upload(mp);
+        const uint64_t n_reads = cur_.block_first.size() > 1 ? cur_.block_first[1] : cur_.read_off.size() - 1;
         std::vector<uint32_t> sizes(n_reads * mp.len());
         idn_batch b{};
         b.n_reads = n_reads;
-        b.n_symbols = read_off_[n_reads];
-        b.acids = acids_.data();
-        b.quals = quals_.data();
-        b.read_off = read_off_.data();
+        b.n_symbols = cur_.read_off[n_reads];
+        b.acids = cur_.acids.data();
+        b.quals = cur_.quals.data();
+        b.read_off = cur_.read_off.data();
         if (n_reads) {
-            int32_t rc = idn_gpu_score(dev_.ctx(), &b, dev_.handles().data(), (uint32_t)mp.len(), sizes.data());
-            if (rc) dev_.raise(rc);
+            int32_t rc = idn_gpu_score(dev0.ctx(), &b, dev0.handles().data(), (uint32_t)mp.len(), sizes.data());
+            if (rc) dev0.raise(rc);
         }
         // ONE Clustering (one random stream) serves the acid models and then the q-score models, as the reference's
         // ModelChooser does (model_chooser.rs:14-24, compressor_initializer.rs:57-64)
@@ -247,7 +291,7 @@ void IdnCompressor::initialize() {
     }
     mp.filter_by_identifiers(ids);  // acid ids first, then q-score ids (compressor_initializer.rs:57-74)
     if (mp.len() > IDN_MAX_MODELS) throw IdnError(IDN_E_UNSUPPORTED, "too many retained models");
-    dev_.upload(mp);
+    for (auto& w : workers_) w->dev.upload(mp);  // every device holds the retained models
     retained_ = ids;
     // header + metadata (writer_idn.rs:25-59, data.rs:3-33)
     std::vector<uint8_t> h(kMagic, kMagic + 8);
@@ -261,23 +305,24 @@ void IdnCompressor::initialize() {
     initialized_ = true;
 }
 
-void IdnCompressor::flush_batch() {
-    const uint32_t n_blocks = (uint32_t)(block_first_.size() - 1);
-    if (n_blocks == 0) return;
-    if (!initialized_) initialize();
-    const uint64_t n_reads = block_first_.back();
+// one batch on one device: identifiers slices on host threads, everything else through the C-ABI
+IdnCompressor::Result IdnCompressor::compress_batch(Worker& w, const Batch& bt) const {
+    std::lock_guard<std::mutex> lock(w.mu);  // a ctx is single-owner
+    Result res;
+    const uint32_t n_blocks = (uint32_t)(bt.block_first.size() - 1);
+    const uint64_t n_reads = bt.block_first.back();
     // identifiers slices on host threads, like write_identifiers (compressor_block.rs:146-206): names joined by '\n'
     std::vector<std::vector<uint8_t>> name_slices(n_blocks);
     std::vector<uint32_t> prefix(n_blocks, 0);
     if (params_.include_identifiers) {
         const bool brotli = params_.quality >= 8;  // BROTLI_THRESHOLD (compressor_block.rs:146)
-        if (brotli && !Brotli::get().enc)  // fail early, on the caller's thread, when the library is missing
+        if (brotli && !Brotli::get().enc)
             throw IdnError(IDN_E_UNSUPPORTED, "Brotli identifier slices (quality 8-9) need libbrotlienc.so.1");
         auto one = [&](uint32_t b) {
             std::vector<uint8_t> joined;
-            for (uint32_t r = block_first_[b]; r < block_first_[b + 1]; r++) {
-                if (r > block_first_[b]) joined.push_back('\n');
-                joined.insert(joined.end(), names_.begin() + name_off_[r], names_.begin() + name_off_[r + 1]);
+            for (uint32_t r = bt.block_first[b]; r < bt.block_first[b + 1]; r++) {
+                if (r > bt.block_first[b]) joined.push_back('\n');
+                joined.insert(joined.end(), bt.names.begin() + bt.name_off[r], bt.names.begin() + bt.name_off[r + 1]);
             }
             std::vector<uint8_t> z = brotli ? Brotli::get().compress(joined.data(), joined.size()) : deflate_raw(joined.data(), joined.size());
             std::vector<uint8_t> s;
@@ -288,50 +333,87 @@ void IdnCompressor::flush_batch() {
             name_slices[b] = std::move(s);
         };
         if (params_.thread_num > 1) {
+            // thread_num workers take the blocks of the batch in turn
             std::vector<std::future<void>> jobs;
-            for (uint32_t b = 0; b < n_blocks; b++) jobs.push_back(std::async(std::launch::async, one, b));
+            std::atomic<uint32_t> next{0};
+            for (uint32_t t = 0; t < std::min<uint32_t>(params_.thread_num, n_blocks); t++)
+                jobs.push_back(std::async(std::launch::async, [&] {
+                    for (uint32_t b = next++; b < n_blocks; b = next++) one(b);
+                }));
             for (auto& j : jobs) j.get();
         } else {
             for (uint32_t b = 0; b < n_blocks; b++) one(b);
         }
         for (uint32_t b = 0; b < n_blocks; b++) prefix[b] = (uint32_t)name_slices[b].size();
     }
-    uint64_t prefix_total = std::accumulate(prefix.begin(), prefix.end(), (uint64_t)0);
+    res.prefix_total = std::accumulate(prefix.begin(), prefix.end(), (uint64_t)0);
     idn_batch b{};
     b.n_reads = n_reads;
-    b.n_symbols = read_off_[n_reads];
+    b.n_symbols = bt.read_off[n_reads];
     b.n_blocks = n_blocks;
-    b.acids = acids_.data();
-    b.quals = quals_.data();
-    b.read_off = read_off_.data();
-    b.block_first_read = block_first_.data();
+    b.acids = bt.acids.data();
+    b.quals = bt.quals.data();
+    b.read_off = bt.read_off.data();
+    b.block_first_read = bt.block_first.data();
     if (params_.include_identifiers) {
-        b.names = names_.empty() ? reinterpret_cast<const uint8_t*>("") : names_.data();
-        b.name_off = name_off_.data();
+        b.names = bt.names.empty() ? reinterpret_cast<const uint8_t*>("") : bt.names.data();
+        b.name_off = bt.name_off.data();
     }
-    out_.resize(idn_gpu_compress_bound(n_reads, b.n_symbols, n_blocks, prefix_total));
+    // capacity: what containers need in practice (1.25 B per symbol is beyond uniformly random input) and, should a batch
+    // ever need more, the library's worst-case bound
+    const uint64_t bound = idn_gpu_compress_bound(n_reads, b.n_symbols, n_blocks, res.prefix_total);
+    uint64_t cap = std::min<uint64_t>(bound, b.n_symbols + b.n_symbols / 4 + 24 * n_reads + 64ull * n_blocks + res.prefix_total + 4096);
     std::vector<uint64_t> block_off(n_blocks + 1);
     idn_compress_stats st{};
-    int32_t rc = idn_gpu_compress_blocks(dev_.ctx(), &b, params_.mode, dev_.handles().data(), (uint32_t)dev_.handles().size(),
-                                         params_.fast ? 1 : 0, params_.include_identifiers ? prefix.data() : nullptr, out_.data(),
-                                         out_.size(), block_off.data(), nullptr, &st);
-    if (rc) dev_.raise(rc);
+    for (;;) {
+        res.bytes.reset(new uint8_t[cap]);
+        int32_t rc = idn_gpu_compress_blocks(w.dev.ctx(), &b, params_.mode, w.dev.handles().data(), (uint32_t)w.dev.handles().size(),
+                                             params_.fast ? 1 : 0, params_.include_identifiers ? prefix.data() : nullptr, res.bytes.get(),
+                                             cap, block_off.data(), nullptr, &st);
+        if (rc == IDN_E_NOSPACE && cap < bound) {
+            cap = bound;
+            continue;
+        }
+        if (rc) w.dev.raise(rc);
+        break;
+    }
     for (uint32_t k = 0; k < n_blocks; k++)
-        if (prefix[k]) std::memcpy(out_.data() + block_off[k] + 8, name_slices[k].data(), prefix[k]);
-    sink_(out_.data(), st.out_bytes);  // blocks in order: this replaces IdnBlockLock (common.rs:10-57)
-    stats_.out_bytes += st.out_bytes;
-    stats_.out_identifier_bytes += prefix_total;
-    stats_.out_payload_bytes += st.payload_bytes;
-    stats_.acid_model_switches += st.acid_switches;
-    stats_.q_score_model_switches += st.q_switches;
-    stats_.blocks += n_blocks;
-    // keep the reads of an unfinished block (none: flush happens at block boundaries) and reset the batch
-    acids_.clear();
-    quals_.clear();
-    names_.clear();
-    read_off_.assign(1, 0);
-    name_off_.assign(1, 0);
-    block_first_.assign(1, 0);
+        if (prefix[k]) std::memcpy(res.bytes.get() + block_off[k] + 8, name_slices[k].data(), prefix[k]);
+    res.out_bytes = st.out_bytes;
+    res.payload_bytes = st.payload_bytes;
+    res.acid_switches = st.acid_switches;
+    res.q_switches = st.q_switches;
+    res.blocks = n_blocks;
+    return res;
+}
+
+void IdnCompressor::flush_batch() {
+    const uint32_t n_blocks = (uint32_t)(cur_.block_first.size() - 1);
+    if (n_blocks == 0) return;
+    if (!initialized_) initialize();
+    // the batch goes to the next device; up to two batches per device are in flight, results are written in block order
+    Worker* w = workers_[next_worker_++ % workers_.size()].get();
+    auto job = std::make_shared<Batch>(std::move(cur_));
+    cur_ = Batch();
+    pending_.push_back(std::async(std::launch::async, [this, w, job] { return compress_batch(*w, *job); }));
+    commit(false);
+}
+
+void IdnCompressor::commit(bool all) {
+    const size_t keep = all ? 0 : 2 * workers_.size();
+    while (!pending_.empty()) {
+        const bool ready = pending_.front().wait_for(std::chrono::seconds(0)) == std::future_status::ready;
+        if (!ready && pending_.size() <= keep) break;
+        Result r = pending_.front().get();  // rethrows what the job threw
+        pending_.pop_front();
+        sink_(r.bytes.get(), r.out_bytes);  // blocks in order: this replaces IdnBlockLock (common.rs:10-57)
+        stats_.out_bytes += r.out_bytes;
+        stats_.out_identifier_bytes += r.prefix_total;
+        stats_.out_payload_bytes += r.payload_bytes;
+        stats_.acid_model_switches += r.acid_switches;
+        stats_.q_score_model_switches += r.q_switches;
+        stats_.blocks += r.blocks;
+    }
 }
 
 void IdnCompressor::finish() {
@@ -339,6 +421,7 @@ void IdnCompressor::finish() {
     make_block();  // flush the partial block (idn/compressor.rs:575-578)
     flush_batch();
     if (!initialized_) initialize();  // empty file: header + metadata still get written
+    commit(true);
     const uint8_t terminator[8] = {0, 0, 0, 0, 0, 0, 0, 0};  // an empty block marks the end (:579)
     sink_(terminator, 8);
     stats_.out_bytes += 8;
@@ -347,10 +430,17 @@ void IdnCompressor::finish() {
 
 // ---- IdnDecompressor -------------------------------------------------------------------------------------------------
 IdnDecompressor::IdnDecompressor(Source source, IdnDecompressorParams params) : source_(std::move(source)), params_(std::move(params)) {
-    dev_.open(params_.device);
+    if (params_.devices.empty()) params_.devices.assign(1, 0);
     if (params_.batch_blocks == 0) params_.batch_blocks = 1;
+    for (int32_t d : params_.devices) {
+        workers_.push_back(std::make_unique<Worker>());
+        workers_.back()->dev.open(d);
+    }
 }
-IdnDecompressor::~IdnDecompressor() = default;
+IdnDecompressor::~IdnDecompressor() {
+    for (auto& f : pending_)
+        if (f.valid()) f.wait();
+}
 
 void IdnDecompressor::read_exact(uint8_t* dst, size_t n, const char* what) {
     size_t got = 0;
@@ -388,17 +478,14 @@ void IdnDecompressor::initialize() {
             if (!params_.model_provider.has_all_models({id})) throw IdnError(IDN_E_UNKNOWN_MODEL, "unknown model " + to_hex(id));
     }
     params_.model_provider.filter_by_identifiers(ids);
-    dev_.upload(params_.model_provider);
+    for (auto& w : workers_) w->dev.upload(params_.model_provider);
     initialized_ = true;
 }
 
-bool IdnDecompressor::read_batch() {
+bool IdnDecompressor::read_raw(RawBatch& rb) {
     // block headers + payloads of up to batch_blocks blocks into one buffer (idn/decompressor.rs:387-428)
-    std::vector<uint8_t> buf;
-    std::vector<uint64_t> off;
-    std::vector<uint32_t> len, crc;
     bool more = true;
-    while (off.size() < params_.batch_blocks) {
+    while (rb.off.size() < params_.batch_blocks) {
         uint8_t h[8];
         read_exact(h, 8, "a block header");
         uint32_t n = get_u32be(h), c = get_u32be(h + 4);
@@ -406,75 +493,109 @@ bool IdnDecompressor::read_batch() {
             more = false;
             break;
         }
-        off.push_back(buf.size());
-        len.push_back(n);
-        crc.push_back(c);
-        buf.resize(buf.size() + n);
-        read_exact(buf.data() + off.back(), n, "a block");
+        rb.off.push_back(rb.buf.size());
+        rb.len.push_back(n);
+        rb.crc.push_back(c);
+        rb.buf.resize(rb.buf.size() + n);
+        read_exact(rb.buf.data() + rb.off.back(), n, "a block");
     }
-    const uint32_t n_blocks = (uint32_t)off.size();
-    if (n_blocks == 0) return more;
-    off.push_back(buf.size());
+    return more;
+}
+
+IdnDecompressor::DecodedBatch IdnDecompressor::decode_batch(Worker& w, const RawBatch& rb) const {
+    std::lock_guard<std::mutex> lock(w.mu);
+    DecodedBatch out;
+    const uint32_t n_blocks = (uint32_t)rb.off.size();
+    if (n_blocks == 0) return out;
+    std::vector<uint64_t> off = rb.off;
+    off.push_back(rb.buf.size());
     const int32_t mode = version_ == 2 ? IDN_MODE_NATIVE : IDN_MODE_COMPAT;
-    const auto& handles = dev_.handles();
+    const auto& handles = w.dev.handles();
     idn_block_index_totals tot{};
     std::vector<uint32_t> block_first(n_blocks + 1);
-    int32_t rc = idn_gpu_index_blocks(dev_.ctx(), buf.data(), off.data(), len.data(), n_blocks, mode, handles.data(),
+    int32_t rc = idn_gpu_index_blocks(w.dev.ctx(), rb.buf.data(), off.data(), rb.len.data(), n_blocks, mode, handles.data(),
                                       (uint32_t)handles.size(), &tot, block_first.data());
-    if (rc) dev_.raise(rc);
+    if (rc) w.dev.raise(rc);
     // identifiers: leading Identifiers slices of every block, inflated on the host (decompressor_block.rs:146-192)
-    std::vector<uint8_t> names;
-    std::vector<uint64_t> name_off(tot.n_reads + 1, 0);
-    bool any_names = false;
+    out.name_off.assign(tot.n_reads + 1, 0);
     for (uint32_t b = 0; b < n_blocks; b++) {
-        const uint8_t* p = buf.data() + off[b];
+        const uint8_t* p = rb.buf.data() + off[b];
         size_t pos = 0;
         uint64_t r = block_first[b];
         const uint64_t r_end = block_first[b + 1];
-        while (pos < len[b] && p[pos] == 0x00) {
-            if (pos + 6 > len[b]) throw IdnError(IDN_E_SERIALIZE, "truncated identifiers slice");
+        while (pos < rb.len[b] && p[pos] == 0x00) {
+            if (pos + 6 > rb.len[b]) throw IdnError(IDN_E_SERIALIZE, "truncated identifiers slice");
             uint32_t n = get_u32be(p + pos + 1);
             uint8_t comp = p[pos + 5];
-            if (n > len[b] - pos - 6) throw IdnError(IDN_E_SERIALIZE, "truncated identifiers slice");
+            if (n > rb.len[b] - pos - 6) throw IdnError(IDN_E_SERIALIZE, "truncated identifiers slice");
             if (comp > 1) throw IdnError(IDN_E_SERIALIZE, "unknown identifier compression");
             std::vector<uint8_t> text = comp == 0 ? Brotli::get().decompress(p + pos + 6, n) : inflate_raw(p + pos + 6, n);
-            any_names = true;
+            out.any_names = true;
             // split at '\n': one identifier per sequence, in order (identifiers_as_lines)
             size_t s = 0;
             while (r < r_end) {
                 size_t e = s;
                 while (e < text.size() && text[e] != '\n') e++;
-                names.insert(names.end(), text.begin() + s, text.begin() + e);
-                name_off[++r] = names.size();
+                out.names.insert(out.names.end(), text.begin() + s, text.begin() + e);
+                out.name_off[++r] = out.names.size();
                 if (e >= text.size()) break;
                 s = e + 1;
             }
             pos += 6 + (size_t)n;
         }
-        for (; r < r_end; r++) name_off[r + 1] = names.size();  // sequences without an identifier
+        for (; r < r_end; r++) out.name_off[r + 1] = out.names.size();  // sequences without an identifier
     }
-    std::vector<uint8_t> acids(tot.n_symbols + 1), quals(tot.n_symbols + 1);
-    std::vector<uint64_t> read_off(tot.n_reads + 1, 0);
+    out.acids.resize(tot.n_symbols + 1);
+    out.quals.resize(tot.n_symbols + 1);
+    out.read_off.assign(tot.n_reads + 1, 0);
     int32_t bad = -1;
-    if (names.empty()) names.push_back(0);
-    rc = idn_gpu_decompress_blocks(dev_.ctx(), buf.data(), off.data(), len.data(), crc.data(), n_blocks, mode, handles.data(),
-                                   (uint32_t)handles.size(), any_names ? names.data() : nullptr, any_names ? name_off.data() : nullptr,
-                                   acids.data(), quals.data(), read_off.data(), tot.n_reads, tot.n_symbols, &bad);
-    if (rc) dev_.raise(rc);
-    for (uint64_t r = 0; r < tot.n_reads; r++) {
-        FastqSequence s;
-        if (any_names) s.identifier.assign(names.begin() + name_off[r], names.begin() + name_off[r + 1]);
-        s.acids.assign(acids.begin() + read_off[r], acids.begin() + read_off[r + 1]);
-        s.quality_scores.assign(quals.begin() + read_off[r], quals.begin() + read_off[r + 1]);
-        queue_.push_back(std::move(s));
+    if (out.names.empty()) out.names.push_back(0);
+    rc = idn_gpu_decompress_blocks(w.dev.ctx(), rb.buf.data(), off.data(), rb.len.data(), rb.crc.data(), n_blocks, mode, handles.data(),
+                                   (uint32_t)handles.size(), out.any_names ? out.names.data() : nullptr,
+                                   out.any_names ? out.name_off.data() : nullptr, out.acids.data(), out.quals.data(), out.read_off.data(),
+                                   tot.n_reads, tot.n_symbols, &bad);
+    if (rc) w.dev.raise(rc);
+    out.acids.resize(tot.n_symbols);
+    out.quals.resize(tot.n_symbols);
+    if (!out.any_names) out.names.clear();
+    return out;
+}
+
+// keeps up to two batches per device in flight (the reference reads and dispatches block jobs ahead the same way,
+// idn/decompressor.rs:387-428)
+void IdnDecompressor::prefetch() {
+    while (!eof_ && pending_.size() < 2 * workers_.size()) {
+        auto rb = std::make_shared<RawBatch>();
+        eof_ = !read_raw(*rb);
+        if (rb->off.empty()) break;
+        Worker* w = workers_[next_worker_++ % workers_.size()].get();
+        pending_.push_back(std::async(std::launch::async, [this, w, rb] { return decode_batch(*w, *rb); }));
     }
-    return more;
+}
+
+bool IdnDecompressor::next_batch(DecodedBatch& out) {
+    if (!initialized_) initialize();
+    prefetch();
+    if (pending_.empty()) return false;
+    out = pending_.front().get();
+    pending_.pop_front();
+    prefetch();
+    return true;
 }
 
 std::optional<FastqSequence> IdnDecompressor::next_sequence() {
-    if (!initialized_) initialize();
-    while (queue_.empty() && !eof_) eof_ = !read_batch();
-    if (queue_.empty()) return std::nullopt;
+    while (queue_.empty()) {
+        DecodedBatch b;
+        if (!next_batch(b)) return std::nullopt;
+        const uint64_t n = b.read_off.size() - 1;
+        for (uint64_t r = 0; r < n; r++) {
+            FastqSequence s;
+            if (b.any_names) s.identifier.assign(b.names.begin() + b.name_off[r], b.names.begin() + b.name_off[r + 1]);
+            s.acids.assign(b.acids.begin() + b.read_off[r], b.acids.begin() + b.read_off[r + 1]);
+            s.quality_scores.assign(b.quals.begin() + b.read_off[r], b.quals.begin() + b.read_off[r + 1]);
+            queue_.push_back(std::move(s));
+        }
+    }
     FastqSequence s = std::move(queue_.front());
     queue_.pop_front();
     return s;

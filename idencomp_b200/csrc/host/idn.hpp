@@ -15,6 +15,9 @@
 #include <cstdint>
 #include <deque>
 #include <functional>
+#include <future>
+#include <memory>
+#include <mutex>
 #include <optional>
 #include <stdexcept>
 #include <string>
@@ -52,7 +55,10 @@ struct IdnCompressorParams {
     uint8_t quality = 7;                              // 1..9
     bool fast = false;
     // additions of this implementation (defaults keep the reference's behaviour)
-    int32_t device = 0;
+    // GPUs that share the file: batches of `batch_blocks` blocks go round robin to the devices (blocks are independent,
+    // compressor_block.rs:61-62), every device holds the retained models, the file-level model selection runs on
+    // devices[0], and the results are committed in block order -- the container does not depend on the device count
+    std::vector<int32_t> devices{0};
     int32_t mode = IDN_MODE_COMPAT;  // IDN_MODE_NATIVE writes container version 2
     uint32_t batch_blocks = 32;      // blocks per device call
     uint32_t lane_symbols = 2048;    // native mode lane quantum
@@ -66,7 +72,8 @@ public:
     IdnCompressorParamsBuilder& include_identifiers(bool v) { p_.include_identifiers = v; return *this; }
     IdnCompressorParamsBuilder& quality(uint8_t v);  // throws std::invalid_argument outside 1..9 (CompressionQuality::new)
     IdnCompressorParamsBuilder& fast(bool v) { p_.fast = v; return *this; }
-    IdnCompressorParamsBuilder& device(int32_t v) { p_.device = v; return *this; }
+    IdnCompressorParamsBuilder& device(int32_t v) { p_.devices.assign(1, v); return *this; }
+    IdnCompressorParamsBuilder& devices(std::vector<int32_t> v) { if (!v.empty()) p_.devices = std::move(v); return *this; }
     IdnCompressorParamsBuilder& mode(int32_t v) { p_.mode = v; return *this; }
     IdnCompressorParamsBuilder& batch_blocks(uint32_t v) { p_.batch_blocks = v ? v : 1; return *this; }
     IdnCompressorParamsBuilder& lane_symbols(uint32_t v) { p_.lane_symbols = v; return *this; }
@@ -100,37 +107,61 @@ public:
     IdnCompressor(Sink sink, IdnCompressorParams params);  // IdnCompressor::with_params
     ~IdnCompressor();
     void add_sequence(FastqSequence seq);  // SequenceTooLong when len > max_block_total_len / 2 (idn/compressor.rs:542-544)
+    // the same for many sequences at once, given as one SoA batch (what a FASTQ parser produces); blocks form exactly as
+    // if add_sequence had been called per read.  name_off / names may be NULL (empty identifiers).
+    void add_batch(uint64_t n_reads, const uint64_t* read_off, const uint8_t* acids, const uint8_t* quals, const uint64_t* name_off,
+                   const uint8_t* names);
     void finish();                         // flushes, writes the empty terminator block; InvalidState if called twice
     const CompressionStats& stats() const { return stats_; }
     // the model identifiers written to the metadata (acid ids first), available after the first block was processed
     const std::vector<ModelIdentifier>& retained_models() const { return retained_; }
 
 private:
-    struct Batch;
+    struct Batch {  // SoA batch of whole blocks
+        std::vector<uint8_t> acids, quals, names;
+        std::vector<uint64_t> read_off{0}, name_off{0};
+        std::vector<uint32_t> block_first{0};
+        void clear() {
+            acids.clear();
+            quals.clear();
+            names.clear();
+            read_off.assign(1, 0);
+            name_off.assign(1, 0);
+            block_first.assign(1, 0);
+        }
+    };
+    struct Result {  // one compressed batch, ready to be written
+        std::unique_ptr<uint8_t[]> bytes;  // (not a vector: no zero fill of the capacity)
+        uint64_t out_bytes = 0, prefix_total = 0, payload_bytes = 0, acid_switches = 0, q_switches = 0, blocks = 0;
+    };
+    struct Worker {  // one device: its context, its uploaded models; one job at a time
+        DeviceModels dev;
+        std::mutex mu;
+    };
     void make_block();
-    void flush_batch();
+    void flush_batch();  // hands the batch under construction to the next device
+    void commit(bool all);  // writes finished batches in order (the reference's IdnBlockLock, idn/common.rs:10-57)
+    Result compress_batch(Worker& w, const Batch& b) const;
     void initialize();  // CompressorInitializer::initialize (idn/compressor_initializer.rs:33-74)
     std::vector<ModelIdentifier> best_models(ModelType type, size_t model_num, const std::vector<uint32_t>& sizes,
                                              const std::vector<size_t>& cols, size_t n_cols, size_t n_reads, class Clustering& clustering);
 
     Sink sink_;
     IdnCompressorParams params_;
-    DeviceModels dev_;
+    std::vector<std::unique_ptr<Worker>> workers_;  // one per entry of params_.devices
+    size_t next_worker_ = 0;
+    std::deque<std::future<Result>> pending_;       // batches in flight, in block order
     CompressionStats stats_;
     std::vector<ModelIdentifier> retained_;
     bool initialized_ = false, finished_ = false;
-    // SoA batch under construction
-    std::vector<uint8_t> acids_, quals_, names_;
-    std::vector<uint64_t> read_off_{0}, name_off_{0};
-    std::vector<uint32_t> block_first_{0};
+    Batch cur_;  // SoA batch under construction
     uint64_t cur_block_len_ = 0;
-    std::vector<uint8_t> out_;
 };
 
 struct IdnDecompressorParams {
     ModelProvider model_provider;
     uint32_t thread_num = 0;
-    int32_t device = 0;
+    std::vector<int32_t> devices{0};  // batches of `batch_blocks` blocks go round robin to these GPUs, results come back in order
     uint32_t batch_blocks = 32;
 };
 
@@ -142,14 +173,36 @@ public:
     std::optional<FastqSequence> next_sequence();  // None at the end of the file
     uint8_t version() const { return version_; }
 
+    // the decoded sequences of the next batch as one SoA batch instead of one FastqSequence at a time (what a FASTQ writer
+    // consumes); false at the end of the file.  Do not mix with next_sequence on one object.
+    struct DecodedBatch {
+        std::vector<uint8_t> acids, quals, names;
+        std::vector<uint64_t> read_off{0}, name_off{0};
+        bool any_names = false;
+    };
+    bool next_batch(DecodedBatch& out);
+
 private:
+    struct RawBatch {  // container bytes of some blocks, as read from the source
+        std::vector<uint8_t> buf;
+        std::vector<uint64_t> off;
+        std::vector<uint32_t> len, crc;
+    };
+    struct Worker {
+        DeviceModels dev;
+        std::mutex mu;
+    };
     void initialize();  // header + metadata (idn/decompressor.rs:304-374)
-    bool read_batch();  // false once the terminator block was seen
+    bool read_raw(RawBatch& rb);  // false once the terminator block was seen (and rb holds no block)
+    DecodedBatch decode_batch(Worker& w, const RawBatch& rb) const;
+    void prefetch();
     void read_exact(uint8_t* dst, size_t n, const char* what);
 
     Source source_;
     IdnDecompressorParams params_;
-    DeviceModels dev_;
+    std::vector<std::unique_ptr<Worker>> workers_;
+    size_t next_worker_ = 0;
+    std::deque<std::future<DecodedBatch>> pending_;
     bool initialized_ = false, eof_ = false;
     uint8_t version_ = 0;
     std::deque<FastqSequence> queue_;

@@ -203,6 +203,18 @@ struct ModelDev {
                                   // becomes ONE gather in the encoder and the scorer), or nullptr
 };
 
+// 8-byte read-only gather that does not allocate in L1: the per-spec acid tables (hundreds of KB, one random line per lane
+// per position) otherwise sweep L1 clean once per position and take the small position-local q-score tables with them
+__device__ __forceinline__ uint2 ldg_stream8(const uint2* p) {
+#ifdef IDN_ACID_NOALLOC
+    uint2 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p));
+    return v;
+#else
+    return __ldg(p);
+#endif
+}
+
 __device__ __forceinline__ uint32_t hash32(uint32_t k) {
     k ^= k >> 16;
     k *= 0x7feb352dU;

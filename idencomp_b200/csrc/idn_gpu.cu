@@ -81,8 +81,13 @@ constexpr uint64_t kDirectSpecLimit = 1ull << 19;  // acid decode rows stored pe
 
 }  // namespace
 
+struct idn_gpu_pipe;  // idn_pipeline.inc
+
 struct idn_gpu_ctx {
     int device = 0;
+    idn_gpu_pipe* pipe = nullptr;       // streams, events and double-buffered staging of the pipelined host-pointer calls
+    uint32_t pipe_blocks = 32;          // blocks per sub-chunk of a host-pointer call (idn_gpu_set_pipeline_blocks)
+    uint32_t* pipe_err_out = nullptr;   // where compress_blocks_dev leaves its error flags for the pipeline (device)
     cudaStream_t stream = nullptr;  // used by the host-pointer entry points
     cudaEvent_t ev = nullptr;
     std::string err;
@@ -352,6 +357,7 @@ extern "C" int32_t idn_gpu_create(int32_t device, idn_gpu_ctx** out) {
     if (n <= 0 || device < 0 || device >= n) return IDN_E_CUDA;  // no CPU fallback
     idn_gpu_ctx* ctx = new idn_gpu_ctx();
     ctx->device = device;
+    if (const char* pb = getenv("IDN_PIPE_BLOCKS")) ctx->pipe_blocks = std::max(1, atoi(pb));
     if (const char* w = getenv("IDN_WALK")) ctx->walk_mode = strcmp(w, "serial") == 0 ? 1 : (strcmp(w, "fast") == 0 ? 2 : 0);
     auto bail = [&](const char* what) {
         fprintf(stderr, "idn_gpu_create: %s failed: %s\n", what, cudaGetErrorString(cudaGetLastError()));
@@ -374,6 +380,8 @@ extern "C" int32_t idn_gpu_create(int32_t device, idn_gpu_ctx** out) {
     return IDN_OK;
 }
 
+static void pipe_destroy(idn_gpu_pipe* p);  // idn_pipeline.inc
+
 extern "C" void idn_gpu_destroy(idn_gpu_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
@@ -390,6 +398,7 @@ extern "C" void idn_gpu_destroy(idn_gpu_ctx* ctx) {
                       &ctx->s_nameoff, &ctx->s_out,     &ctx->s_blockoff, &ctx->s_crc,       &ctx->s_stats,  &ctx->s_sizes,
                       &ctx->s_blocks,  &ctx->s_blocklen, &ctx->s_aout,    &ctx->s_qout,    &ctx->s_offout,     &ctx->s_status, &ctx->s_idx};
     for (DevBuf* b : bufs) b->release();
+    pipe_destroy(ctx->pipe);
     cudaFree(ctx->d_models);
     cudaFree(ctx->d_crc_tab);
     cudaFree(ctx->d_xpow);
@@ -913,7 +922,7 @@ extern "C" int32_t idn_gpu_compress_blocks_dev(idn_gpu_ctx* ctx, const idn_batch
     rc = idn_gpu_block_crc_dev_impl(ctx, batch, block_crc, out, reinterpret_cast<unsigned long long*>(block_off), out_cap, st);
     if (rc) return rc;
     if (stats_dev) {
-        finish_stats_kernel<<<1, 32, 0, st>>>(dsp->stats, &dsp->err, reinterpret_cast<unsigned long long*>(stats_dev));
+        finish_stats_kernel<<<1, 32, 0, st>>>(dsp->stats, &dsp->err, reinterpret_cast<unsigned long long*>(stats_dev), ctx->pipe_err_out);
         LAUNCHED("finish_stats");
     }
     return IDN_OK;
@@ -1102,7 +1111,7 @@ static int32_t compress_native_dev(idn_gpu_ctx* ctx, const idn_batch* batch, Sma
     rc = idn_gpu_block_crc_dev_impl(ctx, batch, block_crc, out, boff, out_cap, st);
     if (rc) return rc;
     if (stats_dev) {
-        finish_stats_kernel<<<1, 32, 0, st>>>(dsp->stats, &dsp->err, reinterpret_cast<unsigned long long*>(stats_dev));
+        finish_stats_kernel<<<1, 32, 0, st>>>(dsp->stats, &dsp->err, reinterpret_cast<unsigned long long*>(stats_dev), ctx->pipe_err_out);
         LAUNCHED("finish_stats");
     }
     return IDN_OK;
@@ -1168,61 +1177,24 @@ static int32_t check_host_batch(idn_gpu_ctx* ctx, const idn_batch* b, bool need_
     return IDN_OK;
 }
 
+static int32_t compress_blocks_pipelined(idn_gpu_ctx* ctx, const idn_batch* b, int32_t mode, const idn_model_t* models,
+                                         uint32_t n_models, int32_t fast, const uint32_t* prefix_len, uint8_t* out, uint64_t out_cap,
+                                         uint64_t* block_off, uint32_t* block_crc, idn_compress_stats* stats);
+
 extern "C" int32_t idn_gpu_compress_blocks(idn_gpu_ctx* ctx, const idn_batch* b, int32_t mode, const idn_model_t* models,
                                            uint32_t n_models, int32_t fast, const uint32_t* prefix_len, uint8_t* out,
                                            uint64_t out_cap, uint64_t* block_off, uint32_t* block_crc,
                                            idn_compress_stats* stats) {
     if (!ctx) return IDN_E_INVALID_ARG;
-    HostTimer hv(ctx);
     int32_t rc = check_host_batch(ctx, b, true);
     if (rc) return rc;
-    hv.lap("host:c_validate");
-    if (!block_off) return fail(ctx, IDN_E_INVALID_ARG, "block_off is NULL");
+    rc = check_models(ctx, models, n_models);
+    if (rc) return rc;
+    if (!block_off || (!out && out_cap)) return fail(ctx, IDN_E_INVALID_ARG, "NULL argument");
+    if (mode != IDN_MODE_COMPAT && mode != IDN_MODE_NATIVE) return fail(ctx, IDN_E_UNSUPPORTED, "unknown mode %d", mode);
     CU(cudaSetDevice(ctx->device));
-    cudaStream_t st = ctx->stream;
-    HostTimer ht(ctx);
-    idn_batch d;
-    rc = stage_batch(ctx, b, &d, st);
-    if (rc) return rc;
-    ht.lap("host:c_stage_enqueue");
-    uint32_t* d_prefix = nullptr;
-    uint64_t prefix_total = 0;
-    if (prefix_len) {
-        for (uint32_t i = 0; i < b->n_blocks; i++) prefix_total += prefix_len[i];
-        CU(ctx->s_prefix.ensure((size_t)b->n_blocks * 4));
-        CU(cudaMemcpyAsync(ctx->s_prefix.p, prefix_len, (size_t)b->n_blocks * 4, cudaMemcpyHostToDevice, st));
-        d_prefix = ctx->s_prefix.as<uint32_t>();
-    }
-    uint64_t bound = idn_gpu_compress_bound(b->n_reads, b->n_symbols, b->n_blocks, prefix_total);
-    uint64_t dcap = out_cap < bound ? out_cap : bound;
-    CU(ctx->s_out.ensure(dcap + 16));
-    CU(ctx->s_blockoff.ensure(((size_t)b->n_blocks + 1) * 8));
-    CU(ctx->s_crc.ensure((size_t)b->n_blocks * 4));
-    CU(ctx->s_stats.ensure(sizeof(idn_compress_stats)));
-    rc = idn_gpu_compress_blocks_dev(ctx, &d, mode, models, n_models, fast, d_prefix, ctx->s_out.as<uint8_t>(), dcap,
-                                     ctx->s_blockoff.as<uint64_t>(), ctx->s_crc.as<uint32_t>(),
-                                     ctx->s_stats.as<idn_compress_stats>(), st);
-    if (rc) return rc;
-    idn_compress_stats hs;
-    uint32_t err = 0;
-    CU(cudaMemcpyAsync(&hs, ctx->s_stats.p, sizeof hs, cudaMemcpyDeviceToHost, st));
-    CU(cudaMemcpyAsync(&err, &ctx->w_small.as<SmallParams>()->err, 4, cudaMemcpyDeviceToHost, st));
-    ht.lap("host:c_kernels_enqueue");
-    CU(sync_stream(ctx, st));
-    ht.lap("host:c_wait_h2d_kernels");
-    if (stats) *stats = hs;
-    if (err & 1) return fail(ctx, IDN_E_INVALID_SYMBOL, "input holds an acid > 4 or a quality score > 93");
-    if (hs.required_bytes > out_cap) {
-        if (stats) stats->out_bytes = 0;
-        return fail(ctx, IDN_E_NOSPACE, "output needs %llu bytes, capacity is %llu", (unsigned long long)hs.required_bytes,
-                    (unsigned long long)out_cap);
-    }
-    if (hs.out_bytes) CU(cudaMemcpyAsync(out, ctx->s_out.p, hs.out_bytes, cudaMemcpyDeviceToHost, st));
-    CU(cudaMemcpyAsync(block_off, ctx->s_blockoff.p, ((size_t)b->n_blocks + 1) * 8, cudaMemcpyDeviceToHost, st));
-    if (block_crc) CU(cudaMemcpyAsync(block_crc, ctx->s_crc.p, (size_t)b->n_blocks * 4, cudaMemcpyDeviceToHost, st));
-    CU(sync_stream(ctx, st));
-    ht.lap("host:c_d2h");
-    return IDN_OK;
+    // sub-chunks of whole blocks flow through upload / kernels / download streams (idn_pipeline.inc)
+    return compress_blocks_pipelined(ctx, b, mode, models, n_models, fast, prefix_len, out, out_cap, block_off, block_crc, stats);
 }
 
 extern "C" int32_t idn_gpu_block_crc(idn_gpu_ctx* ctx, const idn_batch* b, uint32_t* block_crc) {
@@ -1592,6 +1564,15 @@ extern "C" int32_t idn_gpu_index_blocks(idn_gpu_ctx* ctx, const uint8_t* blocks,
     return IDN_OK;
 }
 
+#include "idn_pipeline.inc"
+
+extern "C" int32_t idn_gpu_set_pipeline_blocks(idn_gpu_ctx* ctx, uint32_t blocks) {
+    if (!ctx) return IDN_E_INVALID_ARG;
+    if (blocks == 0) return fail(ctx, IDN_E_INVALID_ARG, "blocks per sub-chunk must be positive");
+    ctx->pipe_blocks = blocks;
+    return IDN_OK;
+}
+
 extern "C" int32_t idn_gpu_decompress_blocks(idn_gpu_ctx* ctx, const uint8_t* blocks, const uint64_t* block_off,
                                              const uint32_t* block_len, const uint32_t* block_crc, uint32_t n_blocks, int32_t mode,
                                              const idn_model_t* models, uint32_t n_models, const uint8_t* names,
@@ -1609,6 +1590,17 @@ extern "C" int32_t idn_gpu_decompress_blocks(idn_gpu_ctx* ctx, const uint8_t* bl
     if (!blocks && nbytes) return fail(ctx, IDN_E_INVALID_ARG, "blocks is NULL");
     CU(cudaSetDevice(ctx->device));
     cudaStream_t st = ctx->stream;
+    if (!names && n_blocks) {
+        // no names on the device (the block CRCs cover the symbols only): sub-chunks of whole blocks flow through upload /
+        // kernels / download streams; a sub-chunk that outgrows its share of the staging sends the call down the path below
+        int32_t rcm = check_models(ctx, models, n_models);
+        if (rcm) return rcm;
+        if (mode != IDN_MODE_COMPAT && mode != IDN_MODE_NATIVE) return fail(ctx, IDN_E_UNSUPPORTED, "unknown mode %d", mode);
+        bool retry_simple = false;
+        int32_t rcp = decompress_blocks_pipelined(ctx, blocks, block_off, block_len, block_crc, n_blocks, mode, models, n_models, acids_out,
+                                                  quals_out, read_off_out, out_reads_cap, out_symbols_cap, bad_block, &retry_simple);
+        if (rcp || !retry_simple) return rcp;
+    }
     CU(ctx->s_blocks.ensure(nbytes + 16));
     CU(ctx->s_blockoff.ensure(((size_t)n_blocks + 1) * 8));
     CU(ctx->s_crc.ensure(((size_t)n_blocks + 1) * 4));

@@ -499,7 +499,7 @@ __device__ __forceinline__ void encode_read_body(const ModelDev& ma, const Model
     rows_next(row_a, row_q);  // generators at len-1, entry 0 = symbol len-1
     uint2 ea = make_uint2(0, 0), eq = make_uint2(0, 0);
     if (len) {
-        ea = __ldg(enc_a + (row_a * kAcidSyms + (raw_a & 7u)));
+        ea = ldg_stream8(enc_a + (row_a * kAcidSyms + (raw_a & 7u)));
         eq = __ldg(mq.enc + (row_q * kQSyms + ((uint32_t)raw_q & 127u)));
     }
     rows_next(row_a, row_q);  // generators at len-2
@@ -508,7 +508,7 @@ __device__ __forceinline__ void encode_read_body(const ModelDev& ma, const Model
         // entries of position i-1 (generators stand at i-1: entry 0), gathered while position i is coded
         uint2 ea_n = make_uint2(0, 0), eq_n = make_uint2(0, 0);
         if (i >= 1) {
-            ea_n = __ldg(enc_a + (row_a * kAcidSyms + (raw_a & 7u)));
+            ea_n = ldg_stream8(enc_a + (row_a * kAcidSyms + (raw_a & 7u)));
             eq_n = __ldg(mq.enc + (row_q * kQSyms + ((uint32_t)raw_q & 127u)));
         }
         rows_next(row_a, row_q);  // generators to i-2
@@ -802,14 +802,17 @@ stats_kernel(const uint32_t* __restrict__ pay_len, const uint8_t* __restrict__ s
 // stats[0] = bytes the container needs, [1] acid switches, [2] q switches, [3] payload bytes
 // -> idn_compress_stats {out_bytes, acid_switches, q_switches, payload_bytes, required_bytes}
 __global__ void finish_stats_kernel(const unsigned long long* __restrict__ stats, const uint32_t* __restrict__ err,
-                                    unsigned long long* __restrict__ out) {
+                                    unsigned long long* __restrict__ out, uint32_t* __restrict__ err_out) {
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
     out[0] = stats[0];
     out[1] = stats[1];
     out[2] = stats[2];
     out[3] = stats[3];
     out[4] = stats[0];
-    (void)err;
+    if (err_out) {  // the pipelined host-pointer path reads the flags next to the stats (a u64 slot)
+        err_out[0] = *err;
+        err_out[1] = 0;
+    }
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -1830,7 +1833,7 @@ __device__ __forceinline__ void decode_read_body(const ModelDev& ma, const Model
     auto step = [&](uint32_t& va, uint32_t& vq) {
         D.refill();
         uint2 pk;  // cum[1..4] of the acid context
-        if (P::kStatic || ma.adirect) pk = __ldg(ma.adirect + ga.index(sa, pf.pos, psa));
+        if (P::kStatic || ma.adirect) pk = ldg_stream8(ma.adirect + ga.index(sa, pf.pos, psa));
         else pk = __ldg(reinterpret_cast<const uint2*>(ma.dec) + gen_row(ma, sa, ga, pf.pos, psa));
 #if defined(IDN_ABL_ROW1)
         const uint32_t row_q = 1;

@@ -33,7 +33,7 @@ class Params(C.Structure):
     """idn_host_params = IdnCompressorParamsBuilder (idn/compressor.rs:164-274) + device / mode / batching."""
     _fields_ = [("max_block_total_len", C.c_uint32), ("thread_num", C.c_uint32), ("include_identifiers", C.c_int32),
                 ("quality", C.c_uint32), ("fast", C.c_int32), ("device", C.c_int32), ("mode", C.c_int32),
-                ("batch_blocks", C.c_uint32), ("lane_symbols", C.c_uint32)]
+                ("batch_blocks", C.c_uint32), ("lane_symbols", C.c_uint32), ("n_devices", C.c_uint32), ("devices", C.c_int32 * 16)]
 
 _LIB = None
 
@@ -214,12 +214,16 @@ class IdnCompressor:
     """
 
     def __init__(self, models, *, max_block_total_len=4 * 1024 * 1024, thread_num=0, include_identifiers=True, quality=7,
-                 fast=False, device=0, mode=capi.MODE_COMPAT, batch_blocks=32, lane_symbols=2048):
+                 fast=False, device=0, devices=None, mode=capi.MODE_COMPAT, batch_blocks=32, lane_symbols=2048):
         self.L = load()
         p = Params()
         self.L.idn_host_params_default(C.byref(p))
         p.max_block_total_len, p.thread_num, p.include_identifiers = max_block_total_len, thread_num, int(include_identifiers)
         p.quality, p.fast, p.device, p.mode, p.batch_blocks, p.lane_symbols = quality, int(fast), device, mode, batch_blocks, lane_symbols
+        if devices:  # several GPUs share the file: same container, whatever their number
+            p.n_devices = len(devices)
+            for i, d in enumerate(devices):
+                p.devices[i] = d
         self._models = list(models)
         h = C.c_void_p()
         _check(self.L.idn_host_compressor_new(_model_array(self._models), len(self._models), C.byref(p), C.byref(h)))
@@ -281,8 +285,11 @@ class IdnCompressor:
             pass
 
 
-def decompress(models, idn: bytes, *, device=0, batch_blocks=32) -> dict:
-    """idencomp::IdnDecompressor (idn/decompressor.rs:455-566): every sequence of the file as one SoA batch."""
+def decompress(models, idn: bytes, *, device=0, n_devices=0, batch_blocks=32) -> dict:
+    """idencomp::IdnDecompressor (idn/decompressor.rs:455-566): every sequence of the file as one SoA batch.
+    n_devices > 1: the first n_devices GPUs share the file."""
+    if n_devices > 1:
+        device = -n_devices
     L = load()
     buf = np.frombuffer(idn, dtype=np.uint8)
     h = C.c_void_p()

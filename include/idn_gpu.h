@@ -76,6 +76,10 @@ int32_t idn_gpu_set_lane_symbols(idn_gpu_ctx *ctx, uint32_t lane_syms);
  * parallel walk first.  Results do not depend on the setting; the environment variable IDN_WALK=serial|fast sets the
  * default of new contexts. */
 int32_t idn_gpu_set_walk(idn_gpu_ctx *ctx, int32_t mode);
+/* the host-pointer entry points idn_gpu_compress_blocks / idn_gpu_decompress_blocks cut a call into sub-chunks of this many
+ * blocks (default 32; environment variable IDN_PIPE_BLOCKS) and overlap the upload of one sub-chunk with the kernels of the
+ * one before and the download of the one before that, on three streams of this ctx.  Results do not depend on the setting. */
+int32_t idn_gpu_set_pipeline_blocks(idn_gpu_ctx *ctx, uint32_t blocks);
 /* number of kernel launches this ctx has issued since creation (bench.py's gpu_launches) */
 uint64_t idn_gpu_launch_count(const idn_gpu_ctx *ctx);
 /* which codec kernel instantiation a call with exactly this (acid, q-score) model pair launches: the index of the

@@ -57,10 +57,13 @@ typedef struct {                    /* IdnCompressorParamsBuilder, idn/compresso
     int32_t include_identifiers;    /* default 1 */
     uint32_t quality;               /* 1..9, default 7 */
     int32_t fast;                   /* default 0; sets quality 1 */
-    int32_t device;                 /* CUDA device, default 0 */
+    int32_t device;                 /* CUDA device, default 0 (used when n_devices == 0) */
     int32_t mode;                   /* IDN_MODE_COMPAT (container version 1) or IDN_MODE_NATIVE (version 2) */
     uint32_t batch_blocks;          /* blocks per device call, default 32 */
     uint32_t lane_symbols;          /* native mode lane quantum, default 2048 */
+    uint32_t n_devices;             /* > 0: the GPUs that share the file (batches go round robin, results are committed in block
+                                       order; the container does not depend on the device count) */
+    int32_t devices[16];
 } idn_host_params;
 void idn_host_params_default(idn_host_params *p);
 /* IdnCompressor::with_params over an in-memory writer; `models` is the ModelProvider (order = provider order) */
@@ -85,6 +88,7 @@ void idn_host_compressor_free(idn_host_compressor *c);
 
 /* ---- IdnDecompressor (idn/decompressor.rs:455-566): next_sequence until None, results as one SoA batch ---- */
 typedef struct idn_host_decoded idn_host_decoded;
+/* `device` >= 0: that GPU; < 0: the first (-device) GPUs share the file */
 int32_t idn_host_decompress(const idn_host_model *const *models, uint32_t n_models, int32_t device, uint32_t batch_blocks,
                             const uint8_t *idn, uint64_t idn_len, idn_host_decoded **out);
 uint64_t idn_host_decoded_reads(const idn_host_decoded *d);

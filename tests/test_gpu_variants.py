@@ -97,7 +97,7 @@ def test_model_pair_vs_oracle(gctx, O, models, pair, mode):
     an, qn, (lo, hi), variant = PAIRS[pair]
     (am, ha), (qm, hq) = models(an), models(qn)
     assert gctx.kernel_variant(ha, hq) == variant, "the pair does not launch the kernel variant this test is meant to cover"
-    ro = lengths(lo, hi, 4.8 * BLOCK, seed=len(pair))
+    ro = lengths(lo, hi, max(4.8 * BLOCK, 201_000 * (lo + hi) // 2 if hi < 1000 else 0), seed=len(pair))
     acids, quals = synth_on_device(gctx, ha, hq, ro, seed=20240601 + len(pair))
     reads = O.Reads(ro, acids, quals, None, None)
     bf = blocks_of(reads, BLOCK)
