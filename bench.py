@@ -544,7 +544,8 @@ def e2e_record(env, rec):
         return None
     world, fq = env.world, rec["fq"]
     return {"value": 2 * fq * e2e["steps"] * world / e2e["_t"] / 1e9, "unit": "GB/s", "h2d_bytes_per_step": e2e["h2d"],
-            "d2h_bytes_per_step": e2e["d2h"], "steps": e2e["steps"], "threads": e2e["threads"], "chunk_blocks": e2e["chunk_blocks"],
+            "d2h_bytes_per_step": e2e["d2h"], "steps": e2e["steps"], "host_threads": e2e["threads"], "blocks_per_call": e2e["chunk_blocks"],
+            "pipeline_blocks": e2e["pipe_blocks"],
             "compress_GBps": e2e["cGBps"] * world, "decompress_GBps": e2e["dGBps"] * world,
             "per_direction_note": "rank 0's own phase times x n_gpus", "sample": e2e["sample"]}
 
@@ -697,38 +698,40 @@ def run_e2e(args, w, env, model_names, chunks, acids_d, quals_d, read_off_h, blo
     torch, capi, host, local, dist = env.torch, env.capi, env.host, env.local, env.dist
     S = int(read_off_h[-1])
     total_out = sum(sizes.values())
-    # the host-pointer calls are synchronous: overlap of H2D, kernels and D2H comes from several ctx in flight, so the
-    # e2e leg uses smaller chunks than the device-resident leg (a short pipeline fill and tail)
+    # A host-pointer call pipelines itself (csrc/idn_pipeline.inc: sub-chunks of blocks on an upload, a compute and a download
+    # stream), so ONE context on ONE host thread gets a whole direction in one call; --e2e-threads / --e2e-chunk-blocks
+    # reproduce round 1's several-contexts-in-flight arrangement for comparison.
     n_blocks_all = len(block_first_h) - 1
-    # a call should carry enough reads to fill the GPU (one thread per read: ~170 k in flight); blocks of long reads
-    # hold a few hundred reads each, so those workloads get more blocks per call, down to 3 calls per workload
     reads_per_block = max(1, (len(read_off_h) - 1) // max(n_blocks_all, 1))
+    # a sub-chunk should carry enough reads to fill the GPU (one thread per read: ~150 k in flight): blocks of long reads
+    # hold a few hundred reads each, so those workloads pipeline in larger sub-chunks
+    pipe_blocks = args.e2e_pipe_blocks or max(32, min(256, -(-E2E_READS_PER_CALL // reads_per_block)))
+    # pinned inputs, pinned container, pinned decoded output: 4 * S + 2 * container bytes of page-locked host memory.  Budget
+    # of this rank: half of what is available, shared by the ranks of the box (or the caller's limit); a workload that
+    # needs more is sampled from its front and the rate scaled
+    need = 4 * S + total_out * 2
+    budget = 0.5 * psutil.virtual_memory().available / max(1, int(os.environ.get("LOCAL_WORLD_SIZE", os.environ.get("WORLD_SIZE", "1"))))
+    if budget_bytes:
+        budget = min(budget, budget_bytes)
+    use_blocks = n_blocks_all
+    if need > budget:
+        use_blocks = max(min(n_blocks_all, 4 * pipe_blocks), int(n_blocks_all * budget / need))
     chunk_blocks = args.e2e_chunk_blocks
-    if chunk_blocks <= 0:  # automatic
-        want = max(32, -(-E2E_READS_PER_CALL // reads_per_block))
-        chunk_blocks = max(1, min(want, max(32, -(-n_blocks_all // 3))))
+    if chunk_blocks <= 0:  # automatic: all blocks of a thread in one call
+        chunk_blocks = max(1, -(-use_blocks // max(1, args.e2e_threads)))
     e2e_chunks = []
-    for b0 in range(0, n_blocks_all, chunk_blocks):
+    for b0 in range(0, use_blocks, chunk_blocks):
         c = Chunk()
-        c.b0, c.b1 = b0, min(n_blocks_all, b0 + chunk_blocks)
+        c.b0, c.b1 = b0, min(use_blocks, b0 + chunk_blocks)
         c.r0, c.r1 = int(block_first_h[c.b0]), int(block_first_h[c.b1])
         c.s0, c.s1 = int(read_off_h[c.r0]), int(read_off_h[c.r1])
         c.n_reads, c.n_syms, c.n_blocks = c.r1 - c.r0, c.s1 - c.s0, c.b1 - c.b0
         e2e_chunks.append(c)
     per_sym = total_out / max(S, 1)
-    sizes = {id(c): int(per_sym * c.n_syms * 1.15) + 64 * c.n_blocks + 4096 for c in e2e_chunks}  # container capacity per chunk
+    sizes = {id(c): int(per_sym * c.n_syms * 1.15) + 64 * c.n_blocks + 4096 for c in e2e_chunks}  # container capacity per call
     chunks = e2e_chunks
     n_threads = max(1, min(args.e2e_threads, len(chunks)))
-    # pinned inputs, pinned container, pinned decoded output
     use = chunks
-    need = 4 * S + total_out * 2
-    # pinned host memory budget of this rank: half of what is available, shared by the ranks of the box
-    budget = 0.5 * psutil.virtual_memory().available / max(1, int(os.environ.get("LOCAL_WORLD_SIZE", os.environ.get("WORLD_SIZE", "1"))))
-    if budget_bytes:
-        budget = min(budget, budget_bytes)
-    if need > budget:
-        keep = max(min(len(chunks), 2 * n_threads), int(len(chunks) * budget / need))
-        use = chunks[:keep]
     s_end = use[-1].s1
     r_end = use[-1].r1
     acids_h = torch.empty(s_end, dtype=torch.uint8, pin_memory=True)
@@ -746,6 +749,7 @@ def run_e2e(args, w, env, model_names, chunks, acids_d, quals_d, read_off_h, blo
     ctxs = []
     for _ in range(n_threads):
         cx = capi.Context(local)
+        cx.set_pipeline_blocks(pipe_blocks)
         ctxs.append((cx, np.asarray([host.Model.load(MODELS / (st + ".msgpack")).upload(cx) for st in model_names], dtype=np.int32)))
     n_models = len(model_names)
 
@@ -847,8 +851,10 @@ def run_e2e(args, w, env, model_names, chunks, acids_d, quals_d, read_off_h, blo
     h2d = 2 * s_end + 8 * (r_end + len(use)) + cbytes
     d2h = cbytes + 2 * s_end + 8 * (r_end + len(use))
     return {"_t": t_all / frac, "steps": steps, "h2d": int(h2d / frac), "d2h": int(d2h / frac), "threads": n_threads, "chunk_blocks": chunk_blocks,
+            "pipe_blocks": pipe_blocks,
             "cGBps": fq * steps / tc / 1e9, "dGBps": fq * steps / td / 1e9,
-            "sample": "whole workload" if use is chunks else f"first {len(use)} of {len(chunks)} chunks ({fq / 1e9:.1f} GB of FASTQ; pinned host memory budget), scaled"}
+            "sample": "whole workload" if use_blocks == n_blocks_all else
+                      f"first {use_blocks} of {n_blocks_all} blocks ({fq / 1e9:.1f} GB of FASTQ; pinned host memory budget), scaled"}
 
 
 def main():
@@ -875,9 +881,9 @@ def main():
     ap.add_argument("--mode", default="", choices=["", "compat", "native"], help="container format (default: the workload's)")
     ap.add_argument("--no-other-mode", action="store_true", help="skip the short run of the other container format")
     ap.add_argument("--lane-symbols", type=int, default=0, help="native mode lane quantum (default: the library's 2048)")
-    ap.add_argument("--e2e-threads", type=int, default=3)
-    ap.add_argument("--e2e-chunk-blocks", type=int, default=0,
-                    help="blocks per host-pointer call in the e2e leg (default: 32, more for long reads so that a call holds ~E2E_READS_PER_CALL reads)")
+    ap.add_argument("--e2e-threads", type=int, default=1, help="host threads (one ctx each) of the e2e leg")
+    ap.add_argument("--e2e-chunk-blocks", type=int, default=0, help="blocks per host-pointer call in the e2e leg (default: all of a thread's blocks in one call)")
+    ap.add_argument("--e2e-pipe-blocks", type=int, default=0, help="blocks per sub-chunk of the pipeline inside a call (default: 32, more for long reads)")
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--e2e-profile", action="store_true", help="print the host-side phase times of the e2e leg to stderr")
     args = ap.parse_args()

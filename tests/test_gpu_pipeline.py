@@ -37,8 +37,13 @@ def test_sub_chunking_changes_nothing(gctx, O, toy_models, toy_handles, reads_1k
     gctx.set_pipeline_blocks(sub)
     try:
         got = gctx.compress_blocks(reads_1k.read_off, reads_1k.acids, reads_1k.quals, bf, toy_handles, **kw)
-        assert np.array_equal(got[0], want[0]) and np.array_equal(got[1], want[1]) and np.array_equal(got[2], want[2])
-        assert got[3] == want[3]
+        assert np.array_equal(got[1], want[1]) and np.array_equal(got[2], want[2]) and got[3] == want[3]
+        a, b = got[0].copy(), want[0].copy()
+        for k in range(nb):  # the reserved bytes behind each block header are the host's to fill (identifiers slice)
+            lo = int(want[1][k]) + 8
+            a[lo:lo + int(prefix[k])] = 0
+            b[lo:lo + int(prefix[k])] = 0
+        assert np.array_equal(a, b)
         # decode without names on the device: compress again without them (the CRC then covers the symbols only)
         out, boff, crc, _ = gctx.compress_blocks(reads_1k.read_off, reads_1k.acids, reads_1k.quals, bf, toy_handles, mode=mode)
         doff = np.append(boff[:-1] + 8, boff[-1]).astype(np.uint64)
