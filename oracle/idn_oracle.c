@@ -1297,27 +1297,62 @@ static uint32_t get_u32be(const uint8_t *p) {
     return (uint32_t)p[0] << 24 | (uint32_t)p[1] << 16 | (uint32_t)p[2] << 8 | p[3];
 }
 
-/* one lane: reads [r0, r1) pushed last -> first onto one 2-state stream; returns the payload length */
-static size_t native_encode_lane(const orc_model_t *am, const orc_model_t *qm, const orc_reads_t *in, uint64_t r0,
-                                 uint64_t r1, uint8_t *tmp, size_t cap, uint8_t **start_out) {
+/* Lane partition of a block (normative text: idencomp_b200/csrc/idn_native.cuh).
+ *   pieces: a read of length L is ONE piece, unless lane_syms >= 256 and L > lane_syms: then it is cut into
+ *           ceil(L / lane_syms) pieces of lane_syms symbols (the last one shorter);
+ *   lanes:  with o_p the block-relative offset of the first symbol of piece p, a new lane starts at the first piece of the
+ *           block and at every piece with o_p / lane_syms != o_(p-1) / lane_syms.
+ * A lane is therefore a contiguous range of the block's symbol stream; empty reads carry no symbols and do not matter.
+ * Returns the lane start offsets (block-relative) in lane_sym[0 .. n_lanes], lane_sym[n_lanes] = block symbols. */
+#define NATIVE_MIN_SPLIT_Q 256u
+#define NATIVE_HIST 8u
+static uint64_t native_lanes(const uint32_t *lens, uint64_t n_reads, uint32_t Q, uint64_t *lane_sym, int *split_out) {
+    uint64_t n_lanes = 0, off = 0, prev_q = 0;
+    int first = 1, split = 0;
+    for (uint64_t i = 0; i < n_reads; i++) {
+        const uint32_t len = lens[i];
+        const uint64_t pc = (Q >= NATIVE_MIN_SPLIT_Q && len > Q) ? ((uint64_t)len + Q - 1) / Q : 1;
+        if (pc > 1) split = 1;
+        for (uint64_t j = 0; j < pc; j++) {
+            const uint64_t o = off + j * Q;
+            if (first || o / Q != prev_q) lane_sym[n_lanes++] = o;
+            first = 0;
+            prev_q = o / Q;
+        }
+        off += len;
+    }
+    lane_sym[n_lanes] = off;
+    if (split_out) *split_out = split;
+    return n_lanes;
+}
+
+/* one lane = the symbols [a, b) of the block's stream, pushed last -> first onto one 2-state stream: every read is walked
+ * by its generators from its first position (the contexts of a piece that starts inside a read are the true ones);
+ * returns the payload length */
+static size_t native_encode_lane(const orc_model_t *am, const orc_model_t *qm, const orc_reads_t *in, uint64_t first_read,
+                                 uint64_t n_reads, uint64_t a, uint64_t b, uint8_t *tmp, size_t cap, uint8_t **start_out) {
     uint32_t s0 = RANS_L, s1 = RANS_L;
     uint8_t *ptr = tmp + cap;
-    for (uint64_t r = r1; r-- > r0;) {
+    const uint64_t base = in->read_off[first_read];
+    for (uint64_t r = first_read + n_reads; r-- > first_read;) {
+        const uint64_t ro = in->read_off[r] - base, re = in->read_off[r + 1] - base;
+        if (ro >= b || re <= a) continue;
+        const uint32_t len = (uint32_t)(re - ro);
+        const uint32_t p0 = (uint32_t)((a > ro ? a : ro) - ro), p1 = (uint32_t)((b < re ? b : re) - ro);
         const uint8_t *ac = in->acids + in->read_off[r];
         const uint8_t *qu = in->quals + in->read_off[r];
-        uint32_t len = (uint32_t)(in->read_off[r + 1] - in->read_off[r]);
-        uint32_t *ctx_a = (uint32_t *)malloc(((size_t)len + 1) * 2 * sizeof(uint32_t));
-        uint32_t *ctx_q = ctx_a + len + 1;
+        uint32_t *ctx_a = (uint32_t *)malloc(((size_t)p1 + 1) * 2 * sizeof(uint32_t));
+        uint32_t *ctx_q = ctx_a + p1 + 1;
         orc_gen_t ga, gq;
         orc_gen_init(&ga, &am->spec, len);
         orc_gen_init(&gq, &qm->spec, len);
-        for (uint32_t i = 0; i < len; i++) {
+        for (uint32_t i = 0; i < p1; i++) {
             ctx_a[i] = ctx_for(am, orc_gen_current(&ga));
             ctx_q[i] = ctx_for(qm, orc_gen_current(&gq));
             orc_gen_update(&ga, ac[i], qu[i]);
             orc_gen_update(&gq, ac[i], qu[i]);
         }
-        for (uint32_t i = len; i-- > 0;) {
+        for (uint32_t i = p1; i-- > p0;) {
             enc_put(&s0, &ptr, &am->enc[(size_t)ctx_a[i] * ORC_ACID_SYMS + ac[i]]);
             enc_put(&s1, &ptr, &qm->enc[(size_t)ctx_q[i] * ORC_Q_SYMS + qu[i]]);
         }
@@ -1360,34 +1395,45 @@ int orc_compress_native_block(const orc_params_t *p, const orc_reads_t *in, uint
     for (uint32_t k = 0; k < p->n_models; k++) cand[p->models[k]->type][n_cand[p->models[k]->type]++] = (int)k;
     if (!n_cand[0] || !n_cand[1]) return fail(ORC_E_INVALID_STATE, "need at least one model per type");
     /* lane partition */
-    uint64_t base = in->read_off[first_read];
-    uint64_t *lane_first = (uint64_t *)malloc(sizeof(uint64_t) * (n_reads + 1));
-    uint64_t n_lanes = 0;
+    const uint64_t base = in->read_off[first_read];
+    const uint64_t n_syms = in->read_off[first_read + n_reads] - base;
+    uint32_t *lens = (uint32_t *)malloc(sizeof(uint32_t) * (n_reads + 1));
     uint32_t mn = 0xffffffffu, mx = 0;
     for (uint64_t i = 0; i < n_reads; i++) {
-        uint64_t r = first_read + i;
-        uint32_t len = (uint32_t)(in->read_off[r + 1] - in->read_off[r]);
-        if (len < mn) mn = len;
-        if (len > mx) mx = len;
-        if (i == 0 || (in->read_off[r] - base) / lane_syms != (in->read_off[r - 1] - base) / lane_syms) lane_first[n_lanes++] = r;
+        lens[i] = (uint32_t)(in->read_off[first_read + i + 1] - in->read_off[first_read + i]);
+        if (lens[i] < mn) mn = lens[i];
+        if (lens[i] > mx) mx = lens[i];
     }
-    lane_first[n_lanes] = first_read + n_reads;
+    uint64_t *lane_sym = (uint64_t *)malloc(sizeof(uint64_t) * (n_reads + n_syms / lane_syms + 2));
+    int split = 0;
+    const uint64_t n_lanes = native_lanes(lens, n_reads, lane_syms, lane_sym, &split);
     uint32_t width = mn == mx ? 0u : (mx < 65536u ? 2u : 4u);
     /* per-lane model choice and payloads */
     uint8_t *mdl = (uint8_t *)malloc(2 * n_lanes + 2);
     uint32_t *llen = (uint32_t *)malloc(sizeof(uint32_t) * (n_lanes + 1));
+    uint64_t *score = NULL;
+    if ((n_cand[0] > 1 || n_cand[1] > 1) && !p->fast) { /* forward scores of every read under every model, computed once */
+        score = (uint64_t *)malloc(sizeof(uint64_t) * n_reads * p->n_models);
+        for (uint64_t i = 0; i < n_reads; i++)
+            for (uint32_t k = 0; k < p->n_models; k++)
+                score[i * p->n_models + k] = orc_score_read(p->models[k], in->acids + in->read_off[first_read + i],
+                                                            in->quals + in->read_off[first_read + i], lens[i]);
+    }
     orc_buf_t pay = {0};
+    uint64_t r_lo = 0; /* first read with a symbol at or behind the start of the current lane */
     for (uint64_t l = 0; l < n_lanes; l++) {
+        const uint64_t a = lane_sym[l], b = lane_sym[l + 1];
+        while (r_lo < n_reads && in->read_off[first_read + r_lo + 1] - base <= a) r_lo++;
         int pick[2];
         for (int type = 0; type < 2; type++) {
             pick[type] = cand[type][0];
             if (n_cand[type] > 1 && !p->fast) {
+                /* argmin over the candidates of the summed forward scores of the reads with at least one symbol in the lane */
                 uint64_t best = ~0ull;
                 for (int k = 0; k < n_cand[type]; k++) {
                     uint64_t sum = 0;
-                    for (uint64_t r = lane_first[l]; r < lane_first[l + 1]; r++)
-                        sum += orc_score_read(p->models[cand[type][k]], in->acids + in->read_off[r], in->quals + in->read_off[r],
-                                              (uint32_t)(in->read_off[r + 1] - in->read_off[r]));
+                    for (uint64_t i = r_lo; i < n_reads && in->read_off[first_read + i] - base < b; i++)
+                        if (in->read_off[first_read + i + 1] - base > a) sum += score[i * p->n_models + cand[type][k]];
                     if (sum < best) { /* first minimum wins */
                         best = sum;
                         pick[type] = cand[type][k];
@@ -1397,10 +1443,25 @@ int orc_compress_native_block(const orc_params_t *p, const orc_reads_t *in, uint
         }
         mdl[2 * l] = (uint8_t)pick[0];
         mdl[2 * l + 1] = (uint8_t)pick[1];
-        size_t cap = 4 * (size_t)(in->read_off[lane_first[l + 1]] - in->read_off[lane_first[l]]) + 8;
+        /* a lane that starts inside a read carries the (acid, quality score) pairs of the NATIVE_HIST positions in front of it
+         * (zeros before the start of the read): the decoder rebuilds the generator states from them */
+        const uint64_t rr = r_lo;
+        const int mid = rr < n_reads && in->read_off[first_read + rr] - base < a && b > a;
+        size_t cap = 4 * (size_t)(b - a) + 8;
         uint8_t *tmp = (uint8_t *)malloc(cap), *start;
-        size_t n = native_encode_lane(p->models[pick[0]], p->models[pick[1]], in, lane_first[l], lane_first[l + 1], tmp, cap, &start);
-        llen[l] = (uint32_t)n;
+        size_t n = native_encode_lane(p->models[pick[0]], p->models[pick[1]], in, first_read, n_reads, a, b, tmp, cap, &start);
+        if (mid) {
+            uint8_t hist[2 * NATIVE_HIST];
+            const uint64_t ro = in->read_off[first_read + rr] - base;
+            for (uint32_t k = 0; k < NATIVE_HIST; k++) {
+                const uint64_t pos = a - NATIVE_HIST + k; /* block-relative */
+                const int inside = a >= NATIVE_HIST - k + ro && pos >= ro;
+                hist[k] = inside ? in->acids[base + pos] : 0;
+                hist[NATIVE_HIST + k] = inside ? in->quals[base + pos] : 0;
+            }
+            buf_put(&pay, hist, sizeof hist);
+        }
+        llen[l] = (uint32_t)(n + (mid ? 2 * NATIVE_HIST : 0));
         buf_put(&pay, start, n);
         free(tmp);
     }
@@ -1417,7 +1478,7 @@ int orc_compress_native_block(const orc_params_t *p, const orc_reads_t *in, uint
     buf_u32be(out, (uint32_t)n_reads);
     buf_u32be(out, (uint32_t)n_lanes);
     buf_u32be(out, lane_syms);
-    buf_u8(out, (uint8_t)width);
+    buf_u8(out, (uint8_t)(width | (split ? 0x80u : 0u)));
     buf_u32be(out, width == 0 ? mn : 0);
     for (uint64_t r = first_read; r < first_read + n_reads && width; r++) {
         uint32_t len = (uint32_t)(in->read_off[r + 1] - in->read_off[r]);
@@ -1434,7 +1495,9 @@ int orc_compress_native_block(const orc_params_t *p, const orc_reads_t *in, uint
     orc_buf_free(&pay);
     free(mdl);
     free(llen);
-    free(lane_first);
+    free(lane_sym);
+    free(lens);
+    free(score);
     *crc_out = crc;
     return ORC_OK;
 }
@@ -1453,7 +1516,7 @@ int orc_native_block_counts(const uint8_t *data, size_t n, uint64_t *n_reads, ui
             pos += 6 + len;
         } else if (data[pos] == 3) {
             if (pos + NATIVE_HDR_FIXED > n) return fail(ORC_E_SERIALIZE, "truncated native slice");
-            uint32_t body = get_u32be(data + pos + 1), nr = get_u32be(data + pos + 5), w = data[pos + 17];
+            uint32_t body = get_u32be(data + pos + 1), nr = get_u32be(data + pos + 5), w = data[pos + 17] & 0x7fu;
             if (body > n - pos - 5) return fail(ORC_E_SERIALIZE, "truncated native slice");
             *n_reads += nr;
             if (w == 0) {
@@ -1484,42 +1547,65 @@ int orc_decompress_native_block(const orc_model_t *const *models, uint32_t n_mod
         }
         if (data[pos] != 3) return fail(ORC_E_SERIALIZE, "unexpected slice kind");
         uint32_t body = get_u32be(data + pos + 1), nr = get_u32be(data + pos + 5), nl = get_u32be(data + pos + 9);
-        uint32_t Q = get_u32be(data + pos + 13), w = data[pos + 17], cl = get_u32be(data + pos + 18);
+        uint32_t Q = get_u32be(data + pos + 13), w = data[pos + 17] & 0x7fu, cl = get_u32be(data + pos + 18);
+        const int split_flag = data[pos + 17] >> 7;
         const uint8_t *t_len = data + pos + NATIVE_HDR_FIXED;
         const uint8_t *t_mdl = t_len + (size_t)nr * w;
         const uint8_t *t_ll = t_mdl + 2 * (size_t)nl;
         const uint8_t *pay = t_ll + 4 * (size_t)nl;
         if (Q == 0 || (size_t)(pay - (data + pos + 5)) > body) return fail(ORC_E_SERIALIZE, "bad native header");
         uint32_t *lens = (uint32_t *)malloc(sizeof(uint32_t) * ((size_t)nr + 1));
-        for (uint32_t i = 0; i < nr; i++)
+        uint64_t *roff = (uint64_t *)malloc(sizeof(uint64_t) * ((size_t)nr + 1));
+        uint64_t total = 0;
+        for (uint32_t i = 0; i < nr; i++) {
             lens[i] = w == 0 ? cl : (w == 2 ? (uint32_t)(t_len[2 * i] << 8 | t_len[2 * i + 1]) : get_u32be(t_len + 4 * (size_t)i));
-        uint64_t off = 0;
-        uint32_t lane = 0, r = 0;
-        while (r < nr) {
-            /* lane = maximal run of reads whose offsets share the quantum off / Q */
-            uint32_t r_end = r;
-            uint64_t o = off, q0 = off / Q;
-            while (r_end < nr && (r_end == r || o / Q == q0)) {
-                o += lens[r_end];
-                r_end++;
-            }
-            if (lane >= nl) { free(lens); return fail(ORC_E_SERIALIZE, "more lanes than the table holds"); }
+            roff[i] = total;
+            total += lens[i];
+            read_len[out_read++] = lens[i];
+        }
+        roff[nr] = total;
+        uint64_t *lane_sym = (uint64_t *)malloc(sizeof(uint64_t) * ((size_t)nr + total / Q + 2));
+        int split = 0;
+        const uint64_t n_lanes = nr ? native_lanes(lens, nr, Q, lane_sym, &split) : 0;
+        if (n_lanes != nl || split != split_flag) {
+            free(lens); free(roff); free(lane_sym);
+            return fail(ORC_E_SERIALIZE, "the lane table does not match the partition of the lengths");
+        }
+        uint32_t r = 0;
+        for (uint64_t lane = 0; lane < n_lanes; lane++) {
+            const uint64_t a = lane_sym[lane], b = lane_sym[lane + 1];
             uint32_t ia = t_mdl[2 * lane], iq = t_mdl[2 * lane + 1], ll = get_u32be(t_ll + 4 * (size_t)lane);
             if (ia >= n_models || iq >= n_models || models[ia]->type != ORC_TYPE_ACID || models[iq]->type != ORC_TYPE_QSCORE) {
-                free(lens);
+                free(lens); free(roff); free(lane_sym);
                 return fail(ORC_E_INVALID_MODEL_INDEX, "lane names a bad model");
             }
-            if (ll < 8 || (size_t)(pay - data) + ll > pos + 5 + (size_t)body) { free(lens); return fail(ORC_E_SERIALIZE, "lane payload out of range"); }
+            while (r < nr && roff[r + 1] <= a) r++; /* first read with a symbol at or behind a */
+            const int mid = r < nr && roff[r] < a && b > a;
+            const uint32_t hdr = mid ? 2 * NATIVE_HIST : 0;
+            if (ll < 8 + hdr || (size_t)(pay - data) + ll > pos + 5 + (size_t)body) {
+                free(lens); free(roff); free(lane_sym);
+                return fail(ORC_E_SERIALIZE, "lane payload out of range");
+            }
             const orc_model_t *am = models[ia], *qm = models[iq];
-            uint32_t sq = (uint32_t)pay[0] | (uint32_t)pay[1] << 8 | (uint32_t)pay[2] << 16 | (uint32_t)pay[3] << 24;
-            uint32_t sa = (uint32_t)pay[4] | (uint32_t)pay[5] << 8 | (uint32_t)pay[6] << 16 | (uint32_t)pay[7] << 24;
-            size_t pp = 8;
-            for (uint32_t k = r; k < r_end; k++) {
-                uint32_t len = lens[k];
+            const uint8_t *st = pay + hdr;
+            uint32_t sq = (uint32_t)st[0] | (uint32_t)st[1] << 8 | (uint32_t)st[2] << 16 | (uint32_t)st[3] << 24;
+            uint32_t sa = (uint32_t)st[4] | (uint32_t)st[5] << 8 | (uint32_t)st[6] << 16 | (uint32_t)st[7] << 24;
+            size_t pp = hdr + 8;
+            for (uint32_t k = r; k < nr && roff[k] < b; k++) {
+                if (roff[k + 1] <= a) continue;
+                const uint32_t len = lens[k];
+                const uint32_t p0 = (uint32_t)((a > roff[k] ? a : roff[k]) - roff[k]), p1 = (uint32_t)((b < roff[k + 1] ? b : roff[k + 1]) - roff[k]);
                 orc_gen_t ga, gq;
                 orc_gen_init(&ga, &am->spec, len);
                 orc_gen_init(&gq, &qm->spec, len);
-                for (uint32_t i = 0; i < len; i++) {
+                if (p0 > 0) { /* a piece that starts inside its read: states from the stored history, position counter = p0 */
+                    ga.position = gq.position = p0 - NATIVE_HIST; /* u32 wrap is undone by the NATIVE_HIST updates below */
+                    for (uint32_t h = 0; h < NATIVE_HIST; h++) {
+                        orc_gen_update(&ga, pay[h], pay[NATIVE_HIST + h]);
+                        orc_gen_update(&gq, pay[h], pay[NATIVE_HIST + h]);
+                    }
+                }
+                for (uint32_t i = p0; i < p1; i++) {
                     uint32_t ca = ctx_for(am, orc_gen_current(&ga)), cq = ctx_for(qm, orc_gen_current(&gq));
                     uint32_t slot_q = sq & mask, slot_a = sa & mask;
                     uint32_t yq = find_sym(qm, cq, slot_q), ya = find_sym(am, ca, slot_a);
@@ -1528,29 +1614,27 @@ int orc_decompress_native_block(const orc_model_t *const *models, uint32_t n_mod
                     sq = (uint32_t)(rq[yq + 1] - rq[yq]) * (sq >> ORC_SCALE_BITS) + slot_q - rq[yq];
                     sa = (uint32_t)(ra[ya + 1] - ra[ya]) * (sa >> ORC_SCALE_BITS) + slot_a - ra[ya];
                     while (sq < RANS_L) {
-                        if (pp >= ll) { free(lens); return fail(ORC_E_SERIALIZE, "lane payload exhausted"); }
+                        if (pp >= ll) { free(lens); free(roff); free(lane_sym); return fail(ORC_E_SERIALIZE, "lane payload exhausted"); }
                         sq = (sq << 8) | pay[pp++];
                     }
                     while (sa < RANS_L) {
-                        if (pp >= ll) { free(lens); return fail(ORC_E_SERIALIZE, "lane payload exhausted"); }
+                        if (pp >= ll) { free(lens); free(roff); free(lane_sym); return fail(ORC_E_SERIALIZE, "lane payload exhausted"); }
                         sa = (sa << 8) | pay[pp++];
                     }
-                    acids[out_sym] = (uint8_t)ya;
-                    quals[out_sym] = (uint8_t)yq;
-                    out_sym++;
+                    acids[out_sym + roff[k] + i] = (uint8_t)ya;
+                    quals[out_sym + roff[k] + i] = (uint8_t)yq;
                     orc_gen_update(&ga, (uint8_t)ya, (uint8_t)yq);
                     orc_gen_update(&gq, (uint8_t)ya, (uint8_t)yq);
                 }
-                read_len[out_read++] = len;
             }
-            if (sq != RANS_L || sa != RANS_L || pp != ll) { free(lens); return fail(ORC_E_SERIALIZE, "lane does not end cleanly"); }
+            if (sq != RANS_L || sa != RANS_L || pp != ll) { free(lens); free(roff); free(lane_sym); return fail(ORC_E_SERIALIZE, "lane does not end cleanly"); }
             pay += ll;
-            off = o;
-            r = r_end;
-            lane++;
         }
+        out_sym += total;
         free(lens);
-        if (lane != nl || (size_t)(pay - (data + pos + 5)) != body) return fail(ORC_E_SERIALIZE, "native slice framing mismatch");
+        free(roff);
+        free(lane_sym);
+        if ((size_t)(pay - (data + pos + 5)) != body) return fail(ORC_E_SERIALIZE, "native slice framing mismatch");
         pos += 5 + (size_t)body;
     }
     return ORC_OK;

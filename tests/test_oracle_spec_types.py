@@ -37,3 +37,28 @@ def test_oracle_round_trip_per_spec_type(O, i):
             hit += am.ctx_for(g.current_context()) != 0
             g.update(int(reads.acids[k]), int(reads.quals[k]))
     assert hit > 0
+
+
+def test_oracle_native_format_splits_long_reads(O, toy_models):
+    """Container version 2: reads longer than the lane quantum (>= 256) are cut into lanes of `lane_syms` symbols, each with
+    the 8-position history its generators need (csrc/idn_native.cuh).  CPU statement: encode -> decode is the identity,
+    a long read yields several lanes, short reads are laid out as before."""
+    rng = np.random.default_rng(21)
+    seqs = []
+    for ln in [5000, 40, 0, 256, 257, 700, 3, 12000, 90, 90, 1024, 1]:
+        seqs.append(("", rng.integers(0, 5, size=ln), rng.integers(0, 94, size=ln)))
+    reads = O.Reads.from_lists(seqs)
+    for q in (256, 300, 1000, 4096):
+        data, crc = O.compress_native_block(toy_models, reads, 0, reads.n_reads, lane_syms=q, include_identifiers=False)
+        ln, a, qq = O.decompress_native_block(toy_models, data)
+        assert ln.tolist() == [len(s[1]) for s in seqs]
+        assert np.array_equal(a, reads.acids) and np.array_equal(qq, reads.quals)
+        n_lanes = int.from_bytes(data[9:13], "big")
+        split = data[17] >> 7
+        assert split == (1 if q < 12000 else 0)
+        assert n_lanes >= sum(-(-len(s[1]) // q) for s in seqs if len(s[1]) > q)
+    # below the threshold nothing is split (one lane may hold a whole long read)
+    data, _ = O.compress_native_block(toy_models, reads, 0, reads.n_reads, lane_syms=64, include_identifiers=False)
+    assert data[17] >> 7 == 0
+    ln, a, qq = O.decompress_native_block(toy_models, data)
+    assert np.array_equal(a, reads.acids) and np.array_equal(qq, reads.quals)
