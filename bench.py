@@ -50,6 +50,10 @@ WORKLOADS = {
     "pacbio": dict(acid="m64187e__sars_cov_2__sequel_ii_e__acids", q="m64187e__sars_cov_2__sequel_ii_e__q_scores",
                    read_len=(10_000, 20_000), reads=166_000, name_len=40, seed=20240603, n_ppm=0, mode="compat", select=1,
                    desc="synthetic 5 GB PacBio Sequel II-shaped FASTQ, 10-20 kb reads, compat mode (BASELINE.json configs[4])"),
+    # the same long reads in the GPU-native format, which cuts them into lanes (a long read is many short chains there)
+    "pacbio_native": dict(acid="m64187e__sars_cov_2__sequel_ii_e__acids", q="m64187e__sars_cov_2__sequel_ii_e__q_scores",
+                          read_len=(10_000, 20_000), reads=166_000, name_len=40, seed=20240603, n_ppm=0, mode="native", select=1,
+                          desc="synthetic 5 GB PacBio Sequel II-shaped FASTQ, 10-20 kb reads, GPU-native multi-lane mode (long reads cut into lanes)"),
     # configs[3] / the reference's default path: per-read greedy selection among the 4 + 4 models that quality 7 retains
     # (idn/compressor.rs:184-194, compressor_initializer.rs:53-74) out of the whole models/ directory
     "hiseq100_select4": dict(acid="ERR174310__human__illumina_hiseq_2000__acids", q="SRR2962693__human__illumina_hiseq_2500__q_scores",
@@ -58,7 +62,7 @@ WORKLOADS = {
                                   "models quality 7 retains from the 22 bundled ones (reference default path; BASELINE.json configs[3])"),
 }
 WORKLOADS["novaseq150"] = WORKLOADS["novaseq150_native"]  # round-1 name
-EXTRA_WORKLOADS = ["novaseq150_native", "pacbio", "hiseq100_select4"]  # sub-records of the default run (the north-star shapes)
+EXTRA_WORKLOADS = ["novaseq150_native", "pacbio", "pacbio_native", "hiseq100_select4"]  # sub-records of the default run (the north-star shapes)
 
 
 def read_lengths(w: dict, n_reads: int, first: int) -> np.ndarray:

@@ -281,6 +281,13 @@ struct PosFwd {
         frac = P - step * len;
         pos = rem = 0;
     }
+    // the state after i advances: pos * len + rem = i * 2^pbmax
+    __device__ __forceinline__ void init_at(uint32_t length, uint32_t pbmax, uint32_t i) {
+        init(length, pbmax);
+        const unsigned long long t = (unsigned long long)i << pbmax;
+        pos = (uint32_t)(t / len);
+        rem = (uint32_t)(t % len);
+    }
     __device__ __forceinline__ void advance() {
         pos += step;
         rem += frac;
@@ -299,6 +306,13 @@ struct PosBack {  // starts at i = len and steps down
         frac = P - step * len;
         pos = P;  // len * P / len
         rem = 0;
+    }
+    // standing at position i (<= length) instead of at the end
+    __device__ __forceinline__ void init_at(uint32_t length, uint32_t pbmax, uint32_t i) {
+        init(length, pbmax);
+        const unsigned long long t = (unsigned long long)i << pbmax;
+        pos = (uint32_t)(t / len);
+        rem = (uint32_t)(t % len);
     }
     __device__ __forceinline__ void retreat() {
         pos -= step;

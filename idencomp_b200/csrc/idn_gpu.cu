@@ -119,7 +119,7 @@ struct idn_gpu_ctx {
     // workspaces of the *_dev paths
     DevBuf w_scratch, w_paylen, w_sizes, w_chosen, w_tiles, w_sliceoff, w_readblock, w_small, w_crcpart, w_crclen;
     DevBuf w_walkdone, w_blockadj;
-    DevBuf w_lanefirst, w_laneoff, w_laneblock, w_blkinfo, w_nhdr;  // native mode
+    DevBuf w_lanefirst, w_laneoff, w_laneblock, w_blkinfo, w_nhdr, w_lanesym;  // native mode
     uint32_t lane_syms = 2048;  // lane quantum of the native format (tools/lane_sweep.sh: decode is 17 % faster than at 4096 for +0.5 % size)
     // FASTQ text <-> symbols (idn_fastq.cuh): results of the last parse stay here until the next one
     DevBuf f_text, f_tilecnt, f_tilebase, f_linestart, f_linefn, f_linestate, f_tilefn, f_tilestate, f_recscan, f_title, f_namelo,
@@ -248,7 +248,8 @@ struct SmallParams {
     uint32_t has_sizes[2];
     int32_t score_ids[256];  // score-matrix column -> slot
     uint32_t err;            // bit 0: invalid symbol
-    uint32_t pad[3];
+    uint32_t native_split;   // native decode: some block of the call cuts long reads into pieces
+    uint32_t pad[2];
     unsigned long long stats[8];
     int32_t status[4];
 };
@@ -390,7 +391,7 @@ extern "C" void idn_gpu_destroy(idn_gpu_ctx* ctx) {
         if (s.used) s.free_all();
     DevBuf* bufs[] = {&ctx->w_scratch, &ctx->w_paylen,  &ctx->w_sizes,   &ctx->w_chosen,     &ctx->w_tiles,  &ctx->w_sliceoff,
                       &ctx->w_readblock, &ctx->w_small, &ctx->w_crcpart, &ctx->w_crclen,     &ctx->w_index,  &ctx->w_blk,
-                      &ctx->w_lanefirst, &ctx->w_laneoff, &ctx->w_laneblock, &ctx->w_blkinfo, &ctx->w_nhdr, &ctx->w_walkdone, &ctx->w_blockadj,
+                      &ctx->w_lanefirst, &ctx->w_laneoff, &ctx->w_laneblock, &ctx->w_blkinfo, &ctx->w_nhdr, &ctx->w_lanesym, &ctx->w_walkdone, &ctx->w_blockadj,
                       &ctx->f_text, &ctx->f_tilecnt, &ctx->f_tilebase, &ctx->f_linestart, &ctx->f_linefn, &ctx->f_linestate, &ctx->f_tilefn,
                       &ctx->f_tilestate, &ctx->f_recscan, &ctx->f_title, &ctx->f_namelo, &ctx->f_namelen, &ctx->f_readlen, &ctx->f_readoff,
                       &ctx->f_nameoff, &ctx->f_names, &ctx->f_acids, &ctx->f_quals, &ctx->f_err, &ctx->f_fmtoff, &ctx->f_fmttext,
@@ -932,18 +933,18 @@ extern "C" int32_t idn_gpu_compress_blocks_dev(idn_gpu_ctx* ctx, const idn_batch
 static int32_t launch_crc_read(idn_gpu_ctx* ctx, const uint8_t* acids, const uint8_t* quals, const unsigned long long* read_off,
                                const uint8_t* names, const unsigned long long* name_off, uint64_t n_reads,
                                const unsigned long long* n_reads_dev, const int32_t* status, uint64_t grid_reads, uint64_t avg_len,
-                               cudaStream_t st) {
+                               cudaStream_t st, const uint32_t* run_flag = nullptr) {
     if (avg_len >= 1024) {
         crc_read_warp_kernel<<<(unsigned)((grid_reads * 32 + 127) / 128), 128, 0, st>>>(
             acids, quals, read_off, names, name_off, n_reads, n_reads_dev, status, ctx->d_crc_tab, ctx->d_xpow,
-            ctx->w_crcpart.as<uint32_t>(), ctx->w_crclen.as<unsigned long long>());
+            ctx->w_crcpart.as<uint32_t>(), ctx->w_crclen.as<unsigned long long>(), run_flag);
     } else {
         const uint64_t tiles = (grid_reads + kCrcThreads - 1) / kCrcThreads;
         const unsigned cgrid = (unsigned)std::min<uint64_t>(tiles ? tiles : 1, (uint64_t)ctx->sm_count * 2);
         crc_read_kernel<<<cgrid, kCrcThreads, 0, st>>>(acids, quals, read_off, names, name_off, n_reads, n_reads_dev,
                                                                              status, ctx->d_crc_tab, ctx->d_xpow,
                                                                              ctx->w_crcpart.as<uint32_t>(),
-                                                                             ctx->w_crclen.as<unsigned long long>());
+                                                                             ctx->w_crclen.as<unsigned long long>(), run_flag);
     }
     LAUNCHED("crc_read");
     return IDN_OK;
@@ -999,19 +1000,22 @@ static int32_t compress_native_dev(idn_gpu_ctx* ctx, const idn_batch* batch, Sma
     int32_t rc = upload_small(ctx, sp, st);
     if (rc) return rc;
     SmallParams* dsp = ctx->w_small.as<SmallParams>();
+    // lanes per block <= 1 + its symbols / Q (a lane starts the block or changes the quantum); without cut reads also <= reads
     uint64_t lane_cap = S / Q + 2ull * B + 1;
-    if (lane_cap > R) lane_cap = R;
+    if (Q < kNativeMinSplitQ && lane_cap > R) lane_cap = R;
     CU(ctx->w_readblock.ensure((R + 1) * 4));
     CU(ctx->w_sliceoff.ensure((R + 2) * 8));          // lane_scan
     CU(ctx->w_lanefirst.ensure((lane_cap + 2) * 4));
+    CU(ctx->w_lanesym.ensure((lane_cap + 2) * 8));
     CU(ctx->w_paylen.ensure((lane_cap + 1) * 4));     // lane_len
     CU(ctx->w_laneoff.ensure((lane_cap + 2) * 8));
     CU(ctx->w_laneblock.ensure((lane_cap + 1) * 4));
     CU(ctx->w_blkinfo.ensure(((size_t)B + 2) * 4 * 3));
-    CU(ctx->w_scratch.ensure(4 * S + 8 * lane_cap + 16));
+    CU(ctx->w_scratch.ensure(4 * S + kLaneSlotExtra * (lane_cap + 1) + 16));
     uint32_t* read_block = ctx->w_readblock.as<uint32_t>();
     unsigned long long* lane_scan = ctx->w_sliceoff.as<unsigned long long>();
     uint32_t* lane_first = ctx->w_lanefirst.as<uint32_t>();
+    unsigned long long* lane_sym = ctx->w_lanesym.as<unsigned long long>();
     uint32_t* lane_len = ctx->w_paylen.as<uint32_t>();
     unsigned long long* lane_off = ctx->w_laneoff.as<unsigned long long>();
     uint32_t* lane_block = ctx->w_laneblock.as<uint32_t>();
@@ -1021,7 +1025,7 @@ static int32_t compress_native_dev(idn_gpu_ctx* ctx, const idn_batch* batch, Sma
     const unsigned long long* n_lanes_dev = lane_scan + R;
     unsigned long long* boff = reinterpret_cast<unsigned long long*>(block_off);
 
-    LaneFlag lf{batch->read_off, batch->block_first_read, read_block, Q};
+    LaneCount lf{batch->read_off, batch->block_first_read, read_block, Q};
     if (R > 0) {
         read_block_kernel<<<B, 256, 0, st>>>(batch->block_first_read, B, read_block);
         LAUNCHED("read_block");
@@ -1032,7 +1036,7 @@ static int32_t compress_native_dev(idn_gpu_ctx* ctx, const idn_batch* batch, Sma
     const bool uniform = sp.n_cand[0] == 1 && sp.n_cand[1] == 1;
     (void)fast;  // one model pair per lane either way; fast only restricts the provider to 2 models
     if (R > 0) {
-        lane_scatter_kernel<<<(unsigned)((R + 255) / 256), 256, 0, st>>>(lf, R, lane_scan, lane_first);
+        lane_scatter_kernel<<<(unsigned)((R + 255) / 256), 256, 0, st>>>(lf, R, lane_scan, lane_first, lane_sym);
         LAUNCHED("lane_scatter");
         uint32_t n_score = 0;
         for (uint32_t t = 0; t < 2; t++)
@@ -1044,8 +1048,8 @@ static int32_t compress_native_dev(idn_gpu_ctx* ctx, const idn_batch* batch, Sma
             rc = launch_score(ctx, sp.score_ids, n_score, batch, n_score, ctx->w_sizes.as<uint32_t>(), &dsp->err, st);
             if (rc) return rc;
             lane_choose_kernel<<<(unsigned)((2 * lane_cap + 127) / 128), 128, 0, st>>>(
-                ctx->w_sizes.as<uint32_t>(), n_score, dsp->cand_cols, dsp->n_cand, dsp->has_sizes, lane_first, n_lanes_dev,
-                lane_cap, lane_choice);
+                ctx->w_sizes.as<uint32_t>(), n_score, dsp->cand_cols, dsp->n_cand, dsp->has_sizes, lane_first, lane_sym, batch->read_off, R,
+                n_lanes_dev, lane_cap, lane_choice);
             LAUNCHED("lane_choose");
         }
         EncodeLaneArgs ea;
@@ -1054,7 +1058,9 @@ static int32_t compress_native_dev(idn_gpu_ctx* ctx, const idn_batch* batch, Sma
         ea.quals = batch->quals;
         ea.n_symbols = S;
         ea.read_off = batch->read_off;
+        ea.n_reads = R;
         ea.lane_first = lane_first;
+        ea.lane_sym = lane_sym;
         ea.n_lanes_dev = n_lanes_dev;
         ea.lane_cap = lane_cap;
         ea.lane_choice = lane_choice;
@@ -1075,7 +1081,7 @@ static int32_t compress_native_dev(idn_gpu_ctx* ctx, const idn_batch* batch, Sma
     LaneLenFn ll{lane_len, n_lanes_dev};
     rc = scan_u64(ctx, ll, lane_cap, lane_off, st);
     if (rc) return rc;
-    native_block_info_kernel<<<B, 256, 0, st>>>(batch->read_off, batch->block_first_read, B, lane_scan, blk_width, blk_const,
+    native_block_info_kernel<<<B, 256, 0, st>>>(batch->read_off, batch->block_first_read, B, lane_scan, Q, blk_width, blk_const,
                                                 blk_lane0);
     LAUNCHED("native_block_info");
     native_layout_kernel<<<1, 32, 0, st>>>(batch->block_first_read, B, prefix_len, blk_width, blk_lane0, lane_off, boff, out,
@@ -1093,6 +1099,7 @@ static int32_t compress_native_dev(idn_gpu_ctx* ctx, const idn_batch* batch, Sma
         aa.blk_const_len = blk_const;
         aa.blk_lane0 = blk_lane0;
         aa.lane_first = lane_first;
+        aa.lane_sym = lane_sym;
         aa.lane_len = lane_len;
         aa.lane_off = lane_off;
         aa.lane_choice = lane_choice;
@@ -1304,9 +1311,12 @@ static int32_t decompress_native_dev(idn_gpu_ctx* ctx, const uint8_t* blocks, co
     BlockCounters bc = carve_counters(ctx->w_blk.p, n_blocks);  // reads, syms, slots (= lanes here)
     CU(ctx->w_nhdr.ensure(((size_t)n_blocks + 1) * sizeof(NativeBlockHdr)));
     NativeBlockHdr* hdr = ctx->w_nhdr.as<NativeBlockHdr>();
-    CU(ctx->w_index.ensure(index_bytes(out_reads_cap + 1)));
-    ReadIndexDev rix = carve_index(ctx->w_index.p, out_reads_cap + 1);
-    NativeIndex ix{rix.pay_off, rix.pay_len, rix.sym_off, rix.am, rix.qm};  // lanes <= reads
+    // lanes <= reads, plus one per kNativeMinSplitQ symbols when long reads are cut into pieces (idn_native.cuh)
+    const uint64_t lane_cap = out_reads_cap + out_symbols_cap / kNativeMinSplitQ + n_blocks + 2;
+    CU(ctx->w_index.ensure(index_bytes(lane_cap)));
+    CU(ctx->w_lanesym.ensure((lane_cap + 2) * 8));
+    ReadIndexDev rix = carve_index(ctx->w_index.p, lane_cap);
+    NativeIndex ix{rix.pay_off, rix.pay_len, rix.sym_off, ctx->w_lanesym.as<unsigned long long>(), rix.am, rix.qm, lane_cap};
     CU(ctx->w_readblock.ensure(((size_t)n_blocks + 2) * 4));
     uint32_t* block_first = ctx->w_readblock.as<uint32_t>();
     unsigned long long* roff = reinterpret_cast<unsigned long long*>(read_off_out);
@@ -1315,7 +1325,7 @@ static int32_t decompress_native_dev(idn_gpu_ctx* ctx, const uint8_t* blocks, co
         roff = ctx->w_sliceoff.as<unsigned long long>();
     }
     native_hdr_kernel<<<n_blocks, 32, 0, st>>>(blocks, boff, block_len, n_blocks, blocks_bytes, n_models, dsp->model_type, hdr,
-                                               bc.reads, bc.syms, bc.slots, dsp->status);
+                                               bc.reads, bc.syms, bc.slots, dsp->status, &dsp->native_split);
     LAUNCHED("native_hdr");
     scan_tiles_kernel<<<1, kScanBlock, 0, st>>>(bc.reads, n_blocks);
     LAUNCHED("scan_tiles");
@@ -1338,6 +1348,7 @@ static int32_t decompress_native_dev(idn_gpu_ctx* ctx, const uint8_t* blocks, co
         da.n_lanes_dev = bc.slots + n_blocks;
         da.read_off = roff;
         da.status = dsp->status;
+        da.split_flag = &dsp->native_split;
         da.acids_out = acids_out;
         da.quals_out = quals_out;
         da.out_dq = (long long)(quals_out - acids_out);
@@ -1352,18 +1363,29 @@ static int32_t decompress_native_dev(idn_gpu_ctx* ctx, const uint8_t* blocks, co
             da.part_len = ctx->w_crclen.as<unsigned long long>();
             da.crc_tab = ctx->d_crc_tab;
             da.xpow = ctx->d_xpow;
+            // empty reads that no lane visits keep the partial of an empty read
+            CU(cudaMemsetAsync(da.part_crc, 0, (out_reads_cap + 1) * 4, st));
+            CU(cudaMemsetAsync(da.part_len, 0, (out_reads_cap + 1) * 8, st));
         }
         int ua = -1, uq = -1, na = 0, nq = 0;
         for (uint32_t i = 0; i < n_models; i++) {
             if (ctx->slots[models[i]].dev.type == IDN_MODEL_ACID) { ua = models[i]; na++; } else { uq = models[i]; nq++; }
         }
-        const unsigned grid = (unsigned)((out_reads_cap + 127) / 128);
+        // one thread per lane; the kernel strides, so a call with more lanes than this estimate (many cut reads) still decodes
+        const uint64_t lanes_est = std::min<uint64_t>(lane_cap, out_reads_cap + out_symbols_cap / 1024 + n_blocks);
+        const unsigned grid = (unsigned)std::max<uint64_t>(1, (lanes_est + 127) / 128);
         if (na == 1 && nq == 1) {
             IDN_LAUNCH_UNIFORM(static_pair_index(ctx, ua, uq), decode_lane_kernel, grid, st, da, ctx->slots[ua].dev, ctx->slots[uq].dev)
         } else {
             decode_lane_kernel<false, DynSpecs><<<grid, 128, 0, st>>>(da, ctx->d_models_host0, ctx->d_models_host0);
         }
         LAUNCHED("decode_lane");
+        if (block_crc) {
+            // blocks that cut reads into pieces: the per-read CRC partials come from a pass over the decoded symbols (a no-op otherwise)
+            int32_t rc = launch_crc_read(ctx, acids_out, quals_out, roff, nullptr, nullptr, 0, bc.reads + n_blocks, dsp->status, out_reads_cap,
+                                         out_reads_cap ? out_symbols_cap / out_reads_cap : 0, st, &dsp->native_split);
+            if (rc) return rc;
+        }
     }
     if (block_crc && out_reads_cap) {
         crc_verify_kernel<<<n_blocks, 256, 0, st>>>(ctx->w_crcpart.as<uint32_t>(), ctx->w_crclen.as<unsigned long long>(),
@@ -1538,7 +1560,7 @@ extern "C" int32_t idn_gpu_index_blocks(idn_gpu_ctx* ctx, const uint8_t* blocks,
         native_hdr_kernel<<<n_blocks, 32, 0, st>>>(ctx->s_blocks.as<uint8_t>(), ctx->s_blockoff.as<unsigned long long>(),
                                                    block_len ? ctx->s_blocklen.as<uint32_t>() : nullptr, n_blocks, nbytes, n_models,
                                                    dsp->model_type, ctx->w_nhdr.as<NativeBlockHdr>(), nbc.reads, nbc.syms,
-                                                   nbc.slots, dsp->status);
+                                                   nbc.slots, dsp->status, &dsp->native_split);
         LAUNCHED("native_hdr");
         scan_tiles_kernel<<<1, kScanBlock, 0, st>>>(nbc.reads, n_blocks);
         LAUNCHED("scan_tiles");

@@ -414,7 +414,10 @@ struct EncStream {
     __device__ __forceinline__ uint32_t total() const { return out.bytes(); }  // bytes emitted so far
 };
 
-// Pushes one read (positions len-1 .. 0) onto the stream   SequenceCompressor::compress, sequence_compressor.rs:82-155
+// Pushes the positions p1-1 .. p0 of one read onto the stream (the whole read: p0 = 0, p1 = len)
+//   SequenceCompressor::compress, sequence_compressor.rs:82-155
+// The generators always see the true symbols in front of a position, so a piece of a read (native format, long reads cut
+// into lanes) is coded with the same contexts as inside the whole read.
 //
 // The loop is software-pipelined over three positions because only the 32-bit rANS states are serial in the encoder:
 // while position i is coded, the encoder entry of position i-1 is being gathered and the context row of position i-2
@@ -422,23 +425,23 @@ struct EncStream {
 template <class P>
 __device__ __forceinline__ void encode_read_body(const ModelDev& ma, const ModelDev& mq, const uint8_t* __restrict__ acids,
                                                  const uint8_t* __restrict__ quals, unsigned long long n_symbols, long long off,
-                                                 uint32_t len, EncStream& S) {
+                                                 uint32_t len, uint32_t p0, uint32_t p1, EncStream& S) {
     constexpr SpecDev ksa = P::sa(), ksq = P::sq();  // compile-time generator parameters of a specialised pair
     const SpecDev& sa = P::kStatic ? ksa : ma.spec;
     const SpecDev& sq = P::kStatic ? ksq : mq.spec;
 #ifndef IDN_NO_SYM16
     SymBackReader rs;
-    rs.start(acids, quals, n_symbols, off, len);  // nothing is loaded when len == 0
+    rs.start(acids, quals, n_symbols, off, p1);  // nothing is loaded when p1 == 0
 #else
     (void)n_symbols;
     BackReader ra, rq;
-    ra.start(acids + off + len - 1);  // nothing is loaded before the first get()
-    rq.start(quals + off + len - 1);
+    ra.start(acids + off + p1 - 1);  // nothing is loaded before the first get()
+    rq.start(quals + off + p1 - 1);
 #endif
     GenBack ga, gq;
     ga.clear(sa);
     gq.clear(sq);
-    int32_t front = (int32_t)len - 1;  // next position to pull into the windows (reads are shorter than 2^31)
+    int32_t front = (int32_t)p1 - 1;  // next position to pull into the windows (reads are shorter than 2^31)
     uint32_t raw_a = 0;                // raw symbols travel in two more shift registers (entry k = position j - k)
     unsigned long long raw_q = 0;
     auto pull = [&]() {
@@ -464,13 +467,13 @@ __device__ __forceinline__ void encode_read_body(const ModelDev& ma, const Model
         raw_q = (raw_q >> 7) | ((unsigned long long)q << (7 * kHist));
     };
 #pragma unroll 1
-    for (int t = 0; t < kHist; t++) pull();  // entry k = symbol at len - k
+    for (int t = 0; t < kHist; t++) pull();  // entry k = symbol at p1 - k
     ga.init_state(sa);
     gq.init_state(sq);
     const uint32_t pbmax = sa.pb > sq.pb ? sa.pb : sq.pb;
     const uint32_t psa = pbmax - sa.pb, psq = pbmax - sq.pb;
     PosBack pb;
-    pb.init(len, pbmax);
+    pb.init_at(len, pbmax, p1);
 
     // acid side: models with a small dense spec space carry the encoder entries per spec (ModelDev::aenc), i.e. the "row" of
     // the acid side is the spec itself and spec -> row -> entry is one gather
@@ -481,11 +484,11 @@ __device__ __forceinline__ void encode_read_body(const ModelDev& ma, const Model
 #endif
     const uint2* __restrict__ enc_a = direct_a ? ma.aenc : ma.enc;
     // generator stage: moves the generators to position j (entry 0 = symbol j) and looks the two rows up
-    int32_t j = (int32_t)len;  // position the generators stand at
+    int32_t j = (int32_t)p1;  // position the generators stand at
     auto rows_next = [&](uint32_t& row_a, uint32_t& row_q) {
         j--;
         row_a = row_q = 0;
-        if (j >= 0) {
+        if (j >= (int32_t)p0) {
             pull();
             ga.step_back(sa);
             gq.step_back(sq);
@@ -494,20 +497,20 @@ __device__ __forceinline__ void encode_read_body(const ModelDev& ma, const Model
             row_q = gen_row<P::kStatic>(mq, sq, gq, pb.pos, psq);
         }
     };
-    // prologue: rows of position len-1, its entries, rows of position len-2
+    // prologue: rows of position p1-1, its entries, rows of position p1-2
     uint32_t row_a, row_q;
-    rows_next(row_a, row_q);  // generators at len-1, entry 0 = symbol len-1
+    rows_next(row_a, row_q);  // generators at p1-1, entry 0 = symbol p1-1
     uint2 ea = make_uint2(0, 0), eq = make_uint2(0, 0);
-    if (len) {
+    if (p1 > p0) {
         ea = ldg_stream8(enc_a + (row_a * kAcidSyms + (raw_a & 7u)));
         eq = __ldg(mq.enc + (row_q * kQSyms + ((uint32_t)raw_q & 127u)));
     }
-    rows_next(row_a, row_q);  // generators at len-2
+    rows_next(row_a, row_q);  // generators at p1-2
 #pragma unroll 1
-    for (uint32_t i = len; i-- > 0;) {
+    for (uint32_t i = p1; i-- > p0;) {
         // entries of position i-1 (generators stand at i-1: entry 0), gathered while position i is coded
         uint2 ea_n = make_uint2(0, 0), eq_n = make_uint2(0, 0);
-        if (i >= 1) {
+        if (i > p0) {
             ea_n = ldg_stream8(enc_a + (row_a * kAcidSyms + (raw_a & 7u)));
             eq_n = __ldg(mq.enc + (row_q * kQSyms + ((uint32_t)raw_q & 127u)));
         }
@@ -546,7 +549,7 @@ encode_kernel(EncodeArgs A, const ModelDev MA, const ModelDev MQ) {
     const uint32_t len = (uint32_t)(A.read_off[r + 1] - A.read_off[r]);
     EncStream S;
     S.begin(A.scratch + 4ull * A.read_off[r + 1] + kSlotExtra * (r + 1));
-    encode_read_body<P>(ma, mq, A.acids, A.quals, A.n_symbols, off, len, S);
+    encode_read_body<P>(ma, mq, A.acids, A.quals, A.n_symbols, off, len, 0, len, S);
     S.flush_states();
     const uint32_t plen = S.total();
     A.pay_len[r] = plen;
@@ -940,10 +943,12 @@ crc_read_kernel(const uint8_t* __restrict__ acids, const uint8_t* __restrict__ q
                 const unsigned long long* __restrict__ name_off, uint64_t n_reads,
                 const unsigned long long* __restrict__ n_reads_dev, const int32_t* __restrict__ status,
                 const uint32_t* __restrict__ crc_tab, const uint32_t* __restrict__ xpow_g,
-                uint32_t* __restrict__ part_crc, unsigned long long* __restrict__ part_len) {
+                uint32_t* __restrict__ part_crc, unsigned long long* __restrict__ part_len,
+                const uint32_t* __restrict__ run_flag /* optional: the kernel does nothing while *run_flag == 0 */) {
     __shared__ uint32_t tab[256 * 32];
     __shared__ uint32_t xpow[64];
     if (status && status[0] != 0) return;
+    if (run_flag && *run_flag == 0) return;
     if (n_reads_dev) n_reads = *n_reads_dev;
     for (int i = threadIdx.x; i < 256 * 32; i += blockDim.x) tab[i] = crc_tab[i >> 5];
     for (int i = threadIdx.x; i < 64; i += blockDim.x) xpow[i] = xpow_g[i];
@@ -995,10 +1000,12 @@ crc_read_warp_kernel(const uint8_t* __restrict__ acids, const uint8_t* __restric
                      const unsigned long long* __restrict__ name_off, uint64_t n_reads,
                      const unsigned long long* __restrict__ n_reads_dev, const int32_t* __restrict__ status,
                      const uint32_t* __restrict__ crc_tab, const uint32_t* __restrict__ xpow_g,
-                     uint32_t* __restrict__ part_crc, unsigned long long* __restrict__ part_len) {
+                     uint32_t* __restrict__ part_crc, unsigned long long* __restrict__ part_len,
+                     const uint32_t* __restrict__ run_flag) {
     __shared__ uint32_t tab[256];
     __shared__ uint32_t xpow[64];
     if (status && status[0] != 0) return;
+    if (run_flag && *run_flag == 0) return;
     if (n_reads_dev) n_reads = *n_reads_dev;
     for (int i = threadIdx.x; i < 256; i += blockDim.x) tab[i] = crc_tab[i];
     for (int i = threadIdx.x; i < 64; i += blockDim.x) xpow[i] = xpow_g[i];
@@ -1817,9 +1824,12 @@ struct DecCrc {
     uint32_t ca, cq;
 };
 
+// positions p0 .. p1-1 of a read of `len` symbols (the whole read: p0 = 0, p1 = len).  p0 > 0 (native format, a lane that
+// starts inside a long read): hist[0 .. kHist) are the acids and hist[kHist .. 2 kHist) the quality scores of the kHist
+// positions in front of p0, from which the generator states are rebuilt (no legal spec type looks further back).
 template <class P>
-__device__ __forceinline__ void decode_read_body(const ModelDev& ma, const ModelDev& mq, uint32_t len, DecStream& D,
-                                                 SymWriter& O, DecCrc& C) {
+__device__ __forceinline__ void decode_read_body(const ModelDev& ma, const ModelDev& mq, uint32_t len, uint32_t p0, uint32_t p1,
+                                                 const uint8_t* __restrict__ hist, DecStream& D, SymWriter& O, DecCrc& C) {
     constexpr SpecDev ksa = P::sa(), ksq = P::sq();
     const SpecDev& sa = P::kStatic ? ksa : ma.spec;
     const SpecDev& sq = P::kStatic ? ksq : mq.spec;
@@ -1829,7 +1839,18 @@ __device__ __forceinline__ void decode_read_body(const ModelDev& ma, const Model
     const uint32_t pbmax = sa.pb > sq.pb ? sa.pb : sq.pb;
     const uint32_t psa = pbmax - sa.pb, psq = pbmax - sq.pb;
     PosFwd pf;
-    pf.init(len, pbmax);
+    pf.init_at(len, pbmax, p0);
+    if (p0) {
+#pragma unroll 1
+        for (int k = 0; k < kHist; k++) {
+            uint32_t ha = __ldg(hist + k), hq = __ldg(hist + kHist + k);
+            ha = ha > 4 ? 0 : ha;   // (a garbled history cannot index outside the tables; the CRC / clean-end checks report it)
+            hq = hq > 93 ? 0 : hq;
+            const bool hz = ha * hq == 0;
+            ga.update(sa, ha, hq, hz);
+            gq.update(sq, ha, hq, hz);
+        }
+    }
     auto step = [&](uint32_t& va, uint32_t& vq) {
         D.refill();
         uint2 pk;  // cum[1..4] of the acid context
@@ -1862,14 +1883,14 @@ __device__ __forceinline__ void decode_read_body(const ModelDev& ma, const Model
         gq.update(sq, va, vq, z);
         pf.advance();
     };
-    uint32_t i = 0, va, vq;
+    uint32_t i = p0, va, vq;
 #pragma unroll 1
-    for (; i < len && !O.aligned(); i++) {  // up to the first word boundary (everything, if the two outputs disagree)
+    for (; i < p1 && !O.aligned(); i++) {  // up to the first word boundary (everything, if the two outputs disagree)
         step(va, vq);
         O.put(va, vq);
     }
 #pragma unroll 1
-    for (; i + 4 <= len; i += 4) {
+    for (; i + 4 <= p1; i += 4) {
         uint32_t wa, wq;
         step(wa, wq);
         step(va, vq);
@@ -1884,7 +1905,7 @@ __device__ __forceinline__ void decode_read_body(const ModelDev& ma, const Model
         O.put4(wa, wq);
     }
 #pragma unroll 1
-    for (; i < len; i++) {
+    for (; i < p1; i++) {
         step(va, vq);
         O.put(va, vq);
     }
@@ -1928,7 +1949,7 @@ decode_kernel(DecodeArgs A, const ModelDev MA, const ModelDev MQ) {
     D.begin(A.payload, A.ix.pay_off[slot], A.ix.pay_len[slot]);
     SymWriter O;
     O.init(A.acids_out + ooff, A.out_dq);
-    decode_read_body<P>(ma, mq, len, D, O, C);
+    decode_read_body<P>(ma, mq, len, 0, len, nullptr, D, O, C);
     O.flush();
     const uint32_t plen = A.ix.pay_len[slot];
     D.finish(A.payload, A.ix.pay_off[slot], plen);

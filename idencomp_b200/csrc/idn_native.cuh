@@ -13,9 +13,17 @@
 //   n_lanes x u32be                       lane payload lengths
 //   lane payloads, back to back
 //
-// Lane partition (recomputed by the decoder from the lengths): with o_r the block-relative symbol offset of read r, a
-// new lane starts at the first read of the block and at every read with o_r / lane_syms != o_(r-1) / lane_syms.
-// Lane payload: [state 1 (q) LE][state 0 (acid) LE][renormalisation bytes]; reads pushed last -> first.
+// Lane partition (recomputed by the decoder from the lengths).  A read is ONE piece, unless lane_syms >= 256 and the read
+// is longer than lane_syms: then it is cut into ceil(len / lane_syms) pieces of lane_syms symbols (the last one shorter).
+// With o_p the block-relative offset of the first symbol of piece p, a new lane starts at the first piece of the block and
+// at every piece with o_p / lane_syms != o_(p-1) / lane_syms.  A lane is thus a contiguous range of the block's symbol
+// stream; bit 7 of len_width is set when some read of the block is cut (then there may be more lanes than reads).
+// Lane payload: [16 history bytes][state 1 (q) LE][state 0 (acid) LE][renormalisation bytes]; the symbols of the lane are
+// pushed last -> first, every position with the contexts it has inside its whole read.  The history bytes exist only
+// when the lane starts inside a read: the acids and then the quality scores of the 8 positions in front of the lane, from
+// which the decoder rebuilds the generator states (no legal spec type looks further back than 8 symbols; long reads thus
+// decode with as many independent chains as they have lanes instead of one chain of 10-20 k positions per read).
+// Model choice per lane: argmin of the summed forward scores of the reads that have a symbol in the lane.
 #pragma once
 #include "idn_kernels.cuh"
 
@@ -33,49 +41,81 @@ __device__ __forceinline__ void store_u32be(uint8_t* p, uint32_t v) {
 // ---------------------------------------------------------------------------------------------------
 // compress side
 // ---------------------------------------------------------------------------------------------------
-// 1 when read r opens a lane
-struct LaneFlag {
+constexpr uint32_t kNativeMinSplitQ = 256;  // reads are only cut into pieces when the lane quantum is at least this
+constexpr uint32_t kNativeHistBytes = 2 * kHist;
+
+__host__ __device__ __forceinline__ uint32_t native_pieces(uint32_t len, uint32_t Q) {
+    return (Q >= kNativeMinSplitQ && len > Q) ? (len + Q - 1) / Q : 1u;
+}
+
+// number of lanes read r opens: its first piece if it crosses into a new quantum (or starts the block), and every
+// further piece
+struct LaneCount {
     const uint64_t* read_off;
     const uint32_t* block_first;
     const uint32_t* read_block;
     uint32_t lane_syms;
+    __device__ __forceinline__ bool first_piece_opens(uint64_t r) const {
+        const uint32_t b = read_block[r];
+        const uint64_t r0 = block_first[b];
+        if (r == r0) return true;
+        const uint64_t base = read_off[r0];
+        const uint32_t plen = (uint32_t)(read_off[r] - read_off[r - 1]);
+        const uint64_t prev_last = (read_off[r - 1] - base) + (uint64_t)(native_pieces(plen, lane_syms) - 1) * lane_syms;
+        return (read_off[r] - base) / lane_syms != prev_last / lane_syms;
+    }
     __device__ __forceinline__ unsigned long long operator()(uint64_t r) const {
-        uint32_t b = read_block[r];
-        uint64_t r0 = block_first[b];
-        if (r == r0) return 1;
-        uint64_t base = read_off[r0];
-        return (read_off[r] - base) / lane_syms != (read_off[r - 1] - base) / lane_syms;
+        const uint32_t len = (uint32_t)(read_off[r + 1] - read_off[r]);
+        return (first_piece_opens(r) ? 1u : 0u) + native_pieces(len, lane_syms) - 1;
     }
 };
 
-// lane_first[l] = first read of lane l (scatter by the scanned flags); lane_first[n_lanes] = n_reads
+// lane_first[l] = the read lane l starts in, lane_sym[l] = absolute offset of its first symbol (scatter by the scanned
+// counts); terminators lane_first[n_lanes] = n_reads, lane_sym[n_lanes] = n_symbols
 __global__ void __launch_bounds__(256)
-lane_scatter_kernel(LaneFlag fn, uint64_t n_reads, const unsigned long long* __restrict__ lane_scan /*[n_reads+1]*/,
-                    uint32_t* __restrict__ lane_first) {
+lane_scatter_kernel(LaneCount fn, uint64_t n_reads, const unsigned long long* __restrict__ lane_scan /*[n_reads+1]*/,
+                    uint32_t* __restrict__ lane_first, unsigned long long* __restrict__ lane_sym) {
     uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (r == 0) lane_first[lane_scan[n_reads]] = (uint32_t)n_reads;
+    if (r == 0) {
+        lane_first[lane_scan[n_reads]] = (uint32_t)n_reads;
+        lane_sym[lane_scan[n_reads]] = fn.read_off[n_reads];
+    }
     if (r >= n_reads) return;
-    if (fn(r)) lane_first[lane_scan[r]] = (uint32_t)r;
+    unsigned long long l = lane_scan[r];
+    const uint32_t len = (uint32_t)(fn.read_off[r + 1] - fn.read_off[r]);
+    const uint32_t pc = native_pieces(len, fn.lane_syms);
+    if (fn.first_piece_opens(r)) {
+        lane_first[l] = (uint32_t)r;
+        lane_sym[l] = fn.read_off[r];
+        l++;
+    }
+    for (uint32_t j = 1; j < pc; j++, l++) {
+        lane_first[l] = (uint32_t)r;
+        lane_sym[l] = fn.read_off[r] + (unsigned long long)j * fn.lane_syms;
+    }
 }
 
-// per-lane model choice: argmin over the candidates of a type of the summed forward scores of the lane's reads
-// (first minimum wins, as everywhere in the reference's choosers); one thread per (lane, type)
+// per-lane model choice: argmin over the candidates of a type of the summed forward scores of the reads that have a symbol
+// in the lane (first minimum wins, as everywhere in the reference's choosers); one thread per (lane, type)
 __global__ void __launch_bounds__(128)
 lane_choose_kernel(const uint32_t* __restrict__ sizes, uint32_t n_cols, const uint32_t* __restrict__ cand_cols,
                    const uint32_t* __restrict__ n_cand2, const uint32_t* __restrict__ has_sizes,
-                   const uint32_t* __restrict__ lane_first, const unsigned long long* __restrict__ n_lanes_dev, uint64_t lane_cap,
-                   uint8_t* __restrict__ lane_choice /*[2][lane_cap]*/) {
+                   const uint32_t* __restrict__ lane_first, const unsigned long long* __restrict__ lane_sym,
+                   const uint64_t* __restrict__ read_off, uint64_t n_reads, const unsigned long long* __restrict__ n_lanes_dev,
+                   uint64_t lane_cap, uint8_t* __restrict__ lane_choice /*[2][lane_cap]*/) {
     uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     uint64_t l = t >> 1;
     uint32_t type = (uint32_t)t & 1;
     if (l >= *n_lanes_dev) return;
     uint32_t best = 0;
     if (has_sizes[type]) {
+        const unsigned long long a = lane_sym[l], b = lane_sym[l + 1];
         unsigned long long best_sum = ~0ull;
         for (uint32_t k = 0; k < n_cand2[type]; k++) {
             uint32_t col = cand_cols[type * kMaxCand + k];
             unsigned long long sum = 0;
-            for (uint64_t r = lane_first[l]; r < lane_first[l + 1]; r++) sum += sizes[r * n_cols + col];
+            for (uint64_t r = lane_first[l]; r < n_reads && read_off[r] < b; r++)
+                if (read_off[r + 1] > a) sum += sizes[r * n_cols + col];
             if (sum < best_sum) {
                 best_sum = sum;
                 best = k;
@@ -91,22 +131,29 @@ struct EncodeLaneArgs {
     const uint8_t* quals;
     uint64_t n_symbols;
     const uint64_t* read_off;
-    const uint32_t* lane_first;   // [n_lanes+1]
+    uint64_t n_reads;
+    const uint32_t* lane_first;   // [n_lanes+1] read the lane starts in
+    const unsigned long long* lane_sym;  // [n_lanes+1] absolute offset of the lane's first symbol
     const unsigned long long* n_lanes_dev;
     uint64_t lane_cap;            // stride of the [2][lane_cap] arrays
     const uint8_t* lane_choice;   // [2][lane_cap] candidate index per type, or nullptr (single pair)
     const int32_t* cand_model;    // [2][kMaxCand] candidate -> models[] index
-    uint8_t* scratch;             // slot of lane l ends at 4*read_off[lane_first[l+1]] + 8*(l+1)
+    uint8_t* scratch;             // slot of lane l ends at 4 * lane_sym[l+1] + kLaneSlotExtra * (l+1)
     uint32_t* lane_len;           // [n_lanes]
     uint32_t* err;
 };
+constexpr unsigned long long kLaneSlotExtra = 8 + kNativeHistBytes;  // two flushed states + the history of a lane that starts inside a read
 
+#ifndef IDN_LANE_MINB
+#define IDN_LANE_MINB 8
+#endif
 template <bool kUniform, class P>
-__global__ void __launch_bounds__(128, kUniform ? IDN_ENC_MINB : 1)
+__global__ void __launch_bounds__(128, kUniform ? IDN_LANE_MINB : 1)
 encode_lane_kernel(EncodeLaneArgs A, const ModelDev MA, const ModelDev MQ) {
     uint64_t l = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (l >= *A.n_lanes_dev) return;
-    const uint32_t r0 = A.lane_first[l], r1 = A.lane_first[l + 1];
+    const unsigned long long a = A.lane_sym[l], b = A.lane_sym[l + 1];
+    const uint64_t r_lo = A.lane_first[l];
     int32_t ia = 0, iq = 0;
     if (!kUniform) {
         ia = A.cand_model[A.lane_choice ? A.lane_choice[l] : 0];
@@ -115,14 +162,34 @@ encode_lane_kernel(EncodeLaneArgs A, const ModelDev MA, const ModelDev MQ) {
     const ModelDev& ma = kUniform ? MA : A.models[ia];
     const ModelDev& mq = kUniform ? MQ : A.models[iq];
     EncStream S;
-    S.begin(A.scratch + 4ull * A.read_off[r1] + 8ull * (l + 1));
+    S.begin(A.scratch + 4ull * b + kLaneSlotExtra * (l + 1));
+    if (b > a) {
+        // the last read with a symbol in the lane, then down to the first
+        uint64_t r = A.lane_first[l + 1] < A.n_reads ? A.lane_first[l + 1] : A.n_reads - 1;
+        while (r > r_lo && A.read_off[r] >= b) r--;
 #pragma unroll 1
-    for (uint32_t r = r1; r-- > r0;) {
-        const long long off = (long long)A.read_off[r];
-        const uint32_t len = (uint32_t)(A.read_off[r + 1] - A.read_off[r]);
-        encode_read_body<P>(ma, mq, A.acids, A.quals, A.n_symbols, off, len, S);
+        for (;; r--) {
+            const unsigned long long ro = A.read_off[r], re = A.read_off[r + 1];
+            if (re > a && ro < b) {
+                const uint32_t p0 = (uint32_t)((a > ro ? a : ro) - ro), p1 = (uint32_t)((b < re ? b : re) - ro);
+                encode_read_body<P>(ma, mq, A.acids, A.quals, A.n_symbols, (long long)ro, (uint32_t)(re - ro), p0, p1, S);
+            }
+            if (r == r_lo) break;
+        }
     }
-    S.flush();
+    S.flush_states();
+    if (b > a && a > A.read_off[r_lo]) {
+        // the lane starts inside a read: the symbols of the kHist positions in front of it go in front of the stream, acids
+        // then quality scores in position order (the writer walks down: last word first)
+        const uint8_t* ha = A.acids + a - kHist;
+        const uint8_t* hq = A.quals + a - kHist;
+        auto word = [](const uint8_t* p) { return (uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16) | ((uint32_t)p[3] << 24); };
+        S.out.push_u32_le(word(hq + 4));
+        S.out.push_u32_le(word(hq));
+        S.out.push_u32_le(word(ha + 4));
+        S.out.push_u32_le(word(ha));
+    }
+    S.out.finish();
     A.lane_len[l] = S.total();
     if (S.bad) atomicOr(A.err, 1u);
 }
@@ -136,7 +203,8 @@ struct LaneLenFn {
 // per block: min / max read length (one CTA per block) -> len_width, and the lane range of the block
 __global__ void __launch_bounds__(256)
 native_block_info_kernel(const uint64_t* __restrict__ read_off, const uint32_t* __restrict__ block_first, uint32_t n_blocks,
-                         const unsigned long long* __restrict__ lane_scan /*[n_reads+1]*/, uint32_t* __restrict__ blk_width,
+                         const unsigned long long* __restrict__ lane_scan /*[n_reads+1]*/, uint32_t lane_syms,
+                         uint32_t* __restrict__ blk_width /* bit 7: a read of the block is cut into pieces */,
                          uint32_t* __restrict__ blk_const_len, uint32_t* __restrict__ blk_lane0 /*[n_blocks+1]*/) {
     __shared__ uint32_t s_min[256], s_max[256];
     uint32_t b = blockIdx.x;
@@ -162,7 +230,7 @@ native_block_info_kernel(const uint64_t* __restrict__ read_off, const uint32_t* 
         mn = s_min[0];
         mx = s_max[0];
         bool is_const = r1 == r0 || mn == mx;
-        blk_width[b] = is_const ? 0u : (mx < 65536u ? 2u : 4u);
+        blk_width[b] = (is_const ? 0u : (mx < 65536u ? 2u : 4u)) | ((r1 > r0 && native_pieces(mx, lane_syms) > 1) ? 0x80u : 0u);
         blk_const_len[b] = (is_const && r1 > r0) ? mn : 0u;
         blk_lane0[b] = (uint32_t)lane_scan[r0];
         if (b == n_blocks - 1) blk_lane0[n_blocks] = (uint32_t)lane_scan[r1];
@@ -184,7 +252,7 @@ native_layout_kernel(const uint32_t* __restrict__ block_first, uint32_t n_blocks
         unsigned long long pre = prefix_len ? prefix_len[b] : 0;
         unsigned long long length = pre;
         if (n_reads)
-            length += kNativeHdrFixed + n_reads * blk_width[b] + n_lanes * 6 + (lane_off[blk_lane0[b + 1]] - lane_off[blk_lane0[b]]);
+            length += kNativeHdrFixed + n_reads * (blk_width[b] & 0x7fu) + n_lanes * 6 + (lane_off[blk_lane0[b + 1]] - lane_off[blk_lane0[b]]);
         if (pos + 8 <= out_cap) store_u32be(out + pos, (uint32_t)length);
         pos += 8 + length;
     }
@@ -202,6 +270,7 @@ struct NativeAssembleArgs {
     const uint32_t* blk_const_len;
     const uint32_t* blk_lane0;
     const uint32_t* lane_first;
+    const unsigned long long* lane_sym;
     const uint32_t* lane_len;
     const unsigned long long* lane_off;
     const uint8_t* lane_choice;   // [2][lane_cap] or nullptr
@@ -223,7 +292,7 @@ native_header_kernel(NativeAssembleArgs A) {
     const uint32_t n_reads = (uint32_t)(r1 - r0);
     if (n_reads == 0) return;
     const uint32_t l0 = A.blk_lane0[b], l1 = A.blk_lane0[b + 1], n_lanes = l1 - l0;
-    const uint32_t w = A.blk_width[b];
+    const uint32_t w = A.blk_width[b] & 0x7fu;
     const unsigned long long pay = A.lane_off[l1] - A.lane_off[l0];
     const unsigned long long body = kNativeHdrFixed - 5 + (unsigned long long)n_reads * w + 6ull * n_lanes + pay;
     unsigned long long base = A.block_off[b] + 8 + (A.prefix_len ? A.prefix_len[b] : 0);
@@ -235,7 +304,7 @@ native_header_kernel(NativeAssembleArgs A) {
         store_u32be(p + 5, n_reads);
         store_u32be(p + 9, n_lanes);
         store_u32be(p + 13, A.lane_syms);
-        p[17] = (uint8_t)w;
+        p[17] = (uint8_t)A.blk_width[b];
         store_u32be(p + 18, A.blk_const_len[b]);
     }
     uint8_t* t_len = p + kNativeHdrFixed;
@@ -269,10 +338,10 @@ native_copy_kernel(NativeAssembleArgs A, const uint8_t* __restrict__ scratch, co
     const uint32_t n_reads = A.block_first[b + 1] - A.block_first[b];
     const uint32_t l0 = A.blk_lane0[b], n_lanes = A.blk_lane0[b + 1] - l0;
     unsigned long long dst = A.block_off[b] + 8 + (A.prefix_len ? A.prefix_len[b] : 0) + kNativeHdrFixed +
-                             (unsigned long long)n_reads * A.blk_width[b] + 6ull * n_lanes + (A.lane_off[l] - A.lane_off[l0]);
+                             (unsigned long long)n_reads * (A.blk_width[b] & 0x7fu) + 6ull * n_lanes + (A.lane_off[l] - A.lane_off[l0]);
     const uint32_t n = A.lane_len[l];
     if (dst + n > A.out_cap) return;
-    const uint8_t* src = scratch + 4ull * A.read_off[A.lane_first[l + 1]] + 8ull * (l + 1) - n;
+    const uint8_t* src = scratch + 4ull * A.lane_sym[l + 1] + kLaneSlotExtra * (l + 1) - n;
     uint8_t* d = A.out + dst;
     // head bytes up to a 4-byte boundary of the destination, then words assembled from two aligned source words
     uint32_t head = (uint32_t)((4 - (reinterpret_cast<uintptr_t>(d) & 3)) & 3);
@@ -305,6 +374,7 @@ __global__ void lane_block_kernel(const uint32_t* __restrict__ blk_lane0, uint32
 struct NativeBlockHdr {  // what the header kernel leaves per block
     unsigned long long tab;  // absolute offset of the read length table in `blocks`
     uint32_t n_reads, n_lanes, lane_syms, width, const_len;
+    uint32_t split;          // bit 7 of len_width: some read of the block is cut into pieces
 };
 
 // one warp per block: find the NativeLanes slice, validate its framing, count symbols
@@ -313,13 +383,13 @@ native_hdr_kernel(const uint8_t* __restrict__ blocks, const unsigned long long* 
                   const uint32_t* __restrict__ block_len, uint32_t n_blocks, unsigned long long blocks_bytes, uint32_t n_models,
                   const uint8_t* __restrict__ model_type, NativeBlockHdr* __restrict__ hdr,
                   unsigned long long* __restrict__ blk_reads, unsigned long long* __restrict__ blk_syms,
-                  unsigned long long* __restrict__ blk_lanes, int32_t* __restrict__ status) {
+                  unsigned long long* __restrict__ blk_lanes, int32_t* __restrict__ status, uint32_t* __restrict__ split_flag) {
     const uint32_t b = blockIdx.x, lane = threadIdx.x;
     if (b >= n_blocks) return;
     const unsigned long long boff = block_off[b];
     const unsigned long long n = block_len ? block_len[b] : block_off[b + 1] - boff;
     int32_t st = 0;
-    NativeBlockHdr h{0, 0, 0, 0, 0, 0};
+    NativeBlockHdr h{0, 0, 0, 0, 0, 0, 0};
     if (boff > blocks_bytes || n > blocks_bytes - boff) st = 3;
     const uint8_t* p = blocks + boff;
     unsigned long long pos = 0, body_end = 0;
@@ -339,12 +409,14 @@ native_hdr_kernel(const uint8_t* __restrict__ blocks, const unsigned long long* 
                 h.n_reads = load_u32be(p + pos + 5);
                 h.n_lanes = load_u32be(p + pos + 9);
                 h.lane_syms = load_u32be(p + pos + 13);
-                h.width = p[pos + 17];
+                h.width = p[pos + 17] & 0x7fu;
+                h.split = p[pos + 17] >> 7;
                 h.const_len = load_u32be(p + pos + 18);
                 h.tab = boff + pos + kNativeHdrFixed;
                 body_end = pos + 5 + body;
                 unsigned long long need = kNativeHdrFixed - 5 + (unsigned long long)h.n_reads * h.width + 6ull * h.n_lanes;
-                if ((h.width != 0 && h.width != 2 && h.width != 4) || h.lane_syms == 0 || need > body || h.n_lanes > h.n_reads ||
+                if ((h.width != 0 && h.width != 2 && h.width != 4) || h.lane_syms == 0 || need > body ||
+                    (!h.split && h.n_lanes > h.n_reads) || (h.split && h.lane_syms < kNativeMinSplitQ) ||
                     (h.n_reads > 0) != (h.n_lanes > 0)) { st = 3; break; }
                 found = true;
                 pos = body_end;
@@ -359,6 +431,7 @@ native_hdr_kernel(const uint8_t* __restrict__ blocks, const unsigned long long* 
     h.n_lanes = __shfl_sync(0xffffffffu, h.n_lanes, 0);
     h.width = __shfl_sync(0xffffffffu, h.width, 0);
     h.const_len = __shfl_sync(0xffffffffu, h.const_len, 0);
+    h.split = __shfl_sync(0xffffffffu, h.split, 0);
     h.lane_syms = __shfl_sync(0xffffffffu, h.lane_syms, 0);
     h.tab = __shfl_sync(0xffffffffu, h.tab, 0);
     body_end = __shfl_sync(0xffffffffu, body_end, 0);
@@ -379,7 +452,7 @@ native_hdr_kernel(const uint8_t* __restrict__ blocks, const unsigned long long* 
             pay += ll;
             uint32_t ma = t_mdl[2 * i], mq = t_mdl[2 * i + 1];
             if (ma >= n_models || mq >= n_models || model_type[ma] != 0 || model_type[mq] != 1) bad = true;
-            if (ll < 8) short_lane = true;  // a lane holds at least its two flushed states
+            if (ll < 8) short_lane = true;  // a lane holds at least its two flushed states (the decoder checks the history bytes)
         }
         for (int d = 16; d > 0; d >>= 1) {
             syms += __shfl_down_sync(0xffffffffu, syms, d);
@@ -396,6 +469,7 @@ native_hdr_kernel(const uint8_t* __restrict__ blocks, const unsigned long long* 
     }
     if (lane == 0) {
         hdr[b] = h;
+        if (st == 0 && h.split) atomicOr(split_flag, 1u);
         blk_reads[b] = st == 0 ? h.n_reads : 0;
         blk_syms[b] = st == 0 ? syms : 0;
         blk_lanes[b] = st == 0 ? h.n_lanes : 0;
@@ -407,15 +481,17 @@ native_hdr_kernel(const uint8_t* __restrict__ blocks, const unsigned long long* 
 }
 
 struct NativeIndex {  // per lane, global lane numbering
-    unsigned long long* pay_off;   // absolute offset of the lane payload in `blocks`
+    unsigned long long* pay_off;     // absolute offset of the lane payload in `blocks`
     uint32_t* pay_len;
-    unsigned long long* first_read;  // [n_lanes + 1]  global read index
+    unsigned long long* first_read;  // [n_lanes + 1]  global index of the read the lane starts in
+    unsigned long long* sym_start;   // [n_lanes + 1]  absolute offset of the lane's first symbol in the output
     uint8_t* am;
     uint8_t* qm;
+    unsigned long long cap;          // entries the arrays hold
 };
 
-// one CTA per block: read offsets (scan of the lengths), lane partition (recomputed from the offsets), lane payload
-// offsets (scan of the lane lengths).  Sequential tiles of 256 with a running carry.
+// one CTA per block: read offsets (scan of the lengths), lane partition (recomputed from the lengths: pieces, quanta),
+// lane payload offsets (scan of the lane lengths).  Sequential tiles of 256 with a running carry.
 __global__ void __launch_bounds__(256)
 native_fill_kernel(const uint8_t* __restrict__ blocks, const NativeBlockHdr* __restrict__ hdr, uint32_t n_blocks,
                    const unsigned long long* __restrict__ blk_read_base, const unsigned long long* __restrict__ blk_sym_base,
@@ -430,16 +506,25 @@ native_fill_kernel(const uint8_t* __restrict__ blocks, const NativeBlockHdr* __r
     if (threadIdx.x == 0) s_status = status[0];
     __syncthreads();
     if (s_status != 0) return;
+    if (blk_lane_base[n_blocks] + 1 > ix.cap) {  // more lanes than the index holds: refuse (uniform over the launch)
+        if (b == 0 && threadIdx.x == 0) {
+            int old = atomicCAS(&status[0], 0, 11);  // IDN_E_NOSPACE
+            if (old == 0) status[1] = -1;
+        }
+        return;
+    }
     if (b == n_blocks) {  // terminators
         if (threadIdx.x == 0) {
             block_first[n_blocks] = (uint32_t)blk_read_base[n_blocks];
             read_off_out[blk_read_base[n_blocks]] = blk_sym_base[n_blocks];
             ix.first_read[blk_lane_base[n_blocks]] = blk_read_base[n_blocks];
+            ix.sym_start[blk_lane_base[n_blocks]] = blk_sym_base[n_blocks];
         }
         return;
     }
     const NativeBlockHdr h = hdr[b];
     const unsigned long long rbase = blk_read_base[b], sbase = blk_sym_base[b], lbase = blk_lane_base[b];
+    const uint32_t Q = h.lane_syms;
     if (threadIdx.x == 0) {
         block_first[b] = (uint32_t)rbase;
         lane_mismatch = 0;
@@ -449,10 +534,12 @@ native_fill_kernel(const uint8_t* __restrict__ blocks, const NativeBlockHdr* __r
     const uint8_t* t_mdl = t_len + (size_t)h.n_reads * h.width;
     const uint8_t* t_ll = t_mdl + 2ull * h.n_lanes;
     const unsigned long long pay0 = h.tab + (unsigned long long)h.n_reads * h.width + 6ull * h.n_lanes;
-    // reads: offsets + lane starts.  A read opens a lane when its offset quantum differs from its predecessor's.
-    unsigned long long carry = 0;      // symbols before this tile
-    unsigned long long lane_carry = 0; // lanes opened before this tile
-    unsigned long long prev_q_carry = 0;  // quantum of the last read of the previous tile
+    // reads: offsets + the lanes they open.  The first piece of a read opens a lane when its quantum differs from the
+    // quantum of the piece before it (the LAST piece of the read before); every further piece opens one.
+    unsigned long long carry = 0;         // symbols before this tile
+    unsigned long long lane_carry = 0;    // lanes opened before this tile
+    unsigned long long prev_q_carry = 0;  // quantum of the last piece of the last read of the previous tile
+    bool any_cut = false;
     for (uint32_t base = 0; base < h.n_reads; base += kScanBlock) {
         uint32_t i = base + threadIdx.x;
         unsigned long long len = 0;
@@ -463,27 +550,44 @@ native_fill_kernel(const uint8_t* __restrict__ blocks, const NativeBlockHdr* __r
         unsigned long long off = carry + ex;  // block-relative symbol offset of read i
         unsigned long long tile_syms = total;
         __syncthreads();
-        // quantum of the predecessor: the previous thread's (off), or the carried one for the first thread of the tile
-        unsigned long long q = off / h.lane_syms;
-        unsigned long long pq = __shfl_up_sync(0xffffffffu, q, 1);
+        const uint32_t pc = native_pieces((uint32_t)len, Q);
+        any_cut = any_cut || pc > 1;
+        const unsigned long long q_first = off / Q, q_last = (off + (unsigned long long)(pc - 1) * Q) / Q;
+        // quantum of the piece before: the previous thread's last piece, or the carried one for the first thread of the tile
+        unsigned long long pq = __shfl_up_sync(0xffffffffu, q_last, 1);
         __shared__ unsigned long long warp_last_q[kScanBlock / 32];
-        if ((threadIdx.x & 31) == 31) warp_last_q[threadIdx.x >> 5] = q;
+        if ((threadIdx.x & 31) == 31) warp_last_q[threadIdx.x >> 5] = q_last;
         __syncthreads();
         if ((threadIdx.x & 31) == 0) pq = threadIdx.x == 0 ? prev_q_carry : warp_last_q[(threadIdx.x >> 5) - 1];
-        unsigned long long flag = 0;
-        if (i < h.n_reads) flag = (i == 0) || (q != pq);
-        unsigned long long lex = block_exclusive_scan(flag, &total, smem);
+        const bool opens = i < h.n_reads && ((i == 0) || (q_first != pq));
+        unsigned long long cnt = 0;
+        if (i < h.n_reads) cnt = (opens ? 1u : 0u) + pc - 1;
+        unsigned long long lex = block_exclusive_scan(cnt, &total, smem);
         unsigned long long tile_lanes = total;
         if (i < h.n_reads) {
             read_off_out[rbase + i] = sbase + off;
-            if (flag) {
-                unsigned long long l = lane_carry + lex;
-                if (l < h.n_lanes) ix.first_read[lbase + l] = rbase + i; else lane_mismatch = 1;
+            unsigned long long l = lane_carry + lex;
+            if (opens) {
+                if (l < h.n_lanes) {
+                    ix.first_read[lbase + l] = rbase + i;
+                    ix.sym_start[lbase + l] = sbase + off;
+                } else {
+                    lane_mismatch = 1;
+                }
+                l++;
+            }
+            for (uint32_t j = 1; j < pc; j++, l++) {
+                if (l < h.n_lanes) {
+                    ix.first_read[lbase + l] = rbase + i;
+                    ix.sym_start[lbase + l] = sbase + off + (unsigned long long)j * Q;
+                } else {
+                    lane_mismatch = 1;
+                }
             }
         }
-        // carry the quantum of the last read of this tile
+        // carry the quantum of the last piece of the last read of this tile
         __shared__ unsigned long long last_q;
-        if (threadIdx.x == kScanBlock - 1) last_q = q;
+        if (threadIdx.x == kScanBlock - 1) last_q = q_last;
         __syncthreads();
         prev_q_carry = last_q;
         carry += tile_syms;
@@ -491,6 +595,7 @@ native_fill_kernel(const uint8_t* __restrict__ blocks, const NativeBlockHdr* __r
         __syncthreads();
     }
     if (threadIdx.x == 0 && lane_carry != h.n_lanes) lane_mismatch = 1;
+    if (__syncthreads_or(any_cut) != (int)(h.split != 0) && threadIdx.x == 0) lane_mismatch = 1;  // the flag must tell the truth
     // lanes: payload offsets + models
     unsigned long long pcarry = 0;
     for (uint32_t base = 0; base < h.n_lanes; base += kScanBlock) {
@@ -521,6 +626,8 @@ struct DecodeLaneArgs {
     const unsigned long long* n_lanes_dev;
     const unsigned long long* read_off;  // [n_reads+1] absolute symbol offsets (native_fill_kernel)
     const int32_t* status;
+    const uint32_t* split_flag;  // some block of the call cuts reads into pieces: the per-read CRC partials come from a pass
+                                 // over the output instead (crc_read kernels), a read's symbols being decoded by several threads
     uint8_t* acids_out;
     uint8_t* quals_out;
     long long out_dq;  // quals_out - acids_out
@@ -533,45 +640,57 @@ struct DecodeLaneArgs {
 };
 
 template <bool kUniform, class P>
-__global__ void __launch_bounds__(128, kUniform ? IDN_DEC_MINB : 1)
+__global__ void __launch_bounds__(128, kUniform ? IDN_LANE_MINB : 1)
 decode_lane_kernel(DecodeLaneArgs A, const ModelDev MA, const ModelDev MQ) {
     __shared__ uint32_t s_tab[256];
     __shared__ uint32_t s_xpow[64];
-    uint64_t l = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (A.status[0] != 0) return;
     DecCrc C{nullptr, 0xffffffffu, 0xffffffffu};
-    if (A.part_crc) {
+    if (A.part_crc && *A.split_flag == 0) {
         for (int i = threadIdx.x; i < 256; i += blockDim.x) s_tab[i] = A.crc_tab[i];
         for (int i = threadIdx.x; i < 64; i += blockDim.x) s_xpow[i] = A.xpow[i];
         __syncthreads();
         C.tab = s_tab;
     }
-    if (l >= *A.n_lanes_dev) return;
-    const ModelDev& ma = kUniform ? MA : A.models[A.model_ids[A.ix.am[l]]];
-    const ModelDev& mq = kUniform ? MQ : A.models[A.model_ids[A.ix.qm[l]]];
-    const unsigned long long r0 = A.ix.first_read[l], r1 = A.ix.first_read[l + 1];
-    DecStream D;
-    D.begin(A.payload, A.ix.pay_off[l], A.ix.pay_len[l]);
-    SymWriter O;
-    unsigned long long o = A.read_off[r0];
-    O.init(A.acids_out + o, A.out_dq);
+    const unsigned long long n_lanes = *A.n_lanes_dev;
+    // (grid-stride: a call whose blocks cut long reads into pieces may hold more lanes than the launch has threads)
 #pragma unroll 1
-    for (unsigned long long r = r0; r < r1; r++) {
-        unsigned long long o_next = A.read_off[r + 1];
-        const uint32_t len = (uint32_t)(o_next - o);
-        decode_read_body<P>(ma, mq, len, D, O, C);
-        if (A.part_crc) {
-            const CrcPair p = crc_concat(CrcPair{~C.ca, len}, CrcPair{~C.cq, len}, s_xpow);
-            A.part_crc[r] = len ? p.crc : 0u;
-            A.part_len[r] = 2ull * len;
-            C.ca = C.cq = 0xffffffffu;
+    for (unsigned long long l = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; l < n_lanes; l += (unsigned long long)gridDim.x * blockDim.x) {
+        const ModelDev& ma = kUniform ? MA : A.models[A.model_ids[A.ix.am[l]]];
+        const ModelDev& mq = kUniform ? MQ : A.models[A.model_ids[A.ix.qm[l]]];
+        const unsigned long long a = A.ix.sym_start[l], b = A.ix.sym_start[l + 1];
+        uint32_t r = (uint32_t)A.ix.first_read[l];
+        unsigned long long o = A.read_off[r];  // (first_read <= n_reads and read_off holds n_reads + 1 entries)
+        const bool mid = b > a && a > o;       // the lane starts inside read r: 16 history bytes lead the payload
+        uint32_t plen = A.ix.pay_len[l];
+        const uint8_t* pay = A.payload + A.ix.pay_off[l];
+        const bool bad = mid && plen < kNativeHistBytes + 8;
+        const uint32_t lead = (mid && !bad) ? kNativeHistBytes : 0u;
+        DecStream D;
+        D.begin(pay, lead, bad ? 0u : plen - lead);
+        SymWriter O;
+        O.init(A.acids_out + a, A.out_dq);
+        // the reads with a symbol in [a, b): the loop ends by itself at the last read (read_off[n_reads] >= b)
+#pragma unroll 1
+        for (; o < b; r++) {
+            const unsigned long long o_next = A.read_off[r + 1];
+            if (o_next > a) {
+                const uint32_t len = (uint32_t)(o_next - o);
+                const uint32_t p0 = (uint32_t)((a > o ? a : o) - o), p1 = (uint32_t)((b < o_next ? b : o_next) - o);
+                decode_read_body<P>(ma, mq, len, p0, p1, pay, D, O, C);
+                if (C.tab) {  // whole reads only (no block of the call cuts reads)
+                    const CrcPair p = crc_concat(CrcPair{~C.ca, len}, CrcPair{~C.cq, len}, s_xpow);
+                    A.part_crc[r] = len ? p.crc : 0u;
+                    A.part_len[r] = 2ull * len;
+                    C.ca = C.cq = 0xffffffffu;
+                }
+            }
+            o = o_next;
         }
-        o = o_next;
+        O.flush();
+        D.finish(pay, lead, plen - lead);
+        if (bad || (D.st & 1) || !D.clean_end(plen - lead)) atomicOr(A.err, 1u);
     }
-    O.flush();
-    const uint32_t plen = A.ix.pay_len[l];
-    D.finish(A.payload, A.ix.pay_off[l], plen);
-    if ((D.st & 1) || !D.clean_end(plen)) atomicOr(A.err, 1u);
 }
 
 }  // namespace idn

@@ -156,3 +156,43 @@ def test_native_rejects_malformed_blocks(gctx, O, toy_models, toy_handles, reads
     with pytest.raises(IdnGpuError) as e:
         decode_all(gctx, outc, boffc, crcc, toy_handles)
     assert e.value.kind == "SerializeError"
+
+
+@pytest.mark.parametrize("lane_syms", [256, 1000, 2048])
+def test_native_long_reads_are_cut_into_lanes(gctx, O, toy_models, toy_handles, lane_syms):
+    """Reads longer than the lane quantum (>= 256) are cut into pieces of lane_syms symbols, each its own lane with the
+    8-position history in front of its rANS bytes, so a long read decodes as many short chains: device == CPU statement
+    byte for byte, the decode is the identity, the block CRC (per-read, computed by a pass over the output in this case)
+    still catches a flipped payload bit, and there are more lanes than reads."""
+    from idencomp_b200.capi import IdnGpuError
+    rng = np.random.default_rng(33)
+    seqs = []
+    for i, ln in enumerate([9000, 40, 0, 256, 257, 700, 3, 12345, 90, 90, 1024, 1, 5000, 2048, 4096, 4097, 0]):
+        seqs.append((b"r%d" % i, rng.integers(0, 5, size=ln), rng.integers(0, 94, size=ln)))
+    reads = O.Reads.from_lists(seqs)
+    bf = np.asarray([0, 6, 6, 13, reads.n_reads], dtype=np.uint32)
+    gctx.set_lane_symbols(lane_syms)
+    try:
+        out, block_off, crc, _ = gctx.compress_blocks(reads.read_off, reads.acids, reads.quals, bf, toy_handles, mode=NATIVE)
+        expect = oracle_native(O, toy_models, reads, bf, lane_syms)
+        check_blocks(out, block_off, crc, expect)
+        n_lanes = sum(int.from_bytes(d[9:13], "big") for d, _ in expect if d)
+        assert n_lanes > reads.n_reads and any(d and d[17] >> 7 for d, _ in expect)
+        ro, a, q = decode_all(gctx, out, block_off, crc, toy_handles)
+        assert np.array_equal(ro, reads.read_off) and np.array_equal(a, reads.acids) and np.array_equal(q, reads.quals)
+        # per-lane model choice with cut reads (two candidates per type)
+        m2 = [O.Model(O.acid_model_prefer(1)), O.Model(O.acid_model_prefer(2))]
+        mdl = [toy_models[0], m2[0], m2[1], toy_models[1]]
+        hd = [toy_handles[0], upload(gctx, O, m2[0]), upload(gctx, O, m2[1]), toy_handles[1]]
+        out2, boff2, crc2, _ = gctx.compress_blocks(reads.read_off, reads.acids, reads.quals, bf, hd, mode=NATIVE)
+        check_blocks(out2, boff2, crc2, oracle_native(O, mdl, reads, bf, lane_syms))
+        ro, a, q = decode_all(gctx, out2, boff2, crc2, hd)
+        assert np.array_equal(a, reads.acids) and np.array_equal(q, reads.quals)
+        # a flipped bit in the middle of the payload of the last block
+        broken = out.copy()
+        broken[int(block_off[-1]) - 40] ^= 0x10
+        with pytest.raises(IdnGpuError) as e:
+            decode_all(gctx, broken, block_off, crc, toy_handles)
+        assert e.value.kind in ("BlockChecksumMismatch", "SerializeError")
+    finally:
+        gctx.set_lane_symbols(2048)

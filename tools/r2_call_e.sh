@@ -1,0 +1,13 @@
+#!/bin/bash
+# round 2, GPU call E: native format with cut reads, pipelined e2e after the validation fix
+mkdir -p gpurun_out
+( time python -m pytest tests -q -m gpu -p no:cacheprovider -x 2>&1 | tail -30 ) > gpurun_out/e_pytest.log 2>&1
+( tools/qb.sh --workload pacbio_native; tools/qb.sh --workload pacbio; tools/qb.sh --reads 12000000 --workload novaseq150_native; tools/qb.sh --reads 12000000
+  echo "== LANE_MINB=7"; IDN_NVCC_EXTRA="-DIDN_LANE_MINB=7" python -c "from idencomp_b200 import build; build.build_gpu(force=True)"
+  tools/qb.sh --workload pacbio_native; tools/qb.sh --reads 12000000 --workload novaseq150_native
+  python -c "from idencomp_b200 import build; build.build_gpu(force=True)" ) > gpurun_out/e_qb.log 2>&1
+B="python bench.py --no-extra-workloads --no-cpu-baseline --no-other-mode --no-fastq --steps 3"
+for cfg in "" "--e2e-threads 3 --e2e-chunk-blocks 32" "--e2e-threads 2" "--e2e-pipe-blocks 64"; do
+  echo "== e2e [$cfg]"; $B $cfg 2> /tmp/e.err | python -c "import json,sys; d=json.load(sys.stdin); e=d['e2e']; print('value %.1f e2e %.1f c %.1f d %.1f'%(d['value'], e['value'], e['compress_GBps'], e['decompress_GBps']))"; tail -2 /tmp/e.err
+done > gpurun_out/e_e2e.log 2>&1
+echo done
