@@ -294,7 +294,7 @@ def retained_models(env, w: dict, block_reads: int):
     return names
 
 
-def run_workload(env, args, name: str, w: dict, *, steps: int, warmup: int, main: bool):
+def run_workload(env, args, name: str, w: dict, *, steps: int, warmup: int, main: bool, shard=None, no_e2e=False, after=None):
     """One workload on this rank's GPU: device-resident leg (timed with CUDA events), optional e2e leg (host buffers),
     and for the main workload the FASTQ text leg.  Returns the raw numbers of this rank; run_gpu reduces them over ranks."""
     torch, capi, ctx = env.torch, env.capi, env.ctx
@@ -302,11 +302,14 @@ def run_workload(env, args, name: str, w: dict, *, steps: int, warmup: int, main
     rank, world = env.rank, env.world
     select = args.select if main and args.select > 1 else w.get("select", 1)
 
-    # ---- the shard of this rank (weak scaling: every rank holds the workload's read count) ----
+    # ---- the shard of this rank (weak scaling: every rank holds the workload's read count; strong scaling: `shard` =
+    # (global index of the first read, reads) of this rank's contiguous block range of ONE file) ----
     n_reads = args.reads or w["reads"]
     lo, hi = w["read_len"]
     note = None
-    if not (main and args.reads):
+    if shard is not None:
+        n_reads = shard[1]
+    elif not (main and args.reads):
         # device memory of the device-resident leg per symbol: symbols in (2) + decoded out (2) + container capacity (1.5) and
         # ~1 more for the library's workspaces of a 1024-block call and the e2e staging
         free_b, _ = torch.cuda.mem_get_info()
@@ -314,7 +317,7 @@ def run_workload(env, args, name: str, w: dict, *, steps: int, warmup: int, main
         if n_reads > fit:
             note = f"{n_reads} reads asked, {fit} fit the free device memory ({free_b / 1e9:.0f} GB)"
             n_reads = fit
-    first_index = rank * n_reads
+    first_index = shard[0] if shard is not None else rank * n_reads
     lens = read_lengths(w, n_reads, first_index)
     read_off_h = np.zeros(n_reads + 1, dtype=np.uint64)
     np.cumsum(lens, out=read_off_h[1:])
@@ -481,8 +484,9 @@ def run_workload(env, args, name: str, w: dict, *, steps: int, warmup: int, main
     if main and not args.no_fastq and rank == 0:  # row f1, timed separately: FASTQ text <-> symbols on the device
         fastq = fastq_leg(args, w, capi, torch, ctx, sp, stream, acids_d, quals_d, read_off_h, min(n_reads, 4_000_000))
 
+    extra = after(chunks, out_d, m) if after is not None else None
     e2e = None
-    if not args.no_e2e:  # the host-pointer C-ABI calls on pinned host buffers
+    if not args.no_e2e and not no_e2e:  # the host-pointer C-ABI calls on pinned host buffers
         del dec_a, dec_q  # the e2e leg decodes into host buffers; give the device memory back first (torch caches it otherwise,
         torch.cuda.empty_cache()  # and the other contexts of the e2e leg allocate with cudaMalloc)
         e2e = run_e2e(args, w, env, model_names, chunks, acids_d, quals_d, read_off_h, block_first_h, m["sizes"], fq, MODES[main_mode],
@@ -490,7 +494,7 @@ def run_workload(env, args, name: str, w: dict, *, steps: int, warmup: int, main
 
     rec = {"name": name, "w": w, "mode": main_mode, "n_reads": n_reads, "S": S, "fq": fq, "n_blocks": n_blocks, "chunks": len(chunks),
            "model_names": model_names, "select": select, "m": m, "other": other, "other_mode": other_mode, "e2e": e2e, "fastq": fastq,
-           "note": note, "steps": steps, "warmup": warmup}
+           "note": note, "steps": steps, "warmup": warmup, "extra": extra}
     del acids_d, quals_d, out_d, chunks
     torch.cuda.empty_cache()
     return rec
@@ -577,6 +581,90 @@ def sub_record(env, rec):
     return out
 
 
+def run_strong(env, args):
+    """ONE file shared by all ranks (strong scaling): the NovaSeq-shaped 50 GB workload of BASELINE.json configs[2] is cut into
+    contiguous block ranges, one per GPU (blocks are independent, compressor_block.rs:61-62); every rank compresses and
+    decompresses its range with its inputs resident in HBM; the ranks then exchange their container sizes (the offset
+    prefix sum -- the only communication of the path) and each writes its range at its offset into one file in /dev/shm,
+    which rank 0 walks from the first block header to the last.  The N-GPU == 1-GPU byte identity of such a concatenation is
+    tests/test_gpu_pipeline.py's business; here it is timed."""
+    import mmap
+    torch, dist, rank, world = env.torch, env.dist, env.rank, env.world
+    w = dict(WORKLOADS["novaseq150_native"])
+    total_reads = w["reads"]
+    per_block = max(1, BLOCK_SYMBOLS // w["read_len"][0])
+    total_blocks = -(-total_reads // per_block)
+    b0, b1 = total_blocks * rank // world, total_blocks * (rank + 1) // world
+    r0, r1 = min(total_reads, b0 * per_block), min(total_reads, b1 * per_block)
+    path = f"/dev/shm/idn_strong_{os.environ.get('MASTER_PORT', '0')}.idn"
+    res = {}
+
+    def concat(chunks, out_d, m):
+        """sizes -> offsets -> every rank writes its bytes at its offset (timed: D2H + the write into the shared file)"""
+        mine = sum(m["sizes"].values())
+        sizes = torch.zeros(world, dtype=torch.int64, device=env.dev)
+        sizes[rank] = mine
+        dist.all_reduce(sizes)
+        sizes = sizes.cpu().numpy()
+        off = int(sizes[:rank].sum())
+        total = int(sizes.sum())
+        if rank == 0:
+            with open(path, "wb") as f:
+                f.truncate(total)
+        dist.barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        with open(path, "r+b") as f:
+            mm = mmap.mmap(f.fileno(), 0)
+            dst = np.frombuffer(mm, dtype=np.uint8)
+            pos = off
+            for c in chunks:
+                n = m["sizes"][id(c)]
+                t = torch.from_numpy(dst[pos:pos + n])
+                t.copy_(out_d[c.out_base:c.out_base + n])  # D2H straight into the shared mapping
+                pos += n
+            torch.cuda.synchronize()
+            del dst, t
+            mm.close()
+        dt = time.perf_counter() - t0
+        tt = torch.tensor([dt], dtype=torch.float64, device=env.dev)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        res["concat_s"] = float(tt[0])
+        res["container_bytes"] = total
+        dist.barrier()
+        if rank == 0:  # the concatenation is one valid block sequence
+            buf = np.memmap(path, dtype=np.uint8, mode="r")
+            pos, nb = 0, 0
+            while pos < total:
+                ln = int.from_bytes(bytes(buf[pos:pos + 4]), "big")
+                pos += 8 + ln
+                nb += 1
+            res["blocks_walked"] = nb
+            res["walk_ok"] = bool(pos == total and nb == total_blocks)
+            del buf
+            os.unlink(path)
+        return None
+
+    rec = run_workload(env, args, "novaseq150_native", w, steps=args.extra_steps, warmup=3, main=False, shard=(r0, r1 - r0), no_e2e=True,
+                       after=concat)
+    # one file: the time of the slowest rank bounds the file
+    t = torch.tensor([rec["m"]["t_total"], rec["m"]["tc"], rec["m"]["td"]], dtype=torch.float64, device=env.dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    fq_total = fastq_bytes(w, total_reads, total_reads * w["read_len"][0])
+    steps = rec["steps"]
+    out = {"workload": w["desc"] + ": ONE file, contiguous block ranges over the GPUs", "scaling": "strong", "reads_total": total_reads,
+           "fastq_bytes_total": fq_total, "blocks_total": total_blocks, "blocks_of_rank0": b1 - b0 if rank == 0 else None,
+           "value": 2 * fq_total * steps / float(t[0]) / 1e9, "compress_GBps": fq_total * steps / float(t[1]) / 1e9,
+           "decompress_GBps": fq_total * steps / float(t[2]) / 1e9, "unit": "GB/s", "steps": steps,
+           "concat_ms": res.get("concat_s", 0.0) * 1e3, "container_bytes": res.get("container_bytes"),
+           "compress_plus_concat_GBps": fq_total / (float(t[1]) / steps + res.get("concat_s", 0.0)) / 1e9,
+           "blocks_walked": res.get("blocks_walked"), "concatenation_is_one_block_sequence": res.get("walk_ok"),
+           "verified_round_trip": rec["m"]["verified"],
+           "note": "device-resident per-rank timing, max over ranks; concat = D2H of every rank's range into one /dev/shm file at its "
+                   "prefix-sum offset (max over ranks), no collective on the data path"}
+    return out
+
+
 def run_gpu(args, w: dict):
     env = setup_gpu()
     rank, world = env.rank, env.world
@@ -590,6 +678,9 @@ def run_gpu(args, w: dict):
             x = run_workload(env, args, xname, dict(WORKLOADS[xname]), steps=args.extra_steps, warmup=3, main=False)
             reduce_record(env, x)
             extras[xname] = x
+    strong = None
+    if world > 1 and args.extra_workloads and not (args.acid or args.q or args.reads):
+        strong = run_strong(env, args)
     if rank == 0:
         m = rec["m"]
         cpu = None
@@ -630,6 +721,8 @@ def run_gpu(args, w: dict):
                                   "note": "this rank only, device-resident, 2 timed steps"}
         if extras:
             line["workloads"] = {k: sub_record(env, x) for k, x in extras.items()}
+        if strong:
+            line["strong_scaling"] = strong
         print(json.dumps(line))
     if env.dist is not None:
         env.dist.barrier()
