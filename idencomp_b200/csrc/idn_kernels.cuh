@@ -144,15 +144,17 @@ struct SymBackReader {
 // accumulator (oldest highest); drain() stores a word once four are there, so at most 7 may be pending before it.
 struct BackWriter {
     uint32_t* wptr;  // next word to fill is wptr[-1]
-    uint32_t* wend;
     unsigned long long acc;
     uint32_t nbits;  // pending bytes * 8
     __device__ __forceinline__ void init(uint8_t* end) {
-        wptr = wend = reinterpret_cast<uint32_t*>(end);
+        wptr = reinterpret_cast<uint32_t*>(end);
         acc = 0;
         nbits = 0;
     }
-    __device__ __forceinline__ uint32_t bytes() const { return (uint32_t)(wend - wptr) * 4u + (nbits >> 3); }
+    // bytes written so far, given the `end` the writer was started at (not kept: two registers across the hot loop)
+    __device__ __forceinline__ uint32_t bytes(const uint8_t* end) const {
+        return (uint32_t)(reinterpret_cast<const uint32_t*>(end) - wptr) * 4u + (nbits >> 3);
+    }
     // appends kbits / 8 bytes given in emission order, first emitted byte highest
     __device__ __forceinline__ void push_bits(uint32_t bytes_be, uint32_t kbits) {
         acc = (acc << kbits) | bytes_be;
@@ -411,7 +413,7 @@ struct EncStream {
         flush_states();
         out.finish();
     }
-    __device__ __forceinline__ uint32_t total() const { return out.bytes(); }  // bytes emitted so far
+    __device__ __forceinline__ uint32_t total(const uint8_t* slot_end) const { return out.bytes(slot_end); }  // bytes emitted so far
 };
 
 // Pushes the positions p1-1 .. p0 of one read onto the stream (the whole read: p0 = 0, p1 = len)
@@ -551,7 +553,7 @@ encode_kernel(EncodeArgs A, const ModelDev MA, const ModelDev MQ) {
     S.begin(A.scratch + 4ull * A.read_off[r + 1] + kSlotExtra * (r + 1));
     encode_read_body<P>(ma, mq, A.acids, A.quals, A.n_symbols, off, len, 0, len, S);
     S.flush_states();
-    const uint32_t plen = S.total();
+    const uint32_t plen = S.total(A.scratch + 4ull * A.read_off[r + 1] + kSlotExtra * (r + 1));
     A.pay_len[r] = plen;
     // the read's slices, complete, in front of the payload (the writer walks down): [01 acid idx][01 q idx] 02 u32be
     // length u32be seq_len   (data.rs:57-84, compressor_block.rs:103-110), so that assembly is one copy per read

@@ -150,10 +150,12 @@ constexpr unsigned long long kLaneSlotExtra = 8 + kNativeHistBytes;  // two flus
 template <bool kUniform, class P>
 __global__ void __launch_bounds__(128, kUniform ? IDN_LANE_MINB : 1)
 encode_lane_kernel(EncodeLaneArgs A, const ModelDev MA, const ModelDev MQ) {
-    uint64_t l = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (l >= *A.n_lanes_dev) return;
-    const unsigned long long a = A.lane_sym[l], b = A.lane_sym[l + 1];
-    const uint64_t r_lo = A.lane_first[l];
+    // (register budget: the per-position loop inside encode_read_body is what counts, so the lane bounds are re-read from
+    // memory per read instead of being kept in registers across it)
+    const uint64_t l64 = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (l64 >= *A.n_lanes_dev) return;
+    const uint32_t l = (uint32_t)l64;
+    const uint32_t r_lo = A.lane_first[l];
     int32_t ia = 0, iq = 0;
     if (!kUniform) {
         ia = A.cand_model[A.lane_choice ? A.lane_choice[l] : 0];
@@ -162,13 +164,14 @@ encode_lane_kernel(EncodeLaneArgs A, const ModelDev MA, const ModelDev MQ) {
     const ModelDev& ma = kUniform ? MA : A.models[ia];
     const ModelDev& mq = kUniform ? MQ : A.models[iq];
     EncStream S;
-    S.begin(A.scratch + 4ull * b + kLaneSlotExtra * (l + 1));
-    if (b > a) {
+    S.begin(A.scratch + 4ull * A.lane_sym[l + 1] + kLaneSlotExtra * ((unsigned long long)l + 1));
+    if (A.lane_sym[l + 1] > A.lane_sym[l]) {
         // the last read with a symbol in the lane, then down to the first
-        uint64_t r = A.lane_first[l + 1] < A.n_reads ? A.lane_first[l + 1] : A.n_reads - 1;
-        while (r > r_lo && A.read_off[r] >= b) r--;
+        uint32_t r = A.lane_first[l + 1] < A.n_reads ? A.lane_first[l + 1] : (uint32_t)A.n_reads - 1;
+        while (r > r_lo && A.read_off[r] >= A.lane_sym[l + 1]) r--;
 #pragma unroll 1
         for (;; r--) {
+            const unsigned long long a = A.lane_sym[l], b = A.lane_sym[l + 1];
             const unsigned long long ro = A.read_off[r], re = A.read_off[r + 1];
             if (re > a && ro < b) {
                 const uint32_t p0 = (uint32_t)((a > ro ? a : ro) - ro), p1 = (uint32_t)((b < re ? b : re) - ro);
@@ -178,19 +181,22 @@ encode_lane_kernel(EncodeLaneArgs A, const ModelDev MA, const ModelDev MQ) {
         }
     }
     S.flush_states();
-    if (b > a && a > A.read_off[r_lo]) {
-        // the lane starts inside a read: the symbols of the kHist positions in front of it go in front of the stream, acids
-        // then quality scores in position order (the writer walks down: last word first)
-        const uint8_t* ha = A.acids + a - kHist;
-        const uint8_t* hq = A.quals + a - kHist;
-        auto word = [](const uint8_t* p) { return (uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16) | ((uint32_t)p[3] << 24); };
-        S.out.push_u32_le(word(hq + 4));
-        S.out.push_u32_le(word(hq));
-        S.out.push_u32_le(word(ha + 4));
-        S.out.push_u32_le(word(ha));
+    {
+        const unsigned long long a = A.lane_sym[l], b = A.lane_sym[l + 1];
+        if (b > a && a > A.read_off[r_lo]) {
+            // the lane starts inside a read: the symbols of the kHist positions in front of it go in front of the stream,
+            // acids then quality scores in position order (the writer walks down: last word first)
+            const uint8_t* ha = A.acids + a - kHist;
+            const uint8_t* hq = A.quals + a - kHist;
+            auto word = [](const uint8_t* p) { return (uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16) | ((uint32_t)p[3] << 24); };
+            S.out.push_u32_le(word(hq + 4));
+            S.out.push_u32_le(word(hq));
+            S.out.push_u32_le(word(ha + 4));
+            S.out.push_u32_le(word(ha));
+        }
     }
     S.out.finish();
-    A.lane_len[l] = S.total();
+    A.lane_len[l] = S.total(A.scratch + 4ull * A.lane_sym[l + 1] + kLaneSlotExtra * ((unsigned long long)l + 1));
     if (S.bad) atomicOr(A.err, 1u);
 }
 
@@ -655,29 +661,32 @@ decode_lane_kernel(DecodeLaneArgs A, const ModelDev MA, const ModelDev MQ) {
     const unsigned long long n_lanes = *A.n_lanes_dev;
     // (grid-stride: a call whose blocks cut long reads into pieces may hold more lanes than the launch has threads)
 #pragma unroll 1
-    for (unsigned long long l = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; l < n_lanes; l += (unsigned long long)gridDim.x * blockDim.x) {
+    for (unsigned long long l64 = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; l64 < n_lanes; l64 += (unsigned long long)gridDim.x * blockDim.x) {
+        // (register budget: the per-position loop inside decode_read_body is what counts, so the lane bounds and the
+        // payload address are re-read from the index per read instead of being kept in registers across it)
+        const uint32_t l = (uint32_t)l64;
         const ModelDev& ma = kUniform ? MA : A.models[A.model_ids[A.ix.am[l]]];
         const ModelDev& mq = kUniform ? MQ : A.models[A.model_ids[A.ix.qm[l]]];
-        const unsigned long long a = A.ix.sym_start[l], b = A.ix.sym_start[l + 1];
         uint32_t r = (uint32_t)A.ix.first_read[l];
-        unsigned long long o = A.read_off[r];  // (first_read <= n_reads and read_off holds n_reads + 1 entries)
-        const bool mid = b > a && a > o;       // the lane starts inside read r: 16 history bytes lead the payload
-        uint32_t plen = A.ix.pay_len[l];
-        const uint8_t* pay = A.payload + A.ix.pay_off[l];
-        const bool bad = mid && plen < kNativeHistBytes + 8;
-        const uint32_t lead = (mid && !bad) ? kNativeHistBytes : 0u;
+        // (first_read <= n_reads and read_off holds n_reads + 1 entries)
+        const bool mid = A.ix.sym_start[l + 1] > A.ix.sym_start[l] && A.ix.sym_start[l] > A.read_off[r];  // the lane starts inside read r
+        const bool bad = mid && A.ix.pay_len[l] < kNativeHistBytes + 8;
+        const uint32_t lead = (mid && !bad) ? kNativeHistBytes : 0u;  // history bytes in front of the stream
         DecStream D;
-        D.begin(pay, lead, bad ? 0u : plen - lead);
+        D.begin(A.payload + A.ix.pay_off[l], lead, bad ? 0u : A.ix.pay_len[l] - lead);
         SymWriter O;
-        O.init(A.acids_out + a, A.out_dq);
+        O.init(A.acids_out + A.ix.sym_start[l], A.out_dq);
         // the reads with a symbol in [a, b): the loop ends by itself at the last read (read_off[n_reads] >= b)
 #pragma unroll 1
-        for (; o < b; r++) {
+        for (;; r++) {
+            const unsigned long long a = A.ix.sym_start[l], b = A.ix.sym_start[l + 1];
+            const unsigned long long o = A.read_off[r];
+            if (o >= b) break;
             const unsigned long long o_next = A.read_off[r + 1];
             if (o_next > a) {
                 const uint32_t len = (uint32_t)(o_next - o);
                 const uint32_t p0 = (uint32_t)((a > o ? a : o) - o), p1 = (uint32_t)((b < o_next ? b : o_next) - o);
-                decode_read_body<P>(ma, mq, len, p0, p1, pay, D, O, C);
+                decode_read_body<P>(ma, mq, len, p0, p1, A.payload + A.ix.pay_off[l], D, O, C);
                 if (C.tab) {  // whole reads only (no block of the call cuts reads)
                     const CrcPair p = crc_concat(CrcPair{~C.ca, len}, CrcPair{~C.cq, len}, s_xpow);
                     A.part_crc[r] = len ? p.crc : 0u;
@@ -685,11 +694,11 @@ decode_lane_kernel(DecodeLaneArgs A, const ModelDev MA, const ModelDev MQ) {
                     C.ca = C.cq = 0xffffffffu;
                 }
             }
-            o = o_next;
         }
         O.flush();
-        D.finish(pay, lead, plen - lead);
-        if (bad || (D.st & 1) || !D.clean_end(plen - lead)) atomicOr(A.err, 1u);
+        const uint32_t plen = A.ix.pay_len[l] - lead;
+        D.finish(A.payload + A.ix.pay_off[l], lead, plen);
+        if (bad || (D.st & 1) || !D.clean_end(plen)) atomicOr(A.err, 1u);
     }
 }
 
