@@ -481,8 +481,11 @@ def run_workload(env, args, name: str, w: dict, *, steps: int, warmup: int, main
     m = measure(main_mode, steps, warmup, True)
 
     fastq = None
+    e2e_file = None
     if main and not args.no_fastq and rank == 0:  # row f1, timed separately: FASTQ text <-> symbols on the device
         fastq = fastq_leg(args, w, capi, torch, ctx, sp, stream, acids_d, quals_d, read_off_h, min(n_reads, 4_000_000))
+        if not args.no_e2e:
+            e2e_file = e2e_file_leg(args, w, env, acids_d, quals_d, read_off_h, min(n_reads, args.e2e_file_reads))
 
     extra = after(chunks, out_d, m) if after is not None else None
     e2e = None
@@ -494,6 +497,7 @@ def run_workload(env, args, name: str, w: dict, *, steps: int, warmup: int, main
 
     rec = {"name": name, "w": w, "mode": main_mode, "n_reads": n_reads, "S": S, "fq": fq, "n_blocks": n_blocks, "chunks": len(chunks),
            "model_names": model_names, "select": select, "m": m, "other": other, "other_mode": other_mode, "e2e": e2e, "fastq": fastq,
+           "e2e_file": e2e_file,
            "note": note, "steps": steps, "warmup": warmup, "extra": extra}
     del acids_d, quals_d, out_d, chunks
     torch.cuda.empty_cache()
@@ -723,6 +727,8 @@ def run_gpu(args, w: dict):
             line["cpu_baseline"] = cpu
         if rec["fastq"]:
             line["fastq_text"] = rec["fastq"]
+        if rec["e2e_file"]:
+            line["e2e_file"] = rec["e2e_file"]
         if rec["other"]:
             o = rec["other"]
             line["other_mode"] = {"mode": rec["other_mode"], "compress_GBps": fq * 2 / o["tc"] / 1e9, "decompress_GBps": fq * 2 / o["td"] / 1e9,
@@ -786,6 +792,94 @@ def fastq_leg(args, w, capi, torch, ctx, sp, stream, acids_d, quals_d, read_off_
     return {"sample": f"first {n} reads, {nbytes / 1e9:.2f} GB of FASTQ text, device-resident, third of three passes",
             "format_GBps": nbytes / (ev[0].elapsed_time(ev[1]) / 1e3) / 1e9, "parse_GBps": nbytes / (ev[2].elapsed_time(ev[3]) / 1e3) / 1e9,
             "verified_round_trip": ok}
+
+
+def e2e_file_leg(args, w, env, acids_d, quals_d, read_off_h, n):
+    """FASTQ TEXT in host memory -> .idn bytes in host memory -> FASTQ text in host memory, through the host mirror of the
+    reference API (IdnCompressor::add_fastq_text / IdnDecompressor::next_fastq_text, csrc/host/idn.cpp): the text is uploaded
+    once, split into records and blocks and compressed on the device; the identifiers go through the host's Deflate.  Timed
+    with and without identifiers (north_star: the name codec stays on the host and is timed separately), on the first n
+    reads of the workload with synthetic titles.  Wall clock of the calls, everything included."""
+    import zlib
+    from concurrent.futures import ThreadPoolExecutor
+    torch, capi, host, ctx = env.torch, env.capi, env.host, env.ctx
+    L, dev, sp = ctx.L, env.dev, env.sp
+    S = int(read_off_h[n])
+    ro_d = torch.from_numpy(read_off_h[:n + 1].view(np.int64)).to(dev)
+    idx = torch.arange(n, dtype=torch.int64, device=dev)
+    digits = torch.stack([(idx // 10 ** k) % 10 for k in range(11, -1, -1)], dim=1).to(torch.uint8) + 48
+    tail = torch.tensor(list(b" 1:N:0"), dtype=torch.uint8, device=dev).expand(n, -1)
+    head = torch.full((n, 1), ord("r"), dtype=torch.uint8, device=dev)
+    names_d = torch.cat([head, digits, tail], dim=1).contiguous().view(-1)
+    nlen = 1 + 12 + 6
+    no_d = (torch.arange(n + 1, dtype=torch.int64, device=dev) * nlen).contiguous()
+    b = capi.Batch()
+    b.n_reads, b.n_symbols, b.n_blocks = n, S, 0
+    b.acids, b.quals, b.read_off = acids_d.data_ptr(), quals_d.data_ptr(), ro_d.data_ptr()
+    b.names, b.name_off = names_d.data_ptr(), no_d.data_ptr()
+    cap = 2 * S + n * (6 + nlen) + 64
+    text_d = torch.empty(cap, dtype=torch.uint8, device=dev)
+    n_out = torch.zeros(1, dtype=torch.int64, device=dev)
+    ctx.check(L.idn_gpu_fastq_format_dev(ctx.h, C.byref(b), 0, text_d.data_ptr(), cap, n_out.data_ptr(), sp))
+    torch.cuda.synchronize()
+    nbytes = int(n_out.item())
+    text_h = torch.empty(nbytes, dtype=torch.uint8, pin_memory=True)
+    text_h.copy_(text_d[:nbytes])
+    torch.cuda.synchronize()
+    text_np = text_h.numpy()
+    names_h = names_d.cpu().numpy()
+    del text_d, names_d, digits
+    torch.cuda.empty_cache()
+    models = [host.Model.load(MODELS / (w["acid"] + ".msgpack")), host.Model.load(MODELS / (w["q"] + ".msgpack"))]
+    cores = os.cpu_count() or 1
+    out = {"sample": f"first {n} reads as {nbytes / 1e9:.2f} GB of FASTQ text (titles of {nlen} bytes), page-locked host memory in, host memory out",
+           "host_threads_for_identifiers": cores}
+    for names in (False, True):
+        best = None
+        for it in range(2):  # the second pass is the timed one (buffers of the contexts are sized by the first)
+            c = host.IdnCompressor(models, include_identifiers=names, thread_num=cores, devices=[env.local, env.local],
+                                   text_chunk_bytes=args.text_chunk_mb << 20, batch_blocks=32)
+            t0 = time.perf_counter()
+            c.add_fastq_text(text_np)
+            c.finish()
+            t1 = time.perf_counter()
+            idn = c.output_view()
+            t2 = time.perf_counter()
+            back, free = host.decompress_text(models, idn, device=env.local, thread_num=cores, batch_blocks=32, as_view=True)
+            t3 = time.perf_counter()
+            if names:
+                ok = back.size == nbytes and bool(np.array_equal(back, text_np))
+            else:  # empty titles: compare the symbol lines
+                ok = back.size == nbytes - n * nlen
+            n_idn = int(idn.size)
+            free()
+            c.close()
+            best = (t1 - t0, t3 - t2, n_idn, ok)
+        tc, td, n_idn, ok = best
+        if not ok:
+            raise SystemExit("e2e_file: the text that came back differs from the text that went in")
+        out["with_identifiers" if names else "no_identifiers"] = {
+            "compress_GBps": nbytes / tc / 1e9, "decompress_GBps": nbytes / td / 1e9, "value": 2 * nbytes / (tc + td) / 1e9,
+            "container_bytes": n_idn, "verified_round_trip": ok}
+    # the identifiers codec alone, as the host mirror runs it: raw Deflate level 6 per block on `cores` threads
+    per_block = max(1, BLOCK_SYMBOLS // int(read_off_h[1] - read_off_h[0])) if n else 1
+    blocks = [b"\n".join(bytes(names_h[r * nlen:(r + 1) * nlen]) for r in range(b0, min(n, b0 + per_block))) for b0 in range(0, min(n, 16 * per_block), per_block)]
+    raw = sum(len(x) for x in blocks)
+
+    def deflate(x):
+        z = zlib.compressobj(6, zlib.DEFLATED, -15)
+        return z.compress(x) + z.flush()
+    with ThreadPoolExecutor(cores) as ex:
+        t0 = time.perf_counter()
+        zs = list(ex.map(deflate, blocks))
+        t1 = time.perf_counter()
+        back = list(ex.map(lambda z: zlib.decompress(z, -15), zs))
+        t2 = time.perf_counter()
+    assert back == blocks
+    out["identifiers_codec_alone"] = {"names_deflate_GBps": raw / (t1 - t0) / 1e9, "names_inflate_GBps": raw / (t2 - t1) / 1e9,
+                                      "threads": cores, "sample_bytes": raw, "ratio": sum(len(z) for z in zs) / max(raw, 1),
+                                      "note": "zlib level 6 raw Deflate per block (the reference uses flate2/miniz_oxide at its default level)"}
+    return out
 
 
 def cpu_baseline(args, w: dict) -> dict:
@@ -994,6 +1088,8 @@ def main():
     ap.add_argument("--e2e-chunk-blocks", type=int, default=0, help="blocks per host-pointer call in the e2e leg (default: all of a thread's blocks in one call)")
     ap.add_argument("--e2e-pipe-blocks", type=int, default=0, help="blocks per sub-chunk of the pipeline inside a call (default: 32, more for long reads)")
     ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--e2e-file-reads", type=int, default=8_000_000, help="reads of the FASTQ-text-in / text-out leg through the host mirror")
+    ap.add_argument("--text-chunk-mb", type=int, default=256, help="FASTQ text per device call of that leg")
     ap.add_argument("--e2e-profile", action="store_true", help="print the host-side phase times of the e2e leg to stderr")
     args = ap.parse_args()
     if args.warmup < 3:

@@ -32,7 +32,8 @@ EXPORTS = [
     "idn_gpu_decompress_blocks", "idn_gpu_decompress_blocks_dev", "idn_gpu_decompress_reads", "idn_gpu_block_crc",
     "idn_gpu_synth_reads_dev", "idn_gpu_profile", "idn_gpu_profile_read", "idn_gpu_set_lane_symbols", "idn_gpu_set_walk",
     "idn_gpu_fastq_parse", "idn_gpu_fastq_parse_dev", "idn_gpu_fastq_fetch", "idn_gpu_fastq_batch_dev", "idn_gpu_fastq_format",
-    "idn_gpu_fastq_format_dev",
+    "idn_gpu_fastq_format_dev", "idn_gpu_fastq_parse_chunk", "idn_gpu_fastq_chunk_fetch", "idn_gpu_compress_parsed",
+    "idn_gpu_decompress_to_fastq",
 ]
 
 
@@ -63,6 +64,11 @@ class IndexTotals(C.Structure):
 class FastqInfo(C.Structure):
     _fields_ = [("n_reads", C.c_uint64), ("n_symbols", C.c_uint64), ("n_name_bytes", C.c_uint64), ("n_lines", C.c_uint64),
                 ("error_kind", C.c_int32), ("reserved", C.c_int32), ("bad_record", C.c_uint64)]
+
+
+class FastqChunk(C.Structure):
+    _fields_ = [("n_reads", C.c_uint64), ("n_symbols", C.c_uint64), ("n_name_bytes", C.c_uint64), ("n_blocks", C.c_uint32),
+                ("error_kind", C.c_int32), ("bad_record", C.c_uint64), ("consumed_text", C.c_uint64)]
 
 
 FASTQ_ERRORS = {1: "InvalidFormat", 2: "InvalidAcid", 3: "InvalidQualityScore", 4: "AcidAndQualityScoreLengthMismatch",
@@ -142,6 +148,15 @@ def load():
     L.idn_gpu_fastq_format.restype = i32
     L.idn_gpu_fastq_format_dev.argtypes = [vp, C.POINTER(Batch), i32, vp, u64, vp, vp]
     L.idn_gpu_fastq_format_dev.restype = i32
+    L.idn_gpu_fastq_parse_chunk.argtypes = [vp, vp, u64, i32, u32, C.POINTER(FastqChunk)]
+    L.idn_gpu_fastq_parse_chunk.restype = i32
+    L.idn_gpu_fastq_chunk_fetch.argtypes = [vp, vp, vp, vp, vp, vp, vp]
+    L.idn_gpu_fastq_chunk_fetch.restype = i32
+    L.idn_gpu_compress_parsed.argtypes = [vp, i32, vp, u32, i32, i32, vp, vp, u64, vp, vp, C.POINTER(CompressStats)]
+    L.idn_gpu_compress_parsed.restype = i32
+    L.idn_gpu_decompress_to_fastq.argtypes = [vp, vp, vp, vp, vp, u32, i32, vp, u32, vp, vp, u64, u64, i32, vp, u64, C.POINTER(u64),
+                                             C.POINTER(u64), C.POINTER(i32)]
+    L.idn_gpu_decompress_to_fastq.restype = i32
     L.idn_gpu_set_lane_symbols.argtypes = [vp, u32]
     L.idn_gpu_set_lane_symbols.restype = i32
     L.idn_gpu_set_walk.argtypes = [vp, i32]

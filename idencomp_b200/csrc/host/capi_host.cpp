@@ -2,6 +2,7 @@
 #include "../../../include/idn_host.h"
 
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 
@@ -150,6 +151,7 @@ extern "C" void idn_host_params_default(idn_host_params* p) {
     p->mode = d.mode;
     p->batch_blocks = d.batch_blocks;
     p->lane_symbols = d.lane_symbols;
+    p->text_chunk_bytes = d.text_chunk_bytes;
     p->n_devices = 0;
     for (int32_t& v : p->devices) v = 0;
 }
@@ -172,6 +174,7 @@ extern "C" int32_t idn_host_compressor_new(const idn_host_model* const* models, 
                                     .mode(params->mode)
                                     .batch_blocks(params->batch_blocks)
                                     .lane_symbols(params->lane_symbols)
+                                    .text_chunk_bytes(params->text_chunk_bytes ? params->text_chunk_bytes : (256ull << 20))
                                     .build();
         auto h = std::make_unique<idn_host_compressor>();
         idn_host_compressor* raw = h.get();
@@ -203,6 +206,67 @@ extern "C" int32_t idn_host_compressor_add_batch(idn_host_compressor* c, uint64_
         return (int32_t)IDN_OK;
     });
 }
+
+extern "C" int32_t idn_host_compressor_add_text(idn_host_compressor* c, const uint8_t* text, uint64_t n) {
+    if (!c || (n && !text)) return set_err(IDN_E_INVALID_ARG, "NULL argument");
+    return guarded([&] {
+        if (c->out.capacity() < c->out.size() + n / 3) c->out.reserve(c->out.size() + n / 3 + (1u << 20));  // the in-memory writer
+        c->c->add_fastq_text(text, n);
+        return (int32_t)IDN_OK;
+    });
+}
+
+extern "C" int32_t idn_host_decompress_text(const idn_host_model* const* models, uint32_t n_models, int32_t device, uint32_t batch_blocks,
+                                            uint32_t thread_num, int32_t title_with_separator, const uint8_t* idn, uint64_t idn_len,
+                                            uint8_t** text, uint64_t* text_len) {
+    if (!text || !text_len || (!idn && idn_len) || (n_models && !models)) return set_err(IDN_E_INVALID_ARG, "NULL argument");
+    *text = nullptr;
+    *text_len = 0;
+    return guarded([&] {
+        IdnDecompressorParams p;
+        p.model_provider = provider_of(models, n_models);
+        p.thread_num = thread_num;
+        if (device >= 0) {
+            p.devices.assign(1, device);
+        } else {
+            p.devices.clear();
+            for (int32_t d = 0; d < -device; d++) p.devices.push_back(d);
+        }
+        p.batch_blocks = batch_blocks ? batch_blocks : 32;
+        uint64_t pos = 0;
+        IdnDecompressor d([&](uint8_t* dst, size_t n) {
+            size_t k = (size_t)std::min<uint64_t>(n, idn_len - pos);
+            std::memcpy(dst, idn + pos, k);
+            pos += k;
+            return k;
+        }, std::move(p));
+        // pieces are appended to one malloc'd buffer that doubles when it runs out (starts at 3.2 x the container)
+        size_t cap = (size_t)(idn_len * 3.2) + (1u << 20), used = 0;
+        uint8_t* buf = static_cast<uint8_t*>(std::malloc(cap));
+        if (!buf) throw IdnError(IDN_E_IO, "out of memory");
+        try {
+            std::unique_ptr<uint8_t[]> piece;
+            size_t n = 0;
+            while (d.next_fastq_text(piece, n, title_with_separator != 0)) {
+                if (used + n > cap) {
+                    while (used + n > cap) cap *= 2;
+                    uint8_t* nb = static_cast<uint8_t*>(std::realloc(buf, cap));
+                    if (!nb) throw IdnError(IDN_E_IO, "out of memory");
+                    buf = nb;
+                }
+                std::memcpy(buf + used, piece.get(), n);
+                used += n;
+            }
+        } catch (...) {
+            std::free(buf);
+            throw;
+        }
+        *text = buf;
+        *text_len = used;
+        return (int32_t)IDN_OK;
+    });
+}
+extern "C" void idn_host_text_free(uint8_t* text) { std::free(text); }
 
 extern "C" int32_t idn_host_compressor_finish(idn_host_compressor* c) {
     if (!c) return set_err(IDN_E_INVALID_ARG, "NULL argument");

@@ -17,6 +17,16 @@ namespace idencomp {
 
 namespace {
 
+template <class W>
+struct WorkerLease {  // a ctx is single-owner: one job at a time per worker
+    W& w;
+    bool adopted;
+    explicit WorkerLease(W& w_, bool already_acquired = false) : w(w_), adopted(already_acquired) {
+        if (!adopted) w.acquire();
+    }
+    ~WorkerLease() { w.release(); }
+};
+
 constexpr char kMagic[8] = {'I', 'D', 'E', 'N', 'C', 'O', 'M', 'P'};  // idn/data.rs:3-8
 
 void put_u32be(std::vector<uint8_t>& b, uint32_t v) {
@@ -188,6 +198,7 @@ void IdnCompressor::add_sequence(FastqSequence seq) {
 void IdnCompressor::add_batch(uint64_t n_reads, const uint64_t* read_off, const uint8_t* acids, const uint8_t* quals,
                               const uint64_t* name_off, const uint8_t* names) {
     if (finished_) throw IdnError(IDN_E_INVALID_STATE, "add_sequence after finish");
+    if (text_mode_) throw IdnError(IDN_E_INVALID_STATE, "add_sequence after add_fastq_text");
     uint64_t r = 0;
     while (r < n_reads) {
         // the run of reads [r, e) that goes into the batch under construction: block forming per read exactly as
@@ -305,47 +316,50 @@ void IdnCompressor::initialize() {
     initialized_ = true;
 }
 
+// identifiers slices on host threads, like write_identifiers (compressor_block.rs:146-206): names joined by '\n', Deflate
+// (Brotli from quality 8 on), one slice per block
+static void identifier_slices(uint8_t quality, uint32_t thread_num, uint32_t n_blocks, const uint32_t* block_first, const uint8_t* names,
+                              const uint64_t* name_off, std::vector<std::vector<uint8_t>>& name_slices, std::vector<uint32_t>& prefix) {
+    const bool brotli = quality >= 8;  // BROTLI_THRESHOLD (compressor_block.rs:146)
+    if (brotli && !Brotli::get().enc) throw IdnError(IDN_E_UNSUPPORTED, "Brotli identifier slices (quality 8-9) need libbrotlienc.so.1");
+    auto one = [&](uint32_t b) {
+        std::vector<uint8_t> joined;
+        for (uint32_t r = block_first[b]; r < block_first[b + 1]; r++) {
+            if (r > block_first[b]) joined.push_back('\n');
+            joined.insert(joined.end(), names + name_off[r], names + name_off[r + 1]);
+        }
+        std::vector<uint8_t> z = brotli ? Brotli::get().compress(joined.data(), joined.size()) : deflate_raw(joined.data(), joined.size());
+        std::vector<uint8_t> s;
+        s.push_back(0x00);  // IdnSliceHeader::Identifiers (data.rs:46-47)
+        put_u32be(s, (uint32_t)z.size());
+        s.push_back(brotli ? 0 : 1);  // IdnIdentifierCompression::{Brotli = 0, Deflate = 1} (data.rs:57-61)
+        s.insert(s.end(), z.begin(), z.end());
+        name_slices[b] = std::move(s);
+    };
+    if (thread_num > 1) {  // thread_num workers take the blocks in turn
+        std::vector<std::future<void>> jobs;
+        std::atomic<uint32_t> next{0};
+        for (uint32_t t = 0; t < std::min<uint32_t>(thread_num, n_blocks); t++)
+            jobs.push_back(std::async(std::launch::async, [&] {
+                for (uint32_t b = next++; b < n_blocks; b = next++) one(b);
+            }));
+        for (auto& j : jobs) j.get();
+    } else {
+        for (uint32_t b = 0; b < n_blocks; b++) one(b);
+    }
+    for (uint32_t b = 0; b < n_blocks; b++) prefix[b] = (uint32_t)name_slices[b].size();
+}
+
 // one batch on one device: identifiers slices on host threads, everything else through the C-ABI
 IdnCompressor::Result IdnCompressor::compress_batch(Worker& w, const Batch& bt) const {
-    std::lock_guard<std::mutex> lock(w.mu);  // a ctx is single-owner
+    WorkerLease<Worker> lease(w);
     Result res;
     const uint32_t n_blocks = (uint32_t)(bt.block_first.size() - 1);
     const uint64_t n_reads = bt.block_first.back();
-    // identifiers slices on host threads, like write_identifiers (compressor_block.rs:146-206): names joined by '\n'
     std::vector<std::vector<uint8_t>> name_slices(n_blocks);
     std::vector<uint32_t> prefix(n_blocks, 0);
-    if (params_.include_identifiers) {
-        const bool brotli = params_.quality >= 8;  // BROTLI_THRESHOLD (compressor_block.rs:146)
-        if (brotli && !Brotli::get().enc)
-            throw IdnError(IDN_E_UNSUPPORTED, "Brotli identifier slices (quality 8-9) need libbrotlienc.so.1");
-        auto one = [&](uint32_t b) {
-            std::vector<uint8_t> joined;
-            for (uint32_t r = bt.block_first[b]; r < bt.block_first[b + 1]; r++) {
-                if (r > bt.block_first[b]) joined.push_back('\n');
-                joined.insert(joined.end(), bt.names.begin() + bt.name_off[r], bt.names.begin() + bt.name_off[r + 1]);
-            }
-            std::vector<uint8_t> z = brotli ? Brotli::get().compress(joined.data(), joined.size()) : deflate_raw(joined.data(), joined.size());
-            std::vector<uint8_t> s;
-            s.push_back(0x00);  // IdnSliceHeader::Identifiers (data.rs:46-47)
-            put_u32be(s, (uint32_t)z.size());
-            s.push_back(brotli ? 0 : 1);  // IdnIdentifierCompression::{Brotli = 0, Deflate = 1} (data.rs:57-61)
-            s.insert(s.end(), z.begin(), z.end());
-            name_slices[b] = std::move(s);
-        };
-        if (params_.thread_num > 1) {
-            // thread_num workers take the blocks of the batch in turn
-            std::vector<std::future<void>> jobs;
-            std::atomic<uint32_t> next{0};
-            for (uint32_t t = 0; t < std::min<uint32_t>(params_.thread_num, n_blocks); t++)
-                jobs.push_back(std::async(std::launch::async, [&] {
-                    for (uint32_t b = next++; b < n_blocks; b = next++) one(b);
-                }));
-            for (auto& j : jobs) j.get();
-        } else {
-            for (uint32_t b = 0; b < n_blocks; b++) one(b);
-        }
-        for (uint32_t b = 0; b < n_blocks; b++) prefix[b] = (uint32_t)name_slices[b].size();
-    }
+    if (params_.include_identifiers)
+        identifier_slices(params_.quality, params_.thread_num, n_blocks, bt.block_first.data(), bt.names.data(), bt.name_off.data(), name_slices, prefix);
     res.prefix_total = std::accumulate(prefix.begin(), prefix.end(), (uint64_t)0);
     idn_batch b{};
     b.n_reads = n_reads;
@@ -416,8 +430,186 @@ void IdnCompressor::commit(bool all) {
     }
 }
 
+// ---- FASTQ text in (row f1 wired into the API) -------------------------------------------------------------------------
+void IdnCompressor::add_fastq_text(const uint8_t* text, size_t n) {
+    if (finished_) throw IdnError(IDN_E_INVALID_STATE, "add_fastq_text after finish");
+    if (!text_mode_ && (cur_.read_off.size() > 1 || initialized_)) throw IdnError(IDN_E_INVALID_STATE, "add_fastq_text after add_sequence");
+    text_mode_ = true;
+    // The caller's buffer is read in place (no copy of the bulk of the text); only what a call leaves unconsumed -- a cut
+    // record and the reads of the last, possibly unfinished block: at most a block's worth of text -- is kept in text_
+    // and put in front of the next call's text.
+    size_t pos = 0;
+    while (!text_.empty() && pos < n) {
+        // carry-over from the call before: complete it with the head of the new text up to one chunk and process that
+        const size_t take = (size_t)std::min<uint64_t>(n - pos, std::max<uint64_t>(params_.text_chunk_bytes, text_.size()) );
+        const size_t carried = text_.size();
+        text_.insert(text_.end(), text + pos, text + pos + take);
+        pos += take;
+        const size_t used = consume_text(text_.data(), text_.size(), false);
+        const size_t tail = text_.size() - used;
+        if (used > 0 && tail <= take) {  // the unconsumed tail lies inside the caller's buffer: go on from there
+            pos -= tail;
+            text_.clear();
+        } else {
+            text_.erase(text_.begin(), text_.begin() + used);
+            if (used == 0 && text_.size() == carried + take && pos == n) break;  // not one block yet: wait for more text
+        }
+    }
+    if (text_.empty()) {
+        while (n - pos >= params_.text_chunk_bytes) {
+            const size_t used = consume_text(text + pos, n - pos, false);
+            if (used == 0) break;
+            pos += used;
+        }
+        text_.assign(text + pos, text + n);
+    }
+}
+
+static const char* fastq_error_name(int32_t kind) {
+    switch (kind) {
+        case 1: return "InvalidFormat";
+        case 2: return "InvalidAcid";
+        case 3: return "InvalidQualityScore";
+        case 4: return "AcidAndQualityScoreLengthMismatch";
+        case 5: return "EofReached";
+        default: return "";
+    }
+}
+
+// processes as many chunks of [buf, buf + total) as hold complete blocks (everything when final); returns the bytes consumed
+size_t IdnCompressor::consume_text(const uint8_t* buf, size_t total, bool final) {
+    uint64_t chunk = params_.text_chunk_bytes;
+    size_t text_pos_ = 0;
+    for (;;) {
+        const size_t avail = total - text_pos_;
+        if (avail == 0 && !(final && !initialized_)) break;
+        size_t len = (size_t)std::min<uint64_t>(avail, chunk);
+        const bool last = final && len == avail;
+        if (!last) {  // a chunk of a longer input ends on a line boundary
+            while (len > 0 && buf[text_pos_ + len - 1] != '\n') len--;
+            if (len == 0) {
+                if (chunk >= avail && !final) break;  // not even one line yet: wait for more text
+                chunk *= 2;
+                continue;
+            }
+        }
+        Worker* w = workers_[next_worker_++ % workers_.size()].get();
+        w->acquire();  // released by the job below
+        idn_fastq_chunk ck{};
+        int32_t rc = idn_gpu_fastq_parse_chunk(w->dev.ctx(), buf + text_pos_, len, last ? 1 : 0, params_.max_block_total_len, &ck);
+        if (rc) {
+            std::string what = idn_gpu_last_error(w->dev.ctx());
+            if (ck.error_kind) what = std::string("FastqReaderError::") + fastq_error_name(ck.error_kind) + ": " + what;
+            w->release();
+            throw IdnError(rc, what);
+        }
+        if (ck.n_blocks == 0) {  // not one complete block in this chunk
+            w->release();
+            if (last) {
+                text_pos_ += len;
+                break;
+            }
+            if (chunk > avail) break;  // wait for more text
+            chunk *= 2;
+            continue;
+        }
+        if (!initialized_) {
+            // file-level model selection on the reads of the first block (compressor_initializer.rs:53-74): they are on the
+            // device; bring them back once and go through the same initialize() as the add_sequence path
+            ModelProvider& mp = params_.model_provider;
+            size_t n_a = 0, n_q = 0;
+            for (size_t i = 0; i < mp.len(); i++) (mp[i].model_type() == ModelType::Acids ? n_a : n_q)++;
+            if (n_a > 1 || n_q > 1) {
+                std::vector<uint32_t> bf(ck.n_blocks + 1);
+                Batch first;
+                first.read_off.assign(ck.n_reads + 1, 0);
+                first.acids.resize(ck.n_symbols + 1);
+                first.quals.resize(ck.n_symbols + 1);
+                rc = idn_gpu_fastq_chunk_fetch(w->dev.ctx(), nullptr, nullptr, bf.data(), first.read_off.data(), first.acids.data(), first.quals.data());
+                if (rc) {
+                    w->release();
+                    w->dev.raise(rc);
+                }
+                first.block_first = {0, bf[1]};
+                std::swap(cur_, first);
+                try {
+                    initialize();
+                } catch (...) {
+                    w->release();
+                    throw;
+                }
+                std::swap(cur_, first);
+            } else {
+                try {
+                    initialize();
+                } catch (...) {
+                    w->release();
+                    throw;
+                }
+            }
+        }
+        text_pos_ += ck.consumed_text;
+        stats_.in_symbols += ck.n_symbols;
+        stats_.in_reads += ck.n_reads;
+        stats_.in_identifier_bytes += ck.n_name_bytes;
+        const uint32_t nb = ck.n_blocks;
+        const uint64_t nr = ck.n_reads, ns = ck.n_symbols, nn = ck.n_name_bytes;
+        pending_.push_back(std::async(std::launch::async, [this, w, nb, nr, ns, nn] { return compress_parsed(*w, nb, nr, ns, nn); }));
+        commit(false);
+        if (last) break;
+    }
+    return text_pos_;
+}
+
+// second half of a text chunk (the worker is already leased): identifiers to the host and through Deflate, the block
+// kernels on the parsed symbols where they lie, container bytes back
+IdnCompressor::Result IdnCompressor::compress_parsed(Worker& w, uint32_t n_blocks, uint64_t n_reads, uint64_t n_symbols,
+                                                     uint64_t n_name_bytes) const {
+    WorkerLease<Worker> lease(w, true);
+    Result res;
+    std::vector<std::vector<uint8_t>> name_slices(n_blocks);
+    std::vector<uint32_t> prefix(n_blocks, 0);
+    if (params_.include_identifiers) {
+        std::vector<uint8_t> names(n_name_bytes + 1);
+        std::vector<uint64_t> name_off(n_reads + 1);
+        std::vector<uint32_t> block_first(n_blocks + 1);
+        int32_t rc = idn_gpu_fastq_chunk_fetch(w.dev.ctx(), names.data(), name_off.data(), block_first.data(), nullptr, nullptr, nullptr);
+        if (rc) w.dev.raise(rc);
+        identifier_slices(params_.quality, params_.thread_num, n_blocks, block_first.data(), names.data(), name_off.data(), name_slices, prefix);
+    }
+    res.prefix_total = std::accumulate(prefix.begin(), prefix.end(), (uint64_t)0);
+    const uint64_t bound = idn_gpu_compress_bound(n_reads, n_symbols, n_blocks, res.prefix_total);
+    uint64_t cap = std::min<uint64_t>(bound, n_symbols + n_symbols / 4 + 24 * n_reads + 64ull * n_blocks + res.prefix_total + 4096);
+    std::vector<uint64_t> block_off(n_blocks + 1);
+    idn_compress_stats st{};
+    for (;;) {
+        res.bytes.reset(new uint8_t[cap]);
+        int32_t rc = idn_gpu_compress_parsed(w.dev.ctx(), params_.mode, w.dev.handles().data(), (uint32_t)w.dev.handles().size(), params_.fast ? 1 : 0,
+                                             params_.include_identifiers ? 1 : 0, params_.include_identifiers ? prefix.data() : nullptr,
+                                             res.bytes.get(), cap, block_off.data(), nullptr, &st);
+        if (rc == IDN_E_NOSPACE && cap < bound) {
+            cap = bound;
+            continue;
+        }
+        if (rc) w.dev.raise(rc);
+        break;
+    }
+    for (uint32_t k = 0; k < n_blocks; k++)
+        if (prefix[k]) std::memcpy(res.bytes.get() + block_off[k] + 8, name_slices[k].data(), prefix[k]);
+    res.out_bytes = st.out_bytes;
+    res.payload_bytes = st.payload_bytes;
+    res.acid_switches = st.acid_switches;
+    res.q_switches = st.q_switches;
+    res.blocks = n_blocks;
+    return res;
+}
+
 void IdnCompressor::finish() {
     if (finished_) throw IdnError(IDN_E_INVALID_STATE, "finish called twice");
+    if (text_mode_) {
+        consume_text(text_.data(), text_.size(), true);
+        text_.clear();
+    }
     make_block();  // flush the partial block (idn/compressor.rs:575-578)
     flush_batch();
     if (!initialized_) initialize();  // empty file: header + metadata still get written
@@ -502,6 +694,62 @@ bool IdnDecompressor::read_raw(RawBatch& rb) {
     return more;
 }
 
+// identifiers: leading Identifiers slices of every block, inflated on the host (decompressor_block.rs:146-192)
+void IdnDecompressor::inflate_names(const RawBatch& rb, const std::vector<uint64_t>& off, const std::vector<uint32_t>& block_first,
+                                    uint64_t n_reads, DecodedBatch& out) const {
+    const uint32_t n_blocks = (uint32_t)rb.off.size();
+    out.name_off.assign(n_reads + 1, 0);
+    // blocks inflate independently: thread_num host threads take them in turn, the pieces are stitched in block order
+    std::vector<std::vector<uint8_t>> text(n_blocks);
+    std::vector<uint8_t> has(n_blocks, 0);
+    auto one = [&](uint32_t b) {
+        const uint8_t* p = rb.buf.data() + off[b];
+        size_t pos = 0;
+        while (pos < rb.len[b] && p[pos] == 0x00) {
+            if (pos + 6 > rb.len[b]) throw IdnError(IDN_E_SERIALIZE, "truncated identifiers slice");
+            uint32_t n = get_u32be(p + pos + 1);
+            uint8_t comp = p[pos + 5];
+            if (n > rb.len[b] - pos - 6) throw IdnError(IDN_E_SERIALIZE, "truncated identifiers slice");
+            if (comp > 1) throw IdnError(IDN_E_SERIALIZE, "unknown identifier compression");
+            std::vector<uint8_t> t = comp == 0 ? Brotli::get().decompress(p + pos + 6, n) : inflate_raw(p + pos + 6, n);
+            if (has[b]) text[b].push_back('\n');
+            text[b].insert(text[b].end(), t.begin(), t.end());
+            has[b] = 1;
+            pos += 6 + (size_t)n;
+        }
+    };
+    if (params_.thread_num > 1 && n_blocks > 1) {
+        std::vector<std::future<void>> jobs;
+        std::atomic<uint32_t> next{0};
+        for (uint32_t t = 0; t < std::min<uint32_t>(params_.thread_num, n_blocks); t++)
+            jobs.push_back(std::async(std::launch::async, [&] {
+                for (uint32_t b = next++; b < n_blocks; b = next++) one(b);
+            }));
+        for (auto& j : jobs) j.get();
+    } else {
+        for (uint32_t b = 0; b < n_blocks; b++) one(b);
+    }
+    for (uint32_t b = 0; b < n_blocks; b++) {
+        uint64_t r = block_first[b];
+        const uint64_t r_end = block_first[b + 1];
+        if (has[b]) {
+            out.any_names = true;
+            // split at '\n': one identifier per sequence, in order (identifiers_as_lines)
+            const std::vector<uint8_t>& t = text[b];
+            size_t s0 = 0;
+            while (r < r_end) {
+                size_t e = s0;
+                while (e < t.size() && t[e] != '\n') e++;
+                out.names.insert(out.names.end(), t.begin() + s0, t.begin() + e);
+                out.name_off[++r] = out.names.size();
+                if (e >= t.size()) break;
+                s0 = e + 1;
+            }
+        }
+        for (; r < r_end; r++) out.name_off[r + 1] = out.names.size();  // sequences without an identifier
+    }
+}
+
 IdnDecompressor::DecodedBatch IdnDecompressor::decode_batch(Worker& w, const RawBatch& rb) const {
     std::lock_guard<std::mutex> lock(w.mu);
     DecodedBatch out;
@@ -516,35 +764,7 @@ IdnDecompressor::DecodedBatch IdnDecompressor::decode_batch(Worker& w, const Raw
     int32_t rc = idn_gpu_index_blocks(w.dev.ctx(), rb.buf.data(), off.data(), rb.len.data(), n_blocks, mode, handles.data(),
                                       (uint32_t)handles.size(), &tot, block_first.data());
     if (rc) w.dev.raise(rc);
-    // identifiers: leading Identifiers slices of every block, inflated on the host (decompressor_block.rs:146-192)
-    out.name_off.assign(tot.n_reads + 1, 0);
-    for (uint32_t b = 0; b < n_blocks; b++) {
-        const uint8_t* p = rb.buf.data() + off[b];
-        size_t pos = 0;
-        uint64_t r = block_first[b];
-        const uint64_t r_end = block_first[b + 1];
-        while (pos < rb.len[b] && p[pos] == 0x00) {
-            if (pos + 6 > rb.len[b]) throw IdnError(IDN_E_SERIALIZE, "truncated identifiers slice");
-            uint32_t n = get_u32be(p + pos + 1);
-            uint8_t comp = p[pos + 5];
-            if (n > rb.len[b] - pos - 6) throw IdnError(IDN_E_SERIALIZE, "truncated identifiers slice");
-            if (comp > 1) throw IdnError(IDN_E_SERIALIZE, "unknown identifier compression");
-            std::vector<uint8_t> text = comp == 0 ? Brotli::get().decompress(p + pos + 6, n) : inflate_raw(p + pos + 6, n);
-            out.any_names = true;
-            // split at '\n': one identifier per sequence, in order (identifiers_as_lines)
-            size_t s = 0;
-            while (r < r_end) {
-                size_t e = s;
-                while (e < text.size() && text[e] != '\n') e++;
-                out.names.insert(out.names.end(), text.begin() + s, text.begin() + e);
-                out.name_off[++r] = out.names.size();
-                if (e >= text.size()) break;
-                s = e + 1;
-            }
-            pos += 6 + (size_t)n;
-        }
-        for (; r < r_end; r++) out.name_off[r + 1] = out.names.size();  // sequences without an identifier
-    }
+    inflate_names(rb, off, block_first, tot.n_reads, out);
     out.acids.resize(tot.n_symbols + 1);
     out.quals.resize(tot.n_symbols + 1);
     out.read_off.assign(tot.n_reads + 1, 0);
@@ -561,6 +781,51 @@ IdnDecompressor::DecodedBatch IdnDecompressor::decode_batch(Worker& w, const Raw
     return out;
 }
 
+// the same with the FASTQ text formatted on the device: the symbols never cross PCIe
+IdnDecompressor::DecodedBatch IdnDecompressor::decode_text(Worker& w, const RawBatch& rb, bool title_with_separator) const {
+    std::lock_guard<std::mutex> lock(w.mu);
+    DecodedBatch out;
+    const uint32_t n_blocks = (uint32_t)rb.off.size();
+    if (n_blocks == 0) return out;
+    std::vector<uint64_t> off = rb.off;
+    off.push_back(rb.buf.size());
+    const int32_t mode = version_ == 2 ? IDN_MODE_NATIVE : IDN_MODE_COMPAT;
+    const auto& handles = w.dev.handles();
+    idn_block_index_totals tot{};
+    std::vector<uint32_t> block_first(n_blocks + 1);
+    int32_t rc = idn_gpu_index_blocks(w.dev.ctx(), rb.buf.data(), off.data(), rb.len.data(), n_blocks, mode, handles.data(),
+                                      (uint32_t)handles.size(), &tot, block_first.data());
+    if (rc) w.dev.raise(rc);
+    inflate_names(rb, off, block_first, tot.n_reads, out);
+    if (out.names.empty()) out.names.push_back(0);
+    const uint64_t name_bytes = out.any_names ? out.name_off[tot.n_reads] : 0;
+    const uint64_t cap = 2 * tot.n_symbols + 6 * tot.n_reads + name_bytes * (title_with_separator ? 2 : 1) + 64;
+    out.text.reset(new uint8_t[cap]);
+    uint64_t text_len = 0, n_reads = 0;
+    int32_t bad = -1;
+    rc = idn_gpu_decompress_to_fastq(w.dev.ctx(), rb.buf.data(), off.data(), rb.len.data(), rb.crc.data(), n_blocks, mode, handles.data(),
+                                     (uint32_t)handles.size(), out.any_names ? out.names.data() : nullptr,
+                                     out.any_names ? out.name_off.data() : nullptr, tot.n_reads, tot.n_symbols, title_with_separator ? 1 : 0,
+                                     out.text.get(), cap, &text_len, &n_reads, &bad);
+    if (rc) w.dev.raise(rc);
+    out.text_len = text_len;
+    out.read_off.assign(1, n_reads);  // [0] = sequences in the text
+    return out;
+}
+
+bool IdnDecompressor::next_fastq_text(std::unique_ptr<uint8_t[]>& out, size_t& len, bool title_with_separator) {
+    if (!initialized_) initialize();
+    text_mode_ = title_with_separator ? 2 : 1;
+    prefetch();
+    if (pending_.empty()) return false;
+    DecodedBatch b = pending_.front().get();
+    pending_.pop_front();
+    prefetch();
+    out = std::move(b.text);
+    len = b.text_len;
+    return true;
+}
+
 // keeps up to two batches per device in flight (the reference reads and dispatches block jobs ahead the same way,
 // idn/decompressor.rs:387-428)
 void IdnDecompressor::prefetch() {
@@ -569,7 +834,8 @@ void IdnDecompressor::prefetch() {
         eof_ = !read_raw(*rb);
         if (rb->off.empty()) break;
         Worker* w = workers_[next_worker_++ % workers_.size()].get();
-        pending_.push_back(std::async(std::launch::async, [this, w, rb] { return decode_batch(*w, *rb); }));
+        const int tm = text_mode_;
+        pending_.push_back(std::async(std::launch::async, [this, w, rb, tm] { return tm ? decode_text(*w, *rb, tm == 2) : decode_batch(*w, *rb); }));
     }
 }
 

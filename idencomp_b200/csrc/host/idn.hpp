@@ -12,6 +12,7 @@
 // host keeps what the reference keeps on the host: block forming, container framing, name Deflate, ordered writes.
 // The reference hands one block to one thread-pool job; here `batch_blocks` blocks go to the device in one call.
 #pragma once
+#include <condition_variable>
 #include <cstdint>
 #include <deque>
 #include <functional>
@@ -62,6 +63,7 @@ struct IdnCompressorParams {
     int32_t mode = IDN_MODE_COMPAT;  // IDN_MODE_NATIVE writes container version 2
     uint32_t batch_blocks = 32;      // blocks per device call
     uint32_t lane_symbols = 2048;    // native mode lane quantum
+    uint64_t text_chunk_bytes = 256ull << 20;  // add_fastq_text: bytes of FASTQ text per device call
 };
 
 class IdnCompressorParamsBuilder {
@@ -77,6 +79,7 @@ public:
     IdnCompressorParamsBuilder& mode(int32_t v) { p_.mode = v; return *this; }
     IdnCompressorParamsBuilder& batch_blocks(uint32_t v) { p_.batch_blocks = v ? v : 1; return *this; }
     IdnCompressorParamsBuilder& lane_symbols(uint32_t v) { p_.lane_symbols = v; return *this; }
+    IdnCompressorParamsBuilder& text_chunk_bytes(uint64_t v) { p_.text_chunk_bytes = v ? v : 1; return *this; }
     IdnCompressorParams build() const { return p_; }
 
 private:
@@ -111,6 +114,11 @@ public:
     // if add_sequence had been called per read.  name_off / names may be NULL (empty identifiers).
     void add_batch(uint64_t n_reads, const uint64_t* read_off, const uint8_t* acids, const uint8_t* quals, const uint64_t* name_off,
                    const uint8_t* names);
+    // FASTQ text instead of parsed sequences (what FastqReader + add_sequence do in the reference, fastq/reader.rs:166-282):
+    // any number of calls with consecutive pieces of the text, cut anywhere.  The text is split into records, turned into
+    // blocks and compressed on the device; identifiers come back for the host's Deflate.  The container is the one
+    // add_sequence would have produced for the same reads.  Not to be mixed with add_sequence / add_batch on one object.
+    void add_fastq_text(const uint8_t* text, size_t n);
     void finish();                         // flushes, writes the empty terminator block; InvalidState if called twice
     const CompressionStats& stats() const { return stats_; }
     // the model identifiers written to the metadata (acid ids first), available after the first block was processed
@@ -134,10 +142,26 @@ private:
         std::unique_ptr<uint8_t[]> bytes;  // (not a vector: no zero fill of the capacity)
         uint64_t out_bytes = 0, prefix_total = 0, payload_bytes = 0, acid_switches = 0, q_switches = 0, blocks = 0;
     };
-    struct Worker {  // one device: its context, its uploaded models; one job at a time
+    struct Worker {  // one device: its context, its uploaded models; one job at a time (a job may change threads)
         DeviceModels dev;
         std::mutex mu;
+        std::condition_variable cv;
+        bool busy = false;
+        void acquire() {
+            std::unique_lock<std::mutex> lk(mu);
+            cv.wait(lk, [this] { return !busy; });
+            busy = true;
+        }
+        void release() {
+            {
+                std::lock_guard<std::mutex> lk(mu);
+                busy = false;
+            }
+            cv.notify_one();
+        }
     };
+    size_t consume_text(const uint8_t* buf, size_t total, bool final);
+    Result compress_parsed(Worker& w, uint32_t n_blocks, uint64_t n_reads, uint64_t n_symbols, uint64_t n_name_bytes) const;
     void make_block();
     void flush_batch();  // hands the batch under construction to the next device
     void commit(bool all);  // writes finished batches in order (the reference's IdnBlockLock, idn/common.rs:10-57)
@@ -156,6 +180,8 @@ private:
     bool initialized_ = false, finished_ = false;
     Batch cur_;  // SoA batch under construction
     uint64_t cur_block_len_ = 0;
+    std::vector<uint8_t> text_;  // add_fastq_text: what the calls so far left unconsumed (at most about a block's worth of text)
+    bool text_mode_ = false;
 };
 
 struct IdnDecompressorParams {
@@ -179,8 +205,13 @@ public:
         std::vector<uint8_t> acids, quals, names;
         std::vector<uint64_t> read_off{0}, name_off{0};
         bool any_names = false;
+        std::unique_ptr<uint8_t[]> text;  // next_fastq_text: the FASTQ text (not a vector: no zero fill of the capacity)
+        size_t text_len = 0;
     };
     bool next_batch(DecodedBatch& out);
+    // the FASTQ text of the next batch of sequences, formatted on the device as FastqWriter does (fastq/writer.rs:190-245);
+    // false at the end of the file.  Do not mix with next_sequence / next_batch on one object.
+    bool next_fastq_text(std::unique_ptr<uint8_t[]>& out, size_t& len, bool title_with_separator = false);
 
 private:
     struct RawBatch {  // container bytes of some blocks, as read from the source
@@ -195,6 +226,9 @@ private:
     void initialize();  // header + metadata (idn/decompressor.rs:304-374)
     bool read_raw(RawBatch& rb);  // false once the terminator block was seen (and rb holds no block)
     DecodedBatch decode_batch(Worker& w, const RawBatch& rb) const;
+    DecodedBatch decode_text(Worker& w, const RawBatch& rb, bool title_with_separator) const;  // text in DecodedBatch::acids
+    void inflate_names(const RawBatch& rb, const std::vector<uint64_t>& off, const std::vector<uint32_t>& block_first, uint64_t n_reads,
+                       DecodedBatch& out) const;
     void prefetch();
     void read_exact(uint8_t* dst, size_t n, const char* what);
 
@@ -203,6 +237,7 @@ private:
     std::vector<std::unique_ptr<Worker>> workers_;
     size_t next_worker_ = 0;
     std::deque<std::future<DecodedBatch>> pending_;
+    int text_mode_ = 0;  // 0 sequences / batches, 1 text, 2 text with the title repeated on the separator line
     bool initialized_ = false, eof_ = false;
     uint8_t version_ = 0;
     std::deque<FastqSequence> queue_;

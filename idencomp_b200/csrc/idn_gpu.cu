@@ -125,6 +125,10 @@ struct idn_gpu_ctx {
     DevBuf f_text, f_tilecnt, f_tilebase, f_linestart, f_linefn, f_linestate, f_tilefn, f_tilestate, f_recscan, f_title, f_namelo,
         f_namelen, f_readlen, f_readoff, f_nameoff, f_names, f_acids, f_quals, f_err, f_fmtoff, f_fmttext;
     idn_fastq_info f_info{};
+    uint64_t f_consumed = 0;       // bytes of the last parsed text that belong to complete records (partial parse)
+    DevBuf f_blockfirst, f_nxt;    // blocks formed over the parsed reads (idn_gpu_fastq_parse_chunk)
+    uint32_t f_blocks = 0;         // blocks idn_gpu_compress_parsed codes
+    uint64_t f_reads_used = 0;     // = block_first[f_blocks]
     DevBuf w_index;  // decode-side per-read index
     DevBuf w_blk;    // decode-side per-block counters
     // staging of the host-pointer paths
@@ -395,6 +399,7 @@ extern "C" void idn_gpu_destroy(idn_gpu_ctx* ctx) {
                       &ctx->f_text, &ctx->f_tilecnt, &ctx->f_tilebase, &ctx->f_linestart, &ctx->f_linefn, &ctx->f_linestate, &ctx->f_tilefn,
                       &ctx->f_tilestate, &ctx->f_recscan, &ctx->f_title, &ctx->f_namelo, &ctx->f_namelen, &ctx->f_readlen, &ctx->f_readoff,
                       &ctx->f_nameoff, &ctx->f_names, &ctx->f_acids, &ctx->f_quals, &ctx->f_err, &ctx->f_fmtoff, &ctx->f_fmttext,
+                      &ctx->f_blockfirst, &ctx->f_nxt,
                       &ctx->s_acids,   &ctx->s_quals,   &ctx->s_readoff, &ctx->s_blockfirst, &ctx->s_prefix, &ctx->s_names,
                       &ctx->s_nameoff, &ctx->s_out,     &ctx->s_blockoff, &ctx->s_crc,       &ctx->s_stats,  &ctx->s_sizes,
                       &ctx->s_blocks,  &ctx->s_blocklen, &ctx->s_aout,    &ctx->s_qout,    &ctx->s_offout,     &ctx->s_status, &ctx->s_idx};
@@ -1590,41 +1595,23 @@ extern "C" int32_t idn_gpu_index_blocks(idn_gpu_ctx* ctx, const uint8_t* blocks,
 
 #include "idn_pipeline.inc"
 
-extern "C" int32_t idn_gpu_set_pipeline_blocks(idn_gpu_ctx* ctx, uint32_t blocks) {
-    if (!ctx) return IDN_E_INVALID_ARG;
-    if (blocks == 0) return fail(ctx, IDN_E_INVALID_ARG, "blocks per sub-chunk must be positive");
-    ctx->pipe_blocks = blocks;
-    return IDN_OK;
-}
-
-extern "C" int32_t idn_gpu_decompress_blocks(idn_gpu_ctx* ctx, const uint8_t* blocks, const uint64_t* block_off,
-                                             const uint32_t* block_len, const uint32_t* block_crc, uint32_t n_blocks, int32_t mode,
-                                             const idn_model_t* models, uint32_t n_models, const uint8_t* names,
-                                             const uint64_t* name_off, uint8_t* acids_out, uint8_t* quals_out,
-                                             uint64_t* read_off_out, uint64_t out_reads_cap, uint64_t out_symbols_cap,
-                                             int32_t* bad_block) {
+// The unpipelined decode of a call: container bytes and tables to the device, the *_dev path into the staging buffers
+// s_aout / s_qout / s_offout (the results STAY on the device), the block CRCs checked -- with the identifiers when the
+// caller passes them (sequence.rs:381-394; they are left staged in s_names / s_nameoff).
+static int32_t decompress_to_staging(idn_gpu_ctx* ctx, const uint8_t* blocks, const uint64_t* block_off, const uint32_t* block_len,
+                                     const uint32_t* block_crc, uint32_t n_blocks, int32_t mode, const idn_model_t* models,
+                                     uint32_t n_models, const uint8_t* names, const uint64_t* name_off, uint64_t out_reads_cap,
+                                     uint64_t out_symbols_cap, uint64_t* R_out, uint64_t* S_out, int32_t* bad_block) {
     if (!ctx) return IDN_E_INVALID_ARG;
     if (bad_block) *bad_block = -1;
-    if (!block_off || !read_off_out) return fail(ctx, IDN_E_INVALID_ARG, "NULL argument");
+    if (!block_off) return fail(ctx, IDN_E_INVALID_ARG, "NULL argument");
     if ((names != nullptr) != (name_off != nullptr)) return fail(ctx, IDN_E_INVALID_ARG, "names and name_off go together");
-    if (out_symbols_cap && (!acids_out || !quals_out)) return fail(ctx, IDN_E_INVALID_ARG, "NULL output");
     int32_t rc0 = check_block_table(ctx, block_off, block_len, n_blocks);
     if (rc0) return rc0;
-    uint64_t nbytes = n_blocks ? block_off[n_blocks] : 0;
+    const uint64_t nbytes = n_blocks ? block_off[n_blocks] : 0;
     if (!blocks && nbytes) return fail(ctx, IDN_E_INVALID_ARG, "blocks is NULL");
     CU(cudaSetDevice(ctx->device));
     cudaStream_t st = ctx->stream;
-    if (!names && n_blocks) {
-        // no names on the device (the block CRCs cover the symbols only): sub-chunks of whole blocks flow through upload /
-        // kernels / download streams; a sub-chunk that outgrows its share of the staging sends the call down the path below
-        int32_t rcm = check_models(ctx, models, n_models);
-        if (rcm) return rcm;
-        if (mode != IDN_MODE_COMPAT && mode != IDN_MODE_NATIVE) return fail(ctx, IDN_E_UNSUPPORTED, "unknown mode %d", mode);
-        bool retry_simple = false;
-        int32_t rcp = decompress_blocks_pipelined(ctx, blocks, block_off, block_len, block_crc, n_blocks, mode, models, n_models, acids_out,
-                                                  quals_out, read_off_out, out_reads_cap, out_symbols_cap, bad_block, &retry_simple);
-        if (rcp || !retry_simple) return rcp;
-    }
     CU(ctx->s_blocks.ensure(nbytes + 16));
     CU(ctx->s_blockoff.ensure(((size_t)n_blocks + 1) * 8));
     CU(ctx->s_crc.ensure(((size_t)n_blocks + 1) * 4));
@@ -1661,15 +1648,10 @@ extern "C" int32_t idn_gpu_decompress_blocks(idn_gpu_ctx* ctx, const uint8_t* bl
         if (bad_block) *bad_block = hst[1];
         return status_to_error(ctx, hst);
     }
-    uint64_t R = tot[0], S = tot[1];
-    if (S) {
-        CU(cudaMemcpyAsync(acids_out, ctx->s_aout.p, S, cudaMemcpyDeviceToHost, st));
-        CU(cudaMemcpyAsync(quals_out, ctx->s_qout.p, S, cudaMemcpyDeviceToHost, st));
-    }
-    CU(cudaMemcpyAsync(read_off_out, ctx->s_offout.p, (R + 1) * 8, cudaMemcpyDeviceToHost, st));
-    CU(sync_stream(ctx, st));
-    ht.lap("host:d_d2h");
-    if (host_crc && block_crc && n_blocks) {
+    const uint64_t R = tot[0], S = tot[1];
+    *R_out = R;
+    *S_out = S;
+    if (host_crc && n_blocks) {
         // CRC with names on the device: stage names and run the CRC kernels over the decoded batch
         idn_batch d;
         memset(&d, 0, sizeof d);
@@ -1687,6 +1669,10 @@ extern "C" int32_t idn_gpu_decompress_blocks(idn_gpu_ctx* ctx, const uint8_t* bl
         CU(cudaMemcpyAsync(ctx->s_nameoff.p, name_off, (R + 1) * 8, cudaMemcpyHostToDevice, st));
         d.names = ctx->s_names.as<uint8_t>();
         d.name_off = ctx->s_nameoff.as<uint64_t>();
+        if (!block_crc) {
+            CU(sync_stream(ctx, st));
+            return IDN_OK;
+        }
         rc = idn_gpu_block_crc_dev_impl(ctx, &d, ctx->s_crc.as<uint32_t>(), nullptr, nullptr, 0, st);
         if (rc) return rc;
         std::vector<uint32_t> got(n_blocks);
@@ -1698,6 +1684,56 @@ extern "C" int32_t idn_gpu_decompress_blocks(idn_gpu_ctx* ctx, const uint8_t* bl
                 return fail(ctx, IDN_E_CHECKSUM, "checksum mismatch in block %u", i);
             }
     }
+    return IDN_OK;
+}
+
+
+
+extern "C" int32_t idn_gpu_set_pipeline_blocks(idn_gpu_ctx* ctx, uint32_t blocks) {
+    if (!ctx) return IDN_E_INVALID_ARG;
+    if (blocks == 0) return fail(ctx, IDN_E_INVALID_ARG, "blocks per sub-chunk must be positive");
+    ctx->pipe_blocks = blocks;
+    return IDN_OK;
+}
+
+extern "C" int32_t idn_gpu_decompress_blocks(idn_gpu_ctx* ctx, const uint8_t* blocks, const uint64_t* block_off,
+                                             const uint32_t* block_len, const uint32_t* block_crc, uint32_t n_blocks, int32_t mode,
+                                             const idn_model_t* models, uint32_t n_models, const uint8_t* names,
+                                             const uint64_t* name_off, uint8_t* acids_out, uint8_t* quals_out,
+                                             uint64_t* read_off_out, uint64_t out_reads_cap, uint64_t out_symbols_cap,
+                                             int32_t* bad_block) {
+    if (!ctx) return IDN_E_INVALID_ARG;
+    if (bad_block) *bad_block = -1;
+    if (!block_off || !read_off_out) return fail(ctx, IDN_E_INVALID_ARG, "NULL argument");
+    if ((names != nullptr) != (name_off != nullptr)) return fail(ctx, IDN_E_INVALID_ARG, "names and name_off go together");
+    if (out_symbols_cap && (!acids_out || !quals_out)) return fail(ctx, IDN_E_INVALID_ARG, "NULL output");
+    int32_t rc0 = check_block_table(ctx, block_off, block_len, n_blocks);
+    if (rc0) return rc0;
+    uint64_t nbytes = n_blocks ? block_off[n_blocks] : 0;
+    if (!blocks && nbytes) return fail(ctx, IDN_E_INVALID_ARG, "blocks is NULL");
+    CU(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    if (!names && n_blocks) {
+        // no names on the device (the block CRCs cover the symbols only): sub-chunks of whole blocks flow through upload /
+        // kernels / download streams; a sub-chunk that outgrows its share of the staging sends the call down the path below
+        int32_t rcm = check_models(ctx, models, n_models);
+        if (rcm) return rcm;
+        if (mode != IDN_MODE_COMPAT && mode != IDN_MODE_NATIVE) return fail(ctx, IDN_E_UNSUPPORTED, "unknown mode %d", mode);
+        bool retry_simple = false;
+        int32_t rcp = decompress_blocks_pipelined(ctx, blocks, block_off, block_len, block_crc, n_blocks, mode, models, n_models, acids_out,
+                                                  quals_out, read_off_out, out_reads_cap, out_symbols_cap, bad_block, &retry_simple);
+        if (rcp || !retry_simple) return rcp;
+    }
+    uint64_t R = 0, S = 0;
+    int32_t rc = decompress_to_staging(ctx, blocks, block_off, block_len, block_crc, n_blocks, mode, models, n_models, names, name_off,
+                                       out_reads_cap, out_symbols_cap, &R, &S, bad_block);
+    if (rc) return rc;
+    if (S) {
+        CU(cudaMemcpyAsync(acids_out, ctx->s_aout.p, S, cudaMemcpyDeviceToHost, st));
+        CU(cudaMemcpyAsync(quals_out, ctx->s_qout.p, S, cudaMemcpyDeviceToHost, st));
+    }
+    CU(cudaMemcpyAsync(read_off_out, ctx->s_offout.p, (R + 1) * 8, cudaMemcpyDeviceToHost, st));
+    CU(sync_stream(ctx, st));
     return IDN_OK;
 }
 
@@ -1872,10 +1908,12 @@ static const char* fastq_err_name(uint32_t e) {
     }
 }
 
-extern "C" int32_t idn_gpu_fastq_parse_dev(idn_gpu_ctx* ctx, const uint8_t* text, uint64_t n, idn_fastq_info* info, void* stream) {
+// partial: the text is a chunk of a longer input that ends on a line boundary; a record cut short at its end is left to
+// the next chunk (ctx->f_consumed = where it starts) instead of being an error
+static int32_t fastq_parse_dev_impl(idn_gpu_ctx* ctx, const uint8_t* text, uint64_t n, idn_fastq_info* info, cudaStream_t st, bool partial) {
     if (!ctx || !info || (!text && n)) return fail(ctx, IDN_E_INVALID_ARG, "NULL argument");
     CU(cudaSetDevice(ctx->device));
-    cudaStream_t st = as_stream(stream);
+    ctx->f_consumed = n;
     PROF_BEGIN();
     memset(info, 0, sizeof *info);
     ctx->f_info = *info;
@@ -1931,6 +1969,19 @@ extern "C" int32_t idn_gpu_fastq_parse_dev(idn_gpu_ctx* ctx, const uint8_t* text
             fq_titles_kernel<<<(unsigned)((n_lines + 255) / 256), 256, 0, st>>>(tf, n_lines, rec_scan, ctx->f_title.as<unsigned long long>());
             LAUNCHED("fq_titles");
         }
+        if (partial && n_reads) {  // a last record with fewer than four lines belongs to the next chunk
+            if (last != '\n') return fail(ctx, IDN_E_INVALID_ARG, "a chunk of a longer FASTQ input must end on a line boundary");
+            unsigned long long t_last = 0;
+            CU(cudaMemcpyAsync(&t_last, ctx->f_title.as<unsigned long long>() + (n_reads - 1), 8, cudaMemcpyDeviceToHost, st));
+            CU(sync_stream(ctx, st));
+            if (t_last + 3 >= n_lines) {
+                unsigned long long off = 0;
+                CU(cudaMemcpyAsync(&off, line_start + t_last, 8, cudaMemcpyDeviceToHost, st));
+                CU(sync_stream(ctx, st));
+                ctx->f_consumed = off;
+                n_reads--;
+            }
+        }
     }
     info->n_reads = n_reads;
     CU(ctx->f_namelo.ensure((n_reads + 1) * 8));
@@ -1977,6 +2028,10 @@ extern "C" int32_t idn_gpu_fastq_parse_dev(idn_gpu_ctx* ctx, const uint8_t* text
     }
     ctx->f_info = *info;
     return IDN_OK;
+}
+
+extern "C" int32_t idn_gpu_fastq_parse_dev(idn_gpu_ctx* ctx, const uint8_t* text, uint64_t n, idn_fastq_info* info, void* stream) {
+    return fastq_parse_dev_impl(ctx, text, n, info, as_stream(stream), false);
 }
 
 extern "C" int32_t idn_gpu_fastq_parse(idn_gpu_ctx* ctx, const uint8_t* text, uint64_t n, idn_fastq_info* info) {
@@ -2073,3 +2128,5 @@ extern "C" int32_t idn_gpu_fastq_format(idn_gpu_ctx* ctx, const idn_batch* b, in
     CU(sync_stream(ctx, st));
     return IDN_OK;
 }
+
+#include "idn_textpath.inc"

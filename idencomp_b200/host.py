@@ -25,7 +25,8 @@ EXPORTS = [
     "idn_host_decoded_reads", "idn_host_decoded_version", "idn_host_decoded_read_off", "idn_host_decoded_acids",
     "idn_host_decoded_quals", "idn_host_decoded_name_off", "idn_host_decoded_names", "idn_host_decoded_free",
     "idn_host_cluster", "idn_host_rank", "idn_host_clustering_new", "idn_host_clustering_free", "idn_host_splitmix64",
-    "idn_host_xoshiro256pp", "idn_host_sample_indices", "idn_host_gen_range",
+    "idn_host_xoshiro256pp", "idn_host_sample_indices", "idn_host_gen_range", "idn_host_compressor_add_text", "idn_host_decompress_text",
+    "idn_host_text_free",
 ]
 
 
@@ -33,7 +34,8 @@ class Params(C.Structure):
     """idn_host_params = IdnCompressorParamsBuilder (idn/compressor.rs:164-274) + device / mode / batching."""
     _fields_ = [("max_block_total_len", C.c_uint32), ("thread_num", C.c_uint32), ("include_identifiers", C.c_int32),
                 ("quality", C.c_uint32), ("fast", C.c_int32), ("device", C.c_int32), ("mode", C.c_int32),
-                ("batch_blocks", C.c_uint32), ("lane_symbols", C.c_uint32), ("n_devices", C.c_uint32), ("devices", C.c_int32 * 16)]
+                ("batch_blocks", C.c_uint32), ("lane_symbols", C.c_uint32), ("text_chunk_bytes", C.c_uint64), ("n_devices", C.c_uint32),
+                ("devices", C.c_int32 * 16)]
 
 _LIB = None
 
@@ -70,6 +72,10 @@ def load():
     L.idn_host_compressor_new.argtypes = [vp, u32, C.POINTER(Params), C.POINTER(vp)]
     L.idn_host_compressor_add.argtypes = [vp, vp, u64, vp, vp, u64]
     L.idn_host_compressor_add_batch.argtypes = [vp, u64, vp, vp, vp, vp, vp]
+    L.idn_host_compressor_add_text.argtypes = [vp, vp, u64]
+    L.idn_host_decompress_text.argtypes = [vp, u32, i32, u32, u32, i32, vp, u64, C.POINTER(vp), C.POINTER(u64)]
+    L.idn_host_text_free.argtypes = [vp]
+    L.idn_host_text_free.restype = None
     L.idn_host_compressor_finish.argtypes = [vp]
     L.idn_host_compressor_output.argtypes = [vp, C.POINTER(vp)]
     L.idn_host_compressor_output.restype = u64
@@ -214,12 +220,14 @@ class IdnCompressor:
     """
 
     def __init__(self, models, *, max_block_total_len=4 * 1024 * 1024, thread_num=0, include_identifiers=True, quality=7,
-                 fast=False, device=0, devices=None, mode=capi.MODE_COMPAT, batch_blocks=32, lane_symbols=2048):
+                 fast=False, device=0, devices=None, mode=capi.MODE_COMPAT, batch_blocks=32, lane_symbols=2048, text_chunk_bytes=0):
         self.L = load()
         p = Params()
         self.L.idn_host_params_default(C.byref(p))
         p.max_block_total_len, p.thread_num, p.include_identifiers = max_block_total_len, thread_num, int(include_identifiers)
         p.quality, p.fast, p.device, p.mode, p.batch_blocks, p.lane_symbols = quality, int(fast), device, mode, batch_blocks, lane_symbols
+        if text_chunk_bytes:
+            p.text_chunk_bytes = text_chunk_bytes
         if devices:  # several GPUs share the file: same container, whatever their number
             p.n_devices = len(devices)
             for i, d in enumerate(devices):
@@ -252,9 +260,20 @@ class IdnCompressor:
                                                     q.ctypes.data if q.size else None, None if no is None else no.ctypes.data,
                                                     None if nm is None else nm.ctypes.data))
 
+    def add_fastq_text(self, text):
+        """consecutive pieces of FASTQ text, cut anywhere (bytes or a uint8 array; not to be mixed with add_sequence / add_batch)"""
+        buf = np.frombuffer(text, dtype=np.uint8) if isinstance(text, (bytes, bytearray, memoryview)) else np.ascontiguousarray(text, dtype=np.uint8)
+        _check(self.L.idn_host_compressor_add_text(self.h, buf.ctypes.data if buf.size else None, buf.size))
+
     def finish(self) -> bytes:
         _check(self.L.idn_host_compressor_finish(self.h))
         return self.output()
+
+    def output_view(self) -> np.ndarray:
+        """the container written so far as a uint8 view of the library's buffer (valid until the next call on this object)"""
+        ptr = C.c_void_p()
+        n = self.L.idn_host_compressor_output(self.h, C.byref(ptr))
+        return np.ctypeslib.as_array(C.cast(ptr, C.POINTER(C.c_uint8)), (n,)) if n else np.zeros(0, dtype=np.uint8)
 
     def output(self) -> bytes:
         ptr = C.c_void_p()
@@ -306,6 +325,25 @@ def decompress(models, idn: bytes, *, device=0, n_devices=0, batch_blocks=32) ->
                 "quals": take(L.idn_host_decoded_quals(h), S), "name_off": no, "names": take(L.idn_host_decoded_names(h), NB)}
     finally:
         L.idn_host_decoded_free(h)
+
+
+def decompress_text(models, idn, *, device=0, n_devices=0, batch_blocks=32, thread_num=0, title_with_separator=False, as_view=False):
+    """IdnDecompressor + FastqWriter (fastq/writer.rs:190-245): the whole file as FASTQ text, formatted on the device."""
+    L = load()
+    buf = np.frombuffer(idn, dtype=np.uint8) if isinstance(idn, (bytes, bytearray, memoryview)) else np.ascontiguousarray(idn, dtype=np.uint8)
+    models = list(models)
+    if n_devices > 1:
+        device = -n_devices
+    ptr, n = C.c_void_p(), C.c_uint64(0)
+    _check(L.idn_host_decompress_text(_model_array(models), len(models), device, batch_blocks, thread_num, int(title_with_separator),
+                                      buf.ctypes.data if buf.size else None, buf.size, C.byref(ptr), C.byref(n)))
+    if as_view:  # (view, free): no copy of the text; call free() when done with the view
+        view = np.ctypeslib.as_array(C.cast(ptr, C.POINTER(C.c_uint8)), (n.value,)) if n.value else np.zeros(0, dtype=np.uint8)
+        return view, (lambda: L.idn_host_text_free(ptr))
+    try:
+        return C.string_at(ptr, n.value) if n.value else b""
+    finally:
+        L.idn_host_text_free(ptr)
 
 
 class Clustering:

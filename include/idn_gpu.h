@@ -247,6 +247,44 @@ int32_t idn_gpu_fastq_format_dev(idn_gpu_ctx *ctx, const idn_batch *batch /* dev
                                  int32_t title_with_separator, uint8_t *text, uint64_t cap, uint64_t *n_out_dev,
                                  void *stream);
 
+/* ---- FASTQ text <-> .idn blocks without a symbol round trip over PCIe ---------------------------------------------------
+ * What the reference does between FastqReader and IdnCompressor::add_sequence (fastq/reader.rs:166-282 ->
+ * idn/compressor.rs:517-585) and between IdnDecompressor::next_sequence and FastqWriter (fastq/writer.rs:190-245), for a
+ * whole chunk of text at a time: the text is uploaded once, records are split and blocks are formed on the device with
+ * the reference's rule (a read that would push the block past max_block_total_len opens the next one), the block kernels
+ * run on the symbol arrays where they lie; only identifiers (for the host's Deflate / Brotli) and container bytes come
+ * back.  All pointers are HOST pointers. */
+typedef struct {
+    uint64_t n_reads, n_symbols, n_name_bytes; /* of the blocks idn_gpu_compress_parsed will code */
+    uint32_t n_blocks;
+    int32_t error_kind;      /* as idn_fastq_info */
+    uint64_t bad_record;
+    uint64_t consumed_text;  /* bytes of `text` those blocks cover: the caller's next chunk starts here */
+} idn_fastq_chunk;
+/* final == 0: `text` is a piece of a longer input and must end on a line boundary; a record cut short at its end and the
+ * reads of the last block (which may go on in the next chunk) are NOT consumed.  final != 0: everything is consumed.
+ * IDN_E_SEQUENCE_TOO_LONG when a read exceeds max_block_total_len / 2 (idn/compressor.rs:542-544). */
+int32_t idn_gpu_fastq_parse_chunk(idn_gpu_ctx *ctx, const uint8_t *text, uint64_t n, int32_t final,
+                                  uint32_t max_block_total_len, idn_fastq_chunk *out);
+/* identifiers (for the host's identifiers codec), tables and -- for the file-level model selection on the first block --
+ * symbols of the blocks of the chunk parsed last; any pointer may be NULL */
+int32_t idn_gpu_fastq_chunk_fetch(idn_gpu_ctx *ctx, uint8_t *names, uint64_t *name_off /*[n_reads+1]*/,
+                                  uint32_t *block_first_read /*[n_blocks+1]*/, uint64_t *read_off /*[n_reads+1]*/,
+                                  uint8_t *acids /*[n_symbols]*/, uint8_t *quals /*[n_symbols]*/);
+/* compress the blocks of the chunk parsed last; output as idn_gpu_compress_blocks.  with_names != 0: the block CRCs cover
+ * the identifiers as the reference's do (sequence.rs:381-394) */
+int32_t idn_gpu_compress_parsed(idn_gpu_ctx *ctx, int32_t mode, const idn_model_t *models, uint32_t n_models, int32_t fast,
+                                int32_t with_names, const uint32_t *prefix_len, uint8_t *out, uint64_t out_cap,
+                                uint64_t *block_off, uint32_t *block_crc, idn_compress_stats *stats);
+/* idn_gpu_decompress_blocks + FastqWriter: the FASTQ text of the decoded reads into `text` (the symbols stay on the
+ * device); names / name_off = the identifiers the caller inflated (optional) */
+int32_t idn_gpu_decompress_to_fastq(idn_gpu_ctx *ctx, const uint8_t *blocks, const uint64_t *block_off,
+                                    const uint32_t *block_len, const uint32_t *block_crc, uint32_t n_blocks, int32_t mode,
+                                    const idn_model_t *models, uint32_t n_models, const uint8_t *names,
+                                    const uint64_t *name_off, uint64_t reads_cap, uint64_t symbols_cap,
+                                    int32_t title_with_separator, uint8_t *text, uint64_t text_cap, uint64_t *text_len,
+                                    uint64_t *n_reads_out, int32_t *bad_block);
+
 /* ---- per-kernel timing (CUDA events on the launching stream; what bench.py's roofline line is made of) ----
  * idn_gpu_profile(ctx, 1) starts recording an event after every kernel launch of the *_dev entry points;
  * idn_gpu_profile_read synchronises the device and writes one text line per kernel, "name launches total_ms",

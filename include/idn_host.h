@@ -61,6 +61,7 @@ typedef struct {                    /* IdnCompressorParamsBuilder, idn/compresso
     int32_t mode;                   /* IDN_MODE_COMPAT (container version 1) or IDN_MODE_NATIVE (version 2) */
     uint32_t batch_blocks;          /* blocks per device call, default 32 */
     uint32_t lane_symbols;          /* native mode lane quantum, default 2048 */
+    uint64_t text_chunk_bytes;      /* add_text: bytes of FASTQ text per device call, default 256 Mi */
     uint32_t n_devices;             /* > 0: the GPUs that share the file (batches go round robin, results are committed in block
                                        order; the container does not depend on the device count) */
     int32_t devices[16];
@@ -76,6 +77,9 @@ int32_t idn_host_compressor_add(idn_host_compressor *c, const uint8_t *name, uin
 int32_t idn_host_compressor_add_batch(idn_host_compressor *c, uint64_t n_reads, const uint64_t *read_off,
                                       const uint8_t *acids, const uint8_t *quals, const uint64_t *name_off,
                                       const uint8_t *names);
+/* FASTQ text instead of parsed sequences: consecutive pieces of the text, cut anywhere (FastqReader + add_sequence of the
+ * reference, done on the device); not to be mixed with the two calls above on one compressor */
+int32_t idn_host_compressor_add_text(idn_host_compressor *c, const uint8_t *text, uint64_t n);
 int32_t idn_host_compressor_finish(idn_host_compressor *c);     /* IdnCompressor::finish */
 /* the container written so far (complete after finish); the pointer stays valid until the next call on `c` */
 uint64_t idn_host_compressor_output(const idn_host_compressor *c, const uint8_t **data);
@@ -88,6 +92,11 @@ void idn_host_compressor_free(idn_host_compressor *c);
 
 /* ---- IdnDecompressor (idn/decompressor.rs:455-566): next_sequence until None, results as one SoA batch ---- */
 typedef struct idn_host_decoded idn_host_decoded;
+/* the whole file as FASTQ text (FastqWriter of the reference, formatted on the device); free with idn_host_text_free */
+int32_t idn_host_decompress_text(const idn_host_model *const *models, uint32_t n_models, int32_t device, uint32_t batch_blocks,
+                                 uint32_t thread_num, int32_t title_with_separator, const uint8_t *idn, uint64_t idn_len,
+                                 uint8_t **text, uint64_t *text_len);
+void idn_host_text_free(uint8_t *text);
 /* `device` >= 0: that GPU; < 0: the first (-device) GPUs share the file */
 int32_t idn_host_decompress(const idn_host_model *const *models, uint32_t n_models, int32_t device, uint32_t batch_blocks,
                             const uint8_t *idn, uint64_t idn_len, idn_host_decoded **out);
