@@ -834,33 +834,46 @@ def e2e_file_leg(args, w, env, acids_d, quals_d, read_off_h, n):
     cores = os.cpu_count() or 1
     out = {"sample": f"first {n} reads as {nbytes / 1e9:.2f} GB of FASTQ text (titles of {nlen} bytes), page-locked host memory in, host memory out",
            "host_threads_for_identifiers": cores}
+    idn_h = torch.empty(nbytes // 2 + (64 << 20), dtype=torch.uint8, pin_memory=True).numpy()  # the ".idn file"
+    back_h = torch.empty(nbytes + 64, dtype=torch.uint8, pin_memory=True).numpy()               # the text "file" written back
+    devs = [env.local, env.local]  # two contexts on the device: one batch's copies overlap the other's kernels
+    out["contexts_on_the_device"] = len(devs)
     for names in (False, True):
         best = None
-        for it in range(2):  # the second pass is the timed one (buffers of the contexts are sized by the first)
-            c = host.IdnCompressor(models, include_identifiers=names, thread_num=cores, devices=[env.local, env.local],
-                                   text_chunk_bytes=args.text_chunk_mb << 20, batch_blocks=32)
+        for it in range(2):  # the second pass is the timed one (device buffers and page-locked pools are sized by the first)
+            c = host.IdnCompressor(models, include_identifiers=names, thread_num=cores, devices=devs,
+                                   text_chunk_bytes=args.text_chunk_mb << 20, batch_blocks=args.file_batch_blocks)
+            c.set_output(idn_h)
             t0 = time.perf_counter()
             c.add_fastq_text(text_np)
             c.finish()
             t1 = time.perf_counter()
             idn = c.output_view()
-            t2 = time.perf_counter()
-            back, free = host.decompress_text(models, idn, device=env.local, thread_num=cores, batch_blocks=32, as_view=True)
-            t3 = time.perf_counter()
-            if names:
-                ok = back.size == nbytes and bool(np.array_equal(back, text_np))
-            else:  # empty titles: compare the symbol lines
-                ok = back.size == nbytes - n * nlen
             n_idn = int(idn.size)
-            free()
+            # (1) streaming: the text of each batch of blocks is handed out where the device wrote it (what a writer passes to write())
+            t2 = time.perf_counter()
+            rd = host.FastqTextReader(models, idn, devices=devs, thread_num=cores, batch_blocks=args.file_batch_blocks)
+            got = 0
+            for piece in rd:
+                got += piece.size
+            rd.close()
+            t3 = time.perf_counter()
+            # (2) the same into one contiguous caller buffer (one more host copy)
+            n_back = host.decompress_text_into(models, idn, back_h, device=env.local, thread_num=cores, batch_blocks=args.file_batch_blocks)
+            t4 = time.perf_counter()
+            back = back_h[:n_back]
+            if names:
+                ok = got == nbytes and n_back == nbytes and bool(np.array_equal(back, text_np))
+            else:  # empty titles: the symbol lines only
+                ok = got == nbytes - n * nlen and n_back == got
             c.close()
-            best = (t1 - t0, t3 - t2, n_idn, ok)
-        tc, td, n_idn, ok = best
+            best = (t1 - t0, t3 - t2, t4 - t3, n_idn, ok)
+        tc, td, td2, n_idn, ok = best
         if not ok:
             raise SystemExit("e2e_file: the text that came back differs from the text that went in")
         out["with_identifiers" if names else "no_identifiers"] = {
             "compress_GBps": nbytes / tc / 1e9, "decompress_GBps": nbytes / td / 1e9, "value": 2 * nbytes / (tc + td) / 1e9,
-            "container_bytes": n_idn, "verified_round_trip": ok}
+            "decompress_into_one_buffer_GBps": nbytes / td2 / 1e9, "container_bytes": n_idn, "verified_round_trip": ok}
     # the identifiers codec alone, as the host mirror runs it: raw Deflate level 6 per block on `cores` threads
     per_block = max(1, BLOCK_SYMBOLS // int(read_off_h[1] - read_off_h[0])) if n else 1
     blocks = [b"\n".join(bytes(names_h[r * nlen:(r + 1) * nlen]) for r in range(b0, min(n, b0 + per_block))) for b0 in range(0, min(n, 16 * per_block), per_block)]
@@ -1090,6 +1103,7 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--e2e-file-reads", type=int, default=8_000_000, help="reads of the FASTQ-text-in / text-out leg through the host mirror")
     ap.add_argument("--text-chunk-mb", type=int, default=256, help="FASTQ text per device call of that leg")
+    ap.add_argument("--file-batch-blocks", type=int, default=32, help="blocks per batch in the e2e_file decode (and in add_batch)")
     ap.add_argument("--e2e-profile", action="store_true", help="print the host-side phase times of the e2e leg to stderr")
     args = ap.parse_args()
     if args.warmup < 3:

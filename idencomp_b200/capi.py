@@ -27,7 +27,7 @@ MODE_COMPAT, MODE_NATIVE = 1, 2
 # every symbol include/idn_gpu.h declares (tests check the library exports all of them)
 EXPORTS = [
     "idn_gpu_abi_version", "idn_gpu_device_count", "idn_gpu_create", "idn_gpu_destroy", "idn_gpu_last_error",
-    "idn_gpu_launch_count", "idn_gpu_kernel_variant", "idn_gpu_kernel_variant_count", "idn_gpu_set_pipeline_blocks", "idn_gpu_model_upload", "idn_gpu_model_release", "idn_gpu_score", "idn_gpu_score_dev",
+    "idn_gpu_launch_count", "idn_gpu_kernel_variant", "idn_gpu_kernel_variant_count", "idn_gpu_set_pipeline_blocks", "idn_gpu_host_alloc", "idn_gpu_host_free", "idn_gpu_model_upload", "idn_gpu_model_release", "idn_gpu_score", "idn_gpu_score_dev",
     "idn_gpu_compress_blocks", "idn_gpu_compress_blocks_dev", "idn_gpu_compress_bound", "idn_gpu_index_blocks",
     "idn_gpu_decompress_blocks", "idn_gpu_decompress_blocks_dev", "idn_gpu_decompress_reads", "idn_gpu_block_crc",
     "idn_gpu_synth_reads_dev", "idn_gpu_profile", "idn_gpu_profile_read", "idn_gpu_set_lane_symbols", "idn_gpu_set_walk",
@@ -106,6 +106,10 @@ def load():
     L.idn_gpu_kernel_variant.argtypes = [vp, i32, i32]
     L.idn_gpu_kernel_variant.restype = i32
     L.idn_gpu_kernel_variant_count.restype = i32
+    L.idn_gpu_host_alloc.argtypes = [u64, C.POINTER(vp)]
+    L.idn_gpu_host_alloc.restype = i32
+    L.idn_gpu_host_free.argtypes = [vp]
+    L.idn_gpu_host_free.restype = None
     L.idn_gpu_set_pipeline_blocks.argtypes = [vp, u32]
     L.idn_gpu_set_pipeline_blocks.restype = i32
     L.idn_gpu_model_upload.argtypes = [vp, i32, i32, i32, i32, i32, i32, u32, vp, vp, vp, u64, C.POINTER(i32)]
@@ -320,7 +324,8 @@ class Context:
         return int(tot.n_reads), int(tot.n_symbols), bf
 
     def decompress_blocks(self, blocks, block_off, block_crc, models, *, name_off=None, names=None, reads_cap=None,
-                          symbols_cap=None, mode=MODE_COMPAT, block_len=None):
+                          symbols_cap=None, mode=MODE_COMPAT, block_len=None, resident=False):
+        """resident=True: index the blocks, then decode the bytes that call left on the device (blocks == NULL)"""
         blocks = _c(blocks, np.uint8)
         bo = _c(block_off, np.uint64)
         bl = None if block_len is None else _c(block_len, np.uint32)
@@ -339,7 +344,9 @@ class Context:
             nm = _c(names, np.uint8)
             if nm.size == 0:
                 nm = np.zeros(1, dtype=np.uint8)
-        rc = self.L.idn_gpu_decompress_blocks(self.h, _p(blocks), bo.ctypes.data, _p(bl), _p(crc), nb, mode, _p(m), len(m),
+        if resident:
+            reads_cap, symbols_cap, _ = self.index_blocks(blocks, bo, m, bl, mode)
+        rc = self.L.idn_gpu_decompress_blocks(self.h, None if resident else _p(blocks), bo.ctypes.data, _p(bl), _p(crc), nb, mode, _p(m), len(m),
                                               None if nm is None else nm.ctypes.data,
                                               None if no is None else no.ctypes.data, a.ctypes.data, q.ctypes.data,
                                               ro.ctypes.data, reads_cap, symbols_cap, C.byref(bad))

@@ -125,6 +125,8 @@ extern "C" int32_t idn_host_quantise(const float* probs, uint32_t nsym, uint32_t
 
 struct idn_host_compressor {
     std::vector<uint8_t> out;
+    uint8_t* ext = nullptr;  // idn_host_compressor_set_output: the caller's buffer
+    uint64_t ext_cap = 0, ext_len = 0;
     std::unique_ptr<IdnCompressor> c;
 };
 
@@ -178,7 +180,15 @@ extern "C" int32_t idn_host_compressor_new(const idn_host_model* const* models, 
                                     .build();
         auto h = std::make_unique<idn_host_compressor>();
         idn_host_compressor* raw = h.get();
-        h->c = std::make_unique<IdnCompressor>([raw](const uint8_t* d, size_t n) { raw->out.insert(raw->out.end(), d, d + n); }, std::move(p));
+        h->c = std::make_unique<IdnCompressor>([raw](const uint8_t* d, size_t n) {
+            if (raw->ext) {
+                if (raw->ext_len + n > raw->ext_cap) throw IdnError(IDN_E_NOSPACE, "the output buffer is too small");
+                std::memcpy(raw->ext + raw->ext_len, d, n);
+                raw->ext_len += n;
+            } else {
+                raw->out.insert(raw->out.end(), d, d + n);
+            }
+        }, std::move(p));
         *out = h.release();
         return (int32_t)IDN_OK;
     });
@@ -245,7 +255,7 @@ extern "C" int32_t idn_host_decompress_text(const idn_host_model* const* models,
         uint8_t* buf = static_cast<uint8_t*>(std::malloc(cap));
         if (!buf) throw IdnError(IDN_E_IO, "out of memory");
         try {
-            std::unique_ptr<uint8_t[]> piece;
+            std::shared_ptr<PinnedBuf> piece;
             size_t n = 0;
             while (d.next_fastq_text(piece, n, title_with_separator != 0)) {
                 if (used + n > cap) {
@@ -254,7 +264,7 @@ extern "C" int32_t idn_host_decompress_text(const idn_host_model* const* models,
                     if (!nb) throw IdnError(IDN_E_IO, "out of memory");
                     buf = nb;
                 }
-                std::memcpy(buf + used, piece.get(), n);
+                std::memcpy(buf + used, piece->p, n);
                 used += n;
             }
         } catch (...) {
@@ -268,6 +278,108 @@ extern "C" int32_t idn_host_decompress_text(const idn_host_model* const* models,
 }
 extern "C" void idn_host_text_free(uint8_t* text) { std::free(text); }
 
+// the same into the caller's buffer (page-locked and touched, if the caller wants the full rate); IDN_E_NOSPACE with
+// *text_len = bytes written so far when it is too small
+extern "C" int32_t idn_host_decompress_text_into(const idn_host_model* const* models, uint32_t n_models, int32_t device, uint32_t batch_blocks,
+                                                 uint32_t thread_num, int32_t title_with_separator, const uint8_t* idn, uint64_t idn_len,
+                                                 uint8_t* text, uint64_t cap, uint64_t* text_len) {
+    if (!text_len || (!text && cap) || (!idn && idn_len) || (n_models && !models)) return set_err(IDN_E_INVALID_ARG, "NULL argument");
+    *text_len = 0;
+    return guarded([&] {
+        IdnDecompressorParams p;
+        p.model_provider = provider_of(models, n_models);
+        p.thread_num = thread_num;
+        if (device >= 0) {
+            p.devices.assign(1, device);
+        } else {
+            p.devices.clear();
+            for (int32_t d = 0; d < -device; d++) p.devices.push_back(d);
+        }
+        p.batch_blocks = batch_blocks ? batch_blocks : 32;
+        uint64_t pos = 0;
+        IdnDecompressor d([&](uint8_t* dst, size_t n) {
+            size_t k = (size_t)std::min<uint64_t>(n, idn_len - pos);
+            std::memcpy(dst, idn + pos, k);
+            pos += k;
+            return k;
+        }, std::move(p));
+        std::shared_ptr<PinnedBuf> piece;
+        size_t n = 0;
+        uint64_t used = 0;
+        while (d.next_fastq_text(piece, n, title_with_separator != 0)) {
+            if (used + n > cap) {
+                *text_len = used;
+                throw IdnError(IDN_E_NOSPACE, "the text buffer is too small");
+            }
+            std::memcpy(text + used, piece->p, n);
+            used += n;
+        }
+        *text_len = used;
+        return (int32_t)IDN_OK;
+    });
+}
+
+// streaming form: every call hands out the FASTQ text of the next batch of blocks where the device wrote it (page-locked
+// memory of the library, valid until the next call on this reader); a writer passes the pieces to write() as they come
+struct idn_host_text_reader {
+    std::unique_ptr<IdnDecompressor> d;
+    const uint8_t* idn = nullptr;
+    uint64_t idn_len = 0, pos = 0;
+    std::shared_ptr<PinnedBuf> piece;
+    bool sep = false;
+};
+extern "C" int32_t idn_host_text_reader_new(const idn_host_model* const* models, uint32_t n_models, const int32_t* devices, uint32_t n_devices,
+                                            uint32_t batch_blocks, uint32_t thread_num, int32_t title_with_separator, const uint8_t* idn,
+                                            uint64_t idn_len, idn_host_text_reader** out) {
+    if (!out || (!idn && idn_len) || (n_models && !models) || (n_devices && !devices)) return set_err(IDN_E_INVALID_ARG, "NULL argument");
+    *out = nullptr;
+    return guarded([&] {
+        auto r = std::make_unique<idn_host_text_reader>();
+        IdnDecompressorParams p;
+        p.model_provider = provider_of(models, n_models);
+        p.thread_num = thread_num;
+        if (n_devices) p.devices.assign(devices, devices + n_devices);
+        p.batch_blocks = batch_blocks ? batch_blocks : 32;
+        r->idn = idn;
+        r->idn_len = idn_len;
+        r->sep = title_with_separator != 0;
+        idn_host_text_reader* raw = r.get();
+        r->d = std::make_unique<IdnDecompressor>([raw](uint8_t* dst, size_t n) {
+            size_t k = (size_t)std::min<uint64_t>(n, raw->idn_len - raw->pos);
+            std::memcpy(dst, raw->idn + raw->pos, k);
+            raw->pos += k;
+            return k;
+        }, std::move(p));
+        *out = r.release();
+        return (int32_t)IDN_OK;
+    });
+}
+// *len = 0 and *text = NULL at the end of the container
+extern "C" int32_t idn_host_text_reader_next(idn_host_text_reader* r, const uint8_t** text, uint64_t* len) {
+    if (!r || !text || !len) return set_err(IDN_E_INVALID_ARG, "NULL argument");
+    *text = nullptr;
+    *len = 0;
+    return guarded([&] {
+        size_t n = 0;
+        r->piece.reset();
+        if (r->d->next_fastq_text(r->piece, n, r->sep)) {
+            *text = r->piece->p;
+            *len = n;
+        }
+        return (int32_t)IDN_OK;
+    });
+}
+extern "C" void idn_host_text_reader_free(idn_host_text_reader* r) { delete r; }
+
+// the compressor writes into the caller's buffer instead of the library's growing one (set before the first add)
+extern "C" int32_t idn_host_compressor_set_output(idn_host_compressor* c, uint8_t* buf, uint64_t cap) {
+    if (!c || (!buf && cap)) return set_err(IDN_E_INVALID_ARG, "NULL argument");
+    c->ext = buf;
+    c->ext_cap = cap;
+    c->ext_len = 0;
+    return IDN_OK;
+}
+
 extern "C" int32_t idn_host_compressor_finish(idn_host_compressor* c) {
     if (!c) return set_err(IDN_E_INVALID_ARG, "NULL argument");
     return guarded([&] {
@@ -277,6 +389,10 @@ extern "C" int32_t idn_host_compressor_finish(idn_host_compressor* c) {
 }
 
 extern "C" uint64_t idn_host_compressor_output(const idn_host_compressor* c, const uint8_t** data) {
+    if (c->ext) {
+        if (data) *data = c->ext;
+        return c->ext_len;
+    }
     if (data) *data = c->out.data();
     return c->out.size();
 }

@@ -9,6 +9,8 @@
 #include <algorithm>
 #include <atomic>
 #include <chrono>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <future>
 #include <numeric>
@@ -141,6 +143,94 @@ struct Brotli {
 
 }  // namespace
 
+// ---- IDN_HOST_TRACE=1: wall time per stage of the host mirror, summed over threads, printed when an object closes -----------
+namespace {
+struct Trace {
+    static constexpr int kN = 12;
+    const char* name[kN] = {"parse_chunk", "first_block_select", "names_fetch", "names_deflate", "compress_parsed", "compress_blocks",
+                            "sink", "read_raw", "index_blocks", "names_inflate", "decode", "wait_worker"};
+    std::atomic<uint64_t> ns[kN];
+    std::atomic<uint64_t> calls[kN];
+    bool on = std::getenv("IDN_HOST_TRACE") != nullptr;
+    Trace() {
+        for (int i = 0; i < kN; i++) ns[i] = calls[i] = 0;
+    }
+    void print(const char* who) {
+        if (!on) return;
+        std::fprintf(stderr, "[idn_host trace] %s:", who);
+        for (int i = 0; i < kN; i++)
+            if (calls[i]) std::fprintf(stderr, " %s %.1f ms/%llu", name[i], ns[i].exchange(0) / 1e6, (unsigned long long)calls[i].exchange(0));
+        std::fprintf(stderr, "\n");
+    }
+};
+Trace g_trace;
+struct Span {
+    int k;
+    std::chrono::steady_clock::time_point t0;
+    explicit Span(int k_) : k(k_) {
+        if (g_trace.on) t0 = std::chrono::steady_clock::now();
+    }
+    ~Span() {
+        if (!g_trace.on) return;
+        g_trace.ns[k] += (uint64_t)std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now() - t0).count();
+        g_trace.calls[k]++;
+    }
+};
+enum { T_PARSE, T_SELECT, T_NFETCH, T_NDEFLATE, T_CPARSED, T_CBLOCKS, T_SINK, T_READRAW, T_INDEX, T_NINFLATE, T_DECODE, T_WAIT };
+}  // namespace
+
+// ---- page-locked buffers -------------------------------------------------------------------------------------------------
+void PinnedBuf::ensure(size_t n) {
+    if (n <= cap) return;
+    idn_gpu_host_free(p);
+    p = nullptr;
+    cap = 0;
+    void* q = nullptr;
+    const size_t want = n + n / 8 + 4096;
+    if (idn_gpu_host_alloc(want, &q) != IDN_OK) throw IdnError(IDN_E_IO, "cannot allocate " + std::to_string(want) + " bytes of page-locked host memory");
+    p = static_cast<uint8_t*>(q);
+    cap = want;
+}
+
+void PinnedBuf::ensure_keep(size_t n, size_t used) {
+    if (n <= cap) return;
+    void* q = nullptr;
+    const size_t want = n + n / 2 + 4096;
+    if (idn_gpu_host_alloc(want, &q) != IDN_OK) throw IdnError(IDN_E_IO, "cannot allocate " + std::to_string(want) + " bytes of page-locked host memory");
+    if (used) std::memcpy(q, p, used);
+    idn_gpu_host_free(p);
+    p = static_cast<uint8_t*>(q);
+    cap = want;
+}
+
+std::shared_ptr<PinnedBuf> PinnedPool::get(size_t n) {
+    std::unique_ptr<PinnedBuf> b;
+    {
+        std::lock_guard<std::mutex> lk(st_->mu);
+        // the smallest free buffer that fits, else the largest (it grows)
+        size_t pick = st_->free_.size();
+        for (size_t i = 0; i < st_->free_.size(); i++) {
+            const size_t c = st_->free_[i]->cap;
+            if (pick == st_->free_.size()) pick = i;
+            else {
+                const size_t pc = st_->free_[pick]->cap;
+                if ((c >= n && (pc < n || c < pc)) || (c < n && pc < n && c > pc)) pick = i;
+            }
+        }
+        if (pick < st_->free_.size()) {
+            b = std::move(st_->free_[pick]);
+            st_->free_.erase(st_->free_.begin() + pick);
+        }
+    }
+    if (!b) b = std::make_unique<PinnedBuf>();
+    b->ensure(n);
+    std::shared_ptr<State> st = st_;
+    return std::shared_ptr<PinnedBuf>(b.release(), [st](PinnedBuf* q) {
+        std::lock_guard<std::mutex> lk(st->mu);
+        st->free_.emplace_back(q);
+    });
+}
+
 // ---- DeviceModels ---------------------------------------------------------------------------------------------------
 DeviceModels::~DeviceModels() {
     if (ctx_) idn_gpu_destroy(ctx_);
@@ -187,6 +277,7 @@ IdnCompressor::IdnCompressor(Sink sink, IdnCompressorParams params) : sink_(std:
 IdnCompressor::~IdnCompressor() {
     for (auto& f : pending_)  // jobs still running hold references to this object
         if (f.valid()) f.wait();
+    g_trace.print("compressor");
 }
 
 void IdnCompressor::add_sequence(FastqSequence seq) {
@@ -379,10 +470,11 @@ IdnCompressor::Result IdnCompressor::compress_batch(Worker& w, const Batch& bt) 
     uint64_t cap = std::min<uint64_t>(bound, b.n_symbols + b.n_symbols / 4 + 24 * n_reads + 64ull * n_blocks + res.prefix_total + 4096);
     std::vector<uint64_t> block_off(n_blocks + 1);
     idn_compress_stats st{};
+    Span sp_c(T_CBLOCKS);
     for (;;) {
-        res.bytes.reset(new uint8_t[cap]);
+        res.buf = pool_.get(cap);
         int32_t rc = idn_gpu_compress_blocks(w.dev.ctx(), &b, params_.mode, w.dev.handles().data(), (uint32_t)w.dev.handles().size(),
-                                             params_.fast ? 1 : 0, params_.include_identifiers ? prefix.data() : nullptr, res.bytes.get(),
+                                             params_.fast ? 1 : 0, params_.include_identifiers ? prefix.data() : nullptr, res.buf->p,
                                              cap, block_off.data(), nullptr, &st);
         if (rc == IDN_E_NOSPACE && cap < bound) {
             cap = bound;
@@ -392,7 +484,7 @@ IdnCompressor::Result IdnCompressor::compress_batch(Worker& w, const Batch& bt) 
         break;
     }
     for (uint32_t k = 0; k < n_blocks; k++)
-        if (prefix[k]) std::memcpy(res.bytes.get() + block_off[k] + 8, name_slices[k].data(), prefix[k]);
+        if (prefix[k]) std::memcpy(res.buf->p + block_off[k] + 8, name_slices[k].data(), prefix[k]);
     res.out_bytes = st.out_bytes;
     res.payload_bytes = st.payload_bytes;
     res.acid_switches = st.acid_switches;
@@ -418,9 +510,14 @@ void IdnCompressor::commit(bool all) {
     while (!pending_.empty()) {
         const bool ready = pending_.front().wait_for(std::chrono::seconds(0)) == std::future_status::ready;
         if (!ready && pending_.size() <= keep) break;
-        Result r = pending_.front().get();  // rethrows what the job threw
+        Result r;
+        {
+            Span spw(T_WAIT);
+            r = pending_.front().get();  // rethrows what the job threw
+        }
         pending_.pop_front();
-        sink_(r.bytes.get(), r.out_bytes);  // blocks in order: this replaces IdnBlockLock (common.rs:10-57)
+        Span sp(T_SINK);
+        sink_(r.buf->p, r.out_bytes);  // blocks in order: this replaces IdnBlockLock (common.rs:10-57)
         stats_.out_bytes += r.out_bytes;
         stats_.out_identifier_bytes += r.prefix_total;
         stats_.out_payload_bytes += r.payload_bytes;
@@ -494,8 +591,12 @@ size_t IdnCompressor::consume_text(const uint8_t* buf, size_t total, bool final)
             }
         }
         Worker* w = workers_[next_worker_++ % workers_.size()].get();
-        w->acquire();  // released by the job below
+        {
+            Span sp(T_WAIT);
+            w->acquire();  // released by the job below
+        }
         idn_fastq_chunk ck{};
+        Span sp_parse(T_PARSE);
         int32_t rc = idn_gpu_fastq_parse_chunk(w->dev.ctx(), buf + text_pos_, len, last ? 1 : 0, params_.max_block_total_len, &ck);
         if (rc) {
             std::string what = idn_gpu_last_error(w->dev.ctx());
@@ -514,6 +615,7 @@ size_t IdnCompressor::consume_text(const uint8_t* buf, size_t total, bool final)
             continue;
         }
         if (!initialized_) {
+            Span sp_sel(T_SELECT);
             // file-level model selection on the reads of the first block (compressor_initializer.rs:53-74): they are on the
             // device; bring them back once and go through the same initialize() as the add_sequence path
             ModelProvider& mp = params_.model_provider;
@@ -573,8 +675,12 @@ IdnCompressor::Result IdnCompressor::compress_parsed(Worker& w, uint32_t n_block
         std::vector<uint8_t> names(n_name_bytes + 1);
         std::vector<uint64_t> name_off(n_reads + 1);
         std::vector<uint32_t> block_first(n_blocks + 1);
-        int32_t rc = idn_gpu_fastq_chunk_fetch(w.dev.ctx(), names.data(), name_off.data(), block_first.data(), nullptr, nullptr, nullptr);
-        if (rc) w.dev.raise(rc);
+        {
+            Span sp(T_NFETCH);
+            int32_t rc = idn_gpu_fastq_chunk_fetch(w.dev.ctx(), names.data(), name_off.data(), block_first.data(), nullptr, nullptr, nullptr);
+            if (rc) w.dev.raise(rc);
+        }
+        Span sp(T_NDEFLATE);
         identifier_slices(params_.quality, params_.thread_num, n_blocks, block_first.data(), names.data(), name_off.data(), name_slices, prefix);
     }
     res.prefix_total = std::accumulate(prefix.begin(), prefix.end(), (uint64_t)0);
@@ -582,11 +688,12 @@ IdnCompressor::Result IdnCompressor::compress_parsed(Worker& w, uint32_t n_block
     uint64_t cap = std::min<uint64_t>(bound, n_symbols + n_symbols / 4 + 24 * n_reads + 64ull * n_blocks + res.prefix_total + 4096);
     std::vector<uint64_t> block_off(n_blocks + 1);
     idn_compress_stats st{};
+    Span sp_c(T_CPARSED);
     for (;;) {
-        res.bytes.reset(new uint8_t[cap]);
+        res.buf = pool_.get(cap);
         int32_t rc = idn_gpu_compress_parsed(w.dev.ctx(), params_.mode, w.dev.handles().data(), (uint32_t)w.dev.handles().size(), params_.fast ? 1 : 0,
                                              params_.include_identifiers ? 1 : 0, params_.include_identifiers ? prefix.data() : nullptr,
-                                             res.bytes.get(), cap, block_off.data(), nullptr, &st);
+                                             res.buf->p, cap, block_off.data(), nullptr, &st);
         if (rc == IDN_E_NOSPACE && cap < bound) {
             cap = bound;
             continue;
@@ -595,7 +702,7 @@ IdnCompressor::Result IdnCompressor::compress_parsed(Worker& w, uint32_t n_block
         break;
     }
     for (uint32_t k = 0; k < n_blocks; k++)
-        if (prefix[k]) std::memcpy(res.bytes.get() + block_off[k] + 8, name_slices[k].data(), prefix[k]);
+        if (prefix[k]) std::memcpy(res.buf->p + block_off[k] + 8, name_slices[k].data(), prefix[k]);
     res.out_bytes = st.out_bytes;
     res.payload_bytes = st.payload_bytes;
     res.acid_switches = st.acid_switches;
@@ -632,6 +739,7 @@ IdnDecompressor::IdnDecompressor(Source source, IdnDecompressorParams params) : 
 IdnDecompressor::~IdnDecompressor() {
     for (auto& f : pending_)
         if (f.valid()) f.wait();
+    g_trace.print("decompressor");
 }
 
 void IdnDecompressor::read_exact(uint8_t* dst, size_t n, const char* what) {
@@ -676,7 +784,10 @@ void IdnDecompressor::initialize() {
 
 bool IdnDecompressor::read_raw(RawBatch& rb) {
     // block headers + payloads of up to batch_blocks blocks into one buffer (idn/decompressor.rs:387-428)
+    Span sp(T_READRAW);
     bool more = true;
+    rb.buf = pool_.get(raw_hint_);
+    rb.used = 0;
     while (rb.off.size() < params_.batch_blocks) {
         uint8_t h[8];
         read_exact(h, 8, "a block header");
@@ -685,12 +796,14 @@ bool IdnDecompressor::read_raw(RawBatch& rb) {
             more = false;
             break;
         }
-        rb.off.push_back(rb.buf.size());
+        rb.off.push_back(rb.used);
         rb.len.push_back(n);
         rb.crc.push_back(c);
-        rb.buf.resize(rb.buf.size() + n);
-        read_exact(rb.buf.data() + rb.off.back(), n, "a block");
+        rb.buf->ensure_keep(rb.used + n, rb.used);
+        read_exact(rb.buf->p + rb.used, n, "a block");
+        rb.used += n;
     }
+    raw_hint_ = std::max(raw_hint_, rb.used);
     return more;
 }
 
@@ -703,7 +816,7 @@ void IdnDecompressor::inflate_names(const RawBatch& rb, const std::vector<uint64
     std::vector<std::vector<uint8_t>> text(n_blocks);
     std::vector<uint8_t> has(n_blocks, 0);
     auto one = [&](uint32_t b) {
-        const uint8_t* p = rb.buf.data() + off[b];
+        const uint8_t* p = rb.buf->p + off[b];
         size_t pos = 0;
         while (pos < rb.len[b] && p[pos] == 0x00) {
             if (pos + 6 > rb.len[b]) throw IdnError(IDN_E_SERIALIZE, "truncated identifiers slice");
@@ -756,21 +869,30 @@ IdnDecompressor::DecodedBatch IdnDecompressor::decode_batch(Worker& w, const Raw
     const uint32_t n_blocks = (uint32_t)rb.off.size();
     if (n_blocks == 0) return out;
     std::vector<uint64_t> off = rb.off;
-    off.push_back(rb.buf.size());
+    off.push_back(rb.used);
     const int32_t mode = version_ == 2 ? IDN_MODE_NATIVE : IDN_MODE_COMPAT;
     const auto& handles = w.dev.handles();
     idn_block_index_totals tot{};
     std::vector<uint32_t> block_first(n_blocks + 1);
-    int32_t rc = idn_gpu_index_blocks(w.dev.ctx(), rb.buf.data(), off.data(), rb.len.data(), n_blocks, mode, handles.data(),
-                                      (uint32_t)handles.size(), &tot, block_first.data());
+    int32_t rc;
+    {
+        Span sp(T_INDEX);
+        rc = idn_gpu_index_blocks(w.dev.ctx(), rb.buf->p, off.data(), rb.len.data(), n_blocks, mode, handles.data(), (uint32_t)handles.size(), &tot,
+                                  block_first.data());
+    }
     if (rc) w.dev.raise(rc);
-    inflate_names(rb, off, block_first, tot.n_reads, out);
+    {
+        Span sp(T_NINFLATE);
+        inflate_names(rb, off, block_first, tot.n_reads, out);
+    }
+    Span sp_d(T_DECODE);
     out.acids.resize(tot.n_symbols + 1);
     out.quals.resize(tot.n_symbols + 1);
     out.read_off.assign(tot.n_reads + 1, 0);
     int32_t bad = -1;
     if (out.names.empty()) out.names.push_back(0);
-    rc = idn_gpu_decompress_blocks(w.dev.ctx(), rb.buf.data(), off.data(), rb.len.data(), rb.crc.data(), n_blocks, mode, handles.data(),
+    // with identifiers the call is not pipelined and can use the bytes idn_gpu_index_blocks left on the device (blocks == NULL)
+    rc = idn_gpu_decompress_blocks(w.dev.ctx(), out.any_names ? nullptr : rb.buf->p, off.data(), rb.len.data(), rb.crc.data(), n_blocks, mode, handles.data(),
                                    (uint32_t)handles.size(), out.any_names ? out.names.data() : nullptr,
                                    out.any_names ? out.name_off.data() : nullptr, out.acids.data(), out.quals.data(), out.read_off.data(),
                                    tot.n_reads, tot.n_symbols, &bad);
@@ -788,32 +910,41 @@ IdnDecompressor::DecodedBatch IdnDecompressor::decode_text(Worker& w, const RawB
     const uint32_t n_blocks = (uint32_t)rb.off.size();
     if (n_blocks == 0) return out;
     std::vector<uint64_t> off = rb.off;
-    off.push_back(rb.buf.size());
+    off.push_back(rb.used);
     const int32_t mode = version_ == 2 ? IDN_MODE_NATIVE : IDN_MODE_COMPAT;
     const auto& handles = w.dev.handles();
     idn_block_index_totals tot{};
     std::vector<uint32_t> block_first(n_blocks + 1);
-    int32_t rc = idn_gpu_index_blocks(w.dev.ctx(), rb.buf.data(), off.data(), rb.len.data(), n_blocks, mode, handles.data(),
-                                      (uint32_t)handles.size(), &tot, block_first.data());
+    int32_t rc;
+    {
+        Span sp(T_INDEX);
+        rc = idn_gpu_index_blocks(w.dev.ctx(), rb.buf->p, off.data(), rb.len.data(), n_blocks, mode, handles.data(), (uint32_t)handles.size(), &tot,
+                                  block_first.data());
+    }
     if (rc) w.dev.raise(rc);
-    inflate_names(rb, off, block_first, tot.n_reads, out);
+    {
+        Span sp(T_NINFLATE);
+        inflate_names(rb, off, block_first, tot.n_reads, out);
+    }
+    Span sp_d(T_DECODE);
     if (out.names.empty()) out.names.push_back(0);
     const uint64_t name_bytes = out.any_names ? out.name_off[tot.n_reads] : 0;
     const uint64_t cap = 2 * tot.n_symbols + 6 * tot.n_reads + name_bytes * (title_with_separator ? 2 : 1) + 64;
-    out.text.reset(new uint8_t[cap]);
+    out.text = pool_.get(cap);
     uint64_t text_len = 0, n_reads = 0;
     int32_t bad = -1;
-    rc = idn_gpu_decompress_to_fastq(w.dev.ctx(), rb.buf.data(), off.data(), rb.len.data(), rb.crc.data(), n_blocks, mode, handles.data(),
+    // blocks == NULL: the bytes idn_gpu_index_blocks just uploaded are still on the device
+    rc = idn_gpu_decompress_to_fastq(w.dev.ctx(), nullptr, off.data(), rb.len.data(), rb.crc.data(), n_blocks, mode, handles.data(),
                                      (uint32_t)handles.size(), out.any_names ? out.names.data() : nullptr,
                                      out.any_names ? out.name_off.data() : nullptr, tot.n_reads, tot.n_symbols, title_with_separator ? 1 : 0,
-                                     out.text.get(), cap, &text_len, &n_reads, &bad);
+                                     out.text->p, cap, &text_len, &n_reads, &bad);
     if (rc) w.dev.raise(rc);
     out.text_len = text_len;
     out.read_off.assign(1, n_reads);  // [0] = sequences in the text
     return out;
 }
 
-bool IdnDecompressor::next_fastq_text(std::unique_ptr<uint8_t[]>& out, size_t& len, bool title_with_separator) {
+bool IdnDecompressor::next_fastq_text(std::shared_ptr<PinnedBuf>& out, size_t& len, bool title_with_separator) {
     if (!initialized_) initialize();
     text_mode_ = title_with_separator ? 2 : 1;
     prefetch();

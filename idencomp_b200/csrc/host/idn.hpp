@@ -86,6 +86,29 @@ private:
     IdnCompressorParams p_;
 };
 
+// page-locked host buffers, reused: what the device copies into (container bytes, FASTQ text) before the sink / the caller
+// gets it.  Fresh pageable memory per batch costs a page fault per 4 KB and a staged copy; these cost neither.
+struct PinnedBuf {
+    uint8_t* p = nullptr;
+    size_t cap = 0;
+    PinnedBuf() = default;
+    PinnedBuf(const PinnedBuf&) = delete;
+    PinnedBuf& operator=(const PinnedBuf&) = delete;
+    ~PinnedBuf() { idn_gpu_host_free(p); }
+    void ensure(size_t n);                 // contents are not kept
+    void ensure_keep(size_t n, size_t used);  // the first `used` bytes are
+};
+class PinnedPool {
+public:
+    std::shared_ptr<PinnedBuf> get(size_t n);  // a buffer of at least n bytes; goes back to the pool when the last owner lets go
+private:
+    struct State {
+        std::mutex mu;
+        std::vector<std::unique_ptr<PinnedBuf>> free_;
+    };
+    std::shared_ptr<State> st_ = std::make_shared<State>();
+};
+
 // RAII over idn_gpu_ctx + the handles of the uploaded models of one provider
 class DeviceModels {
 public:
@@ -139,7 +162,7 @@ private:
         }
     };
     struct Result {  // one compressed batch, ready to be written
-        std::unique_ptr<uint8_t[]> bytes;  // (not a vector: no zero fill of the capacity)
+        std::shared_ptr<PinnedBuf> buf;  // page-locked, pooled
         uint64_t out_bytes = 0, prefix_total = 0, payload_bytes = 0, acid_switches = 0, q_switches = 0, blocks = 0;
     };
     struct Worker {  // one device: its context, its uploaded models; one job at a time (a job may change threads)
@@ -174,6 +197,7 @@ private:
     IdnCompressorParams params_;
     std::vector<std::unique_ptr<Worker>> workers_;  // one per entry of params_.devices
     size_t next_worker_ = 0;
+    mutable PinnedPool pool_;
     std::deque<std::future<Result>> pending_;       // batches in flight, in block order
     CompressionStats stats_;
     std::vector<ModelIdentifier> retained_;
@@ -205,17 +229,18 @@ public:
         std::vector<uint8_t> acids, quals, names;
         std::vector<uint64_t> read_off{0}, name_off{0};
         bool any_names = false;
-        std::unique_ptr<uint8_t[]> text;  // next_fastq_text: the FASTQ text (not a vector: no zero fill of the capacity)
+        std::shared_ptr<PinnedBuf> text;  // next_fastq_text: the FASTQ text (page-locked, pooled)
         size_t text_len = 0;
     };
     bool next_batch(DecodedBatch& out);
     // the FASTQ text of the next batch of sequences, formatted on the device as FastqWriter does (fastq/writer.rs:190-245);
     // false at the end of the file.  Do not mix with next_sequence / next_batch on one object.
-    bool next_fastq_text(std::unique_ptr<uint8_t[]>& out, size_t& len, bool title_with_separator = false);
+    bool next_fastq_text(std::shared_ptr<PinnedBuf>& out, size_t& len, bool title_with_separator = false);
 
 private:
     struct RawBatch {  // container bytes of some blocks, as read from the source
-        std::vector<uint8_t> buf;
+        std::shared_ptr<PinnedBuf> buf;  // page-locked, pooled: the device reads it at the link's rate
+        size_t used = 0;
         std::vector<uint64_t> off;
         std::vector<uint32_t> len, crc;
     };
@@ -236,6 +261,8 @@ private:
     IdnDecompressorParams params_;
     std::vector<std::unique_ptr<Worker>> workers_;
     size_t next_worker_ = 0;
+    mutable PinnedPool pool_;
+    size_t raw_hint_ = 1 << 20;  // bytes of the largest batch read so far
     std::deque<std::future<DecodedBatch>> pending_;
     int text_mode_ = 0;  // 0 sequences / batches, 1 text, 2 text with the title repeated on the separator line
     bool initialized_ = false, eof_ = false;

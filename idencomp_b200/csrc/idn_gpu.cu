@@ -134,6 +134,8 @@ struct idn_gpu_ctx {
     // staging of the host-pointer paths
     DevBuf s_acids, s_quals, s_readoff, s_blockfirst, s_prefix, s_names, s_nameoff, s_out, s_blockoff, s_crc, s_stats,
         s_sizes, s_blocks, s_blocklen, s_aout, s_qout, s_offout, s_status, s_idx;
+    uint64_t resident_bytes = 0;   // container bytes idn_gpu_index_blocks / the decoder left in s_blocks ...
+    uint32_t resident_blocks = 0;  // ... and how many blocks they are (0: nothing a decode call may reuse)
 };
 
 namespace {
@@ -411,6 +413,20 @@ extern "C" void idn_gpu_destroy(idn_gpu_ctx* ctx) {
     if (ctx->ev) cudaEventDestroy(ctx->ev);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
+}
+
+extern "C" int32_t idn_gpu_host_alloc(uint64_t bytes, void** p) {
+    if (!p) return IDN_E_INVALID_ARG;
+    *p = nullptr;
+    if (cudaHostAlloc(p, bytes ? bytes : 1, cudaHostAllocPortable) != cudaSuccess) {
+        (void)cudaGetLastError();
+        *p = nullptr;
+        return IDN_E_CUDA;
+    }
+    return IDN_OK;
+}
+extern "C" void idn_gpu_host_free(void* p) {
+    if (p) cudaFreeHost(p);
 }
 
 extern "C" int32_t idn_gpu_set_walk(idn_gpu_ctx* ctx, int32_t mode) {
@@ -1550,7 +1566,10 @@ extern "C" int32_t idn_gpu_index_blocks(idn_gpu_ctx* ctx, const uint8_t* blocks,
     CU(ctx->s_blocks.ensure(nbytes + 16));
     CU(ctx->s_blockoff.ensure(((size_t)n_blocks + 1) * 8));
     CU(ctx->s_blocklen.ensure(((size_t)n_blocks + 1) * 4));
+    ctx->resident_blocks = 0;
     if (nbytes) CU(cudaMemcpyAsync(ctx->s_blocks.p, blocks, nbytes, cudaMemcpyHostToDevice, st));
+    ctx->resident_bytes = nbytes;
+    ctx->resident_blocks = n_blocks;
     CU(cudaMemcpyAsync(ctx->s_blockoff.p, block_off, ((size_t)n_blocks + 1) * 8, cudaMemcpyHostToDevice, st));
     if (block_len) CU(cudaMemcpyAsync(ctx->s_blocklen.p, block_len, (size_t)n_blocks * 4, cudaMemcpyHostToDevice, st));
     SmallParams sp;
@@ -1609,10 +1628,15 @@ static int32_t decompress_to_staging(idn_gpu_ctx* ctx, const uint8_t* blocks, co
     int32_t rc0 = check_block_table(ctx, block_off, block_len, n_blocks);
     if (rc0) return rc0;
     const uint64_t nbytes = n_blocks ? block_off[n_blocks] : 0;
-    if (!blocks && nbytes) return fail(ctx, IDN_E_INVALID_ARG, "blocks is NULL");
+    // blocks == NULL: the container bytes the last idn_gpu_index_blocks call on this context uploaded (same table)
+    const bool resident = !blocks && nbytes && ctx->resident_blocks == n_blocks && ctx->resident_bytes == nbytes;
+    if (!blocks && nbytes && !resident) return fail(ctx, IDN_E_INVALID_ARG, "blocks is NULL and the context holds no indexed blocks of this table");
     CU(cudaSetDevice(ctx->device));
     cudaStream_t st = ctx->stream;
-    CU(ctx->s_blocks.ensure(nbytes + 16));
+    if (!resident) {
+        ctx->resident_blocks = 0;
+        CU(ctx->s_blocks.ensure(nbytes + 16));
+    }
     CU(ctx->s_blockoff.ensure(((size_t)n_blocks + 1) * 8));
     CU(ctx->s_crc.ensure(((size_t)n_blocks + 1) * 4));
     CU(ctx->s_aout.ensure(out_symbols_cap + 16));
@@ -1620,7 +1644,7 @@ static int32_t decompress_to_staging(idn_gpu_ctx* ctx, const uint8_t* blocks, co
     CU(ctx->s_offout.ensure((out_reads_cap + 1) * 8));
     CU(ctx->s_status.ensure(64));
     HostTimer ht(ctx);
-    if (nbytes) CU(cudaMemcpyAsync(ctx->s_blocks.p, blocks, nbytes, cudaMemcpyHostToDevice, st));
+    if (nbytes && !resident) CU(cudaMemcpyAsync(ctx->s_blocks.p, blocks, nbytes, cudaMemcpyHostToDevice, st));
     CU(cudaMemcpyAsync(ctx->s_blockoff.p, block_off, ((size_t)n_blocks + 1) * 8, cudaMemcpyHostToDevice, st));
     CU(ctx->s_blocklen.ensure(((size_t)n_blocks + 1) * 4));
     if (block_len && n_blocks) CU(cudaMemcpyAsync(ctx->s_blocklen.p, block_len, (size_t)n_blocks * 4, cudaMemcpyHostToDevice, st));
@@ -1709,11 +1733,9 @@ extern "C" int32_t idn_gpu_decompress_blocks(idn_gpu_ctx* ctx, const uint8_t* bl
     if (out_symbols_cap && (!acids_out || !quals_out)) return fail(ctx, IDN_E_INVALID_ARG, "NULL output");
     int32_t rc0 = check_block_table(ctx, block_off, block_len, n_blocks);
     if (rc0) return rc0;
-    uint64_t nbytes = n_blocks ? block_off[n_blocks] : 0;
-    if (!blocks && nbytes) return fail(ctx, IDN_E_INVALID_ARG, "blocks is NULL");
     CU(cudaSetDevice(ctx->device));
     cudaStream_t st = ctx->stream;
-    if (!names && n_blocks) {
+    if (!names && n_blocks && blocks) {
         // no names on the device (the block CRCs cover the symbols only): sub-chunks of whole blocks flow through upload /
         // kernels / download streams; a sub-chunk that outgrows its share of the staging sends the call down the path below
         int32_t rcm = check_models(ctx, models, n_models);
@@ -1770,6 +1792,7 @@ extern "C" int32_t idn_gpu_decompress_reads(idn_gpu_ctx* ctx, const uint8_t* pay
     rc = upload_small(ctx, sp, st);
     if (rc) return rc;
     SmallParams* dsp = ctx->w_small.as<SmallParams>();
+    ctx->resident_blocks = 0;
     CU(ctx->s_blocks.ensure(payload_bytes + 16));
     CU(ctx->w_index.ensure(index_bytes(R)));
     CU(ctx->s_aout.ensure(S + 16));

@@ -26,7 +26,8 @@ EXPORTS = [
     "idn_host_decoded_quals", "idn_host_decoded_name_off", "idn_host_decoded_names", "idn_host_decoded_free",
     "idn_host_cluster", "idn_host_rank", "idn_host_clustering_new", "idn_host_clustering_free", "idn_host_splitmix64",
     "idn_host_xoshiro256pp", "idn_host_sample_indices", "idn_host_gen_range", "idn_host_compressor_add_text", "idn_host_decompress_text",
-    "idn_host_text_free",
+    "idn_host_text_free", "idn_host_decompress_text_into", "idn_host_compressor_set_output",
+    "idn_host_text_reader_new", "idn_host_text_reader_next", "idn_host_text_reader_free",
 ]
 
 
@@ -74,6 +75,12 @@ def load():
     L.idn_host_compressor_add_batch.argtypes = [vp, u64, vp, vp, vp, vp, vp]
     L.idn_host_compressor_add_text.argtypes = [vp, vp, u64]
     L.idn_host_decompress_text.argtypes = [vp, u32, i32, u32, u32, i32, vp, u64, C.POINTER(vp), C.POINTER(u64)]
+    L.idn_host_decompress_text_into.argtypes = [vp, u32, i32, u32, u32, i32, vp, u64, vp, u64, C.POINTER(u64)]
+    L.idn_host_compressor_set_output.argtypes = [vp, vp, u64]
+    L.idn_host_text_reader_new.argtypes = [vp, u32, C.POINTER(i32), u32, u32, u32, i32, vp, u64, C.POINTER(vp)]
+    L.idn_host_text_reader_next.argtypes = [vp, C.POINTER(vp), C.POINTER(u64)]
+    L.idn_host_text_reader_free.argtypes = [vp]
+    L.idn_host_text_reader_free.restype = None
     L.idn_host_text_free.argtypes = [vp]
     L.idn_host_text_free.restype = None
     L.idn_host_compressor_finish.argtypes = [vp]
@@ -260,6 +267,11 @@ class IdnCompressor:
                                                     q.ctypes.data if q.size else None, None if no is None else no.ctypes.data,
                                                     None if nm is None else nm.ctypes.data))
 
+    def set_output(self, buf: np.ndarray):
+        """write the container into `buf` (a uint8 array, e.g. page-locked) instead of the library's growing buffer"""
+        self._out_keep = buf
+        _check(self.L.idn_host_compressor_set_output(self.h, buf.ctypes.data, buf.size))
+
     def add_fastq_text(self, text):
         """consecutive pieces of FASTQ text, cut anywhere (bytes or a uint8 array; not to be mixed with add_sequence / add_batch)"""
         buf = np.frombuffer(text, dtype=np.uint8) if isinstance(text, (bytes, bytearray, memoryview)) else np.ascontiguousarray(text, dtype=np.uint8)
@@ -344,6 +356,57 @@ def decompress_text(models, idn, *, device=0, n_devices=0, batch_blocks=32, thre
         return C.string_at(ptr, n.value) if n.value else b""
     finally:
         L.idn_host_text_free(ptr)
+
+
+def decompress_text_into(models, idn, out: np.ndarray, *, device=0, n_devices=0, batch_blocks=32, thread_num=0, title_with_separator=False) -> int:
+    """decompress_text into the caller's uint8 array (e.g. page-locked); returns the length of the text"""
+    L = load()
+    buf = np.frombuffer(idn, dtype=np.uint8) if isinstance(idn, (bytes, bytearray, memoryview)) else np.ascontiguousarray(idn, dtype=np.uint8)
+    models = list(models)
+    if n_devices > 1:
+        device = -n_devices
+    n = C.c_uint64(0)
+    _check(L.idn_host_decompress_text_into(_model_array(models), len(models), device, batch_blocks, thread_num, int(title_with_separator),
+                                           buf.ctypes.data if buf.size else None, buf.size, out.ctypes.data, out.size, C.byref(n)))
+    return int(n.value)
+
+
+class FastqTextReader:
+    """streaming text out: iterating yields the FASTQ text of one batch of blocks at a time as a uint8 view of the library's
+    page-locked memory (valid until the next step) -- what a writer would hand to write()"""
+
+    def __init__(self, models, idn, *, devices=(0,), batch_blocks=32, thread_num=0, title_with_separator=False):
+        self.L = load()
+        self._idn = np.frombuffer(idn, dtype=np.uint8) if isinstance(idn, (bytes, bytearray, memoryview)) else np.ascontiguousarray(idn, dtype=np.uint8)
+        models = list(models)
+        self._models = models
+        devs = (C.c_int32 * max(1, len(devices)))(*devices)
+        h = C.c_void_p()
+        _check(self.L.idn_host_text_reader_new(_model_array(models), len(models), devs, len(devices), batch_blocks, thread_num,
+                                               int(title_with_separator), self._idn.ctypes.data if self._idn.size else None, self._idn.size,
+                                               C.byref(h)))
+        self.h = h
+
+    def __iter__(self):
+        return self
+
+    def __next__(self):
+        p, n = C.c_void_p(), C.c_uint64(0)
+        _check(self.L.idn_host_text_reader_next(self.h, C.byref(p), C.byref(n)))
+        if n.value == 0:
+            raise StopIteration
+        return np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_uint8)), shape=(n.value,))
+
+    def close(self):
+        if self.h:
+            self.L.idn_host_text_reader_free(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 class Clustering:

@@ -89,6 +89,11 @@ uint64_t idn_gpu_launch_count(const idn_gpu_ctx *ctx);
 int32_t idn_gpu_kernel_variant(const idn_gpu_ctx *ctx, idn_model_t acid_model, idn_model_t q_model);
 int32_t idn_gpu_kernel_variant_count(void);
 
+/* page-locked host memory for the buffers a caller passes to the host-pointer entry points (a copy from / to pageable
+ * memory is staged by the driver at a fraction of the link's speed); usable from any thread and any device */
+int32_t idn_gpu_host_alloc(uint64_t bytes, void **p);
+void idn_gpu_host_free(void *p);
+
 /* ---- models: replaces RansEncModel/RansDecModel::from_model (sequence_compressor.rs:21-48,175-201) --
  * `cum`: integer cumulative frequencies, row-major [(n_ctx+1)][nsym+1] u16, row 0 = the uniform dummy
  * context (sequence_compressor.rs:26-29), last column = 1<<14; produced on the host by the bit-exact
@@ -168,7 +173,10 @@ uint64_t idn_gpu_compress_bound(uint64_t n_reads, uint64_t n_symbols, uint32_t n
  * both states back at their initial value and every payload byte consumed, fails the call with IDN_E_SERIALIZE in both
  * container modes, with or without a CRC to compare against.
  * Two-step use: idn_gpu_index_blocks returns the read count / symbol count so the caller can size the
- * outputs, then idn_gpu_decompress_blocks fills them. */
+ * outputs, then idn_gpu_decompress_blocks fills them.  The index call leaves the container bytes on the device: a
+ * decode call (idn_gpu_decompress_blocks, idn_gpu_decompress_to_fastq) that follows it on the same context with the
+ * same table may pass blocks == NULL to decode those bytes instead of uploading them a second time (such a call is not
+ * split into pipelined sub-chunks); NULL without a matching index call before it is IDN_E_INVALID_ARG. */
 typedef struct {
     uint64_t n_reads;
     uint64_t n_symbols;

@@ -97,6 +97,22 @@ int32_t idn_host_decompress_text(const idn_host_model *const *models, uint32_t n
                                  uint32_t thread_num, int32_t title_with_separator, const uint8_t *idn, uint64_t idn_len,
                                  uint8_t **text, uint64_t *text_len);
 void idn_host_text_free(uint8_t *text);
+/* the same into the caller's buffer; IDN_E_NOSPACE when it is too small */
+int32_t idn_host_decompress_text_into(const idn_host_model *const *models, uint32_t n_models, int32_t device,
+                                      uint32_t batch_blocks, uint32_t thread_num, int32_t title_with_separator,
+                                      const uint8_t *idn, uint64_t idn_len, uint8_t *text, uint64_t cap, uint64_t *text_len);
+/* streaming form: each call hands out the FASTQ text of the next batch of blocks in the library's page-locked memory, where
+ * the device wrote it (valid until the next call on the reader); *len = 0 at the end.  devices as in the compressor
+ * parameters (an ordinal may repeat: that many contexts on the device, so that one batch's copies overlap another's
+ * kernels) */
+typedef struct idn_host_text_reader idn_host_text_reader;
+int32_t idn_host_text_reader_new(const idn_host_model *const *models, uint32_t n_models, const int32_t *devices,
+                                 uint32_t n_devices, uint32_t batch_blocks, uint32_t thread_num, int32_t title_with_separator,
+                                 const uint8_t *idn, uint64_t idn_len, idn_host_text_reader **out);
+int32_t idn_host_text_reader_next(idn_host_text_reader *r, const uint8_t **text, uint64_t *len);
+void idn_host_text_reader_free(idn_host_text_reader *r);
+/* the compressor writes the container into the caller's buffer instead of the library's growing one (before the first add) */
+int32_t idn_host_compressor_set_output(idn_host_compressor *c, uint8_t *buf, uint64_t cap);
 /* `device` >= 0: that GPU; < 0: the first (-device) GPUs share the file */
 int32_t idn_host_decompress(const idn_host_model *const *models, uint32_t n_models, int32_t device, uint32_t batch_blocks,
                             const uint8_t *idn, uint64_t idn_len, idn_host_decoded **out);

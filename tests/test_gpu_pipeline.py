@@ -50,6 +50,9 @@ def test_sub_chunking_changes_nothing(gctx, O, toy_models, toy_handles, reads_1k
         dlen = (boff[1:] - boff[:-1] - 8).astype(np.uint32)
         ro, a, q = gctx.decompress_blocks(out, doff, crc, toy_handles, block_len=dlen, mode=mode)
         assert np.array_equal(ro, reads_1k.read_off) and np.array_equal(a, reads_1k.acids) and np.array_equal(q, reads_1k.quals)
+        # the bytes an index call left on the device decode to the same reads (blocks == NULL), and only right after it
+        ro2, a2, q2 = gctx.decompress_blocks(out, doff, crc, toy_handles, block_len=dlen, mode=mode, resident=True)
+        assert np.array_equal(ro2, ro) and np.array_equal(a2, a) and np.array_equal(q2, q)
         # errors keep their block numbers across sub-chunks
         from idencomp_b200.capi import IdnGpuError
         bad = crc.copy()

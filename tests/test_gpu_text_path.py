@@ -67,6 +67,23 @@ def test_text_out_is_what_the_reference_writer_prints(O, toy_models, reads_1k, m
     sep = H.decompress_text(hm, idn, batch_blocks=7, title_with_separator=True)
     lines = sep.split(b"\n")
     assert lines[2] == b"+" + lines[0][1:] and len(sep) == len(want) + sum(len(reads_1k.name(r)) for r in range(reads_1k.n_reads))
+    # the streaming reader (pieces in the library's page-locked memory) and the caller-buffer form give the same bytes
+    rd = H.FastqTextReader(hm, idn, devices=[0, 0], batch_blocks=2)
+    pieces = [bytes(p) for p in rd]
+    rd.close()
+    assert len(pieces) > 2 and b"".join(pieces) == want
+    buf = np.zeros(len(want) + 10, dtype=np.uint8)
+    assert H.decompress_text_into(hm, idn, buf, batch_blocks=3) == len(want) and bytes(buf[:len(want)]) == want
+    with pytest.raises(H.HostError, match="too small"):
+        H.decompress_text_into(hm, idn, buf[:len(want) - 1], batch_blocks=3)
+    # the compressor writing into the caller's buffer
+    c = H.IdnCompressor(hm, max_block_total_len=5000, mode=mode, batch_blocks=3)
+    mine = np.zeros(len(idn) + 8, dtype=np.uint8)
+    c.set_output(mine)
+    c.add_fastq_text(text)
+    c.finish()
+    assert bytes(c.output_view()) == idn and bytes(mine[:len(idn)]) == idn
+    c.close()
     # without identifiers the titles are empty
     idn2, _ = _by_text(H, hm, text, [], max_block_total_len=5000, mode=mode, include_identifiers=False)
     back = O.fastq_parse(H.decompress_text(hm, idn2))
