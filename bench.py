@@ -840,7 +840,8 @@ def e2e_file_leg(args, w, env, acids_d, quals_d, read_off_h, n):
     out["contexts_on_the_device"] = len(devs)
     for names in (False, True):
         best = None
-        for it in range(2):  # the second pass is the timed one (device buffers and page-locked pools are sized by the first)
+        for it in range(2):  # the second pass is the timed one: the library keeps device contexts and page-locked buffers
+            # between objects (sized by the first pass), as a process that compresses more than one file would find them
             c = host.IdnCompressor(models, include_identifiers=names, thread_num=cores, devices=devs,
                                    text_chunk_bytes=args.text_chunk_mb << 20, batch_blocks=args.file_batch_blocks)
             c.set_output(idn_h)
@@ -874,6 +875,8 @@ def e2e_file_leg(args, w, env, acids_d, quals_d, read_off_h, n):
         out["with_identifiers" if names else "no_identifiers"] = {
             "compress_GBps": nbytes / tc / 1e9, "decompress_GBps": nbytes / td / 1e9, "value": 2 * nbytes / (tc + td) / 1e9,
             "decompress_into_one_buffer_GBps": nbytes / td2 / 1e9, "container_bytes": n_idn, "verified_round_trip": ok}
+    host.release_cached()  # the contexts and page-locked buffers the host mirror keeps between objects
+    del idn_h, back_h
     # the identifiers codec alone, as the host mirror runs it: raw Deflate level 6 per block on `cores` threads
     per_block = max(1, BLOCK_SYMBOLS // int(read_off_h[1] - read_off_h[0])) if n else 1
     blocks = [b"\n".join(bytes(names_h[r * nlen:(r + 1) * nlen]) for r in range(b0, min(n, b0 + per_block))) for b0 in range(0, min(n, 16 * per_block), per_block)]

@@ -277,6 +277,7 @@ extern "C" int32_t idn_host_decompress_text(const idn_host_model* const* models,
     });
 }
 extern "C" void idn_host_text_free(uint8_t* text) { std::free(text); }
+extern "C" void idn_host_release_cached(void) { release_cached_resources(); }
 
 // the same into the caller's buffer (page-locked and touched, if the caller wants the full rate); IDN_E_NOSPACE with
 // *text_len = bytes written so far when it is too small

@@ -203,40 +203,92 @@ void PinnedBuf::ensure_keep(size_t n, size_t used) {
     cap = want;
 }
 
+PinnedPool::State& PinnedPool::state() {
+    static State* st = new State;  // never destroyed: at process exit the CUDA runtime may be gone before static destructors run
+    return *st;
+}
+
 std::shared_ptr<PinnedBuf> PinnedPool::get(size_t n) {
+    State& st = state();
     std::unique_ptr<PinnedBuf> b;
     {
-        std::lock_guard<std::mutex> lk(st_->mu);
+        std::lock_guard<std::mutex> lk(st.mu);
         // the smallest free buffer that fits, else the largest (it grows)
-        size_t pick = st_->free_.size();
-        for (size_t i = 0; i < st_->free_.size(); i++) {
-            const size_t c = st_->free_[i]->cap;
-            if (pick == st_->free_.size()) pick = i;
+        size_t pick = st.free_.size();
+        for (size_t i = 0; i < st.free_.size(); i++) {
+            const size_t c = st.free_[i]->cap;
+            if (pick == st.free_.size()) pick = i;
             else {
-                const size_t pc = st_->free_[pick]->cap;
+                const size_t pc = st.free_[pick]->cap;
                 if ((c >= n && (pc < n || c < pc)) || (c < n && pc < n && c > pc)) pick = i;
             }
         }
-        if (pick < st_->free_.size()) {
-            b = std::move(st_->free_[pick]);
-            st_->free_.erase(st_->free_.begin() + pick);
+        if (pick < st.free_.size()) {
+            b = std::move(st.free_[pick]);
+            st.free_.erase(st.free_.begin() + pick);
         }
     }
     if (!b) b = std::make_unique<PinnedBuf>();
     b->ensure(n);
-    std::shared_ptr<State> st = st_;
-    return std::shared_ptr<PinnedBuf>(b.release(), [st](PinnedBuf* q) {
-        std::lock_guard<std::mutex> lk(st->mu);
-        st->free_.emplace_back(q);
+    return std::shared_ptr<PinnedBuf>(b.release(), [](PinnedBuf* q) {
+        State& s2 = state();
+        std::lock_guard<std::mutex> lk(s2.mu);
+        s2.free_.emplace_back(q);
     });
+}
+
+void PinnedPool::trim() {
+    State& st = state();
+    std::lock_guard<std::mutex> lk(st.mu);
+    st.free_.clear();
+}
+
+// device contexts between uses: a context's staging and work buffers on the device are sized by the batches it has seen,
+// and allocating them again for every compressor costs more than compressing a few GB
+namespace {
+struct CtxCache {
+    std::mutex mu;
+    std::vector<std::pair<int32_t, idn_gpu_ctx*>> free_;
+    static constexpr size_t kKeepPerDevice = 4;
+};
+CtxCache& ctx_cache() {
+    static CtxCache* c = new CtxCache;
+    return *c;
+}
+}  // namespace
+
+void release_cached_resources() {
+    PinnedPool::trim();
+    CtxCache& c = ctx_cache();
+    std::lock_guard<std::mutex> lk(c.mu);
+    for (auto& e : c.free_) idn_gpu_destroy(e.second);
+    c.free_.clear();
 }
 
 // ---- DeviceModels ---------------------------------------------------------------------------------------------------
 DeviceModels::~DeviceModels() {
-    if (ctx_) idn_gpu_destroy(ctx_);
+    if (!ctx_) return;
+    for (idn_model_t h : handles_) idn_gpu_model_release(ctx_, h);
+    CtxCache& c = ctx_cache();
+    std::lock_guard<std::mutex> lk(c.mu);
+    size_t same = 0;
+    for (auto& e : c.free_) same += e.first == device_;
+    if (same < CtxCache::kKeepPerDevice) c.free_.emplace_back(device_, ctx_);
+    else idn_gpu_destroy(ctx_);
 }
 void DeviceModels::open(int32_t device) {
     if (ctx_) return;
+    device_ = device;
+    {
+        CtxCache& c = ctx_cache();
+        std::lock_guard<std::mutex> lk(c.mu);
+        for (size_t i = 0; i < c.free_.size(); i++)
+            if (c.free_[i].first == device) {
+                ctx_ = c.free_[i].second;
+                c.free_.erase(c.free_.begin() + i);
+                return;
+            }
+    }
     int32_t rc = idn_gpu_create(device, &ctx_);
     if (rc) throw IdnError(rc, "no usable CUDA device (this implementation has no CPU fallback)");
 }
@@ -277,7 +329,6 @@ IdnCompressor::IdnCompressor(Sink sink, IdnCompressorParams params) : sink_(std:
 IdnCompressor::~IdnCompressor() {
     for (auto& f : pending_)  // jobs still running hold references to this object
         if (f.valid()) f.wait();
-    g_trace.print("compressor");
 }
 
 void IdnCompressor::add_sequence(FastqSequence seq) {
@@ -672,16 +723,17 @@ IdnCompressor::Result IdnCompressor::compress_parsed(Worker& w, uint32_t n_block
     std::vector<std::vector<uint8_t>> name_slices(n_blocks);
     std::vector<uint32_t> prefix(n_blocks, 0);
     if (params_.include_identifiers) {
-        std::vector<uint8_t> names(n_name_bytes + 1);
-        std::vector<uint64_t> name_off(n_reads + 1);
+        auto names = pool_.get(n_name_bytes + 1);
+        auto name_off = pool_.get((n_reads + 1) * 8);
+        uint64_t* no = reinterpret_cast<uint64_t*>(name_off->p);
         std::vector<uint32_t> block_first(n_blocks + 1);
         {
             Span sp(T_NFETCH);
-            int32_t rc = idn_gpu_fastq_chunk_fetch(w.dev.ctx(), names.data(), name_off.data(), block_first.data(), nullptr, nullptr, nullptr);
+            int32_t rc = idn_gpu_fastq_chunk_fetch(w.dev.ctx(), names->p, no, block_first.data(), nullptr, nullptr, nullptr);
             if (rc) w.dev.raise(rc);
         }
         Span sp(T_NDEFLATE);
-        identifier_slices(params_.quality, params_.thread_num, n_blocks, block_first.data(), names.data(), name_off.data(), name_slices, prefix);
+        identifier_slices(params_.quality, params_.thread_num, n_blocks, block_first.data(), names->p, no, name_slices, prefix);
     }
     res.prefix_total = std::accumulate(prefix.begin(), prefix.end(), (uint64_t)0);
     const uint64_t bound = idn_gpu_compress_bound(n_reads, n_symbols, n_blocks, res.prefix_total);
@@ -725,6 +777,7 @@ void IdnCompressor::finish() {
     sink_(terminator, 8);
     stats_.out_bytes += 8;
     finished_ = true;
+    g_trace.print("compressor");
 }
 
 // ---- IdnDecompressor -------------------------------------------------------------------------------------------------

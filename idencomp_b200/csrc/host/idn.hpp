@@ -98,16 +98,21 @@ struct PinnedBuf {
     void ensure(size_t n);                 // contents are not kept
     void ensure_keep(size_t n, size_t used);  // the first `used` bytes are
 };
+// One pool per process: page-locking memory costs about as much per byte as the page faults it avoids, so the buffers
+// outlive the compressor / decompressor that asked for them (release_cached_resources() gives them back).
 class PinnedPool {
 public:
     std::shared_ptr<PinnedBuf> get(size_t n);  // a buffer of at least n bytes; goes back to the pool when the last owner lets go
+    static void trim();
 private:
     struct State {
         std::mutex mu;
         std::vector<std::unique_ptr<PinnedBuf>> free_;
     };
-    std::shared_ptr<State> st_ = std::make_shared<State>();
+    static State& state();
 };
+// frees the page-locked buffers and device contexts the library keeps for the next compressor / decompressor
+void release_cached_resources();
 
 // RAII over idn_gpu_ctx + the handles of the uploaded models of one provider
 class DeviceModels {
@@ -116,7 +121,7 @@ public:
     ~DeviceModels();
     DeviceModels(const DeviceModels&) = delete;
     DeviceModels& operator=(const DeviceModels&) = delete;
-    void open(int32_t device);
+    void open(int32_t device);  // a context from the process-wide cache (its device buffers are already sized) or a new one
     void upload(const ModelProvider& provider);  // replaces the current set
     idn_gpu_ctx* ctx() const { return ctx_; }
     const std::vector<idn_model_t>& handles() const { return handles_; }
@@ -124,6 +129,7 @@ public:
 
 private:
     idn_gpu_ctx* ctx_ = nullptr;
+    int32_t device_ = 0;
     std::vector<idn_model_t> handles_;
 };
 

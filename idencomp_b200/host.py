@@ -27,7 +27,7 @@ EXPORTS = [
     "idn_host_cluster", "idn_host_rank", "idn_host_clustering_new", "idn_host_clustering_free", "idn_host_splitmix64",
     "idn_host_xoshiro256pp", "idn_host_sample_indices", "idn_host_gen_range", "idn_host_compressor_add_text", "idn_host_decompress_text",
     "idn_host_text_free", "idn_host_decompress_text_into", "idn_host_compressor_set_output",
-    "idn_host_text_reader_new", "idn_host_text_reader_next", "idn_host_text_reader_free",
+    "idn_host_release_cached", "idn_host_text_reader_new", "idn_host_text_reader_next", "idn_host_text_reader_free",
 ]
 
 
@@ -81,6 +81,8 @@ def load():
     L.idn_host_text_reader_next.argtypes = [vp, C.POINTER(vp), C.POINTER(u64)]
     L.idn_host_text_reader_free.argtypes = [vp]
     L.idn_host_text_reader_free.restype = None
+    L.idn_host_release_cached.argtypes = []
+    L.idn_host_release_cached.restype = None
     L.idn_host_text_free.argtypes = [vp]
     L.idn_host_text_free.restype = None
     L.idn_host_compressor_finish.argtypes = [vp]
@@ -369,6 +371,11 @@ def decompress_text_into(models, idn, out: np.ndarray, *, device=0, n_devices=0,
     _check(L.idn_host_decompress_text_into(_model_array(models), len(models), device, batch_blocks, thread_num, int(title_with_separator),
                                            buf.ctypes.data if buf.size else None, buf.size, out.ctypes.data, out.size, C.byref(n)))
     return int(n.value)
+
+
+def release_cached():
+    """give back the device contexts and page-locked buffers the library keeps between compressors / decompressors"""
+    load().idn_host_release_cached()
 
 
 class FastqTextReader:

@@ -97,6 +97,9 @@ int32_t idn_host_decompress_text(const idn_host_model *const *models, uint32_t n
                                  uint32_t thread_num, int32_t title_with_separator, const uint8_t *idn, uint64_t idn_len,
                                  uint8_t **text, uint64_t *text_len);
 void idn_host_text_free(uint8_t *text);
+/* The library keeps device contexts (with their device buffers) and page-locked host buffers of closed compressors /
+ * decompressors for the next one; this gives them back. */
+void idn_host_release_cached(void);
 /* the same into the caller's buffer; IDN_E_NOSPACE when it is too small */
 int32_t idn_host_decompress_text_into(const idn_host_model *const *models, uint32_t n_models, int32_t device,
                                       uint32_t batch_blocks, uint32_t thread_num, int32_t title_with_separator,
