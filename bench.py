@@ -847,7 +847,7 @@ def e2e_file_leg(args, w, env, acids_d, quals_d, read_off_h, n):
             c.set_output(idn_h)
             t0 = time.perf_counter()
             c.add_fastq_text(text_np)
-            c.finish()
+            c.finish(copy=False)
             t1 = time.perf_counter()
             idn = c.output_view()
             n_idn = int(idn.size)

@@ -220,7 +220,7 @@ extern "C" int32_t idn_host_compressor_add_batch(idn_host_compressor* c, uint64_
 extern "C" int32_t idn_host_compressor_add_text(idn_host_compressor* c, const uint8_t* text, uint64_t n) {
     if (!c || (n && !text)) return set_err(IDN_E_INVALID_ARG, "NULL argument");
     return guarded([&] {
-        if (c->out.capacity() < c->out.size() + n / 3) c->out.reserve(c->out.size() + n / 3 + (1u << 20));  // the in-memory writer
+        if (!c->ext && c->out.capacity() < c->out.size() + n / 3) c->out.reserve(c->out.size() + n / 3 + (1u << 20));  // the in-memory writer
         c->c->add_fastq_text(text, n);
         return (int32_t)IDN_OK;
     });
@@ -297,13 +297,7 @@ extern "C" int32_t idn_host_decompress_text_into(const idn_host_model* const* mo
             for (int32_t d = 0; d < -device; d++) p.devices.push_back(d);
         }
         p.batch_blocks = batch_blocks ? batch_blocks : 32;
-        uint64_t pos = 0;
-        IdnDecompressor d([&](uint8_t* dst, size_t n) {
-            size_t k = (size_t)std::min<uint64_t>(n, idn_len - pos);
-            std::memcpy(dst, idn + pos, k);
-            pos += k;
-            return k;
-        }, std::move(p));
+        IdnDecompressor d(idn, (size_t)idn_len, std::move(p));
         std::shared_ptr<PinnedBuf> piece;
         size_t n = 0;
         uint64_t used = 0;
@@ -344,13 +338,7 @@ extern "C" int32_t idn_host_text_reader_new(const idn_host_model* const* models,
         r->idn = idn;
         r->idn_len = idn_len;
         r->sep = title_with_separator != 0;
-        idn_host_text_reader* raw = r.get();
-        r->d = std::make_unique<IdnDecompressor>([raw](uint8_t* dst, size_t n) {
-            size_t k = (size_t)std::min<uint64_t>(n, raw->idn_len - raw->pos);
-            std::memcpy(dst, raw->idn + raw->pos, k);
-            raw->pos += k;
-            return k;
-        }, std::move(p));
+        r->d = std::make_unique<IdnDecompressor>(idn, (size_t)idn_len, std::move(p));
         *out = r.release();
         return (int32_t)IDN_OK;
     });

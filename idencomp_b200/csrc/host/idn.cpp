@@ -176,6 +176,7 @@ struct Span {
         g_trace.calls[k]++;
     }
 };
+std::atomic<size_t> g_raw_hint{1 << 20};  // bytes of the largest batch of container bytes read so far (sizes the next buffer)
 enum { T_PARSE, T_SELECT, T_NFETCH, T_NDEFLATE, T_CPARSED, T_CBLOCKS, T_SINK, T_READRAW, T_INDEX, T_NINFLATE, T_DECODE, T_WAIT };
 }  // namespace
 
@@ -789,6 +790,17 @@ IdnDecompressor::IdnDecompressor(Source source, IdnDecompressorParams params) : 
         workers_.back()->dev.open(d);
     }
 }
+IdnDecompressor::IdnDecompressor(const uint8_t* data, size_t len, IdnDecompressorParams params)
+    : IdnDecompressor(Source([this](uint8_t* dst, size_t n) {
+                          const size_t k = std::min(n, mem_len_ - mem_pos_);
+                          std::memcpy(dst, mem_ + mem_pos_, k);
+                          mem_pos_ += k;
+                          return k;
+                      }),
+                      std::move(params)) {
+    mem_ = data;
+    mem_len_ = len;
+}
 IdnDecompressor::~IdnDecompressor() {
     for (auto& f : pending_)
         if (f.valid()) f.wait();
@@ -839,8 +851,29 @@ bool IdnDecompressor::read_raw(RawBatch& rb) {
     // block headers + payloads of up to batch_blocks blocks into one buffer (idn/decompressor.rs:387-428)
     Span sp(T_READRAW);
     bool more = true;
-    rb.buf = pool_.get(raw_hint_);
     rb.used = 0;
+    if (mem_) {  // the payloads stay where they are: offsets from the first one, headers in between
+        size_t first = 0;
+        while (rb.off.size() < params_.batch_blocks) {
+            uint8_t h[8];
+            read_exact(h, 8, "a block header");
+            uint32_t n = get_u32be(h), c = get_u32be(h + 4);
+            if (n == 0) {
+                more = false;
+                break;
+            }
+            if (n > mem_len_ - mem_pos_) throw IdnError(IDN_E_IO, "unexpected end of input while reading a block");
+            if (rb.off.empty()) first = mem_pos_;
+            rb.off.push_back(mem_pos_ - first);
+            rb.len.push_back(n);
+            rb.crc.push_back(c);
+            mem_pos_ += n;
+            rb.used = mem_pos_ - first;
+        }
+        rb.base = mem_ + first;
+        return more;
+    }
+    rb.buf = pool_.get(g_raw_hint.load());
     while (rb.off.size() < params_.batch_blocks) {
         uint8_t h[8];
         read_exact(h, 8, "a block header");
@@ -856,7 +889,8 @@ bool IdnDecompressor::read_raw(RawBatch& rb) {
         read_exact(rb.buf->p + rb.used, n, "a block");
         rb.used += n;
     }
-    raw_hint_ = std::max(raw_hint_, rb.used);
+    for (size_t h = g_raw_hint.load(); h < rb.used && !g_raw_hint.compare_exchange_weak(h, rb.used);) {}
+    rb.base = rb.buf->p;
     return more;
 }
 
@@ -869,7 +903,7 @@ void IdnDecompressor::inflate_names(const RawBatch& rb, const std::vector<uint64
     std::vector<std::vector<uint8_t>> text(n_blocks);
     std::vector<uint8_t> has(n_blocks, 0);
     auto one = [&](uint32_t b) {
-        const uint8_t* p = rb.buf->p + off[b];
+        const uint8_t* p = rb.base + off[b];
         size_t pos = 0;
         while (pos < rb.len[b] && p[pos] == 0x00) {
             if (pos + 6 > rb.len[b]) throw IdnError(IDN_E_SERIALIZE, "truncated identifiers slice");
@@ -884,36 +918,61 @@ void IdnDecompressor::inflate_names(const RawBatch& rb, const std::vector<uint64
             pos += 6 + (size_t)n;
         }
     };
-    if (params_.thread_num > 1 && n_blocks > 1) {
-        std::vector<std::future<void>> jobs;
-        std::atomic<uint32_t> next{0};
-        for (uint32_t t = 0; t < std::min<uint32_t>(params_.thread_num, n_blocks); t++)
-            jobs.push_back(std::async(std::launch::async, [&] {
-                for (uint32_t b = next++; b < n_blocks; b = next++) one(b);
-            }));
-        for (auto& j : jobs) j.get();
-    } else {
-        for (uint32_t b = 0; b < n_blocks; b++) one(b);
-    }
-    for (uint32_t b = 0; b < n_blocks; b++) {
-        uint64_t r = block_first[b];
-        const uint64_t r_end = block_first[b + 1];
-        if (has[b]) {
-            out.any_names = true;
-            // split at '\n': one identifier per sequence, in order (identifiers_as_lines)
-            const std::vector<uint8_t>& t = text[b];
-            size_t s0 = 0;
-            while (r < r_end) {
-                size_t e = s0;
-                while (e < t.size() && t[e] != '\n') e++;
-                out.names.insert(out.names.end(), t.begin() + s0, t.begin() + e);
-                out.name_off[++r] = out.names.size();
-                if (e >= t.size()) break;
-                s0 = e + 1;
-            }
+    // one identifier per sequence, in order (identifiers_as_lines): split at '\n' inside the block's job -- the line lengths
+    // of the block's reads and the text without its separators -- so that only a prefix sum over blocks stays serial
+    std::vector<std::vector<uint32_t>> lens(n_blocks);
+    auto split = [&](uint32_t b) {
+        one(b);
+        if (!has[b]) return;
+        std::vector<uint8_t>& t = text[b];
+        const uint64_t want = block_first[b + 1] - block_first[b];
+        lens[b].reserve(want);
+        size_t s0 = 0, w = 0;
+        while (lens[b].size() < want) {
+            const uint8_t* nl = static_cast<const uint8_t*>(std::memchr(t.data() + s0, '\n', t.size() - s0));
+            const size_t e = nl ? (size_t)(nl - t.data()) : t.size();
+            if (w != s0) std::memmove(t.data() + w, t.data() + s0, e - s0);
+            w += e - s0;
+            lens[b].push_back((uint32_t)(e - s0));
+            if (!nl) break;
+            s0 = e + 1;
         }
-        for (; r < r_end; r++) out.name_off[r + 1] = out.names.size();  // sequences without an identifier
+        t.resize(w);
+    };
+    auto for_blocks = [&](auto&& fn) {
+        if (params_.thread_num > 1 && n_blocks > 1) {
+            std::vector<std::future<void>> jobs;
+            std::atomic<uint32_t> next{0};
+            for (uint32_t t = 0; t < std::min<uint32_t>(params_.thread_num, n_blocks); t++)
+                jobs.push_back(std::async(std::launch::async, [&] {
+                    for (uint32_t b = next++; b < n_blocks; b = next++) fn(b);
+                }));
+            std::exception_ptr err;
+            for (auto& j : jobs) {
+                try {
+                    j.get();
+                } catch (...) {
+                    if (!err) err = std::current_exception();
+                }
+            }
+            if (err) std::rethrow_exception(err);
+        } else {
+            for (uint32_t b = 0; b < n_blocks; b++) fn(b);
+        }
+    };
+    for_blocks(split);
+    std::vector<uint64_t> base(n_blocks + 1, 0);
+    for (uint32_t b = 0; b < n_blocks; b++) {
+        base[b + 1] = base[b] + text[b].size();
+        out.any_names = out.any_names || has[b];
     }
+    out.names.resize(base[n_blocks]);
+    for_blocks([&](uint32_t b) {
+        if (!text[b].empty()) std::memcpy(out.names.data() + base[b], text[b].data(), text[b].size());
+        uint64_t at = base[b], r = block_first[b];
+        for (uint32_t n : lens[b]) out.name_off[++r] = (at += n);
+        for (; r < block_first[b + 1]; r++) out.name_off[r + 1] = at;  // sequences without an identifier
+    });
 }
 
 IdnDecompressor::DecodedBatch IdnDecompressor::decode_batch(Worker& w, const RawBatch& rb) const {
@@ -930,7 +989,7 @@ IdnDecompressor::DecodedBatch IdnDecompressor::decode_batch(Worker& w, const Raw
     int32_t rc;
     {
         Span sp(T_INDEX);
-        rc = idn_gpu_index_blocks(w.dev.ctx(), rb.buf->p, off.data(), rb.len.data(), n_blocks, mode, handles.data(), (uint32_t)handles.size(), &tot,
+        rc = idn_gpu_index_blocks(w.dev.ctx(), rb.base, off.data(), rb.len.data(), n_blocks, mode, handles.data(), (uint32_t)handles.size(), &tot,
                                   block_first.data());
     }
     if (rc) w.dev.raise(rc);
@@ -945,7 +1004,7 @@ IdnDecompressor::DecodedBatch IdnDecompressor::decode_batch(Worker& w, const Raw
     int32_t bad = -1;
     if (out.names.empty()) out.names.push_back(0);
     // with identifiers the call is not pipelined and can use the bytes idn_gpu_index_blocks left on the device (blocks == NULL)
-    rc = idn_gpu_decompress_blocks(w.dev.ctx(), out.any_names ? nullptr : rb.buf->p, off.data(), rb.len.data(), rb.crc.data(), n_blocks, mode, handles.data(),
+    rc = idn_gpu_decompress_blocks(w.dev.ctx(), out.any_names ? nullptr : rb.base, off.data(), rb.len.data(), rb.crc.data(), n_blocks, mode, handles.data(),
                                    (uint32_t)handles.size(), out.any_names ? out.names.data() : nullptr,
                                    out.any_names ? out.name_off.data() : nullptr, out.acids.data(), out.quals.data(), out.read_off.data(),
                                    tot.n_reads, tot.n_symbols, &bad);
@@ -971,7 +1030,7 @@ IdnDecompressor::DecodedBatch IdnDecompressor::decode_text(Worker& w, const RawB
     int32_t rc;
     {
         Span sp(T_INDEX);
-        rc = idn_gpu_index_blocks(w.dev.ctx(), rb.buf->p, off.data(), rb.len.data(), n_blocks, mode, handles.data(), (uint32_t)handles.size(), &tot,
+        rc = idn_gpu_index_blocks(w.dev.ctx(), rb.base, off.data(), rb.len.data(), n_blocks, mode, handles.data(), (uint32_t)handles.size(), &tot,
                                   block_first.data());
     }
     if (rc) w.dev.raise(rc);

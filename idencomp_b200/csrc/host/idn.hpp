@@ -225,6 +225,9 @@ class IdnDecompressor {
 public:
     using Source = std::function<size_t(uint8_t*, size_t)>;  // reads up to n bytes, returns the count (0 = end of input)
     IdnDecompressor(Source source, IdnDecompressorParams params);  // IdnDecompressor::with_params
+    // the container in memory: the blocks are uploaded from where they lie (no copy into the library's buffers; full link
+    // rate when the memory is page-locked).  [data, data + len) must stay valid while the object lives.
+    IdnDecompressor(const uint8_t* data, size_t len, IdnDecompressorParams params);
     ~IdnDecompressor();
     std::optional<FastqSequence> next_sequence();  // None at the end of the file
     uint8_t version() const { return version_; }
@@ -246,7 +249,8 @@ public:
 private:
     struct RawBatch {  // container bytes of some blocks, as read from the source
         std::shared_ptr<PinnedBuf> buf;  // page-locked, pooled: the device reads it at the link's rate
-        size_t used = 0;
+        const uint8_t* base = nullptr;   // buf->p, or the position of the first payload in the caller's memory
+        size_t used = 0;                 // bytes from base to the end of the last payload
         std::vector<uint64_t> off;
         std::vector<uint32_t> len, crc;
     };
@@ -264,11 +268,12 @@ private:
     void read_exact(uint8_t* dst, size_t n, const char* what);
 
     Source source_;
+    const uint8_t* mem_ = nullptr;  // the in-memory form
+    size_t mem_len_ = 0, mem_pos_ = 0;
     IdnDecompressorParams params_;
     std::vector<std::unique_ptr<Worker>> workers_;
     size_t next_worker_ = 0;
     mutable PinnedPool pool_;
-    size_t raw_hint_ = 1 << 20;  // bytes of the largest batch read so far
     std::deque<std::future<DecodedBatch>> pending_;
     int text_mode_ = 0;  // 0 sequences / batches, 1 text, 2 text with the title repeated on the separator line
     bool initialized_ = false, eof_ = false;

@@ -279,9 +279,10 @@ class IdnCompressor:
         buf = np.frombuffer(text, dtype=np.uint8) if isinstance(text, (bytes, bytearray, memoryview)) else np.ascontiguousarray(text, dtype=np.uint8)
         _check(self.L.idn_host_compressor_add_text(self.h, buf.ctypes.data if buf.size else None, buf.size))
 
-    def finish(self) -> bytes:
+    def finish(self, copy: bool = True):
+        """copy=False: no bytes object of the container is made (read it with output_view() or from the set_output buffer)"""
         _check(self.L.idn_host_compressor_finish(self.h))
-        return self.output()
+        return self.output() if copy else None
 
     def output_view(self) -> np.ndarray:
         """the container written so far as a uint8 view of the library's buffer (valid until the next call on this object)"""
