@@ -840,8 +840,8 @@ def e2e_file_leg(args, w, env, acids_d, quals_d, read_off_h, n):
     out["contexts_on_the_device"] = len(devs)
     for names in (False, True):
         best = None
-        for it in range(2):  # the second pass is the timed one: the library keeps device contexts and page-locked buffers
-            # between objects (sized by the first pass), as a process that compresses more than one file would find them
+        for it in range(3):  # the last pass is the timed one: the library keeps device contexts and page-locked buffers
+            # between objects (sized by the passes before), as a process that compresses more than one file would find them
             c = host.IdnCompressor(models, include_identifiers=names, thread_num=cores, devices=devs,
                                    text_chunk_bytes=args.text_chunk_mb << 20, batch_blocks=args.file_batch_blocks)
             c.set_output(idn_h)
@@ -1104,7 +1104,7 @@ def main():
     ap.add_argument("--e2e-chunk-blocks", type=int, default=0, help="blocks per host-pointer call in the e2e leg (default: all of a thread's blocks in one call)")
     ap.add_argument("--e2e-pipe-blocks", type=int, default=0, help="blocks per sub-chunk of the pipeline inside a call (default: 32, more for long reads)")
     ap.add_argument("--e2e-steps", type=int, default=3)
-    ap.add_argument("--e2e-file-reads", type=int, default=8_000_000, help="reads of the FASTQ-text-in / text-out leg through the host mirror")
+    ap.add_argument("--e2e-file-reads", type=int, default=24_000_000, help="reads of the FASTQ-text-in / text-out leg through the host mirror")
     ap.add_argument("--text-chunk-mb", type=int, default=256, help="FASTQ text per device call of that leg")
     ap.add_argument("--file-batch-blocks", type=int, default=32, help="blocks per batch in the e2e_file decode (and in add_batch)")
     ap.add_argument("--e2e-profile", action="store_true", help="print the host-side phase times of the e2e leg to stderr")
