@@ -210,27 +210,30 @@ PinnedPool::State& PinnedPool::state() {
 }
 
 std::shared_ptr<PinnedBuf> PinnedPool::get(size_t n) {
+    // Sizes are rounded up to a power of two (1 MB at least) and a buffer is never regrown for a larger request: requests of
+    // about the same size then find each other's buffers whatever order the worker threads ask in, and the pool stops
+    // allocating once it has seen the peak number of buffers in flight per size class (at most 2 x the memory).
+    size_t cls = 1 << 20;
+    while (cls < n) cls <<= 1;
     State& st = state();
     std::unique_ptr<PinnedBuf> b;
     {
         std::lock_guard<std::mutex> lk(st.mu);
-        // the smallest free buffer that fits, else the largest (it grows)
         size_t pick = st.free_.size();
-        for (size_t i = 0; i < st.free_.size(); i++) {
-            const size_t c = st.free_[i]->cap;
-            if (pick == st.free_.size()) pick = i;
-            else {
-                const size_t pc = st.free_[pick]->cap;
-                if ((c >= n && (pc < n || c < pc)) || (c < n && pc < n && c > pc)) pick = i;
-            }
-        }
+        for (size_t i = 0; i < st.free_.size(); i++)
+            if (st.free_[i]->cap >= n && (pick == st.free_.size() || st.free_[i]->cap < st.free_[pick]->cap)) pick = i;
         if (pick < st.free_.size()) {
             b = std::move(st.free_[pick]);
             st.free_.erase(st.free_.begin() + pick);
         }
     }
-    if (!b) b = std::make_unique<PinnedBuf>();
-    b->ensure(n);
+    if (!b) {
+        b = std::make_unique<PinnedBuf>();
+        void* q = nullptr;
+        if (idn_gpu_host_alloc(cls, &q) != IDN_OK) throw IdnError(IDN_E_IO, "cannot allocate " + std::to_string(cls) + " bytes of page-locked host memory");
+        b->p = static_cast<uint8_t*>(q);
+        b->cap = cls;
+    }
     return std::shared_ptr<PinnedBuf>(b.release(), [](PinnedBuf* q) {
         State& s2 = state();
         std::lock_guard<std::mutex> lk(s2.mu);

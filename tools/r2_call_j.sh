@@ -1,0 +1,18 @@
+#!/bin/bash
+# round 2, GPU call J: the whole GPU suite, the default bench line, the reference arm, the launch list of the default command and
+# ncu --set full captures of the codec kernels (each after its command ran clean without ncu)
+mkdir -p gpurun_out
+( time python -m pytest tests -q -m gpu -p no:cacheprovider 2>&1 | tail -8 ) > gpurun_out/j_pytest.log 2>&1
+( time python bench.py > gpurun_out/j_bench.json 2> gpurun_out/j_bench.err ) > gpurun_out/j_bench.time 2>&1
+( time python bench.py --impl reference > gpurun_out/j_bench_ref.json 2> gpurun_out/j_bench_ref.err ) > gpurun_out/j_bench_ref.time 2>&1
+python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" > gpurun_out/j_smoke.log 2>&1
+Q="--steps 1 --warmup 3 --no-e2e --no-cpu-baseline --no-other-mode --no-fastq --no-extra-workloads"
+python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-extra-workloads > gpurun_out/j_plain.log 2>&1 && \
+ncu --metrics gpu__time_duration.sum --clock-control none -c 1200 --csv --log-file gpurun_out/r2_launches.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-extra-workloads > gpurun_out/j_ncu_list.log 2>&1
+python bench.py --reads 4000000 $Q > /dev/null 2>&1 && \
+ncu --set full --clock-control none --import-source on -k regex:'^(decode|encode)_kernel' -s 6 -c 2 -o gpurun_out/prof_r2_codec python bench.py --reads 4000000 $Q > gpurun_out/j_ncu_codec.log 2>&1
+python bench.py --workload novaseq150_native --reads 4000000 $Q > /dev/null 2>&1 && \
+ncu --set full --clock-control none --import-source on -k regex:'^(decode|encode)_lane_kernel' -s 6 -c 2 -o gpurun_out/prof_r2_lane python bench.py --workload novaseq150_native --reads 4000000 $Q > gpurun_out/j_ncu_lane.log 2>&1
+python bench.py --workload hiseq100_select4 --reads 4000000 $Q > /dev/null 2>&1 && \
+ncu --set full --clock-control none --import-source on -k regex:'^score_multi_kernel' -s 2 -c 1 -o gpurun_out/prof_r2_score python bench.py --workload hiseq100_select4 --reads 4000000 $Q > gpurun_out/j_ncu_score.log 2>&1
+echo done
