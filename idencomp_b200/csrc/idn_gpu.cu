@@ -134,6 +134,8 @@ struct idn_gpu_ctx {
     // staging of the host-pointer paths
     DevBuf s_acids, s_quals, s_readoff, s_blockfirst, s_prefix, s_names, s_nameoff, s_out, s_blockoff, s_crc, s_stats,
         s_sizes, s_blocks, s_blocklen, s_aout, s_qout, s_offout, s_status, s_idx;
+    DevBuf w_bucket, w_list;       // per-read selection: reads bucketed by model pair (cnt | base | cursor, read list)
+    bool bucket_pairs = true;      // IDN_NO_BUCKETS=1: the run-time generic kernels over all reads instead (for comparison)
     uint64_t resident_bytes = 0;   // container bytes idn_gpu_index_blocks / the decoder left in s_blocks ...
     uint32_t resident_blocks = 0;  // ... and how many blocks they are (0: nothing a decode call may reuse)
 };
@@ -323,6 +325,20 @@ static unsigned debug_smem() {
         default: KERNEL<true, DynSpecs><<<grid, 128, debug_smem(), st>>>(__VA_ARGS__); break;             \
     }
 
+// the list kernels over one bucket of reads (per-read model selection, see bucket_scatter_kernel)
+#define IDN_LAUNCH_LIST(idx, KERNEL, grid, st, ...)                                            \
+    switch (idx) {                                                                             \
+        case 0: KERNEL<SP0><<<grid, 128, debug_smem(), st>>>(__VA_ARGS__); break;                         \
+        case 1: KERNEL<SP1><<<grid, 128, debug_smem(), st>>>(__VA_ARGS__); break;                         \
+        case 2: KERNEL<SP2><<<grid, 128, debug_smem(), st>>>(__VA_ARGS__); break;                         \
+        case 3: KERNEL<SP3><<<grid, 128, debug_smem(), st>>>(__VA_ARGS__); break;                         \
+        case 4: KERNEL<SP4><<<grid, 128, debug_smem(), st>>>(__VA_ARGS__); break;                         \
+        case 5: KERNEL<SP5><<<grid, 128, debug_smem(), st>>>(__VA_ARGS__); break;                         \
+        case 6: KERNEL<SP6><<<grid, 128, debug_smem(), st>>>(__VA_ARGS__); break;                         \
+        case 7: KERNEL<SP7><<<grid, 128, debug_smem(), st>>>(__VA_ARGS__); break;                         \
+        default: KERNEL<DynSpecs><<<grid, 128, debug_smem(), st>>>(__VA_ARGS__); break;                   \
+    }
+
 // ======================================================================================================
 // lifecycle
 // ======================================================================================================
@@ -365,6 +381,7 @@ extern "C" int32_t idn_gpu_create(int32_t device, idn_gpu_ctx** out) {
     idn_gpu_ctx* ctx = new idn_gpu_ctx();
     ctx->device = device;
     if (const char* pb = getenv("IDN_PIPE_BLOCKS")) ctx->pipe_blocks = std::max(1, atoi(pb));
+    if (getenv("IDN_NO_BUCKETS")) ctx->bucket_pairs = false;
     if (const char* w = getenv("IDN_WALK")) ctx->walk_mode = strcmp(w, "serial") == 0 ? 1 : (strcmp(w, "fast") == 0 ? 2 : 0);
     auto bail = [&](const char* what) {
         fprintf(stderr, "idn_gpu_create: %s failed: %s\n", what, cudaGetErrorString(cudaGetLastError()));
@@ -401,7 +418,7 @@ extern "C" void idn_gpu_destroy(idn_gpu_ctx* ctx) {
                       &ctx->f_text, &ctx->f_tilecnt, &ctx->f_tilebase, &ctx->f_linestart, &ctx->f_linefn, &ctx->f_linestate, &ctx->f_tilefn,
                       &ctx->f_tilestate, &ctx->f_recscan, &ctx->f_title, &ctx->f_namelo, &ctx->f_namelen, &ctx->f_readlen, &ctx->f_readoff,
                       &ctx->f_nameoff, &ctx->f_names, &ctx->f_acids, &ctx->f_quals, &ctx->f_err, &ctx->f_fmtoff, &ctx->f_fmttext,
-                      &ctx->f_blockfirst, &ctx->f_nxt,
+                      &ctx->f_blockfirst, &ctx->f_nxt, &ctx->w_bucket, &ctx->w_list,
                       &ctx->s_acids,   &ctx->s_quals,   &ctx->s_readoff, &ctx->s_blockfirst, &ctx->s_prefix, &ctx->s_names,
                       &ctx->s_nameoff, &ctx->s_out,     &ctx->s_blockoff, &ctx->s_crc,       &ctx->s_stats,  &ctx->s_sizes,
                       &ctx->s_blocks,  &ctx->s_blocklen, &ctx->s_aout,    &ctx->s_qout,    &ctx->s_offout,     &ctx->s_status, &ctx->s_idx};
@@ -890,12 +907,39 @@ extern "C" int32_t idn_gpu_compress_blocks_dev(idn_gpu_ctx* ctx, const idn_batch
         const ModelDev& hma = ctx->slots[sp.cand_model[0]].dev;
         const ModelDev& hmq = ctx->slots[sp.cand_model[kMaxCand]].dev;
         const unsigned egrid = (unsigned)((R + 127) / 128);
+        const uint32_t n_pairs = sp.n_cand[0] * sp.n_cand[1];
         if (uniform) {
             IDN_LAUNCH_UNIFORM(static_pair_index(ctx, sp.cand_model[0], sp.cand_model[kMaxCand]), encode_kernel, egrid, st, ea, hma, hmq)
+            LAUNCHED("encode");
+        } else if (ctx->bucket_pairs && n_pairs <= kMaxPairs && R < 0xffffffffull) {
+            // reads bucketed by the pair they chose; one launch of the uniform (specialised where bundled) kernel per pair
+            CU(ctx->w_bucket.ensure(3 * kMaxPairs * 4));
+            CU(ctx->w_list.ensure(R * 4 + 16));
+            uint32_t* cnt = ctx->w_bucket.as<uint32_t>();
+            uint32_t *base = cnt + kMaxPairs, *cursor = cnt + 2 * kMaxPairs;
+            CU(cudaMemsetAsync(cnt, 0, kMaxPairs * 4, st));
+            const EncodePairKey key{chosen, R, sp.n_cand[1]};
+            const unsigned bgrid = (unsigned)((R + 255) / 256);
+            bucket_count_kernel<<<bgrid, 256, 0, st>>>(key, R, n_pairs, cnt);
+            LAUNCHED("bucket_count");
+            bucket_base_kernel<<<1, 32, 0, st>>>(cnt, n_pairs, base, cursor);
+            LAUNCHED("bucket_base");
+            bucket_scatter_kernel<<<bgrid, 256, 0, st>>>(key, R, n_pairs, cursor, ctx->w_list.as<uint32_t>());
+            LAUNCHED("bucket_scatter");
+            ReadList rl{ctx->w_list.as<uint32_t>(), nullptr, nullptr};
+            const unsigned lgrid = (unsigned)std::min<uint64_t>(egrid, (uint64_t)ctx->sm_count * IDN_ENC_MINB);
+            for (uint32_t a = 0; a < sp.n_cand[0]; a++)
+                for (uint32_t q = 0; q < sp.n_cand[1]; q++) {
+                    const int32_t ia = sp.cand_model[a], iq = sp.cand_model[kMaxCand + q];
+                    rl.base = base + a * sp.n_cand[1] + q;
+                    rl.count = cnt + a * sp.n_cand[1] + q;
+                    IDN_LAUNCH_LIST(static_pair_index(ctx, ia, iq), encode_list_kernel, lgrid, st, ea, ctx->slots[ia].dev, ctx->slots[iq].dev, rl)
+                    LAUNCHED("encode");
+                }
         } else {
             encode_kernel<false, DynSpecs><<<egrid, 128, 0, st>>>(ea, hma, hmq);
+            LAUNCHED("encode");
         }
-        LAUNCHED("encode");
     }
 
     // slice offsets: exclusive scan of per-read slice sizes
@@ -1502,10 +1546,40 @@ extern "C" int32_t idn_gpu_decompress_blocks_dev(idn_gpu_ctx* ctx, const uint8_t
         const unsigned grid = (unsigned)((out_reads_cap + 127) / 128);
         if (na == 1 && nq == 1) {
             IDN_LAUNCH_UNIFORM(static_pair_index(ctx, ua, uq), decode_kernel, grid, st, da, ctx->slots[ua].dev, ctx->slots[uq].dev)
+            LAUNCHED("decode");
+        } else if (ctx->bucket_pairs && n_models * n_models <= kMaxPairs && out_reads_cap < 0xffffffffull) {
+            // reads bucketed by the model pair the walk recorded; one launch of the uniform kernel per (acid, q-score) pair
+            const uint32_t n_pairs = n_models * n_models;
+            CU(ctx->w_bucket.ensure(3 * kMaxPairs * 4));
+            CU(ctx->w_list.ensure(out_reads_cap * 4 + 16));
+            uint32_t* cnt = ctx->w_bucket.as<uint32_t>();
+            uint32_t *base = cnt + kMaxPairs, *cursor = cnt + 2 * kMaxPairs;
+            CU(cudaMemsetAsync(cnt, 0, kMaxPairs * 4, st));
+            const DecodePairKey key{da, n_models};
+            const unsigned bgrid = (unsigned)((out_reads_cap + 255) / 256);
+            bucket_count_kernel<<<bgrid, 256, 0, st>>>(key, out_reads_cap, n_pairs, cnt);
+            LAUNCHED("bucket_count");
+            bucket_base_kernel<<<1, 32, 0, st>>>(cnt, n_pairs, base, cursor);
+            LAUNCHED("bucket_base");
+            bucket_scatter_kernel<<<bgrid, 256, 0, st>>>(key, out_reads_cap, n_pairs, cursor, ctx->w_list.as<uint32_t>());
+            LAUNCHED("bucket_scatter");
+            ReadList rl{ctx->w_list.as<uint32_t>(), nullptr, nullptr};
+            const unsigned lgrid = (unsigned)std::min<uint64_t>(grid, (uint64_t)ctx->sm_count * IDN_DEC_MINB);
+            for (uint32_t a = 0; a < n_models; a++) {
+                if (ctx->slots[models[a]].dev.type != IDN_MODEL_ACID) continue;
+                for (uint32_t q = 0; q < n_models; q++) {
+                    if (ctx->slots[models[q]].dev.type == IDN_MODEL_ACID) continue;
+                    rl.base = base + a * n_models + q;
+                    rl.count = cnt + a * n_models + q;
+                    IDN_LAUNCH_LIST(static_pair_index(ctx, models[a], models[q]), decode_list_kernel, lgrid, st, da, ctx->slots[models[a]].dev,
+                                    ctx->slots[models[q]].dev, rl)
+                    LAUNCHED("decode");
+                }
+            }
         } else {
             decode_kernel<false, DynSpecs><<<grid, 128, 0, st>>>(da, ctx->d_models_host0, ctx->d_models_host0);
+            LAUNCHED("decode");
         }
-        LAUNCHED("decode");
     }
     // CRC of the decoded symbols per block, compared with the header value (decompressor_block.rs:131-144)
     if (want_crc) {

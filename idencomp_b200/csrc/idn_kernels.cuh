@@ -391,6 +391,13 @@ struct EncodeArgs {
     const uint8_t* switched;            // [2][n_reads]: a SwitchModel slice precedes the read's Sequence slice, or nullptr
     const uint8_t* cand_index;          // [2][kMaxCand] candidate -> SwitchModel index
 };
+// the reads of one launch of a *_list_kernel: list[*base .. *base + *count), one bucket of bucket_scatter_kernel (the reads
+// that chose this launch's model pair)
+struct ReadList {
+    const uint32_t* list;
+    const uint32_t* base;
+    const uint32_t* count;
+};
 // scratch bytes per read besides 4 per symbol: two flushed states (8) + Sequence slice header (9) + two SwitchModel
 // slices (4), rounded up to keep the slot ends word-aligned
 constexpr unsigned long long kSlotExtra = 24;
@@ -536,10 +543,7 @@ __device__ __forceinline__ void encode_read_body(const ModelDev& ma, const Model
 #define IDN_DEC_MINB 8
 #endif
 template <bool kUniform, class P>
-__global__ void __launch_bounds__(128, kUniform ? IDN_ENC_MINB : 1)
-encode_kernel(EncodeArgs A, const ModelDev MA, const ModelDev MQ) {
-    uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (r >= A.n_reads) return;
+__device__ __forceinline__ void encode_one(const EncodeArgs& A, const ModelDev& MA, const ModelDev& MQ, uint64_t r) {
     int32_t ia = A.fixed_acid, iq = A.fixed_q;
     if (!kUniform && A.chosen) {
         ia = A.cand_model[A.chosen[r]];
@@ -573,6 +577,83 @@ encode_kernel(EncodeArgs A, const ModelDev MA, const ModelDev MQ) {
     }
     S.out.finish();
     if (S.bad) atomicOr(A.err, 1u);
+}
+
+template <bool kUniform, class P>
+__global__ void __launch_bounds__(128, kUniform ? IDN_ENC_MINB : 1)
+encode_kernel(EncodeArgs A, const ModelDev MA, const ModelDev MQ) {
+    uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= A.n_reads) return;
+    encode_one<kUniform, P>(A, MA, MQ, r);
+}
+
+// Per-read model selection: one launch per model pair over the reads that chose it (a fixed grid strides over the bucket,
+// whose size only the device knows), so that those reads run the uniform -- and, for the bundled pairs, the compile-time
+// specialised -- arithmetic instead of the run-time generic one.
+template <class P>
+__global__ void __launch_bounds__(128, IDN_ENC_MINB)
+encode_list_kernel(EncodeArgs A, const ModelDev MA, const ModelDev MQ, ReadList L) {
+    const uint32_t n = *L.count;
+    const uint32_t* __restrict__ list = L.list + *L.base;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x)
+        encode_one<true, P>(A, MA, MQ, list[i]);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Buckets of reads by model pair (per-read selection): count, exclusive scan, scatter.  KeyFn(r) = pair number of read r
+// or 0xffffffff (no such read).  The order inside a bucket depends on the order the CTAs arrive in; the output does not
+// (every read writes its own slot).
+// ---------------------------------------------------------------------------------------------------
+constexpr uint32_t kMaxPairs = 1024;
+
+struct EncodePairKey {  // compress side: the candidates the greedy switcher chose
+    const uint8_t* chosen;  // [2][n_reads]
+    uint64_t n_reads;
+    uint32_t n_q;
+    __device__ __forceinline__ uint32_t operator()(uint64_t r) const {
+        return r < n_reads ? (uint32_t)chosen[r] * n_q + chosen[n_reads + r] : 0xffffffffu;
+    }
+};
+
+template <class KeyFn>
+__global__ void __launch_bounds__(256)
+bucket_count_kernel(KeyFn key, uint64_t n, uint32_t n_pairs, uint32_t* __restrict__ cnt) {
+    __shared__ uint32_t hist[kMaxPairs];
+    for (uint32_t k = threadIdx.x; k < n_pairs; k += blockDim.x) hist[k] = 0;
+    __syncthreads();
+    const uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t k = r < n ? key(r) : 0xffffffffu;
+    if (k < n_pairs) atomicAdd(&hist[k], 1u);
+    __syncthreads();
+    for (uint32_t j = threadIdx.x; j < n_pairs; j += blockDim.x)
+        if (hist[j]) atomicAdd(&cnt[j], hist[j]);
+}
+
+// cnt[n_pairs] -> base[n_pairs] (exclusive scan), cursor = base
+__global__ void bucket_base_kernel(const uint32_t* __restrict__ cnt, uint32_t n_pairs, uint32_t* __restrict__ base, uint32_t* __restrict__ cursor) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    uint32_t acc = 0;
+    for (uint32_t k = 0; k < n_pairs; k++) {
+        base[k] = cursor[k] = acc;
+        acc += cnt[k];
+    }
+}
+
+template <class KeyFn>
+__global__ void __launch_bounds__(256)
+bucket_scatter_kernel(KeyFn key, uint64_t n, uint32_t n_pairs, uint32_t* __restrict__ cursor, uint32_t* __restrict__ list) {
+    __shared__ uint32_t hist[kMaxPairs];
+    for (uint32_t k = threadIdx.x; k < n_pairs; k += blockDim.x) hist[k] = 0;
+    __syncthreads();
+    const uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t k = r < n ? key(r) : 0xffffffffu;
+    uint32_t rank = 0;
+    if (k < n_pairs) rank = atomicAdd(&hist[k], 1u);
+    __syncthreads();
+    for (uint32_t j = threadIdx.x; j < n_pairs; j += blockDim.x)
+        if (hist[j]) hist[j] = atomicAdd(&cursor[j], hist[j]);  // the CTA's range in bucket j
+    __syncthreads();
+    if (k < n_pairs) list[hist[k] + rank] = (uint32_t)r;
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -1913,31 +1994,28 @@ __device__ __forceinline__ void decode_read_body(const ModelDev& ma, const Model
     }
 }
 
-template <bool kUniform, class P>
-__global__ void __launch_bounds__(128, kUniform ? IDN_DEC_MINB : 1)
-decode_kernel(DecodeArgs A, const ModelDev MA, const ModelDev MQ) {
-    __shared__ uint32_t s_tab[256];
-    __shared__ uint32_t s_xpow[64];
-    uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (A.status && A.status[0] != 0) return;
-    DecCrc C{nullptr, 0xffffffffu, 0xffffffffu};
-    if (A.part_crc) {
-        for (int i = threadIdx.x; i < 256; i += blockDim.x) s_tab[i] = A.crc_tab[i];
-        for (int i = threadIdx.x; i < 64; i += blockDim.x) s_xpow[i] = A.xpow[i];
-        __syncthreads();
-        C.tab = s_tab;
+// block and index slot of read r of a block-strided index; false past the last read
+__device__ __forceinline__ bool decode_locate(const DecodeArgs& A, uint64_t r, unsigned long long& slot, unsigned long long& sym_base) {
+    const unsigned long long R = A.blk_read_base[A.n_blocks];
+    if (r >= R) return false;
+    uint32_t lo = 0, hi = A.n_blocks;  // largest b with blk_read_base[b] <= r
+    while (hi - lo > 1) {
+        uint32_t mid = (lo + hi) >> 1;
+        if (__ldg(A.blk_read_base + mid) <= r) lo = mid; else hi = mid;
     }
+    slot = A.slot_base[lo] + (r - A.blk_read_base[lo]);
+    sym_base = A.blk_sym_base[lo];
+    return true;
+}
+
+template <bool kUniform, class P>
+__device__ __forceinline__ void decode_one(const DecodeArgs& A, const ModelDev& MA, const ModelDev& MQ, uint64_t r, const uint32_t* s_tab,
+                                           const uint32_t* s_xpow) {
+    DecCrc C{A.part_crc ? s_tab : nullptr, 0xffffffffu, 0xffffffffu};
     unsigned long long slot = r, sym_base = 0;
     if (A.blk_read_base) {
+        if (!decode_locate(A, r, slot, sym_base)) return;
         const unsigned long long R = A.blk_read_base[A.n_blocks];
-        if (r >= R) return;
-        uint32_t lo = 0, hi = A.n_blocks;  // largest b with blk_read_base[b] <= r
-        while (hi - lo > 1) {
-            uint32_t mid = (lo + hi) >> 1;
-            if (__ldg(A.blk_read_base + mid) <= r) lo = mid; else hi = mid;
-        }
-        slot = A.slot_base[lo] + (r - A.blk_read_base[lo]);
-        sym_base = A.blk_sym_base[lo];
         if (r == R - 1 && A.read_off_out) A.read_off_out[R] = A.blk_sym_base[A.n_blocks];
     } else if (r >= A.n_reads) {
         return;
@@ -1965,6 +2043,52 @@ decode_kernel(DecodeArgs A, const ModelDev MA, const ModelDev MQ) {
         A.part_len[r] = 2ull * len;
     }
 }
+
+template <bool kUniform, class P>
+__global__ void __launch_bounds__(128, kUniform ? IDN_DEC_MINB : 1)
+decode_kernel(DecodeArgs A, const ModelDev MA, const ModelDev MQ) {
+    __shared__ uint32_t s_tab[256];
+    __shared__ uint32_t s_xpow[64];
+    uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (A.status && A.status[0] != 0) return;
+    if (A.part_crc) {
+        for (int k = threadIdx.x; k < 256; k += blockDim.x) s_tab[k] = A.crc_tab[k];
+        for (int k = threadIdx.x; k < 64; k += blockDim.x) s_xpow[k] = A.xpow[k];
+        __syncthreads();
+    }
+    decode_one<kUniform, P>(A, MA, MQ, r, s_tab, s_xpow);
+}
+
+// one model pair's bucket of reads (block-strided index only), see encode_list_kernel
+template <class P>
+__global__ void __launch_bounds__(128, IDN_DEC_MINB)
+decode_list_kernel(DecodeArgs A, const ModelDev MA, const ModelDev MQ, ReadList L) {
+    __shared__ uint32_t s_tab[256];
+    __shared__ uint32_t s_xpow[64];
+    if (A.status && A.status[0] != 0) return;
+    if (A.part_crc) {
+        for (int k = threadIdx.x; k < 256; k += blockDim.x) s_tab[k] = A.crc_tab[k];
+        for (int k = threadIdx.x; k < 64; k += blockDim.x) s_xpow[k] = A.xpow[k];
+        __syncthreads();
+    }
+    const uint32_t n = *L.count;
+    const uint32_t* __restrict__ list = L.list + *L.base;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x)
+        decode_one<true, P>(A, MA, MQ, list[i], s_tab, s_xpow);
+}
+
+// decompress side: the model pair the slice walk recorded for read r (container model indices; a pair that is not
+// (acid model, q-score model) in that order never reaches the decoder: the walk rejects it)
+struct DecodePairKey {
+    DecodeArgs A;
+    uint32_t n_models;
+    __device__ __forceinline__ uint32_t operator()(uint64_t r) const {
+        if (A.status && A.status[0] != 0) return 0xffffffffu;
+        unsigned long long slot, sym_base;
+        if (!decode_locate(A, r, slot, sym_base)) return 0xffffffffu;
+        return (uint32_t)A.ix.am[slot] * n_models + A.ix.qm[slot];
+    }
+};
 
 // final status word of a device-side decompress call
 __global__ void finish_decode_kernel(const int32_t* __restrict__ status, const uint32_t* __restrict__ err,
