@@ -88,15 +88,54 @@ def test_rans_small_output(O):
 
 
 def test_rans_two_channels_layout(O):
-    # two interleaved states, 4 puts each: flush order puts state 1 first in memory
-    c1 = O.quantise([0.25] * 4, 6)
-    c2 = O.quantise([0.125] * 8, 6)
+    """compressor.rs:293-321 (round_trip_two_channels): four puts on two interleaved states, then the reference's
+    assertions -- the decoder returns the pairs last-in-first-out and channel k of get() is channel k of put() -- checked
+    with an independent byte-wise decoder (ryg rans_byte: RansDecInit / RansDecAdvance / renormalisation) written out here."""
+    SB, L = 6, 1 << 23
+    c1 = O.quantise([0.25] * 4, SB)
+    c2 = O.quantise([0.125] * 8, SB)
+    assert list(c1) == [0, 16, 32, 48] and list(c2) == list(range(0, 64, 8))
+    pairs = [(0, 1), (1, 3), (2, 5), (3, 7)]
     starts, freqs = [], []
-    for s1, s2 in [(0, 1), (1, 3), (2, 5), (3, 7)]:
+    for s1, s2 in pairs:  # put(ctx1, s1, ctx2, s2) = put_at(0, s1) then put_at(1, s2)   (compressor.rs:95-96)
         starts += [c1[s1], c2[s2]]
         freqs += [16, 8]
-    out = O.rans_encode_raw(starts, freqs, 2, 6)
-    assert len(out) >= 8
+    out = O.rans_encode_raw(starts, freqs, 2, SB)
+    assert len(out) == 10  # two flushed states + one renormalisation byte per state (the 4th put of each overflows 2^31 / 2^6 * freq)
+    pos = 0
+
+    def init():
+        nonlocal pos
+        x = int.from_bytes(out[pos:pos + 4], "little")
+        pos += 4
+        return x
+
+    def get(x, cum, freq):
+        nonlocal pos
+        slot = x & ((1 << SB) - 1)
+        sym = max(k for k in range(len(cum)) if cum[k] <= slot)
+        x = freq * (x >> SB) + slot - int(cum[sym])
+        while x < L:
+            x = (x << 8) | out[pos]
+            pos += 1
+        return x, sym
+
+    # flush() writes state 0 then state 1, each in front of what is there: state 1 comes first in memory (compressor.rs:99-106),
+    # and the decoder undoes the puts in reverse: channel 1 before channel 0 (compressor.rs:181-193)
+    x1, x0 = init(), init()
+    got = []
+    for _ in pairs:
+        x1, s2 = get(x1, c2, 8)
+        x0, s1 = get(x0, c1, 16)
+        got.append((s1, s2))
+    assert got == pairs[::-1]  # LIFO order, channel pairing kept
+    assert pos == len(out) and x0 == L and x1 == L  # every byte consumed, both states back at their initial value
+    # the two channels are not interchangeable: reading the states the other way round breaks the pairing
+    pos = 0
+    y0, y1 = init(), init()
+    y1, t2 = get(y1, c2, 8)
+    y0, t1 = get(y0, c1, 16)
+    assert (t1, t2) != pairs[-1]
 
 
 # ---- model identifiers: model.rs:314, model_serializer.rs:177-189 ------------------------------------
