@@ -979,9 +979,7 @@ extern "C" int32_t idn_gpu_compress_blocks_dev(idn_gpu_ctx* ctx, const idn_batch
         aa.cand_index = dsp->cand_index;
         aa.out = out;
         aa.out_cap = out_cap;
-        static const bool thread_assemble = getenv("IDN_ASSEMBLE_THREAD") != nullptr;  // round 1's thread-per-read copy, for comparison
-        if (thread_assemble) assemble_kernel<<<(unsigned)((R + 127) / 128), 128, 0, st>>>(aa);
-        else assemble_warp_kernel<<<(unsigned)((R + 255) / 256), 256, 0, st>>>(aa);
+        assemble_kernel<<<(unsigned)((R + 127) / 128), 128, 0, st>>>(aa);
         LAUNCHED("assemble");
         stats_kernel<<<592, 256, 0, st>>>(ctx->w_paylen.as<uint32_t>(), switched, R, dsp->stats);
         LAUNCHED("stats");

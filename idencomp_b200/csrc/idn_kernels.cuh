@@ -853,51 +853,6 @@ assemble_kernel(AssembleArgs A) {
     copy_bytes_words(A.out + dst, src, total);
 }
 
-// The same with one WARP per 32 reads: lane k looks up read k's source, destination and size, then the warp copies the 32
-// reads one after the other, a word per lane (destination-aligned words funnel-shifted from two source words).  A
-// thread-per-read copy pays one L1 wavefront per lane and access (~43 per read of ~75 bytes: the kernel was wavefront
-// bound at 4.5 ms per 10 GB); here a read is two coalesced loads and one coalesced store.
-__global__ void __launch_bounds__(256)
-assemble_warp_kernel(AssembleArgs A) {
-    const uint32_t lane = threadIdx.x & 31;
-    const uint64_t r0 = (((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5) << 5;
-    if (r0 >= A.n_reads) return;
-    const uint64_t r = r0 + lane;
-    unsigned long long dst = 0, src = 0;
-    uint32_t total = 0;
-    if (r < A.n_reads) {
-        dst = A.slice_off[r] + A.block_adj[A.read_block[r]];
-        uint32_t nsw = 0;
-        if (A.switched) nsw = A.switched[r] + A.switched[A.n_reads + r];
-        total = 2u * nsw + 9u + A.pay_len[r];
-        if (dst + total > A.out_cap) total = 0;  // IDN_E_NOSPACE is reported by the host from stats
-        src = reinterpret_cast<unsigned long long>(A.scratch + 4ull * A.read_off[r + 1] + kSlotExtra * (r + 1) - total);
-    }
-    const uint32_t n_here = (uint32_t)min((uint64_t)32, A.n_reads - r0);
-#pragma unroll 1
-    for (uint32_t k = 0; k < n_here; k++) {
-        const uint32_t t = __shfl_sync(0xffffffffu, total, k);
-        if (t == 0) continue;
-        uint8_t* D = A.out + __shfl_sync(0xffffffffu, dst, k);
-        const uint8_t* S = reinterpret_cast<const uint8_t*>(__shfl_sync(0xffffffffu, src, k));
-        uint32_t head = (4u - (uint32_t)(reinterpret_cast<uintptr_t>(D) & 3)) & 3u;
-        if (head > t) head = t;
-        if (lane < head) D[lane] = S[lane];
-        const uint32_t words = (t - head) >> 2;
-        const uint8_t* s2 = S + head;
-        const uint32_t sh = (uint32_t)(reinterpret_cast<uintptr_t>(s2) & 3);
-        const uint32_t* sw = reinterpret_cast<const uint32_t*>(s2 - sh);
-        uint32_t* dw = reinterpret_cast<uint32_t*>(D + head);
-        for (uint32_t i = lane; i < words; i += 32) {
-            const uint32_t lo = __ldg(sw + i);
-            // word i + 1 holds at least one byte of the range when sh != 0 (see copy_bytes_words)
-            dw[i] = sh ? __funnelshift_r(lo, __ldg(sw + i + 1), 8 * sh) : lo;
-        }
-        const uint32_t done = head + 4 * words;
-        if (lane < t - done) D[done + lane] = S[done + lane];
-    }
-}
-
 // read -> block map (one thread per block fills its range; blocks are large, so use a grid-stride loop)
 __global__ void read_block_kernel(const uint32_t* __restrict__ block_first, uint32_t n_blocks,
                                   uint32_t* __restrict__ read_block) {
@@ -1032,10 +987,7 @@ __device__ __forceinline__ uint32_t crc_bytes_rep(const uint8_t* __restrict__ ba
     return ~c;
 }
 // two byte strings of the same length and alignment (the acids and the quality scores of a read) in lock step: two
-// independent look-up chains per thread.  kWide: the two pointers also agree modulo 16, and the middle of the strings is
-// read in 16-byte chunks (a thread-per-read kernel pays one L1 wavefront per lane and load, whatever the width: words
-// made this kernel wavefront bound at 4.5 ms per 8 GB)
-template <bool kWide>
+// independent look-up chains per thread
 __device__ __forceinline__ void crc_bytes_rep2(const uint8_t* __restrict__ pa, const uint8_t* __restrict__ pq, uint32_t n,
                                                const uint32_t* __restrict__ rtab, uint32_t& crc_a, uint32_t& crc_q) {
     uint32_t ca = 0xffffffffu, cq = 0xffffffffu;
@@ -1046,30 +998,15 @@ __device__ __forceinline__ void crc_bytes_rep2(const uint8_t* __restrict__ pa, c
     }
     const uint32_t* wa = reinterpret_cast<const uint32_t*>(pa);
     const uint32_t* wq = reinterpret_cast<const uint32_t*>(pq);
-    auto word = [&](uint32_t a, uint32_t q) {
-        ca ^= a;
-        cq ^= q;
+    for (; n >= 4; n -= 4) {
+        ca ^= __ldg(wa++);
+        cq ^= __ldg(wq++);
 #pragma unroll
         for (int k = 0; k < 4; k++) {
             ca = crc_step(ca, rtab);
             cq = crc_step(cq, rtab);
         }
-    };
-    if (kWide) {
-        for (; n >= 4 && (reinterpret_cast<uintptr_t>(wa) & 15); n -= 4) word(__ldg(wa++), __ldg(wq++));
-        const uint4* va = reinterpret_cast<const uint4*>(wa);
-        const uint4* vq = reinterpret_cast<const uint4*>(wq);
-        for (; n >= 16; n -= 16) {
-            const uint4 a = __ldg(va++), q = __ldg(vq++);
-            word(a.x, q.x);
-            word(a.y, q.y);
-            word(a.z, q.z);
-            word(a.w, q.w);
-        }
-        wa = reinterpret_cast<const uint32_t*>(va);
-        wq = reinterpret_cast<const uint32_t*>(vq);
     }
-    for (; n >= 4; n -= 4) word(__ldg(wa++), __ldg(wq++));
     pa = reinterpret_cast<const uint8_t*>(wa);
     pq = reinterpret_cast<const uint8_t*>(wq);
     for (; n; n--) {
@@ -1100,8 +1037,7 @@ crc_read_kernel(const uint8_t* __restrict__ acids, const uint8_t* __restrict__ q
     for (int i = threadIdx.x; i < 64; i += blockDim.x) xpow[i] = xpow_g[i];
     __syncthreads();
     const uint32_t* rtab = tab + (threadIdx.x & 31);
-    const uintptr_t adiff = reinterpret_cast<uintptr_t>(acids) ^ reinterpret_cast<uintptr_t>(quals);
-    const bool same_align = (adiff & 3) == 0, same_align16 = (adiff & 15) == 0;
+    const bool same_align = ((reinterpret_cast<uintptr_t>(acids) ^ reinterpret_cast<uintptr_t>(quals)) & 3) == 0;
     for (uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n_reads; r += (uint64_t)gridDim.x * blockDim.x) {
         unsigned long long off = read_off[r];
         uint32_t len = (uint32_t)(read_off[r + 1] - off);
@@ -1112,10 +1048,8 @@ crc_read_kernel(const uint8_t* __restrict__ acids, const uint8_t* __restrict__ q
             p.len = nl;
         }
         CrcPair a{0, len}, q{0, len};
-        if (same_align16) {
-            crc_bytes_rep2<true>(acids + off, quals + off, len, rtab, a.crc, q.crc);
-        } else if (same_align) {
-            crc_bytes_rep2<false>(acids + off, quals + off, len, rtab, a.crc, q.crc);
+        if (same_align) {
+            crc_bytes_rep2(acids + off, quals + off, len, rtab, a.crc, q.crc);
         } else {
             a.crc = crc_bytes_rep(acids, off, len, rtab);
             q.crc = crc_bytes_rep(quals, off, len, rtab);
