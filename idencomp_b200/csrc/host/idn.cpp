@@ -277,7 +277,7 @@ DeviceModels::~DeviceModels() {
     std::lock_guard<std::mutex> lk(c.mu);
     size_t same = 0;
     for (auto& e : c.free_) same += e.first == device_;
-    if (same < CtxCache::kKeepPerDevice) c.free_.emplace_back(device_, ctx_);
+    if (!broken_ && same < CtxCache::kKeepPerDevice) c.free_.emplace_back(device_, ctx_);
     else idn_gpu_destroy(ctx_);
 }
 void DeviceModels::open(int32_t device) {
@@ -296,7 +296,10 @@ void DeviceModels::open(int32_t device) {
     int32_t rc = idn_gpu_create(device, &ctx_);
     if (rc) throw IdnError(rc, "no usable CUDA device (this implementation has no CPU fallback)");
 }
-void DeviceModels::raise(int32_t rc) const { throw IdnError(rc, ctx_ ? idn_gpu_last_error(ctx_) : "no device context"); }
+void DeviceModels::raise(int32_t rc) const {
+    if (rc == IDN_E_CUDA) broken_ = true;
+    throw IdnError(rc, ctx_ ? idn_gpu_last_error(ctx_) : "no device context");
+}
 void DeviceModels::upload(const ModelProvider& provider) {
     for (idn_model_t h : handles_) idn_gpu_model_release(ctx_, h);
     handles_.clear();
@@ -656,6 +659,7 @@ size_t IdnCompressor::consume_text(const uint8_t* buf, size_t total, bool final)
         if (rc) {
             std::string what = idn_gpu_last_error(w->dev.ctx());
             if (ck.error_kind) what = std::string("FastqReaderError::") + fastq_error_name(ck.error_kind) + ": " + what;
+            if (rc == IDN_E_CUDA) w->dev.mark_broken();
             w->release();
             throw IdnError(rc, what);
         }

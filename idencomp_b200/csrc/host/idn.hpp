@@ -126,10 +126,12 @@ public:
     idn_gpu_ctx* ctx() const { return ctx_; }
     const std::vector<idn_model_t>& handles() const { return handles_; }
     [[noreturn]] void raise(int32_t rc) const;  // IdnError from idn_gpu_last_error
+    void mark_broken() const { broken_ = true; }
 
 private:
     idn_gpu_ctx* ctx_ = nullptr;
     int32_t device_ = 0;
+    mutable bool broken_ = false;  // a CUDA error was reported on this context: it is destroyed, not kept for the next object
     std::vector<idn_model_t> handles_;
 };
 
