@@ -1136,12 +1136,39 @@ static int32_t compress_native_dev(idn_gpu_ctx* ctx, const idn_batch* batch, Sma
         const ModelDev& hma = ctx->slots[sp.cand_model[0]].dev;
         const ModelDev& hmq = ctx->slots[sp.cand_model[kMaxCand]].dev;
         const unsigned grid = (unsigned)((lane_cap + 127) / 128);
+        const uint32_t n_pairs = sp.n_cand[0] * sp.n_cand[1];
         if (uniform) {
             IDN_LAUNCH_UNIFORM(static_pair_index(ctx, sp.cand_model[0], sp.cand_model[kMaxCand]), encode_lane_kernel, grid, st, ea, hma, hmq)
+            LAUNCHED("encode_lane");
+        } else if (ctx->bucket_pairs && lane_choice && n_pairs <= kMaxPairs && lane_cap < 0xffffffffull) {
+            // lanes bucketed by the pair lane_choose_kernel picked; one launch of the uniform kernel per pair (see the compat path)
+            CU(ctx->w_bucket.ensure(3 * kMaxPairs * 4));
+            CU(ctx->w_list.ensure(lane_cap * 4 + 16));
+            uint32_t* cnt = ctx->w_bucket.as<uint32_t>();
+            uint32_t *base = cnt + kMaxPairs, *cursor = cnt + 2 * kMaxPairs;
+            CU(cudaMemsetAsync(cnt, 0, kMaxPairs * 4, st));
+            const EncodeLanePairKey key{lane_choice, n_lanes_dev, lane_cap, sp.n_cand[1]};
+            const unsigned bgrid = (unsigned)((lane_cap + 255) / 256);
+            bucket_count_kernel<<<bgrid, 256, 0, st>>>(key, lane_cap, n_pairs, cnt);
+            LAUNCHED("bucket_count");
+            bucket_base_kernel<<<1, 32, 0, st>>>(cnt, n_pairs, base, cursor);
+            LAUNCHED("bucket_base");
+            bucket_scatter_kernel<<<bgrid, 256, 0, st>>>(key, lane_cap, n_pairs, cursor, ctx->w_list.as<uint32_t>());
+            LAUNCHED("bucket_scatter");
+            ReadList rl{ctx->w_list.as<uint32_t>(), nullptr, nullptr};
+            const unsigned lgrid = (unsigned)std::min<uint64_t>(grid, (uint64_t)ctx->sm_count * IDN_LANE_MINB);
+            for (uint32_t a = 0; a < sp.n_cand[0]; a++)
+                for (uint32_t q = 0; q < sp.n_cand[1]; q++) {
+                    const int32_t ia = sp.cand_model[a], iq = sp.cand_model[kMaxCand + q];
+                    rl.base = base + a * sp.n_cand[1] + q;
+                    rl.count = cnt + a * sp.n_cand[1] + q;
+                    IDN_LAUNCH_LIST(static_pair_index(ctx, ia, iq), encode_lane_list_kernel, lgrid, st, ea, ctx->slots[ia].dev, ctx->slots[iq].dev, rl)
+                    LAUNCHED("encode_lane");
+                }
         } else {
             encode_lane_kernel<false, DynSpecs><<<grid, 128, 0, st>>>(ea, hma, hmq);
+            LAUNCHED("encode_lane");
         }
-        LAUNCHED("encode_lane");
     }
     LaneLenFn ll{lane_len, n_lanes_dev};
     rc = scan_u64(ctx, ll, lane_cap, lane_off, st);
@@ -1441,10 +1468,40 @@ static int32_t decompress_native_dev(idn_gpu_ctx* ctx, const uint8_t* blocks, co
         const unsigned grid = (unsigned)std::max<uint64_t>(1, (lanes_est + 127) / 128);
         if (na == 1 && nq == 1) {
             IDN_LAUNCH_UNIFORM(static_pair_index(ctx, ua, uq), decode_lane_kernel, grid, st, da, ctx->slots[ua].dev, ctx->slots[uq].dev)
+            LAUNCHED("decode_lane");
+        } else if (ctx->bucket_pairs && n_models * n_models <= kMaxPairs && lane_cap < 0xffffffffull) {
+            // lanes bucketed by the model pair of the lane table; one launch of the uniform kernel per (acid, q-score) pair
+            const uint32_t n_pairs = n_models * n_models;
+            CU(ctx->w_bucket.ensure(3 * kMaxPairs * 4));
+            CU(ctx->w_list.ensure(lane_cap * 4 + 16));
+            uint32_t* cnt = ctx->w_bucket.as<uint32_t>();
+            uint32_t *base = cnt + kMaxPairs, *cursor = cnt + 2 * kMaxPairs;
+            CU(cudaMemsetAsync(cnt, 0, kMaxPairs * 4, st));
+            const DecodeLanePairKey key{ix.am, ix.qm, da.n_lanes_dev, dsp->status, n_models};
+            const unsigned bgrid = (unsigned)((lane_cap + 255) / 256);
+            bucket_count_kernel<<<bgrid, 256, 0, st>>>(key, lane_cap, n_pairs, cnt);
+            LAUNCHED("bucket_count");
+            bucket_base_kernel<<<1, 32, 0, st>>>(cnt, n_pairs, base, cursor);
+            LAUNCHED("bucket_base");
+            bucket_scatter_kernel<<<bgrid, 256, 0, st>>>(key, lane_cap, n_pairs, cursor, ctx->w_list.as<uint32_t>());
+            LAUNCHED("bucket_scatter");
+            ReadList rl{ctx->w_list.as<uint32_t>(), nullptr, nullptr};
+            const unsigned lgrid = (unsigned)std::min<uint64_t>(grid, (uint64_t)ctx->sm_count * IDN_LANE_MINB);
+            for (uint32_t a = 0; a < n_models; a++) {
+                if (ctx->slots[models[a]].dev.type != IDN_MODEL_ACID) continue;
+                for (uint32_t q = 0; q < n_models; q++) {
+                    if (ctx->slots[models[q]].dev.type == IDN_MODEL_ACID) continue;
+                    rl.base = base + a * n_models + q;
+                    rl.count = cnt + a * n_models + q;
+                    IDN_LAUNCH_LIST(static_pair_index(ctx, models[a], models[q]), decode_lane_list_kernel, lgrid, st, da, ctx->slots[models[a]].dev,
+                                    ctx->slots[models[q]].dev, rl)
+                    LAUNCHED("decode_lane");
+                }
+            }
         } else {
             decode_lane_kernel<false, DynSpecs><<<grid, 128, 0, st>>>(da, ctx->d_models_host0, ctx->d_models_host0);
+            LAUNCHED("decode_lane");
         }
-        LAUNCHED("decode_lane");
         if (block_crc) {
             // blocks that cut reads into pieces: the per-read CRC partials come from a pass over the decoded symbols (a no-op otherwise)
             int32_t rc = launch_crc_read(ctx, acids_out, quals_out, roff, nullptr, nullptr, 0, bc.reads + n_blocks, dsp->status, out_reads_cap,

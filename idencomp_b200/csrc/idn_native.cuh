@@ -148,12 +148,7 @@ constexpr unsigned long long kLaneSlotExtra = 8 + kNativeHistBytes;  // two flus
 #define IDN_LANE_MINB 8
 #endif
 template <bool kUniform, class P>
-__global__ void __launch_bounds__(128, kUniform ? IDN_LANE_MINB : 1)
-encode_lane_kernel(EncodeLaneArgs A, const ModelDev MA, const ModelDev MQ) {
-    // (register budget: the per-position loop inside encode_read_body is what counts, so the lane bounds are re-read from
-    // memory per read instead of being kept in registers across it)
-    const uint64_t l64 = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (l64 >= *A.n_lanes_dev) return;
+__device__ __forceinline__ void encode_lane_one(const EncodeLaneArgs& A, const ModelDev& MA, const ModelDev& MQ, uint64_t l64) {
     const uint32_t l = (uint32_t)l64;
     const uint32_t r_lo = A.lane_first[l];
     int32_t ia = 0, iq = 0;
@@ -199,6 +194,36 @@ encode_lane_kernel(EncodeLaneArgs A, const ModelDev MA, const ModelDev MQ) {
     A.lane_len[l] = S.total(A.scratch + 4ull * A.lane_sym[l + 1] + kLaneSlotExtra * ((unsigned long long)l + 1));
     if (S.bad) atomicOr(A.err, 1u);
 }
+
+template <bool kUniform, class P>
+__global__ void __launch_bounds__(128, kUniform ? IDN_LANE_MINB : 1)
+encode_lane_kernel(EncodeLaneArgs A, const ModelDev MA, const ModelDev MQ) {
+    // (register budget: the per-position loop inside encode_read_body is what counts, so the lane bounds are re-read from
+    // memory per read instead of being kept in registers across it)
+    const uint64_t l64 = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (l64 >= *A.n_lanes_dev) return;
+    encode_lane_one<kUniform, P>(A, MA, MQ, l64);
+}
+
+// per-lane model selection: the lanes that chose one model pair (a bucket of bucket_scatter_kernel), see encode_list_kernel
+template <class P>
+__global__ void __launch_bounds__(128, IDN_LANE_MINB)
+encode_lane_list_kernel(EncodeLaneArgs A, const ModelDev MA, const ModelDev MQ, ReadList L) {
+    const uint32_t n = *L.count;
+    const uint32_t* __restrict__ list = L.list + *L.base;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x)
+        encode_lane_one<true, P>(A, MA, MQ, list[i]);
+}
+
+struct EncodeLanePairKey {  // compress side: the candidates lane_choose_kernel picked
+    const uint8_t* lane_choice;  // [2][lane_cap]
+    const unsigned long long* n_lanes_dev;
+    uint64_t lane_cap;
+    uint32_t n_q;
+    __device__ __forceinline__ uint32_t operator()(uint64_t l) const {
+        return l < *n_lanes_dev ? (uint32_t)lane_choice[l] * n_q + lane_choice[lane_cap + l] : 0xffffffffu;
+    }
+};
 
 struct LaneLenFn {
     const uint32_t* lane_len;
@@ -646,6 +671,48 @@ struct DecodeLaneArgs {
 };
 
 template <bool kUniform, class P>
+__device__ __forceinline__ void decode_lane_one(const DecodeLaneArgs& A, const ModelDev& MA, const ModelDev& MQ, unsigned long long l64, DecCrc& C,
+                                                const uint32_t* s_xpow) {
+    // (register budget: the per-position loop inside decode_read_body is what counts, so the lane bounds and the
+    // payload address are re-read from the index per read instead of being kept in registers across it)
+    const uint32_t l = (uint32_t)l64;
+    const ModelDev& ma = kUniform ? MA : A.models[A.model_ids[A.ix.am[l]]];
+    const ModelDev& mq = kUniform ? MQ : A.models[A.model_ids[A.ix.qm[l]]];
+    uint32_t r = (uint32_t)A.ix.first_read[l];
+    // (first_read <= n_reads and read_off holds n_reads + 1 entries)
+    const bool mid = A.ix.sym_start[l + 1] > A.ix.sym_start[l] && A.ix.sym_start[l] > A.read_off[r];  // the lane starts inside read r
+    const bool bad = mid && A.ix.pay_len[l] < kNativeHistBytes + 8;
+    const uint32_t lead = (mid && !bad) ? kNativeHistBytes : 0u;  // history bytes in front of the stream
+    DecStream D;
+    D.begin(A.payload + A.ix.pay_off[l], lead, bad ? 0u : A.ix.pay_len[l] - lead);
+    SymWriter O;
+    O.init(A.acids_out + A.ix.sym_start[l], A.out_dq);
+    // the reads with a symbol in [a, b): the loop ends by itself at the last read (read_off[n_reads] >= b)
+#pragma unroll 1
+    for (;; r++) {
+        const unsigned long long a = A.ix.sym_start[l], b = A.ix.sym_start[l + 1];
+        const unsigned long long o = A.read_off[r];
+        if (o >= b) break;
+        const unsigned long long o_next = A.read_off[r + 1];
+        if (o_next > a) {
+            const uint32_t len = (uint32_t)(o_next - o);
+            const uint32_t p0 = (uint32_t)((a > o ? a : o) - o), p1 = (uint32_t)((b < o_next ? b : o_next) - o);
+            decode_read_body<P>(ma, mq, len, p0, p1, A.payload + A.ix.pay_off[l], D, O, C);
+            if (C.tab) {  // whole reads only (no block of the call cuts reads)
+                const CrcPair p = crc_concat(CrcPair{~C.ca, len}, CrcPair{~C.cq, len}, s_xpow);
+                A.part_crc[r] = len ? p.crc : 0u;
+                A.part_len[r] = 2ull * len;
+                C.ca = C.cq = 0xffffffffu;
+            }
+        }
+    }
+    O.flush();
+    const uint32_t plen = A.ix.pay_len[l] - lead;
+    D.finish(A.payload + A.ix.pay_off[l], lead, plen);
+    if (bad || (D.st & 1) || !D.clean_end(plen)) atomicOr(A.err, 1u);
+}
+
+template <bool kUniform, class P>
 __global__ void __launch_bounds__(128, kUniform ? IDN_LANE_MINB : 1)
 decode_lane_kernel(DecodeLaneArgs A, const ModelDev MA, const ModelDev MQ) {
     __shared__ uint32_t s_tab[256];
@@ -661,45 +728,41 @@ decode_lane_kernel(DecodeLaneArgs A, const ModelDev MA, const ModelDev MQ) {
     const unsigned long long n_lanes = *A.n_lanes_dev;
     // (grid-stride: a call whose blocks cut long reads into pieces may hold more lanes than the launch has threads)
 #pragma unroll 1
-    for (unsigned long long l64 = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; l64 < n_lanes; l64 += (unsigned long long)gridDim.x * blockDim.x) {
-        // (register budget: the per-position loop inside decode_read_body is what counts, so the lane bounds and the
-        // payload address are re-read from the index per read instead of being kept in registers across it)
-        const uint32_t l = (uint32_t)l64;
-        const ModelDev& ma = kUniform ? MA : A.models[A.model_ids[A.ix.am[l]]];
-        const ModelDev& mq = kUniform ? MQ : A.models[A.model_ids[A.ix.qm[l]]];
-        uint32_t r = (uint32_t)A.ix.first_read[l];
-        // (first_read <= n_reads and read_off holds n_reads + 1 entries)
-        const bool mid = A.ix.sym_start[l + 1] > A.ix.sym_start[l] && A.ix.sym_start[l] > A.read_off[r];  // the lane starts inside read r
-        const bool bad = mid && A.ix.pay_len[l] < kNativeHistBytes + 8;
-        const uint32_t lead = (mid && !bad) ? kNativeHistBytes : 0u;  // history bytes in front of the stream
-        DecStream D;
-        D.begin(A.payload + A.ix.pay_off[l], lead, bad ? 0u : A.ix.pay_len[l] - lead);
-        SymWriter O;
-        O.init(A.acids_out + A.ix.sym_start[l], A.out_dq);
-        // the reads with a symbol in [a, b): the loop ends by itself at the last read (read_off[n_reads] >= b)
-#pragma unroll 1
-        for (;; r++) {
-            const unsigned long long a = A.ix.sym_start[l], b = A.ix.sym_start[l + 1];
-            const unsigned long long o = A.read_off[r];
-            if (o >= b) break;
-            const unsigned long long o_next = A.read_off[r + 1];
-            if (o_next > a) {
-                const uint32_t len = (uint32_t)(o_next - o);
-                const uint32_t p0 = (uint32_t)((a > o ? a : o) - o), p1 = (uint32_t)((b < o_next ? b : o_next) - o);
-                decode_read_body<P>(ma, mq, len, p0, p1, A.payload + A.ix.pay_off[l], D, O, C);
-                if (C.tab) {  // whole reads only (no block of the call cuts reads)
-                    const CrcPair p = crc_concat(CrcPair{~C.ca, len}, CrcPair{~C.cq, len}, s_xpow);
-                    A.part_crc[r] = len ? p.crc : 0u;
-                    A.part_len[r] = 2ull * len;
-                    C.ca = C.cq = 0xffffffffu;
-                }
-            }
-        }
-        O.flush();
-        const uint32_t plen = A.ix.pay_len[l] - lead;
-        D.finish(A.payload + A.ix.pay_off[l], lead, plen);
-        if (bad || (D.st & 1) || !D.clean_end(plen)) atomicOr(A.err, 1u);
-    }
+    for (unsigned long long l64 = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; l64 < n_lanes; l64 += (unsigned long long)gridDim.x * blockDim.x)
+        decode_lane_one<kUniform, P>(A, MA, MQ, l64, C, s_xpow);
 }
+
+// the lanes of one model pair, see decode_list_kernel
+template <class P>
+__global__ void __launch_bounds__(128, IDN_LANE_MINB)
+decode_lane_list_kernel(DecodeLaneArgs A, const ModelDev MA, const ModelDev MQ, ReadList L) {
+    __shared__ uint32_t s_tab[256];
+    __shared__ uint32_t s_xpow[64];
+    if (A.status[0] != 0) return;
+    DecCrc C{nullptr, 0xffffffffu, 0xffffffffu};
+    if (A.part_crc && *A.split_flag == 0) {
+        for (int i = threadIdx.x; i < 256; i += blockDim.x) s_tab[i] = A.crc_tab[i];
+        for (int i = threadIdx.x; i < 64; i += blockDim.x) s_xpow[i] = A.xpow[i];
+        __syncthreads();
+        C.tab = s_tab;
+    }
+    const uint32_t n = *L.count;
+    const uint32_t* __restrict__ list = L.list + *L.base;
+#pragma unroll 1
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x)
+        decode_lane_one<true, P>(A, MA, MQ, list[i], C, s_xpow);
+}
+
+struct DecodeLanePairKey {  // decompress side: the model pair of lane l from the lane table (container model indices)
+    const uint8_t* am;
+    const uint8_t* qm;
+    const unsigned long long* n_lanes_dev;
+    const int32_t* status;
+    uint32_t n_models;
+    __device__ __forceinline__ uint32_t operator()(uint64_t l) const {
+        if (status[0] != 0 || l >= *n_lanes_dev) return 0xffffffffu;
+        return (uint32_t)am[l] * n_models + qm[l];
+    }
+};
 
 }  // namespace idn
