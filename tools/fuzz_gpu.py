@@ -76,7 +76,7 @@ def one_case(gctx, seed, log):
         block_len = int(max(2 * max_len, rng.choice([200, 1000, 5000, 60000])))
         bf = blocks_of(reads, block_len)
         nb = len(bf) - 1
-        fast = bool(rng.random() < 0.25)
+        fast = bool(rng.random() < 0.4) and n_a == 1 and n_q == 1  # fast mode takes exactly one model per type (compressor_block.rs:96)
         gctx.set_pipeline_blocks(int(rng.integers(1, 6)))
         what = f"seed {seed}: {reads.n_reads} reads, max len {max_len}, {n_a}+{n_q} models {[m.md.spec_name for m in models]}, {nb} blocks of {block_len}, fast {fast}"
         # ---- compat
