@@ -249,64 +249,6 @@ score_multi_kernel(const ModelPack<M> P, const uint8_t* __restrict__ acids, cons
     ra.start(acids + off);
     rq.start(quals + off);
     bool bad = false;
-#ifndef IDN_SCORE_NOPIPE
-    // Software pipeline over the two dependent gather levels (spec -> row, row -> encoder entry): iteration i gathers the
-    // entries of position i (rows known since iteration i-1), moves the generators to position i+1 and gathers its rows,
-    // and only then codes position i-1 with the entries iteration i-1 gathered -- every load has one iteration of the
-    // other models' work to arrive in.  (The generators depend on the symbols only, never on the coder state.)
-    uint32_t row[M];   // position i: acid models with aenc: spec index, else the context row
-    uint2 ep[M];       // entries of position i-1
-#pragma unroll
-    for (int k = 0; k < M; k++) {
-        row[k] = 0;
-        ep[k] = make_uint2(0, 0);
-        if (k < (int)P.n && len) {
-            const ModelDev& m = P.m[k];
-            row[k] = m.aenc ? g[k].index(m.spec, pf.pos, pbmax - m.spec.pb) : gen_row<kDense>(m, m.spec, g[k], pf.pos, pbmax - m.spec.pb);
-        }
-    }
-#pragma unroll 1
-    for (uint32_t i = 0; i < len; i++) {
-        uint32_t a = ra.get(), q = rq.get();
-        if (a > 4 || q > 93) {
-            bad = true;
-            a = a > 4 ? 0 : a;
-            q = q > 93 ? 0 : q;
-        }
-        const bool z = a * q == 0;
-        uint2 en[M];
-#pragma unroll
-        for (int k = 0; k < M; k++)
-            if (k < (int)P.n) {
-                const ModelDev& m = P.m[k];
-                en[k] = m.aenc ? __ldg(m.aenc + (row[k] * kAcidSyms + a)) : __ldg(m.enc + (row[k] * m.nsym + (m.type == 0 ? a : q)));
-            }
-#pragma unroll
-        for (int k = 0; k < M; k++)
-            if (k < (int)P.n) g[k].update(P.m[k].spec, a, q, z);
-        pf.advance();
-        if (i + 1 < len) {
-#pragma unroll
-            for (int k = 0; k < M; k++)
-                if (k < (int)P.n) {
-                    const ModelDev& m = P.m[k];
-                    row[k] = m.aenc ? g[k].index(m.spec, pf.pos, pbmax - m.spec.pb) : gen_row<kDense>(m, m.spec, g[k], pf.pos, pbmax - m.spec.pb);
-                }
-        }
-        if (i) {
-#pragma unroll
-            for (int k = 0; k < M; k++)
-                if (k < (int)P.n) rans_put_count(x[k], ep[k], bytes[k]);
-        }
-#pragma unroll
-        for (int k = 0; k < M; k++) ep[k] = en[k];
-    }
-    if (len) {
-#pragma unroll
-        for (int k = 0; k < M; k++)
-            if (k < (int)P.n) rans_put_count(x[k], ep[k], bytes[k]);
-    }
-#else
 #pragma unroll 1
     for (uint32_t i = 0; i < len; i++) {
         uint32_t a = ra.get(), q = rq.get();
@@ -336,7 +278,6 @@ score_multi_kernel(const ModelPack<M> P, const uint8_t* __restrict__ acids, cons
             }
         pf.advance();
     }
-#endif
 #pragma unroll
     for (int k = 0; k < M; k++)
         if (k < (int)P.n) sizes[r * n_cols + col0 + k] = bytes[k] + 4;
