@@ -116,6 +116,8 @@ struct idn_gpu_ctx {
     int32_t walk_mode = 0;  // idn_gpu_set_walk
     uint32_t* d_crc_tab = nullptr;  // [256]
     uint32_t* d_xpow = nullptr;     // [64]
+    uint32_t* d_crc_back = nullptr;  // [512 + 2 * kCrcLenTab]: Tinv | U (backward CRC step) | {x^(8n), x^(16n)} for n < kCrcLenTab
+    bool enc_crc = true;             // IDN_NO_ENC_CRC=1: the per-read CRC partials of a compress call come from crc_read_kernel
     // workspaces of the *_dev paths
     DevBuf w_scratch, w_paylen, w_sizes, w_chosen, w_tiles, w_sliceoff, w_readblock, w_small, w_crcpart, w_crclen;
     DevBuf w_walkdone, w_blockadj;
@@ -373,6 +375,34 @@ static void make_crc_tables(uint32_t* tab, uint32_t* xpow) {
     for (int k = 1; k < 64; k++) xpow[k] = mul(xpow[k - 1], xpow[k - 1]);
 }
 
+// Tables of the backward CRC the encoder runs (it visits a read's symbols last to first; EncCrc in idn_kernels.cuh):
+// Tinv / U undo one "advance by a zero byte" step, xlen[n] = {x^(8n), x^(16n)} mod P bring the result back into place.
+static void make_crc_back_tables(const uint32_t* tab, const uint32_t* xpow, uint32_t* back /*[512 + 2 * kCrcLenTab]*/) {
+    uint32_t rtop[256];
+    for (uint32_t i = 0; i < 256; i++) rtop[tab[i] >> 24] = i;  // the top bytes of the table are a permutation
+    uint32_t* tinv = back;
+    uint32_t* u = back + 256;
+    for (uint32_t t = 0; t < 256; t++) tinv[t] = (tab[rtop[t]] << 8) | rtop[t];
+    auto linv = [&](uint32_t v) { return (v << 8) ^ tinv[v >> 24]; };
+    for (uint32_t b = 0; b < 256; b++) u[b] = linv(tab[b]);
+    auto mul = [](uint32_t a, uint32_t b) {
+        uint32_t p = 0;
+        for (int i = 0; i < 32; i++) {
+            if (b & 0x80000000u) p ^= a;
+            a = (a >> 1) ^ ((a & 1) ? 0xEDB88320u : 0);
+            b <<= 1;
+        }
+        return p;
+    };
+    uint32_t* xlen = back + 512;
+    uint32_t x = 0x80000000u;  // x^0
+    for (uint32_t n = 0; n < kCrcLenTab; n++) {
+        xlen[2 * n] = x;
+        xlen[2 * n + 1] = mul(x, x);
+        x = mul(x, xpow[0]);
+    }
+}
+
 extern "C" int32_t idn_gpu_create(int32_t device, idn_gpu_ctx** out) {
     if (!out) return IDN_E_INVALID_ARG;
     *out = nullptr;
@@ -400,6 +430,13 @@ extern "C" int32_t idn_gpu_create(int32_t device, idn_gpu_ctx** out) {
     if (cudaMalloc(&ctx->d_xpow, sizeof xpow) != cudaSuccess) return bail("cudaMalloc");
     if (cudaMemcpy(ctx->d_crc_tab, tab, sizeof tab, cudaMemcpyHostToDevice) != cudaSuccess) return bail("cudaMemcpy");
     if (cudaMemcpy(ctx->d_xpow, xpow, sizeof xpow, cudaMemcpyHostToDevice) != cudaSuccess) return bail("cudaMemcpy");
+    {
+        std::vector<uint32_t> back(512 + 2 * kCrcLenTab);
+        make_crc_back_tables(tab, xpow, back.data());
+        if (cudaMalloc(&ctx->d_crc_back, back.size() * 4) != cudaSuccess) return bail("cudaMalloc");
+        if (cudaMemcpy(ctx->d_crc_back, back.data(), back.size() * 4, cudaMemcpyHostToDevice) != cudaSuccess) return bail("cudaMemcpy");
+    }
+    if (getenv("IDN_NO_ENC_CRC")) ctx->enc_crc = false;
     *out = ctx;
     return IDN_OK;
 }
@@ -427,6 +464,7 @@ extern "C" void idn_gpu_destroy(idn_gpu_ctx* ctx) {
     cudaFree(ctx->d_models);
     cudaFree(ctx->d_crc_tab);
     cudaFree(ctx->d_xpow);
+    cudaFree(ctx->d_crc_back);
     if (ctx->ev) cudaEventDestroy(ctx->ev);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
@@ -806,7 +844,7 @@ extern "C" uint64_t idn_gpu_compress_bound(uint64_t n_reads, uint64_t n_symbols,
 }
 
 static int32_t idn_gpu_block_crc_dev_impl(idn_gpu_ctx* ctx, const idn_batch* batch, uint32_t* block_crc, uint8_t* out,
-                                          const unsigned long long* block_off, uint64_t out_cap, cudaStream_t st);
+                                          const unsigned long long* block_off, uint64_t out_cap, cudaStream_t st, bool have_partials = false);
 static int32_t compress_native_dev(idn_gpu_ctx* ctx, const idn_batch* batch, SmallParams& sp, int32_t fast,
                                    const uint32_t* prefix_len, uint8_t* out, uint64_t out_cap, uint64_t* block_off,
                                    uint32_t* block_crc, idn_compress_stats* stats_dev, cudaStream_t st);
@@ -830,6 +868,7 @@ extern "C" int32_t idn_gpu_compress_blocks_dev(idn_gpu_ctx* ctx, const idn_batch
     PROF_BEGIN();
     const uint64_t R = batch->n_reads, S = batch->n_symbols;
     const uint32_t B = batch->n_blocks;
+    const bool fuse_crc = ctx->enc_crc && batch->names == nullptr && R > 0;  // compat mode only (the native path returns above this use)
 
     // candidate lists per type, in provider order (model_provider.rs:210-238)
     SmallParams sp;
@@ -903,6 +942,19 @@ extern "C" int32_t idn_gpu_compress_blocks_dev(idn_gpu_ctx* ctx, const idn_batch
         ea.err = &dsp->err;
         ea.switched = switched;
         ea.cand_index = dsp->cand_index;
+        // no identifiers in the block CRC: the encoder leaves the per-read partials crc(acids | quals) itself (it walks the
+        // symbols anyway, backwards: EncCrc), and the pass of crc_read_kernel over the input is not needed
+        ea.crc_back = nullptr;
+        ea.xpow = ctx->d_xpow;
+        ea.part_crc = nullptr;
+        ea.part_len = nullptr;
+        if (fuse_crc) {
+            CU(ctx->w_crcpart.ensure((R + 1) * 4));
+            CU(ctx->w_crclen.ensure((R + 1) * 8));
+            ea.crc_back = ctx->d_crc_back;
+            ea.part_crc = ctx->w_crcpart.as<uint32_t>();
+            ea.part_len = ctx->w_crclen.as<unsigned long long>();
+        }
         const bool uniform = !chosen || (sp.n_cand[0] == 1 && sp.n_cand[1] == 1);
         const ModelDev& hma = ctx->slots[sp.cand_model[0]].dev;
         const ModelDev& hmq = ctx->slots[sp.cand_model[kMaxCand]].dev;
@@ -985,7 +1037,7 @@ extern "C" int32_t idn_gpu_compress_blocks_dev(idn_gpu_ctx* ctx, const idn_batch
         LAUNCHED("stats");
     }
     // K7: block CRCs into the block headers
-    rc = idn_gpu_block_crc_dev_impl(ctx, batch, block_crc, out, reinterpret_cast<unsigned long long*>(block_off), out_cap, st);
+    rc = idn_gpu_block_crc_dev_impl(ctx, batch, block_crc, out, reinterpret_cast<unsigned long long*>(block_off), out_cap, st, fuse_crc);
     if (rc) return rc;
     if (stats_dev) {
         finish_stats_kernel<<<1, 32, 0, st>>>(dsp->stats, &dsp->err, reinterpret_cast<unsigned long long*>(stats_dev), ctx->pipe_err_out);
@@ -1016,11 +1068,11 @@ static int32_t launch_crc_read(idn_gpu_ctx* ctx, const uint8_t* acids, const uin
 }
 
 static int32_t idn_gpu_block_crc_dev_impl(idn_gpu_ctx* ctx, const idn_batch* batch, uint32_t* block_crc, uint8_t* out,
-                                          const unsigned long long* block_off, uint64_t out_cap, cudaStream_t st) {
+                                          const unsigned long long* block_off, uint64_t out_cap, cudaStream_t st, bool have_partials) {
     const uint64_t R = batch->n_reads;
     CU(ctx->w_crcpart.ensure((R + 1) * 4));
     CU(ctx->w_crclen.ensure((R + 1) * 8));
-    if (R > 0) {
+    if (R > 0 && !have_partials) {  // (have_partials: the encoder of this call left them)
         int32_t rc = launch_crc_read(ctx, batch->acids, batch->quals, reinterpret_cast<const unsigned long long*>(batch->read_off),
                                      batch->names, reinterpret_cast<const unsigned long long*>(batch->name_off), R, nullptr, nullptr, R,
                                      batch->n_symbols / R, st);

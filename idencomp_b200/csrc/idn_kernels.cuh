@@ -390,6 +390,11 @@ struct EncodeArgs {
     uint32_t* err;
     const uint8_t* switched;            // [2][n_reads]: a SwitchModel slice precedes the read's Sequence slice, or nullptr
     const uint8_t* cand_index;          // [2][kMaxCand] candidate -> SwitchModel index
+    // optional: the per-read CRC-32 partials crc(acids | quals) for crc_block_kernel, computed on the way (EncCrc)
+    const uint32_t* crc_back;           // [512 + 2 * kCrcLenTab] (make_crc_back_tables), or nullptr
+    const uint32_t* xpow;               // [64]
+    uint32_t* part_crc;
+    unsigned long long* part_len;
 };
 // the reads of one launch of a *_list_kernel: list[*base .. *base + *count), one bucket of bucket_scatter_kernel (the reads
 // that chose this launch's model pair)
@@ -423,6 +428,25 @@ struct EncStream {
     __device__ __forceinline__ uint32_t total(const uint8_t* slot_end) const { return out.bytes(slot_end); }  // bytes emitted so far
 };
 
+// CRC-32 of a byte string whose bytes arrive LAST TO FIRST (the encoder's order).  With L = "advance the register by one
+// zero byte" (c -> tab[c & 0xff] ^ (c >> 8), linear over GF(2)) the register after the string b_0 .. b_{n-1} is
+// L^n(ff..f) ^ XOR_i L^(n-1-i)(tab[b_i]).  Keeping B = L^-(n-i)(contribution of b_i .. b_{n-1}) turns the backward walk into
+// B <- Linv(B) ^ Linv(tab[b]) = (B << 8) ^ tinv[B >> 24] ^ u[b]  -- one shift and two look-ups per byte, like the forward
+// step -- and crc = ~L^n(B ^ ff..f), where L^n is the multiplication by x^(8n) mod P (gf2_mul).  For acids | quals of one
+// read (two strings of n bytes walked in lock step): crc = ~(x^(8n) * Bq  ^  x^(16n) * (Ba ^ ff..f)).
+constexpr uint32_t kCrcLenTab = 1024;  // read lengths whose x^(8n), x^(16n) come from a table
+__device__ __forceinline__ uint32_t gf2_mul(uint32_t a, uint32_t b);  // (K7 section below)
+__device__ __forceinline__ uint32_t x8n_mod_p(unsigned long long n, const uint32_t* __restrict__ xpow);
+struct EncCrc {
+    const uint32_t* tinv;  // shared memory [256], or nullptr: no CRC
+    const uint32_t* u;     // shared memory [256]
+    uint32_t ba, bq;
+    __device__ __forceinline__ void add(uint32_t a, uint32_t q) {
+        ba = (ba << 8) ^ tinv[ba >> 24] ^ u[a];
+        bq = (bq << 8) ^ tinv[bq >> 24] ^ u[q];
+    }
+};
+
 // Pushes the positions p1-1 .. p0 of one read onto the stream (the whole read: p0 = 0, p1 = len)
 //   SequenceCompressor::compress, sequence_compressor.rs:82-155
 // The generators always see the true symbols in front of a position, so a piece of a read (native format, long reads cut
@@ -434,7 +458,7 @@ struct EncStream {
 template <class P>
 __device__ __forceinline__ void encode_read_body(const ModelDev& ma, const ModelDev& mq, const uint8_t* __restrict__ acids,
                                                  const uint8_t* __restrict__ quals, unsigned long long n_symbols, long long off,
-                                                 uint32_t len, uint32_t p0, uint32_t p1, EncStream& S) {
+                                                 uint32_t len, uint32_t p0, uint32_t p1, EncStream& S, EncCrc& C) {
     constexpr SpecDev ksa = P::sa(), ksq = P::sq();  // compile-time generator parameters of a specialised pair
     const SpecDev& sa = P::kStatic ? ksa : ma.spec;
     const SpecDev& sq = P::kStatic ? ksq : mq.spec;
@@ -467,6 +491,7 @@ __device__ __forceinline__ void encode_read_body(const ModelDev& ma, const Model
                 a = a > 4 ? 0 : a;
                 q = q > 93 ? 0 : q;
             }
+            if (C.tinv) C.add(a, q);  // uniform per launch; whole reads only (every position is pulled exactly once, last to first)
         }
         front--;
         const bool z = a * q == 0;
@@ -543,7 +568,7 @@ __device__ __forceinline__ void encode_read_body(const ModelDev& ma, const Model
 #define IDN_DEC_MINB 8
 #endif
 template <bool kUniform, class P>
-__device__ __forceinline__ void encode_one(const EncodeArgs& A, const ModelDev& MA, const ModelDev& MQ, uint64_t r) {
+__device__ __forceinline__ void encode_one(const EncodeArgs& A, const ModelDev& MA, const ModelDev& MQ, uint64_t r, const uint32_t* s_back) {
     int32_t ia = A.fixed_acid, iq = A.fixed_q;
     if (!kUniform && A.chosen) {
         ia = A.cand_model[A.chosen[r]];
@@ -555,7 +580,21 @@ __device__ __forceinline__ void encode_one(const EncodeArgs& A, const ModelDev& 
     const uint32_t len = (uint32_t)(A.read_off[r + 1] - A.read_off[r]);
     EncStream S;
     S.begin(A.scratch + 4ull * A.read_off[r + 1] + kSlotExtra * (r + 1));
-    encode_read_body<P>(ma, mq, A.acids, A.quals, A.n_symbols, off, len, 0, len, S);
+    EncCrc C{A.crc_back ? s_back : nullptr, s_back + 256, 0u, 0u};
+    encode_read_body<P>(ma, mq, A.acids, A.quals, A.n_symbols, off, len, 0, len, S, C);
+    if (A.crc_back) {  // crc(acids | quals) of the read, as crc_read_kernel computes it
+        uint32_t x1, x2;  // x^(8 len), x^(16 len) mod P
+        if (len < kCrcLenTab) {
+            const uint2 x = __ldg(reinterpret_cast<const uint2*>(A.crc_back + 512) + len);
+            x1 = x.x;
+            x2 = x.y;
+        } else {
+            x1 = x8n_mod_p(len, A.xpow);
+            x2 = gf2_mul(x1, x1);
+        }
+        A.part_crc[r] = len ? ~(gf2_mul(x1, C.bq) ^ gf2_mul(x2, ~C.ba)) : 0u;
+        A.part_len[r] = 2ull * len;
+    }
     S.flush_states();
     const uint32_t plen = S.total(A.scratch + 4ull * A.read_off[r + 1] + kSlotExtra * (r + 1));
     A.pay_len[r] = plen;
@@ -582,9 +621,14 @@ __device__ __forceinline__ void encode_one(const EncodeArgs& A, const ModelDev& 
 template <bool kUniform, class P>
 __global__ void __launch_bounds__(128, kUniform ? IDN_ENC_MINB : 1)
 encode_kernel(EncodeArgs A, const ModelDev MA, const ModelDev MQ) {
+    __shared__ uint32_t s_back[512];
+    if (A.crc_back) {
+        for (int i = threadIdx.x; i < 512; i += blockDim.x) s_back[i] = A.crc_back[i];
+        __syncthreads();
+    }
     uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= A.n_reads) return;
-    encode_one<kUniform, P>(A, MA, MQ, r);
+    encode_one<kUniform, P>(A, MA, MQ, r, s_back);
 }
 
 // Per-read model selection: one launch per model pair over the reads that chose it (a fixed grid strides over the bucket,
@@ -593,10 +637,15 @@ encode_kernel(EncodeArgs A, const ModelDev MA, const ModelDev MQ) {
 template <class P>
 __global__ void __launch_bounds__(128, IDN_ENC_MINB)
 encode_list_kernel(EncodeArgs A, const ModelDev MA, const ModelDev MQ, ReadList L) {
+    __shared__ uint32_t s_back[512];
+    if (A.crc_back) {
+        for (int i = threadIdx.x; i < 512; i += blockDim.x) s_back[i] = A.crc_back[i];
+        __syncthreads();
+    }
     const uint32_t n = *L.count;
     const uint32_t* __restrict__ list = L.list + *L.base;
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x)
-        encode_one<true, P>(A, MA, MQ, list[i]);
+        encode_one<true, P>(A, MA, MQ, list[i], s_back);
 }
 
 // ---------------------------------------------------------------------------------------------------

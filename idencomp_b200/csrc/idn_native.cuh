@@ -159,6 +159,7 @@ __device__ __forceinline__ void encode_lane_one(const EncodeLaneArgs& A, const M
     const ModelDev& ma = kUniform ? MA : A.models[ia];
     const ModelDev& mq = kUniform ? MQ : A.models[iq];
     EncStream S;
+    EncCrc C{nullptr, nullptr, 0u, 0u};  // (the native path takes its CRC partials from crc_read_kernel)
     S.begin(A.scratch + 4ull * A.lane_sym[l + 1] + kLaneSlotExtra * ((unsigned long long)l + 1));
     if (A.lane_sym[l + 1] > A.lane_sym[l]) {
         // the last read with a symbol in the lane, then down to the first
@@ -170,7 +171,7 @@ __device__ __forceinline__ void encode_lane_one(const EncodeLaneArgs& A, const M
             const unsigned long long ro = A.read_off[r], re = A.read_off[r + 1];
             if (re > a && ro < b) {
                 const uint32_t p0 = (uint32_t)((a > ro ? a : ro) - ro), p1 = (uint32_t)((b < re ? b : re) - ro);
-                encode_read_body<P>(ma, mq, A.acids, A.quals, A.n_symbols, (long long)ro, (uint32_t)(re - ro), p0, p1, S);
+                encode_read_body<P>(ma, mq, A.acids, A.quals, A.n_symbols, (long long)ro, (uint32_t)(re - ro), p0, p1, S, C);
             }
             if (r == r_lo) break;
         }
