@@ -7,7 +7,13 @@
 A step = one pass of the hot path over the workload's batch: compress every block, then decompress every block.
 `value` = FASTQ text bytes through the codec per second (2 x FASTQ bytes / (t_compress + t_decompress)), inputs
 resident in HBM, timed with CUDA events on the launching stream.  `e2e` = the same through the host-pointer C-ABI
-calls (pinned host buffers, H2D/D2H inside the timed region).  Nothing here reads /root/reference.
+calls (pinned host buffers, H2D/D2H inside the timed region; one context, one host thread, one self-pipelining call per
+direction).  The same JSON line carries `workloads` (sub-records with value / e2e / roofline for the other named
+configurations: NovaSeq-shaped 150 bp in the native format, PacBio-shaped long reads in both formats, per-read selection
+among 4 + 4 models), `e2e_file` (FASTQ text -> .idn -> FASTQ text through the host mirror of the reference API, with and
+without identifiers, and the identifiers codec alone), `fastq_text`, `other_mode` and, at N > 1, `strong_scaling` (ONE file
+over the ranks).  --no-extra-workloads / --no-e2e / --no-fastq / --no-other-mode / --no-cpu-baseline trim the run.
+Nothing here reads /root/reference.
 The oracle (oracle/) is used only for `cpu_baseline` / `--impl reference`: the Rust reference cannot be built in
 this image, so its CPU restatement (pinned bit-exactly to the reference's golden container) is what is timed.
 """
