@@ -846,7 +846,7 @@ def e2e_file_leg(args, w, env, acids_d, quals_d, read_off_h, n):
     out["contexts_on_the_device"] = len(devs)
     for names in (False, True):
         best = None
-        for it in range(3):  # the last pass is the timed one: the library keeps device contexts and page-locked buffers
+        for it in range(4):  # the last pass is the timed one: the library keeps device contexts and page-locked buffers
             # between objects (sized by the passes before), as a process that compresses more than one file would find them
             c = host.IdnCompressor(models, include_identifiers=names, thread_num=cores, devices=devs,
                                    text_chunk_bytes=args.text_chunk_mb << 20, batch_blocks=args.file_batch_blocks)

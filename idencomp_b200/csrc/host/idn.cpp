@@ -210,11 +210,15 @@ PinnedPool::State& PinnedPool::state() {
 }
 
 std::shared_ptr<PinnedBuf> PinnedPool::get(size_t n) {
-    // Sizes are rounded up to a power of two (1 MB at least) and a buffer is never regrown for a larger request: requests of
+    // Sizes are rounded up to a size class (1 MB at least) and a buffer is never regrown for a larger request: requests of
     // about the same size then find each other's buffers whatever order the worker threads ask in, and the pool stops
-    // allocating once it has seen the peak number of buffers in flight per size class (at most 2 x the memory).
+    // allocating once it has seen the peak number of buffers in flight per size class.
     size_t cls = 1 << 20;
     while (cls < n) cls <<= 1;
+    if (cls > (1 << 20)) {  // eighths of the power of two above n: at most 12.5 % over
+        const size_t step = cls >> 4;
+        cls = (n + step - 1) / step * step;
+    }
     State& st = state();
     std::unique_ptr<PinnedBuf> b;
     {
@@ -253,7 +257,7 @@ namespace {
 struct CtxCache {
     std::mutex mu;
     std::vector<std::pair<int32_t, idn_gpu_ctx*>> free_;
-    static constexpr size_t kKeepPerDevice = 4;
+    static constexpr size_t kKeepPerDevice = 8;
 };
 CtxCache& ctx_cache() {
     static CtxCache* c = new CtxCache;
@@ -286,8 +290,8 @@ void DeviceModels::open(int32_t device) {
     {
         CtxCache& c = ctx_cache();
         std::lock_guard<std::mutex> lk(c.mu);
-        for (size_t i = 0; i < c.free_.size(); i++)
-            if (c.free_[i].first == device) {
+        for (size_t i = c.free_.size(); i-- > 0;)  // the one released last: objects opened and closed in the same order get the
+            if (c.free_[i].first == device) {        // contexts they had before, with the buffers of their role already sized
                 ctx_ = c.free_[i].second;
                 c.free_.erase(c.free_.begin() + i);
                 return;
