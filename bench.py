@@ -860,11 +860,16 @@ def e2e_file_leg(args, w, env, acids_d, quals_d, read_off_h, n):
             # (1) streaming: the text of each batch of blocks is handed out where the device wrote it (what a writer passes to write())
             t2 = time.perf_counter()
             rd = host.FastqTextReader(models, idn, devices=devs, thread_num=cores, batch_blocks=args.file_batch_blocks)
+            t2a = time.perf_counter()
             got = 0
             for piece in rd:
                 got += piece.size
+            t2b = time.perf_counter()
             rd.close()
             t3 = time.perf_counter()
+            if os.environ.get("IDN_HOST_TRACE"):
+                print(f"[bench e2e_file] pass {it} names {names}: compress {t1 - t0:.3f} s; reader open {t2a - t2:.3f} pieces {t2b - t2a:.3f} close {t3 - t2b:.3f} s",
+                      file=sys.stderr, flush=True)
             # (2) the same into one contiguous caller buffer (one more host copy)
             n_back = host.decompress_text_into(models, idn, back_h, device=env.local, thread_num=cores, batch_blocks=args.file_batch_blocks)
             t4 = time.perf_counter()

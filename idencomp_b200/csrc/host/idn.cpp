@@ -146,9 +146,10 @@ struct Brotli {
 // ---- IDN_HOST_TRACE=1: wall time per stage of the host mirror, summed over threads, printed when an object closes -----------
 namespace {
 struct Trace {
-    static constexpr int kN = 12;
+    static constexpr int kN = 16;
     const char* name[kN] = {"parse_chunk", "first_block_select", "names_fetch", "names_deflate", "compress_parsed", "compress_blocks",
-                            "sink", "read_raw", "index_blocks", "names_inflate", "decode", "wait_worker"};
+                            "sink", "read_raw", "index_blocks", "names_inflate", "decode", "wait_worker", "open", "initialize", "wait_result",
+                            "close"};
     std::atomic<uint64_t> ns[kN];
     std::atomic<uint64_t> calls[kN];
     bool on = std::getenv("IDN_HOST_TRACE") != nullptr;
@@ -177,7 +178,7 @@ struct Span {
     }
 };
 std::atomic<size_t> g_raw_hint{1 << 20};  // bytes of the largest batch of container bytes read so far (sizes the next buffer)
-enum { T_PARSE, T_SELECT, T_NFETCH, T_NDEFLATE, T_CPARSED, T_CBLOCKS, T_SINK, T_READRAW, T_INDEX, T_NINFLATE, T_DECODE, T_WAIT };
+enum { T_PARSE, T_SELECT, T_NFETCH, T_NDEFLATE, T_CPARSED, T_CBLOCKS, T_SINK, T_READRAW, T_INDEX, T_NINFLATE, T_DECODE, T_WAIT, T_OPEN, T_INIT, T_WAITRES, T_CLOSE };
 }  // namespace
 
 // ---- page-locked buffers -------------------------------------------------------------------------------------------------
@@ -794,6 +795,7 @@ void IdnCompressor::finish() {
 
 // ---- IdnDecompressor -------------------------------------------------------------------------------------------------
 IdnDecompressor::IdnDecompressor(Source source, IdnDecompressorParams params) : source_(std::move(source)), params_(std::move(params)) {
+    Span sp(T_OPEN);
     if (params_.devices.empty()) params_.devices.assign(1, 0);
     if (params_.batch_blocks == 0) params_.batch_blocks = 1;
     for (int32_t d : params_.devices) {
@@ -813,8 +815,13 @@ IdnDecompressor::IdnDecompressor(const uint8_t* data, size_t len, IdnDecompresso
     mem_len_ = len;
 }
 IdnDecompressor::~IdnDecompressor() {
-    for (auto& f : pending_)
-        if (f.valid()) f.wait();
+    {
+        Span sp(T_CLOSE);
+        for (auto& f : pending_)
+            if (f.valid()) f.wait();
+        pending_.clear();
+        workers_.clear();  // contexts back to the cache
+    }
     g_trace.print("decompressor");
 }
 
@@ -828,6 +835,7 @@ void IdnDecompressor::read_exact(uint8_t* dst, size_t n, const char* what) {
 }
 
 void IdnDecompressor::initialize() {
+    Span sp(T_INIT);
     uint8_t h[9];
     read_exact(h, 9, "the header");
     if (std::memcmp(h, kMagic, 8) != 0) throw IdnError(IDN_E_SERIALIZE, "not an IDN file (bad magic)");
@@ -1072,7 +1080,11 @@ bool IdnDecompressor::next_fastq_text(std::shared_ptr<PinnedBuf>& out, size_t& l
     text_mode_ = title_with_separator ? 2 : 1;
     prefetch();
     if (pending_.empty()) return false;
-    DecodedBatch b = pending_.front().get();
+    DecodedBatch b;
+    {
+        Span sp(T_WAITRES);
+        b = pending_.front().get();
+    }
     pending_.pop_front();
     prefetch();
     out = std::move(b.text);
