@@ -255,9 +255,14 @@ void PinnedPool::trim() {
 // device contexts between uses: a context's staging and work buffers on the device are sized by the batches it has seen,
 // and allocating them again for every compressor costs more than compressing a few GB
 namespace {
+struct CachedCtx {
+    int32_t first;  // device
+    idn_gpu_ctx* second;
+    std::vector<std::pair<ModelIdentifier, idn_model_t>> resident;  // models left on it
+};
 struct CtxCache {
     std::mutex mu;
-    std::vector<std::pair<int32_t, idn_gpu_ctx*>> free_;
+    std::vector<CachedCtx> free_;
     static constexpr size_t kKeepPerDevice = 8;
 };
 CtxCache& ctx_cache() {
@@ -270,20 +275,19 @@ void release_cached_resources() {
     PinnedPool::trim();
     CtxCache& c = ctx_cache();
     std::lock_guard<std::mutex> lk(c.mu);
-    for (auto& e : c.free_) idn_gpu_destroy(e.second);
+    for (auto& e : c.free_) idn_gpu_destroy(e.second);  // (with the models left on it)
     c.free_.clear();
 }
 
 // ---- DeviceModels ---------------------------------------------------------------------------------------------------
 DeviceModels::~DeviceModels() {
     if (!ctx_) return;
-    for (idn_model_t h : handles_) idn_gpu_model_release(ctx_, h);
     CtxCache& c = ctx_cache();
     std::lock_guard<std::mutex> lk(c.mu);
     size_t same = 0;
     for (auto& e : c.free_) same += e.first == device_;
-    if (!broken_ && same < CtxCache::kKeepPerDevice) c.free_.emplace_back(device_, ctx_);
-    else idn_gpu_destroy(ctx_);
+    if (!broken_ && same < CtxCache::kKeepPerDevice) c.free_.push_back(CachedCtx{device_, ctx_, std::move(resident_)});
+    else idn_gpu_destroy(ctx_);  // (frees its models too)
 }
 void DeviceModels::open(int32_t device) {
     if (ctx_) return;
@@ -294,6 +298,7 @@ void DeviceModels::open(int32_t device) {
         for (size_t i = c.free_.size(); i-- > 0;)  // the one released last: objects opened and closed in the same order get the
             if (c.free_[i].first == device) {        // contexts they had before, with the buffers of their role already sized
                 ctx_ = c.free_[i].second;
+                resident_ = std::move(c.free_[i].resident);
                 c.free_.erase(c.free_.begin() + i);
                 return;
             }
@@ -306,13 +311,32 @@ void DeviceModels::raise(int32_t rc) const {
     throw IdnError(rc, ctx_ ? idn_gpu_last_error(ctx_) : "no device context");
 }
 void DeviceModels::upload(const ModelProvider& provider) {
-    for (idn_model_t h : handles_) idn_gpu_model_release(ctx_, h);
+    constexpr size_t kKeepResident = 64;  // models a context keeps beyond the ones in use
     handles_.clear();
+    std::vector<char> used(resident_.size(), 0);
     for (size_t i = 0; i < provider.len(); i++) {
-        idn_model_t h = -1;
-        int32_t rc = upload_model(ctx_, provider[i], &h);
-        if (rc) raise(rc);
-        handles_.push_back(h);
+        const ModelIdentifier& id = provider[i].identifier();
+        size_t k = 0;
+        while (k < resident_.size() && resident_[k].first != id) k++;
+        if (k == resident_.size()) {
+            idn_model_t h = -1;
+            int32_t rc = upload_model(ctx_, provider[i], &h);
+            if (rc) raise(rc);
+            resident_.emplace_back(id, h);
+            used.push_back(0);
+        }
+        used[k] = 1;
+        handles_.push_back(resident_[k].second);
+    }
+    // the oldest unused ones go when the context holds too many
+    for (size_t k = 0; k < resident_.size() && resident_.size() > provider.len() + kKeepResident;) {
+        if (used[k]) {
+            k++;
+            continue;
+        }
+        idn_gpu_model_release(ctx_, resident_[k].second);
+        resident_.erase(resident_.begin() + k);
+        used.erase(used.begin() + k);
     }
 }
 
