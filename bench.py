@@ -100,13 +100,17 @@ def fastq_bytes(w: dict, n_reads: int, n_symbols: int) -> int:
 
 
 class ClockSampler:
-    """nvidia-smi clocks/throttle reasons DURING the timed region (B200_PROFILING.md)."""
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+    """nvidia-smi clocks/throttle reasons DURING the timed region (B200_PROFILING.md).  The sampler is started ahead of the
+    region (nvidia-smi takes a few hundred ms to deliver its first line, more with 8 ranks starting it at once) and only the
+    samples whose own timestamps fall between begin() and end() count; a region shorter than the 100 ms period takes the
+    nearest sample and says so."""
+    Q = ("timestamp,index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, device: int):
         self.device = device
         self.proc = None
+        self.t0 = self.t1 = None
 
     def start(self):
         try:
@@ -115,34 +119,64 @@ class ClockSampler:
         except OSError:
             self.proc = None
 
+    def begin(self):
+        import datetime
+        self.t0 = datetime.datetime.now()
+
+    def end(self):
+        import datetime
+        self.t1 = datetime.datetime.now()
+
+    @staticmethod
+    def parse(out: str):
+        """[(timestamp or None, sm, sm_max, power, {reasons})] of the nvidia-smi lines"""
+        import datetime
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        rows = []
+        for ln in out.splitlines():
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 10:
+                continue
+            try:
+                ts = datetime.datetime.strptime(f[0], "%Y/%m/%d %H:%M:%S.%f")
+            except ValueError:
+                ts = None
+            try:
+                row = (ts, float(f[2]), float(f[3]), float(f[4]), {n for n, v in zip(names, f[6:10]) if v.lower().startswith("active")})
+            except ValueError:
+                continue
+            rows.append(row)
+        return rows
+
     def stop(self) -> dict:
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        if self.t1 is None:
+            self.end()
         self.proc.terminate()
         try:
             out, _ = self.proc.communicate(timeout=10)
         except subprocess.TimeoutExpired:
             self.proc.kill()
             out, _ = self.proc.communicate()
-        sm, smax, power, reasons = [], [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in out.splitlines():
-            f = [x.strip() for x in ln.split(",")]
-            if len(f) < 9:
-                continue
-            try:
-                sm.append(float(f[1]))
-                smax.append(float(f[2]))
-                power.append(float(f[3]))
-            except ValueError:
-                continue
-            for n, v in zip(names, f[5:9]):
-                if v.lower().startswith("active"):
-                    reasons.add(n)
-        if not sm:
+        rows = self.parse(out)
+        if not rows:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
-        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(smax), "power_w_max": max(power), "samples": len(sm),
-                "reasons": sorted(reasons)}
+        note = None
+        if self.t0 is not None and all(r[0] is not None for r in rows):
+            inside = [r for r in rows if self.t0 <= r[0] <= self.t1]
+            if not inside:  # the region is shorter than the sampling period: the sample nearest to it
+                mid = self.t0 + (self.t1 - self.t0) / 2
+                near = min(rows, key=lambda r: abs((r[0] - mid).total_seconds()))
+                off = min(abs((near[0] - self.t0).total_seconds()), abs((near[0] - self.t1).total_seconds()))
+                note = f"no sample inside the {(self.t1 - self.t0).total_seconds() * 1e3:.0f} ms timed region: the nearest one, {off * 1e3:.0f} ms away"
+                inside = [near]
+            rows = inside
+        res = {"sm_mhz": statistics.median(r[1] for r in rows), "sm_max_mhz": max(r[2] for r in rows), "power_w_max": max(r[3] for r in rows),
+               "samples": len(rows), "reasons": sorted(set().union(*(r[4] for r in rows)))}
+        if note:
+            res["note"] = note
+        return res
 
 
 def measured_peak_gbs():
@@ -437,6 +471,8 @@ def run_workload(env, args, name: str, w: dict, *, steps: int, warmup: int, main
         decompress_all(mode, sizes)
         torch.cuda.synchronize()
         check_decode_status()
+        sampler = ClockSampler(env.local)
+        sampler.start()  # ahead of the timed region: only the samples stamped inside it count
         for _ in range(max(0, warmup - 1)):
             compress_all(mode)
             decompress_all(mode, sizes)
@@ -444,9 +480,9 @@ def run_workload(env, args, name: str, w: dict, *, steps: int, warmup: int, main
         if profile:
             ctx.profile(True)
         launches0 = ctx.launches
-        sampler = ClockSampler(env.local)
-        sampler.start()
         ev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(steps)]
+        torch.cuda.synchronize()
+        sampler.begin()
         t_wall0 = time.perf_counter()
         for k in range(steps):
             ev[k][0].record(stream)
@@ -456,6 +492,7 @@ def run_workload(env, args, name: str, w: dict, *, steps: int, warmup: int, main
             ev[k][2].record(stream)
         torch.cuda.synchronize()
         t_wall = time.perf_counter() - t_wall0
+        sampler.end()
         clocks = sampler.stop()
         res = {"launches": ctx.launches - launches0, "clocks": clocks, "t_wall": t_wall, "sizes": sizes, "out_bytes": out_bytes,
                "payload_bytes": payload_bytes, "prof": ctx.profile_read() if profile else {},
