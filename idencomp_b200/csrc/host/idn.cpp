@@ -363,7 +363,15 @@ IdnCompressor::IdnCompressor(Sink sink, IdnCompressorParams params) : sink_(std:
 }
 
 IdnCompressor::~IdnCompressor() {
-    for (auto& f : pending_)  // jobs still running hold references to this object
+    if (writer_.joinable()) {  // the writer drains what is pending (jobs still running hold references to this object)
+        {
+            std::lock_guard<std::mutex> lk(wmu_);
+            writer_stop_ = true;
+        }
+        wcv_.notify_all();
+        writer_.join();
+    }
+    for (auto& f : pending_)
         if (f.valid()) f.wait();
 }
 
@@ -588,29 +596,72 @@ void IdnCompressor::flush_batch() {
     Worker* w = workers_[next_worker_++ % workers_.size()].get();
     auto job = std::make_shared<Batch>(std::move(cur_));
     cur_ = Batch();
-    pending_.push_back(std::async(std::launch::async, [this, w, job] { return compress_batch(*w, *job); }));
+    submit(std::async(std::launch::async, [this, w, job] { return compress_batch(*w, *job); }));
     commit(false);
 }
 
+void IdnCompressor::submit(std::future<Result> f) {
+    {
+        std::lock_guard<std::mutex> lk(wmu_);
+        pending_.push_back(std::move(f));
+        if (!writer_.joinable()) writer_ = std::thread([this] { writer_loop(); });
+    }
+    wcv_.notify_all();
+}
+
+// the writer thread: results in block order to the sink.  After an error it keeps taking results off the queue (without
+// writing them), so that nobody waits for ever and every job has finished before the object goes away.
+void IdnCompressor::writer_loop() {
+    std::unique_lock<std::mutex> lk(wmu_);
+    for (;;) {
+        wcv_.wait(lk, [this] { return writer_stop_ || !pending_.empty(); });
+        if (pending_.empty()) break;  // (stop requested and nothing left)
+        std::future<Result> f = std::move(pending_.front());  // the entry stays in the queue until it is written: commit() counts it
+        const bool failed = writer_err_ != nullptr;
+        lk.unlock();
+        std::exception_ptr err;
+        Result r;
+        try {
+            {
+                Span spw(T_WAIT);
+                r = f.get();  // rethrows what the job threw
+            }
+            if (!failed) {
+                Span sp(T_SINK);
+                sink_(r.buf->p, r.out_bytes);
+            }
+        } catch (...) {
+            err = std::current_exception();
+        }
+        lk.lock();
+        if (err && !writer_err_) writer_err_ = err;
+        if (!err && !failed) {
+            stats_.out_bytes += r.out_bytes;
+            stats_.out_identifier_bytes += r.prefix_total;
+            stats_.out_payload_bytes += r.payload_bytes;
+            stats_.acid_model_switches += r.acid_switches;
+            stats_.q_score_model_switches += r.q_switches;
+            stats_.blocks += r.blocks;
+        }
+        r = Result();  // the page-locked buffer goes back to the pool before the next wait
+        pending_.pop_front();
+        wcv_.notify_all();
+    }
+}
+
+// waits until at most two batches per device are pending (all = false) or everything is written (all = true); rethrows
+// what a job or the sink threw
 void IdnCompressor::commit(bool all) {
     const size_t keep = all ? 0 : 2 * workers_.size();
-    while (!pending_.empty()) {
-        const bool ready = pending_.front().wait_for(std::chrono::seconds(0)) == std::future_status::ready;
-        if (!ready && pending_.size() <= keep) break;
-        Result r;
-        {
-            Span spw(T_WAIT);
-            r = pending_.front().get();  // rethrows what the job threw
-        }
-        pending_.pop_front();
-        Span sp(T_SINK);
-        sink_(r.buf->p, r.out_bytes);  // blocks in order: this replaces IdnBlockLock (common.rs:10-57)
-        stats_.out_bytes += r.out_bytes;
-        stats_.out_identifier_bytes += r.prefix_total;
-        stats_.out_payload_bytes += r.payload_bytes;
-        stats_.acid_model_switches += r.acid_switches;
-        stats_.q_score_model_switches += r.q_switches;
-        stats_.blocks += r.blocks;
+    std::unique_lock<std::mutex> lk(wmu_);
+    {
+        Span spw(T_WAIT);
+        wcv_.wait(lk, [&] { return pending_.size() <= keep; });
+    }
+    if (writer_err_) {
+        std::exception_ptr e = writer_err_;
+        if (all) writer_err_ = nullptr;  // reported once by finish(); an add_* after an error keeps failing
+        std::rethrow_exception(e);
     }
 }
 
@@ -744,7 +795,7 @@ size_t IdnCompressor::consume_text(const uint8_t* buf, size_t total, bool final)
         stats_.in_identifier_bytes += ck.n_name_bytes;
         const uint32_t nb = ck.n_blocks;
         const uint64_t nr = ck.n_reads, ns = ck.n_symbols, nn = ck.n_name_bytes;
-        pending_.push_back(std::async(std::launch::async, [this, w, nb, nr, ns, nn] { return compress_parsed(*w, nb, nr, ns, nn); }));
+        submit(std::async(std::launch::async, [this, w, nb, nr, ns, nn] { return compress_parsed(*w, nb, nr, ns, nn); }));
         commit(false);
         if (last) break;
     }

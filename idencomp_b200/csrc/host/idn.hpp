@@ -22,6 +22,7 @@
 #include <optional>
 #include <stdexcept>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../../include/idn_gpu.h"
@@ -155,7 +156,7 @@ public:
     // add_sequence would have produced for the same reads.  Not to be mixed with add_sequence / add_batch on one object.
     void add_fastq_text(const uint8_t* text, size_t n);
     void finish();                         // flushes, writes the empty terminator block; InvalidState if called twice
-    const CompressionStats& stats() const { return stats_; }
+    const CompressionStats& stats() const { return stats_; }  // (the out_* fields are final after finish())
     // the model identifiers written to the metadata (acid ids first), available after the first block was processed
     const std::vector<ModelIdentifier>& retained_models() const { return retained_; }
 
@@ -210,7 +211,17 @@ private:
     std::vector<std::unique_ptr<Worker>> workers_;  // one per entry of params_.devices
     size_t next_worker_ = 0;
     mutable PinnedPool pool_;
-    std::deque<std::future<Result>> pending_;       // batches in flight, in block order
+    // Batches in flight, in block order.  A writer thread takes the results off the front as they complete and hands them
+    // to the sink (ONE thread, in order: this replaces IdnBlockLock, common.rs:10-57), so the thread that adds sequences or
+    // text does not spend its time in the sink; it only waits when more than two batches per device are pending.
+    std::deque<std::future<Result>> pending_;
+    std::mutex wmu_;                // pending_, writer_stop_, writer_err_, the out_* fields of stats_
+    std::condition_variable wcv_;
+    std::thread writer_;
+    bool writer_stop_ = false;
+    std::exception_ptr writer_err_;  // what a job or the sink threw; rethrown by the next add_* / finish
+    void submit(std::future<Result> f);
+    void writer_loop();
     CompressionStats stats_;
     std::vector<ModelIdentifier> retained_;
     bool initialized_ = false, finished_ = false;
