@@ -81,7 +81,9 @@ int32_t idn_host_compressor_add_batch(idn_host_compressor *c, uint64_t n_reads, 
  * reference, done on the device); not to be mixed with the two calls above on one compressor */
 int32_t idn_host_compressor_add_text(idn_host_compressor *c, const uint8_t *text, uint64_t n);
 int32_t idn_host_compressor_finish(idn_host_compressor *c);     /* IdnCompressor::finish */
-/* the container written so far (complete after finish); the pointer stays valid until the next call on `c` */
+/* the container (complete after finish: blocks reach the output from a writer thread, in order, while the add_* calls go
+ * on; an error of a block or of the output is reported by the next add_* call or by finish); the pointer stays valid until
+ * the next call on `c` */
 uint64_t idn_host_compressor_output(const idn_host_compressor *c, const uint8_t **data);
 /* identifiers written to the metadata, acid models first; returns their number */
 uint32_t idn_host_compressor_retained(const idn_host_compressor *c, uint8_t *ids /* [cap][32] */, uint32_t cap);
