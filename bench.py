@@ -38,7 +38,8 @@ if str(ROOT) not in sys.path:
 
 MODELS = ROOT / "models"
 BLOCK_SYMBOLS = 4 * 1024 * 1024  # IdnCompressorParams::max_block_total_len default, idn/compressor.rs:187
-E2E_READS_PER_CALL = 16384       # e2e leg: reads a host-pointer call should carry at least (PacBio-shaped sweep: 25 blocks 31.5, 50-64 blocks 44-45, 200 blocks 41.6 GB/s)
+E2E_READS_PER_CALL = 16384       # e2e leg, native format: reads a sub-chunk of a host-pointer call should carry at least (PacBio-shaped sweep: 25 blocks 31.5, 50-64 blocks 44-48, 160-200 blocks 41.6-46 GB/s)
+E2E_READS_PER_CALL_COMPAT = 32768  # compat format (a read is one serial chain): 59 blocks 31.7, 110-160 blocks 43, 320 blocks 41 GB/s (tools/r2_call_y.sh)
 
 # SURVEY.md 8d.  fastq_overhead = bytes of a FASTQ record besides the 2*L symbol characters: '@' + name + '\n',
 # '\n' after the acids, "+\n", '\n' after the quality scores.
@@ -972,7 +973,8 @@ def run_e2e(args, w, env, model_names, chunks, acids_d, quals_d, read_off_h, blo
     reads_per_block = max(1, (len(read_off_h) - 1) // max(n_blocks_all, 1))
     # a sub-chunk should carry enough reads to fill the GPU (one thread per read: ~150 k in flight): blocks of long reads
     # hold a few hundred reads each, so those workloads pipeline in larger sub-chunks
-    pipe_blocks = args.e2e_pipe_blocks or max(32, min(256, -(-E2E_READS_PER_CALL // reads_per_block)))
+    per_call = E2E_READS_PER_CALL_COMPAT if mode == capi.MODE_COMPAT else E2E_READS_PER_CALL
+    pipe_blocks = args.e2e_pipe_blocks or max(32, min(256, -(-per_call // reads_per_block)))
     # pinned inputs, pinned container, pinned decoded output: 4 * S + 2 * container bytes of page-locked host memory.  Budget
     # of this rank: half of what is available, shared by the ranks of the box (or the caller's limit); a workload that
     # needs more is sampled from its front and the rate scaled

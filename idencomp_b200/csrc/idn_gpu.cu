@@ -87,6 +87,7 @@ struct idn_gpu_ctx {
     int device = 0;
     idn_gpu_pipe* pipe = nullptr;       // streams, events and double-buffered staging of the pipelined host-pointer calls
     uint32_t pipe_blocks = 32;          // blocks per sub-chunk of a host-pointer call (idn_gpu_set_pipeline_blocks)
+    bool pipe_blocks_set = false;       // set by the caller: taken as is; otherwise long reads get larger sub-chunks (pipe_sub_blocks)
     uint32_t* pipe_err_out = nullptr;   // where compress_blocks_dev leaves its error flags for the pipeline (device)
     cudaStream_t stream = nullptr;  // used by the host-pointer entry points
     cudaEvent_t ev = nullptr;
@@ -410,7 +411,10 @@ extern "C" int32_t idn_gpu_create(int32_t device, idn_gpu_ctx** out) {
     if (n <= 0 || device < 0 || device >= n) return IDN_E_CUDA;  // no CPU fallback
     idn_gpu_ctx* ctx = new idn_gpu_ctx();
     ctx->device = device;
-    if (const char* pb = getenv("IDN_PIPE_BLOCKS")) ctx->pipe_blocks = std::max(1, atoi(pb));
+    if (const char* pb = getenv("IDN_PIPE_BLOCKS")) {
+        ctx->pipe_blocks = std::max(1, atoi(pb));
+        ctx->pipe_blocks_set = true;
+    }
     if (getenv("IDN_NO_BUCKETS")) ctx->bucket_pairs = false;
     if (const char* w = getenv("IDN_WALK")) ctx->walk_mode = strcmp(w, "serial") == 0 ? 1 : (strcmp(w, "fast") == 0 ? 2 : 0);
     auto bail = [&](const char* what) {
@@ -1900,6 +1904,7 @@ extern "C" int32_t idn_gpu_set_pipeline_blocks(idn_gpu_ctx* ctx, uint32_t blocks
     if (!ctx) return IDN_E_INVALID_ARG;
     if (blocks == 0) return fail(ctx, IDN_E_INVALID_ARG, "blocks per sub-chunk must be positive");
     ctx->pipe_blocks = blocks;
+    ctx->pipe_blocks_set = true;
     return IDN_OK;
 }
 
